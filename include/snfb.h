@@ -1,0 +1,283 @@
+/*
+ * snfb.h — C ABI of libsnfb200.so: the B200-native lead -> cluster -> consensus hot path
+ * of Sniffles2, callable through ctypes from the Python host (sniffles_b200/binding.py).
+ *
+ * Every entry point replaces a Python call site of the reference (paths relative to
+ * /root/reference/src/sniffles/):
+ *
+ *   snfb_load_records      <- pysam `bam.fetch()` iteration + AlignedSegment accessors
+ *                             (leadprov.py:488, accessor list SURVEY.md §2)
+ *   snfb_extract_leads     <- LeadProvider.build_leadtab / iter_region / read_iterindels /
+ *                             Lead.for_bnd / read_itersplits (leadprov.py:445-670),
+ *                             sv.classify_splits (sv.py:649-782); call site parallel.py:90-102
+ *   snfb_cluster_call      <- cluster.resolve + merge_inner + resplit + resplit_bnd
+ *                             (cluster.py:85-353), sv.call_from / resolve_bnd (sv.py:497-639),
+ *                             postprocessing.coverage (postprocessing.py:69-130);
+ *                             call site Task.call_candidates parallel.py:104-127
+ *   snfb_consensus         <- postprocessing.annotate_sv INS branch (postprocessing.py:33-66)
+ *                             + consensus.novel_from_reads (consensus.py:280-394);
+ *                             call site Task.finalize_candidates parallel.py:145
+ *
+ * Conventions: all functions return 0 on success, non-zero on error (message via
+ * snfb_last_error).  No exceptions, no Python or torch types.  Views are library-owned
+ * pinned host buffers, valid until the next call on the same ctx.  A ctx is bound to
+ * one CUDA device and is not thread safe.  There is NO CPU fallback: if no CUDA device
+ * is usable snfb_ctx_create fails.
+ */
+#ifndef SNFB_H
+#define SNFB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SNFB_ABI_VERSION 1
+
+/* SV types in the reference's ALL_TYPES order (sv.py:31-33); the emission order of
+ * candidates follows this order (parallel.py:106). */
+enum { SNFB_INS = 0, SNFB_DEL = 1, SNFB_DUP = 2, SNFB_INV = 3, SNFB_BND = 4,
+       SNFB_SINGLE_LEFT = 5, SNFB_SINGLE_RIGHT = 6, SNFB_NTYPES = 7 };
+/* Lead.source (leadprov.py:46) */
+enum { SNFB_SRC_INLINE = 0, SNFB_SRC_SPLIT_PRIM = 1, SNFB_SRC_SPLIT_SUP = 2, SNFB_SRC_BND_SA = 3 };
+
+/* aux_flags bits of snfb_rec */
+#define SNFB_AUX_NM 1u
+#define SNFB_AUX_HP 2u
+#define SNFB_AUX_PS 4u
+#define SNFB_AUX_SA 8u
+
+/* One packed alignment record: the fields of a BAM record the path reads,
+ * fixed 64 bytes so a warp fetches it with one coalesced request.  Base qualities are
+ * never shipped.  Variable-length parts live in three arenas of the block:
+ *   cigar[cigar_off .. +n_cigar)   BAM encoding, len<<4|op (op: MIDNSHP=X = 0..8)
+ *   var[var_off .. +l_qname)       query name bytes (no NUL), followed by
+ *   var[var_off+l_qname .. +sa_len) the SA:Z tag text (no NUL)
+ *   seq[seq_off .. +(l_seq+1)/2)   BAM 4-bit bases ("=ACMGRSVTWYHKDBN"), high nibble first
+ */
+typedef struct snfb_rec {
+    int32_t  task;        /* index into the task table (one task per contig/region)   */
+    int32_t  pos;         /* 0-based reference_start                                    */
+    uint16_t flag;        /* SAM flag                                                   */
+    uint8_t  mapq;
+    uint8_t  aux_flags;   /* SNFB_AUX_*                                                 */
+    uint8_t  hp;          /* HP:i tag value (0 when absent); must be 0,1,2              */
+    uint8_t  l_qname;
+    uint16_t _pad0;
+    int32_t  nm;          /* NM:i tag value                                             */
+    int32_t  ps;          /* PS:i tag value                                             */
+    uint32_t n_cigar;
+    int32_t  l_seq;       /* query_length (bases stored in seq)                         */
+    uint32_t sa_len;
+    uint32_t _pad1;
+    uint64_t cigar_off;   /* in 32-bit ops                                              */
+    uint64_t seq_off;     /* in bytes                                                   */
+    uint64_t var_off;     /* in bytes                                                   */
+} snfb_rec;
+
+/* One unit of work = what the reference hands to one CallTask (parallel.py:47-60):
+ * a contig and one region on it.  Clusters never cross tasks. */
+typedef struct snfb_task {
+    int32_t contig;       /* index into the contig table                               */
+    int32_t start;        /* region.start                                              */
+    int32_t end;          /* region.end (exclusive)                                    */
+    int32_t contig_len;   /* bam.get_reference_length(contig)                          */
+    int32_t task_id;      /* Task.id (only used for ids on the host)                   */
+    int32_t tr_off;       /* first tandem-repeat interval of this task in tr[]         */
+    int32_t tr_n;         /* number of intervals (sorted by start, already padded)     */
+    int32_t _pad;
+} snfb_task;
+
+/* Reference names: the SA tag names its mate contig as a string (leadprov.py:82);
+ * the library resolves it through FNV-1a 64 hashes of the names and needs the
+ * lexicographic rank of each name for util.most_common_top ties (util.py:101-103). */
+typedef struct snfb_contig {
+    uint64_t name_hash;   /* snfb_hash_name(name)                                      */
+    int32_t  length;
+    int32_t  lex_rank;    /* rank of the name among all contig names, byte-wise order  */
+} snfb_contig;
+
+typedef struct snfb_records {
+    uint64_t n_rec;
+    uint64_t n_cigar;     /* total ops   */
+    uint64_t n_var;       /* bytes       */
+    uint64_t n_seq;       /* bytes       */
+    const snfb_rec* rec;
+    const uint32_t* cigar;
+    const uint8_t*  var;
+    const uint8_t*  seq;
+    uint32_t n_task;
+    uint32_t n_contig;
+    uint32_t n_tr;
+    uint32_t on_device;   /* 1: the five arenas above are device pointers (no copy)    */
+    const snfb_task*   task;
+    const snfb_contig* contig;
+    const int32_t*     tr;    /* n_tr pairs (start,end), per task sorted (util.py:121-147) */
+} snfb_records;
+
+/* Flat POD of the reference's config values that the path reads (config.py:449-619). */
+typedef struct snfb_config {
+    int32_t mapq;                      /* config.py:533-534  */
+    int32_t min_alignment_length;      /* config.py:535-536  */
+    int32_t exclude_flags;             /* 0 = None           */
+    int32_t minsvlen;                  /* config.py:508-514  */
+    int32_t minsvlen_screen;           /* config.py:517      */
+    int32_t long_ins_length;           /* 2500               */
+    int32_t detect_large_ins;          /* bool               */
+    int32_t dev_seq_cache_maxlen;      /* 50000              */
+    int32_t max_splits_base;           /* 3                  */
+    int32_t dev_keep_lowqual_splits;   /* bool               */
+    int32_t qc_nm_measure;             /* config.py:596-599  */
+    int32_t phase;                     /* bool               */
+    int32_t cluster_binsize;           /* 100                */
+    int32_t cluster_merge_pos;         /* 150                */
+    int32_t cluster_merge_bnd;         /* 1000               */
+    int32_t cluster_resplit_binsize;   /* 20                 */
+    int32_t repeat;                    /* --repeat           */
+    int32_t dev_min_leads_cluster;     /* config.py:607-611  */
+    int32_t dev_no_resplit;
+    int32_t dev_no_resplit_repeat;
+    int32_t consensus_max_reads_bin;   /* 10                 */
+    int32_t consensus_min_reads;       /* 4                  */
+    int32_t consensus_kmer_len;        /* 6 (only 6 is supported on device) */
+    int32_t consensus_kmer_skip_base;  /* 3                  */
+    int32_t no_consensus;
+    int32_t symbolic;
+    int32_t precise;                   /* 25                 */
+    int32_t coverage_binsize;          /* = cluster_binsize  */
+    int32_t coverage_updown_bins;      /* 5                  */
+    int32_t _pad;
+    double  max_splits_kb;             /* 0.1                */
+    double  cluster_r;                 /* 2.5                */
+    double  cluster_repeat_h;          /* 1.5                */
+    double  cluster_repeat_h_max;      /* 1000               */
+    double  cluster_merge_len;         /* 0.22 / 0.27 mosaic */
+    double  consensus_kmer_skip_seqlen_mult; /* 1/500        */
+} snfb_config;
+
+/* Lead as written by the device (64 B).  One lead = one reference `Lead`
+ * (leadprov.py:34-55) that landed inside its task's region (leadprov.py:464-466). */
+typedef struct snfb_lead {
+    uint32_t rec;          /* index of the alignment record (stands in for read_id)   */
+    int32_t  ref_start;
+    int32_t  ref_end;
+    int32_t  qry_start;
+    int32_t  qry_end;
+    int32_t  svlen;        /* undefined when SNFB_LF_SVLEN_NONE                        */
+    int32_t  seq_off;      /* offset into the read's query_sequence, -1 = no sequence  */
+    int32_t  seq_len;      /* length of the sequence slice                             */
+    int32_t  read_len;     /* query_alignment_length for INLINE leads, else 0          */
+    int32_t  mate_pos;     /* BND: bnd_info.mate_ref_start                             */
+    int32_t  mate_contig;  /* BND: contig-table index of bnd_info.mate_contig          */
+    int32_t  nm_sa;        /* BND: NM field of the SA entry (leadprov.py:119)          */
+    uint32_t flags;        /* SNFB_LF_*                                                */
+    uint16_t task;
+    uint16_t k;            /* ordinal of the lead inside its read (A9 ordering)        */
+    uint64_t qname_hash;   /* FNV-style 64-bit hash of query_name                      */
+} snfb_lead;
+
+#define SNFB_LF_TYPE(f)      ((f) & 7u)
+#define SNFB_LF_SOURCE(f)    (((f) >> 3) & 3u)
+#define SNFB_LF_REVERSE      (1u << 5)   /* strand == "-"                     */
+#define SNFB_LF_IS_SA        (1u << 6)   /* read.is_supplementary             */
+#define SNFB_LF_SVLEN_NONE   (1u << 7)   /* svlen is None ("long INS")        */
+#define SNFB_LF_BND_FIRST    (1u << 8)
+#define SNFB_LF_BND_REVERSE  (1u << 9)
+#define SNFB_LF_HAS_SEQ      (1u << 10)  /* seq is not None                   */
+#define SNFB_LF_MAPQ(f)      (((f) >> 16) & 255u)
+#define SNFB_LF_HAP(f)       (((f) >> 24) & 3u)
+
+typedef struct snfb_lead_view {
+    uint64_t n_leads;
+    const snfb_lead* leads;        /* in bin order: (task, svtype, bin, record, k)     */
+    uint64_t n_pass;               /* LeadProvider.read_count summed over tasks        */
+    const uint32_t* task_read_count;  /* [n_task]                                       */
+    const double*   task_mean_nm;     /* [n_task] config.average_regional_nm (leadprov.py:577) */
+    const double*   rec_nm;        /* [n_rec] per-read nm (leadprov.py:524), -1 if none */
+    uint64_t soft_errors;          /* malformed SA entries etc. (never fatal)          */
+} snfb_lead_view;
+
+/* One SV candidate = one reference SVCall as it leaves Task.call_candidates
+ * (sv.py:561-598 + postprocessing.coverage), before QC/genotyping. */
+typedef struct snfb_cand {
+    int32_t  task;
+    int32_t  svtype;
+    int32_t  pos;
+    int32_t  end;
+    int32_t  svlen;
+    int32_t  support;
+    int32_t  qual;
+    int32_t  precise;
+    int32_t  fwd;
+    int32_t  rev;
+    int32_t  support_long;       /* INS: SUPPORT_LONG                                  */
+    int32_t  support_sa;         /* DEL: SUPPORT_SA                                    */
+    int32_t  cov_upstream, cov_start, cov_center, cov_end, cov_downstream;
+    int32_t  hap_counts[6];      /* cluster.hap_counts (cluster.py:255-260)            */
+    int32_t  sa_count;           /* cluster.sa_counts[0] (cluster.py:79-82)            */
+    int32_t  sa_total;           /* denominator of sa_counts[1]                        */
+    int32_t  bnd_mate_contig;
+    int32_t  bnd_mate_pos;
+    int32_t  bnd_is_first;
+    int32_t  bnd_is_reverse;
+    int32_t  n_strands;          /* len(set(lead.strand))                              */
+    int32_t  support_inline;     /* distinct qnames among INLINE leads (sv.py:195)     */
+    int32_t  lead_off;           /* first lead of this candidate in cand_leads[]       */
+    int32_t  lead_n;
+    int32_t  long_off;           /* INS: cluster.leads_long in cand_leads[]            */
+    int32_t  long_n;
+    int32_t  alt_off;            /* INS consensus: offset into alt[] (after snfb_consensus), -1 none */
+    int32_t  alt_len;
+    int32_t  hp_top, hp_support, hp_other;     /* phase_sv aggregates (postprocessing.py:626-654) */
+    int32_t  ps_top, ps_top_null, ps_support, ps_other;
+    int32_t  cluster_seed;       /* first bin of the merged cluster                    */
+    int32_t  resplit_bin;        /* id suffix of cluster.resplit (cluster.py:151)      */
+    double   stdev_pos;
+    double   stdev_len;          /* NaN when absent (BND)                              */
+    double   nm_mean;            /* -1 unless qc_nm_measure                            */
+} snfb_cand;
+
+typedef struct snfb_cand_view {
+    uint64_t n_cand;
+    const snfb_cand* cand;          /* in reference emission order: task, svtype, cluster */
+    uint64_t n_cand_leads;
+    const snfb_lead* cand_leads;    /* post merge_inner/resplit leads, reference order    */
+    const uint64_t*  rnames;        /* distinct qname hashes per candidate, CSR below     */
+    const uint32_t*  rnames_off;    /* [n_cand+1]                                          */
+    const double*    task_coverage_mean; /* [n_task] coverage_average_total (postprocessing.py:130) */
+    uint64_t unverified_breaks;     /* chain splits whose independence check failed (must be 0) */
+} snfb_cand_view;
+
+typedef struct snfb_seq_view {
+    uint64_t n_alt_bytes;
+    const uint8_t* alt;             /* ASCII, indexed by snfb_cand.alt_off/alt_len        */
+} snfb_seq_view;
+
+typedef struct snfb_ctx snfb_ctx;
+
+int         snfb_version(void);
+uint64_t    snfb_hash_name(const char* s, size_t n);
+int         snfb_ctx_create(int device, snfb_ctx** out);
+void        snfb_ctx_destroy(snfb_ctx* ctx);
+const char* snfb_last_error(snfb_ctx* ctx);
+int         snfb_set_config(snfb_ctx* ctx, const snfb_config* cfg);
+int         snfb_load_records(snfb_ctx* ctx, const snfb_records* block);
+int         snfb_extract_leads(snfb_ctx* ctx, snfb_lead_view* out);   /* out may be NULL: stay on device */
+int         snfb_cluster_call(snfb_ctx* ctx, snfb_cand_view* out);
+int         snfb_consensus(snfb_ctx* ctx, snfb_seq_view* out);
+/* all three stages back to back with no host synchronisation in between; the views
+ * (any may be NULL) are filled after one final synchronisation */
+int         snfb_run(snfb_ctx* ctx, snfb_lead_view* leads, snfb_cand_view* cands, snfb_seq_view* seqs);
+/* device-time accounting of the last run: per-kernel milliseconds from CUDA events on
+ * the ctx stream; names[i] is a static string.  Returns the number of entries. */
+int         snfb_last_timings(snfb_ctx* ctx, const char** names, float* ms, uint64_t* bytes, int cap);
+/* device pointer + count of the candidate buffer (for the NCCL all-gather done by the
+ * Python host through torch.distributed) */
+int         snfb_device_candidates(snfb_ctx* ctx, void** dptr, uint64_t* n_cand);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SNFB_H */
