@@ -134,31 +134,34 @@ def make_config(*extra_args):
 
 def run_task(block, t, config, finalize=True):
     """build_leadtab -> call_candidates -> finalize_candidates of the reference on task t.
-    Returns (lead_provider, candidates, finalized calls or None, coverage_average_total)."""
+    Returns a dict: leadtab (dumped before clustering mutates the leads), read_count, mean_nm,
+    cands (as they leave call_candidates), final (after finalize_candidates), cov_mean."""
     import_reference()
     from sniffles import leadprov, parallel
     from sniffles.region import Region
     task = block.task[t]
     contig = block.contig_names[int(task["contig"])]
     tr = None
-    if int(task["tr_n"]) > 0 or getattr(config, "tandem_repeats", None):
+    if int(task["tr_n"]) > 0:
         o, n = int(task["tr_off"]), int(task["tr_n"])
         tr = [(int(block.tr[2 * (o + k)]), int(block.tr[2 * (o + k) + 1])) for k in range(n)]
+    if not hasattr(config, "mode"):
+        config.mode = "call_sample"          # set by the CLI driver (sniffles:101-148)
     tk = parallel.CallTask(id=int(task["task_id"]), sv_id=0, contig=contig, start=int(task["start"]),
                            end=int(task["end"]), config=config, tandem_repeats=tr)
     config.task_read_id_offset_mult = 10 ** 9
     tk.lead_provider = leadprov.LeadProvider(config, tk.id * config.task_read_id_offset_mult, contig)
     tk.lead_provider.build_leadtab([Region(contig, tk.start, tk.end)], DuckBam(block, t))
+    out = dict(leadtab=leadtab_dump(tk.lead_provider), read_count=tk.lead_provider.read_count,
+               mean_nm=float(config.average_regional_nm))
     qc = not (config.snf is not None or config.no_qc)
     cands = tk.call_candidates(qc, config)
-    cov = float(tk.coverage_average_total)
-    final = None
+    out["cov_mean"] = float(tk.coverage_average_total)
+    out["cands"] = [_cand_dict(c, block) for c in cands]
     if finalize:
-        import copy
-        snap = [_cand_dict(c, block) for c in cands]
         final = tk.finalize_candidates(cands, not qc, config)
-        return tk.lead_provider, snap, [_final_dict(c) for c in final], cov
-    return tk.lead_provider, [_cand_dict(c, block) for c in cands], final, cov
+        out["final"] = [_final_dict(c) for c in final]
+    return out
 
 
 def lead_tuple(ld):
