@@ -186,6 +186,7 @@ typedef struct snfb_lead {
 #define SNFB_LF_BND_FIRST    (1u << 8)
 #define SNFB_LF_BND_REVERSE  (1u << 9)
 #define SNFB_LF_HAS_SEQ      (1u << 10)  /* seq is not None                   */
+#define SNFB_LF_NM_NONE      (1u << 11)  /* BND lead of a read without NM tag */
 #define SNFB_LF_MAPQ(f)      (((f) >> 16) & 255u)
 #define SNFB_LF_HAP(f)       (((f) >> 24) & 3u)
 

@@ -60,7 +60,7 @@ typedef struct {
     uint16_t* cov;
     int32_t* hapref;          /* [3][nbins+1] */
     long nbins;
-    uint32_t read_count; double nm_sum; long nm_count;
+    uint32_t read_count; double nm_sum; long nm_count; int cur_k;
     /* outputs */
     VEC(snfb_lead) lead_out;  /* snapshot of the leadtab before clustering mutates leads */
     VEC(snfb_cand) cands; leadvec cand_leads; VEC(uint64_t) rnames; VEC(uint32_t) rn_off;
@@ -201,7 +201,7 @@ static void emit_lead(task_t* T, olead* ld, int contig) {
     const snfb_task* tk = &T->R->task[T->t];
     /* build_leadtab keeps a lead only on the task's contig and inside its region (leadprov.py:464-468) */
     if (contig != tk->contig || ld->L.ref_start < tk->start || ld->L.ref_start >= tk->end) return;
-    ld->L.task = (uint16_t)T->t;
+    ld->L.task = (uint16_t)T->t; ld->L.k = (uint16_t)T->cur_k++;   /* ordinal among the read's kept leads */
     vpush(T->leads, *ld);
 }
 static long add_piece(task_t* T, int rec, int off, int len) { piece_t p = { rec, off, len }; vpush(T->pieces, p); return T->pieces.n - 1; }
@@ -294,7 +294,7 @@ static void process_read(task_t* T, uint64_t ri, double* rec_nm) {
     if (rec_nm) rec_nm[ri] = nm;
     uint64_t qh = so_qname_hash(R->var + r->var_off, r->l_qname);
     uint32_t base_flags = (rev ? SNFB_LF_REVERSE : 0) | ((uint32_t)r->mapq << 16);
-    int k_ord = 0;
+    T->cur_k = 0;
     /* read_iterindels (leadprov.py:583-670) */
     {
         long pos_read = 0, pos_ref = r->pos;
@@ -325,7 +325,7 @@ static void process_read(task_t* T, uint64_t ri, double* rec_nm) {
                     ld.L.qry_start = (int32_t)pos_read; ld.L.qry_end = (int32_t)(pos_read + len); ld.L.svlen = 0;
                 } else emit = 0;
                 if (emit) {
-                    ld.L.flags = f; ld.L.k = (uint16_t)k_ord++;
+                    ld.L.flags = f;
                     if (f & SNFB_LF_HAS_SEQ) { ld.pc_off = add_piece(T, (int)ri, ld.L.seq_off, ld.L.seq_len); ld.pc_n = 1; }
                     emit_lead(T, &ld, tk->contig);
                 }
@@ -364,8 +364,8 @@ static void process_read(task_t* T, uint64_t ri, double* rec_nm) {
                     ld.L.svlen = 0; ld.L.mate_pos = (int32_t)mate; ld.L.mate_contig = contig_lookup(R, e0.f[0], e0.l[0]);
                     if (ld.L.mate_contig < 0) T->soft_errors++;
                     ld.has_nm = (r->aux_flags & SNFB_AUX_NM) != 0; ld.nm = (double)sanm; ld.L.nm_sa = (int32_t)sanm;
-                    ld.L.flags = base_flags | SNFB_BND | ((uint32_t)SNFB_SRC_BND_SA << 3) | (is_first ? SNFB_LF_BND_FIRST : 0) | (is_reverse ? SNFB_LF_BND_REVERSE : 0);
-                    ld.L.k = (uint16_t)k_ord++;    /* hap "0", phase_set None, is_sa False, read_len 0: dataclass defaults */
+                    ld.L.flags = base_flags | SNFB_BND | ((uint32_t)SNFB_SRC_BND_SA << 3) | (is_first ? SNFB_LF_BND_FIRST : 0) | (is_reverse ? SNFB_LF_BND_REVERSE : 0) | (ld.has_nm ? 0 : SNFB_LF_NM_NONE);
+                    /* hap "0", phase_set None, is_sa False, read_len 0: dataclass defaults */
                     emit_lead(T, &ld, tk->contig);
                 }
             }
@@ -406,7 +406,7 @@ static void process_read(task_t* T, uint64_t ri, double* rec_nm) {
                         if (segs[i].h_none[h]) f |= SNFB_LF_SVLEN_NONE;
                         if (ty == SNFB_INS && segs[i].has_seq) { f |= SNFB_LF_HAS_SEQ; ld.L.seq_off = (int32_t)segs[i].seq_off; ld.L.seq_len = (int32_t)segs[i].seq_len;
                             ld.pc_off = add_piece(T, (int)ri, ld.L.seq_off, ld.L.seq_len); ld.pc_n = 1; }
-                        ld.L.flags = f; ld.L.k = (uint16_t)k_ord++;
+                        ld.L.flags = f;
                         emit_lead(T, &ld, segs[i].contig);
                     }
                 }

@@ -1,0 +1,169 @@
+"""ctypes binding of libsnfb200.so (include/snfb.h).  The library is CUDA-only: importing this
+module works anywhere, but creating a `Context` requires a GPU and raises otherwise — there is
+no CPU fallback for the lead -> cluster -> consensus path."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsnfb200.so")
+_LIB = None
+
+EXPORTS = ["snfb_version", "snfb_hash_name", "snfb_ctx_create", "snfb_ctx_destroy", "snfb_last_error", "snfb_set_config",
+           "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
+           "snfb_last_timings", "snfb_device_candidates"]
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the CUDA extension is required; there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.snfb_version.restype = C.c_int
+        L.snfb_hash_name.restype = C.c_uint64
+        L.snfb_hash_name.argtypes = [C.c_char_p, C.c_size_t]
+        L.snfb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.snfb_ctx_destroy.argtypes = [C.c_void_p]
+        L.snfb_last_error.restype = C.c_char_p
+        L.snfb_last_error.argtypes = [C.c_void_p]
+        L.snfb_set_config.argtypes = [C.c_void_p, C.POINTER(abi.Config)]
+        L.snfb_load_records.argtypes = [C.c_void_p, C.POINTER(abi.Records)]
+        L.snfb_extract_leads.argtypes = [C.c_void_p, C.POINTER(abi.LeadView)]
+        L.snfb_cluster_call.argtypes = [C.c_void_p, C.POINTER(abi.CandView)]
+        L.snfb_consensus.argtypes = [C.c_void_p, C.POINTER(abi.SeqView)]
+        L.snfb_run.argtypes = [C.c_void_p, C.POINTER(abi.LeadView), C.POINTER(abi.CandView), C.POINTER(abi.SeqView)]
+        L.snfb_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.c_int]
+        L.snfb_device_candidates.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        _LIB = L
+    return _LIB
+
+
+class SnfbError(RuntimeError):
+    pass
+
+
+class Result:
+    """Host copies of one run's outputs (numpy, struct layouts of include/snfb.h)."""
+
+    def __init__(self):
+        self.leads = None
+        self.task_read_count = None
+        self.task_mean_nm = None
+        self.rec_nm = None
+        self.n_pass = 0
+        self.soft_errors = 0
+        self.cand = np.zeros(0, abi.CAND_DTYPE)
+        self.cand_leads = np.zeros(0, abi.LEAD_DTYPE)
+        self.rnames = np.zeros(0, "<u8")
+        self.rn_off = np.zeros(1, "<u4")
+        self.task_cov_mean = None
+        self.alt = np.zeros(0, "u1")
+
+    def alt_of(self, i):
+        c = self.cand[i]
+        if c["alt_off"] < 0:
+            return None
+        return self.alt[int(c["alt_off"]):int(c["alt_off"]) + int(c["alt_len"])].tobytes().decode()
+
+
+class Context:
+    """One CUDA device, one stream.  Not thread safe; create it in the process that uses it
+    (after fork), never pickle it."""
+
+    def __init__(self, device: int = 0):
+        self._lib = lib()
+        h = C.c_void_p()
+        rc = self._lib.snfb_ctx_create(int(device), C.byref(h))
+        if rc != 0 or not h:
+            raise SnfbError(f"snfb_ctx_create(device={device}) failed with code {rc}: a CUDA device is required "
+                            "(libsnfb200 has no CPU fallback)")
+        self._h = h
+        self.device = device
+        self._block = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.snfb_ctx_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SnfbError(f"{what}: {self._lib.snfb_last_error(self._h).decode()}")
+
+    def set_config(self, cfg: abi.Config):
+        self._check(self._lib.snfb_set_config(self._h, C.byref(cfg)), "snfb_set_config")
+
+    def load(self, block):
+        """block: sniffles_b200.synth.RecordBlock-like (numpy arenas) or an abi.Records struct."""
+        rs = block if isinstance(block, abi.Records) else block.as_struct()
+        self._block = block          # keep host arrays alive during the async copy
+        self._check(self._lib.snfb_load_records(self._h, C.byref(rs)), "snfb_load_records")
+
+    def run(self, want_leads=True, want_cands=True, want_seqs=True, copy=True) -> Result:
+        lv, cv, sv = abi.LeadView(), abi.CandView(), abi.SeqView()
+        rc = self._lib.snfb_run(self._h, C.byref(lv) if want_leads else None, C.byref(cv) if want_cands else None,
+                                C.byref(sv) if want_seqs else None)
+        self._check(rc, "snfb_run")
+        return self._collect(lv if want_leads else None, cv if want_cands else None, sv if want_seqs else None, copy)
+
+    def extract_leads(self, want=True):
+        lv = abi.LeadView()
+        self._check(self._lib.snfb_extract_leads(self._h, C.byref(lv) if want else None), "snfb_extract_leads")
+        return self._collect(lv if want else None, None, None, True)
+
+    def cluster_call(self, want=True):
+        cv = abi.CandView()
+        self._check(self._lib.snfb_cluster_call(self._h, C.byref(cv) if want else None), "snfb_cluster_call")
+        return self._collect(None, cv if want else None, None, True)
+
+    def consensus(self, want=True):
+        sv = abi.SeqView()
+        self._check(self._lib.snfb_consensus(self._h, C.byref(sv) if want else None), "snfb_consensus")
+        return self._collect(None, None, sv if want else None, True)
+
+    def _collect(self, lv, cv, sv, copy) -> Result:
+        r = Result()
+        cp = (lambda a: a.copy()) if copy else (lambda a: a)
+        nt = None
+        if lv is not None:
+            r.leads = cp(abi.view(lv.leads, abi.LEAD_DTYPE, lv.n_leads))
+            nt = self._n_task()
+            r.task_read_count = cp(abi.view(lv.task_read_count, "<u4", nt))
+            r.task_mean_nm = cp(abi.view(lv.task_mean_nm, "<f8", nt))
+            r.n_pass, r.soft_errors = int(lv.n_pass), int(lv.soft_errors)
+            r._rec_nm_ptr = lv.rec_nm
+        if cv is not None:
+            nt = self._n_task()
+            r.cand = cp(abi.view(cv.cand, abi.CAND_DTYPE, cv.n_cand))
+            r.cand_leads = cp(abi.view(cv.cand_leads, abi.LEAD_DTYPE, cv.n_cand_leads))
+            r.rn_off = cp(abi.view(cv.rnames_off, "<u4", cv.n_cand + 1))
+            r.rnames = cp(abi.view(cv.rnames, "<u8", int(r.rn_off[-1]) if cv.n_cand else 0))
+            r.task_cov_mean = cp(abi.view(cv.task_coverage_mean, "<f8", nt))
+        if sv is not None:
+            r.alt = cp(abi.view(sv.alt, "u1", sv.n_alt_bytes))
+        return r
+
+    def _n_task(self):
+        b = self._block
+        return int(b.n_task) if isinstance(b, abi.Records) else len(b.task)
+
+    def timings(self):
+        """[(name, ms, algorithmic_bytes)] of the last run, from CUDA events on the ctx stream."""
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        by = (C.c_uint64 * 64)()
+        n = self._lib.snfb_last_timings(self._h, names, ms, by, 64)
+        return [(names[i].decode(), float(ms[i]), int(by[i])) for i in range(n)]
+
+    def device_candidates(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self._lib.snfb_device_candidates(self._h, C.byref(p), C.byref(n)), "snfb_device_candidates")
+        return p.value, int(n.value)

@@ -1,0 +1,191 @@
+// consensus.cuh — stage C: INS ALT sequences.
+//   postprocessing.annotate_sv INS branch (best read selection)        postprocessing.py:33-66
+//   consensus.novel_from_reads (k-mer anchored pile-up polish, k = 6)  consensus.py:280-394
+// One thread block per INS candidate.  The best read's strided 6-mers live in a shared-memory
+// hash table; every other read is aligned by one warp (32 k-mer probes per step, hits replayed
+// in order through the reference's anchor automaton); the column vote is one thread per column.
+#pragma once
+#include "common.cuh"
+
+namespace consensus {
+
+constexpr int THREADS = 128;
+constexpr int TAB = 2048;                  // > 4 x the at most ~500 strided k-mers of the best read
+constexpr uint8_t DASH = 0xff;
+
+struct C {
+    const snfb_cand* cand; snfb_cand* cand_rw; const snfb_lead* cand_leads; const uint32_t* cand_lead_ml;
+    const uint32_t* ml_plo; const uint32_t* ml_pn; const uint32_t* ord; const snfb_lead* leads;
+    const snfb_rec* rec; const uint8_t* seq;
+    uint32_t* plan_best; uint32_t* plan_nother; uint32_t* alt_len; uint32_t* scr_len; uint32_t* alt_off; uint32_t* scr_off;   // scr in units of 16 bytes
+    uint8_t* alt; uint8_t* scr; unsigned long long alt_cap, scr_cap16, cand_cap;
+    DevCounters* ctr; snfb_config cfg;
+};
+
+__device__ __forceinline__ uint8_t seq_code(const uint8_t* sq, long long q) { const uint8_t v = sq[q >> 1]; return (q & 1) ? (v & 15) : (v >> 4); }
+
+// choose the best read, size the outputs
+__global__ void k_plan(C c) {
+    const unsigned long long nc = c.ctr->n_cand < c.cand_cap ? c.ctr->n_cand : c.cand_cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < c.cand_cap; i += (unsigned long long)gridDim.x * blockDim.x) {
+        uint32_t al = 0, sl = 0;
+        if (i < nc && c.cand[i].svtype == SNFB_INS && !c.cfg.symbolic) {
+            const snfb_cand* cd = &c.cand[i]; long nm = 0, bi = -1; long long bd = 0; long long tot = 0;
+            for (int k = 0; k < cd->lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ)) continue;
+                // abs(len(seq) - svlen) + abs(ref_start - pos) * 1.5, compared exactly in halves
+                long long a = (long long)l->seq_len - cd->svlen; if (a < 0) a = -a; long long p = (long long)l->ref_start - cd->pos; if (p < 0) p = -p;
+                const long long d = 2 * a + 3 * p; if (nm == 0 || d < bd) { bd = d; bi = k; } ++nm; tot += l->seq_len; }
+            if (nm > 0) {
+                const uint32_t L = (uint32_t)c.cand_leads[cd->lead_off + bi].seq_len; al = L;
+                const bool cons = (nm - 1 >= c.cfg.consensus_min_reads) && !c.cfg.no_consensus;
+                c.plan_best[i] = (uint32_t)bi; c.plan_nother[i] = cons ? (uint32_t)(nm - 1) : 0u;
+                // scratch: best codes + others' codes + one row of L per other read + accept flags, 16-byte units
+                const unsigned long long bytes = cons ? (unsigned long long)tot + (unsigned long long)(nm - 1) * L + (unsigned long long)(nm - 1) * 16 + 64 : (unsigned long long)L + 16;
+                sl = (uint32_t)((bytes + 15) / 16);
+                c.cand_rw[i].alt_len = (int)L;
+            }
+        }
+        c.alt_len[i] = al; c.scr_len[i] = sl;
+    }
+}
+
+// unpack the (possibly merged) sequence of candidate lead `k` as 4-bit codes, one byte per base
+__device__ inline void unpack_lead(const C& c, uint32_t cl_index, uint8_t* dst) {
+    const uint32_t mi = c.cand_lead_ml[cl_index]; const uint32_t plo = c.ml_plo[mi], pn = c.ml_pn[mi];
+    long long o = 0;
+    for (uint32_t p = 0; p < pn; ++p) {
+        const snfb_lead* l = &c.leads[c.ord[plo + p]]; const uint8_t* sq = c.seq + c.rec[l->rec].seq_off; const long long off = l->seq_off; const int len = l->seq_len;
+        for (int j = threadIdx.x; j < len; j += blockDim.x) dst[o + j] = seq_code(sq, off + j);
+        o += len;
+    }
+}
+
+__device__ __forceinline__ uint32_t kmer6(const uint8_t* s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 4) | ((uint32_t)s[2] << 8) | ((uint32_t)s[3] << 12) | ((uint32_t)s[4] << 16) | ((uint32_t)s[5] << 20); }
+__device__ __forceinline__ uint32_t kslot(uint32_t key) { return (key * 2654435761u) >> 21; }    // top 11 bits
+
+__global__ void __launch_bounds__(THREADS) k_run(C c) {
+    __shared__ uint32_t t_key[TAB]; __shared__ int t_pos[TAB]; __shared__ uint32_t t_cnt[TAB];
+    __shared__ int n_accept;
+    const unsigned long long nc = c.ctr->n_cand < c.cand_cap ? c.ctr->n_cand : c.cand_cap;
+    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    static const char CODE[17] = "=ACMGRSVTWYHKDBN";
+    for (unsigned long long ci = blockIdx.x; ci < nc; ci += gridDim.x) {
+        const uint32_t L = c.alt_len[ci];
+        __syncthreads();
+        if (c.scr_len[ci] == 0) continue;
+        const snfb_cand cd = c.cand[ci];
+        if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) { if (threadIdx.x == 0) atomicAdd(&c.ctr->scratch_overflow, 1ULL); continue; }
+        uint8_t* out = c.alt + c.alt_off[ci];
+        uint8_t* scr = c.scr + (size_t)c.scr_off[ci] * 16;
+        uint8_t* best = scr;
+        const uint32_t bi = c.plan_best[ci], no = c.plan_nother[ci];
+        unpack_lead(c, cd.lead_off + bi, best);
+        if (threadIdx.x == 0) { c.cand_rw[ci].alt_off = (int)c.alt_off[ci]; n_accept = 0; }
+        __syncthreads();
+        if (no == 0 || L == 0) { for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) out[h] = (uint8_t)CODE[best[h]]; continue; }
+        // layout: best[L] | per other read: codes | rows[no][L] | accept[no]
+        uint8_t* oth = best + L;
+        const int klen = 6; const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
+        // anchors: k-mers of the best read seen exactly once among the strided positions (consensus.py:292-299)
+        for (int i = threadIdx.x; i < TAB; i += blockDim.x) { t_key[i] = 0xffffffffu; t_cnt[i] = 0; }
+        __syncthreads();
+        for (long i = (long)threadIdx.x * skip; i < (long)L - klen; i += (long)blockDim.x * skip) {
+            const uint32_t key = kmer6(best + i); uint32_t s = kslot(key);
+            for (;;) { const uint32_t old = atomicCAS(&t_key[s], 0xffffffffu, key); if (old == 0xffffffffu || old == key) break; s = (s + 1) & (TAB - 1); }
+            if (atomicAdd(&t_cnt[s], 1u) == 0) t_pos[s] = (int)i;
+        }
+        // offsets of the other reads' codes
+        // (serial prefix over the candidate's leads; a handful of entries)
+        __syncthreads();
+        // unpack all other reads
+        {
+            long long o = 0; uint32_t r = 0;
+            for (int k = 0; k < cd.lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd.lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ) || (uint32_t)k == bi) continue; unpack_lead(c, cd.lead_off + k, oth + o); o += l->seq_len; ++r; }
+            uint8_t* rows = oth + o; uint8_t* acc = rows + (size_t)no * L;
+            __syncthreads();
+            // ---- align every other read (one warp each) ----
+            long long ro = 0; uint32_t ridx = 0;
+            for (int k = 0; k < cd.lead_n; ++k) {
+                const snfb_lead* l = &c.cand_leads[cd.lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ) || (uint32_t)k == bi) continue;
+                const long Lo = l->seq_len; const uint8_t* rd = oth + ro; const uint32_t myr = ridx; ro += Lo; ++ridx;
+                if ((int)(myr % nwarp) != warp) continue;
+                uint8_t* row = rows + (size_t)myr * L;
+                long last_i = -1, last_j = -1, cl = 0, span = 0; bool have = false;
+                const long nk = Lo - klen > 0 ? (Lo - klen + skip - 1) / skip : 0;         // number of strided k-mers
+                for (long kb = 0; kb < nk; kb += 32) {
+                    const long kk = kb + lane; const long j = kk * skip; int ai = -1;
+                    if (kk < nk) { const uint32_t key = kmer6(rd + j); uint32_t s = kslot(key);
+                        for (;;) { const uint32_t tk = t_key[s]; if (tk == 0xffffffffu) break; if (tk == key) { if (t_cnt[s] == 1) ai = t_pos[s]; break; } s = (s + 1) & (TAB - 1); }
+                        if (ai >= 0) { long d = ai - j; if (d < 0) d = -d; if (d > klen) ai = -1; } }
+                    unsigned hits = __ballot_sync(FULL, ai >= 0);
+                    while (hits) {
+                        const int src = __ffs(hits) - 1; hits &= hits - 1;
+                        const long i = __shfl_sync(FULL, ai, src); const long jj = (kb + src) * skip;
+                        if (have && i <= last_i) continue;
+                        if (!have) { if (jj > 0) { for (long q = lane; q < i; q += 32) row[q] = DASH; cl = i; } }
+                        else {
+                            const long fwd_i = i - last_i; long fwd_j = jj - last_j;
+                            if (cl + fwd_j > (long)L) fwd_j = (long)L - cl;
+                            bool copy = false;
+                            if (fwd_i == fwd_j && fwd_j > 0) {
+                                const long d = jj - last_j; span += d; int m = 0;
+                                for (long q = 1 + lane; q <= d; q += 32) if (last_i + q < (long)L && rd[last_j + q] == best[last_i + q]) ++m;
+                                m = __reduce_add_sync(FULL, m);
+                                copy = __ddiv_rn((double)m, (double)d) >= 0.5;
+                            }
+                            if (copy) { for (long q = lane; q < fwd_j; q += 32) row[cl + q] = rd[last_j + q]; }
+                            else { for (long q = lane; q < fwd_j; q += 32) row[cl + q] = DASH; }
+                            if (fwd_j > 0) cl += fwd_j;
+                        }
+                        last_i = i; last_j = jj; have = true;
+                    }
+                }
+                for (long q = cl + lane; q < (long)L; q += 32) row[q] = DASH;
+                __syncwarp();
+                // ---- dash-free runs survive only with identity > 0.5 and more than 5 matches (consensus.py:343-360) ----
+                bool in_run = false; long run_start = 0; long ident = 0;
+                for (long h0 = 0; h0 < (long)L; h0 += 32) {
+                    const long h = h0 + lane; const uint8_t cc = h < (long)L ? row[h] : DASH;
+                    const unsigned nd = __ballot_sync(FULL, cc != DASH), mt = __ballot_sync(FULL, cc != DASH && cc == best[h < (long)L ? h : 0]);
+                    int p = 0;
+                    while (p < 32) {
+                        if (in_run) {
+                            const unsigned rest = ~(nd >> p); int cnt = rest ? __ffs(rest) - 1 : 32; if (cnt > 32 - p) cnt = 32 - p;
+                            const unsigned mask = cnt >= 32 ? 0xffffffffu : (((1u << cnt) - 1u) << p);
+                            ident += __popc(mt & mask); p += cnt;
+                            if (p < 32) {       // the run ended on a dash at h0 + p
+                                const long len = h0 + p - run_start;
+                                if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q = run_start + lane; q < h0 + p; q += 32) row[q] = DASH;
+                                in_run = false;
+                            }
+                        } else {
+                            const unsigned rest = nd >> p; if (!rest) { p = 32; break; }
+                            p += __ffs(rest) - 1; in_run = true; run_start = h0 + p; ident = 0;
+                        }
+                    }
+                }
+                if (in_run) { const long len = (long)L - run_start; if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q = run_start + lane; q < (long)L; q += 32) row[q] = DASH; }
+                const bool ok = __ddiv_rn((double)span, (double)L) > 0.2;
+                if (lane == 0) { acc[myr] = ok; if (ok) atomicAdd(&n_accept, 1); }
+            }
+            __syncthreads();
+            // ---- column vote (consensus.py:365-380) ----
+            const double maxal = (double)(1 + n_accept);
+            for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) {
+                unsigned long long cnt[4] = { 0, 0, 0, 0 }; int nal = 0;
+                for (uint32_t r2 = 0; r2 < no; ++r2) { if (!acc[r2]) continue; const uint8_t cc = rows[(size_t)r2 * L + h]; if (cc != DASH) { cnt[cc >> 2] += 1ull << (16 * (cc & 3)); ++nal; } }
+                uint8_t res = best[h];
+                if (!(nal < 2 || __ddiv_rn((double)nal, maxal) < 0.25)) {
+                    cnt[best[h] >> 2] += 1ull << (16 * (best[h] & 3));
+                    int t0 = -1, t1 = -1, c0 = 0, nd = 0;
+                    #pragma unroll
+                    for (int code = 0; code < 16; ++code) { const int v = (int)((cnt[code >> 2] >> (16 * (code & 3))) & 0xffff); if (!v) continue; ++nd; if (v > t0) { t1 = t0; t0 = v; c0 = code; } else if (v > t1) t1 = v; }
+                    if (nd > 1 && t0 - t1 >= 3) res = (uint8_t)c0;
+                }
+                out[h] = (uint8_t)CODE[res];
+            }
+        }
+    }
+}
+
+}  // namespace consensus

@@ -1,0 +1,388 @@
+// extract.cuh — stage A: alignment records -> SV leads.
+//
+// One warp per alignment record.  The warp streams the record's CIGAR with 16-byte loads
+// (128 ops per iteration, coalesced), turns op lengths into running read/reference
+// positions with a shuffle scan, and appends a 64-byte lead for every signature it meets.
+// Reference behaviour reproduced (paths relative to /root/reference/src/sniffles/):
+//   LeadProvider.iter_region filters / NM / coverage bookkeeping     leadprov.py:474-581
+//   get_cigar_indels                                                  leadprov.py:198-224
+//   read_iterindels                                                   leadprov.py:583-670
+//   Lead.for_bnd + CIGAR_analyze                                      leadprov.py:57-176
+//   read_itersplits + sv.classify_splits                              leadprov.py:227-355, sv.py:649-782
+//   build_leadtab region filter                                       leadprov.py:464-468
+#pragma once
+#include "common.cuh"
+
+namespace extract {
+
+constexpr int THREADS = 256;
+constexpr int WARPS = THREADS / 32;
+constexpr int MAXSEG = 40;     // primary + supplementary segments per read held in shared memory
+
+struct Params {
+    const snfb_rec* rec; const uint32_t* cigar; const uint8_t* var;
+    const snfb_task* task; const snfb_contig* contig;
+    uint32_t n_rec, n_task, n_contig;
+    snfb_lead* leads; unsigned long long lead_cap;
+    // per-record outputs
+    int32_t* rec_pos; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
+    // per-task outputs
+    uint32_t* task_first; uint32_t* task_last; uint32_t* task_reads; unsigned long long* task_cov_bp; int32_t* task_maxspan;
+    DevCounters* ctr;
+    snfb_config cfg;
+};
+
+// rec_flags bits
+constexpr uint8_t RF_PASS = 1, RF_HAS_NM = 2;   // bits 2..3: hp
+
+struct Seg {
+    int contig, ref_start, ref_end, qry_start, qry_end;
+    int meta;                 // bit0 rev, bits 8..15 mapq, bits 16..17 source, bit 20 has_seq
+    int nhint;
+    int h_type[2], h_start[2], h_len[2], h_none[2];
+    int seq_off, seq_len;
+};
+
+__device__ __forceinline__ bool op_adds_read(int op) { return (0x193u >> op) & 1u; }   // M I S = X  (0,1,4,7,8)
+__device__ __forceinline__ bool op_adds_ref(int op) { return (0x18Du >> op) & 1u; }    // M D N = X  (0,2,3,7,8)
+__device__ __forceinline__ bool op_is_event(int op) { return (0x016u >> op) & 1u; }    // I D S      (1,2,4)
+
+__device__ __forceinline__ void store_lead(snfb_lead* dst, const snfb_lead& l) {
+    const uint4* s = reinterpret_cast<const uint4*>(&l); uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = s[3];
+}
+
+// ---- text helpers (lane-serial; SA tags are short in the compact form aligners write) ----
+__device__ inline bool parse_int_dev(const uint8_t* s, int n, long long* out) {
+    if (n <= 0) return false; long long v = 0; int i = 0; bool neg = false;
+    if (s[0] == '-' || s[0] == '+') { neg = s[0] == '-'; i = 1; if (n == 1) return false; }
+    for (; i < n; ++i) { int c = s[i]; if (c < '0' || c > '9') return false; v = v * 10 + (c - '0'); if (v > (1LL << 40)) return false; }
+    *out = neg ? -v : v; return true;
+}
+// leadprov.CIGAR_analyze
+__device__ inline bool cigar_analyze_dev(const uint8_t* c, int n, long long* clip_start, long long* clip_end, long long* refspan, long long* readspan) {
+    long long rs = 0, qs = 0, clip = 0, cstart = -1, val = 0; bool have = false;
+    for (int i = 0; i < n; ++i) {
+        int ch = c[i];
+        if (ch >= '0' && ch <= '9') { val = val * 10 + (ch - '0'); have = true; if (val > (1LL << 40)) return false; continue; }
+        if (!have) return false;
+        bool h = false;
+        if (ch == 'M' || ch == 'I' || ch == 'X' || ch == '=') { qs += val; h = true; }
+        if (ch == 'M' || ch == 'D' || ch == 'X' || ch == '=' || ch == 'N') { rs += val; h = true; }
+        if (!h) { if (ch == 'S' || ch == 'H') { if (cstart < 0 && qs + rs > 0) cstart = clip; clip += val; } else return false; }
+        val = 0; have = false;
+    }
+    if (cstart < 0) cstart = clip;
+    *clip_start = cstart; *clip_end = clip - cstart; *refspan = rs; *readspan = qs; return true;
+}
+struct SaEntry { int off[6]; int len[6]; };
+__device__ inline bool sa_fields_dev(const uint8_t* s, int n, SaEntry* e) {
+    int k = 0, st = 0;
+    for (int i = 0; i <= n; ++i) if (i == n || s[i] == ',') { if (k == 6) return false; e->off[k] = st; e->len[k] = i - st; ++k; st = i + 1; }
+    return k == 6;
+}
+__device__ inline int contig_lookup_dev(const snfb_contig* ct, uint32_t nct, const uint8_t* s, int n) {
+    uint64_t h = fnv1a64(s, n);
+    for (uint32_t i = 0; i < nct; ++i) if (ct[i].name_hash == h) return (int)i;
+    return -1;
+}
+__device__ __forceinline__ void py_slice(long long L, long long a, long long b, int* off, int* len) {
+    if (a > L) a = L; if (b > L) b = L; *off = (int)a; *len = b > a ? (int)(b - a) : 0;
+}
+
+// sv.classify_splits on the warp's shared segment list (lane-serial); returns the new count
+__device__ inline int classify_splits_dev(const snfb_config& cfg, Seg* s, int n, int l_seq) {
+    for (int pass = 0; pass < 2; ++pass) {
+        for (int i = 1; i < n; ++i) { Seg x = s[i]; int j = i - 1; while (j >= 0 && s[j].qry_start > x.qry_start) { s[j + 1] = s[j]; --j; } s[j + 1] = x; }
+        for (int i = 0; i < n; ++i) s[i].nhint = 0;
+        int hints = 0; const int ms = cfg.minsvlen_screen;
+        if ((double)s[0].qry_start >= (double)cfg.long_ins_length * 0.5) { s[0].h_type[0] = SNFB_INS; s[0].h_start[0] = s[0].ref_start; s[0].h_len[0] = 0; s[0].h_none[0] = 1; s[0].nhint = 1; }
+        for (int i = 1; i < n; ++i) {
+            Seg* cu = &s[i]; const Seg* la = &s[i - 1];
+            if (cu->contig != la->contig) continue;
+            const bool rev = cu->meta & 1, fwd = !rev; int ty = -1; long long st = 0, ln = 0;
+            if ((cu->meta & 1) == (la->meta & 1)) {
+                long long dq = (long long)cu->qry_start - la->qry_end;
+                if (fwd && dq >= ms && dq - ((long long)cu->ref_start - la->ref_end) >= ms) {
+                    ty = SNFB_INS; st = cu->ref_start; ln = dq;
+                    if (ln <= cfg.dev_seq_cache_maxlen) { cu->meta |= 1 << 20; py_slice(l_seq, la->qry_end, cu->qry_start, &cu->seq_off, &cu->seq_len); } else cu->meta &= ~(1 << 20);
+                } else if (rev && dq >= ms && dq - ((long long)la->ref_start - cu->ref_end) >= ms) {
+                    ty = SNFB_INS; st = la->ref_start; ln = dq;
+                    if (ln <= cfg.dev_seq_cache_maxlen) { cu->meta |= 1 << 20; py_slice(l_seq, la->qry_end, cu->qry_start, &cu->seq_off, &cu->seq_len); } else cu->meta &= ~(1 << 20);
+                } else if (fwd && ((long long)cu->ref_start - la->ref_end) >= ms && ((long long)cu->ref_start - la->ref_end) - dq >= ms) {
+                    ty = SNFB_DEL; st = cu->ref_start; ln = -((long long)cu->ref_start - la->ref_end);
+                } else if (rev && ((long long)la->ref_start - cu->ref_end) >= ms && ((long long)la->ref_start - cu->ref_end) - dq >= ms) {
+                    ty = SNFB_DEL; st = la->ref_start; ln = -((long long)la->ref_start - cu->ref_end);
+                } else if (fwd && cu->ref_start <= la->ref_end) {
+                    st = cu->ref_start; ln = (long long)la->ref_end - cu->ref_start; if (ln >= ms) ty = SNFB_DUP;
+                } else if (rev && la->ref_start <= cu->ref_end) {
+                    st = la->ref_start; ln = (long long)cu->ref_end - la->ref_start; if (ln >= ms) ty = SNFB_DUP;
+                }
+            } else {
+                if (fwd && cu->ref_start <= la->ref_start) { st = cu->ref_start; ln = (long long)la->ref_start - cu->ref_start; if (ln >= ms) ty = SNFB_INV; }
+                else if (fwd && cu->ref_start > la->ref_start) { st = la->ref_start; ln = (long long)cu->ref_start - la->ref_start; if (ln >= ms) ty = SNFB_INV; }
+                else if (rev && cu->ref_end >= la->ref_end) { st = la->ref_end; ln = (long long)cu->ref_end - la->ref_end; if (ln >= ms) ty = SNFB_INV; }
+                else if (rev && cu->ref_end < la->ref_end) { st = cu->ref_end; ln = (long long)la->ref_end - cu->ref_end; if (ln >= ms) ty = SNFB_INV; }
+            }
+            if (ty >= 0) { int k = cu->nhint++; cu->h_type[k] = ty; cu->h_start[k] = (int)st; cu->h_len[k] = (int)ln; cu->h_none[k] = 0; ++hints; }
+        }
+        if (!hints && n > 2) {
+            int m = 0; const int c0 = s[0].contig, r0 = s[0].meta & 1;
+            for (int i = 0; i < n; ++i) if (s[i].contig == c0 && (s[i].meta & 1) == r0) { Seg t = s[i]; s[m++] = t; }
+            if (m == 2) { s[0].meta &= ~(1 << 20); s[1].meta &= ~(1 << 20); n = 2; continue; }   // one recursion level (sv.py:779-780)
+            return m;
+        }
+        return n;
+    }
+    return n;
+}
+
+__global__ void __launch_bounds__(THREADS) k_extract(const Params P) {
+    __shared__ Seg segs[WARPS][MAXSEG];
+    const snfb_config& cfg = P.cfg;
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    const unsigned nwarps = gridDim.x * WARPS;
+    // per-warp accumulators flushed when the task changes (records are grouped by task)
+    int acc_task = -1; unsigned acc_reads = 0; unsigned long long acc_bp = 0; int acc_span = 0;
+    unsigned long long soft = 0, overflow = 0, unsorted = 0;
+
+    for (unsigned rec = blockIdx.x * WARPS + wib; rec < P.n_rec; rec += nwarps) {
+        const snfb_rec r = P.rec[rec];
+        const snfb_task tk = P.task[r.task];
+        const uint32_t* __restrict__ cg = P.cigar + r.cigar_off;
+        const int n = (int)r.n_cigar;
+        if (lane == 0) {
+            P.rec_pos[rec] = r.pos;
+            if (rec == 0 || P.rec[rec - 1].task != r.task) P.task_first[r.task] = rec;
+            else if (P.rec[rec - 1].pos > r.pos) ++unsorted;
+            if (rec + 1 == P.n_rec || P.rec[rec + 1].task != r.task) P.task_last[r.task] = rec + 1;
+        }
+        // pysam query_alignment_start / _end
+        int qas = 0, qae = r.l_seq;
+        for (int k = 0; k < n; ++k) { uint32_t c = cg[k]; int op = c & 15; if (op == 4) qas += (int)(c >> 4); else if (op != 5) break; }
+        for (int k = n - 1; k >= 1; --k) { uint32_t c = cg[k]; int op = c & 15; if (op == 4) qae -= (int)(c >> 4); else if (op != 5) break; }
+        const int alen = qae - qas;
+        bool pass = !(r.mapq < cfg.mapq || (r.flag & 256) || alen < cfg.min_alignment_length);
+        if (cfg.exclude_flags && (r.flag & cfg.exclude_flags)) pass = false;
+        if (r.pos < tk.start || r.pos >= tk.end) pass = false;
+        if (!pass || n == 0) {
+            if (lane == 0) { P.rec_end[rec] = -1; P.rec_flags[rec] = 0; P.rec_nm[rec] = -1.0; P.rec_nlead[rec] = 0; }
+            continue;
+        }
+        int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0;
+        if (hp > 2) { hp = 0; if (lane == 0) ++soft; }
+        const bool is_supp = r.flag & 2048, rev = r.flag & 16, has_sa = r.aux_flags & SNFB_AUX_SA;
+        const bool use_clips = cfg.detect_large_ins && !is_supp && !has_sa;
+        const double longinslen = (double)cfg.long_ins_length / 2.0;
+        const uint32_t base_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r.mapq << 16);
+        const uint32_t inl_flags = base_flags | ((uint32_t)SNFB_SRC_INLINE << 3) | ((uint32_t)hp << 24) | (is_supp ? SNFB_LF_IS_SA : 0u);
+        uint64_t qh = 0; bool have_qh = false;
+        unsigned nlead = 0;
+
+        // ---- CIGAR stream: 4 ops per lane per iteration ----
+        unsigned pos_q = 0; int pos_r = r.pos; unsigned big = 0;
+        const long long c_begin = (long long)r.cigar_off, c_end = c_begin + n;
+        for (long long c0 = c_begin & ~3LL; c0 < c_end; c0 += 128) {
+            const long long i0 = c0 + lane * 4;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            if (i0 < c_end && i0 + 3 >= c_begin) v = *reinterpret_cast<const uint4*>(P.cigar + i0);
+            uint32_t w[4] = { v.x, v.y, v.z, v.w };
+            unsigned lq = 0, lr = 0; unsigned eq[4], er[4]; bool ev[4]; bool anyev = false;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long gi = i0 + j; const bool valid = gi >= c_begin && gi < c_end;
+                const int op = valid ? (int)(w[j] & 15u) : 6; const unsigned len = valid ? (w[j] >> 4) : 0u;
+                w[j] = (len << 4) | (unsigned)op;
+                eq[j] = lq; er[j] = lr;
+                if (op_adds_read(op)) lq += len;
+                if (op_adds_ref(op)) lr += len;
+                if ((op == 1 || op == 2) && len > 10) big += len;             // get_cigar_indels, minoplen 10
+                ev[j] = op_is_event(op) && (int)len >= cfg.minsvlen_screen;
+                anyev |= ev[j];
+            }
+            unsigned iq = lq, ir = lr;      // inclusive warp scan of the lane totals
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
+            const unsigned lane_q = pos_q + iq - lq; const int lane_r = pos_r + (int)(ir - lr);
+            if (__any_sync(FULL, anyev)) {
+                // which events become leads that stay in the task's region (leadprov.py:464-466)
+                int cnt = 0; bool em[4];
+                #pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    em[j] = false;
+                    if (ev[j]) { const int op = w[j] & 15; const int len = (int)(w[j] >> 4); const int pr = lane_r + (int)er[j];
+                        const int rs = op == 2 ? pr + len : pr; em[j] = rs >= tk.start && rs < tk.end; cnt += em[j]; }
+                }
+                int inc = cnt;
+                #pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+                const int total = __shfl_sync(FULL, inc, 31);
+                if (total > 0) {
+                    if (!have_qh) { qh = qname_hash_warp(P.var + r.var_off, r.l_qname); have_qh = true; }
+                    unsigned long long slot0 = 0;
+                    if (lane == 0) slot0 = atomicAdd(&P.ctr->n_leads, (unsigned long long)total);
+                    slot0 = __shfl_sync(FULL, slot0, 0);
+                    int mine = inc - cnt;
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) if (em[j]) {
+                        const int op = w[j] & 15; const int len = (int)(w[j] >> 4);
+                        const int pq = (int)(lane_q + eq[j]); const int pr = lane_r + (int)er[j];
+                        snfb_lead L;
+                        L.rec = rec; L.qname_hash = qh; L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
+                        L.task = (uint16_t)r.task; L.k = (uint16_t)(nlead + mine);
+                        uint32_t f = inl_flags;
+                        if (op == 1) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pq; L.qry_end = pq + len; L.svlen = len;
+                            if (len <= cfg.dev_seq_cache_maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pq; L.seq_len = len; } }
+                        else if (op == 2) { f |= SNFB_DEL; L.ref_start = pr + len; L.ref_end = pr; L.qry_start = pq; L.qry_end = pq; L.svlen = -len; }
+                        else if (use_clips && (double)len >= longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pq; L.qry_end = pq + len; L.svlen = 0; }
+                        else { f |= (pr == r.pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pq; L.qry_end = pq + len; L.svlen = 0; }
+                        L.flags = f;
+                        const unsigned long long slot = slot0 + (unsigned long long)mine;
+                        if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
+                        ++mine;
+                    }
+                    nlead += (unsigned)total;
+                }
+            }
+            pos_q += __shfl_sync(FULL, iq, 31); pos_r += (int)__shfl_sync(FULL, ir, 31);
+        }
+        const int ref_end = pos_r;
+        big = __reduce_add_sync(FULL, big);
+        double nm = -1.0; bool has_nm = false;
+        if ((cfg.qc_nm_measure || cfg.phase) && (r.aux_flags & SNFB_AUX_NM)) {      // leadprov.py:517-526
+            nm = __ddiv_rn((double)((long long)r.nm - (long long)big), (double)(alen + 1)); has_nm = true;
+        }
+
+        // ---- supplementary alignments (SA tag): lane-serial ----
+        if (has_sa) {
+            if (!have_qh) { qh = qname_hash_warp(P.var + r.var_off, r.l_qname); have_qh = true; }
+            unsigned added = 0;
+            if (lane == 0) {
+                const uint8_t* sa = P.var + r.var_off + r.l_qname; const int sl = (int)r.sa_len;
+                Seg* sg = segs[wib];
+                // pass 1: count the non-empty entries and locate the first one
+                int ne = 0, f_off = 0, f_len = 0;
+                for (int i = 0, st = 0; i <= sl; ++i) if (i == sl || sa[i] == ';') { if (i > st) { if (ne == 0) { f_off = st; f_len = i - st; } ++ne; } st = i + 1; }
+                bool sa_ok = true; SaEntry e0;
+                if (ne > 0 && !sa_fields_dev(sa + f_off, f_len, &e0)) { sa_ok = false; ++soft; }
+                if (ne > 0 && sa_ok) {                                   // Lead.for_bnd: first entry only
+                    const uint8_t* e = sa + f_off;
+                    int left = 0, right = 0;
+                    { uint32_t c = cg[0]; int op = c & 15; if (op == 4 || op == 5) left = (int)(c >> 4); }
+                    { uint32_t c = cg[n - 1]; int op = c & 15; if (op == 4 || op == 5) right = (int)(c >> 4); }
+                    int bstart; bool is_first;
+                    if (left > right) { bstart = r.pos + 1; is_first = false; } else { bstart = ref_end; is_first = true; }
+                    const bool same = e0.len[2] == 1 && ((e[e0.off[2]] == '-' && rev) || (e[e0.off[2]] == '+' && !rev));
+                    if (!same) {
+                        long long p1, cs, ce, rs, qs, sanm = 0;
+                        if (!parse_int_dev(e + e0.off[1], e0.len[1], &p1)) ++soft;
+                        else if (!cigar_analyze_dev(e + e0.off[3], e0.len[3], &cs, &ce, &rs, &qs)) ++soft;
+                        else if ((r.aux_flags & SNFB_AUX_NM) && !parse_int_dev(e + e0.off[5], e0.len[5], &sanm)) ++soft;
+                        else {
+                            const long long p0 = p1 - 1; const bool is_reverse = ce > cs;
+                            const long long mate = is_reverse ? p0 + rs : (is_first ? p0 + 1 : p0 + 2);
+                            if (bstart >= tk.start && bstart < tk.end) {
+                                snfb_lead L;
+                                L.rec = rec; L.qname_hash = qh; L.read_len = 0; L.seq_off = -1; L.seq_len = 0;
+                                L.ref_start = L.ref_end = bstart; L.qry_start = qas; L.qry_end = qae; L.svlen = 0;
+                                L.mate_pos = (int)mate; L.mate_contig = contig_lookup_dev(P.contig, P.n_contig, e + e0.off[0], e0.len[0]);
+                                if (L.mate_contig < 0) ++soft;
+                                L.nm_sa = (int)sanm; L.task = (uint16_t)r.task; L.k = (uint16_t)(nlead + added);
+                                L.flags = base_flags | SNFB_BND | ((uint32_t)SNFB_SRC_BND_SA << 3) | (is_first ? SNFB_LF_BND_FIRST : 0u) | (is_reverse ? SNFB_LF_BND_REVERSE : 0u)
+                                          | ((r.aux_flags & SNFB_AUX_NM) ? 0u : (1u << 11));   // bit 11: nm is None
+                                const unsigned long long slot = atomicAdd(&P.ctr->n_leads, 1ULL);
+                                if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
+                                ++added;
+                            }
+                        }
+                    }
+                }
+                // read_itersplits: primary alignments only
+                if (!is_supp && sa_ok && ne > 0) {
+                    const double lim = __dadd_rn((double)cfg.max_splits_base, __dmul_rn(cfg.max_splits_kb, __ddiv_rn((double)r.l_seq, 1000.0)));
+                    if (!((double)ne > lim)) {
+                        if (ne + 1 > MAXSEG) ++soft;
+                        else {
+                            bool ok = true;
+                            sg[0].contig = tk.contig; sg[0].ref_start = r.pos; sg[0].ref_end = ref_end;
+                            sg[0].qry_start = rev ? r.l_seq - qae : qas; sg[0].qry_end = sg[0].qry_start + alen;
+                            sg[0].meta = (rev ? 1 : 0) | ((int)r.mapq << 8) | (SNFB_SRC_SPLIT_PRIM << 16); sg[0].nhint = 0;
+                            int ei = 0;
+                            for (int i = 0, st = 0; i <= sl && ok; ++i) if (i == sl || sa[i] == ';') {
+                                if (i > st) {
+                                    SaEntry en; const uint8_t* e = sa + st; long long p1, cs, ce, rs, qs, mq;
+                                    if (!sa_fields_dev(e, i - st, &en) || !parse_int_dev(e + en.off[4], en.len[4], &mq)) { ok = false; ++soft; break; }
+                                    const bool srev = en.len[2] == 1 && e[en.off[2]] == '-';
+                                    if (!cigar_analyze_dev(e + en.off[3], en.len[3], &cs, &ce, &rs, &qs)) { ok = false; ++soft; break; }
+                                    if (!parse_int_dev(e + en.off[1], en.len[1], &p1)) { ok = false; ++soft; break; }
+                                    Seg* g = &sg[++ei];
+                                    g->contig = contig_lookup_dev(P.contig, P.n_contig, e + en.off[0], en.len[0]); if (g->contig < 0) { g->contig = -2 - ei; ++soft; }
+                                    g->ref_start = (int)(p1 - 1); g->ref_end = (int)(p1 - 1 + rs); g->qry_start = (int)(srev ? ce : cs); g->qry_end = g->qry_start + (int)qs;
+                                    g->meta = (srev ? 1 : 0) | ((int)mq << 8) | (SNFB_SRC_SPLIT_SUP << 16); g->nhint = 0;
+                                }
+                                st = i + 1;
+                            }
+                            if (ok) {
+                                const int m = classify_splits_dev(cfg, sg, ne + 1, r.l_seq);
+                                for (int i = 0; i < m; ++i) for (int h = 0; h < sg[i].nhint; ++h) {
+                                    const int mqc = (sg[i].meta >> 8) & 255, mqp = (sg[i > 0 ? i - 1 : 0].meta >> 8) & 255;
+                                    if (!cfg.dev_keep_lowqual_splits && (mqc < mqp ? mqc : mqp) < cfg.mapq) continue;
+                                    const int ty = sg[i].h_type[h]; const int hs = sg[i].h_start[h];
+                                    if (sg[i].contig != tk.contig || hs < tk.start || hs >= tk.end) continue;
+                                    snfb_lead L;
+                                    L.rec = rec; L.qname_hash = qh; L.read_len = 0; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
+                                    L.ref_start = hs; L.ref_end = (!sg[i].h_none[h] && ty != SNFB_INS) ? hs + sg[i].h_len[h] : hs;
+                                    L.qry_start = sg[i].qry_start; L.qry_end = sg[i].qry_end; L.svlen = sg[i].h_len[h];
+                                    uint32_t f = (uint32_t)ty | ((uint32_t)((sg[i].meta >> 16) & 3) << 3) | ((sg[i].meta & 1) ? SNFB_LF_REVERSE : 0u) | ((uint32_t)mqc << 16) | ((uint32_t)hp << 24);
+                                    if (sg[i].h_none[h]) f |= SNFB_LF_SVLEN_NONE;
+                                    if (ty == SNFB_INS && (sg[i].meta & (1 << 20))) { f |= SNFB_LF_HAS_SEQ; L.seq_off = sg[i].seq_off; L.seq_len = sg[i].seq_len; }
+                                    L.flags = f; L.task = (uint16_t)r.task; L.k = (uint16_t)(nlead + added);
+                                    const unsigned long long slot = atomicAdd(&P.ctr->n_leads, 1ULL);
+                                    if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
+                                    ++added;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            nlead += __shfl_sync(FULL, added, 0);
+        }
+        if (lane == 0) {
+            P.rec_end[rec] = ref_end;
+            P.rec_flags[rec] = (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2));
+            P.rec_nm[rec] = nm; P.rec_nlead[rec] = nlead;
+            if (acc_task != r.task) {
+                if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
+                acc_task = r.task; acc_reads = 0; acc_bp = 0; acc_span = 0;
+            }
+            ++acc_reads;
+            const int ce = ref_end < tk.contig_len ? ref_end : tk.contig_len;
+            if (ce > r.pos) acc_bp += (unsigned long long)(ce - r.pos);
+            if (ref_end - r.pos > acc_span) acc_span = ref_end - r.pos;
+        }
+    }
+    if (lane == 0) {
+        if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); atomicAdd(&P.ctr->n_pass, (unsigned long long)0); }
+        if (soft) atomicAdd(&P.ctr->soft_errors, soft);
+        if (unsorted) atomicAdd(&P.ctr->unsorted, unsorted);
+    }
+    // overflow is counted by whichever lane hit it
+    if (overflow) atomicAdd(&P.ctr->lead_overflow, overflow);
+}
+
+// deterministic per-task mean of the per-read nm values (config.average_regional_nm, leadprov.py:577).
+// Fixed reduction tree: the result does not depend on scheduling (it can differ from the
+// reference's sequential float accumulation in the last bits).
+__global__ void __launch_bounds__(256) k_task_nm(const uint8_t* __restrict__ rec_flags, const double* __restrict__ rec_nm, const uint32_t* __restrict__ task_first,
+                                                 const uint32_t* __restrict__ task_last, double* __restrict__ task_mean_nm) {
+    __shared__ double ssum[256]; __shared__ unsigned long long scnt[256];
+    const int t = blockIdx.x; const uint32_t lo = task_first[t], hi = task_last[t];
+    double s = 0; unsigned long long c = 0;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) if ((rec_flags[i] & (RF_PASS | RF_HAS_NM)) == (RF_PASS | RF_HAS_NM)) { s += rec_nm[i]; ++c; }
+    ssum[threadIdx.x] = s; scnt[threadIdx.x] = c; __syncthreads();
+    for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) task_mean_nm[t] = ssum[0] / (double)(scnt[0] > 1 ? scnt[0] : 1);
+}
+
+}  // namespace extract

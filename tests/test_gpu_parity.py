@@ -1,0 +1,54 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs."""
+import pytest
+
+from sniffles_b200 import abi, binding, synth
+from sniffles_b200 import config as sconfig
+import devcheck
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(blk, *args):
+    import oracle.oracle as orc
+    cfg = abi.Config.from_sniffles(sconfig.default_config(*args))
+    ctx = binding.Context(0)
+    try:
+        ctx.set_config(cfg)
+        ctx.load(blk)
+        got = ctx.run()
+    finally:
+        ctx.close()
+    want = orc.run(blk, cfg, 3, 4)
+    devcheck.assert_same(want, got)
+    return got
+
+
+def test_config1_shape():
+    got = _run(synth.config_block(1))
+    assert len(got.cand) > 20
+
+
+@pytest.mark.parametrize("args", [(), ("--mosaic",), ("--no-qc",), ("--repeat",), ("--minsvlen", "30")])
+def test_config2_scaled(args):
+    _run(synth.config_block(2, 0.004), *args)
+
+
+def test_config3_hifi_mosaic():
+    _run(synth.config_block(3, 0.003), "--mosaic")
+
+
+def test_config5_ins_heavy():
+    got = _run(synth.config_block(5, 0.05))
+    assert (got.cand["svtype"] == 0).sum() > 100
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes(seed):
+    import random
+    rnd = random.Random(seed)
+    lens = [rnd.randrange(150000, 600000) for _ in range(rnd.choice([1, 2, 3]))]
+    blk = synth.generate(1000 + seed, lens, coverage=rnd.choice([8, 15, 30, 60]), len_mean=rnd.choice([3000.0, 8000.0, 20000.0]),
+                         len_sd=rnd.choice([300.0, 2000.0]), tech=rnd.choice(["ont", "hifi"]), sv_spacing=rnd.choice([800.0, 3000.0, 20000.0]),
+                         phased_frac=rnd.choice([0.0, 0.5, 1.0]), tr_frac=rnd.choice([0.0, 0.15, 0.6]), ins_only=rnd.random() < 0.2,
+                         clip_prob=rnd.choice([0.0, 0.1, 0.5]), lowmapq_prob=rnd.choice([0.05, 0.3]))
+    _run(blk, *rnd.choice([(), ("--mosaic",), ("--no-qc",), ("--qc-nm",), ("--cluster-merge-pos", "50")]))
