@@ -259,6 +259,8 @@ typedef struct snfb_seq_view {
 typedef struct snfb_ctx snfb_ctx;
 
 int         snfb_version(void);
+/* sizeof of the ABI structs, for binding self-checks: 0 rec, 1 task, 2 contig, 3 records, 4 config, 5 lead, 6 cand */
+size_t      snfb_sizeof(int which);
 uint64_t    snfb_hash_name(const char* s, size_t n);
 int         snfb_ctx_create(int device, snfb_ctx** out);
 void        snfb_ctx_destroy(snfb_ctx* ctx);

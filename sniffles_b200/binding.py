@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsnfb200.so")
 _LIB = None
 
-EXPORTS = ["snfb_version", "snfb_hash_name", "snfb_ctx_create", "snfb_ctx_destroy", "snfb_last_error", "snfb_set_config",
+EXPORTS = ["snfb_version", "snfb_sizeof", "snfb_hash_name", "snfb_ctx_create", "snfb_ctx_destroy", "snfb_last_error", "snfb_set_config",
            "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
            "snfb_last_timings", "snfb_device_candidates"]
 
@@ -25,6 +25,8 @@ def lib():
                                "(the CUDA extension is required; there is no CPU fallback)")
         L = C.CDLL(LIB_PATH)
         L.snfb_version.restype = C.c_int
+        L.snfb_sizeof.restype = C.c_size_t
+        L.snfb_sizeof.argtypes = [C.c_int]
         L.snfb_hash_name.restype = C.c_uint64
         L.snfb_hash_name.argtypes = [C.c_char_p, C.c_size_t]
         L.snfb_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]

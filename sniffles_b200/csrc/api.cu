@@ -87,6 +87,10 @@ static void mark(snfb_ctx* ctx, const char* name, uint64_t bytes = 0) {
 extern "C" {
 
 int snfb_version(void) { return SNFB_ABI_VERSION; }
+size_t snfb_sizeof(int which) {
+    switch (which) { case 0: return sizeof(snfb_rec); case 1: return sizeof(snfb_task); case 2: return sizeof(snfb_contig); case 3: return sizeof(snfb_records);
+                     case 4: return sizeof(snfb_config); case 5: return sizeof(snfb_lead); case 6: return sizeof(snfb_cand); default: return 0; }
+}
 
 uint64_t snfb_hash_name(const char* s, size_t n) {
     uint64_t h = 0xcbf29ce484222325ull; for (size_t i = 0; i < n; ++i) { h ^= (uint8_t)s[i]; h *= 0x100000001b3ull; } return h;

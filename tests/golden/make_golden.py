@@ -1,0 +1,108 @@
+"""Generates the committed golden fixtures from the UNMODIFIED reference
+(/root/reference/src/sniffles behind oracle/pyref's stub pysam).  Runs only in the build
+container; the fixtures travel, the reference does not.
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/<name>.json (reference outputs for a seeded synthetic block: the lead
+table before clustering, the candidates as they leave Task.call_candidates, the finalized
+calls with FILTER / GT / ALT) and tests/golden/hg008_bnd.npz + .json (the reference's own
+test BAMs src/tests/data/hg008.bam, hg002.bam packed into a record block, with what
+Lead.for_bnd returns per record — the vectors of src/tests/test_bnd_leads.py)."""
+import hashlib
+import json
+import logging
+import os
+import platform
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle", "pyref")]
+logging.disable(logging.CRITICAL)
+
+import harness  # noqa: E402
+from sniffles_b200 import bampack, synth  # noqa: E402
+
+FIXTURES = {
+    # name: (synth.generate kwargs, reference CLI args)
+    "c1_ont_1mb": (dict(seed=1001, contig_len=[1_000_000], coverage=20.0, len_model=0, len_mean=100000.0, len_sd=10000.0,
+                        len_min=1000, len_max=200000, tech="ont", sv_spacing=25000.0), []),
+    "c2_ont_wgs_small": (dict(seed=1002, contig_len=[300_000, 260_000, 220_000, 150_000], coverage=30.0, len_model=1, len_mean=15000.0,
+                              len_sd=600.0, tech="ont", sv_spacing=15000.0), []),
+    "c3_hifi_mosaic": (dict(seed=1003, contig_len=[400_000, 300_000], coverage=60.0, len_model=0, len_mean=18000.0, len_sd=3000.0,
+                            len_max=60000, tech="hifi", mosaic=True, sv_spacing=12000.0), ["--mosaic"]),
+    "c5_ins_heavy": (dict(seed=1005, contig_len=[150_000], coverage=20.0, len_model=0, len_mean=20000.0, len_sd=2000.0, len_min=5000,
+                          len_max=60000, tech="ont", sv_spacing=1000.0, ins_only=True, tr_frac=0.0, clip_prob=0.0), []),
+    "tr_repeat_noqc": (dict(seed=77, contig_len=[250_000], coverage=25.0, len_mean=9000.0, len_sd=2500.0, tech="ont", sv_spacing=2500.0,
+                            tr_frac=0.6, clip_prob=0.3, phased_frac=1.0), ["--no-qc"]),
+    "auto_support_qcnm": (dict(seed=78, contig_len=[200_000, 180_000], coverage=40.0, len_mean=6000.0, len_sd=1500.0, tech="ont",
+                               sv_spacing=4000.0, lowmapq_prob=0.3, phased_frac=0.0), ["--minsupport", "auto", "--qc-nm"]),
+}
+
+
+def block_digest(blk):
+    h = hashlib.sha256()
+    for a in (blk.rec, blk.cigar, blk.var, blk.seq, blk.task, blk.tr):
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def make_synthetic():
+    for name, (kw, args) in FIXTURES.items():
+        kw2 = dict(kw)
+        blk = synth.generate(kw2.pop("seed"), kw2.pop("contig_len"), kw2.pop("coverage"), **kw2)
+        cfg = harness.make_config(*args)
+        tasks = [harness.run_task(blk, t, cfg) for t in range(len(blk.task))]
+        out = dict(generator=kw, args=args, digest=block_digest(blk), n_rec=len(blk.rec), tasks=tasks,
+                   made_with=dict(python=platform.python_version(), numpy=np.__version__, reference="fritzsedlazeck/Sniffles 2.8.1-dev @7fcaf867"))
+        path = os.path.join(HERE, name + ".json")
+        with open(path, "w") as f:
+            json.dump(out, f, separators=(",", ":"))
+        print(name, "records", len(blk.rec), "cands", sum(len(t["cands"]) for t in tasks), os.path.getsize(path) // 1024, "KiB")
+
+
+def make_bam_vectors():
+    harness.import_reference()
+    from sniffles.leadprov import Lead
+    data = os.path.join(harness.REFERENCE_SRC, "tests", "data")
+    blocks, expect = [], []
+    for fn in ("hg008.bam", "hg002.bam"):
+        contigs, recs = bampack.read_bam(os.path.join(data, fn))
+        blk = bampack.pack(contigs, recs, with_seq=False)
+        for i in range(len(blk.rec)):
+            rd = harness.DuckRead(blk, i)
+            ld = Lead.for_bnd(0, rd)
+            expect.append(dict(file=fn, qname=rd.query_name, contig=rd.reference_name, pos=rd.reference_start,
+                               lead=None if ld is None else [ld.ref_start, ld.bnd_info.mate_contig, ld.bnd_info.mate_ref_start,
+                                                             bool(ld.bnd_info.is_first), bool(ld.bnd_info.is_reverse)]))
+        blocks.append((fn, blk))
+    arrays = {}
+    for fn, blk in blocks:
+        k = fn.split(".")[0]
+        for nm in ("rec", "cigar", "var", "task", "contig"):
+            arrays[f"{k}_{nm}"] = getattr(blk, nm)
+        arrays[f"{k}_names"] = np.array(blk.contig_names)
+    np.savez_compressed(os.path.join(HERE, "hg008_bnd.npz"), **arrays)
+    with open(os.path.join(HERE, "hg008_bnd.json"), "w") as f:
+        json.dump(dict(source="src/tests/data/hg008.bam, hg002.bam; expectations = Lead.for_bnd of the reference at HEAD "
+                              "(8 leads equal the tuples asserted in src/tests/test_bnd_leads.py:48-188, 9 are None)", records=expect), f, indent=1)
+    print("bam vectors", [(e["qname"][:8], e["lead"]) for e in expect])
+
+
+def make_config_dump():
+    out = {}
+    for args in ([], ["--mosaic"], ["--no-qc"], ["--minsvlen", "30"], ["--minsupport", "auto"], ["--dev-no-qc"], ["--qc-nm", "--cluster-merge-len", "0.3"]):
+        cfg = harness.make_config(*args)
+        out[" ".join(args)] = {k: v for k, v in vars(cfg).items() if isinstance(v, (int, float, str, bool, type(None))) and k not in
+                               ("start_date", "run_id", "command", "workdir", "tmp_dir", "version", "build", "snf_format_version", "input", "vcf")}
+    with open(os.path.join(HERE, "config_defaults.json"), "w") as f:
+        json.dump(out, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    make_config_dump()
+    make_synthetic()
+    make_bam_vectors()
