@@ -279,6 +279,12 @@ int         snfb_last_timings(snfb_ctx* ctx, const char** names, float* ms, uint
 /* device pointer + count of the candidate buffer (for the NCCL all-gather done by the
  * Python host through torch.distributed) */
 int         snfb_device_candidates(snfb_ctx* ctx, void** dptr, uint64_t* n_cand);
+int         snfb_device_alt(snfb_ctx* ctx, void** dptr, uint64_t* n_bytes);
+/* number of kernels launched by the library on this ctx since it was created */
+uint64_t    snfb_launch_count(snfb_ctx* ctx);
+/* page-lock / unlock caller-owned host memory so that snfb_load_records copies at full PCIe rate */
+int         snfb_pin_host(void* p, size_t bytes);
+int         snfb_unpin_host(void* p);
 
 #ifdef __cplusplus
 }

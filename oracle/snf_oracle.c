@@ -874,6 +874,7 @@ so_result* so_run(const snfb_records* R, const snfb_config* cfg, int stages, int
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads > 0 ? threads : 1)
     for (int t = 0; t < (int)nt; ++t) {
         T[t].R = R; T[t].cfg = cfg; T[t].t = t;
+        if (!(lo[t] < hi[t])) { vpush(T[t].rn_off, 0u); continue; }   /* no records: nothing to do for this task */
         run_task(&T[t], out->rec_nm, stages, lo[t] < hi[t] ? lo[t] : 0, lo[t] < hi[t] ? hi[t] : 0);
     }
     uint64_t nl = 0, ncd = 0, ncl = 0, nrn = 0, nalt = 0;

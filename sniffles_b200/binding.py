@@ -14,7 +14,8 @@ _LIB = None
 
 EXPORTS = ["snfb_version", "snfb_sizeof", "snfb_hash_name", "snfb_ctx_create", "snfb_ctx_destroy", "snfb_last_error", "snfb_set_config",
            "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
-           "snfb_last_timings", "snfb_device_candidates"]
+           "snfb_last_timings", "snfb_device_candidates", "snfb_device_alt", "snfb_launch_count",
+           "snfb_pin_host", "snfb_unpin_host"]
 
 
 def lib():
@@ -41,6 +42,11 @@ def lib():
         L.snfb_run.argtypes = [C.c_void_p, C.POINTER(abi.LeadView), C.POINTER(abi.CandView), C.POINTER(abi.SeqView)]
         L.snfb_last_timings.argtypes = [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_uint64), C.c_int]
         L.snfb_device_candidates.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.snfb_device_alt.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.snfb_launch_count.restype = C.c_uint64
+        L.snfb_launch_count.argtypes = [C.c_void_p]
+        L.snfb_pin_host.argtypes = [C.c_void_p, C.c_size_t]
+        L.snfb_unpin_host.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -163,6 +169,15 @@ class Context:
         by = (C.c_uint64 * 64)()
         n = self._lib.snfb_last_timings(self._h, names, ms, by, 64)
         return [(names[i].decode(), float(ms[i]), int(by[i])) for i in range(n)]
+
+    def launch_count(self):
+        return int(self._lib.snfb_launch_count(self._h))
+
+    def device_alt(self):
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self._lib.snfb_device_alt(self._h, C.byref(p), C.byref(n)), "snfb_device_alt")
+        return p.value, int(n.value)
 
     def device_candidates(self):
         p = C.c_void_p()

@@ -70,7 +70,7 @@ struct snfb_ctx {
     HostBuf h_leads, h_task_reads, h_task_nm, h_rec_nm, h_cand, h_cand_leads, h_rnames, h_rn_off, h_task_cov, h_alt;
     std::vector<double> task_cov_mean; std::vector<snfb_task> tasks;
     // timings
-    cudaEvent_t ev[MAX_TIMINGS + 1]; const char* ev_name[MAX_TIMINGS + 1]; uint64_t ev_bytes[MAX_TIMINGS + 1]; int n_ev = 0; int n_ev_load = 0;
+    cudaEvent_t ev[MAX_TIMINGS + 1]; const char* ev_name[MAX_TIMINGS + 1]; uint64_t ev_bytes[MAX_TIMINGS + 1]; int n_ev = 0; int n_ev_load = 0; uint64_t launches = 0;
 };
 
 static void ctx_fail(snfb_ctx* ctx, const char* what, const char* msg) { ctx->err = std::string(what) + ": " + msg; }
@@ -179,6 +179,7 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     ctx->loaded = true; return 0;
 }
 
+#define LAUNCHED(ctx, k) ((ctx)->launches += (k))
 static int grid_for(unsigned long long n, int threads) { unsigned long long g = (n + threads - 1) / threads; if (g < 1) g = 1; if (g > 148ull * 64) g = 148ull * 64; return (int)g; }
 
 static int fetch_counters(snfb_ctx* ctx) {
@@ -264,12 +265,12 @@ static int run_stage_a(snfb_ctx* ctx) {
         mark(ctx, "k_extract", sizeof(snfb_rec) * nrec + 4 * ctx->n_cigar + ctx->n_var);
         if (nrec) {
             unsigned long long blocks = (nrec + extract::WARPS - 1) / extract::WARPS; const unsigned long long maxb = 148ull * 8 * 4;
-            extract::k_extract<<<(int)std::min(blocks, maxb), extract::THREADS, 0, ctx->st>>>(P);
+            extract::k_extract<<<(int)std::min(blocks, maxb), extract::THREADS, 0, ctx->st>>>(P); LAUNCHED(ctx, 2);
             mark(ctx, "k_task_nm");
             extract::k_task_nm<<<nt, 256, 0, ctx->st>>>(P.rec_flags, P.rec_nm, P.task_first, P.task_last, ctx->b_task_nm.as<double>());
         }
         mark(ctx, "scan_rec_leads");
-        prims::exclusive_scan(P.rec_nlead, ctx->b_rec_lead_off.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, nrec, nullptr, ctx->st);
+        LAUNCHED(ctx, prims::exclusive_scan(P.rec_nlead, ctx->b_rec_lead_off.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, nrec, nullptr, ctx->st));
         mark(ctx, nullptr);
         CUDA_TRY(cudaGetLastError());
         if (fetch_counters(ctx)) return 1;
@@ -288,11 +289,11 @@ static int run_stage_a(snfb_ctx* ctx) {
         cluster::k_scatter_keys<<<g, 256, 0, ctx->st>>>(b);
         prims::RadixTemp rt{ ctx->b_hist.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>() };
         bool first = true;
-        prims::radix_sort(b.key0, b.val0, b.key1, b.val1, rt, &b.ctr->n_leads, nb, cluster::TASK_SHIFT + bits_for(ctx->n_task), &first, ctx->st);
+        LAUNCHED(ctx, 1 + 3); LAUNCHED(ctx, prims::radix_sort(b.key0, b.val0, b.key1, b.val1, rt, &b.ctr->n_leads, nb, cluster::TASK_SHIFT + bits_for(ctx->n_task), &first, ctx->st));
         ctx->sorted_in_first = first; b = make_b(ctx);
         mark(ctx, "bins");
         cluster::k_bin_heads<<<g, 256, 0, ctx->st>>>(b);
-        prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &b.ctr->n_bins, ctx->st);
+        LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &b.ctr->n_bins, ctx->st));
         cluster::k_bin_build<<<g, 256, 0, ctx->st>>>(b);
         cluster::k_bin_stats<<<g, 256, 0, ctx->st>>>(b);
         mark(ctx, nullptr);
@@ -342,32 +343,32 @@ static int run_stage_b(snfb_ctx* ctx) {
     DevCounters* ctr = b.ctr;
     if (nb) {
         mark(ctx, "kept_bins");
-        prims::exclusive_scan(b.bin_nl, b.kl_off, b.scan_tmp, nullptr, nb, nullptr, ctx->st);
-        prims::exclusive_scan(b.bin_nlong, b.kll_off, b.scan_tmp, nullptr, nb, nullptr, ctx->st);
-        prims::exclusive_scan(b.bin_kept, b.kb_idx, b.scan_tmp, nullptr, nb, &ctr->n_kbins, ctx->st);
+        LAUNCHED(ctx, prims::exclusive_scan(b.bin_nl, b.kl_off, b.scan_tmp, nullptr, nb, nullptr, ctx->st));
+        LAUNCHED(ctx, prims::exclusive_scan(b.bin_nlong, b.kll_off, b.scan_tmp, nullptr, nb, nullptr, ctx->st));
+        LAUNCHED(ctx, prims::exclusive_scan(b.bin_kept, b.kb_idx, b.scan_tmp, nullptr, nb, &ctr->n_kbins, ctx->st));
         cluster::k_kbin_build<<<g, 128, 0, ctx->st>>>(b);
         mark(ctx, "merge_chains");
         cluster::k_seg_heads<<<g, 128, 0, ctx->st>>>(b);
-        prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &ctr->n_segs, ctx->st);
+        LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &ctr->n_segs, ctx->st));
         cluster::k_seg_build<<<g, 128, 0, ctx->st>>>(b);
         cluster::k_merge<<<g, 128, 0, ctx->st>>>(b);
         cluster::k_verify_cuts<<<g, 128, 0, ctx->st>>>(b);
-        prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &ctr->n_clusters, ctx->st);
+        LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &ctr->n_clusters, ctx->st));
         cluster::k_cluster_build<<<g, 128, 0, ctx->st>>>(b);
         mark(ctx, "cluster_post");
         cluster::k_cluster_post<<<g, 128, 0, ctx->st>>>(b);
-        prims::exclusive_scan(b.sub_cnt, b.sub_off, b.scan_tmp, nullptr, nb, &ctr->n_sub, ctx->st);
+        LAUNCHED(ctx, prims::exclusive_scan(b.sub_cnt, b.sub_off, b.scan_tmp, nullptr, nb, &ctr->n_sub, ctx->st));
         cluster::k_sub_build<<<g, 128, 0, ctx->st>>>(b);
         mark(ctx, "call_from");
         cluster::k_call<<<g, 128, 0, ctx->st>>>(b);
-        prims::exclusive_scan(b.cand_valid, b.cand_id, b.scan_tmp, nullptr, nb, &ctr->n_cand, ctx->st);
-        prims::exclusive_scan(b.cand_nlead, b.cand_lead_off, b.scan_tmp, nullptr, nb, &ctr->n_cand_leads, ctx->st);
-        prims::exclusive_scan(b.cand_nrn, b.cand_rn_off, b.scan_tmp, nullptr, nb, &ctr->n_rnames, ctx->st);
+        LAUNCHED(ctx, prims::exclusive_scan(b.cand_valid, b.cand_id, b.scan_tmp, nullptr, nb, &ctr->n_cand, ctx->st));
+        LAUNCHED(ctx, prims::exclusive_scan(b.cand_nlead, b.cand_lead_off, b.scan_tmp, nullptr, nb, &ctr->n_cand_leads, ctx->st));
+        LAUNCHED(ctx, prims::exclusive_scan(b.cand_nrn, b.cand_rn_off, b.scan_tmp, nullptr, nb, &ctr->n_rnames, ctx->st));
         mark(ctx, "cand_finish");
         cluster::k_cand_finish<<<g, 128, 0, ctx->st>>>(b);
         k_copy_ml<<<g, 128, 0, ctx->st>>>(b.subl, b.sub_lo, b.cand_valid, b.cand_lead_off, b.cand_tmp, b.cand_lead_ml, &ctr->n_sub, ctx->cand_lead_cap);
         mark(ctx, "coverage");
-        cluster::k_coverage<<<g, 128, 0, ctx->st>>>(b);
+        cluster::k_coverage<<<g, 128, 0, ctx->st>>>(b); LAUNCHED(ctx, 12);
         mark(ctx, nullptr);
     }
     CUDA_TRY(cudaGetLastError());
@@ -411,9 +412,9 @@ static int run_stage_c(snfb_ctx* ctx) {
     c.plan_best = ctx->b_plan_best.as<uint32_t>(); c.plan_nother = ctx->b_plan_nother.as<uint32_t>(); c.alt_len = ctx->b_alt_len.as<uint32_t>(); c.scr_len = ctx->b_scr_len.as<uint32_t>();
     c.alt_off = ctx->b_alt_off.as<uint32_t>(); c.scr_off = ctx->b_scr_off.as<uint32_t>(); c.cand_cap = ctx->cand_cap; c.ctr = ctx->b_ctr.as<DevCounters>(); c.cfg = ctx->cfg;
     mark(ctx, "consensus_plan");
-    consensus::k_plan<<<grid_for(ctx->cand_cap, 128), 128, 0, ctx->st>>>(c);
-    prims::exclusive_scan(c.alt_len, c.alt_off, ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->cand_cap, &c.ctr->n_alt_bytes, ctx->st);
-    prims::exclusive_scan(c.scr_len, c.scr_off, ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->cand_cap, &c.ctr->n_seq_bytes, ctx->st);
+    consensus::k_plan<<<grid_for(ctx->cand_cap, 128), 128, 0, ctx->st>>>(c); LAUNCHED(ctx, 1);
+    LAUNCHED(ctx, prims::exclusive_scan(c.alt_len, c.alt_off, ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->cand_cap, &c.ctr->n_alt_bytes, ctx->st));
+    LAUNCHED(ctx, prims::exclusive_scan(c.scr_len, c.scr_off, ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->cand_cap, &c.ctr->n_seq_bytes, ctx->st));
     mark(ctx, nullptr);
     if (fetch_counters(ctx)) return 1;
     if (ctx->h_ctr.n_seq_bytes > 0xfffffff0ull) return fail(ctx, "consensus scratch exceeds 64 GiB");
@@ -422,7 +423,7 @@ static int run_stage_c(snfb_ctx* ctx) {
     if (ctx->h_ctr.n_cand) {
         mark(ctx, "consensus", ctx->h_ctr.n_seq_bytes * 16);
         const unsigned long long nblk = std::min<unsigned long long>(ctx->h_ctr.n_cand, 148ull * 16);
-        consensus::k_run<<<(int)nblk, consensus::THREADS, 0, ctx->st>>>(c);
+        consensus::k_run<<<(int)nblk, consensus::THREADS, 0, ctx->st>>>(c); LAUNCHED(ctx, 1);
         mark(ctx, nullptr);
     }
     CUDA_TRY(cudaGetLastError());
@@ -483,6 +484,10 @@ int snfb_last_timings(snfb_ctx* ctx, const char** names, float* ms, uint64_t* by
         float t = 0; if (cudaEventElapsedTime(&t, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) t = -1.f;
         names[n] = ctx->ev_name[i]; ms[n] = t; if (bytes) bytes[n] = ctx->ev_bytes[i]; ++n;
     }
+    if (ctx->n_ev - ctx->n_ev_load >= 2 && n < cap) {   // first stage mark .. last mark: device time of the run including its host round trips
+        float t = 0; if (cudaEventElapsedTime(&t, ctx->ev[ctx->n_ev_load], ctx->ev[ctx->n_ev - 1]) != cudaSuccess) t = -1.f;
+        names[n] = "total"; ms[n] = t; if (bytes) bytes[n] = 0; ++n;
+    }
     return n;
 }
 
@@ -490,5 +495,13 @@ int snfb_device_candidates(snfb_ctx* ctx, void** dptr, uint64_t* n_cand) {
     if (!ctx || !ctx->stage_b_done) return 1;
     if (dptr) *dptr = ctx->b_cand.p; if (n_cand) *n_cand = ctx->h_ctr.n_cand; return 0;
 }
+
+int snfb_device_alt(snfb_ctx* ctx, void** dptr, uint64_t* n_bytes) {
+    if (!ctx || !ctx->stage_b_done) return 1;
+    if (dptr) *dptr = ctx->b_alt.p; if (n_bytes) *n_bytes = ctx->h_ctr.n_alt_bytes; return 0;
+}
+uint64_t snfb_launch_count(snfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int snfb_pin_host(void* p, size_t bytes) { return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1; }
+int snfb_unpin_host(void* p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : 1; }
 
 }  // extern "C"

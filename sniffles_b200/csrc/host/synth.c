@@ -163,7 +163,7 @@ static inline int carries(const snfb_synth_site* st, int read_hap, uint64_t h) {
     return st->hap == 0 || st->hap == read_hap;
 }
 
-static void gen_read(const model_t* m, local_t* L, int c, int64_t idx, int64_t nreads) {
+static void gen_read(const model_t* m, local_t* L, int c, int64_t idx, int64_t nreads, int src) {
     const snfb_synth_params* p = m->p;
     rng_t r = { mix64(p->seed ^ mix64(((uint64_t)(uint32_t)c << 40) ^ (uint64_t)idx)) };
     int64_t clen = p->contig_len[c];
@@ -275,7 +275,7 @@ static void gen_read(const model_t* m, local_t* L, int c, int64_t idx, int64_t n
         S.ins_off = ins0; S.ins_n = ins1 - ins0;
         /* query positions of insertions shift by the leading clip */
         for (uint32_t k = ins0; k < ins1; ++k) ((insrec_t*)L->ins.p)[k].qpos += (int32_t)S.clipL;
-        emit_record(L, &S, NULL, 0, secondary, S.clipL + q + S.clipR, c, idx, read_hap, ps, has_phase, seq_seed, c, order);
+        emit_record(L, &S, NULL, 0, secondary, S.clipL + q + S.clipR, c, idx, read_hap, ps, has_phase, seq_seed, src, order);
         /* drop the scratch ops that were copied: compact by moving the record's ops down */
         grec_t* g = (grec_t*)(L->recs.p + L->recs.n - sizeof(grec_t));
         size_t nbytes = (size_t)g->r.n_cigar * 4;
@@ -301,8 +301,8 @@ static void gen_read(const model_t* m, local_t* L, int c, int64_t idx, int64_t n
         else { B.ins_off = gi; B.ins_n = 1; }
     }
     int a_primary = A.q >= B.q;
-    emit_record(L, &A, &B, !a_primary, secondary, Q, c, idx, read_hap, ps, has_phase, seq_seed, c, order);
-    emit_record(L, &B, &A, a_primary, secondary, Q, c, idx, read_hap, ps, has_phase, mix64(seq_seed ^ 5), c, order | 1);
+    emit_record(L, &A, &B, !a_primary, secondary, Q, c, idx, read_hap, ps, has_phase, seq_seed, src, order);
+    emit_record(L, &B, &A, a_primary, secondary, Q, c, idx, read_hap, ps, has_phase, mix64(seq_seed ^ 5), src, order | 1);
     /* compact: the two emitted records sit after the scratch ops; move them down */
     grec_t* gb = (grec_t*)(L->recs.p + L->recs.n - sizeof(grec_t));
     grec_t* ga = gb - 1;
@@ -401,21 +401,32 @@ snfb_synth_block* snfb_synth_generate(const snfb_synth_params* p) {
     { uint64_t k = 0; for (int c = 0; c <= nc; ++c) { while (k < ns && sites[k].contig < c) ++k; site_first[c] = (int64_t)k; } site_first[nc] = (int64_t)ns; }
     m.sites = sites; m.site_first = site_first;
 
-    /* reads, one local arena per contig */
-    local_t* loc = (local_t*)calloc((size_t)nc, sizeof *loc);
+    /* reads: work units of at most UNIT reads, one local arena each (a read depends only on (seed, contig, index)) */
+    enum { UNIT = 4096 };
+    int64_t* nreads_c = (int64_t*)calloc((size_t)nc + 1, sizeof(int64_t));
+    int64_t nunits = 0;
+    for (int c = 0; c < nc; ++c) {
+        if (p->contig_mask && !p->contig_mask[c]) continue;
+        int64_t nr = (int64_t)(p->coverage * (double)p->contig_len[c] / p->len_mean + 0.5); if (nr < 1) nr = 1;
+        nreads_c[c] = nr; nunits += (nr + UNIT - 1) / UNIT;
+    }
+    int32_t* unit_c = (int32_t*)malloc((size_t)(nunits + 1) * sizeof(int32_t)); int64_t* unit_i0 = (int64_t*)malloc((size_t)(nunits + 1) * sizeof(int64_t));
+    { int64_t u = 0; for (int c = 0; c < nc; ++c) for (int64_t i0 = 0; i0 < nreads_c[c]; i0 += UNIT) { unit_c[u] = c; unit_i0[u] = i0; ++u; } }
+    local_t* loc = (local_t*)calloc((size_t)nunits + 1, sizeof *loc);
 #ifdef _OPENMP
     if (p->threads > 0) omp_set_num_threads(p->threads);
 #endif
 #pragma omp parallel for schedule(dynamic, 1)
-    for (int c = 0; c < nc; ++c) {
-        int64_t nreads = (int64_t)(p->coverage * (double)p->contig_len[c] / p->len_mean + 0.5);
-        if (nreads < 1) nreads = 1;
-        for (int64_t i = 0; i < nreads; ++i) gen_read(&m, &loc[c], c, i, nreads);
+    for (int64_t u = 0; u < nunits; ++u) {
+        const int c = unit_c[u]; const int64_t i0 = unit_i0[u], i1 = i0 + UNIT < nreads_c[c] ? i0 + UNIT : nreads_c[c];
+        for (int64_t i = i0; i < i1; ++i) gen_read(&m, &loc[u], c, i, nreads_c[c], (int)u);
     }
     /* global order */
-    uint64_t nrec = 0; for (int c = 0; c < nc; ++c) nrec += loc[c].recs.n / sizeof(grec_t);
+    uint64_t nrec = 0; for (int64_t c = 0; c < nunits; ++c) nrec += loc[c].recs.n / sizeof(grec_t);
     const grec_t** ord = (const grec_t**)malloc((nrec ? nrec : 1) * sizeof *ord);
-    { uint64_t k = 0; for (int c = 0; c < nc; ++c) { grec_t* g = (grec_t*)loc[c].recs.p; uint64_t n = loc[c].recs.n / sizeof(grec_t); for (uint64_t i = 0; i < n; ++i) ord[k++] = &g[i]; } }
+    { uint64_t k = 0; for (int64_t c = 0; c < nunits; ++c) { grec_t* g = (grec_t*)loc[c].recs.p; uint64_t n = loc[c].recs.n / sizeof(grec_t);
+        for (uint64_t i = 0; i < n; ++i) if (!p->contig_mask || p->contig_mask[g[i].r.task]) ord[k++] = &g[i]; }
+      nrec = k; }
     g_sort_base = ord;
     qsort(ord, nrec, sizeof *ord, cmp_rec);
     /* offsets */
@@ -485,8 +496,8 @@ snfb_synth_block* snfb_synth_generate(const snfb_synth_params* p) {
     R->rec = blk->rec; R->cigar = blk->cigar; R->var = blk->var; R->seq = blk->seq;
     R->n_task = (uint32_t)nc; R->n_contig = (uint32_t)nc; R->n_tr = (uint32_t)(trbuf.n / 8); R->on_device = 0;
     R->task = blk->task; R->contig = blk->contig; R->tr = blk->tr;
-    for (int c = 0; c < nc; ++c) { free(loc[c].recs.p); free(loc[c].cigar.p); free(loc[c].var.p); free(loc[c].ins.p); }
-    free(loc); free(ord); free(coff); free(voff); free(soff); free(site_first); free(tr_first); free(trbuf.p);
+    for (int64_t c = 0; c < nunits; ++c) { free(loc[c].recs.p); free(loc[c].cigar.p); free(loc[c].var.p); free(loc[c].ins.p); }
+    free(loc); free(nreads_c); free(unit_c); free(unit_i0); free(ord); free(coff); free(voff); free(soff); free(site_first); free(tr_first); free(trbuf.p);
     return blk;
 }
 

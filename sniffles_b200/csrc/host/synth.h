@@ -41,6 +41,7 @@ typedef struct snfb_synth_params {
     int32_t  sv_max;
     int32_t  threads;          /* 0 = omp default */
     int32_t  _pad;
+    const uint8_t* contig_mask; /* NULL = all; otherwise only contigs with mask[c] != 0 get reads and keep records (rank sharding) */
 } snfb_synth_params;
 
 typedef struct snfb_synth_site {

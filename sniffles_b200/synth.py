@@ -24,7 +24,8 @@ class _Params(C.Structure):
                 ("lowmapq_prob", C.c_double), ("secondary_prob", C.c_double), ("sv_spacing", C.c_double),
                 ("phased_frac", C.c_double), ("tr_frac", C.c_double), ("ins_noise", C.c_double),
                 ("mosaic", C.c_int32), ("with_seq", C.c_int32), ("ins_only", C.c_int32),
-                ("sv_min", C.c_int32), ("sv_max", C.c_int32), ("threads", C.c_int32), ("_pad", C.c_int32)]
+                ("sv_min", C.c_int32), ("sv_max", C.c_int32), ("threads", C.c_int32), ("_pad", C.c_int32),
+                ("contig_mask", C.POINTER(C.c_uint8))]
 
 
 SITE_DTYPE = np.dtype([("contig", "<i4"), ("pos", "<i4"), ("svtype", "<i4"), ("size", "<i4"),
@@ -94,7 +95,7 @@ class _Owner:
 def generate(seed: int, contig_len, coverage: float, *, len_model=0, len_mean=15000.0, len_sd=0.6 * 1000,
              len_min=1000, len_max=200000, tech="ont", clip_prob=0.10, lowmapq_prob=0.05,
              secondary_prob=0.02, sv_spacing=120000.0, phased_frac=0.5, tr_frac=0.15, ins_noise=0.03,
-             mosaic=False, with_seq=True, ins_only=False, sv_min=50, sv_max=5000, threads=0) -> RecordBlock:
+             mosaic=False, with_seq=True, ins_only=False, sv_min=50, sv_max=5000, threads=0, contig_mask=None) -> RecordBlock:
     lib = host_lib()
     lens = (C.c_int32 * len(contig_len))(*[int(x) for x in contig_len])
     p = _Params()
@@ -105,6 +106,10 @@ def generate(seed: int, contig_len, coverage: float, *, len_model=0, len_mean=15
     p.sv_spacing, p.phased_frac, p.tr_frac, p.ins_noise = sv_spacing, phased_frac, tr_frac, ins_noise
     p.mosaic, p.with_seq, p.ins_only = int(mosaic), int(with_seq), int(ins_only)
     p.sv_min, p.sv_max, p.threads = int(sv_min), int(sv_max), int(threads)
+    mask = None
+    if contig_mask is not None:
+        mask = (C.c_uint8 * len(contig_len))(*[1 if m else 0 for m in contig_mask])
+        p.contig_mask = C.cast(mask, C.POINTER(C.c_uint8))
     h = lib.snfb_synth_generate(C.byref(p))
     if not h:
         raise MemoryError("snfb_synth_generate failed")
@@ -122,18 +127,18 @@ def generate(seed: int, contig_len, coverage: float, *, len_model=0, len_mean=15
 
 
 # ---- the BASELINE.json configurations; `scale` shrinks contig lengths ----
-def config_block(index: int, scale: float = 1.0, threads: int = 0, with_seq: bool = True) -> RecordBlock:
+def config_block(index: int, scale: float = 1.0, threads: int = 0, with_seq: bool = True, contig_mask=None) -> RecordBlock:
     seed = 1000 + index
     if index == 1:      # 1 Mb contig, ~200 ONT reads of ~100 kb @20x
         return generate(seed, [int(1_000_000 * scale)], 20.0, len_model=0, len_mean=100000.0, len_sd=10000.0,
                         len_min=1000, len_max=200000, tech="ont", sv_spacing=25000.0, threads=threads, with_seq=with_seq)
     if index == 2:      # 30x ONT WGS, lognormal 15 kb
         return generate(seed, [max(200000, int(x * scale)) for x in GRCH38], 30.0, len_model=1, len_mean=15000.0,
-                        len_sd=600.0, len_min=1000, len_max=200000, tech="ont", threads=threads, with_seq=with_seq)
+                        len_sd=600.0, len_min=1000, len_max=200000, tech="ont", threads=threads, with_seq=with_seq, contig_mask=contig_mask)
     if index == 3:      # 60x HiFi WGS, mosaic
         return generate(seed, [max(200000, int(x * scale)) for x in GRCH38], 60.0, len_model=0, len_mean=18000.0,
                         len_sd=3000.0, len_min=1000, len_max=60000, tech="hifi", mosaic=True, threads=threads,
-                        with_seq=with_seq)
+                        with_seq=with_seq, contig_mask=contig_mask)
     if index == 5:      # INS-heavy: 5 Mb region, 5000 sites x 20 reads
         return generate(seed, [int(5_000_000 * scale)], 20.0, len_model=0, len_mean=20000.0, len_sd=2000.0,
                         len_min=5000, len_max=60000, tech="ont", sv_spacing=1000.0, ins_only=True, tr_frac=0.0,
