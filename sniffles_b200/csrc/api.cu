@@ -51,7 +51,7 @@ struct snfb_ctx {
     const snfb_rec* d_rec = nullptr; const uint32_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
     DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp;
     // stage A outputs
-    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm;
+    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt;
     unsigned long long lead_cap = 0;
     DevCounters h_ctr{};
     // stage B
@@ -114,7 +114,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_ctr, &ctx->b_leads, &ctx->b_rec_pos, &ctx->b_rec_end,
-        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm,
+        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt,
         &ctx->b_key0, &ctx->b_val0, &ctx->b_key1, &ctx->b_val1, &ctx->b_flag, &ctx->b_scan, &ctx->b_hist, &ctx->b_scan_tmp, &ctx->b_bin_start, &ctx->b_bin_nl, &ctx->b_bin_nlong, &ctx->b_bin_kept,
         &ctx->b_bin_hap, &ctx->b_kl_off, &ctx->b_kll_off, &ctx->b_kb_idx, &ctx->b_kl, &ctx->b_kll, &ctx->b_kb_bin, &ctx->b_kb_lead_off, &ctx->b_kb_lead_n, &ctx->b_kb_long_off, &ctx->b_kb_long_n,
         &ctx->b_kb_seed, &ctx->b_kb_chain, &ctx->b_kb_repeat, &ctx->b_seg_start, &ctx->b_c_next, &ctx->b_c_last, &ctx->b_c_sd, &ctx->b_c_mean, &ctx->b_c_rep, &ctx->b_seg_sd_last, &ctx->b_seg_maxsd,
@@ -267,7 +267,10 @@ static int run_stage_a(snfb_ctx* ctx) {
             unsigned long long blocks = (nrec + extract::WARPS - 1) / extract::WARPS; const unsigned long long maxb = 148ull * 8 * 4;
             extract::k_extract<<<(int)std::min(blocks, maxb), extract::THREADS, 0, ctx->st>>>(P); LAUNCHED(ctx, 2);
             mark(ctx, "k_task_nm");
-            extract::k_task_nm<<<nt, 256, 0, ctx->st>>>(P.rec_flags, P.rec_nm, P.task_first, P.task_last, ctx->b_task_nm.as<double>());
+            const int cpt = (int)((nrec + extract::NM_CHUNK - 1) / extract::NM_CHUNK);
+            if (ctx->b_nm_part.ensure(8 * (size_t)cpt * nt + 8) || ctx->b_nm_cnt.ensure(4 * (size_t)cpt * nt + 8)) return fail(ctx, "out of device memory (nm partials)");
+            extract::k_nm_partial<<<dim3(cpt, nt), 256, 0, ctx->st>>>(P.rec_flags, P.rec_nm, P.task_first, P.task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>());
+            extract::k_task_nm<<<nt, 256, 0, ctx->st>>>(P.task_first, P.task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>(), cpt, ctx->b_task_nm.as<double>()); LAUNCHED(ctx, 1);
         }
         mark(ctx, "scan_rec_leads");
         LAUNCHED(ctx, prims::exclusive_scan(P.rec_nlead, ctx->b_rec_lead_off.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, nrec, nullptr, ctx->st));

@@ -465,21 +465,29 @@ __global__ void k_call(B b) {
     }
 }
 
-// coverage restricted by haplotype at one position: reads with start <= p < end (leadprov.py:510)
-__device__ inline void cover_count(const B& b, int t, long long p, uint32_t out[3]) {
+// coverage restricted by haplotype at one position: reads with start <= p < end (leadprov.py:510).
+// Warp-cooperative: records are coordinate sorted, so the covering reads start inside
+// (p - longest reference span, p]; the lanes split that window.
+__device__ inline void cover_count_warp(const B& b, int t, long long p, uint32_t out[3]) {
     out[0] = out[1] = out[2] = 0;
     const uint32_t lo = b.task_first[t], hi = b.task_last[t];
     if (lo >= hi) return;
     uint32_t a = lo, z = hi;                     // first record with pos > p
     while (a < z) { uint32_t mid = a + ((z - a) >> 1); if ((long long)b.rec_pos[mid] <= p) a = mid + 1; else z = mid; }
     const long long span = b.task_maxspan[t];
-    for (uint32_t i = a; i > lo;) { --i; const long long ps = b.rec_pos[i]; if (ps + span <= p) break; const uint8_t f = b.rec_flags[i]; if ((f & extract::RF_PASS) && (long long)b.rec_end[i] > p) out[(f >> 2) & 3]++; }
+    uint32_t c0 = 0, c1 = 0, c2 = 0;
+    for (long long i = (long long)a - 1 - lane_id(); i >= (long long)lo; i -= 32) {
+        const long long ps = b.rec_pos[i]; if (ps + span <= p) break;
+        const uint8_t f = b.rec_flags[i];
+        if ((f & extract::RF_PASS) && (long long)b.rec_end[i] > p) { const int h = (f >> 2) & 3; c0 += h == 0; c1 += h == 1; c2 += h == 2; }
+    }
+    out[0] = __reduce_add_sync(FULL, c0); out[1] = __reduce_add_sync(FULL, c1); out[2] = __reduce_add_sync(FULL, c2);
 }
-__device__ inline bool cov_at(const B& b, int t, long long idx, int* out) {     // numpy indexing of the uint16 coverage vector
+__device__ inline void cov_at_warp(const B& b, int t, long long idx, int* out) {     // numpy indexing of the uint16 coverage vector
     const long long L = b.task[t].contig_len;
     if (idx < 0) idx += L;
-    if (idx < 0 || idx >= L) return false;
-    uint32_t c[3]; cover_count(b, t, idx, c); *out = (int)((c[0] + c[1] + c[2]) & 0xffffu); return true;
+    if (idx < 0 || idx >= L) return;             // IndexError: the field keeps its default 0
+    uint32_t c[3]; cover_count_warp(b, t, idx, c); *out = (int)((c[0] + c[1] + c[2]) & 0xffffu);
 }
 
 // final candidate records in reference order + their leads, read names, phase aggregates, coverage
@@ -543,27 +551,33 @@ __global__ void k_cand_finish(B b) {
                 if (gt) { bc = cnt; bv = w2[i]; have = true; } i = j; }
             cd.ps_top_null = bv == 0xffffffffffffffffull; cd.ps_top = cd.ps_top_null ? 0 : (int)unbias64(bv); cd.ps_support = (int)bc; cd.ps_other = (int)(nonnull - (cd.ps_top_null ? 0 : bc));
         }
-        // hap-REF counts of the cluster's first bin (cluster.py:255-260): coverage by haplotype at the bin's last base
-        { uint32_t hr[3]; const int bs = b.cfg.cluster_binsize; cover_count(b, cd.task, (long long)(cd.cluster_seed / bs) * bs + bs - 1, hr); for (int h = 0; h < 3; ++h) cd.hap_counts[3 + h] = (int)(hr[h] > 65535u ? 65535u : hr[h]); }
         b.cand[id] = cd;
     }
 }
-// postprocessing.coverage (postprocessing.py:69-130) including the `end` that leaks from the previous call
+// postprocessing.coverage (postprocessing.py:69-130) including the `end` that leaks from the previous call,
+// plus the hap-REF counts of the cluster's first bin (cluster.py:255-260).  One warp per candidate.
 __global__ void k_coverage(B b) {
     const unsigned long long nc = b.ctr->n_cand < b.cand_cap ? b.ctr->n_cand : b.cand_cap;
     const long long bs = b.cfg.coverage_binsize, ud = (long long)b.cfg.coverage_binsize * b.cfg.coverage_updown_bins;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nc; i += (unsigned long long)gridDim.x * blockDim.x) {
-        snfb_cand* c = &b.cand[i]; long long start = c->pos, end; const int t = c->task;
-        if (c->svtype == SNFB_INS) end = start + 1;
-        else if (c->svtype == SNFB_BND) {
+    const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long i = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nc; i += nw) {
+        snfb_cand* c = &b.cand[i]; long long start = c->pos, end; const int t = c->task; const int svtype = c->svtype;
+        if (svtype == SNFB_INS) end = start + 1;
+        else if (svtype == SNFB_BND) {
             if (c->bnd_is_first) start -= 1;
             long long j = (long long)i - 1; while (j >= 0 && b.cand[j].task == t && b.cand[j].svtype == SNFB_BND) --j;
             if (j >= 0 && b.cand[j].task == t) { const snfb_cand* p = &b.cand[j]; end = p->svtype == SNFB_INS ? (long long)p->pos + 1 : (long long)p->pos + (p->svlen < 0 ? -(long long)p->svlen : p->svlen); }
-            else { end = start; atomicAdd(&b.ctr->soft_errors, 1ULL); }
+            else { end = start; if (lane_id() == 0) atomicAdd(&b.ctr->soft_errors, 1ULL); }
         } else end = (long long)c->pos + (c->svlen < 0 ? -(long long)c->svlen : c->svlen);
-        if (c->svtype == SNFB_INS || c->svtype == SNFB_BND) { cov_at(b, t, start - bs, &c->cov_start); cov_at(b, t, start, &c->cov_center); cov_at(b, t, end + bs, &c->cov_end); }
-        else { cov_at(b, t, start, &c->cov_start); cov_at(b, t, (long long)__ddiv_rn((double)(start + end), 2.0), &c->cov_center); cov_at(b, t, end - bs, &c->cov_end); }
-        cov_at(b, t, start - ud, &c->cov_upstream); cov_at(b, t, end + ud, &c->cov_downstream);
+        int v[5] = { 0, 0, 0, 0, 0 };          // upstream, start, center, end, downstream
+        if (svtype == SNFB_INS || svtype == SNFB_BND) { cov_at_warp(b, t, start - bs, &v[1]); cov_at_warp(b, t, start, &v[2]); cov_at_warp(b, t, end + bs, &v[3]); }
+        else { cov_at_warp(b, t, start, &v[1]); cov_at_warp(b, t, (long long)__ddiv_rn((double)(start + end), 2.0), &v[2]); cov_at_warp(b, t, end - bs, &v[3]); }
+        cov_at_warp(b, t, start - ud, &v[0]); cov_at_warp(b, t, end + ud, &v[4]);
+        uint32_t hr[3]; const int cb = b.cfg.cluster_binsize; cover_count_warp(b, t, (long long)(c->cluster_seed / cb) * cb + cb - 1, hr);
+        if (lane_id() == 0) {
+            c->cov_upstream = v[0]; c->cov_start = v[1]; c->cov_center = v[2]; c->cov_end = v[3]; c->cov_downstream = v[4];
+            for (int h = 0; h < 3; ++h) c->hap_counts[3 + h] = (int)(hr[h] > 65535u ? 65535u : hr[h]);
+        }
     }
 }
 

@@ -137,7 +137,111 @@ __device__ inline int classify_splits_dev(const snfb_config& cfg, Seg* s, int n,
     return n;
 }
 
-__global__ void __launch_bounds__(THREADS) k_extract(const Params P) {
+// ---- supplementary alignments (SA tag) of one record: Lead.for_bnd + read_itersplits, run by lane 0 ----
+struct SaArgs { uint32_t rec; int qas, qae, alen, ref_end, hp; uint32_t base_flags; uint64_t qh; unsigned nlead; bool rev, is_supp; };
+__device__ __noinline__ unsigned process_sa(const Params& P, const snfb_rec& r, const snfb_task& tk, const uint32_t* __restrict__ cg, Seg* sg, const SaArgs a,
+                                            unsigned long long* soft_p, unsigned long long* overflow_p) {
+    const snfb_config& cfg = P.cfg;
+    const int n = (int)r.n_cigar; const uint32_t rec = a.rec; const bool rev = a.rev;
+    unsigned long long soft = 0, overflow = 0; unsigned added = 0;
+    const uint8_t* sa = P.var + r.var_off + r.l_qname; const int sl = (int)r.sa_len;
+    // pass 1: count the non-empty entries and locate the first one
+    int ne = 0, f_off = 0, f_len = 0;
+    for (int i = 0, st = 0; i <= sl; ++i) if (i == sl || sa[i] == ';') { if (i > st) { if (ne == 0) { f_off = st; f_len = i - st; } ++ne; } st = i + 1; }
+    bool sa_ok = true; SaEntry e0;
+    if (ne > 0 && !sa_fields_dev(sa + f_off, f_len, &e0)) { sa_ok = false; ++soft; }
+    if (ne > 0 && sa_ok) {                                   // Lead.for_bnd: first entry only
+        const uint8_t* e = sa + f_off;
+        int left = 0, right = 0;
+        { uint32_t c = cg[0]; int op = c & 15; if (op == 4 || op == 5) left = (int)(c >> 4); }
+        { uint32_t c = cg[n - 1]; int op = c & 15; if (op == 4 || op == 5) right = (int)(c >> 4); }
+        int bstart; bool is_first;
+        if (left > right) { bstart = r.pos + 1; is_first = false; } else { bstart = a.ref_end; is_first = true; }
+        const bool same = e0.len[2] == 1 && ((e[e0.off[2]] == '-' && rev) || (e[e0.off[2]] == '+' && !rev));
+        if (!same) {
+            long long p1, cs, ce, rs, qs, sanm = 0;
+            if (!parse_int_dev(e + e0.off[1], e0.len[1], &p1)) ++soft;
+            else if (!cigar_analyze_dev(e + e0.off[3], e0.len[3], &cs, &ce, &rs, &qs)) ++soft;
+            else if ((r.aux_flags & SNFB_AUX_NM) && !parse_int_dev(e + e0.off[5], e0.len[5], &sanm)) ++soft;
+            else {
+                const long long p0 = p1 - 1; const bool is_reverse = ce > cs;
+                const long long mate = is_reverse ? p0 + rs : (is_first ? p0 + 1 : p0 + 2);
+                if (bstart >= tk.start && bstart < tk.end) {
+                    snfb_lead L;
+                    L.rec = rec; L.qname_hash = a.qh; L.read_len = 0; L.seq_off = -1; L.seq_len = 0;
+                    L.ref_start = L.ref_end = bstart; L.qry_start = a.qas; L.qry_end = a.qae; L.svlen = 0;
+                    L.mate_pos = (int)mate; L.mate_contig = contig_lookup_dev(P.contig, P.n_contig, e + e0.off[0], e0.len[0]);
+                    if (L.mate_contig < 0) ++soft;
+                    L.nm_sa = (int)sanm; L.task = (uint16_t)r.task; L.k = (uint16_t)(a.nlead + added);
+                    L.flags = a.base_flags | SNFB_BND | ((uint32_t)SNFB_SRC_BND_SA << 3) | (is_first ? SNFB_LF_BND_FIRST : 0u) | (is_reverse ? SNFB_LF_BND_REVERSE : 0u)
+                              | ((r.aux_flags & SNFB_AUX_NM) ? 0u : SNFB_LF_NM_NONE);
+                    const unsigned long long slot = atomicAdd(&P.ctr->n_leads, 1ULL);
+                    if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
+                    ++added;
+                }
+            }
+        }
+    }
+    // read_itersplits: primary alignments only
+    if (!a.is_supp && sa_ok && ne > 0) {
+        const double lim = __dadd_rn((double)cfg.max_splits_base, __dmul_rn(cfg.max_splits_kb, __ddiv_rn((double)r.l_seq, 1000.0)));
+        if (!((double)ne > lim)) {
+            if (ne + 1 > MAXSEG) ++soft;
+            else {
+                bool ok = true;
+                sg[0].contig = tk.contig; sg[0].ref_start = r.pos; sg[0].ref_end = a.ref_end;
+                sg[0].qry_start = rev ? r.l_seq - a.qae : a.qas; sg[0].qry_end = sg[0].qry_start + a.alen;
+                sg[0].meta = (rev ? 1 : 0) | ((int)r.mapq << 8) | (SNFB_SRC_SPLIT_PRIM << 16); sg[0].nhint = 0;
+                int ei = 0;
+                for (int i = 0, st = 0; i <= sl && ok; ++i) if (i == sl || sa[i] == ';') {
+                    if (i > st) {
+                        SaEntry en; const uint8_t* e = sa + st; long long p1, cs, ce, rs, qs, mq;
+                        if (!sa_fields_dev(e, i - st, &en) || !parse_int_dev(e + en.off[4], en.len[4], &mq)) { ok = false; ++soft; break; }
+                        const bool srev = en.len[2] == 1 && e[en.off[2]] == '-';
+                        if (!cigar_analyze_dev(e + en.off[3], en.len[3], &cs, &ce, &rs, &qs)) { ok = false; ++soft; break; }
+                        if (!parse_int_dev(e + en.off[1], en.len[1], &p1)) { ok = false; ++soft; break; }
+                        Seg* g = &sg[++ei];
+                        g->contig = contig_lookup_dev(P.contig, P.n_contig, e + en.off[0], en.len[0]); if (g->contig < 0) { g->contig = -2 - ei; ++soft; }
+                        g->ref_start = (int)(p1 - 1); g->ref_end = (int)(p1 - 1 + rs); g->qry_start = (int)(srev ? ce : cs); g->qry_end = g->qry_start + (int)qs;
+                        g->meta = (srev ? 1 : 0) | ((int)mq << 8) | (SNFB_SRC_SPLIT_SUP << 16); g->nhint = 0;
+                    }
+                    st = i + 1;
+                }
+                if (ok) {
+                    const int m = classify_splits_dev(cfg, sg, ne + 1, r.l_seq);
+                    for (int i = 0; i < m; ++i) for (int h = 0; h < sg[i].nhint; ++h) {
+                        const int mqc = (sg[i].meta >> 8) & 255, mqp = (sg[i > 0 ? i - 1 : 0].meta >> 8) & 255;
+                        if (!cfg.dev_keep_lowqual_splits && (mqc < mqp ? mqc : mqp) < cfg.mapq) continue;
+                        const int ty = sg[i].h_type[h]; const int hs = sg[i].h_start[h];
+                        if (sg[i].contig != tk.contig || hs < tk.start || hs >= tk.end) continue;
+                        snfb_lead L;
+                        L.rec = rec; L.qname_hash = a.qh; L.read_len = 0; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
+                        L.ref_start = hs; L.ref_end = (!sg[i].h_none[h] && ty != SNFB_INS) ? hs + sg[i].h_len[h] : hs;
+                        L.qry_start = sg[i].qry_start; L.qry_end = sg[i].qry_end; L.svlen = sg[i].h_len[h];
+                        uint32_t f = (uint32_t)ty | ((uint32_t)((sg[i].meta >> 16) & 3) << 3) | ((sg[i].meta & 1) ? SNFB_LF_REVERSE : 0u) | ((uint32_t)mqc << 16) | ((uint32_t)a.hp << 24);
+                        if (sg[i].h_none[h]) f |= SNFB_LF_SVLEN_NONE;
+                        if (ty == SNFB_INS && (sg[i].meta & (1 << 20))) { f |= SNFB_LF_HAS_SEQ; L.seq_off = sg[i].seq_off; L.seq_len = sg[i].seq_len; }
+                        L.flags = f; L.task = (uint16_t)r.task; L.k = (uint16_t)(a.nlead + added);
+                        const unsigned long long slot = atomicAdd(&P.ctr->n_leads, 1ULL);
+                        if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
+                        ++added;
+                    }
+                }
+            }
+        }
+    }
+    *soft_p += soft; *overflow_p += overflow;
+    return added;
+}
+
+// one 16-byte slice of a record's CIGAR (4 ops) for this lane; zero outside the record
+__device__ __forceinline__ uint4 load_chunk(const uint32_t* __restrict__ cigar, long long c, int lane, long long c_begin, long long c_end) {
+    const long long i0 = c + lane * 4;
+    if (i0 < c_end && i0 + 3 >= c_begin) return __ldg(reinterpret_cast<const uint4*>(cigar + i0));
+    return make_uint4(0, 0, 0, 0);
+}
+
+__global__ void __launch_bounds__(THREADS, 3) k_extract(const Params P) {
     __shared__ Seg segs[WARPS][MAXSEG];
     const snfb_config& cfg = P.cfg;
     const int lane = lane_id(), wib = threadIdx.x >> 5;
@@ -145,12 +249,30 @@ __global__ void __launch_bounds__(THREADS) k_extract(const Params P) {
     // per-warp accumulators flushed when the task changes (records are grouped by task)
     int acc_task = -1; unsigned acc_reads = 0; unsigned long long acc_bp = 0; int acc_span = 0;
     unsigned long long soft = 0, overflow = 0, unsorted = 0;
+    snfb_task tk; int tk_id = -1;
+    tk.contig = tk.start = tk.end = tk.contig_len = 0;
 
-    for (unsigned rec = blockIdx.x * WARPS + wib; rec < P.n_rec; rec += nwarps) {
-        const snfb_rec r = P.rec[rec];
-        const snfb_task tk = P.task[r.task];
+    unsigned rec = blockIdx.x * WARPS + wib;
+    // software pipeline over records: the next record's 64-byte core is in flight while this one is processed
+    uint32_t wnext = (rec < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + rec) + lane) : 0u;
+    for (; rec < P.n_rec; rec += nwarps) {
+        const uint32_t wcur = wnext;
+        { const unsigned nrec2 = rec + nwarps; wnext = (nrec2 < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + nrec2) + lane) : 0u; }
+        snfb_rec r;
+        r.task = (int)__shfl_sync(FULL, wcur, 0); r.pos = (int)__shfl_sync(FULL, wcur, 1);
+        { const uint32_t x = __shfl_sync(FULL, wcur, 2); r.flag = (uint16_t)x; r.mapq = (uint8_t)(x >> 16); r.aux_flags = (uint8_t)(x >> 24); }
+        { const uint32_t x = __shfl_sync(FULL, wcur, 3); r.hp = (uint8_t)x; r.l_qname = (uint8_t)(x >> 8); }
+        r.nm = (int)__shfl_sync(FULL, wcur, 4); r.ps = (int)__shfl_sync(FULL, wcur, 5); r.n_cigar = __shfl_sync(FULL, wcur, 6); r.l_seq = (int)__shfl_sync(FULL, wcur, 7);
+        r.sa_len = __shfl_sync(FULL, wcur, 8);
+        r.cigar_off = (uint64_t)__shfl_sync(FULL, wcur, 10) | ((uint64_t)__shfl_sync(FULL, wcur, 11) << 32);
+        r.var_off = (uint64_t)__shfl_sync(FULL, wcur, 14) | ((uint64_t)__shfl_sync(FULL, wcur, 15) << 32);
+        r.seq_off = 0;
         const uint32_t* __restrict__ cg = P.cigar + r.cigar_off;
         const int n = (int)r.n_cigar;
+        const long long c_begin = (long long)r.cigar_off, c_end = c_begin + n; const long long c0 = c_begin & ~3LL;
+        // issue the first CIGAR slices before anything that depends on them
+        uint4 v0 = load_chunk(P.cigar, c0, lane, c_begin, c_end), v1 = load_chunk(P.cigar, c0 + 128, lane, c_begin, c_end), v2 = load_chunk(P.cigar, c0 + 256, lane, c_begin, c_end);
+        if (r.task != tk_id) { tk = P.task[r.task]; tk_id = r.task; }
         if (lane == 0) {
             P.rec_pos[rec] = r.pos;
             if (rec == 0 || P.rec[rec - 1].task != r.task) P.task_first[r.task] = rec;
@@ -159,8 +281,8 @@ __global__ void __launch_bounds__(THREADS) k_extract(const Params P) {
         }
         // pysam query_alignment_start / _end
         int qas = 0, qae = r.l_seq;
-        for (int k = 0; k < n; ++k) { uint32_t c = cg[k]; int op = c & 15; if (op == 4) qas += (int)(c >> 4); else if (op != 5) break; }
-        for (int k = n - 1; k >= 1; --k) { uint32_t c = cg[k]; int op = c & 15; if (op == 4) qae -= (int)(c >> 4); else if (op != 5) break; }
+        for (int k = 0; k < n; ++k) { uint32_t c = __ldg(cg + k); int op = c & 15; if (op == 4) qas += (int)(c >> 4); else if (op != 5) break; }
+        for (int k = n - 1; k >= 1; --k) { uint32_t c = __ldg(cg + k); int op = c & 15; if (op == 4) qae -= (int)(c >> 4); else if (op != 5) break; }
         const int alen = qae - qas;
         bool pass = !(r.mapq < cfg.mapq || (r.flag & 256) || alen < cfg.min_alignment_length);
         if (cfg.exclude_flags && (r.flag & cfg.exclude_flags)) pass = false;
@@ -179,13 +301,11 @@ __global__ void __launch_bounds__(THREADS) k_extract(const Params P) {
         uint64_t qh = 0; bool have_qh = false;
         unsigned nlead = 0;
 
-        // ---- CIGAR stream: 4 ops per lane per iteration ----
+        // ---- CIGAR stream: 4 ops per lane per iteration, two further slices in flight ----
         unsigned pos_q = 0; int pos_r = r.pos; unsigned big = 0;
-        const long long c_begin = (long long)r.cigar_off, c_end = c_begin + n;
-        for (long long c0 = c_begin & ~3LL; c0 < c_end; c0 += 128) {
-            const long long i0 = c0 + lane * 4;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (i0 < c_end && i0 + 3 >= c_begin) v = *reinterpret_cast<const uint4*>(P.cigar + i0);
+        for (long long c = c0; c < c_end; c += 128) {
+            const uint4 v = v0; v0 = v1; v1 = v2; v2 = load_chunk(P.cigar, c + 384, lane, c_begin, c_end);
+            const long long i0 = c + lane * 4;
             uint32_t w[4] = { v.x, v.y, v.z, v.w };
             unsigned lq = 0, lr = 0; unsigned eq[4], er[4]; bool ev[4]; bool anyev = false;
             #pragma unroll
@@ -252,99 +372,12 @@ __global__ void __launch_bounds__(THREADS) k_extract(const Params P) {
         if ((cfg.qc_nm_measure || cfg.phase) && (r.aux_flags & SNFB_AUX_NM)) {      // leadprov.py:517-526
             nm = __ddiv_rn((double)((long long)r.nm - (long long)big), (double)(alen + 1)); has_nm = true;
         }
-
-        // ---- supplementary alignments (SA tag): lane-serial ----
         if (has_sa) {
             if (!have_qh) { qh = qname_hash_warp(P.var + r.var_off, r.l_qname); have_qh = true; }
             unsigned added = 0;
             if (lane == 0) {
-                const uint8_t* sa = P.var + r.var_off + r.l_qname; const int sl = (int)r.sa_len;
-                Seg* sg = segs[wib];
-                // pass 1: count the non-empty entries and locate the first one
-                int ne = 0, f_off = 0, f_len = 0;
-                for (int i = 0, st = 0; i <= sl; ++i) if (i == sl || sa[i] == ';') { if (i > st) { if (ne == 0) { f_off = st; f_len = i - st; } ++ne; } st = i + 1; }
-                bool sa_ok = true; SaEntry e0;
-                if (ne > 0 && !sa_fields_dev(sa + f_off, f_len, &e0)) { sa_ok = false; ++soft; }
-                if (ne > 0 && sa_ok) {                                   // Lead.for_bnd: first entry only
-                    const uint8_t* e = sa + f_off;
-                    int left = 0, right = 0;
-                    { uint32_t c = cg[0]; int op = c & 15; if (op == 4 || op == 5) left = (int)(c >> 4); }
-                    { uint32_t c = cg[n - 1]; int op = c & 15; if (op == 4 || op == 5) right = (int)(c >> 4); }
-                    int bstart; bool is_first;
-                    if (left > right) { bstart = r.pos + 1; is_first = false; } else { bstart = ref_end; is_first = true; }
-                    const bool same = e0.len[2] == 1 && ((e[e0.off[2]] == '-' && rev) || (e[e0.off[2]] == '+' && !rev));
-                    if (!same) {
-                        long long p1, cs, ce, rs, qs, sanm = 0;
-                        if (!parse_int_dev(e + e0.off[1], e0.len[1], &p1)) ++soft;
-                        else if (!cigar_analyze_dev(e + e0.off[3], e0.len[3], &cs, &ce, &rs, &qs)) ++soft;
-                        else if ((r.aux_flags & SNFB_AUX_NM) && !parse_int_dev(e + e0.off[5], e0.len[5], &sanm)) ++soft;
-                        else {
-                            const long long p0 = p1 - 1; const bool is_reverse = ce > cs;
-                            const long long mate = is_reverse ? p0 + rs : (is_first ? p0 + 1 : p0 + 2);
-                            if (bstart >= tk.start && bstart < tk.end) {
-                                snfb_lead L;
-                                L.rec = rec; L.qname_hash = qh; L.read_len = 0; L.seq_off = -1; L.seq_len = 0;
-                                L.ref_start = L.ref_end = bstart; L.qry_start = qas; L.qry_end = qae; L.svlen = 0;
-                                L.mate_pos = (int)mate; L.mate_contig = contig_lookup_dev(P.contig, P.n_contig, e + e0.off[0], e0.len[0]);
-                                if (L.mate_contig < 0) ++soft;
-                                L.nm_sa = (int)sanm; L.task = (uint16_t)r.task; L.k = (uint16_t)(nlead + added);
-                                L.flags = base_flags | SNFB_BND | ((uint32_t)SNFB_SRC_BND_SA << 3) | (is_first ? SNFB_LF_BND_FIRST : 0u) | (is_reverse ? SNFB_LF_BND_REVERSE : 0u)
-                                          | ((r.aux_flags & SNFB_AUX_NM) ? 0u : (1u << 11));   // bit 11: nm is None
-                                const unsigned long long slot = atomicAdd(&P.ctr->n_leads, 1ULL);
-                                if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
-                                ++added;
-                            }
-                        }
-                    }
-                }
-                // read_itersplits: primary alignments only
-                if (!is_supp && sa_ok && ne > 0) {
-                    const double lim = __dadd_rn((double)cfg.max_splits_base, __dmul_rn(cfg.max_splits_kb, __ddiv_rn((double)r.l_seq, 1000.0)));
-                    if (!((double)ne > lim)) {
-                        if (ne + 1 > MAXSEG) ++soft;
-                        else {
-                            bool ok = true;
-                            sg[0].contig = tk.contig; sg[0].ref_start = r.pos; sg[0].ref_end = ref_end;
-                            sg[0].qry_start = rev ? r.l_seq - qae : qas; sg[0].qry_end = sg[0].qry_start + alen;
-                            sg[0].meta = (rev ? 1 : 0) | ((int)r.mapq << 8) | (SNFB_SRC_SPLIT_PRIM << 16); sg[0].nhint = 0;
-                            int ei = 0;
-                            for (int i = 0, st = 0; i <= sl && ok; ++i) if (i == sl || sa[i] == ';') {
-                                if (i > st) {
-                                    SaEntry en; const uint8_t* e = sa + st; long long p1, cs, ce, rs, qs, mq;
-                                    if (!sa_fields_dev(e, i - st, &en) || !parse_int_dev(e + en.off[4], en.len[4], &mq)) { ok = false; ++soft; break; }
-                                    const bool srev = en.len[2] == 1 && e[en.off[2]] == '-';
-                                    if (!cigar_analyze_dev(e + en.off[3], en.len[3], &cs, &ce, &rs, &qs)) { ok = false; ++soft; break; }
-                                    if (!parse_int_dev(e + en.off[1], en.len[1], &p1)) { ok = false; ++soft; break; }
-                                    Seg* g = &sg[++ei];
-                                    g->contig = contig_lookup_dev(P.contig, P.n_contig, e + en.off[0], en.len[0]); if (g->contig < 0) { g->contig = -2 - ei; ++soft; }
-                                    g->ref_start = (int)(p1 - 1); g->ref_end = (int)(p1 - 1 + rs); g->qry_start = (int)(srev ? ce : cs); g->qry_end = g->qry_start + (int)qs;
-                                    g->meta = (srev ? 1 : 0) | ((int)mq << 8) | (SNFB_SRC_SPLIT_SUP << 16); g->nhint = 0;
-                                }
-                                st = i + 1;
-                            }
-                            if (ok) {
-                                const int m = classify_splits_dev(cfg, sg, ne + 1, r.l_seq);
-                                for (int i = 0; i < m; ++i) for (int h = 0; h < sg[i].nhint; ++h) {
-                                    const int mqc = (sg[i].meta >> 8) & 255, mqp = (sg[i > 0 ? i - 1 : 0].meta >> 8) & 255;
-                                    if (!cfg.dev_keep_lowqual_splits && (mqc < mqp ? mqc : mqp) < cfg.mapq) continue;
-                                    const int ty = sg[i].h_type[h]; const int hs = sg[i].h_start[h];
-                                    if (sg[i].contig != tk.contig || hs < tk.start || hs >= tk.end) continue;
-                                    snfb_lead L;
-                                    L.rec = rec; L.qname_hash = qh; L.read_len = 0; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
-                                    L.ref_start = hs; L.ref_end = (!sg[i].h_none[h] && ty != SNFB_INS) ? hs + sg[i].h_len[h] : hs;
-                                    L.qry_start = sg[i].qry_start; L.qry_end = sg[i].qry_end; L.svlen = sg[i].h_len[h];
-                                    uint32_t f = (uint32_t)ty | ((uint32_t)((sg[i].meta >> 16) & 3) << 3) | ((sg[i].meta & 1) ? SNFB_LF_REVERSE : 0u) | ((uint32_t)mqc << 16) | ((uint32_t)hp << 24);
-                                    if (sg[i].h_none[h]) f |= SNFB_LF_SVLEN_NONE;
-                                    if (ty == SNFB_INS && (sg[i].meta & (1 << 20))) { f |= SNFB_LF_HAS_SEQ; L.seq_off = sg[i].seq_off; L.seq_len = sg[i].seq_len; }
-                                    L.flags = f; L.task = (uint16_t)r.task; L.k = (uint16_t)(nlead + added);
-                                    const unsigned long long slot = atomicAdd(&P.ctr->n_leads, 1ULL);
-                                    if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
-                                    ++added;
-                                }
-                            }
-                        }
-                    }
-                }
+                SaArgs a; a.rec = rec; a.qas = qas; a.qae = qae; a.alen = alen; a.ref_end = ref_end; a.hp = hp; a.base_flags = base_flags; a.qh = qh; a.nlead = nlead; a.rev = rev; a.is_supp = is_supp;
+                added = process_sa(P, r, tk, cg, segs[wib], a, &soft, &overflow);
             }
             nlead += __shfl_sync(FULL, added, 0);
         }
@@ -363,23 +396,36 @@ __global__ void __launch_bounds__(THREADS) k_extract(const Params P) {
         }
     }
     if (lane == 0) {
-        if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); atomicAdd(&P.ctr->n_pass, (unsigned long long)0); }
+        if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
         if (soft) atomicAdd(&P.ctr->soft_errors, soft);
         if (unsorted) atomicAdd(&P.ctr->unsorted, unsorted);
     }
-    // overflow is counted by whichever lane hit it
     if (overflow) atomicAdd(&P.ctr->lead_overflow, overflow);
 }
 
 // deterministic per-task mean of the per-read nm values (config.average_regional_nm, leadprov.py:577).
-// Fixed reduction tree: the result does not depend on scheduling (it can differ from the
-// reference's sequential float accumulation in the last bits).
-__global__ void __launch_bounds__(256) k_task_nm(const uint8_t* __restrict__ rec_flags, const double* __restrict__ rec_nm, const uint32_t* __restrict__ task_first,
-                                                 const uint32_t* __restrict__ task_last, double* __restrict__ task_mean_nm) {
+// Fixed two-level reduction tree (4096-record chunks of each task, then the chunk partials in order): the result does
+// not depend on scheduling; it can differ from the reference's sequential float accumulation in the last bits.
+constexpr int NM_CHUNK = 4096;
+__global__ void __launch_bounds__(256) k_nm_partial(const uint8_t* __restrict__ rec_flags, const double* __restrict__ rec_nm, const uint32_t* __restrict__ task_first,
+                                                    const uint32_t* __restrict__ task_last, double* __restrict__ part_sum, unsigned* __restrict__ part_cnt) {
+    __shared__ double ssum[256]; __shared__ unsigned scnt[256];
+    const int t = blockIdx.y; const uint32_t lo = task_first[t] + blockIdx.x * NM_CHUNK, end = task_last[t];
+    if (lo >= end) return;                                  // whole block exits together
+    const uint32_t hi = lo + NM_CHUNK < end ? lo + NM_CHUNK : end;
+    double s = 0; unsigned c = 0;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) if ((rec_flags[i] & (RF_PASS | RF_HAS_NM)) == (RF_PASS | RF_HAS_NM)) { s += rec_nm[i]; ++c; }
+    ssum[threadIdx.x] = s; scnt[threadIdx.x] = c; __syncthreads();
+    for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; } __syncthreads(); }
+    if (threadIdx.x == 0) { part_sum[(size_t)t * gridDim.x + blockIdx.x] = ssum[0]; part_cnt[(size_t)t * gridDim.x + blockIdx.x] = scnt[0]; }
+}
+__global__ void __launch_bounds__(256) k_task_nm(const uint32_t* __restrict__ task_first, const uint32_t* __restrict__ task_last, const double* __restrict__ part_sum,
+                                                 const unsigned* __restrict__ part_cnt, int chunks_per_task, double* __restrict__ task_mean_nm) {
     __shared__ double ssum[256]; __shared__ unsigned long long scnt[256];
     const int t = blockIdx.x; const uint32_t lo = task_first[t], hi = task_last[t];
+    const uint32_t nch = hi > lo ? (hi - lo + NM_CHUNK - 1) / NM_CHUNK : 0;
     double s = 0; unsigned long long c = 0;
-    for (uint32_t i = lo + threadIdx.x; i < hi; i += 256) if ((rec_flags[i] & (RF_PASS | RF_HAS_NM)) == (RF_PASS | RF_HAS_NM)) { s += rec_nm[i]; ++c; }
+    for (uint32_t ch = threadIdx.x; ch < nch; ch += 256) { s += part_sum[(size_t)t * chunks_per_task + ch]; c += part_cnt[(size_t)t * chunks_per_task + ch]; }
     ssum[threadIdx.x] = s; scnt[threadIdx.x] = c; __syncthreads();
     for (int o = 128; o; o >>= 1) { if (threadIdx.x < o) { ssum[threadIdx.x] += ssum[threadIdx.x + o]; scnt[threadIdx.x] += scnt[threadIdx.x + o]; } __syncthreads(); }
     if (threadIdx.x == 0) task_mean_nm[t] = ssum[0] / (double)(scnt[0] > 1 ? scnt[0] : 1);
