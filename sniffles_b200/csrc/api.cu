@@ -65,7 +65,7 @@ struct snfb_ctx {
     unsigned long long n_bound = 0, cand_cap = 0, cand_lead_cap = 0, rn_cap = 0;
     bool sorted_in_first = true, stage_a_done = false, stage_b_done = false;
     // stage C
-    DevBuf b_plan_best, b_plan_nother, b_alt_len, b_scr_len, b_alt_off, b_scr_off, b_alt, b_scr, b_sorted_leads;
+    DevBuf b_plan_best, b_plan_nother, b_alt_len, b_scr_len, b_alt_off, b_scr_off, b_alt, b_scr, b_sorted_leads, b_work_big, b_work_small, b_work_ctr;
     // host staging
     HostBuf h_leads, h_task_reads, h_task_nm, h_rec_nm, h_cand, h_cand_leads, h_rnames, h_rn_off, h_task_cov, h_alt;
     std::vector<double> task_cov_mean; std::vector<snfb_task> tasks;
@@ -122,7 +122,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
         &ctx->b_ml_seqlen, &ctx->b_ml_plo, &ctx->b_ml_pn, &ctx->b_ml_has, &ctx->b_subl, &ctx->b_sub_cnt, &ctx->b_sub_off, &ctx->b_t_lo, &ctx->b_t_n, &ctx->b_t_bin, &ctx->b_sub_cluster, &ctx->b_sub_lo,
         &ctx->b_sub_n, &ctx->b_sub_bin, &ctx->b_cand_tmp, &ctx->b_cand_valid, &ctx->b_cand_id, &ctx->b_cand_nlead, &ctx->b_cand_lead_off, &ctx->b_cand_nrn, &ctx->b_cand_rn_off, &ctx->b_cand,
         &ctx->b_cand_leads, &ctx->b_cand_lead_ml, &ctx->b_rnames, &ctx->b_rn_off_out, &ctx->b_plan_best, &ctx->b_plan_nother, &ctx->b_alt_len, &ctx->b_scr_len, &ctx->b_alt_off, &ctx->b_scr_off,
-        &ctx->b_alt, &ctx->b_scr, &ctx->b_sorted_leads };
+        &ctx->b_alt, &ctx->b_scr, &ctx->b_sorted_leads, &ctx->b_work_big, &ctx->b_work_small, &ctx->b_work_ctr };
     for (DevBuf* b : bufs) b->release();
     HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt };
     for (HostBuf* b : hb) b->release();
@@ -414,6 +414,9 @@ static int run_stage_c(snfb_ctx* ctx) {
     c.ml_plo = ctx->b_ml_plo.as<uint32_t>(); c.ml_pn = ctx->b_ml_pn.as<uint32_t>(); c.ord = ctx->b_ord.as<uint32_t>(); c.leads = ctx->b_leads.as<snfb_lead>(); c.rec = ctx->d_rec; c.seq = ctx->d_seq;
     c.plan_best = ctx->b_plan_best.as<uint32_t>(); c.plan_nother = ctx->b_plan_nother.as<uint32_t>(); c.alt_len = ctx->b_alt_len.as<uint32_t>(); c.scr_len = ctx->b_scr_len.as<uint32_t>();
     c.alt_off = ctx->b_alt_off.as<uint32_t>(); c.scr_off = ctx->b_scr_off.as<uint32_t>(); c.cand_cap = ctx->cand_cap; c.ctr = ctx->b_ctr.as<DevCounters>(); c.cfg = ctx->cfg;
+    if (ctx->b_work_big.ensure(4 * ctx->cand_cap) || ctx->b_work_small.ensure(4 * ctx->cand_cap) || ctx->b_work_ctr.ensure(16)) return fail(ctx, "out of device memory (consensus queue)");
+    c.work_big = ctx->b_work_big.as<uint32_t>(); c.work_small = ctx->b_work_small.as<uint32_t>(); c.work_ctr = ctx->b_work_ctr.as<uint32_t>();
+    CUDA_TRY(cudaMemsetAsync(c.work_ctr, 0, 16, ctx->st));
     mark(ctx, "consensus_plan");
     consensus::k_plan<<<grid_for(ctx->cand_cap, 128), 128, 0, ctx->st>>>(c); LAUNCHED(ctx, 1);
     LAUNCHED(ctx, prims::exclusive_scan(c.alt_len, c.alt_off, ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->cand_cap, &c.ctr->n_alt_bytes, ctx->st));
@@ -425,7 +428,7 @@ static int run_stage_c(snfb_ctx* ctx) {
     c.alt = ctx->b_alt.as<uint8_t>(); c.scr = ctx->b_scr.as<uint8_t>(); c.alt_cap = ctx->h_ctr.n_alt_bytes; c.scr_cap16 = ctx->h_ctr.n_seq_bytes;
     if (ctx->h_ctr.n_cand) {
         mark(ctx, "consensus", ctx->h_ctr.n_seq_bytes * 16);
-        const unsigned long long nblk = std::min<unsigned long long>(ctx->h_ctr.n_cand, 148ull * 16);
+        const unsigned long long nblk = std::min<unsigned long long>(ctx->h_ctr.n_cand, 148ull * 4);
         consensus::k_run<<<(int)nblk, consensus::THREADS, 0, ctx->st>>>(c); LAUNCHED(ctx, 1);
         mark(ctx, nullptr);
     }

@@ -19,6 +19,7 @@ struct C {
     const snfb_rec* rec; const uint8_t* seq;
     uint32_t* plan_best; uint32_t* plan_nother; uint32_t* alt_len; uint32_t* scr_len; uint32_t* alt_off; uint32_t* scr_off;   // scr in units of 16 bytes
     uint8_t* alt; uint8_t* scr; unsigned long long alt_cap, scr_cap16, cand_cap;
+    uint32_t* work_big; uint32_t* work_small; uint32_t* work_ctr;      // work_ctr: [0] n_big, [1] n_small, [2] queue position
     DevCounters* ctr; snfb_config cfg;
 };
 
@@ -43,124 +44,193 @@ __global__ void k_plan(C c) {
                 const unsigned long long bytes = cons ? (unsigned long long)tot + (unsigned long long)(nm - 1) * L + (unsigned long long)(nm - 1) * 16 + 64 : (unsigned long long)L + 16;
                 sl = (uint32_t)((bytes + 15) / 16);
                 c.cand_rw[i].alt_len = (int)L;
+                // work queue: the heavy tail (long insertions with many reads) is scheduled first
+                const unsigned long long work = (unsigned long long)L * (unsigned long long)nm;
+                if (work > 200000ull) c.work_big[atomicAdd(&c.work_ctr[0], 1u)] = (uint32_t)i; else c.work_small[atomicAdd(&c.work_ctr[1], 1u)] = (uint32_t)i;
             }
         }
         c.alt_len[i] = al; c.scr_len[i] = sl;
     }
 }
 
-// unpack the (possibly merged) sequence of candidate lead `k` as 4-bit codes, one byte per base
+// unpack `len` bases starting at nibble `off` of sq into dst (one code per byte); `tid`/`nthr` = cooperating threads.
+// Each thread takes 8 consecutive bases per step and four steps are kept in flight so that the 4-bit arena is
+// streamed from HBM with enough loads outstanding.
+__device__ __forceinline__ void unpack_span(const uint8_t* __restrict__ sq, long long off, int len, uint8_t* __restrict__ dst, int tid, int nthr) {
+    const int stride = nthr * 8;
+    for (int j0 = tid * 8; j0 < len; j0 += 4 * stride) {
+        uint8_t v[4][5];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) { const int jb = j0 + u * stride; const long long q = off + jb; const uint8_t* p = sq + (q >> 1);
+            #pragma unroll
+            for (int t = 0; t < 5; ++t) v[u][t] = (jb + 2 * t - (int)(q & 1) < len + 1 && jb < len) ? __ldg(p + t) : (uint8_t)0; }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) { const int jb = j0 + u * stride; const int ph = (int)((off + jb) & 1);
+            #pragma unroll
+            for (int t = 0; t < 8; ++t) { const int nb = t + ph; const uint8_t by = v[u][nb >> 1]; if (jb + t < len) dst[jb + t] = (nb & 1) ? (by & 15) : (by >> 4); } }
+    }
+}
+// unpack the (possibly merged) sequence of candidate lead `cl_index` as 4-bit codes, one byte per base
 __device__ inline void unpack_lead(const C& c, uint32_t cl_index, uint8_t* dst) {
     const uint32_t mi = c.cand_lead_ml[cl_index]; const uint32_t plo = c.ml_plo[mi], pn = c.ml_pn[mi];
     long long o = 0;
     for (uint32_t p = 0; p < pn; ++p) {
-        const snfb_lead* l = &c.leads[c.ord[plo + p]]; const uint8_t* sq = c.seq + c.rec[l->rec].seq_off; const long long off = l->seq_off; const int len = l->seq_len;
-        for (int j = threadIdx.x; j < len; j += blockDim.x) dst[o + j] = seq_code(sq, off + j);
-        o += len;
+        const snfb_lead* l = &c.leads[c.ord[plo + p]]; const uint8_t* sq = c.seq + c.rec[l->rec].seq_off;
+        unpack_span(sq, l->seq_off, l->seq_len, dst + o, threadIdx.x, blockDim.x);
+        o += l->seq_len;
     }
 }
 
 __device__ __forceinline__ uint32_t kmer6(const uint8_t* s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 4) | ((uint32_t)s[2] << 8) | ((uint32_t)s[3] << 12) | ((uint32_t)s[4] << 16) | ((uint32_t)s[5] << 20); }
 __device__ __forceinline__ uint32_t kslot(uint32_t key) { return (key * 2654435761u) >> 21; }    // top 11 bits
 
+constexpr int MAXHIT = 512;       // strided k-mer hits of one read are bounded by (L + 6) / skip + 1 < 512 (skip = 3 + L / 500)
+
+// the same with the calling warp only
+__device__ inline void unpack_lead_warp(const C& c, uint32_t cl_index, uint8_t* dst) {
+    const uint32_t mi = c.cand_lead_ml[cl_index]; const uint32_t plo = c.ml_plo[mi], pn = c.ml_pn[mi];
+    long long o = 0;
+    for (uint32_t p = 0; p < pn; ++p) {
+        const snfb_lead* l = &c.leads[c.ord[plo + p]]; const uint8_t* sq = c.seq + c.rec[l->rec].seq_off;
+        unpack_span(sq, l->seq_off, l->seq_len, dst + o, lane_id(), 32);
+        o += l->seq_len;
+    }
+}
+
+// One block per INS candidate, candidates pulled from a two-level work queue (heavy ones first).
+// Per other read (one warp each):  (1) 32 k-mer probes per step collect the anchor hits, (2) the reference's
+// order-dependent anchor automaton runs over the compact hit list in shared memory (no memory latency in the
+// serial part), (3) the accepted hits become independent segments that the lanes compare / copy in parallel,
+// (4) dash-free runs are filtered with ballots.  Then one thread per column votes.
 __global__ void __launch_bounds__(THREADS) k_run(C c) {
-    __shared__ uint32_t t_key[TAB]; __shared__ int t_pos[TAB]; __shared__ uint32_t t_cnt[TAB];
-    __shared__ int n_accept;
-    const unsigned long long nc = c.ctr->n_cand < c.cand_cap ? c.ctr->n_cand : c.cand_cap;
+    __shared__ uint32_t t_key[TAB]; __shared__ int t_pos[TAB];      // t_pos: -1 empty, -2 k-mer seen more than once (banned), else its position
+    __shared__ int h_i[THREADS / 32][MAXHIT], h_j[THREADS / 32][MAXHIT], h_cl[THREADS / 32][MAXHIT];
+    __shared__ int n_accept; __shared__ uint32_t s_cand;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     static const char CODE[17] = "=ACMGRSVTWYHKDBN";
-    for (unsigned long long ci = blockIdx.x; ci < nc; ci += gridDim.x) {
-        const uint32_t L = c.alt_len[ci];
+    for (;;) {
         __syncthreads();
-        if (c.scr_len[ci] == 0) continue;
+        if (threadIdx.x == 0) {
+            const uint32_t q = atomicAdd(&c.work_ctr[2], 1u); const uint32_t nb = c.work_ctr[0], ns = c.work_ctr[1];
+            s_cand = q < nb ? c.work_big[q] : (q < nb + ns ? c.work_small[q - nb] : 0xffffffffu);
+            n_accept = 0;
+        }
+        __syncthreads();
+        const uint32_t ci = s_cand;
+        if (ci == 0xffffffffu) break;
+        const uint32_t L = c.alt_len[ci];
         const snfb_cand cd = c.cand[ci];
         if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) { if (threadIdx.x == 0) atomicAdd(&c.ctr->scratch_overflow, 1ULL); continue; }
         uint8_t* out = c.alt + c.alt_off[ci];
-        uint8_t* scr = c.scr + (size_t)c.scr_off[ci] * 16;
-        uint8_t* best = scr;
+        uint8_t* best = c.scr + (size_t)c.scr_off[ci] * 16;
         const uint32_t bi = c.plan_best[ci], no = c.plan_nother[ci];
         unpack_lead(c, cd.lead_off + bi, best);
-        if (threadIdx.x == 0) { c.cand_rw[ci].alt_off = (int)c.alt_off[ci]; n_accept = 0; }
+        if (threadIdx.x == 0) c.cand_rw[ci].alt_off = (int)c.alt_off[ci];
         __syncthreads();
         if (no == 0 || L == 0) { for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) out[h] = (uint8_t)CODE[best[h]]; continue; }
-        // layout: best[L] | per other read: codes | rows[no][L] | accept[no]
+        // layout: best[L] | other reads' codes | rows[no][L] | accept[no]
         uint8_t* oth = best + L;
         const int klen = 6; const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
         // anchors: k-mers of the best read seen exactly once among the strided positions (consensus.py:292-299)
-        for (int i = threadIdx.x; i < TAB; i += blockDim.x) { t_key[i] = 0xffffffffu; t_cnt[i] = 0; }
+        for (int i = threadIdx.x; i < TAB; i += blockDim.x) { t_key[i] = 0xffffffffu; t_pos[i] = -1; }
         __syncthreads();
         for (long i = (long)threadIdx.x * skip; i < (long)L - klen; i += (long)blockDim.x * skip) {
             const uint32_t key = kmer6(best + i); uint32_t s = kslot(key);
             for (;;) { const uint32_t old = atomicCAS(&t_key[s], 0xffffffffu, key); if (old == 0xffffffffu || old == key) break; s = (s + 1) & (TAB - 1); }
-            if (atomicAdd(&t_cnt[s], 1u) == 0) t_pos[s] = (int)i;
+            if (atomicCAS(&t_pos[s], -1, (int)i) != -1) t_pos[s] = -2;
         }
-        // offsets of the other reads' codes
-        // (serial prefix over the candidate's leads; a handful of entries)
+        long long o_total = 0;
+        for (int k = 0; k < cd.lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd.lead_off + k]; if ((l->flags & SNFB_LF_HAS_SEQ) && (uint32_t)k != bi) o_total += l->seq_len; }
+        uint8_t* rows = oth + o_total; uint8_t* acc = rows + (size_t)no * L;
         __syncthreads();
-        // unpack all other reads
+        // ---- every other read: one warp ----
         {
-            long long o = 0; uint32_t r = 0;
-            for (int k = 0; k < cd.lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd.lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ) || (uint32_t)k == bi) continue; unpack_lead(c, cd.lead_off + k, oth + o); o += l->seq_len; ++r; }
-            uint8_t* rows = oth + o; uint8_t* acc = rows + (size_t)no * L;
-            __syncthreads();
-            // ---- align every other read (one warp each) ----
             long long ro = 0; uint32_t ridx = 0;
+            int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp];
             for (int k = 0; k < cd.lead_n; ++k) {
                 const snfb_lead* l = &c.cand_leads[cd.lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ) || (uint32_t)k == bi) continue;
-                const long Lo = l->seq_len; const uint8_t* rd = oth + ro; const uint32_t myr = ridx; ro += Lo; ++ridx;
+                const long Lo = l->seq_len; uint8_t* rd = oth + ro; const uint32_t myr = ridx; ro += Lo; ++ridx;
                 if ((int)(myr % nwarp) != warp) continue;
+                unpack_lead_warp(c, cd.lead_off + k, rd);
+                __syncwarp();
                 uint8_t* row = rows + (size_t)myr * L;
-                long last_i = -1, last_j = -1, cl = 0, span = 0; bool have = false;
-                const long nk = Lo - klen > 0 ? (Lo - klen + skip - 1) / skip : 0;         // number of strided k-mers
+                // (1) anchor hits in j order
+                int nh = 0;
+                const long nk = Lo - klen > 0 ? (Lo - klen + skip - 1) / skip : 0;
                 for (long kb = 0; kb < nk; kb += 32) {
                     const long kk = kb + lane; const long j = kk * skip; int ai = -1;
                     if (kk < nk) { const uint32_t key = kmer6(rd + j); uint32_t s = kslot(key);
-                        for (;;) { const uint32_t tk = t_key[s]; if (tk == 0xffffffffu) break; if (tk == key) { if (t_cnt[s] == 1) ai = t_pos[s]; break; } s = (s + 1) & (TAB - 1); }
+                        for (;;) { const uint32_t tk = t_key[s]; if (tk == 0xffffffffu) break; if (tk == key) { ai = t_pos[s]; break; } s = (s + 1) & (TAB - 1); }
                         if (ai >= 0) { long d = ai - j; if (d < 0) d = -d; if (d > klen) ai = -1; } }
-                    unsigned hits = __ballot_sync(FULL, ai >= 0);
-                    while (hits) {
-                        const int src = __ffs(hits) - 1; hits &= hits - 1;
-                        const long i = __shfl_sync(FULL, ai, src); const long jj = (kb + src) * skip;
-                        if (have && i <= last_i) continue;
-                        if (!have) { if (jj > 0) { for (long q = lane; q < i; q += 32) row[q] = DASH; cl = i; } }
-                        else {
-                            const long fwd_i = i - last_i; long fwd_j = jj - last_j;
-                            if (cl + fwd_j > (long)L) fwd_j = (long)L - cl;
-                            bool copy = false;
-                            if (fwd_i == fwd_j && fwd_j > 0) {
-                                const long d = jj - last_j; span += d; int m = 0;
-                                for (long q = 1 + lane; q <= d; q += 32) if (last_i + q < (long)L && rd[last_j + q] == best[last_i + q]) ++m;
-                                m = __reduce_add_sync(FULL, m);
-                                copy = __ddiv_rn((double)m, (double)d) >= 0.5;
-                            }
-                            if (copy) { for (long q = lane; q < fwd_j; q += 32) row[cl + q] = rd[last_j + q]; }
-                            else { for (long q = lane; q < fwd_j; q += 32) row[cl + q] = DASH; }
-                            if (fwd_j > 0) cl += fwd_j;
-                        }
-                        last_i = i; last_j = jj; have = true;
-                    }
+                    const unsigned hm = __ballot_sync(FULL, ai >= 0);
+                    if (ai >= 0) { const int p = nh + __popc(hm & lanemask_lt()); if (p < MAXHIT) { hi[p] = ai; hj[p] = (int)j; } }
+                    nh += __popc(hm);
                 }
+                if (nh > MAXHIT) nh = MAXHIT;       // cannot happen (see MAXHIT); keeps the buffers safe
+                __syncwarp();
+                // (2) the anchor automaton over the hit list (consensus.py:306-338), all lanes in lockstep on shared memory.
+                //     accepted hit m: (hi[m], hj[m]) with hcl[m] = len(conseq) before its segment is appended
+                int na = 0; long last_i = -1, cl = 0;
+                for (int h = 0; h < nh; ++h) {
+                    const int i = hi[h], j = hj[h];
+                    if (na > 0 && i <= last_i) continue;
+                    long before = cl;
+                    if (na == 0) { if (j > 0) cl = i; before = 0; }
+                    else { long fwd_j = (long)j - hj[na - 1]; if (cl + fwd_j > (long)L) fwd_j = (long)L - cl; cl += fwd_j; }
+                    __syncwarp();
+                    if (lane == 0) { hi[na] = i; hj[na] = j; hcl[na] = (int)before; }
+                    __syncwarp();
+                    ++na; last_i = i;
+                }
+                // (3) segments in parallel: lane per segment
+                long span = 0;
+                if (na > 0) { const long c0 = hj[0] > 0 ? hi[0] : 0; for (long q = lane; q < c0; q += 32) row[q] = DASH; }
+                for (int m = 1 + lane; m < na; m += 32) {
+                    const long li = hi[m - 1], lj = hj[m - 1], i = hi[m], j = hj[m], cs = hcl[m];
+                    const long d = j - lj; long fwd_j = d; if (cs + fwd_j > (long)L) fwd_j = (long)L - cs;
+                    const long fwd_i = i - li; bool copy = false;
+                    if (fwd_i == fwd_j && fwd_j > 0) {
+                        span += d; int mt = 0;
+                        #pragma unroll 8
+                        for (long q = 1; q <= d; ++q) mt += (li + q < (long)L && rd[lj + q] == best[li + q]) ? 1 : 0;
+                        copy = __ddiv_rn((double)mt, (double)d) >= 0.5;
+                    }
+                    if (copy) {
+                        #pragma unroll 8
+                        for (long q = 0; q < fwd_j; ++q) row[cs + q] = rd[lj + q];
+                    } else { for (long q = 0; q < fwd_j; ++q) row[cs + q] = DASH; }
+                }
+                span = (long)__reduce_add_sync(FULL, (unsigned)span);
                 for (long q = cl + lane; q < (long)L; q += 32) row[q] = DASH;
                 __syncwarp();
-                // ---- dash-free runs survive only with identity > 0.5 and more than 5 matches (consensus.py:343-360) ----
+                // (4) dash-free runs survive only with identity > 0.5 and more than 5 matches (consensus.py:343-360)
                 bool in_run = false; long run_start = 0; long ident = 0;
-                for (long h0 = 0; h0 < (long)L; h0 += 32) {
-                    const long h = h0 + lane; const uint8_t cc = h < (long)L ? row[h] : DASH;
-                    const unsigned nd = __ballot_sync(FULL, cc != DASH), mt = __ballot_sync(FULL, cc != DASH && cc == best[h < (long)L ? h : 0]);
-                    int p = 0;
-                    while (p < 32) {
-                        if (in_run) {
-                            const unsigned rest = ~(nd >> p); int cnt = rest ? __ffs(rest) - 1 : 32; if (cnt > 32 - p) cnt = 32 - p;
-                            const unsigned mask = cnt >= 32 ? 0xffffffffu : (((1u << cnt) - 1u) << p);
-                            ident += __popc(mt & mask); p += cnt;
-                            if (p < 32) {       // the run ended on a dash at h0 + p
-                                const long len = h0 + p - run_start;
-                                if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q = run_start + lane; q < h0 + p; q += 32) row[q] = DASH;
-                                in_run = false;
+                for (long hb = 0; hb < (long)L; hb += 128) {
+                    // four 32-column steps are loaded up front so that their latencies overlap
+                    uint8_t ccs[4], bbs[4];
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u) { const long h = hb + 32 * u + lane; const bool in = h < (long)L; ccs[u] = in ? row[h] : DASH; bbs[u] = in ? best[h] : (uint8_t)0; }
+                    #pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const long h0 = hb + 32 * u; if (h0 >= (long)L) break;
+                        const uint8_t cc = ccs[u];
+                        const unsigned nd = __ballot_sync(FULL, cc != DASH), mt = __ballot_sync(FULL, cc != DASH && cc == bbs[u]);
+                        if (!in_run && nd == 0) continue;
+                        int p = 0;
+                        while (p < 32) {
+                            if (in_run) {
+                                const unsigned rest = ~(nd >> p); int cnt = rest ? __ffs(rest) - 1 : 32; if (cnt > 32 - p) cnt = 32 - p;
+                                const unsigned mask = cnt >= 32 ? 0xffffffffu : (((1u << cnt) - 1u) << p);
+                                ident += __popc(mt & mask); p += cnt;
+                                if (p < 32) {       // the run ended on a dash at h0 + p
+                                    const long len = h0 + p - run_start;
+                                    if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q = run_start + lane; q < h0 + p; q += 32) row[q] = DASH;
+                                    in_run = false;
+                                }
+                            } else {
+                                const unsigned rest = nd >> p; if (!rest) { p = 32; break; }
+                                p += __ffs(rest) - 1; in_run = true; run_start = h0 + p; ident = 0;
                             }
-                        } else {
-                            const unsigned rest = nd >> p; if (!rest) { p = 32; break; }
-                            p += __ffs(rest) - 1; in_run = true; run_start = h0 + p; ident = 0;
                         }
                     }
                 }
@@ -168,22 +238,28 @@ __global__ void __launch_bounds__(THREADS) k_run(C c) {
                 const bool ok = __ddiv_rn((double)span, (double)L) > 0.2;
                 if (lane == 0) { acc[myr] = ok; if (ok) atomicAdd(&n_accept, 1); }
             }
-            __syncthreads();
-            // ---- column vote (consensus.py:365-380) ----
-            const double maxal = (double)(1 + n_accept);
-            for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) {
-                unsigned long long cnt[4] = { 0, 0, 0, 0 }; int nal = 0;
-                for (uint32_t r2 = 0; r2 < no; ++r2) { if (!acc[r2]) continue; const uint8_t cc = rows[(size_t)r2 * L + h]; if (cc != DASH) { cnt[cc >> 2] += 1ull << (16 * (cc & 3)); ++nal; } }
-                uint8_t res = best[h];
-                if (!(nal < 2 || __ddiv_rn((double)nal, maxal) < 0.25)) {
-                    cnt[best[h] >> 2] += 1ull << (16 * (best[h] & 3));
-                    int t0 = -1, t1 = -1, c0 = 0, nd = 0;
-                    #pragma unroll
-                    for (int code = 0; code < 16; ++code) { const int v = (int)((cnt[code >> 2] >> (16 * (code & 3))) & 0xffff); if (!v) continue; ++nd; if (v > t0) { t1 = t0; t0 = v; c0 = code; } else if (v > t1) t1 = v; }
-                    if (nd > 1 && t0 - t1 >= 3) res = (uint8_t)c0;
-                }
-                out[h] = (uint8_t)CODE[res];
+        }
+        __syncthreads();
+        // ---- column vote (consensus.py:365-380) ----
+        const double maxal = (double)(1 + n_accept);
+        for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) {
+            unsigned long long cnt[4] = { 0, 0, 0, 0 }; int nal = 0;
+            for (uint32_t r0 = 0; r0 < no; r0 += 8) {       // eight row bytes in flight per thread
+                uint8_t cv[8];
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) { const uint32_t r2 = r0 + u; cv[u] = (r2 < no && acc[r2]) ? rows[(size_t)r2 * L + h] : DASH; }
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) { const uint8_t cc = cv[u]; if (cc != DASH) { cnt[cc >> 2] += 1ull << (16 * (cc & 3)); ++nal; } }
             }
+            uint8_t res = best[h];
+            if (!(nal < 2 || __ddiv_rn((double)nal, maxal) < 0.25)) {
+                cnt[best[h] >> 2] += 1ull << (16 * (best[h] & 3));
+                int t0 = -1, t1 = -1, c0 = 0, nd = 0;
+                #pragma unroll
+                for (int code = 0; code < 16; ++code) { const int v = (int)((cnt[code >> 2] >> (16 * (code & 3))) & 0xffff); if (!v) continue; ++nd; if (v > t0) { t1 = t0; t0 = v; c0 = code; } else if (v > t1) t1 = v; }
+                if (nd > 1 && t0 - t1 >= 3) res = (uint8_t)c0;
+            }
+            out[h] = (uint8_t)CODE[res];
         }
     }
 }

@@ -138,13 +138,22 @@ __device__ inline int classify_splits_dev(const snfb_config& cfg, Seg* s, int n,
 }
 
 // ---- supplementary alignments (SA tag) of one record: Lead.for_bnd + read_itersplits, run by lane 0 ----
-struct SaArgs { uint32_t rec; int qas, qae, alen, ref_end, hp; uint32_t base_flags; uint64_t qh; unsigned nlead; bool rev, is_supp; };
-__device__ __noinline__ unsigned process_sa(const Params& P, const snfb_rec& r, const snfb_task& tk, const uint32_t* __restrict__ cg, Seg* sg, const SaArgs a,
-                                            unsigned long long* soft_p, unsigned long long* overflow_p) {
-    const snfb_config& cfg = P.cfg;
-    const int n = (int)r.n_cigar; const uint32_t rec = a.rec; const bool rev = a.rev;
+struct SaArgs {
+    uint32_t rec; int qas, qae, alen, ref_end, hp; uint32_t base_flags; uint64_t qh; unsigned nlead; bool rev, is_supp;
+    // the pieces of Params / snfb_rec / snfb_task the SA path needs, by value (keeps the caller's structs out of local memory)
+    const uint8_t* sa; int sa_len; uint32_t c_first, c_last; int pos, l_seq, mapq, aux_flags, task;
+    int tk_contig, tk_start, tk_end;
+    const snfb_contig* contig; uint32_t n_contig; snfb_lead* leads; unsigned long long lead_cap; unsigned long long* n_leads;
+    int mapq_min, dev_keep_lowqual_splits, max_splits_base; double max_splits_kb;
+};
+__device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp, Seg* sg, const SaArgs a, unsigned long long* soft_p, unsigned long long* overflow_p) {
+    const snfb_config& cfg = *cfgp;
+    const uint32_t rec = a.rec; const bool rev = a.rev;
     unsigned long long soft = 0, overflow = 0; unsigned added = 0;
-    const uint8_t* sa = P.var + r.var_off + r.l_qname; const int sl = (int)r.sa_len;
+    const uint8_t* sa = a.sa; const int sl = a.sa_len;
+    struct { int pos, l_seq, mapq, aux_flags, task; } r = { a.pos, a.l_seq, a.mapq, a.aux_flags, a.task };
+    struct { int contig, start, end; } tk = { a.tk_contig, a.tk_start, a.tk_end };
+    struct { const snfb_contig* contig; uint32_t n_contig; snfb_lead* leads; unsigned long long lead_cap; } P = { a.contig, a.n_contig, a.leads, a.lead_cap };
     // pass 1: count the non-empty entries and locate the first one
     int ne = 0, f_off = 0, f_len = 0;
     for (int i = 0, st = 0; i <= sl; ++i) if (i == sl || sa[i] == ';') { if (i > st) { if (ne == 0) { f_off = st; f_len = i - st; } ++ne; } st = i + 1; }
@@ -153,8 +162,8 @@ __device__ __noinline__ unsigned process_sa(const Params& P, const snfb_rec& r, 
     if (ne > 0 && sa_ok) {                                   // Lead.for_bnd: first entry only
         const uint8_t* e = sa + f_off;
         int left = 0, right = 0;
-        { uint32_t c = cg[0]; int op = c & 15; if (op == 4 || op == 5) left = (int)(c >> 4); }
-        { uint32_t c = cg[n - 1]; int op = c & 15; if (op == 4 || op == 5) right = (int)(c >> 4); }
+        { uint32_t c = a.c_first; int op = c & 15; if (op == 4 || op == 5) left = (int)(c >> 4); }
+        { uint32_t c = a.c_last; int op = c & 15; if (op == 4 || op == 5) right = (int)(c >> 4); }
         int bstart; bool is_first;
         if (left > right) { bstart = r.pos + 1; is_first = false; } else { bstart = a.ref_end; is_first = true; }
         const bool same = e0.len[2] == 1 && ((e[e0.off[2]] == '-' && rev) || (e[e0.off[2]] == '+' && !rev));
@@ -175,7 +184,7 @@ __device__ __noinline__ unsigned process_sa(const Params& P, const snfb_rec& r, 
                     L.nm_sa = (int)sanm; L.task = (uint16_t)r.task; L.k = (uint16_t)(a.nlead + added);
                     L.flags = a.base_flags | SNFB_BND | ((uint32_t)SNFB_SRC_BND_SA << 3) | (is_first ? SNFB_LF_BND_FIRST : 0u) | (is_reverse ? SNFB_LF_BND_REVERSE : 0u)
                               | ((r.aux_flags & SNFB_AUX_NM) ? 0u : SNFB_LF_NM_NONE);
-                    const unsigned long long slot = atomicAdd(&P.ctr->n_leads, 1ULL);
+                    const unsigned long long slot = atomicAdd(a.n_leads, 1ULL);
                     if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
                     ++added;
                 }
@@ -222,7 +231,7 @@ __device__ __noinline__ unsigned process_sa(const Params& P, const snfb_rec& r, 
                         if (sg[i].h_none[h]) f |= SNFB_LF_SVLEN_NONE;
                         if (ty == SNFB_INS && (sg[i].meta & (1 << 20))) { f |= SNFB_LF_HAS_SEQ; L.seq_off = sg[i].seq_off; L.seq_len = sg[i].seq_len; }
                         L.flags = f; L.task = (uint16_t)r.task; L.k = (uint16_t)(a.nlead + added);
-                        const unsigned long long slot = atomicAdd(&P.ctr->n_leads, 1ULL);
+                        const unsigned long long slot = atomicAdd(a.n_leads, 1ULL);
                         if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
                         ++added;
                     }
@@ -234,23 +243,18 @@ __device__ __noinline__ unsigned process_sa(const Params& P, const snfb_rec& r, 
     return added;
 }
 
-// one 16-byte slice of a record's CIGAR (4 ops) for this lane; zero outside the record
-__device__ __forceinline__ uint4 load_chunk(const uint32_t* __restrict__ cigar, long long c, int lane, long long c_begin, long long c_end) {
-    const long long i0 = c + lane * 4;
-    if (i0 < c_end && i0 + 3 >= c_begin) return __ldg(reinterpret_cast<const uint4*>(cigar + i0));
-    return make_uint4(0, 0, 0, 0);
-}
-
 __global__ void __launch_bounds__(THREADS, 3) k_extract(const Params P) {
     __shared__ Seg segs[WARPS][MAXSEG];
-    const snfb_config& cfg = P.cfg;
+    __shared__ snfb_config s_cfg;
+    if (threadIdx.x < sizeof(snfb_config) / 4) reinterpret_cast<uint32_t*>(&s_cfg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&P.cfg)[threadIdx.x];
+    __syncthreads();
     const int lane = lane_id(), wib = threadIdx.x >> 5;
     const unsigned nwarps = gridDim.x * WARPS;
+    const int minsv = P.cfg.minsvlen_screen, mapq_min = P.cfg.mapq, alen_min = P.cfg.min_alignment_length, excl = P.cfg.exclude_flags;
     // per-warp accumulators flushed when the task changes (records are grouped by task)
     int acc_task = -1; unsigned acc_reads = 0; unsigned long long acc_bp = 0; int acc_span = 0;
-    unsigned long long soft = 0, overflow = 0, unsorted = 0;
-    snfb_task tk; int tk_id = -1;
-    tk.contig = tk.start = tk.end = tk.contig_len = 0;
+    unsigned long long soft = 0, overflow = 0; unsigned unsorted = 0;
+    int tk_id = -1, tk_contig = 0, tk_start = 0, tk_end = 0, tk_len = 0;
 
     unsigned rec = blockIdx.x * WARPS + wib;
     // software pipeline over records: the next record's 64-byte core is in flight while this one is processed
@@ -258,126 +262,133 @@ __global__ void __launch_bounds__(THREADS, 3) k_extract(const Params P) {
     for (; rec < P.n_rec; rec += nwarps) {
         const uint32_t wcur = wnext;
         { const unsigned nrec2 = rec + nwarps; wnext = (nrec2 < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + nrec2) + lane) : 0u; }
-        snfb_rec r;
-        r.task = (int)__shfl_sync(FULL, wcur, 0); r.pos = (int)__shfl_sync(FULL, wcur, 1);
-        { const uint32_t x = __shfl_sync(FULL, wcur, 2); r.flag = (uint16_t)x; r.mapq = (uint8_t)(x >> 16); r.aux_flags = (uint8_t)(x >> 24); }
-        { const uint32_t x = __shfl_sync(FULL, wcur, 3); r.hp = (uint8_t)x; r.l_qname = (uint8_t)(x >> 8); }
-        r.nm = (int)__shfl_sync(FULL, wcur, 4); r.ps = (int)__shfl_sync(FULL, wcur, 5); r.n_cigar = __shfl_sync(FULL, wcur, 6); r.l_seq = (int)__shfl_sync(FULL, wcur, 7);
-        r.sa_len = __shfl_sync(FULL, wcur, 8);
-        r.cigar_off = (uint64_t)__shfl_sync(FULL, wcur, 10) | ((uint64_t)__shfl_sync(FULL, wcur, 11) << 32);
-        r.var_off = (uint64_t)__shfl_sync(FULL, wcur, 14) | ((uint64_t)__shfl_sync(FULL, wcur, 15) << 32);
-        r.seq_off = 0;
-        const uint32_t* __restrict__ cg = P.cigar + r.cigar_off;
-        const int n = (int)r.n_cigar;
-        const long long c_begin = (long long)r.cigar_off, c_end = c_begin + n; const long long c0 = c_begin & ~3LL;
-        // issue the first CIGAR slices before anything that depends on them
-        uint4 v0 = load_chunk(P.cigar, c0, lane, c_begin, c_end), v1 = load_chunk(P.cigar, c0 + 128, lane, c_begin, c_end), v2 = load_chunk(P.cigar, c0 + 256, lane, c_begin, c_end);
-        if (r.task != tk_id) { tk = P.task[r.task]; tk_id = r.task; }
+        const int r_task = (int)__shfl_sync(FULL, wcur, 0), r_pos = (int)__shfl_sync(FULL, wcur, 1);
+        const uint32_t x2 = __shfl_sync(FULL, wcur, 2), x3 = __shfl_sync(FULL, wcur, 3);
+        const int r_flag = x2 & 0xffff, r_mapq = (x2 >> 16) & 255, r_aux = x2 >> 24, r_hp = x3 & 255, r_lq = (x3 >> 8) & 255;
+        const int n = (int)__shfl_sync(FULL, wcur, 6), r_lseq = (int)__shfl_sync(FULL, wcur, 7);
+        const uint64_t cigar_off = (uint64_t)__shfl_sync(FULL, wcur, 10) | ((uint64_t)__shfl_sync(FULL, wcur, 11) << 32);
+        const uint32_t* __restrict__ cg = P.cigar + cigar_off;           // this record's ops
+        const int mis = (int)(cigar_off & 3);                              // ops between the 16-byte boundary and the record's first op
+        const uint32_t* __restrict__ cga = cg - mis;                       // 16-byte aligned
+        const int n_al = n + mis;                                          // local index space [mis, n_al) is the record
+        // issue the first CIGAR slices before anything that depends on them; lane l owns local ops 4l..4l+3 of a 128-op slice
+        #define LOAD_SLICE(base) (((base) + lane * 4 < n_al) ? __ldg(reinterpret_cast<const uint4*>(cga + (base)) + lane) : make_uint4(0, 0, 0, 0))
+        uint4 v0 = LOAD_SLICE(0), v1 = LOAD_SLICE(128), v2 = LOAD_SLICE(256);
+        const uint32_t c_first = n > 0 ? __ldg(cg) : 0u, c_last = n > 0 ? __ldg(cg + n - 1) : 0u;
+        if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_contig = t.contig; tk_start = t.start; tk_end = t.end; tk_len = t.contig_len; }
         if (lane == 0) {
-            P.rec_pos[rec] = r.pos;
-            if (rec == 0 || P.rec[rec - 1].task != r.task) P.task_first[r.task] = rec;
-            else if (P.rec[rec - 1].pos > r.pos) ++unsorted;
-            if (rec + 1 == P.n_rec || P.rec[rec + 1].task != r.task) P.task_last[r.task] = rec + 1;
+            P.rec_pos[rec] = r_pos;
+            if (rec == 0 || P.rec[rec - 1].task != r_task) P.task_first[r_task] = rec;
+            else if (P.rec[rec - 1].pos > r_pos) ++unsorted;
+            if (rec + 1 == P.n_rec || P.rec[rec + 1].task != r_task) P.task_last[r_task] = rec + 1;
         }
-        // pysam query_alignment_start / _end
-        int qas = 0, qae = r.l_seq;
-        for (int k = 0; k < n; ++k) { uint32_t c = __ldg(cg + k); int op = c & 15; if (op == 4) qas += (int)(c >> 4); else if (op != 5) break; }
-        for (int k = n - 1; k >= 1; --k) { uint32_t c = __ldg(cg + k); int op = c & 15; if (op == 4) qae -= (int)(c >> 4); else if (op != 5) break; }
+        // pysam query_alignment_start / _end: leading / trailing soft clips (hard clips are skipped)
+        int qas = 0, qae = r_lseq;
+        { int op = c_first & 15; if (op == 4) qas = (int)(c_first >> 4);
+          if (op == 4 || op == 5) for (int k = 1; k < n; ++k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qas += (int)(c >> 4); else if (o2 != 5) break; } }
+        if (n > 1) { int op = c_last & 15; if (op == 4) qae -= (int)(c_last >> 4);
+          if (op == 4 || op == 5) for (int k = n - 2; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qae -= (int)(c >> 4); else if (o2 != 5) break; } }
         const int alen = qae - qas;
-        bool pass = !(r.mapq < cfg.mapq || (r.flag & 256) || alen < cfg.min_alignment_length);
-        if (cfg.exclude_flags && (r.flag & cfg.exclude_flags)) pass = false;
-        if (r.pos < tk.start || r.pos >= tk.end) pass = false;
-        if (!pass || n == 0) {
+        bool pass = !(r_mapq < mapq_min || (r_flag & 256) || alen < alen_min) && !(excl && (r_flag & excl)) && r_pos >= tk_start && r_pos < tk_end && n > 0;
+        if (!pass) {
             if (lane == 0) { P.rec_end[rec] = -1; P.rec_flags[rec] = 0; P.rec_nm[rec] = -1.0; P.rec_nlead[rec] = 0; }
             continue;
         }
-        int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0;
+        int hp = (r_aux & SNFB_AUX_HP) ? r_hp : 0;
         if (hp > 2) { hp = 0; if (lane == 0) ++soft; }
-        const bool is_supp = r.flag & 2048, rev = r.flag & 16, has_sa = r.aux_flags & SNFB_AUX_SA;
-        const bool use_clips = cfg.detect_large_ins && !is_supp && !has_sa;
-        const double longinslen = (double)cfg.long_ins_length / 2.0;
-        const uint32_t base_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r.mapq << 16);
-        const uint32_t inl_flags = base_flags | ((uint32_t)SNFB_SRC_INLINE << 3) | ((uint32_t)hp << 24) | (is_supp ? SNFB_LF_IS_SA : 0u);
+        const bool is_supp = r_flag & 2048, rev = r_flag & 16, has_sa = r_aux & SNFB_AUX_SA;
+        const uint32_t base_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r_mapq << 16);
         uint64_t qh = 0; bool have_qh = false;
         unsigned nlead = 0;
 
-        // ---- CIGAR stream: 4 ops per lane per iteration, two further slices in flight ----
-        unsigned pos_q = 0; int pos_r = r.pos; unsigned big = 0;
-        for (long long c = c0; c < c_end; c += 128) {
-            const uint4 v = v0; v0 = v1; v1 = v2; v2 = load_chunk(P.cigar, c + 384, lane, c_begin, c_end);
-            const long long i0 = c + lane * 4;
-            uint32_t w[4] = { v.x, v.y, v.z, v.w };
-            unsigned lq = 0, lr = 0; unsigned eq[4], er[4]; bool ev[4]; bool anyev = false;
-            #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const long long gi = i0 + j; const bool valid = gi >= c_begin && gi < c_end;
-                const int op = valid ? (int)(w[j] & 15u) : 6; const unsigned len = valid ? (w[j] >> 4) : 0u;
-                w[j] = (len << 4) | (unsigned)op;
-                eq[j] = lq; er[j] = lr;
-                if (op_adds_read(op)) lq += len;
-                if (op_adds_ref(op)) lr += len;
-                if ((op == 1 || op == 2) && len > 10) big += len;             // get_cigar_indels, minoplen 10
-                ev[j] = op_is_event(op) && (int)len >= cfg.minsvlen_screen;
-                anyev |= ev[j];
+        // ---- CIGAR stream: 4 ops per lane per iteration, two further slices in flight.
+        //      Common path: per-op decode + two warp reductions; the prefix scan runs only when a slice holds a signature. ----
+        unsigned pos_q = 0; int pos_r = r_pos; unsigned big = 0;
+        for (int base = 0; base < n_al; base += 128) {
+            const uint4 v = v0; v0 = v1; v1 = v2; v2 = LOAD_SLICE(base + 384);
+            const int li = base + lane * 4;                               // local index of this lane's first op
+            uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+            // ops outside [mis, n_al) become zero-length pads (op 6 = P adds nothing and is no event)
+            if (li < mis || li + 3 >= n_al) {
+                if (li < mis || li >= n_al) w0 = 6u; if (li + 1 < mis || li + 1 >= n_al) w1 = 6u; if (li + 2 < mis || li + 2 >= n_al) w2 = 6u; if (li + 3 < mis || li + 3 >= n_al) w3 = 6u;
             }
-            unsigned iq = lq, ir = lr;      // inclusive warp scan of the lane totals
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
-            const unsigned lane_q = pos_q + iq - lq; const int lane_r = pos_r + (int)(ir - lr);
-            if (__any_sync(FULL, anyev)) {
-                // which events become leads that stay in the task's region (leadprov.py:464-466)
-                int cnt = 0; bool em[4];
+            unsigned lq = 0, lr = 0, evm = 0;
+            #define OP_STEP(w, bit) { const unsigned op = (w) & 15u, len = (w) >> 4; \
+                lq += len & (0u - ((0x193u >> op) & 1u)); lr += len & (0u - ((0x18Du >> op) & 1u)); \
+                big += (len > 10u && (op == 1u || op == 2u)) ? len : 0u; \
+                evm |= (((0x016u >> op) & 1u) && (int)len >= minsv) ? (bit) : 0u; }
+            OP_STEP(w0, 1u) OP_STEP(w1, 2u) OP_STEP(w2, 4u) OP_STEP(w3, 8u)
+            #undef OP_STEP
+            const unsigned tot_q = __reduce_add_sync(FULL, lq), tot_r = __reduce_add_sync(FULL, lr);
+            if (__any_sync(FULL, evm != 0)) {
+                // rare path: exclusive prefix of (read, ref) advances, then one 64-byte lead per signature inside the region
+                unsigned iq = lq, ir = lr;
                 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    em[j] = false;
-                    if (ev[j]) { const int op = w[j] & 15; const int len = (int)(w[j] >> 4); const int pr = lane_r + (int)er[j];
-                        const int rs = op == 2 ? pr + len : pr; em[j] = rs >= tk.start && rs < tk.end; cnt += em[j]; }
-                }
+                for (int o = 1; o < 32; o <<= 1) { unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
+                unsigned pq = pos_q + iq - lq; int pr = pos_r + (int)(ir - lr);
+                const uint32_t ww[4] = { w0, w1, w2, w3 };
+                int cnt = 0; unsigned emm = 0; { unsigned q2 = 0; int r2 = pr;
+                    #pragma unroll
+                    for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4;
+                        if (evm & (1u << j)) { const int rs = op == 2u ? r2 + (int)len : r2; if (rs >= tk_start && rs < tk_end) { emm |= 1u << j; ++cnt; } }
+                        q2 += len & (0u - ((0x193u >> op) & 1u)); r2 += (int)(len & (0u - ((0x18Du >> op) & 1u))); } (void)q2; }
                 int inc = cnt;
                 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
                 const int total = __shfl_sync(FULL, inc, 31);
                 if (total > 0) {
-                    if (!have_qh) { qh = qname_hash_warp(P.var + r.var_off, r.l_qname); have_qh = true; }
+                    if (!have_qh) { const uint64_t var_off = (uint64_t)__shfl_sync(FULL, wcur, 14) | ((uint64_t)__shfl_sync(FULL, wcur, 15) << 32); qh = qname_hash_warp(P.var + var_off, r_lq); have_qh = true; }
                     unsigned long long slot0 = 0;
                     if (lane == 0) slot0 = atomicAdd(&P.ctr->n_leads, (unsigned long long)total);
                     slot0 = __shfl_sync(FULL, slot0, 0);
                     int mine = inc - cnt;
+                    const bool use_clips = s_cfg.detect_large_ins && !is_supp && !has_sa;
+                    const double longinslen = (double)s_cfg.long_ins_length / 2.0;
+                    const uint32_t inl_flags = base_flags | ((uint32_t)SNFB_SRC_INLINE << 3) | ((uint32_t)hp << 24) | (is_supp ? SNFB_LF_IS_SA : 0u);
                     #pragma unroll
-                    for (int j = 0; j < 4; ++j) if (em[j]) {
-                        const int op = w[j] & 15; const int len = (int)(w[j] >> 4);
-                        const int pq = (int)(lane_q + eq[j]); const int pr = lane_r + (int)er[j];
-                        snfb_lead L;
-                        L.rec = rec; L.qname_hash = qh; L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
-                        L.task = (uint16_t)r.task; L.k = (uint16_t)(nlead + mine);
-                        uint32_t f = inl_flags;
-                        if (op == 1) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pq; L.qry_end = pq + len; L.svlen = len;
-                            if (len <= cfg.dev_seq_cache_maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pq; L.seq_len = len; } }
-                        else if (op == 2) { f |= SNFB_DEL; L.ref_start = pr + len; L.ref_end = pr; L.qry_start = pq; L.qry_end = pq; L.svlen = -len; }
-                        else if (use_clips && (double)len >= longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pq; L.qry_end = pq + len; L.svlen = 0; }
-                        else { f |= (pr == r.pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pq; L.qry_end = pq + len; L.svlen = 0; }
-                        L.flags = f;
-                        const unsigned long long slot = slot0 + (unsigned long long)mine;
-                        if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
-                        ++mine;
+                    for (int j = 0; j < 4; ++j) {
+                        const unsigned op = ww[j] & 15u; const int len = (int)(ww[j] >> 4);
+                        if (emm & (1u << j)) {
+                            snfb_lead L;
+                            L.rec = rec; L.qname_hash = qh; L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
+                            L.task = (uint16_t)r_task; L.k = (uint16_t)(nlead + mine);
+                            uint32_t f = inl_flags; const int pqi = (int)pq;
+                            if (op == 1u) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = len;
+                                if (len <= s_cfg.dev_seq_cache_maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pqi; L.seq_len = len; } }
+                            else if (op == 2u) { f |= SNFB_DEL; L.ref_start = pr + len; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi; L.svlen = -len; }
+                            else if (use_clips && (double)len >= longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = 0; }
+                            else { f |= (pr == r_pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = 0; }
+                            L.flags = f;
+                            const unsigned long long slot = slot0 + (unsigned long long)mine;
+                            if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
+                            ++mine;
+                        }
+                        pq += (unsigned)len & (0u - ((0x193u >> op) & 1u)); pr += (int)((unsigned)len & (0u - ((0x18Du >> op) & 1u)));
                     }
                     nlead += (unsigned)total;
                 }
             }
-            pos_q += __shfl_sync(FULL, iq, 31); pos_r += (int)__shfl_sync(FULL, ir, 31);
+            pos_q += tot_q; pos_r += (int)tot_r;
         }
+        #undef LOAD_SLICE
         const int ref_end = pos_r;
         big = __reduce_add_sync(FULL, big);
         double nm = -1.0; bool has_nm = false;
-        if ((cfg.qc_nm_measure || cfg.phase) && (r.aux_flags & SNFB_AUX_NM)) {      // leadprov.py:517-526
-            nm = __ddiv_rn((double)((long long)r.nm - (long long)big), (double)(alen + 1)); has_nm = true;
+        if ((s_cfg.qc_nm_measure || s_cfg.phase) && (r_aux & SNFB_AUX_NM)) {      // leadprov.py:517-526
+            const int r_nm = (int)__shfl_sync(FULL, wcur, 4);
+            nm = __ddiv_rn((double)((long long)r_nm - (long long)big), (double)(alen + 1)); has_nm = true;
         }
         if (has_sa) {
-            if (!have_qh) { qh = qname_hash_warp(P.var + r.var_off, r.l_qname); have_qh = true; }
+            const uint64_t var_off = (uint64_t)__shfl_sync(FULL, wcur, 14) | ((uint64_t)__shfl_sync(FULL, wcur, 15) << 32);
+            const uint32_t sa_len = __shfl_sync(FULL, wcur, 8);
+            if (!have_qh) { qh = qname_hash_warp(P.var + var_off, r_lq); have_qh = true; }
             unsigned added = 0;
             if (lane == 0) {
                 SaArgs a; a.rec = rec; a.qas = qas; a.qae = qae; a.alen = alen; a.ref_end = ref_end; a.hp = hp; a.base_flags = base_flags; a.qh = qh; a.nlead = nlead; a.rev = rev; a.is_supp = is_supp;
-                added = process_sa(P, r, tk, cg, segs[wib], a, &soft, &overflow);
+                a.sa = P.var + var_off + r_lq; a.sa_len = (int)sa_len; a.c_first = c_first; a.c_last = c_last; a.pos = r_pos; a.l_seq = r_lseq; a.mapq = r_mapq; a.aux_flags = r_aux; a.task = r_task;
+                a.tk_contig = tk_contig; a.tk_start = tk_start; a.tk_end = tk_end; a.contig = P.contig; a.n_contig = P.n_contig; a.leads = P.leads; a.lead_cap = P.lead_cap; a.n_leads = &P.ctr->n_leads;
+                a.mapq_min = mapq_min; a.dev_keep_lowqual_splits = s_cfg.dev_keep_lowqual_splits; a.max_splits_base = s_cfg.max_splits_base; a.max_splits_kb = s_cfg.max_splits_kb;
+                added = process_sa(&s_cfg, segs[wib], a, &soft, &overflow);
             }
             nlead += __shfl_sync(FULL, added, 0);
         }
@@ -385,20 +396,20 @@ __global__ void __launch_bounds__(THREADS, 3) k_extract(const Params P) {
             P.rec_end[rec] = ref_end;
             P.rec_flags[rec] = (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2));
             P.rec_nm[rec] = nm; P.rec_nlead[rec] = nlead;
-            if (acc_task != r.task) {
+            if (acc_task != r_task) {
                 if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
-                acc_task = r.task; acc_reads = 0; acc_bp = 0; acc_span = 0;
+                acc_task = r_task; acc_reads = 0; acc_bp = 0; acc_span = 0;
             }
             ++acc_reads;
-            const int ce = ref_end < tk.contig_len ? ref_end : tk.contig_len;
-            if (ce > r.pos) acc_bp += (unsigned long long)(ce - r.pos);
-            if (ref_end - r.pos > acc_span) acc_span = ref_end - r.pos;
+            const int ce = ref_end < tk_len ? ref_end : tk_len;
+            if (ce > r_pos) acc_bp += (unsigned long long)(ce - r_pos);
+            if (ref_end - r_pos > acc_span) acc_span = ref_end - r_pos;
         }
     }
     if (lane == 0) {
         if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
         if (soft) atomicAdd(&P.ctr->soft_errors, soft);
-        if (unsorted) atomicAdd(&P.ctr->unsorted, unsorted);
+        if (unsorted) atomicAdd(&P.ctr->unsorted, (unsigned long long)unsorted);
     }
     if (overflow) atomicAdd(&P.ctr->lead_overflow, overflow);
 }
