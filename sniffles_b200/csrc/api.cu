@@ -428,8 +428,13 @@ static int run_stage_c(snfb_ctx* ctx) {
     c.alt = ctx->b_alt.as<uint8_t>(); c.scr = ctx->b_scr.as<uint8_t>(); c.alt_cap = ctx->h_ctr.n_alt_bytes; c.scr_cap16 = ctx->h_ctr.n_seq_bytes;
     if (ctx->h_ctr.n_cand) {
         mark(ctx, "consensus", ctx->h_ctr.n_seq_bytes * 16);
-        const unsigned long long nblk = std::min<unsigned long long>(ctx->h_ctr.n_cand, 148ull * 4);
-        consensus::k_run<<<(int)nblk, consensus::THREADS, 0, ctx->st>>>(c); LAUNCHED(ctx, 1);
+        // heavy candidates (long insertions x many reads) first, with 16 warps each; then the bulk with 4 warps each
+        constexpr int NWB = 16, NWS = 4;
+        const size_t smem_b = (size_t)3 * NWB * consensus::MAXHIT * sizeof(int), smem_s = (size_t)3 * NWS * consensus::MAXHIT * sizeof(int);
+        static bool attr_set = false;
+        if (!attr_set) { cudaFuncSetAttribute(consensus::k_run<NWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b); cudaFuncSetAttribute(consensus::k_run<NWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s); attr_set = true; }
+        consensus::k_run<NWB><<<148 * 2, NWB * 32, smem_b, ctx->st>>>(c, 1);
+        consensus::k_run<NWS><<<(int)std::min<unsigned long long>(ctx->h_ctr.n_cand, 148ull * 6), NWS * 32, smem_s, ctx->st>>>(c, 0); LAUNCHED(ctx, 2);
         mark(ctx, nullptr);
     }
     CUDA_TRY(cudaGetLastError());

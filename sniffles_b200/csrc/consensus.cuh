@@ -46,7 +46,7 @@ __global__ void k_plan(C c) {
                 c.cand_rw[i].alt_len = (int)L;
                 // work queue: the heavy tail (long insertions with many reads) is scheduled first
                 const unsigned long long work = (unsigned long long)L * (unsigned long long)nm;
-                if (work > 200000ull) c.work_big[atomicAdd(&c.work_ctr[0], 1u)] = (uint32_t)i; else c.work_small[atomicAdd(&c.work_ctr[1], 1u)] = (uint32_t)i;
+                if (work > 60000ull) c.work_big[atomicAdd(&c.work_ctr[0], 1u)] = (uint32_t)i; else c.work_small[atomicAdd(&c.work_ctr[1], 1u)] = (uint32_t)i;
             }
         }
         c.alt_len[i] = al; c.scr_len[i] = sl;
@@ -102,17 +102,21 @@ __device__ inline void unpack_lead_warp(const C& c, uint32_t cl_index, uint8_t* 
 // order-dependent anchor automaton runs over the compact hit list in shared memory (no memory latency in the
 // serial part), (3) the accepted hits become independent segments that the lanes compare / copy in parallel,
 // (4) dash-free runs are filtered with ballots.  Then one thread per column votes.
-__global__ void __launch_bounds__(THREADS) k_run(C c) {
+// NW warps per block; `big` selects which of the two work lists the launch drains (heavy candidates get wide blocks).
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) k_run(C c, int big) {
+    extern __shared__ int dyn_smem[];
     __shared__ uint32_t t_key[TAB]; __shared__ int t_pos[TAB];      // t_pos: -1 empty, -2 k-mer seen more than once (banned), else its position
-    __shared__ int h_i[THREADS / 32][MAXHIT], h_j[THREADS / 32][MAXHIT], h_cl[THREADS / 32][MAXHIT];
+    int (*h_i)[MAXHIT] = reinterpret_cast<int (*)[MAXHIT]>(dyn_smem);
+    int (*h_j)[MAXHIT] = h_i + NW; int (*h_cl)[MAXHIT] = h_j + NW;
     __shared__ int n_accept; __shared__ uint32_t s_cand;
     const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     static const char CODE[17] = "=ACMGRSVTWYHKDBN";
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) {
-            const uint32_t q = atomicAdd(&c.work_ctr[2], 1u); const uint32_t nb = c.work_ctr[0], ns = c.work_ctr[1];
-            s_cand = q < nb ? c.work_big[q] : (q < nb + ns ? c.work_small[q - nb] : 0xffffffffu);
+            const uint32_t q = atomicAdd(&c.work_ctr[big ? 2 : 3], 1u); const uint32_t nq = c.work_ctr[big ? 0 : 1];
+            s_cand = q < nq ? (big ? c.work_big[q] : c.work_small[q]) : 0xffffffffu;
             n_accept = 0;
         }
         __syncthreads();

@@ -52,3 +52,30 @@ def test_random_shapes(seed):
                          phased_frac=rnd.choice([0.0, 0.5, 1.0]), tr_frac=rnd.choice([0.0, 0.15, 0.6]), ins_only=rnd.random() < 0.2,
                          clip_prob=rnd.choice([0.0, 0.1, 0.5]), lowmapq_prob=rnd.choice([0.05, 0.3]))
     _run(blk, *rnd.choice([(), ("--mosaic",), ("--no-qc",), ("--qc-nm",), ("--cluster-merge-pos", "50")]))
+
+
+@pytest.mark.parametrize("name", ["c1_ont_1mb", "c2_ont_wgs_small", "c3_hifi_mosaic", "c5_ins_heavy", "tr_repeat_noqc", "auto_support_qcnm"])
+def test_device_against_reference_golden(name):
+    """CUDA path -> host epilogue vs what the unmodified reference produced (tests/golden/*.json):
+    lead table, candidates, FILTER / GT / ALT of the finalized calls."""
+    from test_oracle_golden import load_fixture, check_against_golden
+    from test_host_epilogue import check_final
+    from sniffles_b200 import tasks
+    fx, blk = load_fixture(name)
+    cfg = sconfig.default_config(*fx["args"])
+    br = tasks.run_block(blk, cfg, 0)
+    check_against_golden(fx, blk, br.result)
+    check_final(fx, blk, br.result, br.rec_nm, cfg)
+
+
+def test_calltask_surface():
+    """The Task mirror keeps the reference's call sequence (parallel.py:256-271)."""
+    from sniffles_b200 import tasks
+    blk = synth.config_block(1)
+    cfg = sconfig.default_config()
+    br = tasks.run_block(blk, cfg, 0)
+    t = tasks.CallTask(id=0, sv_id=0, contig=blk.contig_names[0], start=0, end=int(blk.task[0]["end"]), config=cfg, block_run=br, task_index=0)
+    calls, read_count = t.execute()
+    assert read_count == int(br.result.task_read_count[0]) and len(calls) > 10
+    assert all(c.qc for c in calls) and calls == sorted(calls, key=lambda c: c.pos)
+    assert {c.svtype for c in calls} >= {"INS", "DEL"}
