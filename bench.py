@@ -32,17 +32,6 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
-def lpt_assign(lengths, n):
-    """contig -> rank by longest-processing-time-first (the reference's unit of parallelism is the contig)."""
-    load = [0] * n
-    owner = [0] * len(lengths)
-    for c in sorted(range(len(lengths)), key=lambda k: -lengths[k]):
-        r = min(range(n), key=lambda k: load[k])
-        owner[c] = r
-        load[r] += lengths[c]
-    return owner
-
-
 def aligned_bp_passing(blk, cfg):
     """sum of query_alignment_length over the records that pass the A2 filters (leadprov.py:494-503)"""
     rec = blk.rec
@@ -186,7 +175,7 @@ def run_reference(args):
 
 def run_b200(args):
     import torch
-    from sniffles_b200 import abi, binding, config as sconfig, synth
+    from sniffles_b200 import abi, binding, config as sconfig, synth, dist as sdist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -203,7 +192,7 @@ def run_b200(args):
     cfg = sconfig.default_config()
     ccfg = abi.Config.from_sniffles(cfg)
     lens = [max(200000, int(x * args.scale)) for x in synth.GRCH38]
-    owner = lpt_assign(lens, world)
+    owner = sdist.lpt_assign(lens, world)
     mask = [o == rank for o in owner] if world > 1 else None
     ncores = os.cpu_count() or 1
     blk = workload(args, mask, max(1, ncores // world))
@@ -220,27 +209,15 @@ def run_b200(args):
     ctx.set_config(ccfg)
     ctx.load(blk)
 
-    class _DevView:
-        """zero-copy torch view of a library-owned device buffer"""
-        def __init__(self, ptr, nbytes):
-            self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 3}
-
     def gather(res):
         """one NCCL all-gather of the per-rank candidate buffers before VCF emission"""
         if world == 1:
             return len(res.cand)
         dptr, n = ctx.device_candidates()
         nbytes = n * abi.CAND_DTYPE.itemsize
-        cnt = torch.tensor([nbytes], device="cuda", dtype=torch.int64)
-        cnts = [torch.zeros_like(cnt) for _ in range(world)]
-        dist.all_gather(cnts, cnt)
-        mx = max(int(c.item()) for c in cnts)
-        mine = torch.zeros(max(mx, 16), dtype=torch.uint8, device="cuda")
-        if nbytes:
-            mine[:nbytes].copy_(torch.as_tensor(_DevView(dptr, nbytes), device="cuda"))
-        outs = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(outs, mine)
-        return sum(int(c.item()) for c in cnts) // abi.CAND_DTYPE.itemsize
+        local = torch.as_tensor(sdist.DeviceBytes(dptr, nbytes), device="cuda") if nbytes else torch.zeros(0, dtype=torch.uint8, device="cuda")
+        parts = sdist.allgather_bytes(local)
+        return sum(p.numel() for p in parts) // abi.CAND_DTYPE.itemsize
 
     def step():
         res = ctx.run(want_leads=False, want_cands=True, want_seqs=True, copy=False)
