@@ -48,13 +48,14 @@ def aligned_bp_passing(blk, cfg):
 
 
 def algorithmic_bytes_stage_a(blk, n_leads, n_pass):
-    """SURVEY.md 8(d): per fetched record 36 + l_qname + 4*n_cigar + aux(SA,NM,HP,PS incl. 3-byte tag headers), read once;
-    writes 64 B per lead + 16 B per passing read."""
+    """SURVEY.md 8(d) for the streaming kernel k_scan: per fetched record 36 + 4*n_cigar + aux(NM,HP,PS incl. 3-byte tag headers), read once
+    (query names and SA text are read by k_emit / k_sa, not by this kernel); writes 16 B per passing read + 32 B per event slice (<= 64 B per lead)."""
     rec = blk.rec
     a = rec["aux_flags"].astype(np.int64)
     aux = ((a & 1) > 0) * 7 + ((a & 2) > 0) * 4 + ((a & 4) > 0) * 7 + ((a & 8) > 0) * (3 + rec["sa_len"].astype(np.int64))
-    rd = int((36 + rec["l_qname"].astype(np.int64) + 4 * rec["n_cigar"].astype(np.int64) + aux).sum())
-    return rd + 64 * int(n_leads) + 16 * int(n_pass), rd
+    aux = ((a & 1) > 0) * 7 + ((a & 2) > 0) * 4 + ((a & 4) > 0) * 7
+    rd = int((36 + 4 * rec["n_cigar"].astype(np.int64) + aux).sum())
+    return rd + 32 * int(n_leads) + 16 * int(n_pass), rd
 
 
 class ClockSampler(threading.Thread):
@@ -282,11 +283,11 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (stage A lead extraction) ----
     full = ctx.run(want_leads=True, want_cands=False, want_seqs=False, copy=False)
     alg, alg_read = algorithmic_bytes_stage_a(blk, len(full.leads), full.n_pass)
-    k_ms = kern.get("k_extract", [0.0, 0])[0] / args.steps
+    k_ms = kern.get("k_scan", [0.0, 0])[0] / args.steps
     peak, peak_src = measured_peak()
     achieved = alg / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
     traffic = ncu_traffic()
-    roof = {"bound": "hbm", "kernel": "extract::k_extract", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+    roof = {"bound": "hbm", "kernel": "extract::k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
             "traffic": traffic.get("dram_bytes_per_launch") if traffic else None}
     if rank == 0:

@@ -51,7 +51,7 @@ struct snfb_ctx {
     const snfb_rec* d_rec = nullptr; const uint32_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
     DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp;
     // stage A outputs
-    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt;
+    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_ev_cnt, b_ev_slot, b_sa_list;
     unsigned long long lead_cap = 0;
     DevCounters h_ctr{};
     // stage B
@@ -114,7 +114,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_ctr, &ctx->b_leads, &ctx->b_rec_pos, &ctx->b_rec_end,
-        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt,
+        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_ev_cnt, &ctx->b_ev_slot, &ctx->b_sa_list,
         &ctx->b_key0, &ctx->b_val0, &ctx->b_key1, &ctx->b_val1, &ctx->b_flag, &ctx->b_scan, &ctx->b_hist, &ctx->b_scan_tmp, &ctx->b_bin_start, &ctx->b_bin_nl, &ctx->b_bin_nlong, &ctx->b_bin_kept,
         &ctx->b_bin_hap, &ctx->b_kl_off, &ctx->b_kll_off, &ctx->b_kb_idx, &ctx->b_kl, &ctx->b_kll, &ctx->b_kb_bin, &ctx->b_kb_lead_off, &ctx->b_kb_lead_n, &ctx->b_kb_long_off, &ctx->b_kb_long_n,
         &ctx->b_kb_seed, &ctx->b_kb_chain, &ctx->b_kb_repeat, &ctx->b_seg_start, &ctx->b_c_next, &ctx->b_c_last, &ctx->b_c_sd, &ctx->b_c_mean, &ctx->b_c_rep, &ctx->b_seg_sd_last, &ctx->b_seg_maxsd,
@@ -247,7 +247,7 @@ static int run_stage_a(snfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     const uint64_t nrec = ctx->n_rec; const uint32_t nt = ctx->n_task;
     for (int attempt = 0; attempt < 3; ++attempt) {
-        if (ctx->lead_cap == 0) ctx->lead_cap = std::max<unsigned long long>(1ull << 16, nrec * 2);
+        if (ctx->lead_cap == 0) ctx->lead_cap = std::max<unsigned long long>(1ull << 16, nrec * 2) + 148ull * 8 * 4 * extract::WARPS * extract::SLOT_CHUNK;
         int bad = ctx->b_ctr.ensure(sizeof(DevCounters)) | ctx->b_leads.ensure(sizeof(snfb_lead) * ctx->lead_cap) | ctx->b_rec_pos.ensure(4 * (nrec + 1)) | ctx->b_rec_end.ensure(4 * (nrec + 1)) | ctx->b_rec_flags.ensure(nrec + 1)
                 | ctx->b_rec_nm.ensure(8 * (nrec + 1)) | ctx->b_rec_nlead.ensure(4 * (nrec + 1)) | ctx->b_rec_lead_off.ensure(4 * (nrec + 1)) | ctx->b_task_first.ensure(4 * nt) | ctx->b_task_last.ensure(4 * nt)
                 | ctx->b_task_reads.ensure(4 * nt) | ctx->b_task_cov.ensure(8 * nt) | ctx->b_task_span.ensure(4 * nt) | ctx->b_task_nm.ensure(8 * nt) | ctx->b_scan_tmp.ensure(4 * (prims::scan_tmp_elems(nrec) + 16));
@@ -255,31 +255,51 @@ static int run_stage_a(snfb_ctx* ctx) {
         CUDA_TRY(cudaMemsetAsync(ctx->b_ctr.p, 0, sizeof(DevCounters), ctx->st));
         CUDA_TRY(cudaMemsetAsync(ctx->b_task_first.p, 0, 4 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_last.p, 0, 4 * nt, ctx->st));
         CUDA_TRY(cudaMemsetAsync(ctx->b_task_reads.p, 0, 4 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_cov.p, 0, 8 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_span.p, 0, 4 * nt, ctx->st));
-        extract::Params P{};
-        P.rec = ctx->d_rec; P.cigar = ctx->d_cigar; P.var = ctx->d_var; P.task = ctx->b_task.as<snfb_task>(); P.contig = ctx->b_contig.as<snfb_contig>();
-        P.n_rec = (uint32_t)nrec; P.n_task = nt; P.n_contig = ctx->n_contig; P.leads = ctx->b_leads.as<snfb_lead>(); P.lead_cap = ctx->lead_cap;
-        P.rec_pos = ctx->b_rec_pos.as<int32_t>(); P.rec_end = ctx->b_rec_end.as<int32_t>(); P.rec_flags = ctx->b_rec_flags.as<uint8_t>(); P.rec_nm = ctx->b_rec_nm.as<double>(); P.rec_nlead = ctx->b_rec_nlead.as<uint32_t>();
-        P.task_first = ctx->b_task_first.as<uint32_t>(); P.task_last = ctx->b_task_last.as<uint32_t>(); P.task_reads = ctx->b_task_reads.as<uint32_t>(); P.task_cov_bp = ctx->b_task_cov.as<unsigned long long>();
-        P.task_maxspan = ctx->b_task_span.as<int32_t>(); P.ctr = ctx->b_ctr.as<DevCounters>(); P.cfg = ctx->cfg;
-        // algorithmic bytes of the lead kernel: record cores + CIGAR + names/SA; lead writes are added after the count is known
-        mark(ctx, "k_extract", sizeof(snfb_rec) * nrec + 4 * ctx->n_cigar + ctx->n_var);
+        const snfb_config& cf = ctx->cfg;
+        if (ctx->b_ev.ensure(sizeof(extract::EvSlice) * ctx->lead_cap) || ctx->b_ev_cnt.ensure(4 * (ctx->lead_cap + 8)) || ctx->b_ev_slot.ensure(4 * (ctx->lead_cap + 8)) || ctx->b_sa_list.ensure(4 * (nrec + 1))
+            || ctx->b_scan_tmp.ensure(4 * (prims::scan_tmp_elems(std::max<unsigned long long>(nrec, ctx->lead_cap)) + 16))) return fail(ctx, "out of device memory (stage A lists)");
+        DevCounters* ctr = ctx->b_ctr.as<DevCounters>();
+        extract::ScanParams S{};
+        S.rec = ctx->d_rec; S.cigar = ctx->d_cigar; S.task = ctx->b_task.as<snfb_task>(); S.n_rec = (uint32_t)nrec;
+        S.rec_end = ctx->b_rec_end.as<int32_t>(); S.rec_flags = ctx->b_rec_flags.as<uint8_t>(); S.rec_nm = ctx->b_rec_nm.as<double>(); S.rec_nlead = ctx->b_rec_nlead.as<uint32_t>();
+        S.task_reads = ctx->b_task_reads.as<uint32_t>(); S.task_cov_bp = ctx->b_task_cov.as<unsigned long long>(); S.task_maxspan = ctx->b_task_span.as<int32_t>();
+        S.ev = ctx->b_ev.as<extract::EvSlice>(); S.ev_cap = ctx->lead_cap; S.n_ev = &ctr->n_ev; S.sa_list = ctx->b_sa_list.as<uint32_t>(); S.n_sa = &ctr->n_sa; S.ctr = ctr;
+        S.minsv = cf.minsvlen_screen; S.mapq_min = cf.mapq; S.alen_min = cf.min_alignment_length; S.excl = cf.exclude_flags; S.want_nm = (cf.qc_nm_measure || cf.phase) ? 1 : 0;
+        uint32_t* task_first = ctx->b_task_first.as<uint32_t>(); uint32_t* task_last = ctx->b_task_last.as<uint32_t>();
+        mark(ctx, "k_rec_index");
         if (nrec) {
-            unsigned long long blocks = (nrec + extract::WARPS - 1) / extract::WARPS; const unsigned long long maxb = 148ull * 8 * 4;
-            extract::k_extract<<<(int)std::min(blocks, maxb), extract::THREADS, 0, ctx->st>>>(P); LAUNCHED(ctx, 2);
+            extract::k_rec_index<<<(unsigned)((nrec + 255) / 256), 256, 0, ctx->st>>>(ctx->d_rec, (uint32_t)nrec, ctx->b_rec_pos.as<int32_t>(), task_first, task_last, ctr);
+            // algorithmic bytes of the streaming kernel: record cores + CIGAR + names/SA
+            mark(ctx, "k_scan", sizeof(snfb_rec) * nrec + 4 * ctx->n_cigar + ctx->n_var);
+            unsigned long long blocks = (nrec + 7) / 8; const unsigned long long maxb = 148ull * 6 * 4;
+            extract::k_scan<<<(int)std::min(blocks, maxb), 256, 0, ctx->st>>>(S);
+            mark(ctx, "k_emit");
+            extract::k_ev_counts<<<grid_for(ctx->lead_cap, 256), 256, 0, ctx->st>>>(S.ev, ctx->b_ev_cnt.as<uint32_t>(), S.n_ev, ctx->lead_cap);
+            LAUNCHED(ctx, 3 + prims::exclusive_scan(ctx->b_ev_cnt.as<uint32_t>(), ctx->b_ev_slot.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->lead_cap, &ctr->n_slots, ctx->st));
+            extract::EmitParams E{};
+            E.rec = ctx->d_rec; E.cigar = ctx->d_cigar; E.var = ctx->d_var; E.task = S.task; E.ev = S.ev; E.ev_slot = ctx->b_ev_slot.as<uint32_t>(); E.n_ev = S.n_ev; E.ev_cap = ctx->lead_cap;
+            E.leads = ctx->b_leads.as<snfb_lead>(); E.lead_cap = ctx->lead_cap; E.ctr = ctr; E.minsv = cf.minsvlen_screen; E.maxlen = cf.dev_seq_cache_maxlen; E.detect_large_ins = cf.detect_large_ins;
+            E.longinslen = (double)cf.long_ins_length / 2.0;
+            extract::k_emit<<<148 * 8, 256, 0, ctx->st>>>(E);
+            mark(ctx, "k_sa");
+            extract::SaParams A{};
+            A.rec = ctx->d_rec; A.cigar = ctx->d_cigar; A.var = ctx->d_var; A.task = S.task; A.contig = ctx->b_contig.as<snfb_contig>(); A.n_contig = ctx->n_contig;
+            A.sa_list = S.sa_list; A.n_sa = S.n_sa; A.rec_end = S.rec_end; A.rec_nlead = S.rec_nlead; A.leads = E.leads; A.lead_cap = ctx->lead_cap; A.ctr = ctr; A.cfg = cf;
+            extract::k_sa<<<148 * 4, extract::THREADS, 0, ctx->st>>>(A);
             mark(ctx, "k_task_nm");
             const int cpt = (int)((nrec + extract::NM_CHUNK - 1) / extract::NM_CHUNK);
             if (ctx->b_nm_part.ensure(8 * (size_t)cpt * nt + 8) || ctx->b_nm_cnt.ensure(4 * (size_t)cpt * nt + 8)) return fail(ctx, "out of device memory (nm partials)");
-            extract::k_nm_partial<<<dim3(cpt, nt), 256, 0, ctx->st>>>(P.rec_flags, P.rec_nm, P.task_first, P.task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>());
-            extract::k_task_nm<<<nt, 256, 0, ctx->st>>>(P.task_first, P.task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>(), cpt, ctx->b_task_nm.as<double>()); LAUNCHED(ctx, 1);
+            extract::k_nm_partial<<<dim3(cpt, nt), 256, 0, ctx->st>>>(S.rec_flags, S.rec_nm, task_first, task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>());
+            extract::k_task_nm<<<nt, 256, 0, ctx->st>>>(task_first, task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>(), cpt, ctx->b_task_nm.as<double>()); LAUNCHED(ctx, 5);
         }
         mark(ctx, "scan_rec_leads");
-        LAUNCHED(ctx, prims::exclusive_scan(P.rec_nlead, ctx->b_rec_lead_off.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, nrec, nullptr, ctx->st));
+        LAUNCHED(ctx, prims::exclusive_scan(S.rec_nlead, ctx->b_rec_lead_off.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, nrec, &ctr->n_leads, ctx->st));
         mark(ctx, nullptr);
         CUDA_TRY(cudaGetLastError());
         if (fetch_counters(ctx)) return 1;
         if (ctx->h_ctr.unsorted) return fail(ctx, "records are not coordinate sorted inside a task");
-        if (ctx->h_ctr.lead_overflow == 0 && ctx->h_ctr.n_leads <= ctx->lead_cap) break;
-        ctx->lead_cap = ctx->h_ctr.n_leads + ctx->h_ctr.n_leads / 4 + 1024;       // retry with a buffer that fits
+        if (ctx->h_ctr.lead_overflow == 0 && ctx->h_ctr.n_slots <= ctx->lead_cap) break;
+        ctx->lead_cap = ctx->h_ctr.n_slots + ctx->h_ctr.n_slots / 4 + 1024;       // retry with a buffer that fits
         ctx->n_ev = ctx->n_ev_load;
         if (attempt == 2) return fail(ctx, "lead buffer overflow");
     }
@@ -289,7 +309,7 @@ static int run_stage_a(snfb_ctx* ctx) {
     const unsigned long long nb = ctx->n_bound; const int g = grid_for(nb, 256);
     if (nb) {
         mark(ctx, "sort_leads", nb * (sizeof(snfb_lead) + 24));
-        cluster::k_scatter_keys<<<g, 256, 0, ctx->st>>>(b);
+        cluster::k_scatter_keys<<<grid_for(ctx->h_ctr.n_slots, 256), 256, 0, ctx->st>>>(b, ctx->h_ctr.n_slots);
         prims::RadixTemp rt{ ctx->b_hist.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>() };
         bool first = true;
         LAUNCHED(ctx, 1 + 3); LAUNCHED(ctx, prims::radix_sort(b.key0, b.val0, b.key1, b.val1, rt, &b.ctr->n_leads, nb, cluster::TASK_SHIFT + bits_for(ctx->n_task), &first, ctx->st));

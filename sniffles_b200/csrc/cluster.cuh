@@ -91,10 +91,10 @@ __device__ __forceinline__ uint64_t bias64(long long v) { return (uint64_t)v ^ 0
 __device__ __forceinline__ long long unbias64(uint64_t v) { return (long long)(v ^ 0x8000000000000000ull); }
 
 // ---------------------------------------------------------------- canonical order + sort keys
-__global__ void k_scatter_keys(B b) {
-    const unsigned long long n = b.ctr->n_leads < b.n_bound ? b.ctr->n_leads : b.n_bound;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+__global__ void k_scatter_keys(B b, unsigned long long n_slots) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_slots; i += (unsigned long long)gridDim.x * blockDim.x) {
         const snfb_lead* l = &b.leads[i];
+        if (l->rec == extract::HOLE) continue;         // unused slot of a retired allocation chunk
         const uint32_t r = b.rec_lead_off[l->rec] + l->k;
         const uint64_t bin = (uint64_t)(l->ref_start / b.cfg.cluster_binsize);
         b.key0[r] = ((uint64_t)l->task << TASK_SHIFT) | ((uint64_t)lf_type(l->flags) << TYPE_SHIFT) | bin;

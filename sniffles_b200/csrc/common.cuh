@@ -13,7 +13,7 @@ typedef unsigned __int128 u128;
 // ---------------------------------------------------------------- device-side run state
 // Counters written by kernels; copied to the host once per stage.
 struct DevCounters {
-    unsigned long long n_leads;        // leads appended by k_extract
+    unsigned long long n_leads;        // number of leads (sum of the per-record counts)
     unsigned long long n_pass;         // reads passing the filters
     unsigned long long soft_errors;    // malformed SA entries etc.
     unsigned long long lead_overflow;  // leads dropped because the lead buffer was full
@@ -21,7 +21,8 @@ struct DevCounters {
     unsigned long long n_bins, n_kbins, n_segs, n_clusters, n_sub, n_cand, n_cand_leads, n_rnames;
     unsigned long long unverified_breaks;
     unsigned long long n_alt_bytes, n_seq_bytes, scratch_overflow;
-    unsigned long long pad[3];
+    unsigned long long n_slots;        // high-water mark of the lead slot allocator (>= n_leads: warps reserve chunks)
+    unsigned long long n_ev, n_sa;     // event slices / records with an SA tag found by k_scan
 };
 
 // ---------------------------------------------------------------- small utilities

@@ -137,13 +137,34 @@ __device__ inline int classify_splits_dev(const snfb_config& cfg, Seg* s, int n,
     return n;
 }
 
+// ---- lead slot allocation.  A single global counter bumped once per lead serialises in L2; instead every warp reserves
+//      SLOT_CHUNK slots at a time and hands them out locally.  Unused slots of a retired chunk are marked as holes
+//      (rec == HOLE) and skipped later; canonical (record, k) order never depended on slot numbers.
+constexpr unsigned SLOT_CHUNK = 64;
+constexpr uint32_t HOLE = 0xffffffffu;
+struct SlotState { unsigned long long cur, end; };
+__device__ __forceinline__ unsigned long long alloc_slots_warp(SlotState& st, unsigned m, snfb_lead* leads, unsigned long long lead_cap, unsigned long long* n_slots) {
+    if (st.cur + m > st.end) {          // warp-uniform
+        for (unsigned long long s = st.cur + lane_id(); s < st.end; s += 32) if (s < lead_cap) leads[s].rec = HOLE;
+        const unsigned chunk = m > SLOT_CHUNK ? m : SLOT_CHUNK;
+        unsigned long long base = 0; if (lane_id() == 0) base = atomicAdd(n_slots, (unsigned long long)chunk);
+        base = __shfl_sync(FULL, base, 0);
+        st.cur = base; st.end = base + chunk;
+    }
+    const unsigned long long r = st.cur; st.cur += m; return r;
+}
+__device__ __forceinline__ unsigned long long alloc_slot_lane(SlotState& st, snfb_lead* leads, unsigned long long lead_cap, unsigned long long* n_slots) {   // one lane only
+    if (st.cur + 1 > st.end) { const unsigned long long base = atomicAdd(n_slots, (unsigned long long)SLOT_CHUNK); st.cur = base; st.end = base + SLOT_CHUNK; }
+    return st.cur++;
+}
+
 // ---- supplementary alignments (SA tag) of one record: Lead.for_bnd + read_itersplits, run by lane 0 ----
 struct SaArgs {
     uint32_t rec; int qas, qae, alen, ref_end, hp; uint32_t base_flags; uint64_t qh; unsigned nlead; bool rev, is_supp;
     // the pieces of Params / snfb_rec / snfb_task the SA path needs, by value (keeps the caller's structs out of local memory)
     const uint8_t* sa; int sa_len; uint32_t c_first, c_last; int pos, l_seq, mapq, aux_flags, task;
     int tk_contig, tk_start, tk_end;
-    const snfb_contig* contig; uint32_t n_contig; snfb_lead* leads; unsigned long long lead_cap; unsigned long long* n_leads;
+    const snfb_contig* contig; uint32_t n_contig; snfb_lead* leads; unsigned long long lead_cap; unsigned long long* n_slots; SlotState* slots;
     int mapq_min, dev_keep_lowqual_splits, max_splits_base; double max_splits_kb;
 };
 __device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp, Seg* sg, const SaArgs a, unsigned long long* soft_p, unsigned long long* overflow_p) {
@@ -184,7 +205,7 @@ __device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp
                     L.nm_sa = (int)sanm; L.task = (uint16_t)r.task; L.k = (uint16_t)(a.nlead + added);
                     L.flags = a.base_flags | SNFB_BND | ((uint32_t)SNFB_SRC_BND_SA << 3) | (is_first ? SNFB_LF_BND_FIRST : 0u) | (is_reverse ? SNFB_LF_BND_REVERSE : 0u)
                               | ((r.aux_flags & SNFB_AUX_NM) ? 0u : SNFB_LF_NM_NONE);
-                    const unsigned long long slot = atomicAdd(a.n_leads, 1ULL);
+                    const unsigned long long slot = alloc_slot_lane(*a.slots, P.leads, P.lead_cap, a.n_slots);
                     if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
                     ++added;
                 }
@@ -231,7 +252,7 @@ __device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp
                         if (sg[i].h_none[h]) f |= SNFB_LF_SVLEN_NONE;
                         if (ty == SNFB_INS && (sg[i].meta & (1 << 20))) { f |= SNFB_LF_HAS_SEQ; L.seq_off = sg[i].seq_off; L.seq_len = sg[i].seq_len; }
                         L.flags = f; L.task = (uint16_t)r.task; L.k = (uint16_t)(a.nlead + added);
-                        const unsigned long long slot = atomicAdd(a.n_leads, 1ULL);
+                        const unsigned long long slot = alloc_slot_lane(*a.slots, P.leads, P.lead_cap, a.n_slots);
                         if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
                         ++added;
                     }
@@ -243,159 +264,143 @@ __device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp
     return added;
 }
 
-__global__ void __launch_bounds__(THREADS, 3) k_extract(const Params P) {
-    __shared__ Seg segs[WARPS][MAXSEG];
-    __shared__ snfb_config s_cfg;
-    if (threadIdx.x < sizeof(snfb_config) / 4) reinterpret_cast<uint32_t*>(&s_cfg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&P.cfg)[threadIdx.x];
-    __syncthreads();
-    const int lane = lane_id(), wib = threadIdx.x >> 5;
-    const unsigned nwarps = gridDim.x * WARPS;
-    const int minsv = P.cfg.minsvlen_screen, mapq_min = P.cfg.mapq, alen_min = P.cfg.min_alignment_length, excl = P.cfg.exclude_flags;
-    // per-warp accumulators flushed when the task changes (records are grouped by task)
-    int acc_task = -1; unsigned acc_reads = 0; unsigned long long acc_bp = 0; int acc_span = 0;
-    unsigned long long soft = 0, overflow = 0; unsigned unsorted = 0;
-    int tk_id = -1, tk_contig = 0, tk_start = 0, tk_end = 0, tk_len = 0;
+// record index: task boundaries, start positions and the coordinate-order check (one thread per record)
+__global__ void __launch_bounds__(256) k_rec_index(const snfb_rec* __restrict__ rec, uint32_t n_rec, int32_t* __restrict__ rec_pos, uint32_t* __restrict__ task_first,
+                                                   uint32_t* __restrict__ task_last, DevCounters* ctr) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x; if (i >= n_rec) return;
+    const int2 tp = __ldg(reinterpret_cast<const int2*>(rec + i));            // (task, pos)
+    rec_pos[i] = tp.y;
+    if (i == 0) task_first[tp.x] = 0;
+    else { const int2 pv = __ldg(reinterpret_cast<const int2*>(rec + i - 1)); if (pv.x != tp.x) { task_first[tp.x] = i; task_last[pv.x] = i; } else if (pv.y > tp.y) atomicAdd(&ctr->unsorted, 1ULL); }
+    if (i + 1 == n_rec) task_last[tp.x] = n_rec;
+}
 
-    unsigned rec = blockIdx.x * WARPS + wib;
-    // software pipeline over records: the next record's 64-byte core is in flight while this one is processed
+// per-op flags for ops 0..7 (M I D N S H P =): bit0 advances the read, bit1 advances the reference
+__device__ __forceinline__ unsigned op_flags(unsigned op) {
+    const unsigned b = __byte_perm(0x02020103u, 0x03000001u, op) & 3u;
+    return op == 8u ? 3u : b;                      // X (only with --eqx) behaves like M
+}
+
+// ================================================================================================
+// Stage A is three kernels:
+//   k_scan  (hot, HBM-bound): one warp per record streams the CIGAR once: filters, reference end, the NM correction,
+//           coverage bookkeeping — and for every 128-op slice that holds an SV signature just one 32-byte "event slice"
+//           entry.  No lead is built here, which keeps the streaming loop small (registers, I-cache).
+//   k_emit  one warp per event slice: reload the slice (L2), prefix positions, write the 64-byte leads to exact slots.
+//   k_sa    one warp per record with an SA tag: Lead.for_bnd + read_itersplits (lane-serial text parsing).
+// ================================================================================================
+struct EvSlice { uint32_t rec; int32_t base; uint32_t pos_q; int32_t pos_r; uint32_t k0; uint32_t count; uint32_t slot0; uint32_t pad; };
+
+struct ScanParams {
+    const snfb_rec* rec; const uint32_t* cigar; const snfb_task* task;
+    uint32_t n_rec;
+    int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
+    uint32_t* task_reads; unsigned long long* task_cov_bp; int32_t* task_maxspan;
+    EvSlice* ev; unsigned long long ev_cap; unsigned long long* n_ev;
+    uint32_t* sa_list; unsigned long long* n_sa;
+    DevCounters* ctr;
+    int minsv, mapq_min, alen_min, excl, want_nm;
+};
+
+// rare path of k_scan: a slice with at least one op longer than 10 that is not a match.  Returns (big << 32) | leads counted.
+__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr,
+                                                      uint32_t rec, int base, unsigned pos_q, int pos_r, unsigned k0, int tk_start, int tk_end) {
+    const int lane = lane_id();
+    const uint32_t ww[4] = { w0, w1, w2, w3 };
+    unsigned big = 0, evm = 0;
+    #pragma unroll
+    for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4;
+        if (len > 10u && (op == 1u || op == 2u)) big += len;                      // get_cigar_indels, minoplen 10
+        if (((0x016u >> op) & 1u) && (int)len >= P->minsv) evm |= 1u << j; }
+    big = __reduce_add_sync(FULL, big);
+    unsigned count = 0;
+    if (__any_sync(FULL, evm != 0)) {
+        unsigned ir = lr;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) ir += tr; }
+        int r2 = pos_r + (int)(ir - lr); unsigned cnt = 0;
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4;
+            if (evm & (1u << j)) { const int rs = op == 2u ? r2 + (int)len : r2; cnt += (rs >= tk_start && rs < tk_end); }
+            r2 += (int)(len * (op_flags(op) >> 1)); }
+        count = __reduce_add_sync(FULL, cnt);
+        if (count && lane == 0) {
+            const unsigned long long e = atomicAdd(P->n_ev, 1ULL);
+            if (e < P->ev_cap) { EvSlice s; s.rec = rec; s.base = base; s.pos_q = pos_q; s.pos_r = pos_r; s.k0 = k0; s.count = count; s.slot0 = 0; s.pad = 0;
+                *reinterpret_cast<uint4*>(&P->ev[e]) = *reinterpret_cast<const uint4*>(&s); *(reinterpret_cast<uint4*>(&P->ev[e]) + 1) = *(reinterpret_cast<const uint4*>(&s) + 1); }
+            else atomicAdd(&P->ctr->lead_overflow, 1ULL);
+        }
+    }
+    return ((unsigned long long)big << 32) | count;
+}
+
+__global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanParams P) {
+    const int lane = lane_id();
+    const unsigned nwarps = gridDim.x * 8;
+    int acc_task = -1; unsigned acc_reads = 0; unsigned long long acc_bp = 0; int acc_span = 0;
+    int tk_id = -1, tk_start = 0, tk_end = 0, tk_len = 0;
+    unsigned rec = blockIdx.x * 8 + (threadIdx.x >> 5);
     uint32_t wnext = (rec < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + rec) + lane) : 0u;
     for (; rec < P.n_rec; rec += nwarps) {
         const uint32_t wcur = wnext;
         { const unsigned nrec2 = rec + nwarps; wnext = (nrec2 < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + nrec2) + lane) : 0u; }
         const int r_task = (int)__shfl_sync(FULL, wcur, 0), r_pos = (int)__shfl_sync(FULL, wcur, 1);
-        const uint32_t x2 = __shfl_sync(FULL, wcur, 2), x3 = __shfl_sync(FULL, wcur, 3);
-        const int r_flag = x2 & 0xffff, r_mapq = (x2 >> 16) & 255, r_aux = x2 >> 24, r_hp = x3 & 255, r_lq = (x3 >> 8) & 255;
+        const uint32_t x2 = __shfl_sync(FULL, wcur, 2);
+        const int r_flag = x2 & 0xffff, r_mapq = (x2 >> 16) & 255, r_aux = x2 >> 24;
         const int n = (int)__shfl_sync(FULL, wcur, 6), r_lseq = (int)__shfl_sync(FULL, wcur, 7);
         const uint64_t cigar_off = (uint64_t)__shfl_sync(FULL, wcur, 10) | ((uint64_t)__shfl_sync(FULL, wcur, 11) << 32);
-        const uint32_t* __restrict__ cg = P.cigar + cigar_off;           // this record's ops
-        const int mis = (int)(cigar_off & 3);                              // ops between the 16-byte boundary and the record's first op
-        const uint32_t* __restrict__ cga = cg - mis;                       // 16-byte aligned
-        const int n_al = n + mis;                                          // local index space [mis, n_al) is the record
-        // issue the first CIGAR slices before anything that depends on them; lane l owns local ops 4l..4l+3 of a 128-op slice
-        #define LOAD_SLICE(base) (((base) + lane * 4 < n_al) ? __ldg(reinterpret_cast<const uint4*>(cga + (base)) + lane) : make_uint4(0, 0, 0, 0))
-        uint4 v0 = LOAD_SLICE(0), v1 = LOAD_SLICE(128), v2 = LOAD_SLICE(256);
+        const uint32_t* __restrict__ cg = P.cigar + cigar_off;
+        const int mis = (int)(cigar_off & 3);
+        const uint4* __restrict__ cga = reinterpret_cast<const uint4*>(cg - mis) + lane;
+        const int n_al = n + mis, li0 = lane * 4;
+        #define LOAD_SLICE(base) (((base) + li0 < n_al) ? __ldg(cga + ((base) >> 2)) : make_uint4(0, 0, 0, 0))
+        uint4 va = LOAD_SLICE(0), vb = LOAD_SLICE(128), vc = LOAD_SLICE(256);
         const uint32_t c_first = n > 0 ? __ldg(cg) : 0u, c_last = n > 0 ? __ldg(cg + n - 1) : 0u;
-        if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_contig = t.contig; tk_start = t.start; tk_end = t.end; tk_len = t.contig_len; }
-        if (lane == 0) {
-            P.rec_pos[rec] = r_pos;
-            if (rec == 0 || P.rec[rec - 1].task != r_task) P.task_first[r_task] = rec;
-            else if (P.rec[rec - 1].pos > r_pos) ++unsorted;
-            if (rec + 1 == P.n_rec || P.rec[rec + 1].task != r_task) P.task_last[r_task] = rec + 1;
-        }
-        // pysam query_alignment_start / _end: leading / trailing soft clips (hard clips are skipped)
+        if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; tk_len = t.contig_len; }
         int qas = 0, qae = r_lseq;
         { int op = c_first & 15; if (op == 4) qas = (int)(c_first >> 4);
           if (op == 4 || op == 5) for (int k = 1; k < n; ++k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qas += (int)(c >> 4); else if (o2 != 5) break; } }
         if (n > 1) { int op = c_last & 15; if (op == 4) qae -= (int)(c_last >> 4);
           if (op == 4 || op == 5) for (int k = n - 2; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qae -= (int)(c >> 4); else if (o2 != 5) break; } }
         const int alen = qae - qas;
-        bool pass = !(r_mapq < mapq_min || (r_flag & 256) || alen < alen_min) && !(excl && (r_flag & excl)) && r_pos >= tk_start && r_pos < tk_end && n > 0;
+        const bool pass = !(r_mapq < P.mapq_min || (r_flag & 256) || alen < P.alen_min) && !(P.excl && (r_flag & P.excl)) && r_pos >= tk_start && r_pos < tk_end && n > 0;
         if (!pass) {
             if (lane == 0) { P.rec_end[rec] = -1; P.rec_flags[rec] = 0; P.rec_nm[rec] = -1.0; P.rec_nlead[rec] = 0; }
             continue;
         }
-        int hp = (r_aux & SNFB_AUX_HP) ? r_hp : 0;
-        if (hp > 2) { hp = 0; if (lane == 0) ++soft; }
-        const bool is_supp = r_flag & 2048, rev = r_flag & 16, has_sa = r_aux & SNFB_AUX_SA;
-        const uint32_t base_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r_mapq << 16);
-        uint64_t qh = 0; bool have_qh = false;
-        unsigned nlead = 0;
-
-        // ---- CIGAR stream: 4 ops per lane per iteration, two further slices in flight.
-        //      Common path: per-op decode + two warp reductions; the prefix scan runs only when a slice holds a signature. ----
-        unsigned pos_q = 0; int pos_r = r_pos; unsigned big = 0;
-        for (int base = 0; base < n_al; base += 128) {
-            const uint4 v = v0; v0 = v1; v1 = v2; v2 = LOAD_SLICE(base + 384);
-            const int li = base + lane * 4;                               // local index of this lane's first op
-            uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
-            // ops outside [mis, n_al) become zero-length pads (op 6 = P adds nothing and is no event)
-            if (li < mis || li + 3 >= n_al) {
-                if (li < mis || li >= n_al) w0 = 6u; if (li + 1 < mis || li + 1 >= n_al) w1 = 6u; if (li + 2 < mis || li + 2 >= n_al) w2 = 6u; if (li + 3 < mis || li + 3 >= n_al) w3 = 6u;
-            }
-            unsigned lq = 0, lr = 0, evm = 0;
-            #define OP_STEP(w, bit) { const unsigned op = (w) & 15u, len = (w) >> 4; \
-                lq += len & (0u - ((0x193u >> op) & 1u)); lr += len & (0u - ((0x18Du >> op) & 1u)); \
-                big += (len > 10u && (op == 1u || op == 2u)) ? len : 0u; \
-                evm |= (((0x016u >> op) & 1u) && (int)len >= minsv) ? (bit) : 0u; }
-            OP_STEP(w0, 1u) OP_STEP(w1, 2u) OP_STEP(w2, 4u) OP_STEP(w3, 8u)
-            #undef OP_STEP
-            const unsigned tot_q = __reduce_add_sync(FULL, lq), tot_r = __reduce_add_sync(FULL, lr);
-            if (__any_sync(FULL, evm != 0)) {
-                // rare path: exclusive prefix of (read, ref) advances, then one 64-byte lead per signature inside the region
-                unsigned iq = lq, ir = lr;
-                #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
-                unsigned pq = pos_q + iq - lq; int pr = pos_r + (int)(ir - lr);
-                const uint32_t ww[4] = { w0, w1, w2, w3 };
-                int cnt = 0; unsigned emm = 0; { unsigned q2 = 0; int r2 = pr;
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4;
-                        if (evm & (1u << j)) { const int rs = op == 2u ? r2 + (int)len : r2; if (rs >= tk_start && rs < tk_end) { emm |= 1u << j; ++cnt; } }
-                        q2 += len & (0u - ((0x193u >> op) & 1u)); r2 += (int)(len & (0u - ((0x18Du >> op) & 1u))); } (void)q2; }
-                int inc = cnt;
-                #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-                const int total = __shfl_sync(FULL, inc, 31);
-                if (total > 0) {
-                    if (!have_qh) { const uint64_t var_off = (uint64_t)__shfl_sync(FULL, wcur, 14) | ((uint64_t)__shfl_sync(FULL, wcur, 15) << 32); qh = qname_hash_warp(P.var + var_off, r_lq); have_qh = true; }
-                    unsigned long long slot0 = 0;
-                    if (lane == 0) slot0 = atomicAdd(&P.ctr->n_leads, (unsigned long long)total);
-                    slot0 = __shfl_sync(FULL, slot0, 0);
-                    int mine = inc - cnt;
-                    const bool use_clips = s_cfg.detect_large_ins && !is_supp && !has_sa;
-                    const double longinslen = (double)s_cfg.long_ins_length / 2.0;
-                    const uint32_t inl_flags = base_flags | ((uint32_t)SNFB_SRC_INLINE << 3) | ((uint32_t)hp << 24) | (is_supp ? SNFB_LF_IS_SA : 0u);
-                    #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const unsigned op = ww[j] & 15u; const int len = (int)(ww[j] >> 4);
-                        if (emm & (1u << j)) {
-                            snfb_lead L;
-                            L.rec = rec; L.qname_hash = qh; L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
-                            L.task = (uint16_t)r_task; L.k = (uint16_t)(nlead + mine);
-                            uint32_t f = inl_flags; const int pqi = (int)pq;
-                            if (op == 1u) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = len;
-                                if (len <= s_cfg.dev_seq_cache_maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pqi; L.seq_len = len; } }
-                            else if (op == 2u) { f |= SNFB_DEL; L.ref_start = pr + len; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi; L.svlen = -len; }
-                            else if (use_clips && (double)len >= longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = 0; }
-                            else { f |= (pr == r_pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = 0; }
-                            L.flags = f;
-                            const unsigned long long slot = slot0 + (unsigned long long)mine;
-                            if (slot < P.lead_cap) store_lead(P.leads + slot, L); else ++overflow;
-                            ++mine;
-                        }
-                        pq += (unsigned)len & (0u - ((0x193u >> op) & 1u)); pr += (int)((unsigned)len & (0u - ((0x18Du >> op) & 1u)));
-                    }
-                    nlead += (unsigned)total;
-                }
-            }
-            pos_q += tot_q; pos_r += (int)tot_r;
+        unsigned pos_q = 0; int pos_r = r_pos; unsigned big = 0, nlead = 0;
+        #define SLICE_BODY(v, base) { \
+            const int li = (base) + li0; \
+            uint32_t w0 = (v).x, w1 = (v).y, w2 = (v).z, w3 = (v).w; \
+            if (li < mis || li + 3 >= n_al) { \
+                if (li < mis || li >= n_al) w0 = 6u; if (li + 1 < mis || li + 1 >= n_al) w1 = 6u; if (li + 2 < mis || li + 2 >= n_al) w2 = 6u; if (li + 3 < mis || li + 3 >= n_al) w3 = 6u; } \
+            unsigned lq = 0, lr = 0; bool rare = false; \
+            { const unsigned op = w0 & 15u, len = w0 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); } \
+            { const unsigned op = w1 & 15u, len = w1 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); } \
+            { const unsigned op = w2 & 15u, len = w2 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); } \
+            { const unsigned op = w3 & 15u, len = w3 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); } \
+            const unsigned tot_q = __reduce_add_sync(FULL, lq), tot_r = __reduce_add_sync(FULL, lr); \
+            if (__any_sync(FULL, rare)) { const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, rec, (base), pos_q, pos_r, nlead, tk_start, tk_end); \
+                big += (unsigned)(rr >> 32); nlead += (unsigned)rr; } \
+            pos_q += tot_q; pos_r += (int)tot_r; }
+        for (int base = 0; base < n_al; base += 384) {
+            { const uint4 v = va; va = LOAD_SLICE(base + 384); SLICE_BODY(v, base) }
+            if (base + 128 < n_al) { const uint4 v = vb; vb = LOAD_SLICE(base + 512); SLICE_BODY(v, base + 128) }
+            if (base + 256 < n_al) { const uint4 v = vc; vc = LOAD_SLICE(base + 640); SLICE_BODY(v, base + 256) }
         }
+        #undef SLICE_BODY
         #undef LOAD_SLICE
         const int ref_end = pos_r;
-        big = __reduce_add_sync(FULL, big);
-        double nm = -1.0; bool has_nm = false;
-        if ((s_cfg.qc_nm_measure || s_cfg.phase) && (r_aux & SNFB_AUX_NM)) {      // leadprov.py:517-526
-            const int r_nm = (int)__shfl_sync(FULL, wcur, 4);
-            nm = __ddiv_rn((double)((long long)r_nm - (long long)big), (double)(alen + 1)); has_nm = true;
-        }
-        if (has_sa) {
-            const uint64_t var_off = (uint64_t)__shfl_sync(FULL, wcur, 14) | ((uint64_t)__shfl_sync(FULL, wcur, 15) << 32);
-            const uint32_t sa_len = __shfl_sync(FULL, wcur, 8);
-            if (!have_qh) { qh = qname_hash_warp(P.var + var_off, r_lq); have_qh = true; }
-            unsigned added = 0;
-            if (lane == 0) {
-                SaArgs a; a.rec = rec; a.qas = qas; a.qae = qae; a.alen = alen; a.ref_end = ref_end; a.hp = hp; a.base_flags = base_flags; a.qh = qh; a.nlead = nlead; a.rev = rev; a.is_supp = is_supp;
-                a.sa = P.var + var_off + r_lq; a.sa_len = (int)sa_len; a.c_first = c_first; a.c_last = c_last; a.pos = r_pos; a.l_seq = r_lseq; a.mapq = r_mapq; a.aux_flags = r_aux; a.task = r_task;
-                a.tk_contig = tk_contig; a.tk_start = tk_start; a.tk_end = tk_end; a.contig = P.contig; a.n_contig = P.n_contig; a.leads = P.leads; a.lead_cap = P.lead_cap; a.n_leads = &P.ctr->n_leads;
-                a.mapq_min = mapq_min; a.dev_keep_lowqual_splits = s_cfg.dev_keep_lowqual_splits; a.max_splits_base = s_cfg.max_splits_base; a.max_splits_kb = s_cfg.max_splits_kb;
-                added = process_sa(&s_cfg, segs[wib], a, &soft, &overflow);
-            }
-            nlead += __shfl_sync(FULL, added, 0);
-        }
+        int hp = (r_aux & SNFB_AUX_HP) ? (int)(__shfl_sync(FULL, wcur, 3) & 255u) : 0;
+        if (hp > 2) { hp = 0; if (lane == 0) atomicAdd(&P.ctr->soft_errors, 1ULL); }
+        const bool has_nm = P.want_nm && (r_aux & SNFB_AUX_NM);
+        const int r_nm = (int)__shfl_sync(FULL, wcur, 4);
         if (lane == 0) {
             P.rec_end[rec] = ref_end;
             P.rec_flags[rec] = (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2));
-            P.rec_nm[rec] = nm; P.rec_nlead[rec] = nlead;
+            P.rec_nm[rec] = has_nm ? __ddiv_rn((double)((long long)r_nm - (long long)big), (double)(alen + 1)) : -1.0;      // leadprov.py:517-526
+            P.rec_nlead[rec] = nlead;
+            if (r_aux & SNFB_AUX_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = rec; }
             if (acc_task != r_task) {
                 if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
                 acc_task = r_task; acc_reads = 0; acc_bp = 0; acc_span = 0;
@@ -406,12 +411,134 @@ __global__ void __launch_bounds__(THREADS, 3) k_extract(const Params P) {
             if (ref_end - r_pos > acc_span) acc_span = ref_end - r_pos;
         }
     }
-    if (lane == 0) {
-        if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
-        if (soft) atomicAdd(&P.ctr->soft_errors, soft);
-        if (unsorted) atomicAdd(&P.ctr->unsorted, (unsigned long long)unsorted);
+    if (lane == 0 && acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
+}
+
+// exact lead slots of the event slices: exclusive prefix of their counts (slices of one record keep their order through k0)
+__global__ void k_ev_counts(const EvSlice* __restrict__ ev, uint32_t* __restrict__ cnt, const unsigned long long* __restrict__ n_ev, unsigned long long bound) {
+    const unsigned long long n = *n_ev < bound ? *n_ev : bound;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < bound; i += (unsigned long long)gridDim.x * blockDim.x) cnt[i] = i < n ? ev[i].count : 0u;
+}
+
+struct EmitParams {
+    const snfb_rec* rec; const uint32_t* cigar; const uint8_t* var; const snfb_task* task;
+    const EvSlice* ev; const uint32_t* ev_slot; const unsigned long long* n_ev; unsigned long long ev_cap;
+    snfb_lead* leads; unsigned long long lead_cap; DevCounters* ctr;
+    int minsv, maxlen, detect_large_ins; double longinslen;
+};
+// one warp per event slice: read_iterindels' lead construction (leadprov.py:583-670)
+__global__ void __launch_bounds__(256) k_emit(const EmitParams P) {
+    const int lane = lane_id();
+    const unsigned long long n = *P.n_ev < P.ev_cap ? *P.n_ev : P.ev_cap;
+    const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long e = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += nw) {
+        const EvSlice s = P.ev[e];
+        const snfb_rec r = P.rec[s.rec];
+        const snfb_task tk = P.task[r.task];
+        const uint32_t* cg = P.cigar + r.cigar_off; const int n_ops = (int)r.n_cigar;
+        const int mis = (int)(r.cigar_off & 3); const int n_al = n_ops + mis;
+        const int li = s.base + lane * 4;
+        uint4 v = (li < n_al) ? __ldg(reinterpret_cast<const uint4*>(cg - mis) + (s.base >> 2) + lane) : make_uint4(0, 0, 0, 0);
+        uint32_t ww[4] = { v.x, v.y, v.z, v.w };
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) if (li + j < mis || li + j >= n_al) ww[j] = 6u;
+        unsigned lq = 0, lr = 0, evm = 0;
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1);
+            if (((0x016u >> op) & 1u) && (int)len >= P.minsv) evm |= 1u << j; }
+        unsigned iq = lq, ir = lr;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
+        unsigned pq = s.pos_q + iq - lq; int pr = s.pos_r + (int)(ir - lr);
+        // which signatures stay inside the task's region (leadprov.py:464-466), and their rank inside the slice
+        unsigned emm = 0; int cnt = 0; { int r2 = pr;
+            #pragma unroll
+            for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4;
+                if (evm & (1u << j)) { const int rs = op == 2u ? r2 + (int)len : r2; if (rs >= tk.start && rs < tk.end) { emm |= 1u << j; ++cnt; } }
+                r2 += (int)(len * (op_flags(op) >> 1)); } }
+        int inc = cnt;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        int mine = inc - cnt;
+        // per-record facts
+        int qas = 0, qae = r.l_seq;
+        for (int k = 0; k < n_ops; ++k) { const uint32_t c = __ldg(cg + k); const int op = c & 15; if (op == 4) qas += (int)(c >> 4); else if (op != 5) break; }
+        for (int k = n_ops - 1; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int op = c & 15; if (op == 4) qae -= (int)(c >> 4); else if (op != 5) break; }
+        const int alen = qae - qas;
+        const bool is_supp = r.flag & 2048, rev = r.flag & 16, has_sa = r.aux_flags & SNFB_AUX_SA;
+        int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0; if (hp > 2) hp = 0;
+        const bool use_clips = P.detect_large_ins && !is_supp && !has_sa;
+        const uint32_t inl_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r.mapq << 16) | ((uint32_t)SNFB_SRC_INLINE << 3) | ((uint32_t)hp << 24) | (is_supp ? SNFB_LF_IS_SA : 0u);
+        const uint64_t qh = qname_hash_warp(P.var + r.var_off, r.l_qname);
+        const unsigned long long slot0 = P.ev_slot[e];
+        #pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const unsigned op = ww[j] & 15u; const int len = (int)(ww[j] >> 4); const unsigned fl = op_flags(op);
+            if (emm & (1u << j)) {
+                snfb_lead L;
+                L.rec = s.rec; L.qname_hash = qh; L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
+                L.task = (uint16_t)r.task; L.k = (uint16_t)(s.k0 + mine);
+                uint32_t f = inl_flags; const int pqi = (int)pq;
+                if (op == 1u) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = len;
+                    if (len <= P.maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pqi; L.seq_len = len; } }
+                else if (op == 2u) { f |= SNFB_DEL; L.ref_start = pr + len; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi; L.svlen = -len; }
+                else if (use_clips && (double)len >= P.longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = 0; }
+                else { f |= (pr == r.pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = 0; }
+                L.flags = f;
+                const unsigned long long slot = slot0 + (unsigned long long)mine;
+                if (slot < P.lead_cap) store_lead(P.leads + slot, L); else atomicAdd(&P.ctr->lead_overflow, 1ULL);
+                ++mine;
+            }
+            pq += (unsigned)len * (fl & 1u); pr += (int)((unsigned)len * (fl >> 1));
+        }
     }
-    if (overflow) atomicAdd(&P.ctr->lead_overflow, overflow);
+}
+
+struct SaParams {
+    const snfb_rec* rec; const uint32_t* cigar; const uint8_t* var; const snfb_task* task; const snfb_contig* contig; uint32_t n_contig;
+    const uint32_t* sa_list; const unsigned long long* n_sa; const int32_t* rec_end; uint32_t* rec_nlead;
+    snfb_lead* leads; unsigned long long lead_cap; DevCounters* ctr;
+    snfb_config cfg;
+};
+// one warp per record with an SA tag (lane 0 parses; the warp hashes the name)
+__global__ void __launch_bounds__(THREADS) k_sa(const SaParams P) {
+    __shared__ Seg segs[WARPS][MAXSEG];
+    __shared__ snfb_config s_cfg;
+    if (threadIdx.x < sizeof(snfb_config) / 4) reinterpret_cast<uint32_t*>(&s_cfg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&P.cfg)[threadIdx.x];
+    __syncthreads();
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    const unsigned long long n = *P.n_sa;
+    const unsigned long long nw = (unsigned long long)gridDim.x * WARPS;
+    unsigned long long soft = 0, overflow = 0;
+    SlotState slots; slots.cur = 0; slots.end = 0;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS + wib; e < n; e += nw) {
+        const uint32_t rec = P.sa_list[e];
+        const snfb_rec r = P.rec[rec];
+        const snfb_task tk = P.task[r.task];
+        const uint32_t* cg = P.cigar + r.cigar_off; const int n_ops = (int)r.n_cigar;
+        int qas = 0, qae = r.l_seq;
+        for (int k = 0; k < n_ops; ++k) { const uint32_t c = __ldg(cg + k); const int op = c & 15; if (op == 4) qas += (int)(c >> 4); else if (op != 5) break; }
+        for (int k = n_ops - 1; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int op = c & 15; if (op == 4) qae -= (int)(c >> 4); else if (op != 5) break; }
+        const uint64_t qh = qname_hash_warp(P.var + r.var_off, r.l_qname);
+        if (lane == 0) {
+            int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0; if (hp > 2) hp = 0;
+            const bool rev = r.flag & 16;
+            SaArgs a; a.rec = rec; a.qas = qas; a.qae = qae; a.alen = qae - qas; a.ref_end = P.rec_end[rec]; a.hp = hp;
+            a.base_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r.mapq << 16); a.qh = qh; a.nlead = P.rec_nlead[rec]; a.rev = rev; a.is_supp = r.flag & 2048;
+            a.sa = P.var + r.var_off + r.l_qname; a.sa_len = (int)r.sa_len; a.c_first = __ldg(cg); a.c_last = __ldg(cg + n_ops - 1); a.pos = r.pos; a.l_seq = r.l_seq; a.mapq = r.mapq;
+            a.aux_flags = r.aux_flags; a.task = r.task; a.tk_contig = tk.contig; a.tk_start = tk.start; a.tk_end = tk.end; a.contig = P.contig; a.n_contig = P.n_contig;
+            a.leads = P.leads; a.lead_cap = P.lead_cap; a.n_slots = &P.ctr->n_slots; a.slots = &slots;
+            a.mapq_min = s_cfg.mapq; a.dev_keep_lowqual_splits = s_cfg.dev_keep_lowqual_splits; a.max_splits_base = s_cfg.max_splits_base; a.max_splits_kb = s_cfg.max_splits_kb;
+            const unsigned added = process_sa(&s_cfg, segs[wib], a, &soft, &overflow);
+            if (added) P.rec_nlead[rec] += added;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        for (unsigned long long sidx = slots.cur; sidx < slots.end; ++sidx) if (sidx < P.lead_cap) P.leads[sidx].rec = HOLE;   // retire the last chunk
+        if (soft) atomicAdd(&P.ctr->soft_errors, soft);
+        if (overflow) atomicAdd(&P.ctr->lead_overflow, overflow);
+    }
 }
 
 // deterministic per-task mean of the per-read nm values (config.average_regional_nm, leadprov.py:577).
