@@ -266,12 +266,14 @@ def run_b200(args):
 
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H every step) ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    h2d = blk.rec.nbytes + blk.cigar.nbytes + blk.var.nbytes + blk.seq.nbytes
+    full_bytes = blk.rec.nbytes + blk.cigar.nbytes + blk.var.nbytes + blk.seq.nbytes
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.load(blk)
+        ctx.load(blk, seq_on_demand=not args.e2e_full_seq)      # host arenas; the 4-bit seq arena is fetched on demand (slices only)
         res, n_all = step()
+    slice_bytes = sum(by for name, ms, by in ctx.timings() if name == "h2d_seq_slices")
+    h2d = blk.rec.nbytes + blk.cigar.nbytes + blk.var.nbytes + (blk.seq.nbytes if args.e2e_full_seq else slice_bytes)
     barrier()
     e2e_wall = (time.perf_counter() - t0) / e2e_steps
     d2h = res.cand.nbytes + res.cand_leads.nbytes + res.rnames.nbytes + res.alt.nbytes
@@ -281,6 +283,7 @@ def run_b200(args):
     e2e_val = abp_total / float(et[0]) / 1e9
 
     # ---- roofline of the dominant kernel (stage A lead extraction) ----
+    ctx.load(blk)
     full = ctx.run(want_leads=True, want_cands=False, want_seqs=False, copy=False)
     alg, alg_read = algorithmic_bytes_stage_a(blk, len(full.leads), full.n_pass)
     k_ms = kern.get("k_scan", [0.0, 0])[0] / args.steps
@@ -296,10 +299,10 @@ def run_b200(args):
                "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                "config": {"workload": f"BASELINE config {args.config}: synthetic 30x ONT WGS, 24 GRCh38-length contigs x scale {args.scale}, {abp_total / 1e9:.2f} Gbp aligned, germline",
                           "records_rank0": int(len(blk.rec)), "candidates_total": int(n_all), "parallelism": f"contig LPT over {world} GPU(s), one NCCL all-gather of candidates",
-                          "l2": f"inputs {h2d / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed"},
+                          "l2": f"inputs {full_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed"},
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": float(et[0]) * 1e3,
-                       "pinned": bool(pinned)},
+                       "pinned": bool(pinned), "seq": "full arena" if args.e2e_full_seq else "on demand (slices requested by the device, gathered on the host)"},
                "roofline": roof, "stage_ms": {k: v[0] / args.steps for k, v in kern.items()}}
         if world == 1 and not args.no_cpu:
             info, _, _ = cpu_sample(blk, cfg, ccfg, ncores, target_bp=args.cpu_sample_gbp * 1e9)
@@ -323,6 +326,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-gbp", type=float, default=6.0)
     ap.add_argument("--no-pin", action="store_true")
+    ap.add_argument("--e2e-full-seq", action="store_true", help="e2e: copy the whole seq arena every step instead of the on-demand slices")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

@@ -43,6 +43,11 @@ enum { SNFB_INS = 0, SNFB_DEL = 1, SNFB_DUP = 2, SNFB_INV = 3, SNFB_BND = 4,
 /* Lead.source (leadprov.py:46) */
 enum { SNFB_SRC_INLINE = 0, SNFB_SRC_SPLIT_PRIM = 1, SNFB_SRC_SPLIT_SUP = 2, SNFB_SRC_BND_SA = 3 };
 
+/* snfb_records.on_device */
+#define SNFB_MEM_HOST 0u
+#define SNFB_MEM_DEVICE 1u
+#define SNFB_MEM_HOST_SEQ_ON_DEMAND 2u
+
 /* aux_flags bits of snfb_rec */
 #define SNFB_AUX_NM 1u
 #define SNFB_AUX_HP 2u
@@ -111,7 +116,8 @@ typedef struct snfb_records {
     uint32_t n_task;
     uint32_t n_contig;
     uint32_t n_tr;
-    uint32_t on_device;   /* 1: the five arenas above are device pointers (no copy)    */
+    uint32_t on_device;   /* SNFB_MEM_*: 0 host arenas (copied), 1 device arenas (no copy), 2 host arenas with the seq arena
+                             left on the host: only the base slices the consensus stage asks for are fetched ("seq on demand") */
     const snfb_task*   task;
     const snfb_contig* contig;
     const int32_t*     tr;    /* n_tr pairs (start,end), per task sorted (util.py:121-147) */

@@ -108,9 +108,12 @@ class Context:
     def set_config(self, cfg: abi.Config):
         self._check(self._lib.snfb_set_config(self._h, C.byref(cfg)), "snfb_set_config")
 
-    def load(self, block):
-        """block: sniffles_b200.synth.RecordBlock-like (numpy arenas) or an abi.Records struct."""
+    def load(self, block, seq_on_demand=False):
+        """block: sniffles_b200.synth.RecordBlock-like (numpy arenas) or an abi.Records struct.
+        seq_on_demand: leave the 4-bit seq arena on the host and fetch only the slices the consensus stage needs."""
         rs = block if isinstance(block, abi.Records) else block.as_struct()
+        if seq_on_demand:
+            rs.on_device = 2
         self._block = block          # keep host arrays alive during the async copy
         self._check(self._lib.snfb_load_records(self._h, C.byref(rs)), "snfb_load_records")
 

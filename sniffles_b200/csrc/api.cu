@@ -46,7 +46,7 @@ struct snfb_ctx {
     int device = 0; cudaStream_t st = nullptr; std::string err;
     snfb_config cfg{}; bool have_cfg = false;
     // records
-    bool loaded = false, on_device = false;
+    bool loaded = false, on_device = false, seq_on_demand = false; const uint8_t* h_seq = nullptr;
     uint64_t n_rec = 0, n_cigar = 0, n_var = 0, n_seq = 0; uint32_t n_task = 0, n_contig = 0, n_tr = 0;
     const snfb_rec* d_rec = nullptr; const uint32_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
     DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp;
@@ -65,7 +65,8 @@ struct snfb_ctx {
     unsigned long long n_bound = 0, cand_cap = 0, cand_lead_cap = 0, rn_cap = 0;
     bool sorted_in_first = true, stage_a_done = false, stage_b_done = false;
     // stage C
-    DevBuf b_plan_best, b_plan_nother, b_alt_len, b_scr_len, b_alt_off, b_scr_off, b_alt, b_scr, b_sorted_leads, b_work_big, b_work_small, b_work_ctr;
+    DevBuf b_plan_best, b_plan_nother, b_alt_len, b_scr_len, b_alt_off, b_scr_off, b_alt, b_scr, b_sorted_leads, b_work_big, b_work_small, b_work_ctr, b_seq_req, b_arena_off, b_seq_arena;
+    HostBuf h_seq_req, h_seq_arena; uint64_t seq_h2d_bytes = 0;
     // host staging
     HostBuf h_leads, h_task_reads, h_task_nm, h_rec_nm, h_cand, h_cand_leads, h_rnames, h_rn_off, h_task_cov, h_alt;
     std::vector<double> task_cov_mean; std::vector<snfb_task> tasks;
@@ -122,9 +123,9 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
         &ctx->b_ml_seqlen, &ctx->b_ml_plo, &ctx->b_ml_pn, &ctx->b_ml_has, &ctx->b_subl, &ctx->b_sub_cnt, &ctx->b_sub_off, &ctx->b_t_lo, &ctx->b_t_n, &ctx->b_t_bin, &ctx->b_sub_cluster, &ctx->b_sub_lo,
         &ctx->b_sub_n, &ctx->b_sub_bin, &ctx->b_cand_tmp, &ctx->b_cand_valid, &ctx->b_cand_id, &ctx->b_cand_nlead, &ctx->b_cand_lead_off, &ctx->b_cand_nrn, &ctx->b_cand_rn_off, &ctx->b_cand,
         &ctx->b_cand_leads, &ctx->b_cand_lead_ml, &ctx->b_rnames, &ctx->b_rn_off_out, &ctx->b_plan_best, &ctx->b_plan_nother, &ctx->b_alt_len, &ctx->b_scr_len, &ctx->b_alt_off, &ctx->b_scr_off,
-        &ctx->b_alt, &ctx->b_scr, &ctx->b_sorted_leads, &ctx->b_work_big, &ctx->b_work_small, &ctx->b_work_ctr };
+        &ctx->b_alt, &ctx->b_scr, &ctx->b_sorted_leads, &ctx->b_work_big, &ctx->b_work_small, &ctx->b_work_ctr, &ctx->b_seq_req, &ctx->b_arena_off, &ctx->b_seq_arena };
     for (DevBuf* b : bufs) b->release();
-    HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt };
+    HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt, &ctx->h_seq_req, &ctx->h_seq_arena };
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaStreamDestroy(ctx->st);
@@ -147,18 +148,18 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     if (R->n_task == 0 || R->n_task > 65535) return fail(ctx, "n_task must be in 1..65535");
     if (R->n_rec > 0xfffffff0ull) return fail(ctx, "too many records in one block");
     ctx->n_rec = R->n_rec; ctx->n_cigar = R->n_cigar; ctx->n_var = R->n_var; ctx->n_seq = R->n_seq;
-    ctx->n_task = R->n_task; ctx->n_contig = R->n_contig; ctx->n_tr = R->n_tr; ctx->on_device = R->on_device != 0;
+    ctx->n_task = R->n_task; ctx->n_contig = R->n_contig; ctx->n_tr = R->n_tr; ctx->on_device = R->on_device == SNFB_MEM_DEVICE; ctx->seq_on_demand = R->on_device == SNFB_MEM_HOST_SEQ_ON_DEMAND; ctx->h_seq = ctx->seq_on_demand ? R->seq : nullptr;
     ctx->n_ev = 0;
-    mark(ctx, "h2d_records", sizeof(snfb_rec) * R->n_rec + 4 * R->n_cigar + R->n_var + R->n_seq);
-    if (R->on_device) {
+    mark(ctx, "h2d_records", sizeof(snfb_rec) * R->n_rec + 4 * R->n_cigar + R->n_var + (R->on_device == SNFB_MEM_HOST_SEQ_ON_DEMAND ? 0 : R->n_seq));
+    if (ctx->on_device) {
         ctx->d_rec = R->rec; ctx->d_cigar = R->cigar; ctx->d_var = R->var; ctx->d_seq = R->seq;     // caller keeps them alive; cigar must be padded by 16 bytes
     } else {
-        if (ctx->b_rec.ensure(sizeof(snfb_rec) * (R->n_rec + 1)) || ctx->b_cigar.ensure(4 * (R->n_cigar + 8)) || ctx->b_var.ensure(R->n_var + 16) || ctx->b_seq.ensure(R->n_seq + 16))
+        if (ctx->b_rec.ensure(sizeof(snfb_rec) * (R->n_rec + 1)) || ctx->b_cigar.ensure(4 * (R->n_cigar + 8)) || ctx->b_var.ensure(R->n_var + 16) || (!ctx->seq_on_demand && ctx->b_seq.ensure(R->n_seq + 16)))
             return fail(ctx, "out of device memory for the record block");
         CUDA_TRY(cudaMemcpyAsync(ctx->b_rec.p, R->rec, sizeof(snfb_rec) * R->n_rec, cudaMemcpyHostToDevice, ctx->st));
         CUDA_TRY(cudaMemcpyAsync(ctx->b_cigar.p, R->cigar, 4 * R->n_cigar, cudaMemcpyHostToDevice, ctx->st));
         CUDA_TRY(cudaMemcpyAsync(ctx->b_var.p, R->var, R->n_var, cudaMemcpyHostToDevice, ctx->st));
-        CUDA_TRY(cudaMemcpyAsync(ctx->b_seq.p, R->seq, R->n_seq, cudaMemcpyHostToDevice, ctx->st));
+        if (!ctx->seq_on_demand) CUDA_TRY(cudaMemcpyAsync(ctx->b_seq.p, R->seq, R->n_seq, cudaMemcpyHostToDevice, ctx->st));
         ctx->d_rec = ctx->b_rec.as<snfb_rec>(); ctx->d_cigar = ctx->b_cigar.as<uint32_t>(); ctx->d_var = ctx->b_var.as<uint8_t>(); ctx->d_seq = ctx->b_seq.as<uint8_t>();
     }
     ctx->tasks.assign(R->task, R->task + R->n_task);
@@ -446,6 +447,37 @@ static int run_stage_c(snfb_ctx* ctx) {
     if (ctx->h_ctr.n_seq_bytes > 0xfffffff0ull) return fail(ctx, "consensus scratch exceeds 64 GiB");
     if (ctx->b_alt.ensure(ctx->h_ctr.n_alt_bytes + 16) || ctx->b_scr.ensure(ctx->h_ctr.n_seq_bytes * 16 + 64)) return fail(ctx, "out of device memory (consensus)");
     c.alt = ctx->b_alt.as<uint8_t>(); c.scr = ctx->b_scr.as<uint8_t>(); c.alt_cap = ctx->h_ctr.n_alt_bytes; c.scr_cap16 = ctx->h_ctr.n_seq_bytes;
+    c.arena_off = nullptr;
+    if (ctx->seq_on_demand && ctx->h_ctr.n_cand) {
+        // seq on demand: the device lists the base slices it will read, the host gathers exactly those bytes from its
+        // arena into pinned staging, one H2D copy brings them in (PCIe bytes ~ algorithmic bytes instead of the whole arena)
+        mark(ctx, "seq_requests");
+        const unsigned long long req_cap = ctx->cand_lead_cap + 64;
+        if (ctx->b_seq_req.ensure(sizeof(consensus::SeqReq) * req_cap) || ctx->b_arena_off.ensure(4 * (ctx->lead_cap + 8))) return fail(ctx, "out of device memory (seq requests)");
+        DevCounters* ctr = ctx->b_ctr.as<DevCounters>();
+        CUDA_TRY(cudaMemsetAsync(&ctr->n_ev, 0, 16, ctx->st));          // n_ev / n_sa are free again after stage A: reuse as request / unit counters
+        consensus::k_seq_requests<<<grid_for(ctx->h_ctr.n_cand, 128), 128, 0, ctx->st>>>(c, ctx->b_seq_req.as<consensus::SeqReq>(), req_cap, ctx->b_arena_off.as<uint32_t>(), &ctr->n_ev, &ctr->n_sa); LAUNCHED(ctx, 1);
+        mark(ctx, nullptr);
+        if (fetch_counters(ctx)) return 1;
+        const unsigned long long nreq = ctx->h_ctr.n_ev, nunits = ctx->h_ctr.n_sa;
+        if (nreq > req_cap) return fail(ctx, "seq request list overflow");
+        if (ctx->h_seq_req.ensure(sizeof(consensus::SeqReq) * (nreq + 1)) || ctx->h_seq_arena.ensure(nunits * 16 + 64) || ctx->b_seq_arena.ensure(nunits * 16 + 64)) return fail(ctx, "out of memory (seq arena)");
+        if (nreq) {
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_seq_req.p, ctx->b_seq_req.p, sizeof(consensus::SeqReq) * nreq, cudaMemcpyDeviceToHost, ctx->st));
+            CUDA_TRY(cudaStreamSynchronize(ctx->st));
+            const consensus::SeqReq* rq = ctx->h_seq_req.as<consensus::SeqReq>(); uint8_t* dst = ctx->h_seq_arena.as<uint8_t>(); const uint8_t* src = ctx->h_seq; const uint64_t nseq = ctx->n_seq;
+            #pragma omp parallel for schedule(static, 256)
+            for (long long i = 0; i < (long long)nreq; ++i) {
+                unsigned long long s0 = rq[i].src; unsigned long long nb = rq[i].nbytes; if (s0 > nseq) s0 = nseq; if (s0 + nb > nseq) nb = nseq - s0;
+                memcpy(dst + (size_t)rq[i].dst16 * 16, src + s0, (size_t)nb);
+            }
+            mark(ctx, "h2d_seq_slices", nunits * 16);
+            CUDA_TRY(cudaMemcpyAsync(ctx->b_seq_arena.p, ctx->h_seq_arena.p, nunits * 16, cudaMemcpyHostToDevice, ctx->st));
+            mark(ctx, nullptr);
+        }
+        ctx->seq_h2d_bytes = nunits * 16;
+        c.seq = ctx->b_seq_arena.as<uint8_t>(); c.arena_off = ctx->b_arena_off.as<uint32_t>();
+    }
     if (ctx->h_ctr.n_cand) {
         mark(ctx, "consensus", ctx->h_ctr.n_seq_bytes * 16);
         // heavy candidates (long insertions x many reads) first, with 16 warps each; then the bulk with 4 warps each

@@ -17,6 +17,7 @@ struct C {
     const snfb_cand* cand; snfb_cand* cand_rw; const snfb_lead* cand_leads; const uint32_t* cand_lead_ml;
     const uint32_t* ml_plo; const uint32_t* ml_pn; const uint32_t* ord; const snfb_lead* leads;
     const snfb_rec* rec; const uint8_t* seq;
+    const uint32_t* arena_off;       // seq on demand: per lead slot, 16-byte unit offset of its bytes in `seq` (which then is the compact arena); nullptr = full arena
     uint32_t* plan_best; uint32_t* plan_nother; uint32_t* alt_len; uint32_t* scr_len; uint32_t* alt_off; uint32_t* scr_off;   // scr in units of 16 bytes
     uint8_t* alt; uint8_t* scr; unsigned long long alt_cap, scr_cap16, cand_cap;
     uint32_t* work_big; uint32_t* work_small; uint32_t* work_ctr;      // work_ctr: [0] n_big, [1] n_small, [2] queue position
@@ -75,14 +76,39 @@ __device__ inline void unpack_lead(const C& c, uint32_t cl_index, uint8_t* dst) 
     const uint32_t mi = c.cand_lead_ml[cl_index]; const uint32_t plo = c.ml_plo[mi], pn = c.ml_pn[mi];
     long long o = 0;
     for (uint32_t p = 0; p < pn; ++p) {
-        const snfb_lead* l = &c.leads[c.ord[plo + p]]; const uint8_t* sq = c.seq + c.rec[l->rec].seq_off;
-        unpack_span(sq, l->seq_off, l->seq_len, dst + o, threadIdx.x, blockDim.x);
+        const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.leads[slot];
+        const uint8_t* sq = c.arena_off ? c.seq + (size_t)c.arena_off[slot] * 16 : c.seq + c.rec[l->rec].seq_off;
+        unpack_span(sq, c.arena_off ? (l->seq_off & 1) : l->seq_off, l->seq_len, dst + o, threadIdx.x, blockDim.x);
         o += l->seq_len;
     }
 }
 
 __device__ __forceinline__ uint32_t kmer6(const uint8_t* s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 4) | ((uint32_t)s[2] << 8) | ((uint32_t)s[3] << 12) | ((uint32_t)s[4] << 16) | ((uint32_t)s[5] << 20); }
 __device__ __forceinline__ uint32_t kslot(uint32_t key) { return (key * 2654435761u) >> 21; }    // top 11 bits
+
+// seq on demand: the base slices stage C will read, as (source byte offset in the host seq arena, bytes, destination unit)
+struct SeqReq { unsigned long long src; uint32_t nbytes; uint32_t dst16; };
+__global__ void k_seq_requests(C c, SeqReq* req, unsigned long long req_cap, uint32_t* arena_off_rw, unsigned long long* n_req, unsigned long long* n_units) {
+    const unsigned long long nc = c.ctr->n_cand < c.cand_cap ? c.ctr->n_cand : c.cand_cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nc; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (c.scr_len[i] == 0) continue;
+        const snfb_cand* cd = &c.cand[i]; const bool cons = c.plan_nother[i] > 0;
+        for (int k = 0; k < cd->lead_n; ++k) {
+            const snfb_lead* cl = &c.cand_leads[cd->lead_off + k];
+            if (!(cl->flags & SNFB_LF_HAS_SEQ) || (!cons && (uint32_t)k != c.plan_best[i])) continue;
+            const uint32_t mi = c.cand_lead_ml[cd->lead_off + k];
+            for (uint32_t p = 0; p < c.ml_pn[mi]; ++p) {
+                const uint32_t slot = c.ord[c.ml_plo[mi] + p]; const snfb_lead* l = &c.leads[slot];
+                const unsigned long long b0 = (unsigned long long)l->seq_off >> 1, b1 = ((unsigned long long)l->seq_off + l->seq_len + 1) >> 1;
+                const uint32_t nb = (uint32_t)(b1 - b0) + 1;                                  // +1: unpack_span may touch one byte past the last base
+                const unsigned long long u = atomicAdd(n_units, (unsigned long long)((nb + 15) / 16));
+                const unsigned long long r = atomicAdd(n_req, 1ULL);
+                arena_off_rw[slot] = (uint32_t)u;
+                if (r < req_cap) { req[r].src = c.rec[l->rec].seq_off + b0; req[r].nbytes = nb; req[r].dst16 = (uint32_t)u; }
+            }
+        }
+    }
+}
 
 constexpr int MAXHIT = 512;       // strided k-mer hits of one read are bounded by (L + 6) / skip + 1 < 512 (skip = 3 + L / 500)
 
@@ -91,8 +117,9 @@ __device__ inline void unpack_lead_warp(const C& c, uint32_t cl_index, uint8_t* 
     const uint32_t mi = c.cand_lead_ml[cl_index]; const uint32_t plo = c.ml_plo[mi], pn = c.ml_pn[mi];
     long long o = 0;
     for (uint32_t p = 0; p < pn; ++p) {
-        const snfb_lead* l = &c.leads[c.ord[plo + p]]; const uint8_t* sq = c.seq + c.rec[l->rec].seq_off;
-        unpack_span(sq, l->seq_off, l->seq_len, dst + o, lane_id(), 32);
+        const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.leads[slot];
+        const uint8_t* sq = c.arena_off ? c.seq + (size_t)c.arena_off[slot] * 16 : c.seq + c.rec[l->rec].seq_off;
+        unpack_span(sq, c.arena_off ? (l->seq_off & 1) : l->seq_off, l->seq_len, dst + o, lane_id(), 32);
         o += l->seq_len;
     }
 }

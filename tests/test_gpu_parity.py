@@ -79,3 +79,19 @@ def test_calltask_surface():
     assert read_count == int(br.result.task_read_count[0]) and len(calls) > 10
     assert all(c.qc for c in calls) and calls == sorted(calls, key=lambda c: c.pos)
     assert {c.svtype for c in calls} >= {"INS", "DEL"}
+
+
+def test_seq_on_demand_gives_identical_alts():
+    """e2e mode: the seq arena stays on the host, only the requested slices cross PCIe; results must not change."""
+    import oracle.oracle as orc
+    blk = synth.config_block(5, 0.05)
+    cfg = abi.Config.from_sniffles(sconfig.default_config())
+    ctx = binding.Context(0)
+    try:
+        ctx.set_config(cfg)
+        ctx.load(blk, seq_on_demand=True)
+        got = ctx.run()
+    finally:
+        ctx.close()
+    devcheck.assert_same(orc.run(blk, cfg, 3, 4), got)
+    assert len(got.alt) > 10000
