@@ -118,16 +118,17 @@ def cpu_sample(blk, cfg, ccfg, threads, target_bp=6e9):
     import oracle.oracle as orc
     from sniffles_b200 import abi
     rec = blk.rec
-    tasks = np.unique(rec["task"])
-    chosen, bp, lo = [], 0, len(rec)
-    for t in tasks[::-1]:
-        idx = np.nonzero(rec["task"] == t)[0]
+    tasks, counts = np.unique(rec["task"], return_counts=True)
+    # the reference's unit of CPU parallelism is the contig: take the smallest contigs first so that the bounded sample
+    # still keeps many host threads busy
+    chosen, bp = [], 0
+    for t in tasks[np.argsort(counts)]:
         chosen.append(int(t))
-        lo = int(idx[0])
-        bp += int(rec["l_seq"][idx].sum())
+        bp += int(rec["l_seq"][rec["task"] == t].sum())
         if bp >= target_bp:
             break
-    sub = type(blk)(rec=rec[lo:], cigar=blk.cigar, var=blk.var, seq=blk.seq, task=blk.task, contig=blk.contig, tr=blk.tr, contig_names=blk.contig_names)
+    keep = np.isin(rec["task"], chosen)
+    sub = type(blk)(rec=np.ascontiguousarray(rec[keep]), cigar=blk.cigar, var=blk.var, seq=blk.seq, task=blk.task, contig=blk.contig, tr=blk.tr, contig_names=blk.contig_names)
     abp = aligned_bp_passing(sub, cfg)
     nthr = max(1, min(threads, len(chosen)))
     t0 = time.perf_counter()
@@ -150,7 +151,7 @@ def run_reference(args):
     from sniffles_b200 import synth
     lens = [max(200000, int(x * args.scale)) for x in synth.GRCH38]
     mask, bp = [False] * len(lens), 0.0
-    for c in range(len(lens) - 1, -1, -1):
+    for c in sorted(range(len(lens)), key=lambda k: lens[k]):
         mask[c] = True
         bp += 30.0 * lens[c]
         if bp >= args.cpu_sample_gbp * 1e9:
@@ -324,7 +325,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config index (2 = 30x ONT WGS)")
     ap.add_argument("--scale", type=float, default=float(os.environ.get("SNFB_BENCH_SCALE", "1.0")), help="contig length multiplier (1.0 = full GRCh38 lengths)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-gbp", type=float, default=6.0)
+    ap.add_argument("--cpu-sample-gbp", type=float, default=16.0)
     ap.add_argument("--no-pin", action="store_true")
     ap.add_argument("--e2e-full-seq", action="store_true", help="e2e: copy the whole seq arena every step instead of the on-demand slices")
     ap.add_argument("--no-cpu", action="store_true")

@@ -43,7 +43,7 @@ struct HostBuf {
 constexpr int MAX_TIMINGS = 64;
 
 struct snfb_ctx {
-    int device = 0; cudaStream_t st = nullptr; std::string err;
+    int device = 0; cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; std::string err;
     snfb_config cfg{}; bool have_cfg = false;
     // records
     bool loaded = false, on_device = false, seq_on_demand = false; const uint8_t* h_seq = nullptr;
@@ -105,7 +105,8 @@ int snfb_ctx_create(int device, snfb_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return 3;
     snfb_ctx* ctx = new snfb_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 4; }
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 4; }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventCreate(&ctx->ev[i]);
     *out = ctx; return 0;
 }
@@ -128,7 +129,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt, &ctx->h_seq_req, &ctx->h_seq_arena };
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventDestroy(ctx->ev[i]);
-    cudaStreamDestroy(ctx->st);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaStreamDestroy(ctx->st2); cudaStreamDestroy(ctx->st);
     delete ctx;
 }
 
@@ -273,7 +274,9 @@ static int run_stage_a(snfb_ctx* ctx) {
             // algorithmic bytes of the streaming kernel: record cores + CIGAR + names/SA
             mark(ctx, "k_scan", sizeof(snfb_rec) * nrec + 4 * ctx->n_cigar + ctx->n_var);
             unsigned long long blocks = (nrec + 7) / 8; const unsigned long long maxb = 148ull * 6 * 4;
-            extract::k_scan<<<(int)std::min(blocks, maxb), 256, 0, ctx->st>>>(S);
+            static const bool use_tma = []{ const char* e = getenv("SNFB_SCAN"); return e && strcmp(e, "tma") == 0; }();   // measured slower than the register-pipelined kernel (profiles/README.md)
+            if (use_tma) extract::k_scan_tma<<<(int)std::min<unsigned long long>((nrec + extract::tma::WPB - 1) / extract::tma::WPB, 148ull * 6 * 4), extract::tma::WPB * 32, 0, ctx->st>>>(S);
+            else extract::k_scan<<<(int)std::min(blocks, maxb), 256, 0, ctx->st>>>(S);
             mark(ctx, "k_emit");
             extract::k_ev_counts<<<grid_for(ctx->lead_cap, 256), 256, 0, ctx->st>>>(S.ev, ctx->b_ev_cnt.as<uint32_t>(), S.n_ev, ctx->lead_cap);
             LAUNCHED(ctx, 3 + prims::exclusive_scan(ctx->b_ev_cnt.as<uint32_t>(), ctx->b_ev_slot.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->lead_cap, &ctr->n_slots, ctx->st));
@@ -281,12 +284,12 @@ static int run_stage_a(snfb_ctx* ctx) {
             E.rec = ctx->d_rec; E.cigar = ctx->d_cigar; E.var = ctx->d_var; E.task = S.task; E.ev = S.ev; E.ev_slot = ctx->b_ev_slot.as<uint32_t>(); E.n_ev = S.n_ev; E.ev_cap = ctx->lead_cap;
             E.leads = ctx->b_leads.as<snfb_lead>(); E.lead_cap = ctx->lead_cap; E.ctr = ctr; E.minsv = cf.minsvlen_screen; E.maxlen = cf.dev_seq_cache_maxlen; E.detect_large_ins = cf.detect_large_ins;
             E.longinslen = (double)cf.long_ins_length / 2.0;
-            extract::k_emit<<<148 * 8, 256, 0, ctx->st>>>(E);
+            extract::k_emit<<<148 * 32, 256, 0, ctx->st>>>(E);      // one warp per event slice; latency-bound, so oversubscribe
             mark(ctx, "k_sa");
             extract::SaParams A{};
             A.rec = ctx->d_rec; A.cigar = ctx->d_cigar; A.var = ctx->d_var; A.task = S.task; A.contig = ctx->b_contig.as<snfb_contig>(); A.n_contig = ctx->n_contig;
             A.sa_list = S.sa_list; A.n_sa = S.n_sa; A.rec_end = S.rec_end; A.rec_nlead = S.rec_nlead; A.leads = E.leads; A.lead_cap = ctx->lead_cap; A.ctr = ctr; A.cfg = cf;
-            extract::k_sa<<<148 * 4, extract::THREADS, 0, ctx->st>>>(A);
+            extract::k_sa<<<148 * 10, extract::THREADS, 0, ctx->st>>>(A);
             mark(ctx, "k_task_nm");
             const int cpt = (int)((nrec + extract::NM_CHUNK - 1) / extract::NM_CHUNK);
             if (ctx->b_nm_part.ensure(8 * (size_t)cpt * nt + 8) || ctx->b_nm_cnt.ensure(4 * (size_t)cpt * nt + 8)) return fail(ctx, "out of device memory (nm partials)");
@@ -485,8 +488,12 @@ static int run_stage_c(snfb_ctx* ctx) {
         const size_t smem_b = (size_t)3 * NWB * consensus::MAXHIT * sizeof(int), smem_s = (size_t)3 * NWS * consensus::MAXHIT * sizeof(int);
         static bool attr_set = false;
         if (!attr_set) { cudaFuncSetAttribute(consensus::k_run<NWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b); cudaFuncSetAttribute(consensus::k_run<NWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s); attr_set = true; }
+        // the two launches drain different queues: run them concurrently (second stream) so that the bulk fills the SMs
+        // the heavy tail leaves idle
+        CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->st)); CUDA_TRY(cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
         consensus::k_run<NWB><<<148 * 2, NWB * 32, smem_b, ctx->st>>>(c, 1);
-        consensus::k_run<NWS><<<(int)std::min<unsigned long long>(ctx->h_ctr.n_cand, 148ull * 6), NWS * 32, smem_s, ctx->st>>>(c, 0); LAUNCHED(ctx, 2);
+        consensus::k_run<NWS><<<(int)std::min<unsigned long long>(ctx->h_ctr.n_cand, 148ull * 6), NWS * 32, smem_s, ctx->st2>>>(c, 0); LAUNCHED(ctx, 2);
+        CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->st2)); CUDA_TRY(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
         mark(ctx, nullptr);
     }
     CUDA_TRY(cudaGetLastError());

@@ -414,6 +414,152 @@ __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanPar
     if (lane == 0 && acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
 }
 
+// ------------------------------------------------------------------------------------------------
+// k_scan_tma: the same streaming pass with the CIGAR staged through shared memory by the bulk-copy engine
+// (cp.async.bulk global -> shared, completion on an mbarrier).  Every warp owns a ring of NST 2-KB stages; lane 0 runs
+// a fetch cursor up to NST chunks (and records) ahead of the consume cursor, so each warp keeps several KB in flight
+// without holding them in registers — the loads are no longer tied to the warp's own issue slots.
+// ------------------------------------------------------------------------------------------------
+namespace tma {
+constexpr int NST = 4;                 // stages per warp
+constexpr int CH_OPS = 512;            // ops per stage (2 KB = four 128-op slices)
+constexpr int WPB = 4;                 // warps per block (4 x 4 x 2 KB = 32 KB of stages)
+struct Desc { uint32_t rec; int32_t pos; int32_t n_al; int32_t mis; int32_t alen; int32_t nchunks; uint32_t aux_hp_nm; int32_t task; int32_t nm; int32_t tk_start, tk_end, tk_len; };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+}  // namespace tma
+
+__global__ void __launch_bounds__(tma::WPB * 32, 6) k_scan_tma(const __grid_constant__ ScanParams P) {
+    using namespace tma;
+    __shared__ __align__(128) uint8_t s_buf[WPB][NST][CH_OPS * 4];
+    __shared__ __align__(8) uint64_t s_bar[WPB][NST];
+    __shared__ Desc s_desc[WPB][NST + 1];
+    const int lane = lane_id(), wib = threadIdx.x >> 5;
+    const unsigned nwarps = gridDim.x * WPB;
+    if (lane == 0) { for (int i = 0; i < NST; ++i) mbar_init(&s_bar[wib][i], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+    __syncwarp();
+    int acc_task = -1; unsigned acc_reads = 0; unsigned long long acc_bp = 0; int acc_span = 0;
+    // ---- fetch cursor (warp-uniform state; lane 0 acts) ----
+    unsigned f_rec = blockIdx.x * WPB + wib;                // record the cursor stands on
+    int f_chunk = 0, f_nchunks = 0; bool f_open = false;    // f_open: descriptor of f_rec already published
+    const uint32_t* f_base = nullptr; int f_nal = 0;
+    unsigned n_fetch = 0, n_cons = 0, d_w = 0, d_r = 0;     // chunk / descriptor ring counters
+    int tk_id = -1, tk_start = 0, tk_end = 0, tk_len = 0;
+    // record core of the cursor and of the record after it (prefetched)
+    uint32_t wF = (f_rec < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + f_rec) + lane) : 0u;
+    uint32_t wN = (f_rec + nwarps < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + f_rec + nwarps) + lane) : 0u;
+    // ---- consume cursor ----
+    int c_chunk = 0; unsigned pos_q = 0; int pos_r = 0; unsigned big = 0, nlead = 0;
+    for (;;) {
+        // (1) keep the ring full
+        while (n_fetch - n_cons < (unsigned)NST && f_rec < P.n_rec) {
+            if (!f_open) {
+                const int r_task = (int)__shfl_sync(FULL, wF, 0), r_pos = (int)__shfl_sync(FULL, wF, 1);
+                const uint32_t x2 = __shfl_sync(FULL, wF, 2);
+                const int r_flag = x2 & 0xffff, r_mapq = (x2 >> 16) & 255, r_aux = x2 >> 24;
+                const int n = (int)__shfl_sync(FULL, wF, 6), r_lseq = (int)__shfl_sync(FULL, wF, 7);
+                const uint64_t cigar_off = (uint64_t)__shfl_sync(FULL, wF, 10) | ((uint64_t)__shfl_sync(FULL, wF, 11) << 32);
+                const uint32_t* cg = P.cigar + cigar_off; const int mis = (int)(cigar_off & 3);
+                if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; tk_len = t.contig_len; }
+                // cheap rejects first (no CIGAR access), then the alignment length from the clip ops
+                bool pass = !(r_mapq < P.mapq_min || (r_flag & 256)) && !(P.excl && (r_flag & P.excl)) && r_pos >= tk_start && r_pos < tk_end && n > 0;
+                int alen = 0;
+                if (pass) {
+                    const uint32_t c_first = __ldg(cg), c_last = __ldg(cg + n - 1);
+                    int qas = 0, qae = r_lseq;
+                    { int op = c_first & 15; if (op == 4) qas = (int)(c_first >> 4);
+                      if (op == 4 || op == 5) for (int k = 1; k < n; ++k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qas += (int)(c >> 4); else if (o2 != 5) break; } }
+                    if (n > 1) { int op = c_last & 15; if (op == 4) qae -= (int)(c_last >> 4);
+                      if (op == 4 || op == 5) for (int k = n - 2; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qae -= (int)(c >> 4); else if (o2 != 5) break; } }
+                    alen = qae - qas; pass = alen >= P.alen_min;
+                }
+                if (!pass) {
+                    if (lane == 0) { P.rec_end[f_rec] = -1; P.rec_flags[f_rec] = 0; P.rec_nm[f_rec] = -1.0; P.rec_nlead[f_rec] = 0; }
+                    f_rec += nwarps; wF = wN; { const unsigned nx = f_rec + nwarps; wN = (nx < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + nx) + lane) : 0u; }
+                    continue;
+                }
+                f_base = cg - mis; f_nal = n + mis; f_nchunks = (f_nal + CH_OPS - 1) / CH_OPS; f_chunk = 0; f_open = true;
+                if (lane == 0) {
+                    Desc d; d.rec = f_rec; d.pos = r_pos; d.n_al = f_nal; d.mis = mis; d.alen = alen; d.nchunks = f_nchunks;
+                    d.aux_hp_nm = (uint32_t)r_aux;                     // hp / nm are added right below (they need a warp shuffle)
+                    d.task = r_task; d.nm = 0; d.tk_start = tk_start; d.tk_end = tk_end; d.tk_len = tk_len;
+                    s_desc[wib][d_w % (NST + 1)] = d;
+                }
+                { const uint32_t x3 = __shfl_sync(FULL, wF, 3); const int r_nm = (int)__shfl_sync(FULL, wF, 4);
+                  if (lane == 0) { Desc* dp = &s_desc[wib][d_w % (NST + 1)]; dp->aux_hp_nm = (uint32_t)r_aux | ((x3 & 255u) << 8); dp->nm = r_nm; } }
+                ++d_w;
+                __syncwarp();
+            }
+            {   // issue one chunk of the open record
+                const int st = n_fetch % NST; const int ops = min(CH_OPS, f_nal - f_chunk * CH_OPS); const unsigned bytes = (unsigned)(((ops * 4) + 15) & ~15);
+                if (lane == 0) { mbar_expect_tx(&s_bar[wib][st], bytes); bulk_g2s(s_buf[wib][st], f_base + (size_t)f_chunk * CH_OPS, bytes, &s_bar[wib][st]); }
+                ++n_fetch; ++f_chunk;
+                if (f_chunk == f_nchunks) { f_open = false; f_rec += nwarps; wF = wN; { const unsigned nx = f_rec + nwarps; wN = (nx < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + nx) + lane) : 0u; } }
+            }
+        }
+        if (n_cons == n_fetch) break;                     // nothing in flight and nothing left to fetch
+        // (2) consume one chunk
+        const int st = n_cons % NST;
+        mbar_wait(&s_bar[wib][st], (n_cons / NST) & 1u);
+        const Desc d = s_desc[wib][d_r % (NST + 1)];
+        if (c_chunk == 0) { pos_q = 0; pos_r = d.pos; big = 0; nlead = 0; }
+        const uint4* sb = reinterpret_cast<const uint4*>(s_buf[wib][st]) + lane;
+        const int cbase = c_chunk * CH_OPS;
+        #pragma unroll 1
+        for (int sl = 0; sl < 4; ++sl) {
+            const int base = cbase + sl * 128; if (base >= d.n_al) break;
+            const uint4 v = sb[sl * 32];
+            const int li = base + lane * 4;
+            uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+            if (li < d.mis || li + 3 >= d.n_al) {
+                if (li < d.mis || li >= d.n_al) w0 = 6u; if (li + 1 < d.mis || li + 1 >= d.n_al) w1 = 6u; if (li + 2 < d.mis || li + 2 >= d.n_al) w2 = 6u; if (li + 3 < d.mis || li + 3 >= d.n_al) w3 = 6u; }
+            unsigned lq = 0, lr = 0; bool rare = false;
+            { const unsigned op = w0 & 15u, len = w0 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); }
+            { const unsigned op = w1 & 15u, len = w1 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); }
+            { const unsigned op = w2 & 15u, len = w2 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); }
+            { const unsigned op = w3 & 15u, len = w3 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); }
+            const unsigned tot_q = __reduce_add_sync(FULL, lq), tot_r = __reduce_add_sync(FULL, lr);
+            if (__any_sync(FULL, rare)) { const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, d.rec, base, pos_q, pos_r, nlead, d.tk_start, d.tk_end);
+                big += (unsigned)(rr >> 32); nlead += (unsigned)rr; }
+            pos_q += tot_q; pos_r += (int)tot_r;
+        }
+        __syncwarp();                                      // all lanes are done with this stage before lane 0 may refill it
+        ++n_cons; ++c_chunk;
+        if (c_chunk == d.nchunks) {
+            c_chunk = 0; ++d_r;
+            if (lane == 0) {
+                const int r_aux = d.aux_hp_nm & 255; int hp = (r_aux & SNFB_AUX_HP) ? (int)((d.aux_hp_nm >> 8) & 255u) : 0;
+                if (hp > 2) { hp = 0; atomicAdd(&P.ctr->soft_errors, 1ULL); }
+                const bool has_nm = P.want_nm && (r_aux & SNFB_AUX_NM); const int ref_end = pos_r;
+                P.rec_end[d.rec] = ref_end;
+                P.rec_flags[d.rec] = (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2));
+                P.rec_nm[d.rec] = has_nm ? __ddiv_rn((double)((long long)d.nm - (long long)big), (double)(d.alen + 1)) : -1.0;
+                P.rec_nlead[d.rec] = nlead;
+                if (r_aux & SNFB_AUX_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = d.rec; }
+                if (acc_task != d.task) {
+                    if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
+                    acc_task = d.task; acc_reads = 0; acc_bp = 0; acc_span = 0;
+                }
+                ++acc_reads;
+                const int ce = ref_end < d.tk_len ? ref_end : d.tk_len;
+                if (ce > d.pos) acc_bp += (unsigned long long)(ce - d.pos);
+                if (ref_end - d.pos > acc_span) acc_span = ref_end - d.pos;
+            }
+        }
+    }
+    if (lane == 0 && acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
+}
+
 // exact lead slots of the event slices: exclusive prefix of their counts (slices of one record keep their order through k0)
 __global__ void k_ev_counts(const EvSlice* __restrict__ ev, uint32_t* __restrict__ cnt, const unsigned long long* __restrict__ n_ev, unsigned long long bound) {
     const unsigned long long n = *n_ev < bound ? *n_ev : bound;
