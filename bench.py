@@ -98,7 +98,7 @@ def measured_peak():
 
 def ncu_traffic():
     """DRAM bytes per launch of the lead kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "k_extract_dram.json")
+    p = os.path.join(ROOT, "profiles", "k_scan_dram.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
