@@ -121,6 +121,12 @@ typedef struct snfb_records {
     const snfb_task*   task;
     const snfb_contig* contig;
     const int32_t*     tr;    /* n_tr pairs (start,end), per task sorted (util.py:121-147) */
+    /* optional: reference 'N' runs per task for LeadProvider._mask_N_coverage (leadprov.py:420-443, only with --reference):
+     * n_mask half-open pairs (start,end), sorted and disjoint inside a task; task t owns mask[mask_task_off[t] .. mask_task_off[t+1]) */
+    uint32_t n_mask;
+    uint32_t _pad2;
+    const int32_t*  mask;
+    const uint32_t* mask_task_off;   /* [n_task + 1]; may be NULL when n_mask == 0 */
 } snfb_records;
 
 /* Flat POD of the reference's config values that the path reads (config.py:449-619). */

@@ -145,6 +145,24 @@ def run_task(block, t, config, finalize=True):
     if int(task["tr_n"]) > 0:
         o, n = int(task["tr_off"]), int(task["tr_n"])
         tr = [(int(block.tr[2 * (o + k)]), int(block.tr[2 * (o + k) + 1])) for k in range(n)]
+    if getattr(block, "mask", None) is not None and len(block.mask):
+        # --reference: LeadProvider._mask_N_coverage reads the contig through pysam.FastaFile (leadprov.py:420-443)
+        import pysam as _stub
+        lo, hi = int(block.mask_task_off[t]), int(block.mask_task_off[t + 1])
+        runs = [(int(block.mask[2 * m]), int(block.mask[2 * m + 1])) for m in range(lo, hi)]
+        clen = int(task["contig_len"])
+
+        class _Fasta:
+            def __init__(self, path):
+                pass
+
+            def fetch(self, ctg, start=None, end=None):
+                seq = bytearray(b"A" * clen)
+                for a, b in runs:
+                    seq[max(a, 0):min(b, clen)] = b"N" * (min(b, clen) - max(a, 0))
+                return bytes(seq[start:end]).decode() if start is not None else bytes(seq).decode()
+        _stub.FastaFile = _Fasta
+        config.reference = "reference.fa"
     if not hasattr(config, "mode"):
         config.mode = "call_sample"          # set by the CLI driver (sniffles:101-148)
     tk = parallel.CallTask(id=int(task["task_id"]), sv_id=0, contig=contig, start=int(task["start"]),

@@ -849,7 +849,11 @@ static void run_task(task_t* T, double* rec_nm, int stages, uint64_t rec_lo, uin
     for (long i = 0; i < T->leads.n; ++i) vpush(T->lead_out, T->leads.p[i].L);
     /* coverage and hap-REF prefix sums */
     T->cov = malloc((size_t)(L + 1) * sizeof *T->cov);
-    { int32_t acc = 0; double tot = 0; for (long i = 0; i < L; ++i) { acc += T->covdiff[i]; T->cov[i] = (uint16_t)acc; tot += (double)T->cov[i]; } T->cov_mean = L > 0 ? tot / (double)L : 0.0; }
+    { int32_t acc = 0; for (long i = 0; i < L; ++i) { acc += T->covdiff[i]; T->cov[i] = (uint16_t)acc; } }
+    if (R->n_mask && R->mask && R->mask_task_off)        /* _mask_N_coverage: coverage[mask == 'N'] = 0 (leadprov.py:420-443) */
+        for (uint32_t m = R->mask_task_off[T->t]; m < R->mask_task_off[T->t + 1]; ++m) { long a = R->mask[2 * m], b = R->mask[2 * m + 1]; if (a < tk->start) a = tk->start; if (b > tk->end) b = tk->end;   /* the mask is fetched per region (leadprov.py:436-438) */
+            if (a < 0) a = 0; if (b > L) b = L; for (long i = a; i < b; ++i) T->cov[i] = 0; }
+    { double tot = 0; for (long i = 0; i < L; ++i) tot += (double)T->cov[i]; T->cov_mean = L > 0 ? tot / (double)L : 0.0; }
     for (int h = 0; h < 3; ++h) { int32_t acc = 0; for (long b = 0; b <= T->nbins; ++b) { acc += T->hapref[(long)h * (T->nbins + 1) + b]; T->hapref[(long)h * (T->nbins + 1) + b] = acc; } }
     if (stages >= 2) {
         long n = T->leads.n, i = 0;

@@ -49,7 +49,7 @@ struct snfb_ctx {
     bool loaded = false, on_device = false, seq_on_demand = false; const uint8_t* h_seq = nullptr;
     uint64_t n_rec = 0, n_cigar = 0, n_var = 0, n_seq = 0; uint32_t n_task = 0, n_contig = 0, n_tr = 0;
     const snfb_rec* d_rec = nullptr; const uint32_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
-    DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp;
+    DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp, b_mask, b_mask_off, b_mask_task; uint32_t n_mask = 0;
     // stage A outputs
     DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_ev_cnt, b_ev_slot, b_sa_list;
     unsigned long long lead_cap = 0;
@@ -115,7 +115,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
-    DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_ctr, &ctx->b_leads, &ctx->b_rec_pos, &ctx->b_rec_end,
+    DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_mask, &ctx->b_mask_off, &ctx->b_mask_task, &ctx->b_ctr, &ctx->b_leads, &ctx->b_rec_pos, &ctx->b_rec_end,
         &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_ev_cnt, &ctx->b_ev_slot, &ctx->b_sa_list,
         &ctx->b_key0, &ctx->b_val0, &ctx->b_key1, &ctx->b_val1, &ctx->b_flag, &ctx->b_scan, &ctx->b_hist, &ctx->b_scan_tmp, &ctx->b_bin_start, &ctx->b_bin_nl, &ctx->b_bin_nlong, &ctx->b_bin_kept,
         &ctx->b_bin_hap, &ctx->b_kl_off, &ctx->b_kll_off, &ctx->b_kb_idx, &ctx->b_kl, &ctx->b_kll, &ctx->b_kb_bin, &ctx->b_kb_lead_off, &ctx->b_kb_lead_n, &ctx->b_kb_long_off, &ctx->b_kb_long_n,
@@ -176,6 +176,16 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
         CUDA_TRY(cudaMemcpyAsync(ctx->b_trp.p, pm.data(), 4 * (size_t)R->n_tr, cudaMemcpyHostToDevice, ctx->st));
         CUDA_TRY(cudaStreamSynchronize(ctx->st));     // pm is a stack-owned staging vector
     }
+    ctx->n_mask = (R->mask && R->mask_task_off) ? R->n_mask : 0;
+    if (ctx->n_mask) {
+        std::vector<uint32_t> mt(ctx->n_mask);
+        for (uint32_t t = 0; t < R->n_task; ++t) for (uint32_t m = R->mask_task_off[t]; m < R->mask_task_off[t + 1] && m < ctx->n_mask; ++m) mt[m] = t;
+        if (ctx->b_mask.ensure(8 * (size_t)ctx->n_mask) || ctx->b_mask_off.ensure(4 * ((size_t)R->n_task + 1)) || ctx->b_mask_task.ensure(4 * (size_t)ctx->n_mask)) return fail(ctx, "out of device memory (N mask)");
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask.p, R->mask, 8 * (size_t)ctx->n_mask, cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask_off.p, R->mask_task_off, 4 * ((size_t)R->n_task + 1), cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask_task.p, mt.data(), 4 * (size_t)ctx->n_mask, cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaStreamSynchronize(ctx->st));
+    }
     mark(ctx, nullptr);
     ctx->n_ev_load = ctx->n_ev;
     ctx->loaded = true; return 0;
@@ -219,6 +229,7 @@ static cluster::B make_b(snfb_ctx* ctx) {
     b.rec_pos = ctx->b_rec_pos.as<int32_t>(); b.rec_end = ctx->b_rec_end.as<int32_t>(); b.rec_flags = ctx->b_rec_flags.as<uint8_t>(); b.rec_nm = ctx->b_rec_nm.as<double>();
     b.rec_nlead = ctx->b_rec_nlead.as<uint32_t>(); b.rec_lead_off = ctx->b_rec_lead_off.as<uint32_t>();
     b.task_first = ctx->b_task_first.as<uint32_t>(); b.task_last = ctx->b_task_last.as<uint32_t>(); b.task_maxspan = ctx->b_task_span.as<int32_t>();
+    b.mask = ctx->n_mask ? ctx->b_mask.as<int32_t>() : nullptr; b.mask_task_off = ctx->n_mask ? ctx->b_mask_off.as<uint32_t>() : nullptr;
     b.n_task = ctx->n_task; b.n_bound = ctx->n_bound; b.ctr = ctx->b_ctr.as<DevCounters>(); b.cfg = ctx->cfg;
     b.key0 = ctx->b_key0.as<uint64_t>(); b.val0 = ctx->b_val0.as<uint32_t>(); b.key1 = ctx->b_key1.as<uint64_t>(); b.val1 = ctx->b_val1.as<uint32_t>();
     b.skey = ctx->sorted_in_first ? b.key0 : b.key1; b.sval = ctx->sorted_in_first ? b.val0 : b.val1;
@@ -395,6 +406,7 @@ static int run_stage_b(snfb_ctx* ctx) {
         cluster::k_cand_finish<<<g, 128, 0, ctx->st>>>(b);
         k_copy_ml<<<g, 128, 0, ctx->st>>>(b.subl, b.sub_lo, b.cand_valid, b.cand_lead_off, b.cand_tmp, b.cand_lead_ml, &ctr->n_sub, ctx->cand_lead_cap);
         mark(ctx, "coverage");
+        if (ctx->n_mask) { cluster::k_mask_bp<<<grid_for((unsigned long long)ctx->n_mask * 32, 128), 128, 0, ctx->st>>>(b, ctx->b_mask_task.as<uint32_t>(), ctx->n_mask, ctx->b_task_cov.as<unsigned long long>()); LAUNCHED(ctx, 1); }
         cluster::k_coverage<<<g, 128, 0, ctx->st>>>(b); LAUNCHED(ctx, 12);
         mark(ctx, nullptr);
     }

@@ -23,6 +23,7 @@ struct B {
     snfb_lead* leads; const snfb_rec* rec; const snfb_task* task; const snfb_contig* contig; const int32_t* tr; const int32_t* tr_pmax;
     const int32_t* rec_pos; const int32_t* rec_end; const uint8_t* rec_flags; const double* rec_nm; const uint32_t* rec_nlead; const uint32_t* rec_lead_off;
     const uint32_t* task_first; const uint32_t* task_last; const int32_t* task_maxspan;
+    const int32_t* mask; const uint32_t* mask_task_off;      // reference 'N' runs (may be null)
     uint32_t n_task; unsigned long long n_bound;     // upper bound on the number of leads (launch size)
     DevCounters* ctr;
     snfb_config cfg;
@@ -487,6 +488,11 @@ __device__ inline void cov_at_warp(const B& b, int t, long long idx, int* out) {
     const long long L = b.task[t].contig_len;
     if (idx < 0) idx += L;
     if (idx < 0 || idx >= L) return;             // IndexError: the field keeps its default 0
+    if (b.mask) {                                 // _mask_N_coverage: positions inside a reference 'N' run read 0 (leadprov.py:439)
+        uint32_t lo = b.mask_task_off[t], hi = b.mask_task_off[t + 1];
+        while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if ((long long)b.mask[2 * mid + 1] <= idx) lo = mid + 1; else hi = mid; }
+        if (lo < b.mask_task_off[t + 1] && (long long)b.mask[2 * lo] <= idx && idx >= b.task[t].start && idx < b.task[t].end) { *out = 0; return; }   // the mask is fetched per region (leadprov.py:436-438)
+    }
     uint32_t c[3]; cover_count_warp(b, t, idx, c); *out = (int)((c[0] + c[1] + c[2]) & 0xffffu);
 }
 
@@ -578,6 +584,32 @@ __global__ void k_coverage(B b) {
             c->cov_upstream = v[0]; c->cov_start = v[1]; c->cov_center = v[2]; c->cov_end = v[3]; c->cov_downstream = v[4];
             for (int h = 0; h < 3; ++h) c->hap_counts[3 + h] = (int)(hr[h] > 65535u ? 65535u : hr[h]);
         }
+    }
+}
+
+// _mask_N_coverage for the contig mean: subtract the read bases that fall inside reference 'N' runs.  One warp per run.
+__global__ void k_mask_bp(B b, const uint32_t* __restrict__ mask_task, uint32_t n_mask, unsigned long long* task_cov_bp) {
+    const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
+    for (unsigned long long m = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; m < n_mask; m += nw) {
+        const int t = (int)mask_task[m]; const long long L = b.task[t].contig_len;
+        long long a = b.mask[2 * m], e = b.mask[2 * m + 1]; if (a < b.task[t].start) a = b.task[t].start; if (e > b.task[t].end) e = b.task[t].end; if (a < 0) a = 0; if (e > L) e = L;
+        const uint32_t lo = b.task_first[t], hi = b.task_last[t];
+        unsigned long long sum = 0;
+        if (a < e && lo < hi) {
+            uint32_t x = lo, z = hi;                 // first record with pos >= e
+            while (x < z) { const uint32_t mid = x + ((z - x) >> 1); if ((long long)b.rec_pos[mid] < e) x = mid + 1; else z = mid; }
+            const long long span = b.task_maxspan[t];
+            for (long long i = (long long)x - 1 - lane_id(); i >= (long long)lo; i -= 32) {
+                const long long ps = b.rec_pos[i]; if (ps + span <= a) break;
+                if (!(b.rec_flags[i] & extract::RF_PASS)) continue;
+                long long re = b.rec_end[i]; if (re > L) re = L;
+                const long long o0 = ps > a ? ps : a, o1 = re < e ? re : e;
+                if (o1 > o0) sum += (unsigned long long)(o1 - o0);
+            }
+        }
+        #pragma unroll
+        for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        if (lane_id() == 0 && sum) atomicAdd(&task_cov_bp[t], 0ull - sum);
     }
 }
 

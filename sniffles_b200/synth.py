@@ -67,6 +67,8 @@ class RecordBlock:
     aligned_bp: int = 0
     sites: np.ndarray = None
     _owner: object = None
+    mask: np.ndarray = None            # optional reference N runs: int32 pairs (start, end), per task contiguous
+    mask_task_off: np.ndarray = None   # uint32 [n_task + 1]
 
     def as_struct(self) -> abi.Records:
         r = abi.Records()
@@ -75,7 +77,19 @@ class RecordBlock:
         r.var, r.seq = self.var.ctypes.data, self.seq.ctypes.data
         r.n_task, r.n_contig, r.n_tr, r.on_device = len(self.task), len(self.contig), len(self.tr) // 2, 0
         r.task, r.contig, r.tr = self.task.ctypes.data, self.contig.ctypes.data, self.tr.ctypes.data
+        if self.mask is not None and len(self.mask):
+            r.n_mask, r.mask, r.mask_task_off = len(self.mask) // 2, self.mask.ctypes.data, self.mask_task_off.ctypes.data
         return r
+
+    def set_n_mask(self, per_task_intervals):
+        """per_task_intervals: {task index: [(start, end), ...]} of reference 'N' runs (sorted, disjoint)."""
+        off, flat = [0], []
+        for t in range(len(self.task)):
+            iv = sorted(per_task_intervals.get(t, []))
+            flat.extend(x for ab in iv for x in ab)
+            off.append(off[-1] + len(iv))
+        self.mask = np.asarray(flat, dtype="<i4")
+        self.mask_task_off = np.asarray(off, dtype="<u4")
 
     def nbytes(self) -> int:
         return self.rec.nbytes + self.cigar.nbytes + self.var.nbytes + self.seq.nbytes

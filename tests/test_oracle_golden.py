@@ -27,6 +27,8 @@ def load_fixture(name):
     for a in (blk.rec, blk.cigar, blk.var, blk.seq, blk.task, blk.tr):
         h.update(np.ascontiguousarray(a).tobytes())
     assert h.hexdigest() == fx["digest"], "the synthetic generator no longer reproduces the block the fixture was made from"
+    if fx.get("n_mask"):
+        blk.set_n_mask({int(k): [tuple(x) for x in v] for k, v in fx["n_mask"].items()})
     return fx, blk
 
 
