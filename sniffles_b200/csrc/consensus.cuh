@@ -20,7 +20,10 @@ struct C {
     const uint32_t* arena_off;       // seq on demand: per lead slot, 16-byte unit offset of its bytes in `seq` (which then is the compact arena); nullptr = full arena
     uint32_t* plan_best; uint32_t* plan_nother; uint32_t* alt_len; uint32_t* scr_len; uint32_t* alt_off; uint32_t* scr_off;   // scr in units of 16 bytes
     uint8_t* alt; uint8_t* scr; unsigned long long alt_cap, scr_cap16, cand_cap;
-    uint32_t* work_big; uint32_t* work_small; uint32_t* work_ctr;      // work_ctr: [0] n_big, [1] n_small, [2] queue position
+    uint32_t* work_big; uint32_t* work_small; uint32_t* work_ctr;      // work_ctr: [0] n_big, [1] n_small, [2],[3] queue positions, [4] n_items_big, [5] n_items_small, [6],[7] item queue positions, [8] n_tiles, [9] tile queue position
+    // item pipeline: one (candidate, supporting read) pair per warp, one (candidate, column tile) per block
+    struct Item { uint32_t cand; uint32_t k; uint32_t row; uint32_t rd_off; };
+    Item* items_big; Item* items_small; uint2* tiles; unsigned long long item_cap, tile_cap; int use_items;
     DevCounters* ctr; snfb_config cfg;
 };
 
@@ -42,12 +45,23 @@ __global__ void k_plan(C c) {
                 const bool cons = (nm - 1 >= c.cfg.consensus_min_reads) && !c.cfg.no_consensus;
                 c.plan_best[i] = (uint32_t)bi; c.plan_nother[i] = cons ? (uint32_t)(nm - 1) : 0u;
                 // scratch: best codes + others' codes + one row of L per other read + accept flags, 16-byte units
-                const unsigned long long bytes = cons ? (unsigned long long)tot + (unsigned long long)(nm - 1) * L + (unsigned long long)(nm - 1) * 16 + 64 : (unsigned long long)L + 16;
+                const unsigned long long bytes = cons ? (unsigned long long)tot + (unsigned long long)(nm - 1) * L + (unsigned long long)(nm - 1) * 16 + 64 + (c.use_items ? 16 + TAB * 8 : 0) : (unsigned long long)L + 16;
                 sl = (uint32_t)((bytes + 15) / 16);
                 c.cand_rw[i].alt_len = (int)L;
                 // work queue: the heavy tail (long insertions with many reads) is scheduled first
                 const unsigned long long work = (unsigned long long)L * (unsigned long long)nm;
                 if (work > 60000ull) c.work_big[atomicAdd(&c.work_ctr[0], 1u)] = (uint32_t)i; else c.work_small[atomicAdd(&c.work_ctr[1], 1u)] = (uint32_t)i;
+                if (c.use_items && cons) {
+                    // one work item per supporting read (heavy rows first) and one per 4096-column tile of the vote
+                    const bool heavy = L > 4000u; C::Item* dst = heavy ? c.items_big : c.items_small;
+                    const uint32_t base = atomicAdd(&c.work_ctr[heavy ? 4 : 5], (uint32_t)(nm - 1));
+                    uint32_t row = 0, ro = 0;
+                    for (int k = 0; k < cd->lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ) || k == bi) continue;
+                        if ((unsigned long long)base + row < c.item_cap) { C::Item it; it.cand = (uint32_t)i; it.k = (uint32_t)k; it.row = row; it.rd_off = ro; dst[base + row] = it; }
+                        ++row; ro += (uint32_t)l->seq_len; }
+                    const uint32_t nt = (L + 4095u) / 4096u; const uint32_t tb = atomicAdd(&c.work_ctr[8], nt);
+                    for (uint32_t t = 0; t < nt; ++t) if ((unsigned long long)tb + t < c.tile_cap) c.tiles[tb + t] = make_uint2((uint32_t)i, t);
+                }
             }
         }
         c.alt_len[i] = al; c.scr_len[i] = sl;
@@ -276,6 +290,210 @@ __global__ void __launch_bounds__(NW * 32) k_run(C c, int big) {
         for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) {
             unsigned long long cnt[4] = { 0, 0, 0, 0 }; int nal = 0;
             for (uint32_t r0 = 0; r0 < no; r0 += 8) {       // eight row bytes in flight per thread
+                uint8_t cv[8];
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) { const uint32_t r2 = r0 + u; cv[u] = (r2 < no && acc[r2]) ? rows[(size_t)r2 * L + h] : DASH; }
+                #pragma unroll
+                for (int u = 0; u < 8; ++u) { const uint8_t cc = cv[u]; if (cc != DASH) { cnt[cc >> 2] += 1ull << (16 * (cc & 3)); ++nal; } }
+            }
+            uint8_t res = best[h];
+            if (!(nal < 2 || __ddiv_rn((double)nal, maxal) < 0.25)) {
+                cnt[best[h] >> 2] += 1ull << (16 * (best[h] & 3));
+                int t0 = -1, t1 = -1, c0 = 0, nd = 0;
+                #pragma unroll
+                for (int code = 0; code < 16; ++code) { const int v = (int)((cnt[code >> 2] >> (16 * (code & 3))) & 0xffff); if (!v) continue; ++nd; if (v > t0) { t1 = t0; t0 = v; c0 = code; } else if (v > t1) t1 = v; }
+                if (nd > 1 && t0 - t1 >= 3) res = (uint8_t)c0;
+            }
+            out[h] = (uint8_t)CODE[res];
+        }
+    }
+}
+
+// ================================================================================================
+// Item pipeline (default): k_prep (block per candidate: unpack the best read, build its anchor table in global
+// scratch, or copy the best read to ALT when there is no consensus) -> k_align (one warp per (candidate, read)
+// item from a heavy-first queue: no block barriers, the heaviest candidate's reads spread over the whole GPU)
+// -> k_vote (one block per (candidate, 4096-column tile)).
+// ================================================================================================
+__device__ __forceinline__ uint8_t* cand_table(const C& c, uint32_t ci, uint32_t** keys, int** pos) {
+    uint8_t* scr = c.scr + (size_t)c.scr_off[ci] * 16;
+    uint8_t* end = scr + (size_t)c.scr_len[ci] * 16;
+    *keys = reinterpret_cast<uint32_t*>(end - TAB * 8); *pos = reinterpret_cast<int*>(end - TAB * 4);
+    return scr;
+}
+
+__global__ void __launch_bounds__(128) k_prep(C c) {
+    __shared__ uint32_t s_cand;
+    static const char CODE[17] = "=ACMGRSVTWYHKDBN";
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) { const uint32_t q = atomicAdd(&c.work_ctr[2], 1u); const uint32_t nb = c.work_ctr[0], ns = c.work_ctr[1];
+            s_cand = q < nb ? c.work_big[q] : (q < nb + ns ? c.work_small[q - nb] : 0xffffffffu); }
+        __syncthreads();
+        const uint32_t ci = s_cand; if (ci == 0xffffffffu) break;
+        const uint32_t L = c.alt_len[ci];
+        if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) { if (threadIdx.x == 0) atomicAdd(&c.ctr->scratch_overflow, 1ULL); continue; }
+        const snfb_cand cd = c.cand[ci];
+        uint32_t* tk; int* tp; uint8_t* best = cand_table(c, ci, &tk, &tp);
+        unpack_lead(c, cd.lead_off + c.plan_best[ci], best);
+        if (threadIdx.x == 0) c.cand_rw[ci].alt_off = (int)c.alt_off[ci];
+        const uint32_t no = c.plan_nother[ci];
+        if (no == 0 || L == 0) { __syncthreads(); uint8_t* out = c.alt + c.alt_off[ci]; for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) out[h] = (uint8_t)CODE[best[h]]; continue; }
+        for (int i = threadIdx.x; i < TAB; i += blockDim.x) { tk[i] = 0xffffffffu; tp[i] = -1; }
+        __syncthreads();
+        const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
+        for (long i = (long)threadIdx.x * skip; i < (long)L - 6; i += (long)blockDim.x * skip) {
+            const uint32_t key = kmer6(best + i); uint32_t s = kslot(key);
+            for (;;) { const uint32_t old = atomicCAS(&tk[s], 0xffffffffu, key); if (old == 0xffffffffu || old == key) break; s = (s + 1) & (TAB - 1); }
+            if (atomicCAS(&tp[s], -1, (int)i) != -1) tp[s] = -2;
+        }
+    }
+}
+
+constexpr int ALIGN_WARPS = 4;
+__global__ void __launch_bounds__(ALIGN_WARPS * 32) k_align(C c) {
+    __shared__ int h_i[ALIGN_WARPS][MAXHIT], h_j[ALIGN_WARPS][MAXHIT], h_cl[ALIGN_WARPS][MAXHIT];
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp];
+    const int klen = 6;
+    for (;;) {
+        uint32_t q = 0; if (lane == 0) q = atomicAdd(&c.work_ctr[6], 1u);
+        q = __shfl_sync(FULL, q, 0);
+        const uint32_t nb = c.work_ctr[4], ns = c.work_ctr[5];
+        if (q >= nb + ns) break;
+        const C::Item it = q < nb ? c.items_big[q] : c.items_small[q - nb];
+        const uint32_t ci = it.cand; const uint32_t L = c.alt_len[ci];
+        if ((unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
+        const snfb_cand* cd = &c.cand[ci];
+        uint32_t* t_key; int* t_pos; uint8_t* best = cand_table(c, ci, &t_key, &t_pos);
+        const uint32_t no = c.plan_nother[ci];
+        // layout: best[L] | other reads' codes | rows[no][L] | accept[no] | ... | table
+        long long o_total = 0;
+        { const uint32_t bi = c.plan_best[ci]; long long part = 0;
+          for (int k = lane; k < cd->lead_n; k += 32) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if ((l->flags & SNFB_LF_HAS_SEQ) && (uint32_t)k != bi) part += l->seq_len; }
+          #pragma unroll
+          for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
+          o_total = part; }
+        uint8_t* oth = best + L; uint8_t* rows = oth + o_total; uint8_t* acc = rows + (size_t)no * L;
+        const snfb_lead* l = &c.cand_leads[cd->lead_off + it.k];
+        const long Lo = l->seq_len; uint8_t* rd = oth + it.rd_off; uint8_t* row = rows + (size_t)it.row * L;
+        const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
+        unpack_lead_warp(c, cd->lead_off + it.k, rd);
+        __syncwarp();
+        // (1) anchor hits in j order (table lives in global scratch, L2 resident)
+        int nh = 0;
+        const long nk = Lo - klen > 0 ? (Lo - klen + skip - 1) / skip : 0;
+        for (long kb = 0; kb < nk; kb += 32) {
+            const long kk = kb + lane; const long j = kk * skip; int ai = -1;
+            if (kk < nk) { const uint32_t key = kmer6(rd + j); uint32_t s = kslot(key);
+                for (;;) { const uint32_t tk = t_key[s]; if (tk == 0xffffffffu) break; if (tk == key) { ai = t_pos[s]; break; } s = (s + 1) & (TAB - 1); }
+                if (ai >= 0) { long d = ai - j; if (d < 0) d = -d; if (d > klen) ai = -1; } }
+            const unsigned hm = __ballot_sync(FULL, ai >= 0);
+            if (ai >= 0) { const int p = nh + __popc(hm & lanemask_lt()); if (p < MAXHIT) { hi[p] = ai; hj[p] = (int)j; } }
+            nh += __popc(hm);
+        }
+        if (nh > MAXHIT) nh = MAXHIT;
+        __syncwarp();
+        // (2) anchor automaton over the hit list (consensus.py:306-338)
+        int na = 0; long last_i = -1, cl = 0;
+        for (int h = 0; h < nh; ++h) {
+            const int i = hi[h], j = hj[h];
+            if (na > 0 && i <= last_i) continue;
+            long before = cl;
+            if (na == 0) { if (j > 0) cl = i; before = 0; }
+            else { long fwd_j = (long)j - hj[na - 1]; if (cl + fwd_j > (long)L) fwd_j = (long)L - cl; cl += fwd_j; }
+            __syncwarp();
+            if (lane == 0) { hi[na] = i; hj[na] = j; hcl[na] = (int)before; }
+            __syncwarp();
+            ++na; last_i = i;
+        }
+        // (3) segments in parallel: lane per segment
+        long span = 0;
+        if (na > 0) { const long c0 = hj[0] > 0 ? hi[0] : 0; for (long q2 = lane; q2 < c0; q2 += 32) row[q2] = DASH; }
+        for (int m = 1 + lane; m < na; m += 32) {
+            const long li = hi[m - 1], lj = hj[m - 1], i = hi[m], j = hj[m], cs = hcl[m];
+            const long d = j - lj; long fwd_j = d; if (cs + fwd_j > (long)L) fwd_j = (long)L - cs;
+            const long fwd_i = i - li; bool copy = false;
+            if (fwd_i == fwd_j && fwd_j > 0) {
+                span += d; int mt = 0;
+                #pragma unroll 8
+                for (long q2 = 1; q2 <= d; ++q2) mt += (li + q2 < (long)L && rd[lj + q2] == best[li + q2]) ? 1 : 0;
+                copy = __ddiv_rn((double)mt, (double)d) >= 0.5;
+            }
+            if (copy) {
+                #pragma unroll 8
+                for (long q2 = 0; q2 < fwd_j; ++q2) row[cs + q2] = rd[lj + q2];
+            } else { for (long q2 = 0; q2 < fwd_j; ++q2) row[cs + q2] = DASH; }
+        }
+        span = (long)__reduce_add_sync(FULL, (unsigned)span);
+        for (long q2 = cl + lane; q2 < (long)L; q2 += 32) row[q2] = DASH;
+        __syncwarp();
+        // (4) dash-free runs survive only with identity > 0.5 and more than 5 matches (consensus.py:343-360)
+        bool in_run = false; long run_start = 0; long ident = 0;
+        for (long hb = 0; hb < (long)L; hb += 128) {
+            uint8_t ccs[4], bbs[4];
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) { const long h = hb + 32 * u + lane; const bool in = h < (long)L; ccs[u] = in ? row[h] : DASH; bbs[u] = in ? best[h] : (uint8_t)0; }
+            #pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long h0 = hb + 32 * u; if (h0 >= (long)L) break;
+                const uint8_t cc = ccs[u];
+                const unsigned nd = __ballot_sync(FULL, cc != DASH), mt = __ballot_sync(FULL, cc != DASH && cc == bbs[u]);
+                if (!in_run && nd == 0) continue;
+                int p = 0;
+                while (p < 32) {
+                    if (in_run) {
+                        const unsigned rest = ~(nd >> p); int cnt = rest ? __ffs(rest) - 1 : 32; if (cnt > 32 - p) cnt = 32 - p;
+                        const unsigned mask = cnt >= 32 ? 0xffffffffu : (((1u << cnt) - 1u) << p);
+                        ident += __popc(mt & mask); p += cnt;
+                        if (p < 32) {
+                            const long len = h0 + p - run_start;
+                            if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q2 = run_start + lane; q2 < h0 + p; q2 += 32) row[q2] = DASH;
+                            in_run = false;
+                        }
+                    } else {
+                        const unsigned rest = nd >> p; if (!rest) { p = 32; break; }
+                        p += __ffs(rest) - 1; in_run = true; run_start = h0 + p; ident = 0;
+                    }
+                }
+            }
+        }
+        if (in_run) { const long len = (long)L - run_start; if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q2 = run_start + lane; q2 < (long)L; q2 += 32) row[q2] = DASH; }
+        if (lane == 0) acc[it.row] = __ddiv_rn((double)span, (double)L) > 0.2;
+        __syncwarp();
+    }
+}
+
+// column vote (consensus.py:365-380), one block per (candidate, 4096-column tile)
+__global__ void __launch_bounds__(256) k_vote(C c) {
+    __shared__ uint2 s_tile; __shared__ int s_nacc;
+    static const char CODE[17] = "=ACMGRSVTWYHKDBN";
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) { const uint32_t q = atomicAdd(&c.work_ctr[9], 1u); s_tile = q < c.work_ctr[8] && q < c.tile_cap ? c.tiles[q] : make_uint2(0xffffffffu, 0); s_nacc = 0; }
+        __syncthreads();
+        const uint32_t ci = s_tile.x; if (ci == 0xffffffffu) break;
+        const uint32_t L = c.alt_len[ci], no = c.plan_nother[ci];
+        if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
+        const snfb_cand* cd = &c.cand[ci];
+        uint8_t* best = c.scr + (size_t)c.scr_off[ci] * 16;
+        long long part = 0; { const uint32_t bi = c.plan_best[ci];
+          for (int k = threadIdx.x; k < cd->lead_n; k += blockDim.x) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if ((l->flags & SNFB_LF_HAS_SEQ) && (uint32_t)k != bi) part += l->seq_len; } }
+        __shared__ unsigned long long s_tot;
+        if (threadIdx.x == 0) s_tot = 0;
+        __syncthreads();
+        if (part) atomicAdd(&s_tot, (unsigned long long)part);
+        __syncthreads();
+        const uint8_t* rows = best + L + s_tot; const uint8_t* acc = rows + (size_t)no * L;
+        int na = 0; for (uint32_t r = threadIdx.x; r < no; r += blockDim.x) na += acc[r] ? 1 : 0;
+        if (na) atomicAdd(&s_nacc, na);
+        __syncthreads();
+        const double maxal = (double)(1 + s_nacc);
+        uint8_t* out = c.alt + c.alt_off[ci];
+        const uint32_t h_end = min(L, (s_tile.y + 1u) * 4096u);
+        for (uint32_t h = s_tile.y * 4096u + threadIdx.x; h < h_end; h += blockDim.x) {
+            unsigned long long cnt[4] = { 0, 0, 0, 0 }; int nal = 0;
+            for (uint32_t r0 = 0; r0 < no; r0 += 8) {
                 uint8_t cv[8];
                 #pragma unroll
                 for (int u = 0; u < 8; ++u) { const uint32_t r2 = r0 + u; cv[u] = (r2 < no && acc[r2]) ? rows[(size_t)r2 * L + h] : DASH; }
