@@ -501,7 +501,7 @@ static int run_stage_c(snfb_ctx* ctx) {
         mark(ctx, "consensus", ctx->h_ctr.n_seq_bytes * 16);
         if (c.use_items) {
             consensus::k_prep<<<148 * 8, 128, 0, ctx->st>>>(c);
-            consensus::k_align<<<148 * 5, consensus::ALIGN_WARPS * 32, 0, ctx->st>>>(c);
+            consensus::k_align<<<148 * 8, consensus::ALIGN_WARPS * 32, 0, ctx->st>>>(c);
             consensus::k_vote<<<148 * 4, 256, 0, ctx->st>>>(c); LAUNCHED(ctx, 3);
         } else {
         // heavy candidates (long insertions x many reads) first, with 16 warps each; then the bulk with 4 warps each

@@ -315,6 +315,39 @@ __global__ void __launch_bounds__(NW * 32) k_run(C c, int big) {
 // item from a heavy-first queue: no block barriers, the heaviest candidate's reads spread over the whole GPU)
 // -> k_vote (one block per (candidate, 4096-column tile)).
 // ================================================================================================
+// ---- byte-string helpers on unaligned pointers, four bytes per step (sliding aligned 32-bit windows).  They may read up to
+//      7 bytes past the last byte asked for; every buffer they are used on is followed by other scratch of the same candidate.
+__device__ __forceinline__ int match_count(const uint8_t* a, const uint8_t* b, long n) {
+    const uint32_t sa = ((uintptr_t)a & 3) * 8, sb = ((uintptr_t)b & 3) * 8;
+    const uint32_t* wa = reinterpret_cast<const uint32_t*>((uintptr_t)a & ~(uintptr_t)3); const uint32_t* wb = reinterpret_cast<const uint32_t*>((uintptr_t)b & ~(uintptr_t)3);
+    uint32_t alo = wa[0], blo = wb[0]; int mt = 0;
+    for (long q = 0; q < n; q += 4) {
+        const uint32_t ahi = *++wa, bhi = *++wb;
+        const uint32_t x = __funnelshift_r(alo, ahi, sa) ^ __funnelshift_r(blo, bhi, sb);
+        uint32_t eq = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;        // 0x80 in every byte that is equal
+        if (n - q < 4) eq &= (1u << (8 * (n - q))) - 1u;
+        mt += __popc(eq); alo = ahi; blo = bhi;
+    }
+    return mt;
+}
+__device__ __forceinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, long n) {
+    long q = 0;
+    while (q < n && ((uintptr_t)(dst + q) & 3)) { dst[q] = src[q]; ++q; }
+    if (q + 4 <= n) {
+        const uint8_t* s0 = src + q; const uint32_t sh = ((uintptr_t)s0 & 3) * 8;
+        const uint32_t* ws = reinterpret_cast<const uint32_t*>((uintptr_t)s0 & ~(uintptr_t)3); uint32_t lo = ws[0];
+        uint32_t* wd = reinterpret_cast<uint32_t*>(dst + q);
+        for (; q + 4 <= n; q += 4) { const uint32_t hi = *++ws; *wd++ = __funnelshift_r(lo, hi, sh); lo = hi; }
+    }
+    for (; q < n; ++q) dst[q] = src[q];
+}
+__device__ __forceinline__ void fill_dash(uint8_t* dst, long n) {
+    long q = 0;
+    while (q < n && ((uintptr_t)(dst + q) & 3)) dst[q++] = DASH;
+    for (; q + 4 <= n; q += 4) *reinterpret_cast<uint32_t*>(dst + q) = 0xffffffffu;
+    for (; q < n; ++q) dst[q] = DASH;
+}
+
 __device__ __forceinline__ uint8_t* cand_table(const C& c, uint32_t ci, uint32_t** keys, int** pos) {
     uint8_t* scr = c.scr + (size_t)c.scr_off[ci] * 16;
     uint8_t* end = scr + (size_t)c.scr_len[ci] * 16;
@@ -394,71 +427,65 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32) k_align(C c) {
         }
         if (nh > MAXHIT) nh = MAXHIT;
         __syncwarp();
-        // (2) anchor automaton over the hit list (consensus.py:306-338)
-        int na = 0; long last_i = -1, cl = 0;
-        for (int h = 0; h < nh; ++h) {
-            const int i = hi[h], j = hj[h];
-            if (na > 0 && i <= last_i) continue;
-            long before = cl;
-            if (na == 0) { if (j > 0) cl = i; before = 0; }
-            else { long fwd_j = (long)j - hj[na - 1]; if (cl + fwd_j > (long)L) fwd_j = (long)L - cl; cl += fwd_j; }
+        // (2) anchor automaton (consensus.py:306-338) in closed form: a hit is accepted iff its i exceeds every earlier hit's i
+        //     (the accepted hits are the left-to-right maxima), and len(conseq) before accepted hit m is
+        //     min(L, c0 + j[m-1] - j[0]) because every step appends min(j step, room left).  Compacted in place.
+        int na = 0, pm = -1;
+        for (int hb = 0; hb < nh; hb += 32) {
+            const int h = hb + lane; const int vi = h < nh ? hi[h] : -1, vj = h < nh ? hj[h] : 0;
+            int inc = vi;
+            #pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc = max(inc, t); }
+            int exc = __shfl_up_sync(FULL, inc, 1); if (lane == 0) exc = -1; exc = max(exc, pm);
+            const bool accp = h < nh && vi > exc;
+            const unsigned am = __ballot_sync(FULL, accp);
             __syncwarp();
-            if (lane == 0) { hi[na] = i; hj[na] = j; hcl[na] = (int)before; }
+            if (accp) { const int p = na + __popc(am & lanemask_lt()); hi[p] = vi; hj[p] = vj; }
+            na += __popc(am); pm = max(pm, __shfl_sync(FULL, inc, 31));
             __syncwarp();
-            ++na; last_i = i;
         }
-        // (3) segments in parallel: lane per segment
+        const long j0 = na ? hj[0] : 0, c0 = (na && j0 > 0) ? hi[0] : 0;
+        // (3a) lane per segment: agreement with the best read along the diagonal decides copy / dash; a copied segment also
+        //      gets its column identity (the bases it shares with the best read at the columns it lands on)
         long span = 0;
-        if (na > 0) { const long c0 = hj[0] > 0 ? hi[0] : 0; for (long q2 = lane; q2 < c0; q2 += 32) row[q2] = DASH; }
         for (int m = 1 + lane; m < na; m += 32) {
-            const long li = hi[m - 1], lj = hj[m - 1], i = hi[m], j = hj[m], cs = hcl[m];
+            const long li = hi[m - 1], lj = hj[m - 1], i = hi[m], j = hj[m];
+            long cs = c0 + lj - j0; if (cs > (long)L) cs = (long)L;
             const long d = j - lj; long fwd_j = d; if (cs + fwd_j > (long)L) fwd_j = (long)L - cs;
-            const long fwd_i = i - li; bool copy = false;
-            if (fwd_i == fwd_j && fwd_j > 0) {
-                span += d; int mt = 0;
-                #pragma unroll 8
-                for (long q2 = 1; q2 <= d; ++q2) mt += (li + q2 < (long)L && rd[lj + q2] == best[li + q2]) ? 1 : 0;
-                copy = __ddiv_rn((double)mt, (double)d) >= 0.5;
+            int st = -1;
+            if (i - li == fwd_j && fwd_j > 0) {
+                span += d;
+                long nc = (long)L - 1 - li; if (nc > d) nc = d;                       // positions past the end of the best read never match
+                const int mt = nc > 0 ? match_count(rd + lj + 1, best + li + 1, nc) : 0;
+                if (__ddiv_rn((double)mt, (double)d) >= 0.5) st = match_count(rd + lj, best + cs, fwd_j);
             }
-            if (copy) {
-                #pragma unroll 8
-                for (long q2 = 0; q2 < fwd_j; ++q2) row[cs + q2] = rd[lj + q2];
-            } else { for (long q2 = 0; q2 < fwd_j; ++q2) row[cs + q2] = DASH; }
+            hcl[m] = st;
         }
         span = (long)__reduce_add_sync(FULL, (unsigned)span);
-        for (long q2 = cl + lane; q2 < (long)L; q2 += 32) row[q2] = DASH;
         __syncwarp();
-        // (4) dash-free runs survive only with identity > 0.5 and more than 5 matches (consensus.py:343-360)
-        bool in_run = false; long run_start = 0; long ident = 0;
-        for (long hb = 0; hb < (long)L; hb += 128) {
-            uint8_t ccs[4], bbs[4];
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) { const long h = hb + 32 * u + lane; const bool in = h < (long)L; ccs[u] = in ? row[h] : DASH; bbs[u] = in ? best[h] : (uint8_t)0; }
-            #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long h0 = hb + 32 * u; if (h0 >= (long)L) break;
-                const uint8_t cc = ccs[u];
-                const unsigned nd = __ballot_sync(FULL, cc != DASH), mt = __ballot_sync(FULL, cc != DASH && cc == bbs[u]);
-                if (!in_run && nd == 0) continue;
-                int p = 0;
-                while (p < 32) {
-                    if (in_run) {
-                        const unsigned rest = ~(nd >> p); int cnt = rest ? __ffs(rest) - 1 : 32; if (cnt > 32 - p) cnt = 32 - p;
-                        const unsigned mask = cnt >= 32 ? 0xffffffffu : (((1u << cnt) - 1u) << p);
-                        ident += __popc(mt & mask); p += cnt;
-                        if (p < 32) {
-                            const long len = h0 + p - run_start;
-                            if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q2 = run_start + lane; q2 < h0 + p; q2 += 32) row[q2] = DASH;
-                            in_run = false;
-                        }
-                    } else {
-                        const unsigned rest = nd >> p; if (!rest) { p = 32; break; }
-                        p += __ffs(rest) - 1; in_run = true; run_start = h0 + p; ident = 0;
-                    }
-                }
+        // (3b) dash-free runs (= chains of copied segments) survive only with identity > 0.5 and more than 5 matches
+        //      (consensus.py:343-360); decided on the segment list before anything is written
+        {
+            bool in_run = false; int rs = 1; long ident = 0, rlen = 0;
+            for (int m = 1; m <= na; ++m) {
+                int st = -1; long len = 1;
+                if (m < na) { const long lj = hj[m - 1]; long cs = c0 + lj - j0; if (cs > (long)L) cs = (long)L; len = hj[m] - lj; if (cs + len > (long)L) len = (long)L - cs; st = hcl[m]; }
+                if (st >= 0) { if (!in_run) { in_run = true; rs = m; ident = 0; rlen = 0; } ident += st; rlen += len; continue; }
+                if (len == 0 || !in_run) continue;                                      // empty segments do not end a run
+                if (!(__ddiv_rn((double)ident, (double)rlen) > 0.5 && ident > 5)) for (int mm = rs + lane; mm < m; mm += 32) if (hcl[mm] >= 0) hcl[mm] = -1;
+                in_run = false;
             }
+            __syncwarp();
         }
-        if (in_run) { const long len = (long)L - run_start; if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q2 = run_start + lane; q2 < (long)L; q2 += 32) row[q2] = DASH; }
+        // (3c) write the row once
+        for (long q2 = lane; q2 < c0; q2 += 32) row[q2] = DASH;
+        for (int m = 1 + lane; m < na; m += 32) {
+            const long lj = hj[m - 1]; long cs = c0 + lj - j0; if (cs > (long)L) cs = (long)L;
+            long len = hj[m] - lj; if (cs + len > (long)L) len = (long)L - cs;
+            if (len > 0) { if (hcl[m] >= 0) copy_bytes(row + cs, rd + lj, len); else fill_dash(row + cs, len); }
+        }
+        { long cl = 0; if (na) { cl = c0 + hj[na - 1] - j0; if (cl > (long)L) cl = (long)L; }
+          for (long q2 = cl + lane; q2 < (long)L; q2 += 32) row[q2] = DASH; }
         if (lane == 0) acc[it.row] = __ddiv_rn((double)span, (double)L) > 0.2;
         __syncwarp();
     }
