@@ -48,14 +48,12 @@ def aligned_bp_passing(blk, cfg):
 
 
 def algorithmic_bytes_stage_a(blk, n_leads, n_pass):
-    """SURVEY.md 8(d) for the streaming kernel k_scan: per fetched record 36 + 4*n_cigar + aux(NM,HP,PS incl. 3-byte tag headers), read once
-    (query names and SA text are read by k_emit / k_sa, not by this kernel); writes 16 B per passing read + 32 B per event slice (<= 64 B per lead)."""
-    rec = blk.rec
-    a = rec["aux_flags"].astype(np.int64)
-    aux = ((a & 1) > 0) * 7 + ((a & 2) > 0) * 4 + ((a & 4) > 0) * 7 + ((a & 8) > 0) * (3 + rec["sa_len"].astype(np.int64))
-    aux = ((a & 1) > 0) * 7 + ((a & 2) > 0) * 4 + ((a & 4) > 0) * 7
-    rd = int((36 + 4 * rec["n_cigar"].astype(np.int64) + aux).sum())
-    return rd + 32 * int(n_leads) + 16 * int(n_pass), rd
+    """Algorithmic bytes of one launch of the streaming kernel k_scan: per record one 16-byte scan descriptor and
+    its CIGAR16 words (2 bytes each, the record's span rounded up to 16 bytes), read once; 12 bytes written per passing read
+    (reference end, lead count, NM correction).  The 32-byte event-slice entries (at most one per lead) are left out: a lower bound."""
+    w = blk.rec16["n_cigar"].astype(np.int64)
+    rd = int(16 * len(blk.rec16) + 2 * (((w + 7) // 8) * 8).sum())
+    return rd + 12 * int(n_pass), rd
 
 
 class ClockSampler(threading.Thread):
@@ -200,10 +198,13 @@ def run_b200(args):
     blk = workload(args, mask, max(1, ncores // world))
     abp_local = aligned_bp_passing(blk, cfg)
     L = binding.lib()
+    t0 = time.time()
+    blk.pack16()            # BAM CIGAR words -> CIGAR16, once per block (part of packing the block, like dropping the base qualities)
+    log(f"[bench] packed CIGAR16: {blk.cigar.nbytes / 1e9:.2f} GB -> {blk.cigar16.nbytes / 1e9:.2f} GB in {time.time() - t0:.1f}s")
     pinned = []
     if not args.no_pin:
         t0 = time.time()
-        for a in (blk.rec, blk.cigar, blk.var, blk.seq):
+        for a in (blk.rec16, blk.cigar16, blk.var, blk.seq):
             if a.nbytes and L.snfb_pin_host(C.c_void_p(a.ctypes.data), a.nbytes) == 0:
                 pinned.append(a)
         log(f"[bench] pinned {sum(a.nbytes for a in pinned) / 1e9:.2f} GB of host arenas in {time.time() - t0:.1f}s")
@@ -267,14 +268,14 @@ def run_b200(args):
 
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H every step) ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    full_bytes = blk.rec.nbytes + blk.cigar.nbytes + blk.var.nbytes + blk.seq.nbytes
+    full_bytes = blk.rec16.nbytes + blk.cigar16.nbytes + blk.var.nbytes + blk.seq.nbytes
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ctx.load(blk, seq_on_demand=not args.e2e_full_seq)      # host arenas; the 4-bit seq arena is fetched on demand (slices only)
         res, n_all = step()
     slice_bytes = sum(by for name, ms, by in ctx.timings() if name == "h2d_seq_slices")
-    h2d = blk.rec.nbytes + blk.cigar.nbytes + blk.var.nbytes + (blk.seq.nbytes if args.e2e_full_seq else slice_bytes)
+    h2d = blk.rec16.nbytes + blk.cigar16.nbytes + blk.var.nbytes + (blk.seq.nbytes if args.e2e_full_seq else slice_bytes)
     barrier()
     e2e_wall = (time.perf_counter() - t0) / e2e_steps
     d2h = res.cand.nbytes + res.cand_leads.nbytes + res.rnames.nbytes + res.alt.nbytes
@@ -300,7 +301,8 @@ def run_b200(args):
                "vs_baseline": None, "dtype": "int32", "data": "synthetic",
                "config": {"workload": f"BASELINE config {args.config}: synthetic 30x ONT WGS, 24 GRCh38-length contigs x scale {args.scale}, {abp_total / 1e9:.2f} Gbp aligned, germline",
                           "records_rank0": int(len(blk.rec)), "candidates_total": int(n_all), "parallelism": f"contig LPT over {world} GPU(s), one NCCL all-gather of candidates",
-                          "l2": f"inputs {full_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed"},
+                          "l2": f"inputs {full_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed",
+                          "cigar": f"CIGAR16 ({blk.cigar16.nbytes / 1e9:.2f} GB; the BAM words are {blk.cigar.nbytes / 1e9:.2f} GB)"},
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": float(et[0]) * 1e3,
                        "pinned": bool(pinned), "seq": "full arena" if args.e2e_full_seq else "on demand (slices requested by the device, gathered on the host)"},

@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define SNFB_ABI_VERSION 1
+#define SNFB_ABI_VERSION 2
 
 /* SV types in the reference's ALL_TYPES order (sv.py:31-33); the emission order of
  * candidates follows this order (parallel.py:106). */
@@ -48,6 +48,22 @@ enum { SNFB_SRC_INLINE = 0, SNFB_SRC_SPLIT_PRIM = 1, SNFB_SRC_SPLIT_SUP = 2, SNF
 #define SNFB_MEM_DEVICE 1u
 #define SNFB_MEM_HOST_SEQ_ON_DEMAND 2u
 
+/* snfb_records.cigar_fmt
+ *
+ * SNFB_CIGAR_BAM32: the BAM record's own words, len<<4|op (op: MIDNSHP=X = 0..8), 4 bytes per op.
+ *
+ * SNFB_CIGAR_16 (what the kernels read; snfb_pack_cigar16 produces it): 2-byte words, half the PCIe and HBM bytes.
+ *   base word       bit 15 = 0, bits 12..14 = class, bits 0..11 = length & 0xfff
+ *                   class: 0 P (and the zero-length pad word 0x0000), 1 I, 2 D, 3 M/=/X, 4 H, 5 S, 6 N
+ *                   (bit 12: the op advances the read, bit 13: it advances the reference, bit 14: clip / skip)
+ *   extension word  bit 15 = 1, bits 12..14 = level (1 or 2), bits 0..11 = payload: adds payload << (12 * level) to the
+ *                   length of the base word it follows (level 1, then level 2; lengths up to 2^28 as in BAM)
+ *   A base word and its extension words never straddle a 16-byte boundary and every record starts on one; the gaps and
+ *   the tail of the arena are filled with pad words, so a 16-byte load never needs masking.
+ *   M, = and X are one class: the path never tells them apart (leadprov.py:137-142 OPLIST). */
+#define SNFB_CIGAR_BAM32 0u
+#define SNFB_CIGAR_16 1u
+
 /* aux_flags bits of snfb_rec */
 #define SNFB_AUX_NM 1u
 #define SNFB_AUX_HP 2u
@@ -57,7 +73,7 @@ enum { SNFB_SRC_INLINE = 0, SNFB_SRC_SPLIT_PRIM = 1, SNFB_SRC_SPLIT_SUP = 2, SNF
 /* One packed alignment record: the fields of a BAM record the path reads,
  * fixed 64 bytes so a warp fetches it with one coalesced request.  Base qualities are
  * never shipped.  Variable-length parts live in three arenas of the block:
- *   cigar[cigar_off .. +n_cigar)   BAM encoding, len<<4|op (op: MIDNSHP=X = 0..8)
+ *   cigar[cigar_off .. +n_cigar)   CIGAR words in the block's cigar_fmt (SNFB_CIGAR_*)
  *   var[var_off .. +l_qname)       query name bytes (no NUL), followed by
  *   var[var_off+l_qname .. +sa_len) the SA:Z tag text (no NUL)
  *   seq[seq_off .. +(l_seq+1)/2)   BAM 4-bit bases ("=ACMGRSVTWYHKDBN"), high nibble first
@@ -73,11 +89,11 @@ typedef struct snfb_rec {
     uint16_t _pad0;
     int32_t  nm;          /* NM:i tag value                                             */
     int32_t  ps;          /* PS:i tag value                                             */
-    uint32_t n_cigar;
+    uint32_t n_cigar;     /* words of this record (CIGAR16: pad words inside included)   */
     int32_t  l_seq;       /* query_length (bases stored in seq)                         */
     uint32_t sa_len;
     uint32_t _pad1;
-    uint64_t cigar_off;   /* in 32-bit ops                                              */
+    uint64_t cigar_off;   /* in words of the block's cigar_fmt (CIGAR16: a multiple of 8) */
     uint64_t seq_off;     /* in bytes                                                   */
     uint64_t var_off;     /* in bytes                                                   */
 } snfb_rec;
@@ -106,11 +122,11 @@ typedef struct snfb_contig {
 
 typedef struct snfb_records {
     uint64_t n_rec;
-    uint64_t n_cigar;     /* total ops   */
+    uint64_t n_cigar;     /* words in the cigar arena (CIGAR16: a multiple of 8, padded)  */
     uint64_t n_var;       /* bytes       */
     uint64_t n_seq;       /* bytes       */
     const snfb_rec* rec;
-    const uint32_t* cigar;
+    const void*     cigar;   /* uint32_t[] (SNFB_CIGAR_BAM32) or uint16_t[] (SNFB_CIGAR_16) */
     const uint8_t*  var;
     const uint8_t*  seq;
     uint32_t n_task;
@@ -124,7 +140,7 @@ typedef struct snfb_records {
     /* optional: reference 'N' runs per task for LeadProvider._mask_N_coverage (leadprov.py:420-443, only with --reference):
      * n_mask half-open pairs (start,end), sorted and disjoint inside a task; task t owns mask[mask_task_off[t] .. mask_task_off[t+1]) */
     uint32_t n_mask;
-    uint32_t _pad2;
+    uint32_t cigar_fmt;   /* SNFB_CIGAR_*; BAM32 host arenas are converted on the host inside snfb_load_records (device arenas must be CIGAR16) */
     const int32_t*  mask;
     const uint32_t* mask_task_off;   /* [n_task + 1]; may be NULL when n_mask == 0 */
 } snfb_records;
@@ -294,6 +310,10 @@ int         snfb_device_candidates(snfb_ctx* ctx, void** dptr, uint64_t* n_cand)
 int         snfb_device_alt(snfb_ctx* ctx, void** dptr, uint64_t* n_bytes);
 /* number of kernels launched by the library on this ctx since it was created */
 uint64_t    snfb_launch_count(snfb_ctx* ctx);
+/* BAM CIGAR words -> CIGAR16 (host code, OpenMP; no GPU needed).  rec_out receives copies of rec_in with cigar_off / n_cigar
+ * rewritten for the 16-bit arena.  Call with out16 == NULL to get the number of 16-bit words the arena needs (a multiple
+ * of 8); returns that number, or UINT64_MAX when a record holds an op the path does not know (B) or out_cap is too small. */
+uint64_t    snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, snfb_rec* rec_out, uint16_t* out16, uint64_t out_cap);
 /* page-lock / unlock caller-owned host memory so that snfb_load_records copies at full PCIe rate */
 int         snfb_pin_host(void* p, size_t bytes);
 int         snfb_unpin_host(void* p);

@@ -260,7 +260,7 @@ static int classify_splits(const snfb_config* cfg, seg_t* s, int n, long l_seq) 
 static void process_read(task_t* T, uint64_t ri, double* rec_nm) {
     const snfb_records* R = T->R; const snfb_config* cfg = T->cfg; const snfb_rec* r = &R->rec[ri];
     const snfb_task* tk = &R->task[T->t];
-    const uint32_t* cg = R->cigar + r->cigar_off; long n = r->n_cigar;
+    const uint32_t* cg = (const uint32_t*)R->cigar + r->cigar_off;   /* the oracle reads BAM words (SNFB_CIGAR_BAM32) */ long n = r->n_cigar;
     if (rec_nm) rec_nm[ri] = -1.0;
     /* pysam query_alignment_start / _end */
     long qas = 0, qae = r->l_seq;

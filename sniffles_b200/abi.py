@@ -8,6 +8,7 @@ INS, DEL, DUP, INV, BND, SINGLE_LEFT, SINGLE_RIGHT = range(7)
 SVTYPE_NAMES = ["INS", "DEL", "DUP", "INV", "BND", "SINGLE_LEFT", "SINGLE_RIGHT"]  # sv.py:31-33 order
 SOURCE_NAMES = ["INLINE", "SPLIT_PRIM", "SPLIT_SUP", "BND_SA"]
 AUX_NM, AUX_HP, AUX_PS, AUX_SA = 1, 2, 4, 8
+CIGAR_BAM32, CIGAR_16 = 0, 1
 
 LF_REVERSE, LF_IS_SA, LF_SVLEN_NONE, LF_BND_FIRST, LF_BND_REVERSE, LF_HAS_SEQ = (1 << 5, 1 << 6, 1 << 7, 1 << 8, 1 << 9, 1 << 10)
 
@@ -47,7 +48,7 @@ class Records(C.Structure):
                 ("rec", C.c_void_p), ("cigar", C.c_void_p), ("var", C.c_void_p), ("seq", C.c_void_p),
                 ("n_task", C.c_uint32), ("n_contig", C.c_uint32), ("n_tr", C.c_uint32), ("on_device", C.c_uint32),
                 ("task", C.c_void_p), ("contig", C.c_void_p), ("tr", C.c_void_p),
-                ("n_mask", C.c_uint32), ("_pad2", C.c_uint32), ("mask", C.c_void_p), ("mask_task_off", C.c_void_p)]
+                ("n_mask", C.c_uint32), ("cigar_fmt", C.c_uint32), ("mask", C.c_void_p), ("mask_task_off", C.c_void_p)]
 
 
 class Config(C.Structure):

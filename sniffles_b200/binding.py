@@ -15,7 +15,7 @@ _LIB = None
 EXPORTS = ["snfb_version", "snfb_sizeof", "snfb_hash_name", "snfb_ctx_create", "snfb_ctx_destroy", "snfb_last_error", "snfb_set_config",
            "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
            "snfb_last_timings", "snfb_device_candidates", "snfb_device_alt", "snfb_launch_count",
-           "snfb_pin_host", "snfb_unpin_host"]
+           "snfb_pin_host", "snfb_unpin_host", "snfb_pack_cigar16"]
 
 
 def lib():
@@ -47,12 +47,30 @@ def lib():
         L.snfb_launch_count.argtypes = [C.c_void_p]
         L.snfb_pin_host.argtypes = [C.c_void_p, C.c_size_t]
         L.snfb_unpin_host.argtypes = [C.c_void_p]
+        L.snfb_pack_cigar16.restype = C.c_uint64
+        L.snfb_pack_cigar16.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         _LIB = L
     return _LIB
 
 
 class SnfbError(RuntimeError):
     pass
+
+
+def pack_cigar16(rec: np.ndarray, cigar32: np.ndarray):
+    """BAM CIGAR words -> (rec16, cigar16) of include/snfb.h (host code of the library; needs no GPU)."""
+    L = lib()
+    rec = np.ascontiguousarray(rec)
+    cigar32 = np.ascontiguousarray(cigar32, dtype="<u4")
+    need = L.snfb_pack_cigar16(rec.ctypes.data, len(rec), cigar32.ctypes.data, None, None, 0)
+    if need == 0xFFFFFFFFFFFFFFFF:
+        raise SnfbError("snfb_pack_cigar16: a CIGAR holds an operation the path does not know")
+    rec16 = np.empty(len(rec), abi.REC_DTYPE)
+    cigar16 = np.empty(int(need), "<u2")
+    got = L.snfb_pack_cigar16(rec.ctypes.data, len(rec), cigar32.ctypes.data, rec16.ctypes.data, cigar16.ctypes.data, int(need))
+    if got != need:
+        raise SnfbError("snfb_pack_cigar16 failed")
+    return rec16, cigar16
 
 
 class Result:
@@ -108,10 +126,11 @@ class Context:
     def set_config(self, cfg: abi.Config):
         self._check(self._lib.snfb_set_config(self._h, C.byref(cfg)), "snfb_set_config")
 
-    def load(self, block, seq_on_demand=False):
+    def load(self, block, seq_on_demand=False, cigar16=True):
         """block: sniffles_b200.synth.RecordBlock-like (numpy arenas) or an abi.Records struct.
-        seq_on_demand: leave the 4-bit seq arena on the host and fetch only the slices the consensus stage needs."""
-        rs = block if isinstance(block, abi.Records) else block.as_struct()
+        seq_on_demand: leave the 4-bit seq arena on the host and fetch only the slices the consensus stage needs.
+        cigar16: ship the CIGAR16 form (packed once per block); False hands the BAM words to the library, which converts them."""
+        rs = block if isinstance(block, abi.Records) else block.as_struct(cigar16=cigar16)
         if seq_on_demand:
             rs.on_device = 2
         self._block = block          # keep host arrays alive during the async copy

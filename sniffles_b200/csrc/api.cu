@@ -6,6 +6,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <omp.h>
 
 #include "common.cuh"
 #include "prims.cuh"
@@ -43,15 +44,16 @@ struct HostBuf {
 constexpr int MAX_TIMINGS = 64;
 
 struct snfb_ctx {
-    int device = 0; cudaStream_t st = nullptr, st2 = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr; std::string err;
+    int device = 0; cudaStream_t st = nullptr, st2 = nullptr, st_copy = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_copy = nullptr; bool want_cand_prefetch = false, cand_prefetched = false; std::string err;
     snfb_config cfg{}; bool have_cfg = false;
     // records
     bool loaded = false, on_device = false, seq_on_demand = false; const uint8_t* h_seq = nullptr;
     uint64_t n_rec = 0, n_cigar = 0, n_var = 0, n_seq = 0; uint32_t n_task = 0, n_contig = 0, n_tr = 0;
-    const snfb_rec* d_rec = nullptr; const uint32_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
+    const snfb_rec* d_rec = nullptr; const uint16_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
     DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp, b_mask, b_mask_off, b_mask_task; uint32_t n_mask = 0;
     // stage A outputs
-    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_ev_cnt, b_ev_slot, b_sa_list;
+    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_ev_cnt, b_ev_slot, b_sa_list, b_scanrec, b_clip, b_rec_big;
+    HostBuf h_c16, h_rec16;        // BAM32 host input converted to CIGAR16 before the upload
     unsigned long long lead_cap = 0;
     DevCounters h_ctr{};
     // stage B
@@ -105,8 +107,9 @@ int snfb_ctx_create(int device, snfb_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return 3;
     snfb_ctx* ctx = new snfb_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 4; }
-    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 4; }
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventCreate(&ctx->ev[i]);
     *out = ctx; return 0;
 }
@@ -116,7 +119,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_mask, &ctx->b_mask_off, &ctx->b_mask_task, &ctx->b_ctr, &ctx->b_leads, &ctx->b_rec_pos, &ctx->b_rec_end,
-        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_ev_cnt, &ctx->b_ev_slot, &ctx->b_sa_list,
+        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_ev_cnt, &ctx->b_ev_slot, &ctx->b_sa_list, &ctx->b_scanrec, &ctx->b_clip, &ctx->b_rec_big,
         &ctx->b_key0, &ctx->b_val0, &ctx->b_key1, &ctx->b_val1, &ctx->b_flag, &ctx->b_scan, &ctx->b_hist, &ctx->b_scan_tmp, &ctx->b_bin_start, &ctx->b_bin_nl, &ctx->b_bin_nlong, &ctx->b_bin_kept,
         &ctx->b_bin_hap, &ctx->b_kl_off, &ctx->b_kll_off, &ctx->b_kb_idx, &ctx->b_kl, &ctx->b_kll, &ctx->b_kb_bin, &ctx->b_kb_lead_off, &ctx->b_kb_lead_n, &ctx->b_kb_long_off, &ctx->b_kb_long_n,
         &ctx->b_kb_seed, &ctx->b_kb_chain, &ctx->b_kb_repeat, &ctx->b_seg_start, &ctx->b_c_next, &ctx->b_c_last, &ctx->b_c_sd, &ctx->b_c_mean, &ctx->b_c_rep, &ctx->b_seg_sd_last, &ctx->b_seg_maxsd,
@@ -126,10 +129,10 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
         &ctx->b_cand_leads, &ctx->b_cand_lead_ml, &ctx->b_rnames, &ctx->b_rn_off_out, &ctx->b_plan_best, &ctx->b_plan_nother, &ctx->b_alt_len, &ctx->b_scr_len, &ctx->b_alt_off, &ctx->b_scr_off,
         &ctx->b_alt, &ctx->b_scr, &ctx->b_sorted_leads, &ctx->b_work_big, &ctx->b_work_small, &ctx->b_work_ctr, &ctx->b_seq_req, &ctx->b_arena_off, &ctx->b_seq_arena, &ctx->b_items_big, &ctx->b_items_small, &ctx->b_tiles };
     for (DevBuf* b : bufs) b->release();
-    HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt, &ctx->h_seq_req, &ctx->h_seq_arena };
+    HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt, &ctx->h_seq_req, &ctx->h_seq_arena, &ctx->h_c16, &ctx->h_rec16 };
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventDestroy(ctx->ev[i]);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaStreamDestroy(ctx->st2); cudaStreamDestroy(ctx->st);
+    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_copy); cudaStreamDestroy(ctx->st_copy); cudaStreamDestroy(ctx->st2); cudaStreamDestroy(ctx->st);
     delete ctx;
 }
 
@@ -142,6 +145,54 @@ int snfb_set_config(snfb_ctx* ctx, const snfb_config* cfg) {
     ctx->cfg = *cfg; ctx->have_cfg = true; return 0;
 }
 
+// ---- BAM CIGAR words -> CIGAR16 (include/snfb.h).  Host code; the only place the 32-bit form is read. ----
+static inline int c16_group_words(uint32_t len) { return len < (1u << 12) ? 1 : (len < (1u << 24) ? 2 : 3); }
+static const uint8_t C16_CLASS[9] = { 3, 1, 2, 6, 5, 4, 0, 3, 3 };     // M I D N S H P = X
+// number of 16-bit words of one record, pad words included (a group never straddles an 8-word boundary); 0 = bad op
+static inline uint64_t c16_count(const uint32_t* cg, uint32_t n, bool* bad) {
+    uint64_t k = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        if ((cg[i] & 15u) > 8u) { *bad = true; return 0; }
+        const int g = c16_group_words(cg[i] >> 4);
+        if ((k & 7) + g > 8) k = (k + 7) & ~7ull;
+        k += g;
+    }
+    return k;
+}
+static inline void c16_write(const uint32_t* cg, uint32_t n, uint16_t* out) {
+    uint64_t k = 0;
+    for (uint32_t i = 0; i < n; ++i) {
+        const uint32_t len = cg[i] >> 4; const int g = c16_group_words(len);
+        if ((k & 7) + g > 8) { while (k & 7) out[k++] = 0; }
+        out[k++] = (uint16_t)((C16_CLASS[cg[i] & 15u] << 12) | (len & 0xfffu));
+        if (g >= 2) out[k++] = (uint16_t)(0x8000u | (1u << 12) | ((len >> 12) & 0xfffu));
+        if (g >= 3) out[k++] = (uint16_t)(0x8000u | (2u << 12) | ((len >> 24) & 0xfffu));
+    }
+}
+uint64_t snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, snfb_rec* rec_out, uint16_t* out16, uint64_t out_cap) {
+    if (n_rec && (!rec_in || !cigar32)) return UINT64_MAX;
+    std::vector<uint64_t> off(n_rec + 1, 0);
+    bool bad = false;
+    #pragma omp parallel for schedule(static) reduction(|| : bad)
+    for (long long i = 0; i < (long long)n_rec; ++i) { bool b = false; const uint64_t w = c16_count(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, &b); bad = bad || b; off[i + 1] = (w + 7) & ~7ull; }
+    if (bad) return UINT64_MAX;
+    for (uint64_t i = 0; i < n_rec; ++i) off[i + 1] += off[i];
+    const uint64_t total = off[n_rec] + 8;                       // one zero group of slack after the last record
+    if (!out16) return total;
+    if (!rec_out || out_cap < total) return UINT64_MAX;
+    #pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n_rec; ++i) {
+        uint16_t* dst = out16 + off[i]; const uint64_t span = off[i + 1] - off[i];
+        memset(dst, 0, 2 * span);
+        c16_write(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, dst);
+        bool b = false;
+        snfb_rec r = rec_in[i]; r.n_cigar = (uint32_t)c16_count(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, &b); r.cigar_off = off[i];
+        rec_out[i] = r;
+    }
+    memset(out16 + off[n_rec], 0, 16);
+    return total;
+}
+
 int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     if (!ctx || !R) return 1;
     cudaSetDevice(ctx->device);
@@ -151,17 +202,29 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     ctx->n_rec = R->n_rec; ctx->n_cigar = R->n_cigar; ctx->n_var = R->n_var; ctx->n_seq = R->n_seq;
     ctx->n_task = R->n_task; ctx->n_contig = R->n_contig; ctx->n_tr = R->n_tr; ctx->on_device = R->on_device == SNFB_MEM_DEVICE; ctx->seq_on_demand = R->on_device == SNFB_MEM_HOST_SEQ_ON_DEMAND; ctx->h_seq = ctx->seq_on_demand ? R->seq : nullptr;
     ctx->n_ev = 0;
-    mark(ctx, "h2d_records", sizeof(snfb_rec) * R->n_rec + 4 * R->n_cigar + R->n_var + (R->on_device == SNFB_MEM_HOST_SEQ_ON_DEMAND ? 0 : R->n_seq));
+    const snfb_rec* src_rec = R->rec; const uint16_t* src_cigar = reinterpret_cast<const uint16_t*>(R->cigar); uint64_t n_words = R->n_cigar;
+    if (R->cigar_fmt == SNFB_CIGAR_BAM32) {
+        if (R->on_device == SNFB_MEM_DEVICE) return fail(ctx, "device-resident records must carry CIGAR16 (convert with snfb_pack_cigar16)");
+        // host conversion: the kernels only read CIGAR16
+        const uint64_t need = snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), nullptr, nullptr, 0);
+        if (need == UINT64_MAX) return fail(ctx, "a CIGAR holds an operation the path does not know");
+        if (ctx->h_c16.ensure(2 * need + 16) || ctx->h_rec16.ensure(sizeof(snfb_rec) * (R->n_rec + 1))) return fail(ctx, "out of pinned memory for the CIGAR16 conversion");
+        if (snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), ctx->h_rec16.as<snfb_rec>(), ctx->h_c16.as<uint16_t>(), need) != need) return fail(ctx, "CIGAR16 conversion failed");
+        src_rec = ctx->h_rec16.as<snfb_rec>(); src_cigar = ctx->h_c16.as<uint16_t>(); n_words = need;
+    } else if (R->cigar_fmt != SNFB_CIGAR_16) return fail(ctx, "unknown cigar_fmt");
+    if (n_words & 7) return fail(ctx, "a CIGAR16 arena must be padded to a multiple of 8 words");
+    ctx->n_cigar = n_words;
+    mark(ctx, "h2d_records", sizeof(snfb_rec) * R->n_rec + 2 * n_words + R->n_var + (R->on_device == SNFB_MEM_HOST_SEQ_ON_DEMAND ? 0 : R->n_seq));
     if (ctx->on_device) {
-        ctx->d_rec = R->rec; ctx->d_cigar = R->cigar; ctx->d_var = R->var; ctx->d_seq = R->seq;     // caller keeps them alive; cigar must be padded by 16 bytes
+        ctx->d_rec = R->rec; ctx->d_cigar = src_cigar; ctx->d_var = R->var; ctx->d_seq = R->seq;     // caller keeps them alive
     } else {
-        if (ctx->b_rec.ensure(sizeof(snfb_rec) * (R->n_rec + 1)) || ctx->b_cigar.ensure(4 * (R->n_cigar + 8)) || ctx->b_var.ensure(R->n_var + 16) || (!ctx->seq_on_demand && ctx->b_seq.ensure(R->n_seq + 16)))
+        if (ctx->b_rec.ensure(sizeof(snfb_rec) * (R->n_rec + 1)) || ctx->b_cigar.ensure(2 * (n_words + 16)) || ctx->b_var.ensure(R->n_var + 16) || (!ctx->seq_on_demand && ctx->b_seq.ensure(R->n_seq + 16)))
             return fail(ctx, "out of device memory for the record block");
-        CUDA_TRY(cudaMemcpyAsync(ctx->b_rec.p, R->rec, sizeof(snfb_rec) * R->n_rec, cudaMemcpyHostToDevice, ctx->st));
-        CUDA_TRY(cudaMemcpyAsync(ctx->b_cigar.p, R->cigar, 4 * R->n_cigar, cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_rec.p, src_rec, sizeof(snfb_rec) * R->n_rec, cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_cigar.p, src_cigar, 2 * n_words, cudaMemcpyHostToDevice, ctx->st));
         CUDA_TRY(cudaMemcpyAsync(ctx->b_var.p, R->var, R->n_var, cudaMemcpyHostToDevice, ctx->st));
         if (!ctx->seq_on_demand) CUDA_TRY(cudaMemcpyAsync(ctx->b_seq.p, R->seq, R->n_seq, cudaMemcpyHostToDevice, ctx->st));
-        ctx->d_rec = ctx->b_rec.as<snfb_rec>(); ctx->d_cigar = ctx->b_cigar.as<uint32_t>(); ctx->d_var = ctx->b_var.as<uint8_t>(); ctx->d_seq = ctx->b_seq.as<uint8_t>();
+        ctx->d_rec = ctx->b_rec.as<snfb_rec>(); ctx->d_cigar = ctx->b_cigar.as<uint16_t>(); ctx->d_var = ctx->b_var.as<uint8_t>(); ctx->d_seq = ctx->b_seq.as<uint8_t>();
     }
     ctx->tasks.assign(R->task, R->task + R->n_task);
     if (ctx->b_task.ensure(sizeof(snfb_task) * R->n_task) || ctx->b_contig.ensure(sizeof(snfb_contig) * (R->n_contig + 1)) || ctx->b_tr.ensure(8 * ((size_t)R->n_tr + 1)) || ctx->b_trp.ensure(4 * ((size_t)R->n_tr + 1)))
@@ -272,39 +335,47 @@ static int run_stage_a(snfb_ctx* ctx) {
         if (ctx->b_ev.ensure(sizeof(extract::EvSlice) * ctx->lead_cap) || ctx->b_ev_cnt.ensure(4 * (ctx->lead_cap + 8)) || ctx->b_ev_slot.ensure(4 * (ctx->lead_cap + 8)) || ctx->b_sa_list.ensure(4 * (nrec + 1))
             || ctx->b_scan_tmp.ensure(4 * (prims::scan_tmp_elems(std::max<unsigned long long>(nrec, ctx->lead_cap)) + 16))) return fail(ctx, "out of device memory (stage A lists)");
         DevCounters* ctr = ctx->b_ctr.as<DevCounters>();
+        if (ctx->b_scanrec.ensure(sizeof(extract::RecScan) * (nrec + 1)) || ctx->b_clip.ensure(sizeof(extract::RecClip) * (nrec + 1)) || ctx->b_rec_big.ensure(4 * (nrec + 1))) return fail(ctx, "out of device memory (record descriptors)");
         extract::ScanParams S{};
-        S.rec = ctx->d_rec; S.cigar = ctx->d_cigar; S.task = ctx->b_task.as<snfb_task>(); S.n_rec = (uint32_t)nrec;
-        S.rec_end = ctx->b_rec_end.as<int32_t>(); S.rec_flags = ctx->b_rec_flags.as<uint8_t>(); S.rec_nm = ctx->b_rec_nm.as<double>(); S.rec_nlead = ctx->b_rec_nlead.as<uint32_t>();
-        S.task_reads = ctx->b_task_reads.as<uint32_t>(); S.task_cov_bp = ctx->b_task_cov.as<unsigned long long>(); S.task_maxspan = ctx->b_task_span.as<int32_t>();
+        S.scan = ctx->b_scanrec.as<extract::RecScan>(); S.cigar = ctx->d_cigar; S.task = ctx->b_task.as<snfb_task>(); S.n_rec = (uint32_t)nrec;
+        S.rec_end = ctx->b_rec_end.as<int32_t>(); S.rec_nlead = ctx->b_rec_nlead.as<uint32_t>(); S.rec_big = ctx->b_rec_big.as<int32_t>();
         S.ev = ctx->b_ev.as<extract::EvSlice>(); S.ev_cap = ctx->lead_cap; S.n_ev = &ctr->n_ev; S.sa_list = ctx->b_sa_list.as<uint32_t>(); S.n_sa = &ctr->n_sa; S.ctr = ctr;
-        S.minsv = cf.minsvlen_screen; S.mapq_min = cf.mapq; S.alen_min = cf.min_alignment_length; S.excl = cf.exclude_flags; S.want_nm = (cf.qc_nm_measure || cf.phase) ? 1 : 0;
+        S.minsv = cf.minsvlen_screen;
         uint32_t* task_first = ctx->b_task_first.as<uint32_t>(); uint32_t* task_last = ctx->b_task_last.as<uint32_t>();
+        uint8_t* rec_flags = ctx->b_rec_flags.as<uint8_t>(); double* rec_nm = ctx->b_rec_nm.as<double>();
         mark(ctx, "k_rec_index");
         if (nrec) {
-            extract::k_rec_index<<<(unsigned)((nrec + 255) / 256), 256, 0, ctx->st>>>(ctx->d_rec, (uint32_t)nrec, ctx->b_rec_pos.as<int32_t>(), task_first, task_last, ctr);
-            // algorithmic bytes of the streaming kernel: record cores + CIGAR + names/SA
-            mark(ctx, "k_scan", sizeof(snfb_rec) * nrec + 4 * ctx->n_cigar + ctx->n_var);
+            extract::IndexParams I{};
+            I.rec = ctx->d_rec; I.cigar = ctx->d_cigar; I.task = S.task; I.n_rec = (uint32_t)nrec; I.rec_pos = ctx->b_rec_pos.as<int32_t>(); I.task_first = task_first; I.task_last = task_last;
+            I.scan = ctx->b_scanrec.as<extract::RecScan>(); I.clip = ctx->b_clip.as<extract::RecClip>(); I.rec_end = S.rec_end; I.rec_flags = rec_flags; I.rec_nm = rec_nm; I.rec_nlead = S.rec_nlead; I.ctr = ctr;
+            I.mapq_min = cf.mapq; I.alen_min = cf.min_alignment_length; I.excl = cf.exclude_flags; I.want_nm = (cf.qc_nm_measure || cf.phase) ? 1 : 0;
+            extract::k_rec_index<<<(unsigned)((nrec + 255) / 256), 256, 0, ctx->st>>>(I);
+            // algorithmic bytes of the streaming kernel: scan descriptors + CIGAR16 words (+ its per-record outputs and event slices, added by bench.py)
+            mark(ctx, "k_scan", sizeof(extract::RecScan) * nrec + 2 * ctx->n_cigar);
             unsigned long long blocks = (nrec + 7) / 8; const unsigned long long maxb = 148ull * 6 * 4;
-            static const bool use_tma = []{ const char* e = getenv("SNFB_SCAN"); return e && strcmp(e, "tma") == 0; }();   // measured slower than the register-pipelined kernel (profiles/README.md)
-            if (use_tma) extract::k_scan_tma<<<(int)std::min<unsigned long long>((nrec + extract::tma::WPB - 1) / extract::tma::WPB, 148ull * 6 * 4), extract::tma::WPB * 32, 0, ctx->st>>>(S);
-            else extract::k_scan<<<(int)std::min(blocks, maxb), 256, 0, ctx->st>>>(S);
+            extract::k_scan<<<(int)std::min(blocks, maxb), 256, 0, ctx->st>>>(S);
+            mark(ctx, "k_rec_post");
+            extract::PostParams Q{};
+            Q.scan = I.scan; Q.clip = I.clip; Q.task = S.task; Q.n_rec = (uint32_t)nrec; Q.rec_end = S.rec_end; Q.rec_big = S.rec_big; Q.rec_nm = rec_nm;
+            Q.task_reads = ctx->b_task_reads.as<uint32_t>(); Q.task_cov_bp = ctx->b_task_cov.as<unsigned long long>(); Q.task_maxspan = ctx->b_task_span.as<int32_t>();
+            extract::k_rec_post<<<(unsigned)((nrec + 255) / 256), 256, 0, ctx->st>>>(Q); LAUNCHED(ctx, 1);
             mark(ctx, "k_emit");
             extract::k_ev_counts<<<grid_for(ctx->lead_cap, 256), 256, 0, ctx->st>>>(S.ev, ctx->b_ev_cnt.as<uint32_t>(), S.n_ev, ctx->lead_cap);
             LAUNCHED(ctx, 3 + prims::exclusive_scan(ctx->b_ev_cnt.as<uint32_t>(), ctx->b_ev_slot.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->lead_cap, &ctr->n_slots, ctx->st));
             extract::EmitParams E{};
-            E.rec = ctx->d_rec; E.cigar = ctx->d_cigar; E.var = ctx->d_var; E.task = S.task; E.ev = S.ev; E.ev_slot = ctx->b_ev_slot.as<uint32_t>(); E.n_ev = S.n_ev; E.ev_cap = ctx->lead_cap;
+            E.rec = ctx->d_rec; E.clip = ctx->b_clip.as<extract::RecClip>(); E.cigar = ctx->d_cigar; E.var = ctx->d_var; E.task = S.task; E.ev = S.ev; E.ev_slot = ctx->b_ev_slot.as<uint32_t>(); E.n_ev = S.n_ev; E.ev_cap = ctx->lead_cap;
             E.leads = ctx->b_leads.as<snfb_lead>(); E.lead_cap = ctx->lead_cap; E.ctr = ctr; E.minsv = cf.minsvlen_screen; E.maxlen = cf.dev_seq_cache_maxlen; E.detect_large_ins = cf.detect_large_ins;
             E.longinslen = (double)cf.long_ins_length / 2.0;
             extract::k_emit<<<148 * 32, 256, 0, ctx->st>>>(E);      // one warp per event slice; latency-bound, so oversubscribe
             mark(ctx, "k_sa");
             extract::SaParams A{};
-            A.rec = ctx->d_rec; A.cigar = ctx->d_cigar; A.var = ctx->d_var; A.task = S.task; A.contig = ctx->b_contig.as<snfb_contig>(); A.n_contig = ctx->n_contig;
+            A.rec = ctx->d_rec; A.clip = ctx->b_clip.as<extract::RecClip>(); A.var = ctx->d_var; A.task = S.task; A.contig = ctx->b_contig.as<snfb_contig>(); A.n_contig = ctx->n_contig;
             A.sa_list = S.sa_list; A.n_sa = S.n_sa; A.rec_end = S.rec_end; A.rec_nlead = S.rec_nlead; A.leads = E.leads; A.lead_cap = ctx->lead_cap; A.ctr = ctr; A.cfg = cf;
             extract::k_sa<<<148 * 10, extract::THREADS, 0, ctx->st>>>(A);
             mark(ctx, "k_task_nm");
             const int cpt = (int)((nrec + extract::NM_CHUNK - 1) / extract::NM_CHUNK);
             if (ctx->b_nm_part.ensure(8 * (size_t)cpt * nt + 8) || ctx->b_nm_cnt.ensure(4 * (size_t)cpt * nt + 8)) return fail(ctx, "out of device memory (nm partials)");
-            extract::k_nm_partial<<<dim3(cpt, nt), 256, 0, ctx->st>>>(S.rec_flags, S.rec_nm, task_first, task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>());
+            extract::k_nm_partial<<<dim3(cpt, nt), 256, 0, ctx->st>>>(rec_flags, rec_nm, task_first, task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>());
             extract::k_task_nm<<<nt, 256, 0, ctx->st>>>(task_first, task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>(), cpt, ctx->b_task_nm.as<double>()); LAUNCHED(ctx, 5);
         }
         mark(ctx, "scan_rec_leads");
@@ -415,19 +486,26 @@ static int run_stage_b(snfb_ctx* ctx) {
     return 0;
 }
 
-static int fill_cand_view(snfb_ctx* ctx, snfb_cand_view* out) {
+// the bulk of the candidate view (lead table, read names) is final once stage B is done: in snfb_run it is copied on its own
+// stream while the consensus kernels run
+static int cand_bulk_copy(snfb_ctx* ctx, cudaStream_t stream) {
+    const DevCounters& c = ctx->h_ctr;
+    if (c.n_cand > ctx->cand_cap || c.n_cand_leads > ctx->cand_lead_cap || c.n_rnames > ctx->rn_cap) return fail(ctx, "candidate output buffers too small");
+    if (ctx->h_cand.ensure(sizeof(snfb_cand) * (c.n_cand + 1)) || ctx->h_cand_leads.ensure(sizeof(snfb_lead) * (c.n_cand_leads + 1)) || ctx->h_rnames.ensure(8 * (c.n_rnames + 1)) || ctx->h_rn_off.ensure(4 * (c.n_cand + 2)) || ctx->h_task_cov.ensure(8 * ctx->n_task))
+        return fail(ctx, "out of pinned memory for the candidate view");
+    if (c.n_cand) CUDA_TRY(cudaMemcpyAsync(ctx->h_rn_off.p, ctx->b_rn_off_out.p, 4 * c.n_cand, cudaMemcpyDeviceToHost, stream));
+    if (c.n_cand_leads) CUDA_TRY(cudaMemcpyAsync(ctx->h_cand_leads.p, ctx->b_cand_leads.p, sizeof(snfb_lead) * c.n_cand_leads, cudaMemcpyDeviceToHost, stream));
+    if (c.n_rnames) CUDA_TRY(cudaMemcpyAsync(ctx->h_rnames.p, ctx->b_rnames.p, 8 * c.n_rnames, cudaMemcpyDeviceToHost, stream));
+    return 0;
+}
+
+static int fill_cand_view(snfb_ctx* ctx, snfb_cand_view* out, bool cand_copied_later = false) {
     if (fetch_counters(ctx)) return 1;
     const DevCounters& c = ctx->h_ctr; const uint32_t nt = ctx->n_task;
     if (c.scratch_overflow) return fail(ctx, "candidate output buffers overflowed");
-    if (c.n_cand > ctx->cand_cap || c.n_cand_leads > ctx->cand_lead_cap || c.n_rnames > ctx->rn_cap) return fail(ctx, "candidate output buffers too small");
-    if (ctx->h_cand.ensure(sizeof(snfb_cand) * (c.n_cand + 1)) || ctx->h_cand_leads.ensure(sizeof(snfb_lead) * (c.n_cand_leads + 1)) || ctx->h_rnames.ensure(8 * (c.n_rnames + 1)) || ctx->h_rn_off.ensure(4 * (c.n_cand + 2)) || ctx->h_task_cov.ensure(8 * nt))
-        return fail(ctx, "out of pinned memory for the candidate view");
-    if (c.n_cand) {
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_cand.p, ctx->b_cand.p, sizeof(snfb_cand) * c.n_cand, cudaMemcpyDeviceToHost, ctx->st));
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_rn_off.p, ctx->b_rn_off_out.p, 4 * c.n_cand, cudaMemcpyDeviceToHost, ctx->st));
-    }
-    if (c.n_cand_leads) CUDA_TRY(cudaMemcpyAsync(ctx->h_cand_leads.p, ctx->b_cand_leads.p, sizeof(snfb_lead) * c.n_cand_leads, cudaMemcpyDeviceToHost, ctx->st));
-    if (c.n_rnames) CUDA_TRY(cudaMemcpyAsync(ctx->h_rnames.p, ctx->b_rnames.p, 8 * c.n_rnames, cudaMemcpyDeviceToHost, ctx->st));
+    if (ctx->cand_prefetched) { CUDA_TRY(cudaStreamSynchronize(ctx->st_copy)); ctx->cand_prefetched = false; }
+    else if (cand_bulk_copy(ctx, ctx->st)) return 1;
+    if (c.n_cand && !cand_copied_later) CUDA_TRY(cudaMemcpyAsync(ctx->h_cand.p, ctx->b_cand.p, sizeof(snfb_cand) * c.n_cand, cudaMemcpyDeviceToHost, ctx->st));
     std::vector<unsigned long long> cov(nt);
     CUDA_TRY(cudaMemcpyAsync(cov.data(), ctx->b_task_cov.p, 8 * nt, cudaMemcpyDeviceToHost, ctx->st));
     CUDA_TRY(cudaStreamSynchronize(ctx->st));
@@ -463,6 +541,11 @@ static int run_stage_c(snfb_ctx* ctx) {
     LAUNCHED(ctx, prims::exclusive_scan(c.scr_len, c.scr_off, ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->cand_cap, &c.ctr->n_seq_bytes, ctx->st));
     mark(ctx, nullptr);
     if (fetch_counters(ctx)) return 1;
+    if (ctx->want_cand_prefetch) {        // stage B's outputs are final: start their device -> host copy next to the consensus kernels
+        CUDA_TRY(cudaEventRecord(ctx->ev_copy, ctx->st)); CUDA_TRY(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_copy, 0));
+        if (cand_bulk_copy(ctx, ctx->st_copy)) return 1;
+        ctx->cand_prefetched = true;
+    }
     if (ctx->h_ctr.n_seq_bytes > 0xfffffff0ull) return fail(ctx, "consensus scratch exceeds 64 GiB");
     if (ctx->b_alt.ensure(ctx->h_ctr.n_alt_bytes + 16) || ctx->b_scr.ensure(ctx->h_ctr.n_seq_bytes * 16 + 64)) return fail(ctx, "out of device memory (consensus)");
     c.alt = ctx->b_alt.as<uint8_t>(); c.scr = ctx->b_scr.as<uint8_t>(); c.alt_cap = ctx->h_ctr.n_alt_bytes; c.scr_cap16 = ctx->h_ctr.n_seq_bytes;
@@ -557,9 +640,12 @@ int snfb_consensus(snfb_ctx* ctx, snfb_seq_view* out) {
 int snfb_run(snfb_ctx* ctx, snfb_lead_view* leads, snfb_cand_view* cands, snfb_seq_view* seqs) {
     if (!ctx) return 1;
     ctx->n_ev = ctx->n_ev_load;
-    if (run_stage_a(ctx) || run_stage_b(ctx) || run_stage_c(ctx)) return 1;
+    ctx->want_cand_prefetch = cands != nullptr; ctx->cand_prefetched = false;
+    const int rc = run_stage_a(ctx) || run_stage_b(ctx) || run_stage_c(ctx);
+    ctx->want_cand_prefetch = false;
+    if (rc) { if (ctx->cand_prefetched) { cudaStreamSynchronize(ctx->st_copy); ctx->cand_prefetched = false; } return 1; }
     if (leads) { memset(leads, 0, sizeof *leads); if (fill_lead_view(ctx, leads)) return 1; }
-    if (cands) { memset(cands, 0, sizeof *cands); if (fill_cand_view(ctx, cands)) return 1; }
+    if (cands) { memset(cands, 0, sizeof *cands); if (fill_cand_view(ctx, cands, true)) return 1; }
     if (seqs) memset(seqs, 0, sizeof *seqs);
     if (fill_seq_view(ctx, seqs, cands)) return 1;
     if (!cands) { if (ctx->h_ctr.unverified_breaks) return fail(ctx, "a chain cut could not be verified"); }

@@ -1,8 +1,7 @@
 // extract.cuh — stage A: alignment records -> SV leads.
 //
-// One warp per alignment record.  The warp streams the record's CIGAR with 16-byte loads
-// (128 ops per iteration, coalesced), turns op lengths into running read/reference
-// positions with a shuffle scan, and appends a 64-byte lead for every signature it meets.
+// One warp per alignment record streams the record's CIGAR16 words with 16-byte loads (256 words
+// per warp step, coalesced); SV signatures become 64-byte leads in a second, event-driven pass.
 // Reference behaviour reproduced (paths relative to /root/reference/src/sniffles/):
 //   LeadProvider.iter_region filters / NM / coverage bookkeeping     leadprov.py:474-581
 //   get_cigar_indels                                                  leadprov.py:198-224
@@ -18,19 +17,6 @@ namespace extract {
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
 constexpr int MAXSEG = 40;     // primary + supplementary segments per read held in shared memory
-
-struct Params {
-    const snfb_rec* rec; const uint32_t* cigar; const uint8_t* var;
-    const snfb_task* task; const snfb_contig* contig;
-    uint32_t n_rec, n_task, n_contig;
-    snfb_lead* leads; unsigned long long lead_cap;
-    // per-record outputs
-    int32_t* rec_pos; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
-    // per-task outputs
-    uint32_t* task_first; uint32_t* task_last; uint32_t* task_reads; unsigned long long* task_cov_bp; int32_t* task_maxspan;
-    DevCounters* ctr;
-    snfb_config cfg;
-};
 
 // rec_flags bits
 constexpr uint8_t RF_PASS = 1, RF_HAS_NM = 2;   // bits 2..3: hp
@@ -162,7 +148,7 @@ __device__ __forceinline__ unsigned long long alloc_slot_lane(SlotState& st, snf
 struct SaArgs {
     uint32_t rec; int qas, qae, alen, ref_end, hp; uint32_t base_flags; uint64_t qh; unsigned nlead; bool rev, is_supp;
     // the pieces of Params / snfb_rec / snfb_task the SA path needs, by value (keeps the caller's structs out of local memory)
-    const uint8_t* sa; int sa_len; uint32_t c_first, c_last; int pos, l_seq, mapq, aux_flags, task;
+    const uint8_t* sa; int sa_len; int clip_left, clip_right; int pos, l_seq, mapq, aux_flags, task;
     int tk_contig, tk_start, tk_end;
     const snfb_contig* contig; uint32_t n_contig; snfb_lead* leads; unsigned long long lead_cap; unsigned long long* n_slots; SlotState* slots;
     int mapq_min, dev_keep_lowqual_splits, max_splits_base; double max_splits_kb;
@@ -182,9 +168,7 @@ __device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp
     if (ne > 0 && !sa_fields_dev(sa + f_off, f_len, &e0)) { sa_ok = false; ++soft; }
     if (ne > 0 && sa_ok) {                                   // Lead.for_bnd: first entry only
         const uint8_t* e = sa + f_off;
-        int left = 0, right = 0;
-        { uint32_t c = a.c_first; int op = c & 15; if (op == 4 || op == 5) left = (int)(c >> 4); }
-        { uint32_t c = a.c_last; int op = c & 15; if (op == 4 || op == 5) right = (int)(c >> 4); }
+        const int left = a.clip_left, right = a.clip_right;
         int bstart; bool is_first;
         if (left > right) { bstart = r.pos + 1; is_first = false; } else { bstart = a.ref_end; is_first = true; }
         const bool same = e0.len[2] == 1 && ((e[e0.off[2]] == '-' && rev) || (e[e0.off[2]] == '+' && !rev));
@@ -264,54 +248,128 @@ __device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp
     return added;
 }
 
-// record index: task boundaries, start positions and the coordinate-order check (one thread per record)
-__global__ void __launch_bounds__(256) k_rec_index(const snfb_rec* __restrict__ rec, uint32_t n_rec, int32_t* __restrict__ rec_pos, uint32_t* __restrict__ task_first,
-                                                   uint32_t* __restrict__ task_last, DevCounters* ctr) {
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x; if (i >= n_rec) return;
-    const int2 tp = __ldg(reinterpret_cast<const int2*>(rec + i));            // (task, pos)
-    rec_pos[i] = tp.y;
-    if (i == 0) task_first[tp.x] = 0;
-    else { const int2 pv = __ldg(reinterpret_cast<const int2*>(rec + i - 1)); if (pv.x != tp.x) { task_first[tp.x] = i; task_last[pv.x] = i; } else if (pv.y > tp.y) atomicAdd(&ctr->unsorted, 1ULL); }
-    if (i + 1 == n_rec) task_last[tp.x] = n_rec;
-}
-
-// per-op flags for ops 0..7 (M I D N S H P =): bit0 advances the read, bit1 advances the reference
-__device__ __forceinline__ unsigned op_flags(unsigned op) {
-    const unsigned b = __byte_perm(0x02020103u, 0x03000001u, op) & 3u;
-    return op == 8u ? 3u : b;                      // X (only with --eqx) behaves like M
-}
-
 // ================================================================================================
-// Stage A is three kernels:
-//   k_scan  (hot, HBM-bound): one warp per record streams the CIGAR once: filters, reference end, the NM correction,
-//           coverage bookkeeping — and for every 128-op slice that holds an SV signature just one 32-byte "event slice"
-//           entry.  No lead is built here, which keeps the streaming loop small (registers, I-cache).
+// Stage A kernels:
+//   k_rec_index (thread per record): task boundaries, sortedness, and everything that only needs the record core and the
+//           clip ops at the two ends of its CIGAR: query_alignment_start/end, the read filters of iter_region, the
+//           16-byte scan descriptor k_scan streams from and the clip facts k_emit / k_sa use.
+//   k_scan  (hot, HBM-bound): one warp per passing record streams its CIGAR16 words once (16-byte loads, 256 words per
+//           warp step): reference end, the NM correction, lead counts — and for every 256-word slice that holds an SV
+//           signature one 32-byte "event slice" entry.  No lead is built here.
+//   k_rec_post (thread per record): nm per read (the division), per-task read count / covered bases / longest span.
 //   k_emit  one warp per event slice: reload the slice (L2), prefix positions, write the 64-byte leads to exact slots.
 //   k_sa    one warp per record with an SA tag: Lead.for_bnd + read_itersplits (lane-serial text parsing).
 // ================================================================================================
+// CIGAR16 classes (include/snfb.h): bit 0 = advances the read, bit 1 = advances the reference
+constexpr unsigned C16_I = 1, C16_D = 2, C16_M = 3, C16_H = 4, C16_S = 5;
+__device__ __forceinline__ bool c16_is_event(unsigned cls) { return (0x26u >> cls) & 1u; }        // I D S
+
+// the eight 16-bit words one lane holds -> up to eight ops at their word positions (cls 0 / len 0 where a pad, P or
+// extension word sits).  Groups never straddle a 16-byte boundary, so this is lane-local.
+__device__ __forceinline__ void c16_decode8(const uint32_t (&ww)[4], unsigned (&cls)[8], unsigned (&len)[8]) {
+    unsigned x[8];
+    #pragma unroll
+    for (int h = 0; h < 8; ++h) x[h] = (ww[h >> 1] >> (16 * (h & 1))) & 0xffffu;
+    #pragma unroll
+    for (int h = 0; h < 8; ++h) {
+        unsigned c = 0, l = 0;
+        if (!(x[h] & 0x8000u)) {
+            c = (x[h] >> 12) & 7u; l = x[h] & 0xfffu;
+            if (h + 1 < 8 && (x[h + 1 < 8 ? h + 1 : 7] & 0x8000u)) {
+                const unsigned e1 = x[h + 1 < 8 ? h + 1 : 7]; l += (e1 & 0xfffu) << (12u * ((e1 >> 12) & 7u));
+                if (h + 2 < 8 && (x[h + 2 < 8 ? h + 2 : 7] & 0x8000u)) { const unsigned e2 = x[h + 2 < 8 ? h + 2 : 7]; l += (e2 & 0xfffu) << (12u * ((e2 >> 12) & 7u)); }
+            }
+        }
+        cls[h] = c; len[h] = l;
+    }
+}
+
+struct RecScan { uint32_t cig8; uint32_t n_words; int32_t pos; uint32_t meta; };    // what k_scan needs, one 16-byte load
+struct RecClip { int32_t alen, qas, clip_left, clip_right; };                        // query_alignment_length/start, first / last op if it is a clip
+constexpr uint32_t RM_PASS = 1u << 24, RM_HAS_NM = 1u << 25, RM_HAS_SA = 1u << 26;   // RecScan.meta: task (0..15) | mapq (16..23) | flags | hp (27..28)
+
+struct IndexParams {
+    const snfb_rec* rec; const uint16_t* cigar; const snfb_task* task; uint32_t n_rec;
+    int32_t* rec_pos; uint32_t* task_first; uint32_t* task_last;
+    RecScan* scan; RecClip* clip; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
+    DevCounters* ctr; int mapq_min, alen_min, excl, want_nm;
+};
+// leadprov.py:488-516 (filters), pysam query_alignment_start / query_alignment_end
+__global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x; if (i >= P.n_rec) return;
+    const uint4* core = reinterpret_cast<const uint4*>(P.rec + i);
+    const uint4 c0 = __ldg(core), c1 = __ldg(core + 1), c2 = __ldg(core + 2);
+    const int task = (int)c0.x, pos = (int)c0.y; const unsigned flag = c0.z & 0xffffu, mapq = (c0.z >> 16) & 255u, aux = c0.z >> 24; unsigned hp = c0.w & 255u;
+    const int nm = (int)c1.x; const uint32_t n = c1.z; const int l_seq = (int)c1.w;
+    const unsigned long long cigar_off = (unsigned long long)c2.z | ((unsigned long long)c2.w << 32);
+    P.rec_pos[i] = pos;
+    if (i == 0) P.task_first[task] = 0;
+    else { const int2 pv = __ldg(reinterpret_cast<const int2*>(P.rec + i - 1)); if (pv.x != task) { P.task_first[task] = i; P.task_last[pv.x] = i; } else if (pv.y > pos) atomicAdd(&P.ctr->unsorted, 1ULL); }
+    if (i + 1 == P.n_rec) P.task_last[task] = P.n_rec;
+    // clips at the two ends
+    const uint16_t* cg = P.cigar + cigar_off;
+    int qas = 0, qae = l_seq, clip_left = 0, clip_right = 0; uint32_t fe = 0;
+    { bool first = true; uint32_t k = 0;
+      while (k < n) {
+          const unsigned w = __ldg(cg + k); if (w == 0) { ++k; continue; }
+          unsigned len = w & 0xfffu; const unsigned cls = (w >> 12) & 7u; uint32_t k2 = k + 1;
+          while (k2 < n) { const unsigned e = __ldg(cg + k2); if (!(e & 0x8000u)) break; len += (e & 0xfffu) << (12u * ((e >> 12) & 7u)); ++k2; }
+          if (first) { if (cls == C16_S || cls == C16_H) clip_left = (int)len; first = false; fe = k2; }
+          if (cls == C16_S) qas += (int)len; else if (cls != C16_H) break;
+          k = k2;
+      } }
+    { bool last = true; long k = (long)n - 1;
+      while (k >= (long)fe) {
+          long b = k; while (b > (long)fe && (__ldg(cg + b) & 0x8000u)) --b;
+          const unsigned w = __ldg(cg + b); if (w == 0) { k = b - 1; continue; }
+          unsigned len = w & 0xfffu; const unsigned cls = (w >> 12) & 7u;
+          for (long e2 = b + 1; e2 <= k; ++e2) { const unsigned e = __ldg(cg + e2); len += (e & 0xfffu) << (12u * ((e >> 12) & 7u)); }
+          if (last) { if (cls == C16_S || cls == C16_H) clip_right = (int)len; last = false; }
+          if (cls == C16_S) qae -= (int)len; else if (cls != C16_H) break;
+          k = b - 1;
+      }
+      if (last) clip_right = clip_left; }            // a single op is both the first and the last one
+    const int alen = qae - qas;
+    const snfb_task tk = P.task[task];
+    const bool pass = !((int)mapq < P.mapq_min || (flag & 256u) || alen < P.alen_min) && !(P.excl && (flag & (unsigned)P.excl)) && pos >= tk.start && pos < tk.end && n > 0;
+    const bool has_nm = pass && P.want_nm && (aux & SNFB_AUX_NM);
+    if (!(aux & SNFB_AUX_HP)) hp = 0;
+    if (pass && hp > 2) { hp = 0; atomicAdd(&P.ctr->soft_errors, 1ULL); }
+    RecScan s; s.cig8 = (uint32_t)(cigar_off >> 3); s.n_words = n; s.pos = pos;
+    s.meta = ((uint32_t)task & 0xffffu) | (mapq << 16) | (pass ? RM_PASS : 0u) | (has_nm ? RM_HAS_NM : 0u) | ((pass && (aux & SNFB_AUX_SA)) ? RM_HAS_SA : 0u) | ((pass ? hp : 0u) << 27);
+    *reinterpret_cast<uint4*>(P.scan + i) = *reinterpret_cast<const uint4*>(&s);
+    RecClip c; c.alen = alen; c.qas = qas; c.clip_left = clip_left; c.clip_right = clip_right;
+    *reinterpret_cast<int4*>(P.clip + i) = *reinterpret_cast<const int4*>(&c);
+    P.rec_flags[i] = pass ? (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2)) : (uint8_t)0;
+    P.rec_nm[i] = has_nm ? (double)nm : -1.0;        // k_rec_post turns it into (nm - big) / (alen + 1)
+    P.rec_end[i] = -1; P.rec_nlead[i] = 0;
+}
+
 struct EvSlice { uint32_t rec; int32_t base; uint32_t pos_q; int32_t pos_r; uint32_t k0; uint32_t count; uint32_t slot0; uint32_t pad; };
 
 struct ScanParams {
-    const snfb_rec* rec; const uint32_t* cigar; const snfb_task* task;
+    const RecScan* scan; const uint16_t* cigar; const snfb_task* task;
     uint32_t n_rec;
-    int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
-    uint32_t* task_reads; unsigned long long* task_cov_bp; int32_t* task_maxspan;
+    int32_t* rec_end; uint32_t* rec_nlead; int32_t* rec_big;
     EvSlice* ev; unsigned long long ev_cap; unsigned long long* n_ev;
     uint32_t* sa_list; unsigned long long* n_sa;
     DevCounters* ctr;
-    int minsv, mapq_min, alen_min, excl, want_nm;
+    int minsv;
 };
 
-// rare path of k_scan: a slice with at least one op longer than 10 that is not a match.  Returns (big << 32) | leads counted.
-__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr,
+// rare path of k_scan: a slice with an I/D longer than 10, a clip / skip op or an extension word.
+// Returns (big << 32) | leads counted.
+__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lr,
                                                       uint32_t rec, int base, unsigned pos_q, int pos_r, unsigned k0, int tk_start, int tk_end) {
     const int lane = lane_id();
     const uint32_t ww[4] = { w0, w1, w2, w3 };
+    unsigned cls[8], len[8];
+    c16_decode8(ww, cls, len);
     unsigned big = 0, evm = 0;
     #pragma unroll
-    for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4;
-        if (len > 10u && (op == 1u || op == 2u)) big += len;                      // get_cigar_indels, minoplen 10
-        if (((0x016u >> op) & 1u) && (int)len >= P->minsv) evm |= 1u << j; }
+    for (int j = 0; j < 8; ++j) {
+        if (len[j] > 10u && (cls[j] == C16_I || cls[j] == C16_D)) big += len[j];             // get_cigar_indels, minoplen 10
+        if (c16_is_event(cls[j]) && (int)len[j] >= P->minsv) evm |= 1u << j; }
     big = __reduce_add_sync(FULL, big);
     unsigned count = 0;
     if (__any_sync(FULL, evm != 0)) {
@@ -320,9 +378,9 @@ __device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restric
         for (int o = 1; o < 32; o <<= 1) { unsigned tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) ir += tr; }
         int r2 = pos_r + (int)(ir - lr); unsigned cnt = 0;
         #pragma unroll
-        for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4;
-            if (evm & (1u << j)) { const int rs = op == 2u ? r2 + (int)len : r2; cnt += (rs >= tk_start && rs < tk_end); }
-            r2 += (int)(len * (op_flags(op) >> 1)); }
+        for (int j = 0; j < 8; ++j) {
+            if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; cnt += (rs >= tk_start && rs < tk_end); }
+            r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); }
         count = __reduce_add_sync(FULL, cnt);
         if (count && lane == 0) {
             const unsigned long long e = atomicAdd(P->n_ev, 1ULL);
@@ -334,230 +392,92 @@ __device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restric
     return ((unsigned long long)big << 32) | count;
 }
 
+// read / reference advance of a lane's eight words when one of them is an extension word
+__device__ __noinline__ uint2 lane_sums_ext(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
+    const uint32_t ww[4] = { w0, w1, w2, w3 };
+    unsigned cls[8], len[8]; c16_decode8(ww, cls, len);
+    unsigned lq = 0, lr = 0;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) { lq += len[j] * (cls[j] & 1u); lr += len[j] * ((cls[j] >> 1) & 1u); }
+    return make_uint2(lq, lr);
+}
+
 __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanParams P) {
     const int lane = lane_id();
     const unsigned nwarps = gridDim.x * 8;
-    int acc_task = -1; unsigned acc_reads = 0; unsigned long long acc_bp = 0; int acc_span = 0;
-    int tk_id = -1, tk_start = 0, tk_end = 0, tk_len = 0;
+    int tk_id = -1, tk_start = 0, tk_end = 0;
     unsigned rec = blockIdx.x * 8 + (threadIdx.x >> 5);
-    uint32_t wnext = (rec < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + rec) + lane) : 0u;
+    uint4 dnext = rec < P.n_rec ? __ldg(reinterpret_cast<const uint4*>(P.scan + rec)) : make_uint4(0, 0, 0, 0);
     for (; rec < P.n_rec; rec += nwarps) {
-        const uint32_t wcur = wnext;
-        { const unsigned nrec2 = rec + nwarps; wnext = (nrec2 < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + nrec2) + lane) : 0u; }
-        const int r_task = (int)__shfl_sync(FULL, wcur, 0), r_pos = (int)__shfl_sync(FULL, wcur, 1);
-        const uint32_t x2 = __shfl_sync(FULL, wcur, 2);
-        const int r_flag = x2 & 0xffff, r_mapq = (x2 >> 16) & 255, r_aux = x2 >> 24;
-        const int n = (int)__shfl_sync(FULL, wcur, 6), r_lseq = (int)__shfl_sync(FULL, wcur, 7);
-        const uint64_t cigar_off = (uint64_t)__shfl_sync(FULL, wcur, 10) | ((uint64_t)__shfl_sync(FULL, wcur, 11) << 32);
-        const uint32_t* __restrict__ cg = P.cigar + cigar_off;
-        const int mis = (int)(cigar_off & 3);
-        const uint4* __restrict__ cga = reinterpret_cast<const uint4*>(cg - mis) + lane;
-        const int n_al = n + mis, li0 = lane * 4;
-        #define LOAD_SLICE(base) (((base) + li0 < n_al) ? __ldg(cga + ((base) >> 2)) : make_uint4(0, 0, 0, 0))
-        uint4 va = LOAD_SLICE(0), vb = LOAD_SLICE(128), vc = LOAD_SLICE(256);
-        const uint32_t c_first = n > 0 ? __ldg(cg) : 0u, c_last = n > 0 ? __ldg(cg + n - 1) : 0u;
-        if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; tk_len = t.contig_len; }
-        int qas = 0, qae = r_lseq;
-        { int op = c_first & 15; if (op == 4) qas = (int)(c_first >> 4);
-          if (op == 4 || op == 5) for (int k = 1; k < n; ++k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qas += (int)(c >> 4); else if (o2 != 5) break; } }
-        if (n > 1) { int op = c_last & 15; if (op == 4) qae -= (int)(c_last >> 4);
-          if (op == 4 || op == 5) for (int k = n - 2; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qae -= (int)(c >> 4); else if (o2 != 5) break; } }
-        const int alen = qae - qas;
-        const bool pass = !(r_mapq < P.mapq_min || (r_flag & 256) || alen < P.alen_min) && !(P.excl && (r_flag & P.excl)) && r_pos >= tk_start && r_pos < tk_end && n > 0;
-        if (!pass) {
-            if (lane == 0) { P.rec_end[rec] = -1; P.rec_flags[rec] = 0; P.rec_nm[rec] = -1.0; P.rec_nlead[rec] = 0; }
-            continue;
-        }
+        const uint4 d = dnext;
+        { const unsigned nrec2 = rec + nwarps; dnext = nrec2 < P.n_rec ? __ldg(reinterpret_cast<const uint4*>(P.scan + nrec2)) : make_uint4(0, 0, 0, 0); }
+        if (!(d.w & RM_PASS)) continue;
+        const int n = (int)d.y, r_pos = (int)d.z, r_task = (int)(d.w & 0xffffu);
+        const uint4* __restrict__ cga = reinterpret_cast<const uint4*>(P.cigar) + d.x + lane;
+        const int li0 = lane * 8;
+        #define LOAD_SLICE(base) (((base) + li0 < n) ? __ldg(cga + ((base) >> 3)) : make_uint4(0, 0, 0, 0))
+        uint4 va = LOAD_SLICE(0), vb = LOAD_SLICE(256);
+        if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; }
         unsigned pos_q = 0; int pos_r = r_pos; unsigned big = 0, nlead = 0;
+        // Two ops per 32-bit word: both halves are summed at once (a lane's eight 12-bit lengths cannot overflow 16 bits).
+        // bit 12 / 28 of `rb` flags a half that needs the rare path: an I / D longer than 10, a clip / skip op, an extension word.
+        #define WORD_BODY(w) { const uint32_t s_ = (w) >> 12; \
+            aq += (w) & ((s_ & 0x00010001u) * 0xfffu); ar += (w) & (((s_ >> 1) & 0x00010001u) * 0xfffu); \
+            rb |= ((((w) & 0x0fff0fffu) + 0x0ff50ff5u) & ~((w) & ((w) >> 1))) | ((w) >> 2) | ((w) >> 3); }
         #define SLICE_BODY(v, base) { \
-            const int li = (base) + li0; \
-            uint32_t w0 = (v).x, w1 = (v).y, w2 = (v).z, w3 = (v).w; \
-            if (li < mis || li + 3 >= n_al) { \
-                if (li < mis || li >= n_al) w0 = 6u; if (li + 1 < mis || li + 1 >= n_al) w1 = 6u; if (li + 2 < mis || li + 2 >= n_al) w2 = 6u; if (li + 3 < mis || li + 3 >= n_al) w3 = 6u; } \
-            unsigned lq = 0, lr = 0; bool rare = false; \
-            { const unsigned op = w0 & 15u, len = w0 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); } \
-            { const unsigned op = w1 & 15u, len = w1 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); } \
-            { const unsigned op = w2 & 15u, len = w2 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); } \
-            { const unsigned op = w3 & 15u, len = w3 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); } \
+            const uint32_t w0 = (v).x, w1 = (v).y, w2 = (v).z, w3 = (v).w; \
+            uint32_t aq = 0, ar = 0, rb = 0; \
+            WORD_BODY(w0) WORD_BODY(w1) WORD_BODY(w2) WORD_BODY(w3) \
+            unsigned lq = (aq & 0xffffu) + (aq >> 16), lr = (ar & 0xffffu) + (ar >> 16); \
+            if ((w0 | w1 | w2 | w3) & 0x80008000u) { const uint2 t_ = lane_sums_ext(w0, w1, w2, w3); lq = t_.x; lr = t_.y; } \
             const unsigned tot_q = __reduce_add_sync(FULL, lq), tot_r = __reduce_add_sync(FULL, lr); \
-            if (__any_sync(FULL, rare)) { const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, rec, (base), pos_q, pos_r, nlead, tk_start, tk_end); \
+            if (__any_sync(FULL, (rb & 0x10001000u) != 0u)) { const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lr, rec, (base), pos_q, pos_r, nlead, tk_start, tk_end); \
                 big += (unsigned)(rr >> 32); nlead += (unsigned)rr; } \
             pos_q += tot_q; pos_r += (int)tot_r; }
-        for (int base = 0; base < n_al; base += 384) {
-            { const uint4 v = va; va = LOAD_SLICE(base + 384); SLICE_BODY(v, base) }
-            if (base + 128 < n_al) { const uint4 v = vb; vb = LOAD_SLICE(base + 512); SLICE_BODY(v, base + 128) }
-            if (base + 256 < n_al) { const uint4 v = vc; vc = LOAD_SLICE(base + 640); SLICE_BODY(v, base + 256) }
+        for (int base = 0; base < n; base += 512) {
+            { const uint4 v = va; va = LOAD_SLICE(base + 512); SLICE_BODY(v, base) }
+            if (base + 256 < n) { const uint4 v = vb; vb = LOAD_SLICE(base + 768); SLICE_BODY(v, base + 256) }
         }
         #undef SLICE_BODY
+        #undef WORD_BODY
         #undef LOAD_SLICE
-        const int ref_end = pos_r;
-        int hp = (r_aux & SNFB_AUX_HP) ? (int)(__shfl_sync(FULL, wcur, 3) & 255u) : 0;
-        if (hp > 2) { hp = 0; if (lane == 0) atomicAdd(&P.ctr->soft_errors, 1ULL); }
-        const bool has_nm = P.want_nm && (r_aux & SNFB_AUX_NM);
-        const int r_nm = (int)__shfl_sync(FULL, wcur, 4);
         if (lane == 0) {
-            P.rec_end[rec] = ref_end;
-            P.rec_flags[rec] = (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2));
-            P.rec_nm[rec] = has_nm ? __ddiv_rn((double)((long long)r_nm - (long long)big), (double)(alen + 1)) : -1.0;      // leadprov.py:517-526
-            P.rec_nlead[rec] = nlead;
-            if (r_aux & SNFB_AUX_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = rec; }
-            if (acc_task != r_task) {
-                if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
-                acc_task = r_task; acc_reads = 0; acc_bp = 0; acc_span = 0;
-            }
-            ++acc_reads;
+            P.rec_end[rec] = pos_r; P.rec_nlead[rec] = nlead; P.rec_big[rec] = (int)big;
+            if (d.w & RM_HAS_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = rec; }
+        }
+    }
+}
+
+// per read nm (leadprov.py:517-526) and the per-task bookkeeping of iter_region (read count, covered bases, longest span)
+struct PostParams {
+    const RecScan* scan; const RecClip* clip; const snfb_task* task; uint32_t n_rec;
+    const int32_t* rec_end; const int32_t* rec_big; double* rec_nm;
+    uint32_t* task_reads; unsigned long long* task_cov_bp; int32_t* task_maxspan;
+};
+__global__ void __launch_bounds__(256) k_rec_post(const PostParams P) {
+    __shared__ unsigned s_reads; __shared__ unsigned long long s_bp; __shared__ int s_span; __shared__ int s_task;
+    const uint32_t i0 = blockIdx.x * 256, i = i0 + threadIdx.x;
+    if (threadIdx.x == 0) { s_reads = 0; s_bp = 0; s_span = 0; s_task = (int)(P.scan[i0].meta & 0xffffu); }
+    __syncthreads();
+    unsigned mine = 0; unsigned long long bp = 0; int span = 0;
+    if (i < P.n_rec) {
+        const RecScan s = P.scan[i];
+        if (s.meta & RM_PASS) {
+            const int task = (int)(s.meta & 0xffffu), ref_end = P.rec_end[i];
+            if (s.meta & RM_HAS_NM) P.rec_nm[i] = __ddiv_rn(P.rec_nm[i] - (double)P.rec_big[i], (double)(P.clip[i].alen + 1));
+            const int tk_len = P.task[task].contig_len;
             const int ce = ref_end < tk_len ? ref_end : tk_len;
-            if (ce > r_pos) acc_bp += (unsigned long long)(ce - r_pos);
-            if (ref_end - r_pos > acc_span) acc_span = ref_end - r_pos;
+            bp = ce > s.pos ? (unsigned long long)(ce - s.pos) : 0ull; span = ref_end - s.pos; if (span < 0) span = 0;
+            if (task == s_task) mine = 1;
+            else { atomicAdd(&P.task_reads[task], 1u); atomicAdd(&P.task_cov_bp[task], bp); atomicMax(&P.task_maxspan[task], span); bp = 0; span = 0; }   // block straddles a task boundary
         }
     }
-    if (lane == 0 && acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
-}
-
-// ------------------------------------------------------------------------------------------------
-// k_scan_tma: the same streaming pass with the CIGAR staged through shared memory by the bulk-copy engine
-// (cp.async.bulk global -> shared, completion on an mbarrier).  Every warp owns a ring of NST 2-KB stages; lane 0 runs
-// a fetch cursor up to NST chunks (and records) ahead of the consume cursor, so each warp keeps several KB in flight
-// without holding them in registers — the loads are no longer tied to the warp's own issue slots.
-// ------------------------------------------------------------------------------------------------
-namespace tma {
-constexpr int NST = 4;                 // stages per warp
-constexpr int CH_OPS = 512;            // ops per stage (2 KB = four 128-op slices)
-constexpr int WPB = 4;                 // warps per block (4 x 4 x 2 KB = 32 KB of stages)
-struct Desc { uint32_t rec; int32_t pos; int32_t n_al; int32_t mis; int32_t alen; int32_t nchunks; uint32_t aux_hp_nm; int32_t task; int32_t nm; int32_t tk_start, tk_end, tk_len; };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count)); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory"); }
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
-    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
-                 :: "r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-}  // namespace tma
-
-__global__ void __launch_bounds__(tma::WPB * 32, 6) k_scan_tma(const __grid_constant__ ScanParams P) {
-    using namespace tma;
-    __shared__ __align__(128) uint8_t s_buf[WPB][NST][CH_OPS * 4];
-    __shared__ __align__(8) uint64_t s_bar[WPB][NST];
-    __shared__ Desc s_desc[WPB][NST + 1];
-    const int lane = lane_id(), wib = threadIdx.x >> 5;
-    const unsigned nwarps = gridDim.x * WPB;
-    if (lane == 0) { for (int i = 0; i < NST; ++i) mbar_init(&s_bar[wib][i], 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-    __syncwarp();
-    int acc_task = -1; unsigned acc_reads = 0; unsigned long long acc_bp = 0; int acc_span = 0;
-    // ---- fetch cursor (warp-uniform state; lane 0 acts) ----
-    unsigned f_rec = blockIdx.x * WPB + wib;                // record the cursor stands on
-    int f_chunk = 0, f_nchunks = 0; bool f_open = false;    // f_open: descriptor of f_rec already published
-    const uint32_t* f_base = nullptr; int f_nal = 0;
-    unsigned n_fetch = 0, n_cons = 0, d_w = 0, d_r = 0;     // chunk / descriptor ring counters
-    int tk_id = -1, tk_start = 0, tk_end = 0, tk_len = 0;
-    // record core of the cursor and of the record after it (prefetched)
-    uint32_t wF = (f_rec < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + f_rec) + lane) : 0u;
-    uint32_t wN = (f_rec + nwarps < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + f_rec + nwarps) + lane) : 0u;
-    // ---- consume cursor ----
-    int c_chunk = 0; unsigned pos_q = 0; int pos_r = 0; unsigned big = 0, nlead = 0;
-    for (;;) {
-        // (1) keep the ring full
-        while (n_fetch - n_cons < (unsigned)NST && f_rec < P.n_rec) {
-            if (!f_open) {
-                const int r_task = (int)__shfl_sync(FULL, wF, 0), r_pos = (int)__shfl_sync(FULL, wF, 1);
-                const uint32_t x2 = __shfl_sync(FULL, wF, 2);
-                const int r_flag = x2 & 0xffff, r_mapq = (x2 >> 16) & 255, r_aux = x2 >> 24;
-                const int n = (int)__shfl_sync(FULL, wF, 6), r_lseq = (int)__shfl_sync(FULL, wF, 7);
-                const uint64_t cigar_off = (uint64_t)__shfl_sync(FULL, wF, 10) | ((uint64_t)__shfl_sync(FULL, wF, 11) << 32);
-                const uint32_t* cg = P.cigar + cigar_off; const int mis = (int)(cigar_off & 3);
-                if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; tk_len = t.contig_len; }
-                // cheap rejects first (no CIGAR access), then the alignment length from the clip ops
-                bool pass = !(r_mapq < P.mapq_min || (r_flag & 256)) && !(P.excl && (r_flag & P.excl)) && r_pos >= tk_start && r_pos < tk_end && n > 0;
-                int alen = 0;
-                if (pass) {
-                    const uint32_t c_first = __ldg(cg), c_last = __ldg(cg + n - 1);
-                    int qas = 0, qae = r_lseq;
-                    { int op = c_first & 15; if (op == 4) qas = (int)(c_first >> 4);
-                      if (op == 4 || op == 5) for (int k = 1; k < n; ++k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qas += (int)(c >> 4); else if (o2 != 5) break; } }
-                    if (n > 1) { int op = c_last & 15; if (op == 4) qae -= (int)(c_last >> 4);
-                      if (op == 4 || op == 5) for (int k = n - 2; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int o2 = c & 15; if (o2 == 4) qae -= (int)(c >> 4); else if (o2 != 5) break; } }
-                    alen = qae - qas; pass = alen >= P.alen_min;
-                }
-                if (!pass) {
-                    if (lane == 0) { P.rec_end[f_rec] = -1; P.rec_flags[f_rec] = 0; P.rec_nm[f_rec] = -1.0; P.rec_nlead[f_rec] = 0; }
-                    f_rec += nwarps; wF = wN; { const unsigned nx = f_rec + nwarps; wN = (nx < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + nx) + lane) : 0u; }
-                    continue;
-                }
-                f_base = cg - mis; f_nal = n + mis; f_nchunks = (f_nal + CH_OPS - 1) / CH_OPS; f_chunk = 0; f_open = true;
-                if (lane == 0) {
-                    Desc d; d.rec = f_rec; d.pos = r_pos; d.n_al = f_nal; d.mis = mis; d.alen = alen; d.nchunks = f_nchunks;
-                    d.aux_hp_nm = (uint32_t)r_aux;                     // hp / nm are added right below (they need a warp shuffle)
-                    d.task = r_task; d.nm = 0; d.tk_start = tk_start; d.tk_end = tk_end; d.tk_len = tk_len;
-                    s_desc[wib][d_w % (NST + 1)] = d;
-                }
-                { const uint32_t x3 = __shfl_sync(FULL, wF, 3); const int r_nm = (int)__shfl_sync(FULL, wF, 4);
-                  if (lane == 0) { Desc* dp = &s_desc[wib][d_w % (NST + 1)]; dp->aux_hp_nm = (uint32_t)r_aux | ((x3 & 255u) << 8); dp->nm = r_nm; } }
-                ++d_w;
-                __syncwarp();
-            }
-            {   // issue one chunk of the open record
-                const int st = n_fetch % NST; const int ops = min(CH_OPS, f_nal - f_chunk * CH_OPS); const unsigned bytes = (unsigned)(((ops * 4) + 15) & ~15);
-                if (lane == 0) { mbar_expect_tx(&s_bar[wib][st], bytes); bulk_g2s(s_buf[wib][st], f_base + (size_t)f_chunk * CH_OPS, bytes, &s_bar[wib][st]); }
-                ++n_fetch; ++f_chunk;
-                if (f_chunk == f_nchunks) { f_open = false; f_rec += nwarps; wF = wN; { const unsigned nx = f_rec + nwarps; wN = (nx < P.n_rec && lane < 16) ? __ldg(reinterpret_cast<const uint32_t*>(P.rec + nx) + lane) : 0u; } }
-            }
-        }
-        if (n_cons == n_fetch) break;                     // nothing in flight and nothing left to fetch
-        // (2) consume one chunk
-        const int st = n_cons % NST;
-        mbar_wait(&s_bar[wib][st], (n_cons / NST) & 1u);
-        const Desc d = s_desc[wib][d_r % (NST + 1)];
-        if (c_chunk == 0) { pos_q = 0; pos_r = d.pos; big = 0; nlead = 0; }
-        const uint4* sb = reinterpret_cast<const uint4*>(s_buf[wib][st]) + lane;
-        const int cbase = c_chunk * CH_OPS;
-        #pragma unroll 1
-        for (int sl = 0; sl < 4; ++sl) {
-            const int base = cbase + sl * 128; if (base >= d.n_al) break;
-            const uint4 v = sb[sl * 32];
-            const int li = base + lane * 4;
-            uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
-            if (li < d.mis || li + 3 >= d.n_al) {
-                if (li < d.mis || li >= d.n_al) w0 = 6u; if (li + 1 < d.mis || li + 1 >= d.n_al) w1 = 6u; if (li + 2 < d.mis || li + 2 >= d.n_al) w2 = 6u; if (li + 3 < d.mis || li + 3 >= d.n_al) w3 = 6u; }
-            unsigned lq = 0, lr = 0; bool rare = false;
-            { const unsigned op = w0 & 15u, len = w0 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); }
-            { const unsigned op = w1 & 15u, len = w1 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); }
-            { const unsigned op = w2 & 15u, len = w2 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); }
-            { const unsigned op = w3 & 15u, len = w3 >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1); rare |= (len > 10u) & (op != 0u); }
-            const unsigned tot_q = __reduce_add_sync(FULL, lq), tot_r = __reduce_add_sync(FULL, lr);
-            if (__any_sync(FULL, rare)) { const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, d.rec, base, pos_q, pos_r, nlead, d.tk_start, d.tk_end);
-                big += (unsigned)(rr >> 32); nlead += (unsigned)rr; }
-            pos_q += tot_q; pos_r += (int)tot_r;
-        }
-        __syncwarp();                                      // all lanes are done with this stage before lane 0 may refill it
-        ++n_cons; ++c_chunk;
-        if (c_chunk == d.nchunks) {
-            c_chunk = 0; ++d_r;
-            if (lane == 0) {
-                const int r_aux = d.aux_hp_nm & 255; int hp = (r_aux & SNFB_AUX_HP) ? (int)((d.aux_hp_nm >> 8) & 255u) : 0;
-                if (hp > 2) { hp = 0; atomicAdd(&P.ctr->soft_errors, 1ULL); }
-                const bool has_nm = P.want_nm && (r_aux & SNFB_AUX_NM); const int ref_end = pos_r;
-                P.rec_end[d.rec] = ref_end;
-                P.rec_flags[d.rec] = (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2));
-                P.rec_nm[d.rec] = has_nm ? __ddiv_rn((double)((long long)d.nm - (long long)big), (double)(d.alen + 1)) : -1.0;
-                P.rec_nlead[d.rec] = nlead;
-                if (r_aux & SNFB_AUX_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = d.rec; }
-                if (acc_task != d.task) {
-                    if (acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
-                    acc_task = d.task; acc_reads = 0; acc_bp = 0; acc_span = 0;
-                }
-                ++acc_reads;
-                const int ce = ref_end < d.tk_len ? ref_end : d.tk_len;
-                if (ce > d.pos) acc_bp += (unsigned long long)(ce - d.pos);
-                if (ref_end - d.pos > acc_span) acc_span = ref_end - d.pos;
-            }
-        }
-    }
-    if (lane == 0 && acc_task >= 0) { atomicAdd(&P.task_reads[acc_task], acc_reads); atomicAdd(&P.task_cov_bp[acc_task], acc_bp); atomicMax(&P.task_maxspan[acc_task], acc_span); }
+    const unsigned wr = __reduce_add_sync(FULL, mine); const int ws = __reduce_max_sync(FULL, span);
+    #pragma unroll
+    for (int o = 16; o; o >>= 1) bp += __shfl_xor_sync(FULL, bp, o);
+    if (lane_id() == 0 && wr) { atomicAdd(&s_reads, wr); atomicAdd(&s_bp, bp); atomicMax(&s_span, ws); }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_reads) { atomicAdd(&P.task_reads[s_task], s_reads); atomicAdd(&P.task_cov_bp[s_task], s_bp); atomicMax(&P.task_maxspan[s_task], s_span); }
 }
 
 // exact lead slots of the event slices: exclusive prefix of their counts (slices of one record keep their order through k0)
@@ -567,7 +487,7 @@ __global__ void k_ev_counts(const EvSlice* __restrict__ ev, uint32_t* __restrict
 }
 
 struct EmitParams {
-    const snfb_rec* rec; const uint32_t* cigar; const uint8_t* var; const snfb_task* task;
+    const snfb_rec* rec; const RecClip* clip; const uint16_t* cigar; const uint8_t* var; const snfb_task* task;
     const EvSlice* ev; const uint32_t* ev_slot; const unsigned long long* n_ev; unsigned long long ev_cap;
     snfb_lead* leads; unsigned long long lead_cap; DevCounters* ctr;
     int minsv, maxlen, detect_large_ins; double longinslen;
@@ -581,17 +501,16 @@ __global__ void __launch_bounds__(256) k_emit(const EmitParams P) {
         const EvSlice s = P.ev[e];
         const snfb_rec r = P.rec[s.rec];
         const snfb_task tk = P.task[r.task];
-        const uint32_t* cg = P.cigar + r.cigar_off; const int n_ops = (int)r.n_cigar;
-        const int mis = (int)(r.cigar_off & 3); const int n_al = n_ops + mis;
-        const int li = s.base + lane * 4;
-        uint4 v = (li < n_al) ? __ldg(reinterpret_cast<const uint4*>(cg - mis) + (s.base >> 2) + lane) : make_uint4(0, 0, 0, 0);
-        uint32_t ww[4] = { v.x, v.y, v.z, v.w };
-        #pragma unroll
-        for (int j = 0; j < 4; ++j) if (li + j < mis || li + j >= n_al) ww[j] = 6u;
+        const int n_words = (int)r.n_cigar;
+        const int li = s.base + lane * 8;
+        const uint4 v = (li < n_words) ? __ldg(reinterpret_cast<const uint4*>(P.cigar + r.cigar_off) + (s.base >> 3) + lane) : make_uint4(0, 0, 0, 0);
+        const uint32_t ww[4] = { v.x, v.y, v.z, v.w };
+        unsigned cls[8], len[8];
+        c16_decode8(ww, cls, len);
         unsigned lq = 0, lr = 0, evm = 0;
         #pragma unroll
-        for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4, fl = op_flags(op); lq += len * (fl & 1u); lr += len * (fl >> 1);
-            if (((0x016u >> op) & 1u) && (int)len >= P.minsv) evm |= 1u << j; }
+        for (int j = 0; j < 8; ++j) { lq += len[j] * (cls[j] & 1u); lr += len[j] * ((cls[j] >> 1) & 1u);
+            if (c16_is_event(cls[j]) && (int)len[j] >= P.minsv) evm |= 1u << j; }
         unsigned iq = lq, ir = lr;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
@@ -599,18 +518,15 @@ __global__ void __launch_bounds__(256) k_emit(const EmitParams P) {
         // which signatures stay inside the task's region (leadprov.py:464-466), and their rank inside the slice
         unsigned emm = 0; int cnt = 0; { int r2 = pr;
             #pragma unroll
-            for (int j = 0; j < 4; ++j) { const unsigned op = ww[j] & 15u, len = ww[j] >> 4;
-                if (evm & (1u << j)) { const int rs = op == 2u ? r2 + (int)len : r2; if (rs >= tk.start && rs < tk.end) { emm |= 1u << j; ++cnt; } }
-                r2 += (int)(len * (op_flags(op) >> 1)); } }
+            for (int j = 0; j < 8; ++j) {
+                if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; if (rs >= tk.start && rs < tk.end) { emm |= 1u << j; ++cnt; } }
+                r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); } }
         int inc = cnt;
         #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
         int mine = inc - cnt;
         // per-record facts
-        int qas = 0, qae = r.l_seq;
-        for (int k = 0; k < n_ops; ++k) { const uint32_t c = __ldg(cg + k); const int op = c & 15; if (op == 4) qas += (int)(c >> 4); else if (op != 5) break; }
-        for (int k = n_ops - 1; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int op = c & 15; if (op == 4) qae -= (int)(c >> 4); else if (op != 5) break; }
-        const int alen = qae - qas;
+        const int alen = P.clip[s.rec].alen;
         const bool is_supp = r.flag & 2048, rev = r.flag & 16, has_sa = r.aux_flags & SNFB_AUX_SA;
         int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0; if (hp > 2) hp = 0;
         const bool use_clips = P.detect_large_ins && !is_supp && !has_sa;
@@ -618,30 +534,30 @@ __global__ void __launch_bounds__(256) k_emit(const EmitParams P) {
         const uint64_t qh = qname_hash_warp(P.var + r.var_off, r.l_qname);
         const unsigned long long slot0 = P.ev_slot[e];
         #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const unsigned op = ww[j] & 15u; const int len = (int)(ww[j] >> 4); const unsigned fl = op_flags(op);
+        for (int j = 0; j < 8; ++j) {
+            const unsigned op = cls[j]; const int ln = (int)len[j];
             if (emm & (1u << j)) {
                 snfb_lead L;
                 L.rec = s.rec; L.qname_hash = qh; L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
                 L.task = (uint16_t)r.task; L.k = (uint16_t)(s.k0 + mine);
                 uint32_t f = inl_flags; const int pqi = (int)pq;
-                if (op == 1u) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = len;
-                    if (len <= P.maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pqi; L.seq_len = len; } }
-                else if (op == 2u) { f |= SNFB_DEL; L.ref_start = pr + len; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi; L.svlen = -len; }
-                else if (use_clips && (double)len >= P.longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = 0; }
-                else { f |= (pr == r.pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + len; L.svlen = 0; }
+                if (op == C16_I) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = ln;
+                    if (ln <= P.maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pqi; L.seq_len = ln; } }
+                else if (op == C16_D) { f |= SNFB_DEL; L.ref_start = pr + ln; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi; L.svlen = -ln; }
+                else if (use_clips && (double)ln >= P.longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = 0; }
+                else { f |= (pr == r.pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = 0; }
                 L.flags = f;
                 const unsigned long long slot = slot0 + (unsigned long long)mine;
                 if (slot < P.lead_cap) store_lead(P.leads + slot, L); else atomicAdd(&P.ctr->lead_overflow, 1ULL);
                 ++mine;
             }
-            pq += (unsigned)len * (fl & 1u); pr += (int)((unsigned)len * (fl >> 1));
+            pq += (unsigned)ln * (op & 1u); pr += (int)((unsigned)ln * ((op >> 1) & 1u));
         }
     }
 }
 
 struct SaParams {
-    const snfb_rec* rec; const uint32_t* cigar; const uint8_t* var; const snfb_task* task; const snfb_contig* contig; uint32_t n_contig;
+    const snfb_rec* rec; const RecClip* clip; const uint8_t* var; const snfb_task* task; const snfb_contig* contig; uint32_t n_contig;
     const uint32_t* sa_list; const unsigned long long* n_sa; const int32_t* rec_end; uint32_t* rec_nlead;
     snfb_lead* leads; unsigned long long lead_cap; DevCounters* ctr;
     snfb_config cfg;
@@ -661,17 +577,15 @@ __global__ void __launch_bounds__(THREADS) k_sa(const SaParams P) {
         const uint32_t rec = P.sa_list[e];
         const snfb_rec r = P.rec[rec];
         const snfb_task tk = P.task[r.task];
-        const uint32_t* cg = P.cigar + r.cigar_off; const int n_ops = (int)r.n_cigar;
-        int qas = 0, qae = r.l_seq;
-        for (int k = 0; k < n_ops; ++k) { const uint32_t c = __ldg(cg + k); const int op = c & 15; if (op == 4) qas += (int)(c >> 4); else if (op != 5) break; }
-        for (int k = n_ops - 1; k >= 1; --k) { const uint32_t c = __ldg(cg + k); const int op = c & 15; if (op == 4) qae -= (int)(c >> 4); else if (op != 5) break; }
+        const RecClip rc = P.clip[rec];
+        const int qas = rc.qas, qae = rc.qas + rc.alen;
         const uint64_t qh = qname_hash_warp(P.var + r.var_off, r.l_qname);
         if (lane == 0) {
             int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0; if (hp > 2) hp = 0;
             const bool rev = r.flag & 16;
             SaArgs a; a.rec = rec; a.qas = qas; a.qae = qae; a.alen = qae - qas; a.ref_end = P.rec_end[rec]; a.hp = hp;
             a.base_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r.mapq << 16); a.qh = qh; a.nlead = P.rec_nlead[rec]; a.rev = rev; a.is_supp = r.flag & 2048;
-            a.sa = P.var + r.var_off + r.l_qname; a.sa_len = (int)r.sa_len; a.c_first = __ldg(cg); a.c_last = __ldg(cg + n_ops - 1); a.pos = r.pos; a.l_seq = r.l_seq; a.mapq = r.mapq;
+            a.sa = P.var + r.var_off + r.l_qname; a.sa_len = (int)r.sa_len; a.clip_left = rc.clip_left; a.clip_right = rc.clip_right; a.pos = r.pos; a.l_seq = r.l_seq; a.mapq = r.mapq;
             a.aux_flags = r.aux_flags; a.task = r.task; a.tk_contig = tk.contig; a.tk_start = tk.start; a.tk_end = tk.end; a.contig = P.contig; a.n_contig = P.n_contig;
             a.leads = P.leads; a.lead_cap = P.lead_cap; a.n_slots = &P.ctr->n_slots; a.slots = &slots;
             a.mapq_min = s_cfg.mapq; a.dev_keep_lowqual_splits = s_cfg.dev_keep_lowqual_splits; a.max_splits_base = s_cfg.max_splits_base; a.max_splits_kb = s_cfg.max_splits_kb;

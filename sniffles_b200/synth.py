@@ -69,11 +69,26 @@ class RecordBlock:
     _owner: object = None
     mask: np.ndarray = None            # optional reference N runs: int32 pairs (start, end), per task contiguous
     mask_task_off: np.ndarray = None   # uint32 [n_task + 1]
+    rec16: np.ndarray = None           # CIGAR16 twin of rec / cigar (pack16); what the device path ships
+    cigar16: np.ndarray = None
 
-    def as_struct(self) -> abi.Records:
+    def pack16(self):
+        """Convert the BAM CIGAR words to CIGAR16 once (snfb_pack_cigar16, host code of libsnfb200)."""
+        if self.cigar16 is None:
+            from . import binding
+            self.rec16, self.cigar16 = binding.pack_cigar16(self.rec, self.cigar)
+        return self
+
+    def as_struct(self, cigar16: bool = False) -> abi.Records:
+        """cigar16=False: the BAM-word form (what the oracle reads); True: the CIGAR16 form the kernels stream."""
         r = abi.Records()
-        r.n_rec, r.n_cigar, r.n_var, r.n_seq = len(self.rec), len(self.cigar), len(self.var), len(self.seq)
-        r.rec, r.cigar = self.rec.ctypes.data, self.cigar.ctypes.data
+        if cigar16:
+            self.pack16()
+            rec, cig, r.cigar_fmt = self.rec16, self.cigar16, abi.CIGAR_16
+        else:
+            rec, cig, r.cigar_fmt = self.rec, self.cigar, abi.CIGAR_BAM32
+        r.n_rec, r.n_cigar, r.n_var, r.n_seq = len(rec), len(cig), len(self.var), len(self.seq)
+        r.rec, r.cigar = rec.ctypes.data, cig.ctypes.data
         r.var, r.seq = self.var.ctypes.data, self.seq.ctypes.data
         r.n_task, r.n_contig, r.n_tr, r.on_device = len(self.task), len(self.contig), len(self.tr) // 2, 0
         r.task, r.contig, r.tr = self.task.ctypes.data, self.contig.ctypes.data, self.tr.ctypes.data
@@ -92,7 +107,8 @@ class RecordBlock:
         self.mask_task_off = np.asarray(off, dtype="<u4")
 
     def nbytes(self) -> int:
-        return self.rec.nbytes + self.cigar.nbytes + self.var.nbytes + self.seq.nbytes
+        cig = self.cigar16 if self.cigar16 is not None else self.cigar
+        return self.rec.nbytes + cig.nbytes + self.var.nbytes + self.seq.nbytes
 
 
 class _Owner:

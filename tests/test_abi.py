@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     with open(os.path.join(ROOT, "include", "snfb.h")) as f:
         text = f.read()
-    return sorted(set(re.findall(r"\b(snfb_[a-z_]+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(snfb_[a-z_0-9]+)\s*\(", text)))
 
 
 def test_exports_match_header():
@@ -27,7 +27,7 @@ def test_exports_match_header():
 
 def test_struct_sizes():
     L = binding.lib()
-    assert L.snfb_version() == 1
+    assert L.snfb_version() == 2
     want = [abi.REC_DTYPE.itemsize, abi.TASK_DTYPE.itemsize, abi.CONTIG_DTYPE.itemsize, C.sizeof(abi.Records), C.sizeof(abi.Config),
             abi.LEAD_DTYPE.itemsize, abi.CAND_DTYPE.itemsize]
     assert [L.snfb_sizeof(i) for i in range(7)] == want

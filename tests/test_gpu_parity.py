@@ -8,13 +8,13 @@ import devcheck
 pytestmark = pytest.mark.gpu
 
 
-def _run(blk, *args):
+def _run(blk, *args, cigar16=True):
     import oracle.oracle as orc
     cfg = abi.Config.from_sniffles(sconfig.default_config(*args))
     ctx = binding.Context(0)
     try:
         ctx.set_config(cfg)
-        ctx.load(blk)
+        ctx.load(blk, cigar16=cigar16)
         got = ctx.run()
     finally:
         ctx.close()
@@ -31,6 +31,11 @@ def test_config1_shape():
 @pytest.mark.parametrize("args", [(), ("--mosaic",), ("--no-qc",), ("--repeat",), ("--minsvlen", "30")])
 def test_config2_scaled(args):
     _run(synth.config_block(2, 0.004), *args)
+
+
+def test_bam_words_converted_by_the_library():
+    """SNFB_CIGAR_BAM32 host arenas: snfb_load_records converts them itself."""
+    _run(synth.config_block(2, 0.003), cigar16=False)
 
 
 def test_config3_hifi_mosaic():
