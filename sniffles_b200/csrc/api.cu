@@ -332,14 +332,14 @@ static int run_stage_a(snfb_ctx* ctx) {
         CUDA_TRY(cudaMemsetAsync(ctx->b_task_first.p, 0, 4 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_last.p, 0, 4 * nt, ctx->st));
         CUDA_TRY(cudaMemsetAsync(ctx->b_task_reads.p, 0, 4 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_cov.p, 0, 8 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_span.p, 0, 4 * nt, ctx->st));
         const snfb_config& cf = ctx->cfg;
-        if (ctx->b_ev.ensure(sizeof(extract::EvSlice) * ctx->lead_cap) || ctx->b_ev_cnt.ensure(4 * (ctx->lead_cap + 8)) || ctx->b_ev_slot.ensure(4 * (ctx->lead_cap + 8)) || ctx->b_sa_list.ensure(4 * (nrec + 1))
+        if (ctx->b_ev.ensure(sizeof(extract::Event) * ctx->lead_cap) || ctx->b_sa_list.ensure(4 * (nrec + 1))
             || ctx->b_scan_tmp.ensure(4 * (prims::scan_tmp_elems(std::max<unsigned long long>(nrec, ctx->lead_cap)) + 16))) return fail(ctx, "out of device memory (stage A lists)");
         DevCounters* ctr = ctx->b_ctr.as<DevCounters>();
         if (ctx->b_scanrec.ensure(sizeof(extract::RecScan) * (nrec + 1)) || ctx->b_clip.ensure(sizeof(extract::RecClip) * (nrec + 1)) || ctx->b_rec_big.ensure(4 * (nrec + 1))) return fail(ctx, "out of device memory (record descriptors)");
         extract::ScanParams S{};
         S.scan = ctx->b_scanrec.as<extract::RecScan>(); S.cigar = ctx->d_cigar; S.task = ctx->b_task.as<snfb_task>(); S.n_rec = (uint32_t)nrec;
         S.rec_end = ctx->b_rec_end.as<int32_t>(); S.rec_nlead = ctx->b_rec_nlead.as<uint32_t>(); S.rec_big = ctx->b_rec_big.as<int32_t>();
-        S.ev = ctx->b_ev.as<extract::EvSlice>(); S.ev_cap = ctx->lead_cap; S.n_ev = &ctr->n_ev; S.sa_list = ctx->b_sa_list.as<uint32_t>(); S.n_sa = &ctr->n_sa; S.ctr = ctr;
+        S.ev = ctx->b_ev.as<extract::Event>(); S.ev_cap = ctx->lead_cap; S.n_ev = &ctr->n_ev; S.sa_list = ctx->b_sa_list.as<uint32_t>(); S.n_sa = &ctr->n_sa; S.ctr = ctr;
         S.minsv = cf.minsvlen_screen;
         uint32_t* task_first = ctx->b_task_first.as<uint32_t>(); uint32_t* task_last = ctx->b_task_last.as<uint32_t>();
         uint8_t* rec_flags = ctx->b_rec_flags.as<uint8_t>(); double* rec_nm = ctx->b_rec_nm.as<double>();
@@ -360,13 +360,11 @@ static int run_stage_a(snfb_ctx* ctx) {
             Q.task_reads = ctx->b_task_reads.as<uint32_t>(); Q.task_cov_bp = ctx->b_task_cov.as<unsigned long long>(); Q.task_maxspan = ctx->b_task_span.as<int32_t>();
             extract::k_rec_post<<<(unsigned)((nrec + 255) / 256), 256, 0, ctx->st>>>(Q); LAUNCHED(ctx, 1);
             mark(ctx, "k_emit");
-            extract::k_ev_counts<<<grid_for(ctx->lead_cap, 256), 256, 0, ctx->st>>>(S.ev, ctx->b_ev_cnt.as<uint32_t>(), S.n_ev, ctx->lead_cap);
-            LAUNCHED(ctx, 3 + prims::exclusive_scan(ctx->b_ev_cnt.as<uint32_t>(), ctx->b_ev_slot.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->lead_cap, &ctr->n_slots, ctx->st));
             extract::EmitParams E{};
-            E.rec = ctx->d_rec; E.clip = ctx->b_clip.as<extract::RecClip>(); E.cigar = ctx->d_cigar; E.var = ctx->d_var; E.task = S.task; E.ev = S.ev; E.ev_slot = ctx->b_ev_slot.as<uint32_t>(); E.n_ev = S.n_ev; E.ev_cap = ctx->lead_cap;
-            E.leads = ctx->b_leads.as<snfb_lead>(); E.lead_cap = ctx->lead_cap; E.ctr = ctr; E.minsv = cf.minsvlen_screen; E.maxlen = cf.dev_seq_cache_maxlen; E.detect_large_ins = cf.detect_large_ins;
+            E.rec = ctx->d_rec; E.clip = ctx->b_clip.as<extract::RecClip>(); E.var = ctx->d_var; E.ev = S.ev; E.n_ev = S.n_ev; E.ev_cap = ctx->lead_cap;
+            E.leads = ctx->b_leads.as<snfb_lead>(); E.ctr = ctr; E.maxlen = cf.dev_seq_cache_maxlen; E.detect_large_ins = cf.detect_large_ins;
             E.longinslen = (double)cf.long_ins_length / 2.0;
-            extract::k_emit<<<148 * 32, 256, 0, ctx->st>>>(E);      // one warp per event slice; latency-bound, so oversubscribe
+            extract::k_emit<<<148 * 16, 128, 0, ctx->st>>>(E); LAUNCHED(ctx, 3);      // thread per event; k_rec_index and k_scan are counted here too
             mark(ctx, "k_sa");
             extract::SaParams A{};
             A.rec = ctx->d_rec; A.clip = ctx->b_clip.as<extract::RecClip>(); A.var = ctx->d_var; A.task = S.task; A.contig = ctx->b_contig.as<snfb_contig>(); A.n_contig = ctx->n_contig;

@@ -16,6 +16,7 @@ namespace extract {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
+constexpr int SA_STAGE = 768; // bytes of SA text staged per warp
 constexpr int MAXSEG = 40;     // primary + supplementary segments per read held in shared memory
 
 // rec_flags bits
@@ -345,22 +346,23 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     P.rec_end[i] = -1; P.rec_nlead[i] = 0;
 }
 
-struct EvSlice { uint32_t rec; int32_t base; uint32_t pos_q; int32_t pos_r; uint32_t k0; uint32_t count; uint32_t slot0; uint32_t pad; };
+// one SV signature found by k_scan (an I / D / S op of at least minsvlen_screen inside the task's region): all k_emit needs to build its lead
+struct Event { uint32_t rec; uint32_t len; uint32_t pos_q; int32_t pos_r; uint32_t k_cls; uint32_t pad[3]; };   // k_cls: k | class << 16
 
 struct ScanParams {
     const RecScan* scan; const uint16_t* cigar; const snfb_task* task;
     uint32_t n_rec;
     int32_t* rec_end; uint32_t* rec_nlead; int32_t* rec_big;
-    EvSlice* ev; unsigned long long ev_cap; unsigned long long* n_ev;
+    Event* ev; unsigned long long ev_cap; unsigned long long* n_ev;
     uint32_t* sa_list; unsigned long long* n_sa;
     DevCounters* ctr;
     int minsv;
 };
 
-// rare path of k_scan: a slice with an I/D longer than 10, a clip / skip op or an extension word.
-// Returns (big << 32) | leads counted.
-__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lr,
-                                                      uint32_t rec, int base, unsigned pos_q, int pos_r, unsigned k0, int tk_start, int tk_end) {
+// rare path of k_scan: a slice with an I/D longer than 10, a clip / skip op or an extension word.  SV signatures are
+// appended to the event list (any order: a lead's place is fixed later by its record and k).  Returns (big << 32) | leads counted.
+__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr,
+                                                      uint32_t rec, unsigned pos_q, int pos_r, unsigned k0, int tk_start, int tk_end) {
     const int lane = lane_id();
     const uint32_t ww[4] = { w0, w1, w2, w3 };
     unsigned cls[8], len[8];
@@ -373,20 +375,34 @@ __device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restric
     big = __reduce_add_sync(FULL, big);
     unsigned count = 0;
     if (__any_sync(FULL, evm != 0)) {
-        unsigned ir = lr;
+        unsigned iq = lq, ir = lr;
         #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) ir += tr; }
-        int r2 = pos_r + (int)(ir - lr); unsigned cnt = 0;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
+        const unsigned q0 = pos_q + iq - lq; const int r0 = pos_r + (int)(ir - lr);
+        // which signatures stay inside the task's region (leadprov.py:464-466)
+        unsigned emm = 0, cnt = 0; { int r2 = r0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; if (rs >= tk_start && rs < tk_end) { emm |= 1u << j; ++cnt; } }
+                r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); } }
+        unsigned inc = cnt;
         #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; cnt += (rs >= tk_start && rs < tk_end); }
-            r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); }
-        count = __reduce_add_sync(FULL, cnt);
-        if (count && lane == 0) {
-            const unsigned long long e = atomicAdd(P->n_ev, 1ULL);
-            if (e < P->ev_cap) { EvSlice s; s.rec = rec; s.base = base; s.pos_q = pos_q; s.pos_r = pos_r; s.k0 = k0; s.count = count; s.slot0 = 0; s.pad = 0;
-                *reinterpret_cast<uint4*>(&P->ev[e]) = *reinterpret_cast<const uint4*>(&s); *(reinterpret_cast<uint4*>(&P->ev[e]) + 1) = *(reinterpret_cast<const uint4*>(&s) + 1); }
-            else atomicAdd(&P->ctr->lead_overflow, 1ULL);
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        count = __shfl_sync(FULL, inc, 31);
+        if (count) {
+            unsigned long long e0 = 0; if (lane == 0) e0 = atomicAdd(P->n_ev, (unsigned long long)count);
+            e0 = __shfl_sync(FULL, e0, 0);
+            unsigned mine = inc - cnt; unsigned q2 = q0; int r2 = r0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (emm & (1u << j)) {
+                    const unsigned long long e = e0 + mine;
+                    if (e < P->ev_cap) { uint4* dst = reinterpret_cast<uint4*>(P->ev + e); dst[0] = make_uint4(rec, len[j], q2, (uint32_t)r2); dst[1] = make_uint4((k0 + mine) | (cls[j] << 16), 0u, 0u, 0u); }
+                    else atomicAdd(&P->ctr->lead_overflow, 1ULL);
+                    ++mine;
+                }
+                q2 += len[j] * (cls[j] & 1u); r2 += (int)(len[j] * ((cls[j] >> 1) & 1u));
+            }
         }
     }
     return ((unsigned long long)big << 32) | count;
@@ -431,7 +447,7 @@ __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanPar
             unsigned lq = (aq & 0xffffu) + (aq >> 16), lr = (ar & 0xffffu) + (ar >> 16); \
             if ((w0 | w1 | w2 | w3) & 0x80008000u) { const uint2 t_ = lane_sums_ext(w0, w1, w2, w3); lq = t_.x; lr = t_.y; } \
             const unsigned tot_q = __reduce_add_sync(FULL, lq), tot_r = __reduce_add_sync(FULL, lr); \
-            if (__any_sync(FULL, (rb & 0x10001000u) != 0u)) { const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lr, rec, (base), pos_q, pos_r, nlead, tk_start, tk_end); \
+            if (__any_sync(FULL, (rb & 0x10001000u) != 0u)) { const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, rec, pos_q, pos_r, nlead, tk_start, tk_end); \
                 big += (unsigned)(rr >> 32); nlead += (unsigned)rr; } \
             pos_q += tot_q; pos_r += (int)tot_r; }
         for (int base = 0; base < n; base += 512) {
@@ -480,79 +496,49 @@ __global__ void __launch_bounds__(256) k_rec_post(const PostParams P) {
     if (threadIdx.x == 0 && s_reads) { atomicAdd(&P.task_reads[s_task], s_reads); atomicAdd(&P.task_cov_bp[s_task], s_bp); atomicMax(&P.task_maxspan[s_task], s_span); }
 }
 
-// exact lead slots of the event slices: exclusive prefix of their counts (slices of one record keep their order through k0)
-__global__ void k_ev_counts(const EvSlice* __restrict__ ev, uint32_t* __restrict__ cnt, const unsigned long long* __restrict__ n_ev, unsigned long long bound) {
-    const unsigned long long n = *n_ev < bound ? *n_ev : bound;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < bound; i += (unsigned long long)gridDim.x * blockDim.x) cnt[i] = i < n ? ev[i].count : 0u;
-}
-
 struct EmitParams {
-    const snfb_rec* rec; const RecClip* clip; const uint16_t* cigar; const uint8_t* var; const snfb_task* task;
-    const EvSlice* ev; const uint32_t* ev_slot; const unsigned long long* n_ev; unsigned long long ev_cap;
-    snfb_lead* leads; unsigned long long lead_cap; DevCounters* ctr;
-    int minsv, maxlen, detect_large_ins; double longinslen;
+    const snfb_rec* rec; const RecClip* clip; const uint8_t* var;
+    const Event* ev; const unsigned long long* n_ev; unsigned long long ev_cap;
+    snfb_lead* leads; DevCounters* ctr;
+    int maxlen, detect_large_ins; double longinslen;
 };
-// one warp per event slice: read_iterindels' lead construction (leadprov.py:583-670)
-__global__ void __launch_bounds__(256) k_emit(const EmitParams P) {
-    const int lane = lane_id();
-    const unsigned long long n = *P.n_ev < P.ev_cap ? *P.n_ev : P.ev_cap;
-    const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long e = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; e < n; e += nw) {
-        const EvSlice s = P.ev[e];
-        const snfb_rec r = P.rec[s.rec];
-        const snfb_task tk = P.task[r.task];
-        const int n_words = (int)r.n_cigar;
-        const int li = s.base + lane * 8;
-        const uint4 v = (li < n_words) ? __ldg(reinterpret_cast<const uint4*>(P.cigar + r.cigar_off) + (s.base >> 3) + lane) : make_uint4(0, 0, 0, 0);
-        const uint32_t ww[4] = { v.x, v.y, v.z, v.w };
-        unsigned cls[8], len[8];
-        c16_decode8(ww, cls, len);
-        unsigned lq = 0, lr = 0, evm = 0;
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) { lq += len[j] * (cls[j] & 1u); lr += len[j] * ((cls[j] >> 1) & 1u);
-            if (c16_is_event(cls[j]) && (int)len[j] >= P.minsv) evm |= 1u << j; }
-        unsigned iq = lq, ir = lr;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
-        unsigned pq = s.pos_q + iq - lq; int pr = s.pos_r + (int)(ir - lr);
-        // which signatures stay inside the task's region (leadprov.py:464-466), and their rank inside the slice
-        unsigned emm = 0; int cnt = 0; { int r2 = pr;
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; if (rs >= tk.start && rs < tk.end) { emm |= 1u << j; ++cnt; } }
-                r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); } }
-        int inc = cnt;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-        int mine = inc - cnt;
-        // per-record facts
-        const int alen = P.clip[s.rec].alen;
-        const bool is_supp = r.flag & 2048, rev = r.flag & 16, has_sa = r.aux_flags & SNFB_AUX_SA;
-        int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0; if (hp > 2) hp = 0;
+// qname_hash_warp (common.cuh) evaluated by one thread
+__device__ inline uint64_t qname_hash_thread(const uint8_t* s, int n) {
+    uint64_t acc = 0;
+    for (int l = 0; l * 8 < n; ++l) {
+        uint64_t w = 0; const int m = n - l * 8 < 8 ? n - l * 8 : 8;
+        for (int j = 0; j < m; ++j) w |= (uint64_t)s[l * 8 + j] << (8 * j);
+        acc += qname_word(w, (uint32_t)l);
+    }
+    return qname_finish(acc + (0x9E3779B97F4A7C15ull ^ (uint64_t)n));
+}
+// one thread per event: read_iterindels' lead construction (leadprov.py:583-670).  Event e becomes lead slot e; the slots of
+// the SA leads (k_sa) start behind the last event.
+__global__ void __launch_bounds__(128) k_emit(const EmitParams P) {
+    const unsigned long long n_all = *P.n_ev, n = n_all < P.ev_cap ? n_all : P.ev_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) P.ctr->n_slots = n_all;
+    for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(P.ev + e)); const uint32_t kc = __ldg(reinterpret_cast<const uint32_t*>(P.ev + e) + 4);
+        const uint32_t rec = e0.x; const int ln = (int)e0.y, pqi = (int)e0.z, pr = (int)e0.w; const unsigned op = kc >> 16;
+        const uint4* core = reinterpret_cast<const uint4*>(P.rec + rec);
+        const uint4 c0 = __ldg(core), c3 = __ldg(core + 3);
+        const int r_task = (int)c0.x, r_pos = (int)c0.y; const unsigned flag = c0.z & 0xffffu, mapq = (c0.z >> 16) & 255u, aux = c0.z >> 24; const int l_qname = (int)((c0.w >> 8) & 255u);
+        const unsigned long long var_off = (unsigned long long)c3.z | ((unsigned long long)c3.w << 32);
+        const int alen = P.clip[rec].alen;
+        const bool is_supp = flag & 2048u, rev = flag & 16u, has_sa = aux & SNFB_AUX_SA;
+        unsigned hp = (aux & SNFB_AUX_HP) ? (c0.w & 255u) : 0u; if (hp > 2) hp = 0;
         const bool use_clips = P.detect_large_ins && !is_supp && !has_sa;
-        const uint32_t inl_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r.mapq << 16) | ((uint32_t)SNFB_SRC_INLINE << 3) | ((uint32_t)hp << 24) | (is_supp ? SNFB_LF_IS_SA : 0u);
-        const uint64_t qh = qname_hash_warp(P.var + r.var_off, r.l_qname);
-        const unsigned long long slot0 = P.ev_slot[e];
-        #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const unsigned op = cls[j]; const int ln = (int)len[j];
-            if (emm & (1u << j)) {
-                snfb_lead L;
-                L.rec = s.rec; L.qname_hash = qh; L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
-                L.task = (uint16_t)r.task; L.k = (uint16_t)(s.k0 + mine);
-                uint32_t f = inl_flags; const int pqi = (int)pq;
-                if (op == C16_I) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = ln;
-                    if (ln <= P.maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pqi; L.seq_len = ln; } }
-                else if (op == C16_D) { f |= SNFB_DEL; L.ref_start = pr + ln; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi; L.svlen = -ln; }
-                else if (use_clips && (double)ln >= P.longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = 0; }
-                else { f |= (pr == r.pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = 0; }
-                L.flags = f;
-                const unsigned long long slot = slot0 + (unsigned long long)mine;
-                if (slot < P.lead_cap) store_lead(P.leads + slot, L); else atomicAdd(&P.ctr->lead_overflow, 1ULL);
-                ++mine;
-            }
-            pq += (unsigned)ln * (op & 1u); pr += (int)((unsigned)ln * ((op >> 1) & 1u));
-        }
+        snfb_lead L;
+        L.rec = rec; L.qname_hash = qname_hash_thread(P.var + var_off, l_qname); L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
+        L.task = (uint16_t)r_task; L.k = (uint16_t)(kc & 0xffffu);
+        uint32_t f = (rev ? SNFB_LF_REVERSE : 0u) | (mapq << 16) | ((uint32_t)SNFB_SRC_INLINE << 3) | (hp << 24) | (is_supp ? SNFB_LF_IS_SA : 0u);
+        if (op == C16_I) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = ln;
+            if (ln <= P.maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pqi; L.seq_len = ln; } }
+        else if (op == C16_D) { f |= SNFB_DEL; L.ref_start = pr + ln; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi; L.svlen = -ln; }
+        else if (use_clips && (double)ln >= P.longinslen) { f |= SNFB_INS | SNFB_LF_SVLEN_NONE; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = 0; }
+        else { f |= (pr == r_pos) ? SNFB_SINGLE_LEFT : SNFB_SINGLE_RIGHT; L.ref_start = L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = 0; }
+        L.flags = f;
+        store_lead(P.leads + e, L);
     }
 }
 
@@ -565,6 +551,7 @@ struct SaParams {
 // one warp per record with an SA tag (lane 0 parses; the warp hashes the name)
 __global__ void __launch_bounds__(THREADS) k_sa(const SaParams P) {
     __shared__ Seg segs[WARPS][MAXSEG];
+    __shared__ __align__(16) uint8_t s_sa[WARPS][SA_STAGE];     // the SA text is parsed byte by byte by one lane: stage it next to the SM first
     __shared__ snfb_config s_cfg;
     if (threadIdx.x < sizeof(snfb_config) / 4) reinterpret_cast<uint32_t*>(&s_cfg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&P.cfg)[threadIdx.x];
     __syncthreads();
@@ -580,12 +567,15 @@ __global__ void __launch_bounds__(THREADS) k_sa(const SaParams P) {
         const RecClip rc = P.clip[rec];
         const int qas = rc.qas, qae = rc.qas + rc.alen;
         const uint64_t qh = qname_hash_warp(P.var + r.var_off, r.l_qname);
+        const uint8_t* sa_text = P.var + r.var_off + r.l_qname;
+        if (r.sa_len <= (uint32_t)SA_STAGE) { for (uint32_t q = lane; q < r.sa_len; q += 32) s_sa[wib][q] = __ldg(sa_text + q); sa_text = s_sa[wib]; }
+        __syncwarp();
         if (lane == 0) {
             int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0; if (hp > 2) hp = 0;
             const bool rev = r.flag & 16;
             SaArgs a; a.rec = rec; a.qas = qas; a.qae = qae; a.alen = qae - qas; a.ref_end = P.rec_end[rec]; a.hp = hp;
             a.base_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r.mapq << 16); a.qh = qh; a.nlead = P.rec_nlead[rec]; a.rev = rev; a.is_supp = r.flag & 2048;
-            a.sa = P.var + r.var_off + r.l_qname; a.sa_len = (int)r.sa_len; a.clip_left = rc.clip_left; a.clip_right = rc.clip_right; a.pos = r.pos; a.l_seq = r.l_seq; a.mapq = r.mapq;
+            a.sa = sa_text; a.sa_len = (int)r.sa_len; a.clip_left = rc.clip_left; a.clip_right = rc.clip_right; a.pos = r.pos; a.l_seq = r.l_seq; a.mapq = r.mapq;
             a.aux_flags = r.aux_flags; a.task = r.task; a.tk_contig = tk.contig; a.tk_start = tk.start; a.tk_end = tk.end; a.contig = P.contig; a.n_contig = P.n_contig;
             a.leads = P.leads; a.lead_cap = P.lead_cap; a.n_slots = &P.ctr->n_slots; a.slots = &slots;
             a.mapq_min = s_cfg.mapq; a.dev_keep_lowqual_splits = s_cfg.dev_keep_lowqual_splits; a.max_splits_base = s_cfg.max_splits_base; a.max_splits_kb = s_cfg.max_splits_kb;
