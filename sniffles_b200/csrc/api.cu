@@ -52,7 +52,7 @@ struct snfb_ctx {
     const snfb_rec* d_rec = nullptr; const uint16_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
     DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp, b_mask, b_mask_off, b_mask_task; uint32_t n_mask = 0;
     // stage A outputs
-    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_ev_cnt, b_ev_slot, b_sa_list, b_scanrec, b_clip, b_rec_big;
+    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_ev_cnt, b_ev_slot, b_sa_list, b_scanrec, b_clip, b_rec_big, b_sa_seg;
     HostBuf h_c16, h_rec16;        // BAM32 host input converted to CIGAR16 before the upload
     unsigned long long lead_cap = 0;
     DevCounters h_ctr{};
@@ -119,7 +119,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_mask, &ctx->b_mask_off, &ctx->b_mask_task, &ctx->b_ctr, &ctx->b_leads, &ctx->b_rec_pos, &ctx->b_rec_end,
-        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_ev_cnt, &ctx->b_ev_slot, &ctx->b_sa_list, &ctx->b_scanrec, &ctx->b_clip, &ctx->b_rec_big,
+        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_ev_cnt, &ctx->b_ev_slot, &ctx->b_sa_list, &ctx->b_scanrec, &ctx->b_clip, &ctx->b_rec_big, &ctx->b_sa_seg,
         &ctx->b_key0, &ctx->b_val0, &ctx->b_key1, &ctx->b_val1, &ctx->b_flag, &ctx->b_scan, &ctx->b_hist, &ctx->b_scan_tmp, &ctx->b_bin_start, &ctx->b_bin_nl, &ctx->b_bin_nlong, &ctx->b_bin_kept,
         &ctx->b_bin_hap, &ctx->b_kl_off, &ctx->b_kll_off, &ctx->b_kb_idx, &ctx->b_kl, &ctx->b_kll, &ctx->b_kb_bin, &ctx->b_kb_lead_off, &ctx->b_kb_lead_n, &ctx->b_kb_long_off, &ctx->b_kb_long_n,
         &ctx->b_kb_seed, &ctx->b_kb_chain, &ctx->b_kb_repeat, &ctx->b_seg_start, &ctx->b_c_next, &ctx->b_c_last, &ctx->b_c_sd, &ctx->b_c_mean, &ctx->b_c_rep, &ctx->b_seg_sd_last, &ctx->b_seg_maxsd,
@@ -323,7 +323,7 @@ static int run_stage_a(snfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     const uint64_t nrec = ctx->n_rec; const uint32_t nt = ctx->n_task;
     for (int attempt = 0; attempt < 3; ++attempt) {
-        if (ctx->lead_cap == 0) ctx->lead_cap = std::max<unsigned long long>(1ull << 16, nrec * 2) + 148ull * 8 * 4 * extract::WARPS * extract::SLOT_CHUNK;
+        if (ctx->lead_cap == 0) ctx->lead_cap = std::max<unsigned long long>(1ull << 16, nrec * 2) + (unsigned long long)extract::SA_BLOCKS * extract::SA_THREADS * extract::SLOT_CHUNK;
         int bad = ctx->b_ctr.ensure(sizeof(DevCounters)) | ctx->b_leads.ensure(sizeof(snfb_lead) * ctx->lead_cap) | ctx->b_rec_pos.ensure(4 * (nrec + 1)) | ctx->b_rec_end.ensure(4 * (nrec + 1)) | ctx->b_rec_flags.ensure(nrec + 1)
                 | ctx->b_rec_nm.ensure(8 * (nrec + 1)) | ctx->b_rec_nlead.ensure(4 * (nrec + 1)) | ctx->b_rec_lead_off.ensure(4 * (nrec + 1)) | ctx->b_task_first.ensure(4 * nt) | ctx->b_task_last.ensure(4 * nt)
                 | ctx->b_task_reads.ensure(4 * nt) | ctx->b_task_cov.ensure(8 * nt) | ctx->b_task_span.ensure(4 * nt) | ctx->b_task_nm.ensure(8 * nt) | ctx->b_scan_tmp.ensure(4 * (prims::scan_tmp_elems(nrec) + 16));
@@ -341,6 +341,8 @@ static int run_stage_a(snfb_ctx* ctx) {
         S.rec_end = ctx->b_rec_end.as<int32_t>(); S.rec_nlead = ctx->b_rec_nlead.as<uint32_t>(); S.rec_big = ctx->b_rec_big.as<int32_t>();
         S.ev = ctx->b_ev.as<extract::Event>(); S.ev_cap = ctx->lead_cap; S.n_ev = &ctr->n_ev; S.sa_list = ctx->b_sa_list.as<uint32_t>(); S.n_sa = &ctr->n_sa; S.ctr = ctr;
         S.minsv = cf.minsvlen_screen;
+        { const bool want_nm = cf.qc_nm_measure || cf.phase; int t = cf.minsvlen_screen < 1 ? 1 : cf.minsvlen_screen; if (want_nm && t > 11) t = 11; if (t > 0x1000) t = 0x1000;
+          S.gt_add = (uint32_t)(0x1000 - t) * 0x00010001u; }
         uint32_t* task_first = ctx->b_task_first.as<uint32_t>(); uint32_t* task_last = ctx->b_task_last.as<uint32_t>();
         uint8_t* rec_flags = ctx->b_rec_flags.as<uint8_t>(); double* rec_nm = ctx->b_rec_nm.as<double>();
         mark(ctx, "k_rec_index");
@@ -369,7 +371,9 @@ static int run_stage_a(snfb_ctx* ctx) {
             extract::SaParams A{};
             A.rec = ctx->d_rec; A.clip = ctx->b_clip.as<extract::RecClip>(); A.var = ctx->d_var; A.task = S.task; A.contig = ctx->b_contig.as<snfb_contig>(); A.n_contig = ctx->n_contig;
             A.sa_list = S.sa_list; A.n_sa = S.n_sa; A.rec_end = S.rec_end; A.rec_nlead = S.rec_nlead; A.leads = E.leads; A.lead_cap = ctx->lead_cap; A.ctr = ctr; A.cfg = cf;
-            extract::k_sa<<<148 * 10, extract::THREADS, 0, ctx->st>>>(A);
+            if (ctx->b_sa_seg.ensure(sizeof(extract::Seg) * (size_t)extract::MAXSEG * extract::SA_THREADS * extract::SA_BLOCKS)) return fail(ctx, "out of device memory (split segments)");
+            A.seg_scratch = ctx->b_sa_seg.as<extract::Seg>();
+            extract::k_sa<<<extract::SA_BLOCKS, extract::SA_THREADS, 0, ctx->st>>>(A);
             mark(ctx, "k_task_nm");
             const int cpt = (int)((nrec + extract::NM_CHUNK - 1) / extract::NM_CHUNK);
             if (ctx->b_nm_part.ensure(8 * (size_t)cpt * nt + 8) || ctx->b_nm_cnt.ensure(4 * (size_t)cpt * nt + 8)) return fail(ctx, "out of device memory (nm partials)");

@@ -16,7 +16,6 @@ namespace extract {
 
 constexpr int THREADS = 256;
 constexpr int WARPS = THREADS / 32;
-constexpr int SA_STAGE = 768; // bytes of SA text staged per warp
 constexpr int MAXSEG = 40;     // primary + supplementary segments per read held in shared memory
 
 // rec_flags bits
@@ -124,22 +123,12 @@ __device__ inline int classify_splits_dev(const snfb_config& cfg, Seg* s, int n,
     return n;
 }
 
-// ---- lead slot allocation.  A single global counter bumped once per lead serialises in L2; instead every warp reserves
+// ---- lead slot allocation.  A single global counter bumped once per lead serialises in L2; instead every thread reserves
 //      SLOT_CHUNK slots at a time and hands them out locally.  Unused slots of a retired chunk are marked as holes
 //      (rec == HOLE) and skipped later; canonical (record, k) order never depended on slot numbers.
-constexpr unsigned SLOT_CHUNK = 64;
+constexpr unsigned SLOT_CHUNK = 8;          // per allocating thread: at most SLOT_CHUNK - 1 holes each
 constexpr uint32_t HOLE = 0xffffffffu;
 struct SlotState { unsigned long long cur, end; };
-__device__ __forceinline__ unsigned long long alloc_slots_warp(SlotState& st, unsigned m, snfb_lead* leads, unsigned long long lead_cap, unsigned long long* n_slots) {
-    if (st.cur + m > st.end) {          // warp-uniform
-        for (unsigned long long s = st.cur + lane_id(); s < st.end; s += 32) if (s < lead_cap) leads[s].rec = HOLE;
-        const unsigned chunk = m > SLOT_CHUNK ? m : SLOT_CHUNK;
-        unsigned long long base = 0; if (lane_id() == 0) base = atomicAdd(n_slots, (unsigned long long)chunk);
-        base = __shfl_sync(FULL, base, 0);
-        st.cur = base; st.end = base + chunk;
-    }
-    const unsigned long long r = st.cur; st.cur += m; return r;
-}
 __device__ __forceinline__ unsigned long long alloc_slot_lane(SlotState& st, snfb_lead* leads, unsigned long long lead_cap, unsigned long long* n_slots) {   // one lane only
     if (st.cur + 1 > st.end) { const unsigned long long base = atomicAdd(n_slots, (unsigned long long)SLOT_CHUNK); st.cur = base; st.end = base + SLOT_CHUNK; }
     return st.cur++;
@@ -357,9 +346,10 @@ struct ScanParams {
     uint32_t* sa_list; unsigned long long* n_sa;
     DevCounters* ctr;
     int minsv;
+    uint32_t gt_add;      // (0x1000 - t) in both halves: bit 12 / 28 of (length + gt_add) says length >= t, t = the shortest length the rare path cares about
 };
 
-// rare path of k_scan: a slice with an I/D longer than 10, a clip / skip op or an extension word.  SV signatures are
+// rare path of k_scan: a slice with an I / D / S that may be a signature (or count for the NM correction) or an extension word.  SV signatures are
 // appended to the event list (any order: a lead's place is fixed later by its record and k).  Returns (big << 32) | leads counted.
 __device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr,
                                                       uint32_t rec, unsigned pos_q, int pos_r, unsigned k0, int tk_start, int tk_end) {
@@ -434,12 +424,13 @@ __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanPar
         #define LOAD_SLICE(base) (((base) + li0 < n) ? __ldg(cga + ((base) >> 3)) : make_uint4(0, 0, 0, 0))
         uint4 va = LOAD_SLICE(0), vb = LOAD_SLICE(256);
         if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; }
-        unsigned pos_q = 0; int pos_r = r_pos; unsigned big = 0, nlead = 0;
+        unsigned pos_q = 0; int pos_r = r_pos; unsigned big = 0, nlead = 0; const uint32_t gt_add = P.gt_add;
         // Two ops per 32-bit word: both halves are summed at once (a lane's eight 12-bit lengths cannot overflow 16 bits).
-        // bit 12 / 28 of `rb` flags a half that needs the rare path: an I / D longer than 10, a clip / skip op, an extension word.
-        #define WORD_BODY(w) { const uint32_t s_ = (w) >> 12; \
+        // bit 12 / 28 of `rb` flags a half that needs the rare path: an I / D / S of at least the length the path cares about
+        // (minsvlen_screen, or 11 when the NM correction is wanted), or an extension word.
+        #define WORD_BODY(w) { const uint32_t s_ = (w) >> 12, s1_ = (w) >> 1, s2_ = (w) >> 2; \
             aq += (w) & ((s_ & 0x00010001u) * 0xfffu); ar += (w) & (((s_ >> 1) & 0x00010001u) * 0xfffu); \
-            rb |= ((((w) & 0x0fff0fffu) + 0x0ff50ff5u) & ~((w) & ((w) >> 1))) | ((w) >> 2) | ((w) >> 3); }
+            rb |= ((((w) & 0x0fff0fffu) + gt_add) & ((w) ^ s1_) & ~(s1_ & s2_)) | ((w) >> 3); }
         #define SLICE_BODY(v, base) { \
             const uint32_t w0 = (v).x, w1 = (v).y, w2 = (v).z, w3 = (v).w; \
             uint32_t aq = 0, ar = 0, rb = 0; \
@@ -546,49 +537,44 @@ struct SaParams {
     const snfb_rec* rec; const RecClip* clip; const uint8_t* var; const snfb_task* task; const snfb_contig* contig; uint32_t n_contig;
     const uint32_t* sa_list; const unsigned long long* n_sa; const int32_t* rec_end; uint32_t* rec_nlead;
     snfb_lead* leads; unsigned long long lead_cap; DevCounters* ctr;
+    Seg* seg_scratch;                 // MAXSEG segments per thread of the grid
     snfb_config cfg;
 };
-// one warp per record with an SA tag (lane 0 parses; the warp hashes the name)
-__global__ void __launch_bounds__(THREADS) k_sa(const SaParams P) {
-    __shared__ Seg segs[WARPS][MAXSEG];
-    __shared__ __align__(16) uint8_t s_sa[WARPS][SA_STAGE];     // the SA text is parsed byte by byte by one lane: stage it next to the SM first
+constexpr int SA_THREADS = 128, SA_BLOCKS = 148 * 8;
+// one thread per record with an SA tag: the text parse is serial per record, so the parallelism is across records.
+// Segments live in a per-thread slice of global scratch (a read has a handful of them; the touched part stays in L2).
+__global__ void __launch_bounds__(SA_THREADS) k_sa(const SaParams P) {
     __shared__ snfb_config s_cfg;
     if (threadIdx.x < sizeof(snfb_config) / 4) reinterpret_cast<uint32_t*>(&s_cfg)[threadIdx.x] = reinterpret_cast<const uint32_t*>(&P.cfg)[threadIdx.x];
     __syncthreads();
-    const int lane = lane_id(), wib = threadIdx.x >> 5;
     const unsigned long long n = *P.n_sa;
-    const unsigned long long nw = (unsigned long long)gridDim.x * WARPS;
+    const unsigned long long tid = (unsigned long long)blockIdx.x * SA_THREADS + threadIdx.x, nthr = (unsigned long long)gridDim.x * SA_THREADS;
+    Seg* sg = P.seg_scratch + tid * MAXSEG;
     unsigned long long soft = 0, overflow = 0;
     SlotState slots; slots.cur = 0; slots.end = 0;
-    for (unsigned long long e = (unsigned long long)blockIdx.x * WARPS + wib; e < n; e += nw) {
+    for (unsigned long long e = tid; e < n; e += nthr) {
         const uint32_t rec = P.sa_list[e];
-        const snfb_rec r = P.rec[rec];
-        const snfb_task tk = P.task[r.task];
+        const uint4* core = reinterpret_cast<const uint4*>(P.rec + rec);
+        const uint4 c0 = __ldg(core), c1 = __ldg(core + 1), c3 = __ldg(core + 3);
+        const int r_task = (int)c0.x, r_pos = (int)c0.y; const unsigned flag = c0.z & 0xffffu, mapq = (c0.z >> 16) & 255u, aux = c0.z >> 24; const int l_qname = (int)((c0.w >> 8) & 255u);
+        const int l_seq = (int)c1.w; const unsigned long long var_off = (unsigned long long)c3.z | ((unsigned long long)c3.w << 32);
+        const uint32_t sa_len = __ldg(reinterpret_cast<const uint32_t*>(core + 2));
+        const snfb_task tk = P.task[r_task];
         const RecClip rc = P.clip[rec];
-        const int qas = rc.qas, qae = rc.qas + rc.alen;
-        const uint64_t qh = qname_hash_warp(P.var + r.var_off, r.l_qname);
-        const uint8_t* sa_text = P.var + r.var_off + r.l_qname;
-        if (r.sa_len <= (uint32_t)SA_STAGE) { for (uint32_t q = lane; q < r.sa_len; q += 32) s_sa[wib][q] = __ldg(sa_text + q); sa_text = s_sa[wib]; }
-        __syncwarp();
-        if (lane == 0) {
-            int hp = (r.aux_flags & SNFB_AUX_HP) ? r.hp : 0; if (hp > 2) hp = 0;
-            const bool rev = r.flag & 16;
-            SaArgs a; a.rec = rec; a.qas = qas; a.qae = qae; a.alen = qae - qas; a.ref_end = P.rec_end[rec]; a.hp = hp;
-            a.base_flags = (rev ? SNFB_LF_REVERSE : 0u) | ((uint32_t)r.mapq << 16); a.qh = qh; a.nlead = P.rec_nlead[rec]; a.rev = rev; a.is_supp = r.flag & 2048;
-            a.sa = sa_text; a.sa_len = (int)r.sa_len; a.clip_left = rc.clip_left; a.clip_right = rc.clip_right; a.pos = r.pos; a.l_seq = r.l_seq; a.mapq = r.mapq;
-            a.aux_flags = r.aux_flags; a.task = r.task; a.tk_contig = tk.contig; a.tk_start = tk.start; a.tk_end = tk.end; a.contig = P.contig; a.n_contig = P.n_contig;
-            a.leads = P.leads; a.lead_cap = P.lead_cap; a.n_slots = &P.ctr->n_slots; a.slots = &slots;
-            a.mapq_min = s_cfg.mapq; a.dev_keep_lowqual_splits = s_cfg.dev_keep_lowqual_splits; a.max_splits_base = s_cfg.max_splits_base; a.max_splits_kb = s_cfg.max_splits_kb;
-            const unsigned added = process_sa(&s_cfg, segs[wib], a, &soft, &overflow);
-            if (added) P.rec_nlead[rec] += added;
-        }
-        __syncwarp();
+        int hp = (aux & SNFB_AUX_HP) ? (int)(c0.w & 255u) : 0; if (hp > 2) hp = 0;
+        const bool rev = flag & 16u;
+        SaArgs a; a.rec = rec; a.qas = rc.qas; a.qae = rc.qas + rc.alen; a.alen = rc.alen; a.ref_end = P.rec_end[rec]; a.hp = hp;
+        a.base_flags = (rev ? SNFB_LF_REVERSE : 0u) | (mapq << 16); a.qh = qname_hash_thread(P.var + var_off, l_qname); a.nlead = P.rec_nlead[rec]; a.rev = rev; a.is_supp = flag & 2048u;
+        a.sa = P.var + var_off + l_qname; a.sa_len = (int)sa_len; a.clip_left = rc.clip_left; a.clip_right = rc.clip_right; a.pos = r_pos; a.l_seq = l_seq; a.mapq = (int)mapq;
+        a.aux_flags = (int)aux; a.task = r_task; a.tk_contig = tk.contig; a.tk_start = tk.start; a.tk_end = tk.end; a.contig = P.contig; a.n_contig = P.n_contig;
+        a.leads = P.leads; a.lead_cap = P.lead_cap; a.n_slots = &P.ctr->n_slots; a.slots = &slots;
+        a.mapq_min = s_cfg.mapq; a.dev_keep_lowqual_splits = s_cfg.dev_keep_lowqual_splits; a.max_splits_base = s_cfg.max_splits_base; a.max_splits_kb = s_cfg.max_splits_kb;
+        const unsigned added = process_sa(&s_cfg, sg, a, &soft, &overflow);
+        if (added) P.rec_nlead[rec] += added;
     }
-    if (lane == 0) {
-        for (unsigned long long sidx = slots.cur; sidx < slots.end; ++sidx) if (sidx < P.lead_cap) P.leads[sidx].rec = HOLE;   // retire the last chunk
-        if (soft) atomicAdd(&P.ctr->soft_errors, soft);
-        if (overflow) atomicAdd(&P.ctr->lead_overflow, overflow);
-    }
+    for (unsigned long long sidx = slots.cur; sidx < slots.end; ++sidx) if (sidx < P.lead_cap) P.leads[sidx].rec = HOLE;   // retire the last chunk
+    if (soft) atomicAdd(&P.ctr->soft_errors, soft);
+    if (overflow) atomicAdd(&P.ctr->lead_overflow, overflow);
 }
 
 // deterministic per-task mean of the per-read nm values (config.average_regional_nm, leadprov.py:577).
