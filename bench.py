@@ -103,6 +103,36 @@ def ncu_traffic():
     return None
 
 
+def bind_near_gpu(index):
+    """Run on the CPUs of the GPU's NUMA node while the block is generated, packed and pinned: first-touch then places the host
+    arenas next to the GPU's PCIe root, so the e2e host->device copy does not cross the socket interconnect.  Best effort."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        dev = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{dev}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            log(f"[bench] GPU {index} ({dev}): no NUMA node reported")
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        old = os.sched_getaffinity(0)
+        new = cpus & old
+        if not new or new == old:
+            log(f"[bench] GPU {index} ({dev}) is on NUMA node {node}; affinity unchanged ({len(old)} CPUs)")
+            return None
+        os.sched_setaffinity(0, new)
+        log(f"[bench] GPU {index} ({dev}) is on NUMA node {node}: building the block on its {len(new)} of {len(old)} CPUs")
+        return old
+    except Exception as e:          # no sysfs entry, old torch, container without the node files
+        log(f"[bench] NUMA binding skipped: {e}")
+        return None
+
+
 def workload(args, mask, threads):
     from sniffles_b200 import synth
     t0 = time.time()
@@ -195,7 +225,8 @@ def run_b200(args):
     owner = sdist.lpt_assign(lens, world)
     mask = [o == rank for o in owner] if world > 1 else None
     ncores = os.cpu_count() or 1
-    blk = workload(args, mask, max(1, ncores // world))
+    old_affinity = bind_near_gpu(local)
+    blk = workload(args, mask, max(1, (len(os.sched_getaffinity(0)) if old_affinity else ncores // world)))
     abp_local = aligned_bp_passing(blk, cfg)
     L = binding.lib()
     t0 = time.time()
@@ -208,6 +239,12 @@ def run_b200(args):
             if a.nbytes and L.snfb_pin_host(C.c_void_p(a.ctypes.data), a.nbytes) == 0:
                 pinned.append(a)
         log(f"[bench] pinned {sum(a.nbytes for a in pinned) / 1e9:.2f} GB of host arenas in {time.time() - t0:.1f}s")
+    if old_affinity:            # every thread (the OpenMP pool was created under the narrow mask) gets all CPUs back
+        for tid in os.listdir("/proc/self/task"):
+            try:
+                os.sched_setaffinity(int(tid), old_affinity)
+            except OSError:
+                pass
     ctx = binding.Context(local)
     ctx.set_config(ccfg)
     ctx.load(blk)

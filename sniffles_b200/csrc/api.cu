@@ -67,7 +67,7 @@ struct snfb_ctx {
     unsigned long long n_bound = 0, cand_cap = 0, cand_lead_cap = 0, rn_cap = 0;
     bool sorted_in_first = true, stage_a_done = false, stage_b_done = false;
     // stage C
-    DevBuf b_plan_best, b_plan_nother, b_alt_len, b_scr_len, b_alt_off, b_scr_off, b_alt, b_scr, b_sorted_leads, b_work_big, b_work_small, b_work_ctr, b_seq_req, b_arena_off, b_seq_arena, b_items_big, b_items_small, b_tiles;
+    DevBuf b_plan_best, b_plan_nother, b_plan_otot, b_alt_len, b_scr_len, b_alt_off, b_scr_off, b_alt, b_scr, b_sorted_leads, b_work_big, b_work_small, b_work_ctr, b_seq_req, b_arena_off, b_seq_arena, b_items_big, b_items_small, b_tiles;
     HostBuf h_seq_req, h_seq_arena; uint64_t seq_h2d_bytes = 0;
     // host staging
     HostBuf h_leads, h_task_reads, h_task_nm, h_rec_nm, h_cand, h_cand_leads, h_rnames, h_rn_off, h_task_cov, h_alt;
@@ -126,7 +126,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
         &ctx->b_cl_first, &ctx->b_cl_last, &ctx->b_cl_rep, &ctx->b_s_hi, &ctx->b_s_lo, &ctx->b_s_a, &ctx->b_s_b, &ctx->b_s_c, &ctx->b_s_d, &ctx->b_s_e, &ctx->b_ord, &ctx->b_ml_slot, &ctx->b_ml_svlen,
         &ctx->b_ml_seqlen, &ctx->b_ml_plo, &ctx->b_ml_pn, &ctx->b_ml_has, &ctx->b_subl, &ctx->b_sub_cnt, &ctx->b_sub_off, &ctx->b_t_lo, &ctx->b_t_n, &ctx->b_t_bin, &ctx->b_sub_cluster, &ctx->b_sub_lo,
         &ctx->b_sub_n, &ctx->b_sub_bin, &ctx->b_cand_tmp, &ctx->b_cand_valid, &ctx->b_cand_id, &ctx->b_cand_nlead, &ctx->b_cand_lead_off, &ctx->b_cand_nrn, &ctx->b_cand_rn_off, &ctx->b_cand,
-        &ctx->b_cand_leads, &ctx->b_cand_lead_ml, &ctx->b_rnames, &ctx->b_rn_off_out, &ctx->b_plan_best, &ctx->b_plan_nother, &ctx->b_alt_len, &ctx->b_scr_len, &ctx->b_alt_off, &ctx->b_scr_off,
+        &ctx->b_cand_leads, &ctx->b_cand_lead_ml, &ctx->b_rnames, &ctx->b_rn_off_out, &ctx->b_plan_best, &ctx->b_plan_nother, &ctx->b_plan_otot, &ctx->b_alt_len, &ctx->b_scr_len, &ctx->b_alt_off, &ctx->b_scr_off,
         &ctx->b_alt, &ctx->b_scr, &ctx->b_sorted_leads, &ctx->b_work_big, &ctx->b_work_small, &ctx->b_work_ctr, &ctx->b_seq_req, &ctx->b_arena_off, &ctx->b_seq_arena, &ctx->b_items_big, &ctx->b_items_small, &ctx->b_tiles };
     for (DevBuf* b : bufs) b->release();
     HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt, &ctx->h_seq_req, &ctx->h_seq_arena, &ctx->h_c16, &ctx->h_rec16 };
@@ -281,7 +281,7 @@ static int ensure_stage_b(snfb_ctx* ctx, unsigned long long nb) {
     // shared leads_long, so allow 2x and check on device
     ctx->cand_cap = nb + 8; ctx->cand_lead_cap = 2 * nb + 64; ctx->rn_cap = 2 * nb + 64;
     bad |= ctx->b_cand.ensure(sizeof(snfb_cand) * ctx->cand_cap) | ctx->b_cand_leads.ensure(sizeof(snfb_lead) * ctx->cand_lead_cap) | ctx->b_cand_lead_ml.ensure(4 * ctx->cand_lead_cap) | ctx->b_rnames.ensure(8 * ctx->rn_cap) | ctx->b_rn_off_out.ensure(4 * (ctx->cand_cap + 1));
-    bad |= ctx->b_plan_best.ensure(4 * ctx->cand_cap) | ctx->b_plan_nother.ensure(4 * ctx->cand_cap) | ctx->b_alt_len.ensure(4 * ctx->cand_cap) | ctx->b_scr_len.ensure(4 * ctx->cand_cap) | ctx->b_alt_off.ensure(4 * ctx->cand_cap) | ctx->b_scr_off.ensure(4 * ctx->cand_cap);
+    bad |= ctx->b_plan_best.ensure(4 * ctx->cand_cap) | ctx->b_plan_nother.ensure(4 * ctx->cand_cap) | ctx->b_plan_otot.ensure(4 * ctx->cand_cap) | ctx->b_alt_len.ensure(4 * ctx->cand_cap) | ctx->b_scr_len.ensure(4 * ctx->cand_cap) | ctx->b_alt_off.ensure(4 * ctx->cand_cap) | ctx->b_scr_off.ensure(4 * ctx->cand_cap);
     return bad;
 }
 
@@ -528,10 +528,9 @@ static int run_stage_c(snfb_ctx* ctx) {
     consensus::C c{};
     c.cand = ctx->b_cand.as<snfb_cand>(); c.cand_rw = ctx->b_cand.as<snfb_cand>(); c.cand_leads = ctx->b_cand_leads.as<snfb_lead>(); c.cand_lead_ml = ctx->b_cand_lead_ml.as<uint32_t>();
     c.ml_plo = ctx->b_ml_plo.as<uint32_t>(); c.ml_pn = ctx->b_ml_pn.as<uint32_t>(); c.ord = ctx->b_ord.as<uint32_t>(); c.leads = ctx->b_leads.as<snfb_lead>(); c.rec = ctx->d_rec; c.seq = ctx->d_seq;
-    c.plan_best = ctx->b_plan_best.as<uint32_t>(); c.plan_nother = ctx->b_plan_nother.as<uint32_t>(); c.alt_len = ctx->b_alt_len.as<uint32_t>(); c.scr_len = ctx->b_scr_len.as<uint32_t>();
+    c.plan_best = ctx->b_plan_best.as<uint32_t>(); c.plan_nother = ctx->b_plan_nother.as<uint32_t>(); c.plan_otot = ctx->b_plan_otot.as<uint32_t>(); c.alt_len = ctx->b_alt_len.as<uint32_t>(); c.scr_len = ctx->b_scr_len.as<uint32_t>();
     c.alt_off = ctx->b_alt_off.as<uint32_t>(); c.scr_off = ctx->b_scr_off.as<uint32_t>(); c.cand_cap = ctx->cand_cap; c.ctr = ctx->b_ctr.as<DevCounters>(); c.cfg = ctx->cfg;
-    static const bool use_items = []{ const char* e = getenv("SNFB_CONS"); return !(e && strcmp(e, "block") == 0); }();
-    c.item_cap = ctx->cand_lead_cap; c.tile_cap = ctx->cand_cap + ctx->cand_lead_cap / 8 + 1024; c.use_items = use_items ? 1 : 0;
+    c.item_cap = ctx->cand_lead_cap; c.tile_cap = ctx->cand_cap + ctx->cand_lead_cap / 8 + 1024;
     if (ctx->b_work_big.ensure(4 * ctx->cand_cap) || ctx->b_work_small.ensure(4 * ctx->cand_cap) || ctx->b_work_ctr.ensure(64) || ctx->b_items_big.ensure(16 * c.item_cap) || ctx->b_items_small.ensure(16 * c.item_cap)
         || ctx->b_tiles.ensure(8 * c.tile_cap)) return fail(ctx, "out of device memory (consensus queue)");
     c.work_big = ctx->b_work_big.as<uint32_t>(); c.work_small = ctx->b_work_small.as<uint32_t>(); c.work_ctr = ctx->b_work_ctr.as<uint32_t>();
@@ -584,23 +583,11 @@ static int run_stage_c(snfb_ctx* ctx) {
     }
     if (ctx->h_ctr.n_cand) {
         mark(ctx, "consensus", ctx->h_ctr.n_seq_bytes * 16);
-        if (c.use_items) {
-            consensus::k_prep<<<148 * 8, 128, 0, ctx->st>>>(c);
-            consensus::k_align<<<148 * 8, consensus::ALIGN_WARPS * 32, 0, ctx->st>>>(c);
-            consensus::k_vote<<<148 * 4, 256, 0, ctx->st>>>(c); LAUNCHED(ctx, 3);
-        } else {
-        // heavy candidates (long insertions x many reads) first, with 16 warps each; then the bulk with 4 warps each
-        constexpr int NWB = 8, NWS = 4;
-        const size_t smem_b = (size_t)3 * NWB * consensus::MAXHIT * sizeof(int), smem_s = (size_t)3 * NWS * consensus::MAXHIT * sizeof(int);
-        static bool attr_set = false;
-        if (!attr_set) { cudaFuncSetAttribute(consensus::k_run<NWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_b); cudaFuncSetAttribute(consensus::k_run<NWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s); attr_set = true; }
-        // the two launches drain different queues: run them concurrently (second stream) so that the bulk fills the SMs
-        // the heavy tail leaves idle
-        CUDA_TRY(cudaEventRecord(ctx->ev_fork, ctx->st)); CUDA_TRY(cudaStreamWaitEvent(ctx->st2, ctx->ev_fork, 0));
-        consensus::k_run<NWB><<<148 * 3, NWB * 32, smem_b, ctx->st>>>(c, 1);
-        consensus::k_run<NWS><<<(int)std::min<unsigned long long>(ctx->h_ctr.n_cand, 148ull * 6), NWS * 32, smem_s, ctx->st2>>>(c, 0); LAUNCHED(ctx, 2);
-        CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->st2)); CUDA_TRY(cudaStreamWaitEvent(ctx->st, ctx->ev_join, 0));
-        }
+        consensus::k_prep<<<148 * 8, 128, 0, ctx->st>>>(c);
+        mark(ctx, "consensus_align");
+        consensus::k_align<<<148 * 8, consensus::ALIGN_WARPS * 32, 0, ctx->st>>>(c);
+        mark(ctx, "consensus_vote");
+        consensus::k_vote<<<148 * 4, 256, 0, ctx->st>>>(c); LAUNCHED(ctx, 3);
         mark(ctx, nullptr);
     }
     CUDA_TRY(cudaGetLastError());

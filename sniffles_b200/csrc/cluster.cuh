@@ -255,6 +255,12 @@ __global__ void k_cluster_build(B b) {
         if (b.flag[k]) { const uint32_t c = b.scan[k]; b.cl_first[c] = (uint32_t)k; b.cl_last[c] = b.c_last[k]; b.cl_rep[c] = b.c_rep[k]; }
 }
 
+// The per-cluster / per-candidate kernels below run one thread per item, and a heavy item (hundreds of leads in a tandem
+// repeat) is one long chain of dependent gathers of 64-byte leads.  Requesting all of an item's leads up front turns the
+// chain's DRAM / L2 latencies into L1 hits.
+__device__ __forceinline__ void prefetch_lead(const snfb_lead* l) { asm volatile("prefetch.global.L1 [%0];" :: "l"(l)); }
+constexpr long PREFETCH_MIN = 8;
+
 // ---------------------------------------------------------------- per-cluster post-processing
 // cluster.merge_inner (cluster.py:85-122), cluster.resplit (125-161), cluster.resplit_bnd (164-216)
 __global__ void k_cluster_post(B b) {
@@ -266,6 +272,7 @@ __global__ void k_cluster_post(B b) {
         const uint32_t lo = b.kb_lead_off[kf], hi = b.kb_lead_off[kl_] + b.kb_lead_n[kl_];
         const long n = (long)hi - lo; const int svtype = (int)(b.kb_chain[kf] & 7u);
         uint64_t* khi = b.s_hi + lo; uint64_t* klo = b.s_lo + lo;
+        if (n >= PREFETCH_MIN) for (long i = 0; i < n; ++i) prefetch_lead(&b.leads[b.kl[lo + i]]);
         long nm = 0;                    // number of merged leads
         if ((svtype == SNFB_INS || svtype == SNFB_DEL)) {
             const int thr = b.cl_rep[c] ? -1 : cfg.cluster_merge_pos;
@@ -399,6 +406,7 @@ __global__ void k_call(B b) {
         uint64_t* w2 = b.s_lo + slo;
         b.cand_valid[s] = 0; b.cand_nlead[s] = 0; b.cand_nrn[s] = 0;
         if (n == 0) continue;
+        if (n >= PREFETCH_MIN) for (long i = 0; i < n; ++i) prefetch_lead(&b.leads[b.ml_slot[b.subl[slo + i]]]);
         // svlen = center(svlens)
         for (long i = 0; i < n; ++i) w[i] = bias64(b.ml_svlen[b.subl[slo + i]]);
         hsort1(w, n);
@@ -510,6 +518,7 @@ __global__ void k_cand_finish(B b) {
         cd.lead_off = (int)lo_out; cd.long_off = (int)(lo_out + n); cd.alt_off = -1; cd.alt_len = 0;
         if ((unsigned long long)lo_out + n + cd.long_n > b.cand_lead_cap || (unsigned long long)rn_out + cd.support > b.rn_cap) { atomicAdd(&b.ctr->scratch_overflow, 1ULL); continue; }
         uint64_t* w = b.s_hi + slo; uint64_t* w2 = b.s_lo + slo;
+        if (n >= PREFETCH_MIN) for (long i = 0; i < n; ++i) prefetch_lead(&b.leads[b.ml_slot[b.subl[slo + i]]]);
         int nf = 0, nr = 0; long ninl = 0;
         for (long i = 0; i < n; ++i) {
             const uint32_t mi = b.subl[slo + i]; snfb_lead L = b.leads[b.ml_slot[mi]];

@@ -1,9 +1,8 @@
 // consensus.cuh — stage C: INS ALT sequences.
 //   postprocessing.annotate_sv INS branch (best read selection)        postprocessing.py:33-66
 //   consensus.novel_from_reads (k-mer anchored pile-up polish, k = 6)  consensus.py:280-394
-// One thread block per INS candidate.  The best read's strided 6-mers live in a shared-memory
-// hash table; every other read is aligned by one warp (32 k-mer probes per step, hits replayed
-// in order through the reference's anchor automaton); the column vote is one thread per column.
+// k_plan picks the best read per candidate and sizes the work; k_prep unpacks the best read and builds its anchor
+// table; k_align aligns one (candidate, supporting read) pair per warp; k_vote takes the column vote per 4096-column tile.
 #pragma once
 #include "common.cuh"
 
@@ -18,12 +17,12 @@ struct C {
     const uint32_t* ml_plo; const uint32_t* ml_pn; const uint32_t* ord; const snfb_lead* leads;
     const snfb_rec* rec; const uint8_t* seq;
     const uint32_t* arena_off;       // seq on demand: per lead slot, 16-byte unit offset of its bytes in `seq` (which then is the compact arena); nullptr = full arena
-    uint32_t* plan_best; uint32_t* plan_nother; uint32_t* alt_len; uint32_t* scr_len; uint32_t* alt_off; uint32_t* scr_off;   // scr in units of 16 bytes
+    uint32_t* plan_best; uint32_t* plan_nother; uint32_t* plan_otot; uint32_t* alt_len; uint32_t* scr_len; uint32_t* alt_off; uint32_t* scr_off;   // scr in units of 16 bytes
     uint8_t* alt; uint8_t* scr; unsigned long long alt_cap, scr_cap16, cand_cap;
     uint32_t* work_big; uint32_t* work_small; uint32_t* work_ctr;      // work_ctr: [0] n_big, [1] n_small, [2],[3] queue positions, [4] n_items_big, [5] n_items_small, [6],[7] item queue positions, [8] n_tiles, [9] tile queue position
     // item pipeline: one (candidate, supporting read) pair per warp, one (candidate, column tile) per block
     struct Item { uint32_t cand; uint32_t k; uint32_t row; uint32_t rd_off; };
-    Item* items_big; Item* items_small; uint2* tiles; unsigned long long item_cap, tile_cap; int use_items;
+    Item* items_big; Item* items_small; uint2* tiles; unsigned long long item_cap, tile_cap;
     DevCounters* ctr; snfb_config cfg;
 };
 
@@ -43,15 +42,15 @@ __global__ void k_plan(C c) {
             if (nm > 0) {
                 const uint32_t L = (uint32_t)c.cand_leads[cd->lead_off + bi].seq_len; al = L;
                 const bool cons = (nm - 1 >= c.cfg.consensus_min_reads) && !c.cfg.no_consensus;
-                c.plan_best[i] = (uint32_t)bi; c.plan_nother[i] = cons ? (uint32_t)(nm - 1) : 0u;
-                // scratch: best codes + others' codes + one row of L per other read + accept flags, 16-byte units
-                const unsigned long long bytes = cons ? (unsigned long long)tot + (unsigned long long)(nm - 1) * L + (unsigned long long)(nm - 1) * 16 + 64 + (c.use_items ? 16 + TAB * 8 : 0) : (unsigned long long)L + 16;
+                c.plan_best[i] = (uint32_t)bi; c.plan_nother[i] = cons ? (uint32_t)(nm - 1) : 0u; c.plan_otot[i] = (uint32_t)(tot - L);
+                // scratch: best codes | others' codes | (4-byte aligned) one row of align4(L) per other read | accept flags | anchor table; 16-byte units
+                const unsigned long long bytes = cons ? (unsigned long long)tot + 4 + (unsigned long long)(nm - 1) * ((L + 3u) & ~3u) + (unsigned long long)(nm - 1) * 16 + 64 + 16 + TAB * 8 : (unsigned long long)L + 16;
                 sl = (uint32_t)((bytes + 15) / 16);
                 c.cand_rw[i].alt_len = (int)L;
                 // work queue: the heavy tail (long insertions with many reads) is scheduled first
                 const unsigned long long work = (unsigned long long)L * (unsigned long long)nm;
                 if (work > 60000ull) c.work_big[atomicAdd(&c.work_ctr[0], 1u)] = (uint32_t)i; else c.work_small[atomicAdd(&c.work_ctr[1], 1u)] = (uint32_t)i;
-                if (c.use_items && cons) {
+                if (cons) {
                     // one work item per supporting read (heavy rows first) and one per 4096-column tile of the vote
                     const bool heavy = L > 4000u; C::Item* dst = heavy ? c.items_big : c.items_small;
                     const uint32_t base = atomicAdd(&c.work_ctr[heavy ? 4 : 5], (uint32_t)(nm - 1));
@@ -138,179 +137,8 @@ __device__ inline void unpack_lead_warp(const C& c, uint32_t cl_index, uint8_t* 
     }
 }
 
-// One block per INS candidate, candidates pulled from a two-level work queue (heavy ones first).
-// Per other read (one warp each):  (1) 32 k-mer probes per step collect the anchor hits, (2) the reference's
-// order-dependent anchor automaton runs over the compact hit list in shared memory (no memory latency in the
-// serial part), (3) the accepted hits become independent segments that the lanes compare / copy in parallel,
-// (4) dash-free runs are filtered with ballots.  Then one thread per column votes.
-// NW warps per block; `big` selects which of the two work lists the launch drains (heavy candidates get wide blocks).
-template <int NW>
-__global__ void __launch_bounds__(NW * 32) k_run(C c, int big) {
-    extern __shared__ int dyn_smem[];
-    __shared__ uint32_t t_key[TAB]; __shared__ int t_pos[TAB];      // t_pos: -1 empty, -2 k-mer seen more than once (banned), else its position
-    int (*h_i)[MAXHIT] = reinterpret_cast<int (*)[MAXHIT]>(dyn_smem);
-    int (*h_j)[MAXHIT] = h_i + NW; int (*h_cl)[MAXHIT] = h_j + NW;
-    __shared__ int n_accept; __shared__ uint32_t s_cand;
-    const int lane = lane_id(), warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    static const char CODE[17] = "=ACMGRSVTWYHKDBN";
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            const uint32_t q = atomicAdd(&c.work_ctr[big ? 2 : 3], 1u); const uint32_t nq = c.work_ctr[big ? 0 : 1];
-            s_cand = q < nq ? (big ? c.work_big[q] : c.work_small[q]) : 0xffffffffu;
-            n_accept = 0;
-        }
-        __syncthreads();
-        const uint32_t ci = s_cand;
-        if (ci == 0xffffffffu) break;
-        const uint32_t L = c.alt_len[ci];
-        const snfb_cand cd = c.cand[ci];
-        if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) { if (threadIdx.x == 0) atomicAdd(&c.ctr->scratch_overflow, 1ULL); continue; }
-        uint8_t* out = c.alt + c.alt_off[ci];
-        uint8_t* best = c.scr + (size_t)c.scr_off[ci] * 16;
-        const uint32_t bi = c.plan_best[ci], no = c.plan_nother[ci];
-        unpack_lead(c, cd.lead_off + bi, best);
-        if (threadIdx.x == 0) c.cand_rw[ci].alt_off = (int)c.alt_off[ci];
-        __syncthreads();
-        if (no == 0 || L == 0) { for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) out[h] = (uint8_t)CODE[best[h]]; continue; }
-        // layout: best[L] | other reads' codes | rows[no][L] | accept[no]
-        uint8_t* oth = best + L;
-        const int klen = 6; const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
-        // anchors: k-mers of the best read seen exactly once among the strided positions (consensus.py:292-299)
-        for (int i = threadIdx.x; i < TAB; i += blockDim.x) { t_key[i] = 0xffffffffu; t_pos[i] = -1; }
-        __syncthreads();
-        for (long i = (long)threadIdx.x * skip; i < (long)L - klen; i += (long)blockDim.x * skip) {
-            const uint32_t key = kmer6(best + i); uint32_t s = kslot(key);
-            for (;;) { const uint32_t old = atomicCAS(&t_key[s], 0xffffffffu, key); if (old == 0xffffffffu || old == key) break; s = (s + 1) & (TAB - 1); }
-            if (atomicCAS(&t_pos[s], -1, (int)i) != -1) t_pos[s] = -2;
-        }
-        long long o_total = 0;
-        for (int k = 0; k < cd.lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd.lead_off + k]; if ((l->flags & SNFB_LF_HAS_SEQ) && (uint32_t)k != bi) o_total += l->seq_len; }
-        uint8_t* rows = oth + o_total; uint8_t* acc = rows + (size_t)no * L;
-        __syncthreads();
-        // ---- every other read: one warp ----
-        {
-            long long ro = 0; uint32_t ridx = 0;
-            int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp];
-            for (int k = 0; k < cd.lead_n; ++k) {
-                const snfb_lead* l = &c.cand_leads[cd.lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ) || (uint32_t)k == bi) continue;
-                const long Lo = l->seq_len; uint8_t* rd = oth + ro; const uint32_t myr = ridx; ro += Lo; ++ridx;
-                if ((int)(myr % nwarp) != warp) continue;
-                unpack_lead_warp(c, cd.lead_off + k, rd);
-                __syncwarp();
-                uint8_t* row = rows + (size_t)myr * L;
-                // (1) anchor hits in j order
-                int nh = 0;
-                const long nk = Lo - klen > 0 ? (Lo - klen + skip - 1) / skip : 0;
-                for (long kb = 0; kb < nk; kb += 32) {
-                    const long kk = kb + lane; const long j = kk * skip; int ai = -1;
-                    if (kk < nk) { const uint32_t key = kmer6(rd + j); uint32_t s = kslot(key);
-                        for (;;) { const uint32_t tk = t_key[s]; if (tk == 0xffffffffu) break; if (tk == key) { ai = t_pos[s]; break; } s = (s + 1) & (TAB - 1); }
-                        if (ai >= 0) { long d = ai - j; if (d < 0) d = -d; if (d > klen) ai = -1; } }
-                    const unsigned hm = __ballot_sync(FULL, ai >= 0);
-                    if (ai >= 0) { const int p = nh + __popc(hm & lanemask_lt()); if (p < MAXHIT) { hi[p] = ai; hj[p] = (int)j; } }
-                    nh += __popc(hm);
-                }
-                if (nh > MAXHIT) nh = MAXHIT;       // cannot happen (see MAXHIT); keeps the buffers safe
-                __syncwarp();
-                // (2) the anchor automaton over the hit list (consensus.py:306-338), all lanes in lockstep on shared memory.
-                //     accepted hit m: (hi[m], hj[m]) with hcl[m] = len(conseq) before its segment is appended
-                int na = 0; long last_i = -1, cl = 0;
-                for (int h = 0; h < nh; ++h) {
-                    const int i = hi[h], j = hj[h];
-                    if (na > 0 && i <= last_i) continue;
-                    long before = cl;
-                    if (na == 0) { if (j > 0) cl = i; before = 0; }
-                    else { long fwd_j = (long)j - hj[na - 1]; if (cl + fwd_j > (long)L) fwd_j = (long)L - cl; cl += fwd_j; }
-                    __syncwarp();
-                    if (lane == 0) { hi[na] = i; hj[na] = j; hcl[na] = (int)before; }
-                    __syncwarp();
-                    ++na; last_i = i;
-                }
-                // (3) segments in parallel: lane per segment
-                long span = 0;
-                if (na > 0) { const long c0 = hj[0] > 0 ? hi[0] : 0; for (long q = lane; q < c0; q += 32) row[q] = DASH; }
-                for (int m = 1 + lane; m < na; m += 32) {
-                    const long li = hi[m - 1], lj = hj[m - 1], i = hi[m], j = hj[m], cs = hcl[m];
-                    const long d = j - lj; long fwd_j = d; if (cs + fwd_j > (long)L) fwd_j = (long)L - cs;
-                    const long fwd_i = i - li; bool copy = false;
-                    if (fwd_i == fwd_j && fwd_j > 0) {
-                        span += d; int mt = 0;
-                        #pragma unroll 8
-                        for (long q = 1; q <= d; ++q) mt += (li + q < (long)L && rd[lj + q] == best[li + q]) ? 1 : 0;
-                        copy = __ddiv_rn((double)mt, (double)d) >= 0.5;
-                    }
-                    if (copy) {
-                        #pragma unroll 8
-                        for (long q = 0; q < fwd_j; ++q) row[cs + q] = rd[lj + q];
-                    } else { for (long q = 0; q < fwd_j; ++q) row[cs + q] = DASH; }
-                }
-                span = (long)__reduce_add_sync(FULL, (unsigned)span);
-                for (long q = cl + lane; q < (long)L; q += 32) row[q] = DASH;
-                __syncwarp();
-                // (4) dash-free runs survive only with identity > 0.5 and more than 5 matches (consensus.py:343-360)
-                bool in_run = false; long run_start = 0; long ident = 0;
-                for (long hb = 0; hb < (long)L; hb += 128) {
-                    // four 32-column steps are loaded up front so that their latencies overlap
-                    uint8_t ccs[4], bbs[4];
-                    #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const long h = hb + 32 * u + lane; const bool in = h < (long)L; ccs[u] = in ? row[h] : DASH; bbs[u] = in ? best[h] : (uint8_t)0; }
-                    #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const long h0 = hb + 32 * u; if (h0 >= (long)L) break;
-                        const uint8_t cc = ccs[u];
-                        const unsigned nd = __ballot_sync(FULL, cc != DASH), mt = __ballot_sync(FULL, cc != DASH && cc == bbs[u]);
-                        if (!in_run && nd == 0) continue;
-                        int p = 0;
-                        while (p < 32) {
-                            if (in_run) {
-                                const unsigned rest = ~(nd >> p); int cnt = rest ? __ffs(rest) - 1 : 32; if (cnt > 32 - p) cnt = 32 - p;
-                                const unsigned mask = cnt >= 32 ? 0xffffffffu : (((1u << cnt) - 1u) << p);
-                                ident += __popc(mt & mask); p += cnt;
-                                if (p < 32) {       // the run ended on a dash at h0 + p
-                                    const long len = h0 + p - run_start;
-                                    if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q = run_start + lane; q < h0 + p; q += 32) row[q] = DASH;
-                                    in_run = false;
-                                }
-                            } else {
-                                const unsigned rest = nd >> p; if (!rest) { p = 32; break; }
-                                p += __ffs(rest) - 1; in_run = true; run_start = h0 + p; ident = 0;
-                            }
-                        }
-                    }
-                }
-                if (in_run) { const long len = (long)L - run_start; if (!(__ddiv_rn((double)ident, (double)len) > 0.5 && ident > 5)) for (long q = run_start + lane; q < (long)L; q += 32) row[q] = DASH; }
-                const bool ok = __ddiv_rn((double)span, (double)L) > 0.2;
-                if (lane == 0) { acc[myr] = ok; if (ok) atomicAdd(&n_accept, 1); }
-            }
-        }
-        __syncthreads();
-        // ---- column vote (consensus.py:365-380) ----
-        const double maxal = (double)(1 + n_accept);
-        for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) {
-            unsigned long long cnt[4] = { 0, 0, 0, 0 }; int nal = 0;
-            for (uint32_t r0 = 0; r0 < no; r0 += 8) {       // eight row bytes in flight per thread
-                uint8_t cv[8];
-                #pragma unroll
-                for (int u = 0; u < 8; ++u) { const uint32_t r2 = r0 + u; cv[u] = (r2 < no && acc[r2]) ? rows[(size_t)r2 * L + h] : DASH; }
-                #pragma unroll
-                for (int u = 0; u < 8; ++u) { const uint8_t cc = cv[u]; if (cc != DASH) { cnt[cc >> 2] += 1ull << (16 * (cc & 3)); ++nal; } }
-            }
-            uint8_t res = best[h];
-            if (!(nal < 2 || __ddiv_rn((double)nal, maxal) < 0.25)) {
-                cnt[best[h] >> 2] += 1ull << (16 * (best[h] & 3));
-                int t0 = -1, t1 = -1, c0 = 0, nd = 0;
-                #pragma unroll
-                for (int code = 0; code < 16; ++code) { const int v = (int)((cnt[code >> 2] >> (16 * (code & 3))) & 0xffff); if (!v) continue; ++nd; if (v > t0) { t1 = t0; t0 = v; c0 = code; } else if (v > t1) t1 = v; }
-                if (nd > 1 && t0 - t1 >= 3) res = (uint8_t)c0;
-            }
-            out[h] = (uint8_t)CODE[res];
-        }
-    }
-}
-
 // ================================================================================================
-// Item pipeline (default): k_prep (block per candidate: unpack the best read, build its anchor table in global
+// k_prep (block per candidate: unpack the best read, build its anchor table in global
 // scratch, or copy the best read to ALT when there is no consensus) -> k_align (one warp per (candidate, read)
 // item from a heavy-first queue: no block barriers, the heaviest candidate's reads spread over the whole GPU)
 // -> k_vote (one block per (candidate, 4096-column tile)).
@@ -321,12 +149,18 @@ __device__ __forceinline__ int match_count(const uint8_t* a, const uint8_t* b, l
     const uint32_t sa = ((uintptr_t)a & 3) * 8, sb = ((uintptr_t)b & 3) * 8;
     const uint32_t* wa = reinterpret_cast<const uint32_t*>((uintptr_t)a & ~(uintptr_t)3); const uint32_t* wb = reinterpret_cast<const uint32_t*>((uintptr_t)b & ~(uintptr_t)3);
     uint32_t alo = wa[0], blo = wb[0]; int mt = 0;
-    for (long q = 0; q < n; q += 4) {
+    long q = 0;
+    #pragma unroll 2
+    for (; q + 4 <= n; q += 4) {
         const uint32_t ahi = *++wa, bhi = *++wb;
         const uint32_t x = __funnelshift_r(alo, ahi, sa) ^ __funnelshift_r(blo, bhi, sb);
-        uint32_t eq = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;        // 0x80 in every byte that is equal
-        if (n - q < 4) eq &= (1u << (8 * (n - q))) - 1u;
-        mt += __popc(eq); alo = ahi; blo = bhi;
+        mt += __popc(~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u);       // 0x80 in every byte that is equal
+        alo = ahi; blo = bhi;
+    }
+    if (q < n) {
+        const uint32_t ahi = *++wa, bhi = *++wb;
+        const uint32_t x = __funnelshift_r(alo, ahi, sa) ^ __funnelshift_r(blo, bhi, sb);
+        mt += __popc(~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u & ((1u << (8 * (n - q))) - 1u));
     }
     return mt;
 }
@@ -337,6 +171,7 @@ __device__ __forceinline__ void copy_bytes(uint8_t* dst, const uint8_t* src, lon
         const uint8_t* s0 = src + q; const uint32_t sh = ((uintptr_t)s0 & 3) * 8;
         const uint32_t* ws = reinterpret_cast<const uint32_t*>((uintptr_t)s0 & ~(uintptr_t)3); uint32_t lo = ws[0];
         uint32_t* wd = reinterpret_cast<uint32_t*>(dst + q);
+        #pragma unroll 4
         for (; q + 4 <= n; q += 4) { const uint32_t hi = *++ws; *wd++ = __funnelshift_r(lo, hi, sh); lo = hi; }
     }
     for (; q < n; ++q) dst[q] = src[q];
@@ -348,6 +183,13 @@ __device__ __forceinline__ void fill_dash(uint8_t* dst, long n) {
     for (; q < n; ++q) dst[q] = DASH;
 }
 
+// scratch layout of one consensus candidate: best[L] | other reads' codes [otot] | rows[no][Ls] (4-byte aligned, Ls = align4(L)) | accept[no] | ... | table
+struct Layout { uint8_t* best; uint8_t* oth; uint8_t* rows; uint8_t* acc; uint32_t Ls; };
+__device__ __forceinline__ Layout cand_layout(const C& c, uint32_t ci, uint32_t L, uint32_t no) {
+    Layout y; y.best = c.scr + (size_t)c.scr_off[ci] * 16; y.oth = y.best + L;
+    y.rows = reinterpret_cast<uint8_t*>(((uintptr_t)(y.oth + c.plan_otot[ci]) + 3) & ~(uintptr_t)3); y.Ls = (L + 3u) & ~3u; y.acc = y.rows + (size_t)no * y.Ls;
+    return y;
+}
 __device__ __forceinline__ uint8_t* cand_table(const C& c, uint32_t ci, uint32_t** keys, int** pos) {
     uint8_t* scr = c.scr + (size_t)c.scr_off[ci] * 16;
     uint8_t* end = scr + (size_t)c.scr_len[ci] * 16;
@@ -384,10 +226,10 @@ __global__ void __launch_bounds__(128) k_prep(C c) {
 }
 
 constexpr int ALIGN_WARPS = 4;
-__global__ void __launch_bounds__(ALIGN_WARPS * 32) k_align(C c) {
-    __shared__ int h_i[ALIGN_WARPS][MAXHIT], h_j[ALIGN_WARPS][MAXHIT], h_cl[ALIGN_WARPS][MAXHIT];
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
+    __shared__ int h_i[ALIGN_WARPS][MAXHIT], h_j[ALIGN_WARPS][MAXHIT], h_cl[ALIGN_WARPS][MAXHIT], h_a[ALIGN_WARPS][MAXHIT], h_b[ALIGN_WARPS][MAXHIT];
     const int lane = lane_id(), warp = threadIdx.x >> 5;
-    int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp];
+    int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp]; int* run_st = h_a[warp];   /* per-run identity sum */ int* run_len = h_b[warp];
     const int klen = 6;
     for (;;) {
         uint32_t q = 0; if (lane == 0) q = atomicAdd(&c.work_ctr[6], 1u);
@@ -398,18 +240,12 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32) k_align(C c) {
         const uint32_t ci = it.cand; const uint32_t L = c.alt_len[ci];
         if ((unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
         const snfb_cand* cd = &c.cand[ci];
-        uint32_t* t_key; int* t_pos; uint8_t* best = cand_table(c, ci, &t_key, &t_pos);
+        uint32_t* t_key; int* t_pos; cand_table(c, ci, &t_key, &t_pos);
         const uint32_t no = c.plan_nother[ci];
-        // layout: best[L] | other reads' codes | rows[no][L] | accept[no] | ... | table
-        long long o_total = 0;
-        { const uint32_t bi = c.plan_best[ci]; long long part = 0;
-          for (int k = lane; k < cd->lead_n; k += 32) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if ((l->flags & SNFB_LF_HAS_SEQ) && (uint32_t)k != bi) part += l->seq_len; }
-          #pragma unroll
-          for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(FULL, part, o);
-          o_total = part; }
-        uint8_t* oth = best + L; uint8_t* rows = oth + o_total; uint8_t* acc = rows + (size_t)no * L;
+        const Layout y = cand_layout(c, ci, L, no);
+        uint8_t* best = y.best; uint8_t* acc = y.acc;
         const snfb_lead* l = &c.cand_leads[cd->lead_off + it.k];
-        const long Lo = l->seq_len; uint8_t* rd = oth + it.rd_off; uint8_t* row = rows + (size_t)it.row * L;
+        const long Lo = l->seq_len; uint8_t* rd = y.oth + it.rd_off; uint8_t* row = y.rows + (size_t)it.row * y.Ls;
         const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
         unpack_lead_warp(c, cd->lead_off + it.k, rd);
         __syncwarp();
@@ -464,16 +300,27 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32) k_align(C c) {
         span = (long)__reduce_add_sync(FULL, (unsigned)span);
         __syncwarp();
         // (3b) dash-free runs (= chains of copied segments) survive only with identity > 0.5 and more than 5 matches
-        //      (consensus.py:343-360); decided on the segment list before anything is written
+        //      (consensus.py:343-360); decided on the segment list before anything is written.  A non-empty dashed segment
+        //      ends a run; run ids are prefix counts of those, the per-run sums are accumulated in shared memory.
         {
-            bool in_run = false; int rs = 1; long ident = 0, rlen = 0;
-            for (int m = 1; m <= na; ++m) {
-                int st = -1; long len = 1;
+            int* hr = hi;                                   // the anchor i positions are no longer needed
+            for (int m = lane; m < na; m += 32) { run_st[m] = 0; run_len[m] = 0; }
+            __syncwarp();
+            int run_base = 0;
+            for (int mb = 1; mb < na; mb += 32) {
+                const int m = mb + lane; int st = -1; long len = 0;
                 if (m < na) { const long lj = hj[m - 1]; long cs = c0 + lj - j0; if (cs > (long)L) cs = (long)L; len = hj[m] - lj; if (cs + len > (long)L) len = (long)L - cs; st = hcl[m]; }
-                if (st >= 0) { if (!in_run) { in_run = true; rs = m; ident = 0; rlen = 0; } ident += st; rlen += len; continue; }
-                if (len == 0 || !in_run) continue;                                      // empty segments do not end a run
-                if (!(__ddiv_rn((double)ident, (double)rlen) > 0.5 && ident > 5)) for (int mm = rs + lane; mm < m; mm += 32) if (hcl[mm] >= 0) hcl[mm] = -1;
-                in_run = false;
+                const unsigned bm = __ballot_sync(FULL, m < na && st < 0 && len > 0);
+                const int rid = run_base + __popc(bm & lanemask_lt());
+                __syncwarp();
+                if (m < na) { hr[m] = rid; if (st >= 0) { atomicAdd(&run_st[rid], st); atomicAdd(&run_len[rid], (int)len); } }
+                run_base += __popc(bm);
+            }
+            __syncwarp();
+            for (int m = 1 + lane; m < na; m += 32) {
+                if (hcl[m] < 0) continue;
+                const int r = hr[m], ident = run_st[r];
+                if (!(__ddiv_rn((double)ident, (double)run_len[r]) > 0.5 && ident > 5)) hcl[m] = -1;
             }
             __syncwarp();
         }
@@ -491,51 +338,72 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32) k_align(C c) {
     }
 }
 
-// column vote (consensus.py:365-380), one block per (candidate, 4096-column tile)
+// column vote (consensus.py:365-380), one block per (candidate, 4096-column tile); every thread takes four adjacent columns
+// (rows are 4-byte aligned with a stride of align4(L)), eight rows in flight
+constexpr int VOTE_LIST = 256;
+// sixteen 16-bit counters (one per base code) in four registers; the selects keep them out of local memory
+__device__ __forceinline__ void vote_add(unsigned long long (&cnt)[4], uint32_t code) {
+    const unsigned long long inc = 1ull << (16 * (code & 3u)); const uint32_t sel = (code >> 2) & 3u;
+    #pragma unroll
+    for (int k = 0; k < 4; ++k) cnt[k] += sel == (uint32_t)k ? inc : 0ull;
+}
 __global__ void __launch_bounds__(256) k_vote(C c) {
-    __shared__ uint2 s_tile; __shared__ int s_nacc;
+    __shared__ uint2 s_tile; __shared__ int s_nacc, s_nlist; __shared__ uint16_t s_rows[VOTE_LIST];
     static const char CODE[17] = "=ACMGRSVTWYHKDBN";
     for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) { const uint32_t q = atomicAdd(&c.work_ctr[9], 1u); s_tile = q < c.work_ctr[8] && q < c.tile_cap ? c.tiles[q] : make_uint2(0xffffffffu, 0); s_nacc = 0; }
+        if (threadIdx.x == 0) { const uint32_t q = atomicAdd(&c.work_ctr[9], 1u); s_tile = q < c.work_ctr[8] && q < c.tile_cap ? c.tiles[q] : make_uint2(0xffffffffu, 0); }
         __syncthreads();
         const uint32_t ci = s_tile.x; if (ci == 0xffffffffu) break;
         const uint32_t L = c.alt_len[ci], no = c.plan_nother[ci];
         if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
-        const snfb_cand* cd = &c.cand[ci];
-        uint8_t* best = c.scr + (size_t)c.scr_off[ci] * 16;
-        long long part = 0; { const uint32_t bi = c.plan_best[ci];
-          for (int k = threadIdx.x; k < cd->lead_n; k += blockDim.x) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if ((l->flags & SNFB_LF_HAS_SEQ) && (uint32_t)k != bi) part += l->seq_len; } }
-        __shared__ unsigned long long s_tot;
-        if (threadIdx.x == 0) s_tot = 0;
+        const Layout y = cand_layout(c, ci, L, no);
+        const uint8_t* best = y.best; const uint8_t* rows = y.rows; const uint8_t* acc = y.acc; const uint32_t Ls = y.Ls;
+        if (threadIdx.x < 32) {                         // the accepted rows, in order (the first VOTE_LIST rows go through the list)
+            int cnt = 0, extra = 0; const uint32_t lim = no < (uint32_t)VOTE_LIST ? no : (uint32_t)VOTE_LIST;
+            for (uint32_t r0 = 0; r0 < lim; r0 += 32) { const uint32_t r = r0 + threadIdx.x; const bool a = r < lim && acc[r]; const unsigned bm = __ballot_sync(FULL, a);
+                if (a) s_rows[cnt + __popc(bm & lanemask_lt())] = (uint16_t)r; cnt += __popc(bm); }
+            for (uint32_t r = lim + threadIdx.x; r < no; r += 32) extra += acc[r] ? 1 : 0;
+            extra = (int)__reduce_add_sync(FULL, (unsigned)extra);
+            if (threadIdx.x == 0) { s_nlist = cnt; s_nacc = cnt + extra; }
+        }
         __syncthreads();
-        if (part) atomicAdd(&s_tot, (unsigned long long)part);
-        __syncthreads();
-        const uint8_t* rows = best + L + s_tot; const uint8_t* acc = rows + (size_t)no * L;
-        int na = 0; for (uint32_t r = threadIdx.x; r < no; r += blockDim.x) na += acc[r] ? 1 : 0;
-        if (na) atomicAdd(&s_nacc, na);
-        __syncthreads();
-        const double maxal = (double)(1 + s_nacc);
+        const double maxal = (double)(1 + s_nacc); const int nlist = s_nlist;
         uint8_t* out = c.alt + c.alt_off[ci];
         const uint32_t h_end = min(L, (s_tile.y + 1u) * 4096u);
-        for (uint32_t h = s_tile.y * 4096u + threadIdx.x; h < h_end; h += blockDim.x) {
-            unsigned long long cnt[4] = { 0, 0, 0, 0 }; int nal = 0;
-            for (uint32_t r0 = 0; r0 < no; r0 += 8) {
-                uint8_t cv[8];
+        for (uint32_t h = s_tile.y * 4096u + threadIdx.x * 4u; h < h_end; h += blockDim.x * 4u) {
+            unsigned long long cnt[4][4]; int nal[4];
+            #pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2) { nal[b2] = 0; cnt[b2][0] = cnt[b2][1] = cnt[b2][2] = cnt[b2][3] = 0; }
+            for (int r0 = 0; r0 < nlist; r0 += 8) {
+                uint32_t cv[8];
                 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const uint32_t r2 = r0 + u; cv[u] = (r2 < no && acc[r2]) ? rows[(size_t)r2 * L + h] : DASH; }
+                for (int u = 0; u < 8; ++u) cv[u] = r0 + u < nlist ? *reinterpret_cast<const uint32_t*>(rows + (size_t)s_rows[r0 + u] * Ls + h) : 0xffffffffu;
                 #pragma unroll
-                for (int u = 0; u < 8; ++u) { const uint8_t cc = cv[u]; if (cc != DASH) { cnt[cc >> 2] += 1ull << (16 * (cc & 3)); ++nal; } }
+                for (int u = 0; u < 8; ++u) {
+                    #pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) { const uint32_t cc = (cv[u] >> (8 * b2)) & 255u; if (cc != DASH) { vote_add(cnt[b2], cc); ++nal[b2]; } }
+                }
             }
-            uint8_t res = best[h];
-            if (!(nal < 2 || __ddiv_rn((double)nal, maxal) < 0.25)) {
-                cnt[best[h] >> 2] += 1ull << (16 * (best[h] & 3));
-                int t0 = -1, t1 = -1, c0 = 0, nd = 0;
+            for (uint32_t r = VOTE_LIST; r < no; ++r) if (acc[r]) {          // more reads than the list holds: never with the default bins
+                const uint32_t v = *reinterpret_cast<const uint32_t*>(rows + (size_t)r * Ls + h);
                 #pragma unroll
-                for (int code = 0; code < 16; ++code) { const int v = (int)((cnt[code >> 2] >> (16 * (code & 3))) & 0xffff); if (!v) continue; ++nd; if (v > t0) { t1 = t0; t0 = v; c0 = code; } else if (v > t1) t1 = v; }
-                if (nd > 1 && t0 - t1 >= 3) res = (uint8_t)c0;
+                for (int b2 = 0; b2 < 4; ++b2) { const uint32_t cc = (v >> (8 * b2)) & 255u; if (cc != DASH) { vote_add(cnt[b2], cc); ++nal[b2]; } }
             }
-            out[h] = (uint8_t)CODE[res];
+            const uint32_t bw = *reinterpret_cast<const uint32_t*>(best + h);
+            #pragma unroll
+            for (int b2 = 0; b2 < 4; ++b2) {
+                if (h + b2 >= h_end) break;
+                const uint32_t bc = (bw >> (8 * b2)) & 255u; uint32_t res = bc;
+                if (!(nal[b2] < 2 || __ddiv_rn((double)nal[b2], maxal) < 0.25)) {
+                    vote_add(cnt[b2], bc);
+                    int t0 = -1, t1 = -1, c0 = 0, nd = 0;
+                    #pragma unroll
+                    for (int code = 0; code < 16; ++code) { const int v = (int)((cnt[b2][code >> 2] >> (16 * (code & 3))) & 0xffff); if (!v) continue; ++nd; if (v > t0) { t1 = t0; t0 = v; c0 = code; } else if (v > t1) t1 = v; }
+                    if (nd > 1 && t0 - t1 >= 3) res = (uint32_t)c0;
+                }
+                out[h + b2] = (uint8_t)CODE[res];
+            }
         }
     }
 }
