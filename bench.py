@@ -226,7 +226,7 @@ def run_b200(args):
     mask = [o == rank for o in owner] if world > 1 else None
     ncores = os.cpu_count() or 1
     old_affinity = bind_near_gpu(local)
-    blk = workload(args, mask, max(1, (len(os.sched_getaffinity(0)) if old_affinity else ncores // world)))
+    blk = workload(args, mask, max(1, min(len(os.sched_getaffinity(0)), ncores // world if world > 1 else ncores)))
     abp_local = aligned_bp_passing(blk, cfg)
     L = binding.lib()
     t0 = time.time()
@@ -328,7 +328,7 @@ def run_b200(args):
     k_ms = kern.get("k_scan", [0.0, 0])[0] / args.steps
     peak, peak_src = measured_peak()
     achieved = alg / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
-    traffic = ncu_traffic()
+    traffic = ncu_traffic() if (args.config == 2 and args.scale == 1.0) else None      # the capture is of this workload at full size
     roof = {"bound": "hbm", "kernel": "extract::k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
             "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
             "traffic": traffic.get("dram_bytes_per_launch") if traffic else None}
