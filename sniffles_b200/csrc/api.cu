@@ -587,7 +587,7 @@ static int run_stage_c(snfb_ctx* ctx) {
         mark(ctx, "consensus_align");
         consensus::k_align<<<148 * 8, consensus::ALIGN_WARPS * 32, 0, ctx->st>>>(c);
         mark(ctx, "consensus_vote");
-        consensus::k_vote<<<148 * 4, 256, 0, ctx->st>>>(c); LAUNCHED(ctx, 3);
+        consensus::k_vote<<<148 * 16, consensus::VOTE_THREADS, 0, ctx->st>>>(c); LAUNCHED(ctx, 3);
         mark(ctx, nullptr);
     }
     CUDA_TRY(cudaGetLastError());

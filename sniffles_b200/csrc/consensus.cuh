@@ -293,7 +293,9 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
                 span += d;
                 long nc = (long)L - 1 - li; if (nc > d) nc = d;                       // positions past the end of the best read never match
                 const int mt = nc > 0 ? match_count(rd + lj + 1, best + li + 1, nc) : 0;
-                if (__ddiv_rn((double)mt, (double)d) >= 0.5) st = match_count(rd + lj, best + cs, fwd_j);
+                // column identity of the copied bases.  Without drift (cs == li, nothing clamped) it is the same sum shifted by one
+                // position, and both end positions are anchor k-mer bases that match by construction: reuse mt
+                if (__ddiv_rn((double)mt, (double)d) >= 0.5) st = (cs == li && fwd_j == d && nc == d) ? mt : match_count(rd + lj, best + cs, fwd_j);
             }
             hcl[m] = st;
         }
@@ -347,7 +349,8 @@ __device__ __forceinline__ void vote_add(unsigned long long (&cnt)[4], uint32_t 
     #pragma unroll
     for (int k = 0; k < 4; ++k) cnt[k] += sel == (uint32_t)k ? inc : 0ull;
 }
-__global__ void __launch_bounds__(256) k_vote(C c) {
+constexpr int VOTE_THREADS = 64;      // most candidates are a few hundred columns: small blocks, many of them
+__global__ void __launch_bounds__(VOTE_THREADS) k_vote(C c) {
     __shared__ uint2 s_tile; __shared__ int s_nacc, s_nlist; __shared__ uint16_t s_rows[VOTE_LIST];
     static const char CODE[17] = "=ACMGRSVTWYHKDBN";
     for (;;) {
