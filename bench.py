@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.05)
 
     def stop(self):
         self._halt.set()
@@ -358,13 +358,13 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, help="BASELINE.json config index (2 = 30x ONT WGS)")
     ap.add_argument("--scale", type=float, default=float(os.environ.get("SNFB_BENCH_SCALE", "1.0")), help="contig length multiplier (1.0 = full GRCh38 lengths)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-gbp", type=float, default=16.0)
+    ap.add_argument("--cpu-sample-gbp", type=float, default=1000.0, help="aligned Gbp of the CPU arm's sample (smallest contigs first); the default takes every contig: one host thread per contig, the reference's own grain")
     ap.add_argument("--no-pin", action="store_true")
     ap.add_argument("--e2e-full-seq", action="store_true", help="e2e: copy the whole seq arena every step instead of the on-demand slices")
     ap.add_argument("--no-cpu", action="store_true")
