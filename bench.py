@@ -162,9 +162,25 @@ def cpu_sample(blk, cfg, ccfg, threads, target_bp=6e9):
     t0 = time.perf_counter()
     res = orc.run(sub, ccfg, 3, nthr)
     dt = time.perf_counter() - t0
+    cpu_sample.last_result = res
     return dict(value=abp / dt / 1e9, unit="Gbp/s", cores=nthr, kind="port",
                 sample=f"oracle/snf_oracle.c (C port of the pure-Python reference) on tasks {sorted(chosen)} = {abp / 1e9:.2f} Gbp aligned, {len(res.cand)} candidates, {dt:.2f}s; "
                        "the reference itself measured 0.0546 Gbp/s/core (BASELINE.md §2)"), abp, dt
+
+
+PARITY_FIELDS = ["task", "svtype", "pos", "end", "svlen", "support", "qual", "precise", "fwd", "rev", "cov_upstream", "cov_start", "cov_center", "cov_end",
+                 "cov_downstream", "sa_count", "bnd_mate_contig", "bnd_mate_pos", "lead_n", "alt_off", "alt_len", "stdev_pos", "stdev_len"]
+
+
+def same_candidates(dev, ora):
+    """bit-for-bit comparison of the device run with the oracle pass the cpu_baseline leg just timed on the same block (checker only)"""
+    if len(dev.cand) != len(ora.cand) or len(dev.alt) != len(ora.alt):
+        return False
+    for f in PARITY_FIELDS:
+        a, b = dev.cand[f], ora.cand[f]
+        if not (((a == b) | ((a != a) & (b != b))).all()):
+            return False
+    return bool((np.asarray(dev.alt) == np.asarray(ora.alt)).all())
 
 
 def run_reference(args):
@@ -323,7 +339,7 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (stage A lead extraction) ----
     ctx.load(blk)
-    full = ctx.run(want_leads=True, want_cands=False, want_seqs=False, copy=False)
+    full = ctx.run(want_leads=True, want_cands=True, want_seqs=True, copy=False)       # also the run the full-size parity check compares with the oracle
     alg, alg_read = algorithmic_bytes_stage_a(blk, len(full.leads), full.n_pass)
     k_ms = kern.get("k_scan", [0.0, 0])[0] / args.steps
     peak, peak_src = measured_peak()
@@ -347,6 +363,8 @@ def run_b200(args):
         if world == 1 and not args.no_cpu:
             info, _, _ = cpu_sample(blk, cfg, ccfg, ncores, target_bp=args.cpu_sample_gbp * 1e9)
             out["cpu_baseline"] = info
+            if args.cpu_sample_gbp * 1e9 >= abp_total:        # the oracle saw the whole block: compare it with the device run, candidate by candidate
+                out["parity_full_size"] = {"candidates": int(len(full.cand)), "alt_bytes": int(len(full.alt)), "identical_to_oracle": same_candidates(full, cpu_sample.last_result)}
         print(json.dumps(out))
     for a in pinned:
         L.snfb_unpin_host(C.c_void_p(a.ctypes.data))
