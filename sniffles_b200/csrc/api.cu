@@ -44,7 +44,7 @@ struct HostBuf {
 constexpr int MAX_TIMINGS = 64;
 
 struct snfb_ctx {
-    int device = 0; cudaStream_t st = nullptr, st2 = nullptr, st_copy = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_copy = nullptr; bool want_cand_prefetch = false, cand_prefetched = false; std::string err;
+    int device = 0; cudaStream_t st = nullptr, st_copy = nullptr; cudaEvent_t ev_copy = nullptr; bool want_cand_prefetch = false, cand_prefetched = false; std::string err;
     snfb_config cfg{}; bool have_cfg = false;
     // records
     bool loaded = false, on_device = false, seq_on_demand = false; const uint8_t* h_seq = nullptr;
@@ -52,7 +52,7 @@ struct snfb_ctx {
     const snfb_rec* d_rec = nullptr; const uint16_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
     DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp, b_mask, b_mask_off, b_mask_task; uint32_t n_mask = 0;
     // stage A outputs
-    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_ev_cnt, b_ev_slot, b_sa_list, b_scanrec, b_clip, b_rec_big, b_sa_seg;
+    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_sa_list, b_scanrec, b_clip, b_rec_big, b_sa_seg;
     HostBuf h_c16, h_rec16;        // BAM32 host input converted to CIGAR16 before the upload
     unsigned long long lead_cap = 0;
     DevCounters h_ctr{};
@@ -107,9 +107,8 @@ int snfb_ctx_create(int device, snfb_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return 3;
     snfb_ctx* ctx = new snfb_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st2, cudaStreamNonBlocking) != cudaSuccess
-        || cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 4; }
-    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 4; }
+    cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventCreate(&ctx->ev[i]);
     *out = ctx; return 0;
 }
@@ -119,7 +118,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->st);
     DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_mask, &ctx->b_mask_off, &ctx->b_mask_task, &ctx->b_ctr, &ctx->b_leads, &ctx->b_rec_pos, &ctx->b_rec_end,
-        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_ev_cnt, &ctx->b_ev_slot, &ctx->b_sa_list, &ctx->b_scanrec, &ctx->b_clip, &ctx->b_rec_big, &ctx->b_sa_seg,
+        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_sa_list, &ctx->b_scanrec, &ctx->b_clip, &ctx->b_rec_big, &ctx->b_sa_seg,
         &ctx->b_key0, &ctx->b_val0, &ctx->b_key1, &ctx->b_val1, &ctx->b_flag, &ctx->b_scan, &ctx->b_hist, &ctx->b_scan_tmp, &ctx->b_bin_start, &ctx->b_bin_nl, &ctx->b_bin_nlong, &ctx->b_bin_kept,
         &ctx->b_bin_hap, &ctx->b_kl_off, &ctx->b_kll_off, &ctx->b_kb_idx, &ctx->b_kl, &ctx->b_kll, &ctx->b_kb_bin, &ctx->b_kb_lead_off, &ctx->b_kb_lead_n, &ctx->b_kb_long_off, &ctx->b_kb_long_n,
         &ctx->b_kb_seed, &ctx->b_kb_chain, &ctx->b_kb_repeat, &ctx->b_seg_start, &ctx->b_c_next, &ctx->b_c_last, &ctx->b_c_sd, &ctx->b_c_mean, &ctx->b_c_rep, &ctx->b_seg_sd_last, &ctx->b_seg_maxsd,
@@ -132,7 +131,7 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt, &ctx->h_seq_req, &ctx->h_seq_arena, &ctx->h_c16, &ctx->h_rec16 };
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventDestroy(ctx->ev[i]);
-    cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join); cudaEventDestroy(ctx->ev_copy); cudaStreamDestroy(ctx->st_copy); cudaStreamDestroy(ctx->st2); cudaStreamDestroy(ctx->st);
+    cudaEventDestroy(ctx->ev_copy); cudaStreamDestroy(ctx->st_copy); cudaStreamDestroy(ctx->st);
     delete ctx;
 }
 

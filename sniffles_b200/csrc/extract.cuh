@@ -14,8 +14,6 @@
 
 namespace extract {
 
-constexpr int THREADS = 256;
-constexpr int WARPS = THREADS / 32;
 constexpr int MAXSEG = 40;     // primary + supplementary segments per read held in shared memory
 
 // rec_flags bits
