@@ -40,6 +40,8 @@ FIXTURES = {
                             tr_frac=0.6, clip_prob=0.3, phased_frac=1.0), ["--no-qc"]),
     "auto_support_qcnm": (dict(seed=78, contig_len=[200_000, 180_000], coverage=40.0, len_mean=6000.0, len_sd=1500.0, tech="ont",
                                sv_spacing=4000.0, lowmapq_prob=0.3, phased_frac=0.0), ["--minsupport", "auto", "--qc-nm"]),
+    "phased_phase": (dict(seed=79, contig_len=[260_000, 140_000], coverage=30.0, len_mean=12000.0, len_sd=3000.0, tech="ont", sv_spacing=5000.0,
+                          phased_frac=0.8, tr_frac=0.1, clip_prob=0.2), ["--phase"]),
 }
 
 
@@ -53,8 +55,10 @@ def block_digest(blk):
     return h.hexdigest()
 
 
-def make_synthetic():
+def make_synthetic(only=None):
     for name, (kw, args) in FIXTURES.items():
+        if only and name not in only:
+            continue
         kw2 = dict(kw)
         blk = synth.generate(kw2.pop("seed"), kw2.pop("contig_len"), kw2.pop("coverage"), **kw2)
         if name in MASKS:
@@ -108,6 +112,9 @@ def make_config_dump():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:
+        make_synthetic(set(sys.argv[1:]))
+        sys.exit(0)
     make_config_dump()
     make_synthetic()
     make_bam_vectors()

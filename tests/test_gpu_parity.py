@@ -59,7 +59,7 @@ def test_random_shapes(seed):
     _run(blk, *rnd.choice([(), ("--mosaic",), ("--no-qc",), ("--qc-nm",), ("--cluster-merge-pos", "50")]))
 
 
-@pytest.mark.parametrize("name", ["c1_ont_1mb", "c2_ont_wgs_small", "c3_hifi_mosaic", "c5_ins_heavy", "tr_repeat_noqc", "auto_support_qcnm"])
+@pytest.mark.parametrize("name", ["c1_ont_1mb", "c2_ont_wgs_small", "c3_hifi_mosaic", "c5_ins_heavy", "tr_repeat_noqc", "auto_support_qcnm", "phased_phase"])
 def test_device_against_reference_golden(name):
     """CUDA path -> host epilogue vs what the unmodified reference produced (tests/golden/*.json):
     lead table, candidates, FILTER / GT / ALT of the finalized calls."""
