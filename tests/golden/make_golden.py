@@ -42,6 +42,13 @@ FIXTURES = {
                                sv_spacing=4000.0, lowmapq_prob=0.3, phased_frac=0.0), ["--minsupport", "auto", "--qc-nm"]),
     "phased_phase": (dict(seed=79, contig_len=[260_000, 140_000], coverage=30.0, len_mean=12000.0, len_sd=3000.0, tech="ont", sv_spacing=5000.0,
                           phased_frac=0.8, tr_frac=0.1, clip_prob=0.2), ["--phase"]),
+    # the next three pin the oracle only (the GPU golden test lists its fixtures explicitly)
+    "filters_binsize": (dict(seed=80, contig_len=[220_000], coverage=35.0, len_mean=8000.0, len_sd=2500.0, tech="ont", sv_spacing=3000.0,
+                             lowmapq_prob=0.25, clip_prob=0.3), ["--mapq", "30", "--min-alignment-length", "3000", "--cluster-binsize", "50", "--cluster-r", "1.5"]),
+    "long_ins_minsv": (dict(seed=81, contig_len=[240_000], coverage=25.0, len_mean=25000.0, len_sd=5000.0, len_max=80000, tech="ont", sv_spacing=6000.0,
+                            sv_min=30, sv_max=9000, clip_prob=0.4), ["--minsvlen", "30", "--long-ins-length", "1500", "--minsupport", "3"]),
+    "hifi_strict": (dict(seed=82, contig_len=[200_000, 120_000], coverage=45.0, len_mean=16000.0, len_sd=2000.0, len_max=40000, tech="hifi", sv_spacing=4000.0,
+                         phased_frac=0.5, tr_frac=0.3), ["--cluster-merge-pos", "80", "--cluster-merge-len", "0.2", "--no-consensus"]),
 }
 
 
