@@ -163,19 +163,44 @@ static inline int carries(const snfb_synth_site* st, int read_hap, uint64_t h) {
     return st->hap == 0 || st->hap == read_hap;
 }
 
-static void gen_read(const model_t* m, local_t* L, int c, int64_t idx, int64_t nreads, int src) {
-    const snfb_synth_params* p = m->p;
-    rng_t r = { mix64(p->seed ^ mix64(((uint64_t)(uint32_t)c << 40) ^ (uint64_t)idx)) };
+/* the first draws of a read: its length and start (shared by gen_read and the ownership pre-check) */
+static inline void read_span(const snfb_synth_params* p, rng_t* r, int c, int64_t idx, int64_t nreads, int64_t* start_out, int64_t* len_out) {
     int64_t clen = p->contig_len[c];
     double len;
-    if (p->len_model == 1) { double sg = p->len_sd / 1000.0; len = exp(log(p->len_mean) - 0.5 * sg * sg + sg * rnorm(&r)); }
-    else len = p->len_mean + p->len_sd * rnorm(&r);
+    if (p->len_model == 1) { double sg = p->len_sd / 1000.0; len = exp(log(p->len_mean) - 0.5 * sg * sg + sg * rnorm(r)); }
+    else len = p->len_mean + p->len_sd * rnorm(r);
     int64_t Lr = (int64_t)len;
     if (Lr < p->len_min) Lr = p->len_min; if (Lr > p->len_max) Lr = p->len_max;
     if (Lr > clen - 2) Lr = clen - 2;
     int64_t span = clen - Lr; if (span < 1) span = 1;
-    int64_t start = (int64_t)(((double)idx + runif(&r)) * (double)span / (double)nreads);
+    int64_t start = (int64_t)(((double)idx + runif(r)) * (double)span / (double)nreads);
     if (start > clen - Lr - 1) start = clen - Lr - 1; if (start < 0) start = 0;
+    *start_out = start; *len_out = Lr;
+}
+
+/* Sharded generation (contig_mask): a read that starts on a contig this shard does not own still matters when it can
+ * split at a BND site whose mate lies on an owned contig (its second record lands there).  Superset test: the read's span
+ * holds such a site.  Everything else of an unowned contig is never generated. */
+static int read_may_reach_owned(const model_t* m, int c, int64_t idx, int64_t nreads) {
+    const snfb_synth_params* p = m->p;
+    rng_t r = { mix64(p->seed ^ mix64(((uint64_t)(uint32_t)c << 40) ^ (uint64_t)idx)) };
+    int64_t start, Lr; read_span(p, &r, c, idx, nreads, &start, &Lr);
+    int64_t s0 = m->site_first[c], s1 = m->site_first[c + 1];
+    int64_t lo = s0, hi = s1;
+    while (lo < hi) { int64_t mid = (lo + hi) / 2; if (m->sites[mid].pos <= start + 290) lo = mid + 1; else hi = mid; }
+    for (int64_t si = lo; si < s1; ++si) {
+        const snfb_synth_site* st = &m->sites[si];
+        if (st->pos >= start + Lr + 100000) break;     /* in-read deletions extend `end`: a generous bound keeps this a superset */
+        if (st->svtype == SNFB_BND && p->contig_mask[st->mate_contig]) return 1;
+    }
+    return 0;
+}
+
+static void gen_read(const model_t* m, local_t* L, int c, int64_t idx, int64_t nreads, int src) {
+    const snfb_synth_params* p = m->p;
+    rng_t r = { mix64(p->seed ^ mix64(((uint64_t)(uint32_t)c << 40) ^ (uint64_t)idx)) };
+    int64_t clen = p->contig_len[c];
+    int64_t start, Lr; read_span(p, &r, c, idx, nreads, &start, &Lr);
     int rev = (int)(rnext(&r) & 1);
     int mapq = runif(&r) < p->lowmapq_prob ? (int)rrange(&r, 0, 59) : 60;
     int secondary = runif(&r) < p->secondary_prob;
@@ -405,13 +430,16 @@ snfb_synth_block* snfb_synth_generate(const snfb_synth_params* p) {
     enum { UNIT = 4096 };
     int64_t* nreads_c = (int64_t*)calloc((size_t)nc + 1, sizeof(int64_t));
     int64_t nunits = 0;
+    uint8_t* gen_c = (uint8_t*)calloc((size_t)nc + 1, 1);      /* 1 = owned (every read), 2 = unowned but some BND site reaches an owned contig */
     for (int c = 0; c < nc; ++c) {
-        if (p->contig_mask && !p->contig_mask[c]) continue;
         int64_t nr = (int64_t)(p->coverage * (double)p->contig_len[c] / p->len_mean + 0.5); if (nr < 1) nr = 1;
-        nreads_c[c] = nr; nunits += (nr + UNIT - 1) / UNIT;
+        nreads_c[c] = nr;
+        if (!p->contig_mask || p->contig_mask[c]) gen_c[c] = 1;
+        else for (int64_t si = site_first[c]; si < site_first[c + 1]; ++si) if (sites[si].svtype == SNFB_BND && p->contig_mask[sites[si].mate_contig]) { gen_c[c] = 2; break; }
+        if (gen_c[c]) nunits += (nr + UNIT - 1) / UNIT;
     }
     int32_t* unit_c = (int32_t*)malloc((size_t)(nunits + 1) * sizeof(int32_t)); int64_t* unit_i0 = (int64_t*)malloc((size_t)(nunits + 1) * sizeof(int64_t));
-    { int64_t u = 0; for (int c = 0; c < nc; ++c) for (int64_t i0 = 0; i0 < nreads_c[c]; i0 += UNIT) { unit_c[u] = c; unit_i0[u] = i0; ++u; } }
+    { int64_t u = 0; for (int c = 0; c < nc; ++c) if (gen_c[c]) for (int64_t i0 = 0; i0 < nreads_c[c]; i0 += UNIT) { unit_c[u] = c; unit_i0[u] = i0; ++u; } }
     local_t* loc = (local_t*)calloc((size_t)nunits + 1, sizeof *loc);
 #ifdef _OPENMP
     if (p->threads > 0) omp_set_num_threads(p->threads);
@@ -419,7 +447,10 @@ snfb_synth_block* snfb_synth_generate(const snfb_synth_params* p) {
 #pragma omp parallel for schedule(dynamic, 1)
     for (int64_t u = 0; u < nunits; ++u) {
         const int c = unit_c[u]; const int64_t i0 = unit_i0[u], i1 = i0 + UNIT < nreads_c[c] ? i0 + UNIT : nreads_c[c];
-        for (int64_t i = i0; i < i1; ++i) gen_read(&m, &loc[u], c, i, nreads_c[c], (int)u);
+        for (int64_t i = i0; i < i1; ++i) {
+            if (gen_c[c] == 2 && !read_may_reach_owned(&m, c, i, nreads_c[c])) continue;
+            gen_read(&m, &loc[u], c, i, nreads_c[c], (int)u);
+        }
     }
     /* global order */
     uint64_t nrec = 0; for (int64_t c = 0; c < nunits; ++c) nrec += loc[c].recs.n / sizeof(grec_t);
@@ -497,7 +528,7 @@ snfb_synth_block* snfb_synth_generate(const snfb_synth_params* p) {
     R->n_task = (uint32_t)nc; R->n_contig = (uint32_t)nc; R->n_tr = (uint32_t)(trbuf.n / 8); R->on_device = 0;
     R->task = blk->task; R->contig = blk->contig; R->tr = blk->tr;
     for (int64_t c = 0; c < nunits; ++c) { free(loc[c].recs.p); free(loc[c].cigar.p); free(loc[c].var.p); free(loc[c].ins.p); }
-    free(loc); free(nreads_c); free(unit_c); free(unit_i0); free(ord); free(coff); free(voff); free(soff); free(site_first); free(tr_first); free(trbuf.p);
+    free(loc); free(gen_c); free(nreads_c); free(unit_c); free(unit_i0); free(ord); free(coff); free(voff); free(soff); free(site_first); free(tr_first); free(trbuf.p);
     return blk;
 }
 
