@@ -59,7 +59,8 @@ def test_random_shapes(seed):
     _run(blk, *rnd.choice([(), ("--mosaic",), ("--no-qc",), ("--qc-nm",), ("--cluster-merge-pos", "50")]))
 
 
-@pytest.mark.parametrize("name", ["c1_ont_1mb", "c2_ont_wgs_small", "c3_hifi_mosaic", "c5_ins_heavy", "tr_repeat_noqc", "auto_support_qcnm", "phased_phase"])
+@pytest.mark.parametrize("name", ["c1_ont_1mb", "c2_ont_wgs_small", "c3_hifi_mosaic", "c5_ins_heavy", "tr_repeat_noqc", "auto_support_qcnm", "phased_phase",
+                                  "filters_binsize", "long_ins_minsv", "hifi_strict"])
 def test_device_against_reference_golden(name):
     """CUDA path -> host epilogue vs what the unmodified reference produced (tests/golden/*.json):
     lead table, candidates, FILTER / GT / ALT of the finalized calls."""
@@ -100,3 +101,28 @@ def test_seq_on_demand_gives_identical_alts():
         ctx.close()
     devcheck.assert_same(orc.run(blk, cfg, 3, 4), got)
     assert len(got.alt) > 10000
+
+
+@pytest.mark.parametrize("prefix", ["hg008", "hg002"])
+def test_reference_bnd_vectors_on_device(prefix):
+    """The reference's own vectors (src/tests/test_bnd_leads.py: 8 tuples + 9 "no lead" on hg008.bam / hg002.bam) through the CUDA path."""
+    import json
+    import os
+    from test_oracle_golden import GOLDEN, _bam_block, bnd_leads_by_record
+    with open(os.path.join(GOLDEN, "hg008_bnd.json")) as f:
+        exp = [e for e in json.load(f)["records"] if e["file"].startswith(prefix)]
+    blk = _bam_block(prefix)
+    cfg = abi.Config.from_sniffles(sconfig.default_config("--dev-no-qc"))
+    ctx = binding.Context(0)
+    try:
+        ctx.set_config(cfg)
+        ctx.load(blk, cigar16=False)
+        res = ctx.extract_leads()
+    finally:
+        ctx.close()
+    got = bnd_leads_by_record(blk, res.leads)
+    assert len(exp) == len(blk.rec)
+    for i, e in enumerate(exp):
+        assert got.get(i) == e["lead"], (i, e, got.get(i))
+    if prefix == "hg008":
+        assert sum(e["lead"] is not None for e in exp) == 8
