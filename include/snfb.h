@@ -17,6 +17,10 @@
  *   snfb_consensus         <- postprocessing.annotate_sv INS branch (postprocessing.py:33-66)
  *                             + consensus.novel_from_reads (consensus.py:280-394);
  *                             call site Task.finalize_candidates parallel.py:145
+ *   snfb_coverage_bins     <- SNFile.annotate_block_coverages' reshape-mean of lead_provider.coverage
+ *                             (snf.py:248-267)
+ *   snfb_allgather_candidates <- the parent collecting every worker's finished task results before VCF
+ *                             emission (sniffles:544-547, parallel.py:270-271), as one NCCL all-gather
  *
  * Conventions: all functions return 0 on success, non-zero on error (message via
  * snfb_last_error).  No exceptions, no Python or torch types.  Views are library-owned
@@ -34,7 +38,7 @@
 extern "C" {
 #endif
 
-#define SNFB_ABI_VERSION 2
+#define SNFB_ABI_VERSION 3
 
 /* SV types in the reference's ALL_TYPES order (sv.py:31-33); the emission order of
  * candidates follows this order (parallel.py:106). */
@@ -276,7 +280,7 @@ typedef struct snfb_cand_view {
     const uint64_t*  rnames;        /* distinct qname hashes per candidate, CSR below     */
     const uint32_t*  rnames_off;    /* [n_cand+1]                                          */
     const double*    task_coverage_mean; /* [n_task] coverage_average_total (postprocessing.py:130) */
-    uint64_t unverified_breaks;     /* chain splits whose independence check failed (must be 0) */
+    uint64_t unverified_breaks;     /* chain cuts whose independence check failed in the final run (0: a failed cut is redone with whole chains) */
 } snfb_cand_view;
 
 typedef struct snfb_seq_view {
@@ -287,7 +291,7 @@ typedef struct snfb_seq_view {
 typedef struct snfb_ctx snfb_ctx;
 
 int         snfb_version(void);
-/* sizeof of the ABI structs, for binding self-checks: 0 rec, 1 task, 2 contig, 3 records, 4 config, 5 lead, 6 cand */
+/* sizeof of the ABI structs, for binding self-checks: 0 rec, 1 task, 2 contig, 3 records, 4 config, 5 lead, 6 cand, 7 gather_view */
 size_t      snfb_sizeof(int which);
 uint64_t    snfb_hash_name(const char* s, size_t n);
 int         snfb_ctx_create(int device, snfb_ctx** out);
@@ -298,8 +302,11 @@ int         snfb_load_records(snfb_ctx* ctx, const snfb_records* block);
 int         snfb_extract_leads(snfb_ctx* ctx, snfb_lead_view* out);   /* out may be NULL: stay on device */
 int         snfb_cluster_call(snfb_ctx* ctx, snfb_cand_view* out);
 int         snfb_consensus(snfb_ctx* ctx, snfb_seq_view* out);
-/* all three stages back to back with no host synchronisation in between; the views
- * (any may be NULL) are filled after one final synchronisation */
+/* all three stages back to back.  Sizes live in device counters and every buffer has a capacity kept in the ctx, so the
+ * stream is never drained between stages: the host reads the counters once on a side stream (while the consensus kernels
+ * run) to size the device -> host copies, and once at the end.  A run whose capacities were too small (the first run on
+ * a ctx, or a block unlike the previous one) is repeated with capacities that fit; snfb_rerun_count counts those.
+ * The views (any may be NULL) are filled after the final synchronisation. */
 int         snfb_run(snfb_ctx* ctx, snfb_lead_view* leads, snfb_cand_view* cands, snfb_seq_view* seqs);
 /* device-time accounting of the last run: per-kernel milliseconds from CUDA events on
  * the ctx stream; names[i] is a static string.  Returns the number of entries. */
@@ -310,6 +317,35 @@ int         snfb_device_candidates(snfb_ctx* ctx, void** dptr, uint64_t* n_cand)
 int         snfb_device_alt(snfb_ctx* ctx, void** dptr, uint64_t* n_bytes);
 /* number of kernels launched by the library on this ctx since it was created */
 uint64_t    snfb_launch_count(snfb_ctx* ctx);
+/* number of times a run was repeated because a buffer capacity was too small or a chain cut had to be undone */
+uint64_t    snfb_rerun_count(snfb_ctx* ctx);
+/* mean coverage of consecutive `binsize`-base bins over the whole contig of one task, as the SNF writer stores it
+ * (snf.py:248-267: the coverage vector zero-padded to a multiple of binsize, row means; the writer rounds them).
+ * *out is a library-owned buffer of *n_bins doubles, valid until the next call on the ctx.  Needs snfb_extract_leads
+ * (or snfb_run) first. */
+int         snfb_coverage_bins(snfb_ctx* ctx, uint32_t task, int binsize, const double** out, uint64_t* n_bins);
+
+/* ---- multi-GPU: one process per GPU, contigs sharded over the ranks, ONE all-gather of the per-rank candidate buffers ----
+ * snfb_nccl_unique_id fills the 128 bytes of an ncclUniqueId on one rank; the host hands them to every rank (any transport),
+ * then every rank calls snfb_comm_init.  snfb_allgather_candidates runs after snfb_run on every rank: it packs the rank's
+ * candidate records, ALT arena, read names (and, with SNFB_GATHER_LEADS, the candidates' leads) into one buffer, all-gathers
+ * the buffers over NCCL on the ctx stream, and returns the concatenation in rank order with lead_off / long_off / alt_off and
+ * the rnames offsets rebased into the merged arrays (so a candidate of any rank indexes the merged arenas).  Ranks own
+ * disjoint tasks; the caller orders by task id for emission (sniffles:544-547).  The view is library-owned pinned host
+ * memory (dev_* are the same arrays in device memory), valid until the next call. */
+#define SNFB_GATHER_LEADS 1u
+#define SNFB_GATHER_DEVICE_ONLY 2u     /* leave the result in device memory (no device -> host copy; host pointers are NULL) */
+typedef struct snfb_gather_view {
+    uint64_t n_cand;        const snfb_cand* cand;
+    uint64_t n_alt_bytes;   const uint8_t*  alt;
+    uint64_t n_rnames;      const uint64_t* rnames;     const uint32_t* rnames_off;   /* [n_cand + 1] */
+    uint64_t n_cand_leads;  const snfb_lead* cand_leads;                              /* 0 / NULL without SNFB_GATHER_LEADS */
+    const uint64_t* rank_n_cand;                                                      /* [nranks] */
+    const void* dev_buffer; uint64_t dev_bytes_per_rank;                              /* the gathered device buffer (nranks slots) */
+} snfb_gather_view;
+int         snfb_nccl_unique_id(void* out128);
+int         snfb_comm_init(snfb_ctx* ctx, const void* unique_id128, int rank, int nranks);
+int         snfb_allgather_candidates(snfb_ctx* ctx, uint32_t flags, snfb_gather_view* out);
 /* BAM CIGAR words -> CIGAR16 (host code, OpenMP; no GPU needed).  rec_out receives copies of rec_in with cigar_off / n_cigar
  * rewritten for the 16-bit arena.  Call with out16 == NULL to get the number of 16-bit words the arena needs (a multiple
  * of 8); returns that number, or UINT64_MAX when a record holds an op the path does not know (B) or out_cap is too small. */

@@ -120,6 +120,16 @@ class SeqView(C.Structure):
     _fields_ = [("n_alt_bytes", C.c_uint64), ("alt", C.c_void_p)]
 
 
+GATHER_LEADS, GATHER_DEVICE_ONLY = 1, 2
+
+
+class GatherView(C.Structure):
+    _fields_ = [("n_cand", C.c_uint64), ("cand", C.c_void_p), ("n_alt_bytes", C.c_uint64), ("alt", C.c_void_p),
+                ("n_rnames", C.c_uint64), ("rnames", C.c_void_p), ("rnames_off", C.c_void_p),
+                ("n_cand_leads", C.c_uint64), ("cand_leads", C.c_void_p), ("rank_n_cand", C.c_void_p),
+                ("dev_buffer", C.c_void_p), ("dev_bytes_per_rank", C.c_uint64)]
+
+
 def view(ptr, dtype, n):
     """numpy array over library-owned memory (no copy); empty array for n == 0 / NULL."""
     dtype = np.dtype(dtype)

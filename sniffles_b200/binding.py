@@ -15,7 +15,8 @@ _LIB = None
 EXPORTS = ["snfb_version", "snfb_sizeof", "snfb_hash_name", "snfb_ctx_create", "snfb_ctx_destroy", "snfb_last_error", "snfb_set_config",
            "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
            "snfb_last_timings", "snfb_device_candidates", "snfb_device_alt", "snfb_launch_count",
-           "snfb_pin_host", "snfb_unpin_host", "snfb_pack_cigar16"]
+           "snfb_pin_host", "snfb_unpin_host", "snfb_pack_cigar16", "snfb_rerun_count", "snfb_coverage_bins",
+           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates"]
 
 
 def lib():
@@ -47,6 +48,12 @@ def lib():
         L.snfb_launch_count.argtypes = [C.c_void_p]
         L.snfb_pin_host.argtypes = [C.c_void_p, C.c_size_t]
         L.snfb_unpin_host.argtypes = [C.c_void_p]
+        L.snfb_rerun_count.restype = C.c_uint64
+        L.snfb_rerun_count.argtypes = [C.c_void_p]
+        L.snfb_coverage_bins.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+        L.snfb_nccl_unique_id.argtypes = [C.c_void_p]
+        L.snfb_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.snfb_allgather_candidates.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GatherView)]
         L.snfb_pack_cigar16.restype = C.c_uint64
         L.snfb_pack_cigar16.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         _LIB = L
@@ -95,6 +102,22 @@ class Result:
         if c["alt_off"] < 0:
             return None
         return self.alt[int(c["alt_off"]):int(c["alt_off"]) + int(c["alt_len"])].tobytes().decode()
+
+
+class GatheredResult(Result):
+    """Concatenation of every rank's candidates in rank order, offsets rebased into the merged arenas."""
+    n_cand = n_alt_bytes = n_rnames = n_cand_leads = dev_bytes_per_rank = 0
+
+    def in_emission_order(self):
+        """indices that order the merged candidates by task id (sniffles:544-547), each rank's own order kept inside a task"""
+        return np.argsort(self.cand["task"], kind="stable")
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    if lib().snfb_nccl_unique_id(buf) != 0:
+        raise SnfbError("snfb_nccl_unique_id: NCCL is not available")
+    return buf.raw
 
 
 class Context:
@@ -194,6 +217,38 @@ class Context:
 
     def launch_count(self):
         return int(self._lib.snfb_launch_count(self._h))
+
+    def rerun_count(self):
+        return int(self._lib.snfb_rerun_count(self._h))
+
+    def coverage_bins(self, task: int, binsize: int) -> np.ndarray:
+        """Mean coverage per `binsize` bases over the task's contig (snf.py:248-267); the SNF writer rounds them."""
+        p = C.c_void_p()
+        n = C.c_uint64()
+        self._check(self._lib.snfb_coverage_bins(self._h, int(task), int(binsize), C.byref(p), C.byref(n)), "snfb_coverage_bins")
+        return abi.view(p.value, "<f8", n.value).copy()
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        """Join the NCCL communicator of the per-GPU processes (the 128-byte id comes from `nccl_unique_id()` on one rank)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self._lib.snfb_comm_init(self._h, buf, int(rank), int(nranks)), "snfb_comm_init")
+
+    def allgather_candidates(self, with_leads=False, device_only=False, copy=True):
+        """ONE NCCL all-gather of every rank's candidate records, ALT arena and read names -> GatheredResult."""
+        gv = abi.GatherView()
+        flags = (abi.GATHER_LEADS if with_leads else 0) | (abi.GATHER_DEVICE_ONLY if device_only else 0)
+        self._check(self._lib.snfb_allgather_candidates(self._h, flags, C.byref(gv)), "snfb_allgather_candidates")
+        g = GatheredResult()
+        g.n_cand, g.n_alt_bytes, g.n_rnames, g.n_cand_leads = int(gv.n_cand), int(gv.n_alt_bytes), int(gv.n_rnames), int(gv.n_cand_leads)
+        g.dev_bytes_per_rank = int(gv.dev_bytes_per_rank)
+        if not device_only:
+            cp = (lambda a: a.copy()) if copy else (lambda a: a)
+            g.cand = cp(abi.view(gv.cand, abi.CAND_DTYPE, gv.n_cand))
+            g.alt = cp(abi.view(gv.alt, "u1", gv.n_alt_bytes))
+            g.rnames = cp(abi.view(gv.rnames, "<u8", gv.n_rnames))
+            g.rn_off = cp(abi.view(gv.rnames_off, "<u4", gv.n_cand + 1))
+            g.cand_leads = cp(abi.view(gv.cand_leads, abi.LEAD_DTYPE, gv.n_cand_leads)) if with_leads else np.zeros(0, abi.LEAD_DTYPE)
+        return g
 
     def device_alt(self):
         p = C.c_void_p()

@@ -1,11 +1,20 @@
 // api.cu — C ABI of libsnfb200.so (include/snfb.h): context, memory, stage drivers.
 // The product path has no CPU implementation: every stage below launches CUDA kernels.
+//
+// Run model.  Every buffer of the pipeline has a capacity kept in the context.  A run enqueues stage A -> B -> C on the
+// context's stream WITHOUT host synchronisation: sizes live in device counters, kernels are launched for the capacities
+// and bound their loops and stores by the device-side counts.  The host looks at the counters twice: once on the copy
+// stream after stage B (while the consensus kernels run) to size the device -> host copies, and once at the end.  If a
+// capacity was too small (first run on a context, or a block unlike the previous one) the run is repeated with
+// capacities that fit — the counters always report what was needed.
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
+#include <dlfcn.h>
 #include <omp.h>
 
 #include "common.cuh"
@@ -21,7 +30,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; return 1; }
+        if (cudaMalloc(&p, want) != cudaSuccess) { p = nullptr; cudaGetLastError(); return 1; }
         cap = want; return 0;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
@@ -34,46 +43,78 @@ struct HostBuf {
         if (p) cudaFreeHost(p);
         p = nullptr; cap = 0;
         size_t want = bytes + bytes / 8 + 256;
-        if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; return 1; }
+        if (cudaMallocHost(&p, want) != cudaSuccess) { p = nullptr; cudaGetLastError(); return 1; }
         cap = want; return 0;
     }
     void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
     template <class T> T* as() { return reinterpret_cast<T*>(p); }
 };
+// one allocation carved into 256-byte aligned arrays: a measuring pass, then an assigning pass over the same list
+struct Carver {
+    uint8_t* base = nullptr; size_t off = 0;
+    template <class T> T* take(size_t n) { const size_t o = off; off += (n * sizeof(T) + 255) & ~(size_t)255; return base ? reinterpret_cast<T*>(base + o) : nullptr; }
+};
 
 constexpr int MAX_TIMINGS = 64;
 
+// ---- NCCL, resolved at run time (the library links no collective library: a process that never gathers needs none) ----
+struct Id128 { char b[128]; };      // ncclUniqueId is passed by value: 128 bytes
+struct NcclApi {
+    void* h = nullptr; bool tried = false;
+    int (*GetUniqueId)(void*) = nullptr; int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr; int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr; const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static bool nccl_load(std::string* err) {
+    if (g_nccl.tried) { if (!g_nccl.AllGather && err) *err = "NCCL is not available in this process"; return g_nccl.AllGather != nullptr; }
+    g_nccl.tried = true;
+    // a process that already carries NCCL (torch) must use that copy: two NCCL instances do not share bootstrap state
+    void* h = dlopen(nullptr, RTLD_NOW | RTLD_GLOBAL);
+    if (!h || !dlsym(h, "ncclAllGather")) { h = nullptr; const char* names[] = { "libnccl.so.2", "libnccl.so" }; for (const char* n : names) { h = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (h) break; } }
+    if (!h) { if (err) *err = "libnccl.so.2 not found"; return false; }
+    g_nccl.h = h;
+    g_nccl.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather) { g_nccl.AllGather = nullptr; if (err) *err = "NCCL symbols missing"; return false; }
+    return true;
+}
+
+struct Caps { unsigned long long lead = 0, cand = 0, cand_lead = 0, rn = 0, alt = 0, scr16 = 0, item = 0, tile = 0, req = 0, req16 = 0; };
+
 struct snfb_ctx {
-    int device = 0; cudaStream_t st = nullptr, st_copy = nullptr; cudaEvent_t ev_copy = nullptr; bool want_cand_prefetch = false, cand_prefetched = false; std::string err;
+    int device = 0; cudaStream_t st = nullptr, st_copy = nullptr, st_side = nullptr; cudaEvent_t ev_b = nullptr, ev_mid = nullptr, ev_fork = nullptr, ev_join = nullptr; std::string err;
     snfb_config cfg{}; bool have_cfg = false;
     // records
     bool loaded = false, on_device = false, seq_on_demand = false; const uint8_t* h_seq = nullptr;
-    uint64_t n_rec = 0, n_cigar = 0, n_var = 0, n_seq = 0; uint32_t n_task = 0, n_contig = 0, n_tr = 0;
+    uint64_t n_rec = 0, n_cigar = 0, n_var = 0, n_seq = 0; uint32_t n_task = 0, n_contig = 0, n_tr = 0, n_mask = 0;
     const snfb_rec* d_rec = nullptr; const uint16_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
-    DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp, b_mask, b_mask_off, b_mask_task; uint32_t n_mask = 0;
-    // stage A outputs
-    DevBuf b_ctr, b_leads, b_rec_pos, b_rec_end, b_rec_flags, b_rec_nm, b_rec_nlead, b_rec_lead_off, b_task_first, b_task_last, b_task_reads, b_task_cov, b_task_span, b_task_nm, b_nm_part, b_nm_cnt, b_ev, b_sa_list, b_scanrec, b_clip, b_rec_big, b_sa_seg;
+    DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp, b_mask, b_mask_off, b_mask_task;
     HostBuf h_c16, h_rec16;        // BAM32 host input converted to CIGAR16 before the upload
-    unsigned long long lead_cap = 0;
-    DevCounters h_ctr{};
-    // stage B
-    DevBuf b_key0, b_val0, b_key1, b_val1, b_flag, b_scan, b_hist, b_scan_tmp;
-    DevBuf b_bin_start, b_bin_nl, b_bin_nlong, b_bin_kept, b_bin_hap, b_kl_off, b_kll_off, b_kb_idx, b_kl, b_kll;
-    DevBuf b_kb_bin, b_kb_lead_off, b_kb_lead_n, b_kb_long_off, b_kb_long_n, b_kb_seed, b_kb_chain, b_kb_repeat;
-    DevBuf b_seg_start, b_c_next, b_c_last, b_c_sd, b_c_mean, b_c_rep, b_seg_sd_last, b_seg_maxsd, b_cl_first, b_cl_last, b_cl_rep;
-    DevBuf b_s_hi, b_s_lo, b_s_a, b_s_b, b_s_c, b_s_d, b_s_e, b_ord, b_ml_slot, b_ml_svlen, b_ml_seqlen, b_ml_plo, b_ml_pn, b_ml_has, b_subl;
-    DevBuf b_sub_cnt, b_sub_off, b_t_lo, b_t_n, b_t_bin, b_sub_cluster, b_sub_lo, b_sub_n, b_sub_bin;
-    DevBuf b_cand_tmp, b_cand_valid, b_cand_id, b_cand_nlead, b_cand_lead_off, b_cand_nrn, b_cand_rn_off, b_cand, b_cand_leads, b_cand_lead_ml, b_rnames, b_rn_off_out;
-    unsigned long long n_bound = 0, cand_cap = 0, cand_lead_cap = 0, rn_cap = 0;
-    bool sorted_in_first = true, stage_a_done = false, stage_b_done = false;
-    // stage C
-    DevBuf b_plan_best, b_plan_nother, b_plan_otot, b_alt_len, b_scr_len, b_alt_off, b_scr_off, b_alt, b_scr, b_sorted_leads, b_work_big, b_work_small, b_work_ctr, b_seq_req, b_arena_off, b_seq_arena, b_items_big, b_items_small, b_tiles;
+    std::vector<snfb_task> tasks;
+    // capacities and the three arenas carved by them
+    Caps cap; bool force_no_cuts = false;
+    DevBuf b_ctr, arena_r, arena_l, arena_c;            // counters; per-record arrays; per-lead arrays (stages A + B); stage C
+    uint64_t arena_r_for = 0; Caps arena_l_for, arena_c_for; uint32_t arena_r_tasks = 0;
+    // per-record (arena_r)
+    int32_t* rec_pos; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead; uint32_t* rec_lead_off; uint32_t* sa_list; extract::RecScan* scanrec; extract::RecClip* clip; int32_t* rec_big;
+    uint32_t* task_first; uint32_t* task_last; uint32_t* task_reads; unsigned long long* task_cov; int32_t* task_span; double* task_nm; double* nm_part; unsigned* nm_cnt; extract::Seg* sa_seg; uint32_t* scan_tmp_r;
+    // per-lead (arena_l): stage A leads + the whole of stage B
+    snfb_lead* leads; extract::Event* ev_buf; snfb_lead* sorted_leads; uint32_t* radix_hist;
+    cluster::B B{};
+    // stage C (arena_c)
+    consensus::C Cc{}; consensus::SeqReq* seq_req; uint32_t* arena_off; uint8_t* seq_arena;
     HostBuf h_seq_req, h_seq_arena; uint64_t seq_h2d_bytes = 0;
+    bool stage_a_done = false, stage_b_done = false, stage_c_done = false;
     // host staging
-    HostBuf h_leads, h_task_reads, h_task_nm, h_rec_nm, h_cand, h_cand_leads, h_rnames, h_rn_off, h_task_cov, h_alt;
-    std::vector<double> task_cov_mean; std::vector<snfb_task> tasks;
+    HostBuf h_ctr_buf; DevCounters* h_mid = nullptr; DevCounters* h_fin = nullptr; uint32_t* h_work = nullptr;
+    HostBuf h_leads, h_task_reads, h_task_nm, h_rec_nm, h_cand, h_cand_leads, h_rnames, h_rn_off, h_task_cov, h_task_cov_raw, h_alt, h_cov_bins;
+    // gather
+    void* comm = nullptr; int rank = 0, nranks = 1; DevBuf b_gsend, b_grecv; HostBuf h_gather; unsigned long long gather_cap = 0;
     // timings
-    cudaEvent_t ev[MAX_TIMINGS + 1]; const char* ev_name[MAX_TIMINGS + 1]; uint64_t ev_bytes[MAX_TIMINGS + 1]; int n_ev = 0; int n_ev_load = 0; uint64_t launches = 0;
+    cudaEvent_t ev[MAX_TIMINGS + 1]; const char* ev_name[MAX_TIMINGS + 1]; uint64_t ev_bytes[MAX_TIMINGS + 1]; int n_ev = 0; int n_ev_load = 0; uint64_t launches = 0; uint64_t reruns = 0;
 };
 
 static void ctx_fail(snfb_ctx* ctx, const char* what, const char* msg) { ctx->err = std::string(what) + ": " + msg; }
@@ -86,13 +127,92 @@ static void mark(snfb_ctx* ctx, const char* name, uint64_t bytes = 0) {
     cudaEventRecord(ctx->ev[ctx->n_ev], ctx->st);
     ctx->ev_name[ctx->n_ev] = name; ctx->ev_bytes[ctx->n_ev] = bytes; ++ctx->n_ev;
 }
+#define LAUNCHED(ctx, k) ((ctx)->launches += (k))
+static int grid_for(unsigned long long n, int threads) { unsigned long long g = (n + threads - 1) / threads; if (g < 1) g = 1; if (g > 148ull * 32) g = 148ull * 32; return (int)g; }
+static int bits_for(uint32_t n) { int b = 0; while ((1ull << b) < n) ++b; return b; }
+
+__global__ void k_gather_leads(const snfb_lead* __restrict__ leads, const uint32_t* __restrict__ sval, snfb_lead* __restrict__ out, const unsigned long long* n_ptr, unsigned long long cap) {
+    const unsigned long long n = *n_ptr < cap ? *n_ptr : cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) out[i] = leads[sval[i]];
+}
+// mean coverage per bin of `binsize` bases over the whole contig (snf.py:248-267): sum over the bin's positions of the per-base
+// depth / binsize, from the per-record (start, end) arrays: one thread per record adds its overlap with every bin it touches
+__global__ void k_cov_bins(const int32_t* __restrict__ rec_pos, const int32_t* __restrict__ rec_end, const uint8_t* __restrict__ rec_flags, uint32_t lo, uint32_t hi,
+                           int binsize, long long contig_len, long long nbins, unsigned long long* __restrict__ acc) {
+    for (unsigned long long i = lo + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < hi; i += (unsigned long long)gridDim.x * blockDim.x) {
+        if (!(rec_flags[i] & extract::RF_PASS)) continue;
+        long long a = rec_pos[i], e = rec_end[i]; if (a < 0) a = 0; if (e > contig_len) e = contig_len;      // numpy slice clipping (leadprov.py:510)
+        if (e <= a) continue;
+        for (long long bb = a / binsize; bb <= (e - 1) / binsize && bb < nbins; ++bb) {
+            const long long s0 = bb * binsize, s1 = s0 + binsize;
+            const long long o0 = a > s0 ? a : s0, o1 = e < s1 ? e : s1;
+            if (o1 > o0) atomicAdd(&acc[bb], (unsigned long long)(o1 - o0));
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------ all-gather of the candidate buffers
+// slot of one rank: [GatherHdr][cand][alt][rnames][rn_off][cand_leads], every section 16-byte aligned
+struct GatherHdr { unsigned long long n_cand, n_alt, n_rn, n_leads, need_bytes, overflow, pad0, pad1; };
+__host__ __device__ inline void gather_offsets(const GatherHdr& h, unsigned long long off[6]) {
+    auto al = [](unsigned long long x) { return (x + 15ull) & ~15ull; };
+    off[0] = sizeof(GatherHdr); off[1] = al(off[0] + h.n_cand * sizeof(snfb_cand)); off[2] = al(off[1] + h.n_alt); off[3] = al(off[2] + 8 * h.n_rn);
+    off[4] = al(off[3] + 4 * h.n_cand); off[5] = al(off[4] + h.n_leads * sizeof(snfb_lead));
+}
+__device__ inline void copy16(uint8_t* dst, const uint8_t* src, unsigned long long nbytes) {      // both 16-byte aligned, whole grid cooperates
+    const unsigned long long n16 = (nbytes + 15) >> 4;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16; i += (unsigned long long)gridDim.x * blockDim.x)
+        reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+}
+__global__ void k_gather_pack(const DevCounters* ctr, const snfb_cand* cand, const uint8_t* alt, const uint64_t* rnames, const uint32_t* rn_off, const snfb_lead* leads, int with_leads,
+                              uint8_t* slot, unsigned long long cap) {
+    GatherHdr h; h.n_cand = ctr->n_cand; h.n_alt = ctr->n_alt_bytes; h.n_rn = ctr->n_rnames; h.n_leads = with_leads ? ctr->n_cand_leads : 0ull; h.pad0 = h.pad1 = 0;
+    unsigned long long off[6]; gather_offsets(h, off);
+    h.need_bytes = off[5]; h.overflow = off[5] > cap ? 1ull : 0ull;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<GatherHdr*>(slot) = h;
+    if (h.overflow) return;
+    copy16(slot + off[0], reinterpret_cast<const uint8_t*>(cand), h.n_cand * sizeof(snfb_cand));
+    copy16(slot + off[1], alt, h.n_alt);
+    copy16(slot + off[2], reinterpret_cast<const uint8_t*>(rnames), 8 * h.n_rn);
+    copy16(slot + off[3], reinterpret_cast<const uint8_t*>(rn_off), 4 * h.n_cand);
+    if (with_leads) copy16(slot + off[4], reinterpret_cast<const uint8_t*>(leads), h.n_leads * sizeof(snfb_lead));
+}
+// gathered slots -> merged arrays with the offsets of every rank rebased; merged layout: [nranks headers][cand][alt][rnames][rn_off (+1)][leads]
+__global__ void k_gather_merge(const uint8_t* recv, unsigned long long cap, int nranks, int with_leads, uint8_t* out, unsigned long long out_cap, unsigned long long* out_layout /* [8] */) {
+    GatherHdr tot{}; bool ovf = false;
+    for (int r = 0; r < nranks; ++r) { const GatherHdr* h = reinterpret_cast<const GatherHdr*>(recv + (size_t)r * cap); tot.n_cand += h->n_cand; tot.n_alt += h->n_alt; tot.n_rn += h->n_rn; tot.n_leads += h->n_leads; ovf = ovf || h->overflow; }
+    auto al = [](unsigned long long x) { return (x + 255ull) & ~255ull; };
+    const unsigned long long o_hdr = 0, o_cand = al((unsigned long long)nranks * sizeof(GatherHdr)), o_alt = al(o_cand + tot.n_cand * sizeof(snfb_cand)), o_rn = al(o_alt + tot.n_alt), o_ro = al(o_rn + 8 * tot.n_rn),
+                             o_leads = al(o_ro + 4 * (tot.n_cand + 1)), o_end = al(o_leads + tot.n_leads * sizeof(snfb_lead));
+    const bool fits = !ovf && o_end <= out_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { out_layout[0] = o_cand; out_layout[1] = o_alt; out_layout[2] = o_rn; out_layout[3] = o_ro; out_layout[4] = o_leads; out_layout[5] = o_end; out_layout[6] = fits ? 0 : 1; out_layout[7] = tot.n_cand; }
+    if (!fits) return;
+    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x, nthr = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long b_cand = 0, b_alt = 0, b_rn = 0, b_leads = 0;
+    for (int r = 0; r < nranks; ++r) {
+        const uint8_t* slot = recv + (size_t)r * cap; const GatherHdr h = *reinterpret_cast<const GatherHdr*>(slot);
+        unsigned long long off[6]; gather_offsets(h, off);
+        if (tid == 0) reinterpret_cast<GatherHdr*>(out + o_hdr)[r] = h;
+        const snfb_cand* sc = reinterpret_cast<const snfb_cand*>(slot + off[0]); snfb_cand* dc = reinterpret_cast<snfb_cand*>(out + o_cand) + b_cand;
+        for (unsigned long long i = tid; i < h.n_cand; i += nthr) { snfb_cand c = sc[i]; if (c.alt_off >= 0) c.alt_off += (int)b_alt; if (with_leads) { c.lead_off += (int)b_leads; c.long_off += (int)b_leads; } dc[i] = c; }
+        for (unsigned long long i = tid; i < h.n_alt; i += nthr) (out + o_alt + b_alt)[i] = (slot + off[1])[i];
+        const uint64_t* sr = reinterpret_cast<const uint64_t*>(slot + off[2]); uint64_t* dr = reinterpret_cast<uint64_t*>(out + o_rn) + b_rn;
+        for (unsigned long long i = tid; i < h.n_rn; i += nthr) dr[i] = sr[i];
+        const uint32_t* so = reinterpret_cast<const uint32_t*>(slot + off[3]); uint32_t* dof = reinterpret_cast<uint32_t*>(out + o_ro) + b_cand;
+        for (unsigned long long i = tid; i < h.n_cand; i += nthr) dof[i] = so[i] + (uint32_t)b_rn;
+        if (with_leads) { const uint4* sl = reinterpret_cast<const uint4*>(slot + off[4]); uint4* dl = reinterpret_cast<uint4*>(out + o_leads) + 4 * b_leads; for (unsigned long long i = tid; i < 4 * h.n_leads; i += nthr) dl[i] = sl[i]; }
+        b_cand += h.n_cand; b_alt += h.n_alt; b_rn += h.n_rn; b_leads += h.n_leads;
+    }
+    if (tid == 0) reinterpret_cast<uint32_t*>(out + o_ro)[tot.n_cand] = (uint32_t)tot.n_rn;
+}
 
 extern "C" {
 
 int snfb_version(void) { return SNFB_ABI_VERSION; }
 size_t snfb_sizeof(int which) {
     switch (which) { case 0: return sizeof(snfb_rec); case 1: return sizeof(snfb_task); case 2: return sizeof(snfb_contig); case 3: return sizeof(snfb_records);
-                     case 4: return sizeof(snfb_config); case 5: return sizeof(snfb_lead); case 6: return sizeof(snfb_cand); default: return 0; }
+                     case 4: return sizeof(snfb_config); case 5: return sizeof(snfb_lead); case 6: return sizeof(snfb_cand); case 7: return sizeof(snfb_gather_view); default: return 0; }
 }
 
 uint64_t snfb_hash_name(const char* s, size_t n) {
@@ -107,31 +227,33 @@ int snfb_ctx_create(int device, snfb_ctx** out) {
     if (cudaSetDevice(device) != cudaSuccess) return 3;
     snfb_ctx* ctx = new snfb_ctx();
     ctx->device = device;
-    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 4; }
-    cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
+    if (cudaStreamCreateWithFlags(&ctx->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->st_copy, cudaStreamNonBlocking) != cudaSuccess
+        || cudaStreamCreateWithFlags(&ctx->st_side, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return 4; }
+    cudaEventCreateWithFlags(&ctx->ev_b, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_mid, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming); cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventCreate(&ctx->ev[i]);
+    if (ctx->h_ctr_buf.ensure(2 * sizeof(DevCounters) + 256) || ctx->b_ctr.ensure(sizeof(DevCounters) + 64)) { delete ctx; return 5; }
+    ctx->h_mid = ctx->h_ctr_buf.as<DevCounters>(); ctx->h_fin = ctx->h_mid + 1; ctx->h_work = reinterpret_cast<uint32_t*>(ctx->h_fin + 1);
+    memset(ctx->h_ctr_buf.p, 0, 2 * sizeof(DevCounters) + 256);
+    cudaFuncSetAttribute(cluster::k_cluster_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster::CW_SMEM);
+    cudaFuncSetAttribute(cluster::k_cluster_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster::CB_SMEM);
     *out = ctx; return 0;
 }
 
 void snfb_ctx_destroy(snfb_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->st);
-    DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_mask, &ctx->b_mask_off, &ctx->b_mask_task, &ctx->b_ctr, &ctx->b_leads, &ctx->b_rec_pos, &ctx->b_rec_end,
-        &ctx->b_rec_flags, &ctx->b_rec_nm, &ctx->b_rec_nlead, &ctx->b_rec_lead_off, &ctx->b_task_first, &ctx->b_task_last, &ctx->b_task_reads, &ctx->b_task_cov, &ctx->b_task_span, &ctx->b_task_nm, &ctx->b_nm_part, &ctx->b_nm_cnt, &ctx->b_ev, &ctx->b_sa_list, &ctx->b_scanrec, &ctx->b_clip, &ctx->b_rec_big, &ctx->b_sa_seg,
-        &ctx->b_key0, &ctx->b_val0, &ctx->b_key1, &ctx->b_val1, &ctx->b_flag, &ctx->b_scan, &ctx->b_hist, &ctx->b_scan_tmp, &ctx->b_bin_start, &ctx->b_bin_nl, &ctx->b_bin_nlong, &ctx->b_bin_kept,
-        &ctx->b_bin_hap, &ctx->b_kl_off, &ctx->b_kll_off, &ctx->b_kb_idx, &ctx->b_kl, &ctx->b_kll, &ctx->b_kb_bin, &ctx->b_kb_lead_off, &ctx->b_kb_lead_n, &ctx->b_kb_long_off, &ctx->b_kb_long_n,
-        &ctx->b_kb_seed, &ctx->b_kb_chain, &ctx->b_kb_repeat, &ctx->b_seg_start, &ctx->b_c_next, &ctx->b_c_last, &ctx->b_c_sd, &ctx->b_c_mean, &ctx->b_c_rep, &ctx->b_seg_sd_last, &ctx->b_seg_maxsd,
-        &ctx->b_cl_first, &ctx->b_cl_last, &ctx->b_cl_rep, &ctx->b_s_hi, &ctx->b_s_lo, &ctx->b_s_a, &ctx->b_s_b, &ctx->b_s_c, &ctx->b_s_d, &ctx->b_s_e, &ctx->b_ord, &ctx->b_ml_slot, &ctx->b_ml_svlen,
-        &ctx->b_ml_seqlen, &ctx->b_ml_plo, &ctx->b_ml_pn, &ctx->b_ml_has, &ctx->b_subl, &ctx->b_sub_cnt, &ctx->b_sub_off, &ctx->b_t_lo, &ctx->b_t_n, &ctx->b_t_bin, &ctx->b_sub_cluster, &ctx->b_sub_lo,
-        &ctx->b_sub_n, &ctx->b_sub_bin, &ctx->b_cand_tmp, &ctx->b_cand_valid, &ctx->b_cand_id, &ctx->b_cand_nlead, &ctx->b_cand_lead_off, &ctx->b_cand_nrn, &ctx->b_cand_rn_off, &ctx->b_cand,
-        &ctx->b_cand_leads, &ctx->b_cand_lead_ml, &ctx->b_rnames, &ctx->b_rn_off_out, &ctx->b_plan_best, &ctx->b_plan_nother, &ctx->b_plan_otot, &ctx->b_alt_len, &ctx->b_scr_len, &ctx->b_alt_off, &ctx->b_scr_off,
-        &ctx->b_alt, &ctx->b_scr, &ctx->b_sorted_leads, &ctx->b_work_big, &ctx->b_work_small, &ctx->b_work_ctr, &ctx->b_seq_req, &ctx->b_arena_off, &ctx->b_seq_arena, &ctx->b_items_big, &ctx->b_items_small, &ctx->b_tiles };
+    cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_copy); cudaStreamSynchronize(ctx->st_side);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_mask, &ctx->b_mask_off, &ctx->b_mask_task,
+                       &ctx->b_ctr, &ctx->arena_r, &ctx->arena_l, &ctx->arena_c, &ctx->b_gsend, &ctx->b_grecv };
     for (DevBuf* b : bufs) b->release();
-    HostBuf* hb[] = { &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads, &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_alt, &ctx->h_seq_req, &ctx->h_seq_arena, &ctx->h_c16, &ctx->h_rec16 };
+    HostBuf* hb[] = { &ctx->h_c16, &ctx->h_rec16, &ctx->h_seq_req, &ctx->h_seq_arena, &ctx->h_ctr_buf, &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads,
+                      &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_task_cov_raw, &ctx->h_alt, &ctx->h_cov_bins, &ctx->h_gather };
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventDestroy(ctx->ev[i]);
-    cudaEventDestroy(ctx->ev_copy); cudaStreamDestroy(ctx->st_copy); cudaStreamDestroy(ctx->st);
+    cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_mid); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
+    cudaStreamDestroy(ctx->st_side); cudaStreamDestroy(ctx->st_copy); cudaStreamDestroy(ctx->st);
     delete ctx;
 }
 
@@ -141,7 +263,7 @@ int snfb_set_config(snfb_ctx* ctx, const snfb_config* cfg) {
     if (!ctx || !cfg) return 1;
     if (cfg->consensus_kmer_len != 6) return fail(ctx, "consensus_kmer_len must be 6 (the reference fixes it, config.py:550)");
     if (cfg->cluster_binsize <= 0 || cfg->cluster_resplit_binsize <= 0 || cfg->coverage_binsize <= 0) return fail(ctx, "bin sizes must be positive");
-    ctx->cfg = *cfg; ctx->have_cfg = true; return 0;
+    ctx->cfg = *cfg; ctx->have_cfg = true; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false; return 0;
 }
 
 // ---- BAM CIGAR words -> CIGAR16 (include/snfb.h).  Host code; the only place the 32-bit form is read. ----
@@ -192,18 +314,40 @@ uint64_t snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_
     return total;
 }
 
+// thread per record: every offset of the block must stay inside its arena / table (a malformed block fails instead of reading out of bounds)
+__global__ void k_validate(const snfb_rec* __restrict__ rec, uint32_t n_rec, uint32_t n_task, uint64_t n_cigar, uint64_t n_var, uint64_t n_seq, int check_seq, DevCounters* ctr) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i >= n_rec) return;
+    const snfb_rec r = rec[i];
+    bool bad = r.task < 0 || (uint32_t)r.task >= n_task || (r.cigar_off & 7) || r.cigar_off + (uint64_t)r.n_cigar > n_cigar || r.var_off + (uint64_t)r.l_qname + r.sa_len > n_var || r.l_seq < 0;
+    if (check_seq && r.l_seq >= 0 && r.seq_off + (uint64_t)((r.l_seq + 1) / 2) > n_seq) bad = true;
+    if (bad) atomicAdd(&ctr->bad_records, 1ULL);
+}
+
 int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     if (!ctx || !R) return 1;
     cudaSetDevice(ctx->device);
-    ctx->loaded = false; ctx->stage_a_done = ctx->stage_b_done = false;
+    ctx->loaded = false; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false;
     if (R->n_task == 0 || R->n_task > 65535) return fail(ctx, "n_task must be in 1..65535");
     if (R->n_rec > 0xfffffff0ull) return fail(ctx, "too many records in one block");
+    if (!R->task || (R->n_rec && (!R->rec || !R->cigar))) return fail(ctx, "null table in the record block");
+    // host-side checks of the small tables
+    for (uint32_t t = 0; t < R->n_task; ++t) {
+        const snfb_task& k = R->task[t];
+        if (k.tr_n < 0 || k.tr_off < 0 || (uint64_t)k.tr_off + (uint64_t)k.tr_n > R->n_tr) return fail(ctx, "task table: tandem-repeat range outside tr[]");
+        if (R->n_contig && (k.contig < 0 || (uint32_t)k.contig >= R->n_contig)) return fail(ctx, "task table: contig index out of range");
+        if (k.contig_len < 0 || k.start > k.end) return fail(ctx, "task table: bad region");
+        if ((long long)k.contig_len >= ((long long)1 << 26) * (long long)(ctx->have_cfg ? ctx->cfg.cluster_binsize : 100)) return fail(ctx, "contig too long for the bin field of the sort key (contig_len / cluster_binsize must stay below 2^26)");
+    }
+    if (R->n_mask && R->mask && R->mask_task_off) {
+        for (uint32_t t = 0; t < R->n_task; ++t) if (R->mask_task_off[t] > R->mask_task_off[t + 1] || R->mask_task_off[t + 1] > R->n_mask) return fail(ctx, "mask_task_off must be non-decreasing and end at n_mask");
+    }
     ctx->n_rec = R->n_rec; ctx->n_cigar = R->n_cigar; ctx->n_var = R->n_var; ctx->n_seq = R->n_seq;
     ctx->n_task = R->n_task; ctx->n_contig = R->n_contig; ctx->n_tr = R->n_tr; ctx->on_device = R->on_device == SNFB_MEM_DEVICE; ctx->seq_on_demand = R->on_device == SNFB_MEM_HOST_SEQ_ON_DEMAND; ctx->h_seq = ctx->seq_on_demand ? R->seq : nullptr;
     ctx->n_ev = 0;
     const snfb_rec* src_rec = R->rec; const uint16_t* src_cigar = reinterpret_cast<const uint16_t*>(R->cigar); uint64_t n_words = R->n_cigar;
     if (R->cigar_fmt == SNFB_CIGAR_BAM32) {
         if (R->on_device == SNFB_MEM_DEVICE) return fail(ctx, "device-resident records must carry CIGAR16 (convert with snfb_pack_cigar16)");
+        for (uint64_t i = 0; i < R->n_rec; ++i) if (R->rec[i].cigar_off + (uint64_t)R->rec[i].n_cigar > R->n_cigar) return fail(ctx, "a record's CIGAR lies outside the cigar arena");
         // host conversion: the kernels only read CIGAR16
         const uint64_t need = snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), nullptr, nullptr, 0);
         if (need == UINT64_MAX) return fail(ctx, "a CIGAR holds an operation the path does not know");
@@ -253,391 +397,393 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     ctx->loaded = true; return 0;
 }
 
-#define LAUNCHED(ctx, k) ((ctx)->launches += (k))
-static int grid_for(unsigned long long n, int threads) { unsigned long long g = (n + threads - 1) / threads; if (g < 1) g = 1; if (g > 148ull * 64) g = 148ull * 64; return (int)g; }
+}  // extern "C"
 
-static int fetch_counters(snfb_ctx* ctx) {
-    CUDA_TRY(cudaMemcpyAsync(&ctx->h_ctr, ctx->b_ctr.p, sizeof(DevCounters), cudaMemcpyDeviceToHost, ctx->st));
-    CUDA_TRY(cudaStreamSynchronize(ctx->st));
+// ------------------------------------------------------------------------------------------------ arenas
+static void carve_r(snfb_ctx* ctx, Carver& c) {
+    const size_t n = ctx->n_rec + 1, nt = ctx->n_task;
+    ctx->rec_pos = c.take<int32_t>(n); ctx->rec_end = c.take<int32_t>(n); ctx->rec_flags = c.take<uint8_t>(n); ctx->rec_nm = c.take<double>(n); ctx->rec_nlead = c.take<uint32_t>(n); ctx->rec_lead_off = c.take<uint32_t>(n);
+    ctx->sa_list = c.take<uint32_t>(n); ctx->scanrec = c.take<extract::RecScan>(n); ctx->clip = c.take<extract::RecClip>(n); ctx->rec_big = c.take<int32_t>(n);
+    ctx->task_first = c.take<uint32_t>(nt); ctx->task_last = c.take<uint32_t>(nt); ctx->task_reads = c.take<uint32_t>(nt); ctx->task_cov = c.take<unsigned long long>(nt); ctx->task_span = c.take<int32_t>(nt); ctx->task_nm = c.take<double>(nt);
+    const size_t cpt = (ctx->n_rec + extract::NM_CHUNK - 1) / extract::NM_CHUNK + 1;
+    ctx->nm_part = c.take<double>(cpt * nt + 1); ctx->nm_cnt = c.take<unsigned>(cpt * nt + 1);
+    ctx->sa_seg = c.take<extract::Seg>((size_t)extract::MAXSEG * extract::SA_THREADS * extract::SA_BLOCKS);
+    ctx->scan_tmp_r = c.take<uint32_t>(prims::scan_tmp_elems(n) + 16);
+}
+static void carve_l(snfb_ctx* ctx, Carver& c) {
+    const size_t n = (size_t)ctx->cap.lead + 8; cluster::B& b = ctx->B;
+    ctx->leads = c.take<snfb_lead>(n); ctx->ev_buf = c.take<extract::Event>(n); ctx->sorted_leads = c.take<snfb_lead>(n);
+    b.key0 = c.take<uint64_t>(n); b.val0 = c.take<uint32_t>(n); b.key1 = c.take<uint64_t>(n); b.val1 = c.take<uint32_t>(n); b.flag = c.take<uint32_t>(n); b.scan = c.take<uint32_t>(n);
+    b.scan_tmp = c.take<uint32_t>(prims::scan_tmp_elems(std::max<unsigned long long>(n, prims::radix_hist_elems(n))) + 16);
+    ctx->radix_hist = c.take<uint32_t>(prims::radix_hist_elems(n) + 16);
+    b.bin_start = c.take<uint32_t>(n); b.bin_nl = c.take<uint32_t>(n); b.bin_nlong = c.take<uint32_t>(n); b.bin_kept = c.take<uint32_t>(n); b.bin_hap = c.take<uint32_t>(3 * n);
+    b.kl_off = c.take<uint32_t>(n); b.kll_off = c.take<uint32_t>(n); b.kb_idx = c.take<uint32_t>(n); b.kl = c.take<uint32_t>(n); b.kll = c.take<uint32_t>(n); b.kleads = c.take<snfb_lead>(n); b.klleads = c.take<snfb_lead>(n);
+    b.kb_bin = c.take<uint32_t>(n); b.kb_lead_off = c.take<uint32_t>(n); b.kb_lead_n = c.take<uint32_t>(n); b.kb_long_off = c.take<uint32_t>(n); b.kb_long_n = c.take<uint32_t>(n); b.kb_seed = c.take<int32_t>(n); b.kb_chain = c.take<uint32_t>(n); b.kb_repeat = c.take<uint8_t>(n);
+    b.seg_start = c.take<uint32_t>(n); b.c_next = c.take<uint32_t>(n); b.c_last = c.take<uint32_t>(n); b.c_sd = c.take<double>(n); b.c_mean = c.take<double>(n); b.c_rep = c.take<uint8_t>(n);
+    b.seg_sd_last = c.take<double>(n); b.seg_maxsd_first = c.take<double>(n); b.cl_first = c.take<uint32_t>(n); b.cl_last = c.take<uint32_t>(n); b.cl_rep = c.take<uint8_t>(n); b.big_list = c.take<uint32_t>(n);
+    b.g_khi = c.take<uint64_t>(n); b.g_klo = c.take<uint64_t>(n); b.g_u32 = c.take<uint32_t>((size_t)cluster::coop::NU32 * n);
+    b.ord = c.take<uint32_t>(n); b.st_leads = c.take<snfb_lead>(n); b.st_plo = c.take<uint32_t>(n); b.st_pn = c.take<uint32_t>(n); b.st_rn = c.take<uint64_t>(n); b.cand_tmp = c.take<snfb_cand>(n); b.sub_valid = c.take<uint8_t>(n);
+    b.cl_nsub = c.take<uint32_t>(n); b.cl_nvalid = c.take<uint32_t>(n); b.cl_nlead = c.take<uint32_t>(n); b.cl_nrn = c.take<uint32_t>(n); b.cl_cand_base = c.take<uint32_t>(n); b.cl_lead_base = c.take<uint32_t>(n); b.cl_rn_base = c.take<uint32_t>(n);
+    ctx->arena_off = c.take<uint32_t>(n);
+}
+static void carve_c(snfb_ctx* ctx, Carver& c) {
+    const Caps& k = ctx->cap; cluster::B& b = ctx->B; consensus::C& cc = ctx->Cc;
+    b.cand = c.take<snfb_cand>(k.cand + 1); b.cand_leads = c.take<snfb_lead>(k.cand_lead + 1); b.out_plo = c.take<uint32_t>(k.cand_lead + 1); b.out_pn = c.take<uint32_t>(k.cand_lead + 1);
+    b.rnames = c.take<uint64_t>(k.rn + 1); b.rn_off_out = c.take<uint32_t>(k.cand + 2);
+    cc.plan_best = c.take<uint32_t>(k.cand + 1); cc.plan_nother = c.take<uint32_t>(k.cand + 1); cc.plan_otot = c.take<uint32_t>(k.cand + 1); cc.alt_len = c.take<uint32_t>(k.cand + 1); cc.scr_len = c.take<uint32_t>(k.cand + 1);
+    cc.alt_off = c.take<uint32_t>(k.cand + 1); cc.scr_off = c.take<uint32_t>(k.cand + 1); cc.work_big = c.take<uint32_t>(k.cand + 1); cc.work_small = c.take<uint32_t>(k.cand + 1); cc.work_ctr = c.take<uint32_t>(64);
+    cc.items_big = c.take<consensus::C::Item>(k.item + 1); cc.items_small = c.take<consensus::C::Item>(k.item + 1); cc.tiles = c.take<uint2>(k.tile + 1);
+    cc.alt = c.take<uint8_t>(k.alt + 64); cc.scr = c.take<uint8_t>(k.scr16 * 16 + 64);
+    ctx->seq_req = c.take<consensus::SeqReq>(k.req + 1); ctx->seq_arena = c.take<uint8_t>(k.req16 * 16 + 64);
+}
+static int ensure_arenas(snfb_ctx* ctx) {
+    if (ctx->arena_r_for != ctx->n_rec + 1 || ctx->arena_r_tasks != ctx->n_task || !ctx->arena_r.p) {
+        Carver m; carve_r(ctx, m);
+        if (ctx->arena_r.ensure(m.off + 256)) return fail(ctx, "out of device memory (per-record arrays)");
+        Carver a; a.base = ctx->arena_r.as<uint8_t>(); carve_r(ctx, a);
+        ctx->arena_r_for = ctx->n_rec + 1; ctx->arena_r_tasks = ctx->n_task;
+    }
+    if (ctx->arena_l_for.lead != ctx->cap.lead || !ctx->arena_l.p) {
+        Carver m; carve_l(ctx, m);
+        if (ctx->arena_l.ensure(m.off + 256)) return fail(ctx, "out of device memory (per-lead arrays)");
+        Carver a; a.base = ctx->arena_l.as<uint8_t>(); carve_l(ctx, a);
+        ctx->arena_l_for = ctx->cap;
+    }
+    const Caps& k = ctx->cap; const Caps& f = ctx->arena_c_for;
+    if (!ctx->arena_c.p || f.cand != k.cand || f.cand_lead != k.cand_lead || f.rn != k.rn || f.alt != k.alt || f.scr16 != k.scr16 || f.item != k.item || f.tile != k.tile || f.req != k.req || f.req16 != k.req16) {
+        Carver m; carve_c(ctx, m);
+        if (ctx->arena_c.ensure(m.off + 256)) return fail(ctx, "out of device memory (candidate / consensus arrays)");
+        Carver a; a.base = ctx->arena_c.as<uint8_t>(); carve_c(ctx, a);
+        ctx->arena_c_for = ctx->cap;
+    }
     return 0;
 }
 
-static int ensure_stage_b(snfb_ctx* ctx, unsigned long long nb) {
-    // every stage-B array is bounded by the number of leads
-    const size_t n = (size_t)nb + 8;
-    int bad = 0;
-    bad |= ctx->b_key0.ensure(8 * n) | ctx->b_val0.ensure(4 * n) | ctx->b_key1.ensure(8 * n) | ctx->b_val1.ensure(4 * n) | ctx->b_flag.ensure(4 * n) | ctx->b_scan.ensure(4 * n);
-    bad |= ctx->b_hist.ensure(4 * prims::radix_hist_elems(nb)) | ctx->b_scan_tmp.ensure(4 * (prims::scan_tmp_elems(std::max<unsigned long long>(nb, (unsigned long long)prims::radix_hist_elems(nb))) + 16));
-    bad |= ctx->b_bin_start.ensure(4 * n) | ctx->b_bin_nl.ensure(4 * n) | ctx->b_bin_nlong.ensure(4 * n) | ctx->b_bin_kept.ensure(4 * n) | ctx->b_bin_hap.ensure(12 * n) | ctx->b_kl_off.ensure(4 * n) | ctx->b_kll_off.ensure(4 * n) | ctx->b_kb_idx.ensure(4 * n);
-    bad |= ctx->b_kl.ensure(4 * n) | ctx->b_kll.ensure(4 * n) | ctx->b_kb_bin.ensure(4 * n) | ctx->b_kb_lead_off.ensure(4 * n) | ctx->b_kb_lead_n.ensure(4 * n) | ctx->b_kb_long_off.ensure(4 * n) | ctx->b_kb_long_n.ensure(4 * n);
-    bad |= ctx->b_kb_seed.ensure(4 * n) | ctx->b_kb_chain.ensure(4 * n) | ctx->b_kb_repeat.ensure(n) | ctx->b_seg_start.ensure(4 * n) | ctx->b_c_next.ensure(4 * n) | ctx->b_c_last.ensure(4 * n) | ctx->b_c_sd.ensure(8 * n) | ctx->b_c_mean.ensure(8 * n);
-    bad |= ctx->b_c_rep.ensure(n) | ctx->b_seg_sd_last.ensure(8 * n) | ctx->b_seg_maxsd.ensure(8 * n) | ctx->b_cl_first.ensure(4 * n) | ctx->b_cl_last.ensure(4 * n) | ctx->b_cl_rep.ensure(n);
-    bad |= ctx->b_s_hi.ensure(8 * n) | ctx->b_s_lo.ensure(8 * n) | ctx->b_s_a.ensure(4 * n) | ctx->b_s_b.ensure(4 * n) | ctx->b_s_c.ensure(4 * n) | ctx->b_s_d.ensure(4 * n) | ctx->b_s_e.ensure(4 * n) | ctx->b_ord.ensure(4 * n);
-    bad |= ctx->b_ml_slot.ensure(4 * n) | ctx->b_ml_svlen.ensure(4 * n) | ctx->b_ml_seqlen.ensure(4 * n) | ctx->b_ml_plo.ensure(4 * n) | ctx->b_ml_pn.ensure(4 * n) | ctx->b_ml_has.ensure(n) | ctx->b_subl.ensure(4 * n);
-    bad |= ctx->b_sub_cnt.ensure(4 * n) | ctx->b_sub_off.ensure(4 * n) | ctx->b_t_lo.ensure(4 * n) | ctx->b_t_n.ensure(4 * n) | ctx->b_t_bin.ensure(4 * n) | ctx->b_sub_cluster.ensure(4 * n) | ctx->b_sub_lo.ensure(4 * n) | ctx->b_sub_n.ensure(4 * n) | ctx->b_sub_bin.ensure(4 * n);
-    bad |= ctx->b_cand_tmp.ensure(sizeof(snfb_cand) * n) | ctx->b_cand_valid.ensure(4 * n) | ctx->b_cand_id.ensure(4 * n) | ctx->b_cand_nlead.ensure(4 * n) | ctx->b_cand_lead_off.ensure(4 * n) | ctx->b_cand_nrn.ensure(4 * n) | ctx->b_cand_rn_off.ensure(4 * n);
-    // outputs: candidates <= sub-clusters <= leads; their leads (incl. leads_long copies) and names can exceed the lead count only through
-    // shared leads_long, so allow 2x and check on device
-    ctx->cand_cap = nb + 8; ctx->cand_lead_cap = 2 * nb + 64; ctx->rn_cap = 2 * nb + 64;
-    bad |= ctx->b_cand.ensure(sizeof(snfb_cand) * ctx->cand_cap) | ctx->b_cand_leads.ensure(sizeof(snfb_lead) * ctx->cand_lead_cap) | ctx->b_cand_lead_ml.ensure(4 * ctx->cand_lead_cap) | ctx->b_rnames.ensure(8 * ctx->rn_cap) | ctx->b_rn_off_out.ensure(4 * (ctx->cand_cap + 1));
-    bad |= ctx->b_plan_best.ensure(4 * ctx->cand_cap) | ctx->b_plan_nother.ensure(4 * ctx->cand_cap) | ctx->b_plan_otot.ensure(4 * ctx->cand_cap) | ctx->b_alt_len.ensure(4 * ctx->cand_cap) | ctx->b_scr_len.ensure(4 * ctx->cand_cap) | ctx->b_alt_off.ensure(4 * ctx->cand_cap) | ctx->b_scr_off.ensure(4 * ctx->cand_cap);
-    return bad;
-}
-
-static cluster::B make_b(snfb_ctx* ctx) {
-    cluster::B b{};
-    b.leads = ctx->b_leads.as<snfb_lead>(); b.rec = ctx->d_rec; b.task = ctx->b_task.as<snfb_task>(); b.contig = ctx->b_contig.as<snfb_contig>();
+// ------------------------------------------------------------------------------------------------ stage drivers (no host synchronisation inside)
+static void bind_inputs(snfb_ctx* ctx) {
+    cluster::B& b = ctx->B;
+    b.leads = ctx->leads; b.rec = ctx->d_rec; b.task = ctx->b_task.as<snfb_task>(); b.contig = ctx->b_contig.as<snfb_contig>();
     b.tr = ctx->n_tr ? ctx->b_tr.as<int32_t>() : nullptr; b.tr_pmax = ctx->b_trp.as<int32_t>();
-    b.rec_pos = ctx->b_rec_pos.as<int32_t>(); b.rec_end = ctx->b_rec_end.as<int32_t>(); b.rec_flags = ctx->b_rec_flags.as<uint8_t>(); b.rec_nm = ctx->b_rec_nm.as<double>();
-    b.rec_nlead = ctx->b_rec_nlead.as<uint32_t>(); b.rec_lead_off = ctx->b_rec_lead_off.as<uint32_t>();
-    b.task_first = ctx->b_task_first.as<uint32_t>(); b.task_last = ctx->b_task_last.as<uint32_t>(); b.task_maxspan = ctx->b_task_span.as<int32_t>();
+    b.rec_pos = ctx->rec_pos; b.rec_end = ctx->rec_end; b.rec_flags = ctx->rec_flags; b.rec_nm = ctx->rec_nm; b.rec_nlead = ctx->rec_nlead; b.rec_lead_off = ctx->rec_lead_off;
+    b.task_first = ctx->task_first; b.task_last = ctx->task_last; b.task_maxspan = ctx->task_span;
     b.mask = ctx->n_mask ? ctx->b_mask.as<int32_t>() : nullptr; b.mask_task_off = ctx->n_mask ? ctx->b_mask_off.as<uint32_t>() : nullptr;
-    b.n_task = ctx->n_task; b.n_bound = ctx->n_bound; b.ctr = ctx->b_ctr.as<DevCounters>(); b.cfg = ctx->cfg;
-    b.key0 = ctx->b_key0.as<uint64_t>(); b.val0 = ctx->b_val0.as<uint32_t>(); b.key1 = ctx->b_key1.as<uint64_t>(); b.val1 = ctx->b_val1.as<uint32_t>();
-    b.skey = ctx->sorted_in_first ? b.key0 : b.key1; b.sval = ctx->sorted_in_first ? b.val0 : b.val1;
-    b.flag = ctx->b_flag.as<uint32_t>(); b.scan = ctx->b_scan.as<uint32_t>();
-    b.bin_start = ctx->b_bin_start.as<uint32_t>(); b.bin_nl = ctx->b_bin_nl.as<uint32_t>(); b.bin_nlong = ctx->b_bin_nlong.as<uint32_t>(); b.bin_kept = ctx->b_bin_kept.as<uint32_t>(); b.bin_hap = ctx->b_bin_hap.as<uint32_t>();
-    b.kl_off = ctx->b_kl_off.as<uint32_t>(); b.kll_off = ctx->b_kll_off.as<uint32_t>(); b.kb_idx = ctx->b_kb_idx.as<uint32_t>(); b.kl = ctx->b_kl.as<uint32_t>(); b.kll = ctx->b_kll.as<uint32_t>();
-    b.kb_bin = ctx->b_kb_bin.as<uint32_t>(); b.kb_lead_off = ctx->b_kb_lead_off.as<uint32_t>(); b.kb_lead_n = ctx->b_kb_lead_n.as<uint32_t>(); b.kb_long_off = ctx->b_kb_long_off.as<uint32_t>(); b.kb_long_n = ctx->b_kb_long_n.as<uint32_t>();
-    b.kb_seed = ctx->b_kb_seed.as<int32_t>(); b.kb_chain = ctx->b_kb_chain.as<uint32_t>(); b.kb_repeat = ctx->b_kb_repeat.as<uint8_t>();
-    b.seg_start = ctx->b_seg_start.as<uint32_t>(); b.c_next = ctx->b_c_next.as<uint32_t>(); b.c_last = ctx->b_c_last.as<uint32_t>(); b.c_sd = ctx->b_c_sd.as<double>(); b.c_mean = ctx->b_c_mean.as<double>(); b.c_rep = ctx->b_c_rep.as<uint8_t>();
-    b.seg_sd_last = ctx->b_seg_sd_last.as<double>(); b.seg_maxsd_first = ctx->b_seg_maxsd.as<double>(); b.cl_first = ctx->b_cl_first.as<uint32_t>(); b.cl_last = ctx->b_cl_last.as<uint32_t>(); b.cl_rep = ctx->b_cl_rep.as<uint8_t>();
-    b.s_hi = ctx->b_s_hi.as<uint64_t>(); b.s_lo = ctx->b_s_lo.as<uint64_t>(); b.s_a = ctx->b_s_a.as<uint32_t>(); b.s_b = ctx->b_s_b.as<uint32_t>(); b.s_c = ctx->b_s_c.as<uint32_t>(); b.s_d = ctx->b_s_d.as<uint32_t>(); b.s_e = ctx->b_s_e.as<uint32_t>();
-    b.ord = ctx->b_ord.as<uint32_t>(); b.ml_slot = ctx->b_ml_slot.as<uint32_t>(); b.ml_svlen = ctx->b_ml_svlen.as<int32_t>(); b.ml_seqlen = ctx->b_ml_seqlen.as<int32_t>(); b.ml_plo = ctx->b_ml_plo.as<uint32_t>(); b.ml_pn = ctx->b_ml_pn.as<uint32_t>();
-    b.ml_has = ctx->b_ml_has.as<uint8_t>(); b.subl = ctx->b_subl.as<uint32_t>(); b.sub_cnt = ctx->b_sub_cnt.as<uint32_t>(); b.sub_off = ctx->b_sub_off.as<uint32_t>();
-    b.t_lo = ctx->b_t_lo.as<uint32_t>(); b.t_n = ctx->b_t_n.as<uint32_t>(); b.t_bin = ctx->b_t_bin.as<int32_t>(); b.sub_cluster = ctx->b_sub_cluster.as<uint32_t>(); b.sub_lo = ctx->b_sub_lo.as<uint32_t>(); b.sub_n = ctx->b_sub_n.as<uint32_t>(); b.sub_bin = ctx->b_sub_bin.as<int32_t>();
-    b.cand_tmp = ctx->b_cand_tmp.as<snfb_cand>(); b.cand_valid = ctx->b_cand_valid.as<uint32_t>(); b.cand_id = ctx->b_cand_id.as<uint32_t>(); b.cand_nlead = ctx->b_cand_nlead.as<uint32_t>(); b.cand_lead_off = ctx->b_cand_lead_off.as<uint32_t>();
-    b.cand_nrn = ctx->b_cand_nrn.as<uint32_t>(); b.cand_rn_off = ctx->b_cand_rn_off.as<uint32_t>(); b.cand = ctx->b_cand.as<snfb_cand>(); b.cand_leads = ctx->b_cand_leads.as<snfb_lead>(); b.cand_lead_ml = ctx->b_cand_lead_ml.as<uint32_t>();
-    b.rnames = ctx->b_rnames.as<uint64_t>(); b.rn_off_out = ctx->b_rn_off_out.as<uint32_t>();
-    b.cand_cap = ctx->cand_cap; b.cand_lead_cap = ctx->cand_lead_cap; b.rn_cap = ctx->rn_cap; b.scan_tmp = ctx->b_scan_tmp.as<uint32_t>();
-    return b;
+    b.n_task = ctx->n_task; b.n_bound = ctx->cap.lead; b.ctr = ctx->b_ctr.as<DevCounters>(); b.cfg = ctx->cfg;
+    b.cut_gap = ctx->force_no_cuts ? INT_MAX : cluster::break_gap(ctx->cfg);
+    b.cand_cap = ctx->cap.cand; b.cand_lead_cap = ctx->cap.cand_lead; b.rn_cap = ctx->cap.rn;
+    consensus::C& c = ctx->Cc;
+    c.cand = b.cand; c.cand_rw = b.cand; c.cand_leads = b.cand_leads; c.out_plo = b.out_plo; c.out_pn = b.out_pn; c.ord = b.ord; c.kleads = b.kleads; c.rec = ctx->d_rec; c.seq = ctx->d_seq; c.arena_off = nullptr;
+    c.cand_cap = ctx->cap.cand; c.ctr = b.ctr; c.cfg = ctx->cfg; c.item_cap = ctx->cap.item; c.tile_cap = ctx->cap.tile; c.alt_cap = ctx->cap.alt; c.scr_cap16 = ctx->cap.scr16;
 }
-
-static int bits_for(uint32_t n) { int b = 0; while ((1ull << b) < n) ++b; return b; }
 
 // stage A plus the bin sort: everything LeadProvider.build_leadtab leaves behind
-static int run_stage_a(snfb_ctx* ctx) {
-    if (!ctx->loaded) return fail(ctx, "no records loaded");
-    if (!ctx->have_cfg) return fail(ctx, "snfb_set_config was not called");
-    cudaSetDevice(ctx->device);
-    const uint64_t nrec = ctx->n_rec; const uint32_t nt = ctx->n_task;
-    for (int attempt = 0; attempt < 3; ++attempt) {
-        if (ctx->lead_cap == 0) ctx->lead_cap = std::max<unsigned long long>(1ull << 16, nrec * 2) + (unsigned long long)extract::SA_BLOCKS * extract::SA_THREADS * extract::SLOT_CHUNK;
-        int bad = ctx->b_ctr.ensure(sizeof(DevCounters)) | ctx->b_leads.ensure(sizeof(snfb_lead) * ctx->lead_cap) | ctx->b_rec_pos.ensure(4 * (nrec + 1)) | ctx->b_rec_end.ensure(4 * (nrec + 1)) | ctx->b_rec_flags.ensure(nrec + 1)
-                | ctx->b_rec_nm.ensure(8 * (nrec + 1)) | ctx->b_rec_nlead.ensure(4 * (nrec + 1)) | ctx->b_rec_lead_off.ensure(4 * (nrec + 1)) | ctx->b_task_first.ensure(4 * nt) | ctx->b_task_last.ensure(4 * nt)
-                | ctx->b_task_reads.ensure(4 * nt) | ctx->b_task_cov.ensure(8 * nt) | ctx->b_task_span.ensure(4 * nt) | ctx->b_task_nm.ensure(8 * nt) | ctx->b_scan_tmp.ensure(4 * (prims::scan_tmp_elems(nrec) + 16));
-        if (bad) return fail(ctx, "out of device memory (stage A)");
-        CUDA_TRY(cudaMemsetAsync(ctx->b_ctr.p, 0, sizeof(DevCounters), ctx->st));
-        CUDA_TRY(cudaMemsetAsync(ctx->b_task_first.p, 0, 4 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_last.p, 0, 4 * nt, ctx->st));
-        CUDA_TRY(cudaMemsetAsync(ctx->b_task_reads.p, 0, 4 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_cov.p, 0, 8 * nt, ctx->st)); CUDA_TRY(cudaMemsetAsync(ctx->b_task_span.p, 0, 4 * nt, ctx->st));
-        const snfb_config& cf = ctx->cfg;
-        if (ctx->b_ev.ensure(sizeof(extract::Event) * ctx->lead_cap) || ctx->b_sa_list.ensure(4 * (nrec + 1))
-            || ctx->b_scan_tmp.ensure(4 * (prims::scan_tmp_elems(std::max<unsigned long long>(nrec, ctx->lead_cap)) + 16))) return fail(ctx, "out of device memory (stage A lists)");
-        DevCounters* ctr = ctx->b_ctr.as<DevCounters>();
-        if (ctx->b_scanrec.ensure(sizeof(extract::RecScan) * (nrec + 1)) || ctx->b_clip.ensure(sizeof(extract::RecClip) * (nrec + 1)) || ctx->b_rec_big.ensure(4 * (nrec + 1))) return fail(ctx, "out of device memory (record descriptors)");
-        extract::ScanParams S{};
-        S.scan = ctx->b_scanrec.as<extract::RecScan>(); S.cigar = ctx->d_cigar; S.task = ctx->b_task.as<snfb_task>(); S.n_rec = (uint32_t)nrec;
-        S.rec_end = ctx->b_rec_end.as<int32_t>(); S.rec_nlead = ctx->b_rec_nlead.as<uint32_t>(); S.rec_big = ctx->b_rec_big.as<int32_t>();
-        S.ev = ctx->b_ev.as<extract::Event>(); S.ev_cap = ctx->lead_cap; S.n_ev = &ctr->n_ev; S.sa_list = ctx->b_sa_list.as<uint32_t>(); S.n_sa = &ctr->n_sa; S.ctr = ctr;
-        S.minsv = cf.minsvlen_screen;
-        { const bool want_nm = cf.qc_nm_measure || cf.phase; int t = cf.minsvlen_screen < 1 ? 1 : cf.minsvlen_screen; if (want_nm && t > 11) t = 11; if (t > 0x1000) t = 0x1000;
-          S.gt_add = (uint32_t)(0x1000 - t) * 0x00010001u; }
-        uint32_t* task_first = ctx->b_task_first.as<uint32_t>(); uint32_t* task_last = ctx->b_task_last.as<uint32_t>();
-        uint8_t* rec_flags = ctx->b_rec_flags.as<uint8_t>(); double* rec_nm = ctx->b_rec_nm.as<double>();
-        mark(ctx, "k_rec_index");
-        if (nrec) {
-            extract::IndexParams I{};
-            I.rec = ctx->d_rec; I.cigar = ctx->d_cigar; I.task = S.task; I.n_rec = (uint32_t)nrec; I.rec_pos = ctx->b_rec_pos.as<int32_t>(); I.task_first = task_first; I.task_last = task_last;
-            I.scan = ctx->b_scanrec.as<extract::RecScan>(); I.clip = ctx->b_clip.as<extract::RecClip>(); I.rec_end = S.rec_end; I.rec_flags = rec_flags; I.rec_nm = rec_nm; I.rec_nlead = S.rec_nlead; I.ctr = ctr;
-            I.mapq_min = cf.mapq; I.alen_min = cf.min_alignment_length; I.excl = cf.exclude_flags; I.want_nm = (cf.qc_nm_measure || cf.phase) ? 1 : 0;
-            extract::k_rec_index<<<(unsigned)((nrec + 255) / 256), 256, 0, ctx->st>>>(I);
-            // algorithmic bytes of the streaming kernel: scan descriptors + CIGAR16 words (+ its per-record outputs and event slices, added by bench.py)
-            mark(ctx, "k_scan", sizeof(extract::RecScan) * nrec + 2 * ctx->n_cigar);
-            unsigned long long blocks = (nrec + 7) / 8; const unsigned long long maxb = 148ull * 6 * 4;
-            extract::k_scan<<<(int)std::min(blocks, maxb), 256, 0, ctx->st>>>(S);
-            mark(ctx, "k_rec_post");
-            extract::PostParams Q{};
-            Q.scan = I.scan; Q.clip = I.clip; Q.task = S.task; Q.n_rec = (uint32_t)nrec; Q.rec_end = S.rec_end; Q.rec_big = S.rec_big; Q.rec_nm = rec_nm;
-            Q.task_reads = ctx->b_task_reads.as<uint32_t>(); Q.task_cov_bp = ctx->b_task_cov.as<unsigned long long>(); Q.task_maxspan = ctx->b_task_span.as<int32_t>();
-            extract::k_rec_post<<<(unsigned)((nrec + 255) / 256), 256, 0, ctx->st>>>(Q); LAUNCHED(ctx, 1);
-            mark(ctx, "k_emit");
-            extract::EmitParams E{};
-            E.rec = ctx->d_rec; E.clip = ctx->b_clip.as<extract::RecClip>(); E.var = ctx->d_var; E.ev = S.ev; E.n_ev = S.n_ev; E.ev_cap = ctx->lead_cap;
-            E.leads = ctx->b_leads.as<snfb_lead>(); E.ctr = ctr; E.maxlen = cf.dev_seq_cache_maxlen; E.detect_large_ins = cf.detect_large_ins;
-            E.longinslen = (double)cf.long_ins_length / 2.0;
-            extract::k_emit<<<148 * 16, 128, 0, ctx->st>>>(E); LAUNCHED(ctx, 3);      // thread per event; k_rec_index and k_scan are counted here too
-            mark(ctx, "k_sa");
-            extract::SaParams A{};
-            A.rec = ctx->d_rec; A.clip = ctx->b_clip.as<extract::RecClip>(); A.var = ctx->d_var; A.task = S.task; A.contig = ctx->b_contig.as<snfb_contig>(); A.n_contig = ctx->n_contig;
-            A.sa_list = S.sa_list; A.n_sa = S.n_sa; A.rec_end = S.rec_end; A.rec_nlead = S.rec_nlead; A.leads = E.leads; A.lead_cap = ctx->lead_cap; A.ctr = ctr; A.cfg = cf;
-            if (ctx->b_sa_seg.ensure(sizeof(extract::Seg) * (size_t)extract::MAXSEG * extract::SA_THREADS * extract::SA_BLOCKS)) return fail(ctx, "out of device memory (split segments)");
-            A.seg_scratch = ctx->b_sa_seg.as<extract::Seg>();
-            extract::k_sa<<<extract::SA_BLOCKS, extract::SA_THREADS, 0, ctx->st>>>(A);
-            mark(ctx, "k_task_nm");
-            const int cpt = (int)((nrec + extract::NM_CHUNK - 1) / extract::NM_CHUNK);
-            if (ctx->b_nm_part.ensure(8 * (size_t)cpt * nt + 8) || ctx->b_nm_cnt.ensure(4 * (size_t)cpt * nt + 8)) return fail(ctx, "out of device memory (nm partials)");
-            extract::k_nm_partial<<<dim3(cpt, nt), 256, 0, ctx->st>>>(rec_flags, rec_nm, task_first, task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>());
-            extract::k_task_nm<<<nt, 256, 0, ctx->st>>>(task_first, task_last, ctx->b_nm_part.as<double>(), ctx->b_nm_cnt.as<unsigned>(), cpt, ctx->b_task_nm.as<double>()); LAUNCHED(ctx, 5);
-        }
-        mark(ctx, "scan_rec_leads");
-        LAUNCHED(ctx, prims::exclusive_scan(S.rec_nlead, ctx->b_rec_lead_off.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>(), nullptr, nrec, &ctr->n_leads, ctx->st));
-        mark(ctx, nullptr);
-        CUDA_TRY(cudaGetLastError());
-        if (fetch_counters(ctx)) return 1;
-        if (ctx->h_ctr.unsorted) return fail(ctx, "records are not coordinate sorted inside a task");
-        if (ctx->h_ctr.lead_overflow == 0 && ctx->h_ctr.n_slots <= ctx->lead_cap) break;
-        ctx->lead_cap = ctx->h_ctr.n_slots + ctx->h_ctr.n_slots / 4 + 1024;       // retry with a buffer that fits
-        ctx->n_ev = ctx->n_ev_load;
-        if (attempt == 2) return fail(ctx, "lead buffer overflow");
+static int enqueue_stage_a(snfb_ctx* ctx) {
+    const uint64_t nrec = ctx->n_rec; const uint32_t nt = ctx->n_task; const snfb_config& cf = ctx->cfg; cluster::B& b = ctx->B;
+    DevCounters* ctr = b.ctr; cudaStream_t st = ctx->st;
+    CUDA_TRY(cudaMemsetAsync(ctr, 0, sizeof(DevCounters), st));
+    CUDA_TRY(cudaMemsetAsync(ctx->task_first, 0, 4 * nt, st)); CUDA_TRY(cudaMemsetAsync(ctx->task_last, 0, 4 * nt, st));
+    CUDA_TRY(cudaMemsetAsync(ctx->task_reads, 0, 4 * nt, st)); CUDA_TRY(cudaMemsetAsync(ctx->task_cov, 0, 8 * nt, st)); CUDA_TRY(cudaMemsetAsync(ctx->task_span, 0, 4 * nt, st));
+    CUDA_TRY(cudaMemsetAsync(ctx->task_nm, 0, 8 * nt, st));
+    extract::ScanParams S{};
+    S.scan = ctx->scanrec; S.cigar = ctx->d_cigar; S.task = b.task; S.n_rec = (uint32_t)nrec; S.rec_end = ctx->rec_end; S.rec_nlead = ctx->rec_nlead; S.rec_big = ctx->rec_big;
+    S.ev = ctx->ev_buf; S.ev_cap = ctx->cap.lead; S.n_ev = &ctr->n_ev; S.sa_list = ctx->sa_list; S.n_sa = &ctr->n_sa; S.ctr = ctr; S.minsv = cf.minsvlen_screen;
+    { const bool want_nm = cf.qc_nm_measure || cf.phase; int t = cf.minsvlen_screen < 1 ? 1 : cf.minsvlen_screen; if (want_nm && t > 11) t = 11; if (t > 0x1000) t = 0x1000;
+      S.gt_add = (uint32_t)(0x1000 - t) * 0x00010001u; }
+    mark(ctx, "k_rec_index");
+    if (nrec) {
+        k_validate<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(ctx->d_rec, (uint32_t)nrec, nt, ctx->n_cigar, ctx->n_var, ctx->n_seq, ctx->seq_on_demand ? 0 : 1, ctr);
+        extract::IndexParams I{};
+        I.rec = ctx->d_rec; I.cigar = ctx->d_cigar; I.task = S.task; I.n_rec = (uint32_t)nrec; I.n_task = nt; I.rec_pos = ctx->rec_pos; I.task_first = ctx->task_first; I.task_last = ctx->task_last;
+        I.scan = ctx->scanrec; I.clip = ctx->clip; I.rec_end = S.rec_end; I.rec_flags = ctx->rec_flags; I.rec_nm = ctx->rec_nm; I.rec_nlead = S.rec_nlead; I.ctr = ctr;
+        I.mapq_min = cf.mapq; I.alen_min = cf.min_alignment_length; I.excl = cf.exclude_flags; I.want_nm = (cf.qc_nm_measure || cf.phase) ? 1 : 0; I.n_cigar = ctx->n_cigar;
+        extract::k_rec_index<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(I);
+        // algorithmic bytes of the streaming kernel: scan descriptors + CIGAR16 words (+ its per-record outputs and event slices, added by bench.py)
+        mark(ctx, "k_scan", sizeof(extract::RecScan) * nrec + 2 * ctx->n_cigar);
+        unsigned long long blocks = (nrec + 7) / 8; const unsigned long long maxb = 148ull * 6 * 4;
+        extract::k_scan<<<(int)std::min(blocks, maxb), 256, 0, st>>>(S);
+        mark(ctx, "k_rec_post");
+        extract::PostParams Q{};
+        Q.scan = I.scan; Q.clip = I.clip; Q.task = S.task; Q.n_rec = (uint32_t)nrec; Q.rec_end = S.rec_end; Q.rec_big = S.rec_big; Q.rec_nm = ctx->rec_nm;
+        Q.task_reads = ctx->task_reads; Q.task_cov_bp = ctx->task_cov; Q.task_maxspan = ctx->task_span;
+        extract::k_rec_post<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(Q);
+        mark(ctx, "k_emit");
+        extract::EmitParams E{};
+        E.rec = ctx->d_rec; E.clip = ctx->clip; E.var = ctx->d_var; E.ev = S.ev; E.n_ev = S.n_ev; E.ev_cap = ctx->cap.lead;
+        E.leads = ctx->leads; E.ctr = ctr; E.maxlen = cf.dev_seq_cache_maxlen; E.detect_large_ins = cf.detect_large_ins; E.longinslen = (double)cf.long_ins_length / 2.0;
+        extract::k_emit<<<148 * 16, 128, 0, st>>>(E);
+        mark(ctx, "k_sa");
+        extract::SaParams A{};
+        A.rec = ctx->d_rec; A.clip = ctx->clip; A.var = ctx->d_var; A.task = S.task; A.contig = b.contig; A.n_contig = ctx->n_contig;
+        A.sa_list = S.sa_list; A.n_sa = S.n_sa; A.rec_end = S.rec_end; A.rec_nlead = S.rec_nlead; A.leads = E.leads; A.lead_cap = ctx->cap.lead; A.ctr = ctr; A.cfg = cf; A.seg_scratch = ctx->sa_seg;
+        extract::k_sa<<<extract::SA_BLOCKS, extract::SA_THREADS, 0, st>>>(A);
+        mark(ctx, "k_task_nm");
+        const int cpt = (int)((nrec + extract::NM_CHUNK - 1) / extract::NM_CHUNK);
+        extract::k_nm_partial<<<dim3(cpt, nt), 256, 0, st>>>(ctx->rec_flags, ctx->rec_nm, ctx->task_first, ctx->task_last, ctx->nm_part, ctx->nm_cnt);
+        extract::k_task_nm<<<nt, 256, 0, st>>>(ctx->task_first, ctx->task_last, ctx->nm_part, ctx->nm_cnt, cpt, ctx->task_nm); LAUNCHED(ctx, 8);
     }
-    ctx->n_bound = ctx->h_ctr.n_leads;
-    if (ensure_stage_b(ctx, ctx->n_bound)) return fail(ctx, "out of device memory (stage B)");
-    cluster::B b = make_b(ctx);
-    const unsigned long long nb = ctx->n_bound; const int g = grid_for(nb, 256);
-    if (nb) {
-        mark(ctx, "sort_leads", nb * (sizeof(snfb_lead) + 24));
-        cluster::k_scatter_keys<<<grid_for(ctx->h_ctr.n_slots, 256), 256, 0, ctx->st>>>(b, ctx->h_ctr.n_slots);
-        prims::RadixTemp rt{ ctx->b_hist.as<uint32_t>(), ctx->b_scan_tmp.as<uint32_t>() };
-        bool first = true;
-        LAUNCHED(ctx, 1 + 3); LAUNCHED(ctx, prims::radix_sort(b.key0, b.val0, b.key1, b.val1, rt, &b.ctr->n_leads, nb, cluster::TASK_SHIFT + bits_for(ctx->n_task), &first, ctx->st));
-        ctx->sorted_in_first = first; b = make_b(ctx);
-        mark(ctx, "bins");
-        cluster::k_bin_heads<<<g, 256, 0, ctx->st>>>(b);
-        LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &b.ctr->n_bins, ctx->st));
-        cluster::k_bin_build<<<g, 256, 0, ctx->st>>>(b);
-        cluster::k_bin_stats<<<g, 256, 0, ctx->st>>>(b);
-        mark(ctx, nullptr);
-    } else CUDA_TRY(cudaMemsetAsync(&b.ctr->n_bins, 0, 8, ctx->st));
+    mark(ctx, "scan_rec_leads");
+    LAUNCHED(ctx, prims::exclusive_scan(S.rec_nlead, ctx->rec_lead_off, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_leads, st));
+    const unsigned long long nb = b.n_bound; const int g = grid_for(nb, 256);
+    mark(ctx, "sort_leads");
+    cluster::k_scatter_keys<<<g, 256, 0, st>>>(b);
+    prims::RadixTemp rt{ ctx->radix_hist, b.scan_tmp };
+    bool first = true;
+    LAUNCHED(ctx, 1 + prims::radix_sort(b.key0, b.val0, b.key1, b.val1, rt, &ctr->n_leads, nb, cluster::TASK_SHIFT + bits_for(ctx->n_task), &first, st));
+    b.skey = first ? b.key0 : b.key1; b.sval = first ? b.val0 : b.val1;
+    mark(ctx, "bins");
+    cluster::k_bin_heads<<<g, 256, 0, st>>>(b);
+    LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, &ctr->n_leads, nb, &ctr->n_bins, st));
+    cluster::k_bin_build<<<g, 256, 0, st>>>(b);
+    cluster::k_bin_stats<<<g, 256, 0, st>>>(b); LAUNCHED(ctx, 3);
+    mark(ctx, nullptr);
     CUDA_TRY(cudaGetLastError());
-    ctx->stage_a_done = true; ctx->stage_b_done = false;
     return 0;
 }
 
-__global__ void k_gather_leads(const snfb_lead* __restrict__ leads, const uint32_t* __restrict__ sval, snfb_lead* __restrict__ out, unsigned long long n) {
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) out[i] = leads[sval[i]];
-}
-__global__ void k_copy_ml(const uint32_t* __restrict__ subl, const uint32_t* __restrict__ sub_lo, const uint32_t* __restrict__ cand_valid, const uint32_t* __restrict__ cand_lead_off,
-                          const snfb_cand* __restrict__ cand_tmp, uint32_t* __restrict__ cand_lead_ml, const unsigned long long* n_sub, unsigned long long cap) {
-    for (unsigned long long s = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; s < *n_sub; s += (unsigned long long)gridDim.x * blockDim.x) {
-        if (!cand_valid[s]) continue;
-        const uint32_t lo = cand_lead_off[s]; const int n = cand_tmp[s].lead_n;
-        for (int i = 0; i < n; ++i) if ((unsigned long long)lo + i < cap) cand_lead_ml[lo + i] = subl[sub_lo[s] + i];
-    }
+static int enqueue_stage_b(snfb_ctx* ctx) {
+    cluster::B& b = ctx->B; DevCounters* ctr = b.ctr; cudaStream_t st = ctx->st;
+    const unsigned long long nb = b.n_bound; const int g = grid_for(nb, 128);
+    mark(ctx, "kept_bins");
+    LAUNCHED(ctx, prims::exclusive_scan(b.bin_nl, b.kl_off, b.scan_tmp, &ctr->n_bins, nb, &ctr->n_kl, st));
+    LAUNCHED(ctx, prims::exclusive_scan(b.bin_nlong, b.kll_off, b.scan_tmp, &ctr->n_bins, nb, &ctr->n_kll, st));
+    LAUNCHED(ctx, prims::exclusive_scan(b.bin_kept, b.kb_idx, b.scan_tmp, &ctr->n_bins, nb, &ctr->n_kbins, st));
+    cluster::k_kbin_build<<<g, 128, 0, st>>>(b);
+    cluster::k_gather_kept<<<grid_for(nb, 256), 256, 0, st>>>(b);
+    mark(ctx, "merge_chains");
+    cluster::k_seg_heads<<<g, 128, 0, st>>>(b);
+    LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, &ctr->n_kbins, nb, &ctr->n_segs, st));
+    cluster::k_seg_build<<<g, 128, 0, st>>>(b);
+    cluster::k_merge<<<g, 128, 0, st>>>(b);
+    cluster::k_verify_cuts<<<g, 128, 0, st>>>(b);
+    LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, &ctr->n_kbins, nb, &ctr->n_clusters, st));
+    cluster::k_cluster_build<<<g, 128, 0, st>>>(b);
+    mark(ctx, "cluster_call");
+    // clusters too large for one warp's shared memory go to a block each, next to the warp-per-cluster kernel
+    CUDA_TRY(cudaEventRecord(ctx->ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(ctx->st_side, ctx->ev_fork, 0));
+    cluster::k_cluster_block<<<148, cluster::CB_THREADS, cluster::CB_SMEM, ctx->st_side>>>(b);
+    CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->st_side));
+    cluster::k_cluster_warp<<<148 * 3, cluster::CW_WARPS * 32, cluster::CW_SMEM, st>>>(b);
+    CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
+    mark(ctx, "emit_cands");
+    LAUNCHED(ctx, prims::exclusive_scan(b.cl_nvalid, b.cl_cand_base, b.scan_tmp, &ctr->n_clusters, nb, &ctr->n_cand, st));
+    LAUNCHED(ctx, prims::exclusive_scan(b.cl_nlead, b.cl_lead_base, b.scan_tmp, &ctr->n_clusters, nb, &ctr->n_cand_leads, st));
+    LAUNCHED(ctx, prims::exclusive_scan(b.cl_nrn, b.cl_rn_base, b.scan_tmp, &ctr->n_clusters, nb, &ctr->n_rnames, st));
+    cluster::k_emit_cands<<<148 * 8, 128, 0, st>>>(b);
+    mark(ctx, "coverage");
+    if (ctx->n_mask) { cluster::k_mask_bp<<<grid_for((unsigned long long)ctx->n_mask * 32, 128), 128, 0, st>>>(b, ctx->b_mask_task.as<uint32_t>(), ctx->n_mask, ctx->task_cov); LAUNCHED(ctx, 1); }
+    cluster::k_coverage<<<148 * 8, 128, 0, st>>>(b); LAUNCHED(ctx, 12);
+    // consensus plan: best read per INS candidate, sizes and offsets of the ALT bytes and of the scratch; the candidate records are final after this
+    consensus::C& c = ctx->Cc;
+    CUDA_TRY(cudaMemsetAsync(c.work_ctr, 0, 64, st));
+    mark(ctx, "consensus_plan");
+    consensus::k_plan<<<grid_for(ctx->cap.cand, 128), 128, 0, st>>>(c);
+    LAUNCHED(ctx, prims::exclusive_scan(c.alt_len, c.alt_off, b.scan_tmp, &ctr->n_cand, ctx->cap.cand, &ctr->n_alt_bytes, st));
+    LAUNCHED(ctx, prims::exclusive_scan(c.scr_len, c.scr_off, b.scan_tmp, &ctr->n_cand, ctx->cap.cand, &ctr->n_seq_bytes, st));
+    consensus::k_plan_finish<<<grid_for(ctx->cap.cand, 128), 128, 0, st>>>(c); LAUNCHED(ctx, 2);
+    mark(ctx, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
+// the consensus kernels; with the seq arena on the host ("seq on demand") the base slices are requested, gathered and uploaded first
+static int enqueue_stage_c(snfb_ctx* ctx) {
+    cluster::B& b = ctx->B; consensus::C& c = ctx->Cc; DevCounters* ctr = b.ctr; cudaStream_t st = ctx->st;
+    c.seq = ctx->d_seq; c.arena_off = nullptr; ctx->seq_h2d_bytes = 0;
+    if (ctx->seq_on_demand) {
+        // the device lists the base slices it will read, the host gathers exactly those bytes from its arena into pinned staging,
+        // one H2D copy brings them in (PCIe bytes ~ algorithmic bytes instead of the whole arena).  This path needs the host in the loop.
+        mark(ctx, "seq_requests");
+        consensus::k_seq_requests<<<grid_for(ctx->cap.cand, 128), 128, 0, st>>>(c, ctx->seq_req, ctx->cap.req, ctx->arena_off, &ctr->n_req, &ctr->n_req_units); LAUNCHED(ctx, 1);
+        mark(ctx, nullptr);
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_fin, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const unsigned long long nreq = ctx->h_fin->n_req, nunits = ctx->h_fin->n_req_units;
+        if (nreq <= ctx->cap.req && nunits <= ctx->cap.req16 && nreq) {
+            if (ctx->h_seq_req.ensure(sizeof(consensus::SeqReq) * (nreq + 1)) || ctx->h_seq_arena.ensure(nunits * 16 + 64)) return fail(ctx, "out of pinned memory (seq arena)");
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_seq_req.p, ctx->seq_req, sizeof(consensus::SeqReq) * nreq, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            const consensus::SeqReq* rq = ctx->h_seq_req.as<consensus::SeqReq>(); uint8_t* dst = ctx->h_seq_arena.as<uint8_t>(); const uint8_t* src = ctx->h_seq; const uint64_t nseq = ctx->n_seq;
+            #pragma omp parallel for schedule(static, 256)
+            for (long long i = 0; i < (long long)nreq; ++i) {
+                unsigned long long s0 = rq[i].src; unsigned long long nbytes = rq[i].nbytes; if (s0 > nseq) s0 = nseq; if (s0 + nbytes > nseq) nbytes = nseq - s0;
+                memcpy(dst + (size_t)rq[i].dst16 * 16, src + s0, (size_t)nbytes);
+            }
+            mark(ctx, "h2d_seq_slices", nunits * 16);
+            CUDA_TRY(cudaMemcpyAsync(ctx->seq_arena, ctx->h_seq_arena.p, nunits * 16, cudaMemcpyHostToDevice, st));
+            mark(ctx, nullptr);
+            ctx->seq_h2d_bytes = nunits * 16;
+        }
+        c.seq = ctx->seq_arena; c.arena_off = ctx->arena_off;
+    }
+    mark(ctx, "consensus");
+    consensus::k_prep<<<148 * 8, 128, 0, st>>>(c);
+    mark(ctx, "consensus_align");
+    consensus::k_align<<<148 * 8, consensus::ALIGN_WARPS * 32, 0, st>>>(c);
+    mark(ctx, "consensus_vote");
+    consensus::k_vote<<<148 * 16, consensus::VOTE_THREADS, 0, st>>>(c); LAUNCHED(ctx, 3);
+    mark(ctx, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ capacities
+static void initial_caps(snfb_ctx* ctx) {
+    Caps& k = ctx->cap;
+    const unsigned long long nrec = ctx->n_rec;
+    const unsigned long long lead = std::max<unsigned long long>(1ull << 16, nrec) + (unsigned long long)extract::SA_BLOCKS * extract::SA_THREADS * extract::SLOT_CHUNK / 4;
+    if (k.lead < lead) k.lead = lead;
+    if (k.cand < k.lead / 8 + 1024) k.cand = k.lead / 8 + 1024;
+    if (k.cand_lead < k.lead / 2 + 1024) k.cand_lead = k.lead / 2 + 1024;
+    if (k.rn < k.lead / 2 + 1024) k.rn = k.lead / 2 + 1024;
+    if (k.alt < (4ull << 20)) k.alt = 4ull << 20;
+    if (k.scr16 < (2ull << 20)) k.scr16 = 2ull << 20;
+    if (k.item < k.cand_lead / 2 + 1024) k.item = k.cand_lead / 2 + 1024;
+    if (k.tile < k.cand + 4096) k.tile = k.cand + 4096;
+    if (ctx->seq_on_demand) { if (k.req < k.cand_lead / 2 + 1024) k.req = k.cand_lead / 2 + 1024; if (k.req16 < (1ull << 20)) k.req16 = 1ull << 20; }
+    else { if (k.req < 16) k.req = 16; if (k.req16 < 16) k.req16 = 16; }
+}
+static unsigned long long grown(unsigned long long need) { return need + need / 4 + 1024; }
+// does everything the counters report fit the capacities the run used?  If not, raise them (what was needed + 25 %).
+static bool caps_fit(snfb_ctx* ctx, const DevCounters& c, const uint32_t* work, int upto) {
+    Caps& k = ctx->cap; bool ok = true;
+    const unsigned long long need_lead = std::max(c.n_slots, c.n_leads);
+    if (need_lead > k.lead || c.lead_overflow) { k.lead = std::max(grown(need_lead), k.lead + k.lead / 2); ok = false; }
+    if (upto >= 2) {
+        if (c.n_cand > k.cand) { k.cand = grown(c.n_cand); ok = false; }
+        if (c.n_cand_leads > k.cand_lead) { k.cand_lead = grown(c.n_cand_leads); ok = false; }
+        if (c.n_rnames > k.rn) { k.rn = grown(c.n_rnames); ok = false; }
+        if (c.n_alt_bytes > k.alt) { k.alt = grown(c.n_alt_bytes); ok = false; }
+        if (c.n_seq_bytes > k.scr16) { k.scr16 = grown(c.n_seq_bytes); ok = false; }
+        const unsigned long long items = std::max(work[4], work[5]);
+        if (items > k.item) { k.item = grown(items); ok = false; }
+        if (work[8] > k.tile) { k.tile = grown(work[8]); ok = false; }
+    }
+    if (upto >= 3) {
+        if (c.n_req > k.req) { k.req = grown(c.n_req); ok = false; }
+        if (c.n_req_units > k.req16) { k.req16 = grown(c.n_req_units); ok = false; }
+        if (ok && c.scratch_overflow) { ok = false; k.alt = grown(k.alt); k.scr16 = grown(k.scr16); }      // should not happen: every capacity above fit
+    } else if (ok && c.scratch_overflow) { ok = false; k.cand_lead = grown(k.cand_lead); k.rn = grown(k.rn); }
+    return ok;
+}
+
+// ------------------------------------------------------------------------------------------------ views
 static int fill_lead_view(snfb_ctx* ctx, snfb_lead_view* out) {
-    const unsigned long long nl = ctx->n_bound; const uint32_t nt = ctx->n_task;
-    if (ctx->b_sorted_leads.ensure(sizeof(snfb_lead) * (nl + 1)) || ctx->h_leads.ensure(sizeof(snfb_lead) * (nl + 1)) || ctx->h_task_reads.ensure(4 * nt) || ctx->h_task_nm.ensure(8 * nt) || ctx->h_rec_nm.ensure(8 * (ctx->n_rec + 1)))
+    const DevCounters& c = *ctx->h_fin; const unsigned long long nl = c.n_leads; const uint32_t nt = ctx->n_task;
+    if (ctx->h_leads.ensure(sizeof(snfb_lead) * (nl + 1)) || ctx->h_task_reads.ensure(4 * nt) || ctx->h_task_nm.ensure(8 * nt) || ctx->h_rec_nm.ensure(8 * (ctx->n_rec + 1)))
         return fail(ctx, "out of memory for the lead view");
     if (nl) {
-        cluster::B b = make_b(ctx);
-        k_gather_leads<<<grid_for(nl, 256), 256, 0, ctx->st>>>(b.leads, b.sval, ctx->b_sorted_leads.as<snfb_lead>(), nl);
-        CUDA_TRY(cudaMemcpyAsync(ctx->h_leads.p, ctx->b_sorted_leads.p, sizeof(snfb_lead) * nl, cudaMemcpyDeviceToHost, ctx->st));
+        k_gather_leads<<<grid_for(nl, 256), 256, 0, ctx->st>>>(ctx->leads, ctx->B.sval, ctx->sorted_leads, &ctx->B.ctr->n_leads, ctx->cap.lead); LAUNCHED(ctx, 1);
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_leads.p, ctx->sorted_leads, sizeof(snfb_lead) * nl, cudaMemcpyDeviceToHost, ctx->st));
     }
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_task_reads.p, ctx->b_task_reads.p, 4 * nt, cudaMemcpyDeviceToHost, ctx->st));
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_task_nm.p, ctx->b_task_nm.p, 8 * nt, cudaMemcpyDeviceToHost, ctx->st));
-    if (ctx->n_rec) CUDA_TRY(cudaMemcpyAsync(ctx->h_rec_nm.p, ctx->b_rec_nm.p, 8 * ctx->n_rec, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_task_reads.p, ctx->task_reads, 4 * nt, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_task_nm.p, ctx->task_nm, 8 * nt, cudaMemcpyDeviceToHost, ctx->st));
+    if (ctx->n_rec) CUDA_TRY(cudaMemcpyAsync(ctx->h_rec_nm.p, ctx->rec_nm, 8 * ctx->n_rec, cudaMemcpyDeviceToHost, ctx->st));
     CUDA_TRY(cudaStreamSynchronize(ctx->st));
     out->n_leads = nl; out->leads = ctx->h_leads.as<snfb_lead>();
     out->task_read_count = ctx->h_task_reads.as<uint32_t>(); out->task_mean_nm = ctx->h_task_nm.as<double>(); out->rec_nm = ctx->h_rec_nm.as<double>();
     uint64_t np = 0; for (uint32_t t = 0; t < nt; ++t) np += out->task_read_count[t];
-    out->n_pass = np; out->soft_errors = ctx->h_ctr.soft_errors;
+    out->n_pass = np; out->soft_errors = c.soft_errors;
     return 0;
 }
-
-static int run_stage_b(snfb_ctx* ctx) {
-    if (!ctx->stage_a_done) return fail(ctx, "snfb_extract_leads must run first");
-    cudaSetDevice(ctx->device);
-    cluster::B b = make_b(ctx);
-    const unsigned long long nb = ctx->n_bound; const int g = grid_for(nb, 128);
-    DevCounters* ctr = b.ctr;
-    if (nb) {
-        mark(ctx, "kept_bins");
-        LAUNCHED(ctx, prims::exclusive_scan(b.bin_nl, b.kl_off, b.scan_tmp, nullptr, nb, nullptr, ctx->st));
-        LAUNCHED(ctx, prims::exclusive_scan(b.bin_nlong, b.kll_off, b.scan_tmp, nullptr, nb, nullptr, ctx->st));
-        LAUNCHED(ctx, prims::exclusive_scan(b.bin_kept, b.kb_idx, b.scan_tmp, nullptr, nb, &ctr->n_kbins, ctx->st));
-        cluster::k_kbin_build<<<g, 128, 0, ctx->st>>>(b);
-        mark(ctx, "merge_chains");
-        cluster::k_seg_heads<<<g, 128, 0, ctx->st>>>(b);
-        LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &ctr->n_segs, ctx->st));
-        cluster::k_seg_build<<<g, 128, 0, ctx->st>>>(b);
-        cluster::k_merge<<<g, 128, 0, ctx->st>>>(b);
-        cluster::k_verify_cuts<<<g, 128, 0, ctx->st>>>(b);
-        LAUNCHED(ctx, prims::exclusive_scan(b.flag, b.scan, b.scan_tmp, nullptr, nb, &ctr->n_clusters, ctx->st));
-        cluster::k_cluster_build<<<g, 128, 0, ctx->st>>>(b);
-        mark(ctx, "cluster_post");
-        cluster::k_cluster_post<<<g, 128, 0, ctx->st>>>(b);
-        LAUNCHED(ctx, prims::exclusive_scan(b.sub_cnt, b.sub_off, b.scan_tmp, nullptr, nb, &ctr->n_sub, ctx->st));
-        cluster::k_sub_build<<<g, 128, 0, ctx->st>>>(b);
-        mark(ctx, "call_from");
-        cluster::k_call<<<g, 128, 0, ctx->st>>>(b);
-        LAUNCHED(ctx, prims::exclusive_scan(b.cand_valid, b.cand_id, b.scan_tmp, nullptr, nb, &ctr->n_cand, ctx->st));
-        LAUNCHED(ctx, prims::exclusive_scan(b.cand_nlead, b.cand_lead_off, b.scan_tmp, nullptr, nb, &ctr->n_cand_leads, ctx->st));
-        LAUNCHED(ctx, prims::exclusive_scan(b.cand_nrn, b.cand_rn_off, b.scan_tmp, nullptr, nb, &ctr->n_rnames, ctx->st));
-        mark(ctx, "cand_finish");
-        cluster::k_cand_finish<<<g, 128, 0, ctx->st>>>(b);
-        k_copy_ml<<<g, 128, 0, ctx->st>>>(b.subl, b.sub_lo, b.cand_valid, b.cand_lead_off, b.cand_tmp, b.cand_lead_ml, &ctr->n_sub, ctx->cand_lead_cap);
-        mark(ctx, "coverage");
-        if (ctx->n_mask) { cluster::k_mask_bp<<<grid_for((unsigned long long)ctx->n_mask * 32, 128), 128, 0, ctx->st>>>(b, ctx->b_mask_task.as<uint32_t>(), ctx->n_mask, ctx->b_task_cov.as<unsigned long long>()); LAUNCHED(ctx, 1); }
-        cluster::k_coverage<<<g, 128, 0, ctx->st>>>(b); LAUNCHED(ctx, 12);
-        mark(ctx, nullptr);
-    }
-    CUDA_TRY(cudaGetLastError());
-    ctx->stage_b_done = true;
+// device -> host copies of the candidate view on `stream`, sized by the counters `c`
+static int enqueue_cand_copies(snfb_ctx* ctx, const DevCounters& c, cudaStream_t stream) {
+    cluster::B& b = ctx->B; const uint32_t nt = ctx->n_task;
+    if (ctx->h_cand.ensure(sizeof(snfb_cand) * (c.n_cand + 1)) || ctx->h_cand_leads.ensure(sizeof(snfb_lead) * (c.n_cand_leads + 1)) || ctx->h_rnames.ensure(8 * (c.n_rnames + 1)) || ctx->h_rn_off.ensure(4 * (c.n_cand + 2))
+        || ctx->h_task_cov.ensure(8 * nt) || ctx->h_task_cov_raw.ensure(8 * nt)) return fail(ctx, "out of pinned memory for the candidate view");
+    if (c.n_cand) { CUDA_TRY(cudaMemcpyAsync(ctx->h_cand.p, b.cand, sizeof(snfb_cand) * c.n_cand, cudaMemcpyDeviceToHost, stream)); CUDA_TRY(cudaMemcpyAsync(ctx->h_rn_off.p, b.rn_off_out, 4 * c.n_cand, cudaMemcpyDeviceToHost, stream)); }
+    if (c.n_cand_leads) CUDA_TRY(cudaMemcpyAsync(ctx->h_cand_leads.p, b.cand_leads, sizeof(snfb_lead) * c.n_cand_leads, cudaMemcpyDeviceToHost, stream));
+    if (c.n_rnames) CUDA_TRY(cudaMemcpyAsync(ctx->h_rnames.p, b.rnames, 8 * c.n_rnames, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_task_cov_raw.p, ctx->task_cov, 8 * nt, cudaMemcpyDeviceToHost, stream));
     return 0;
 }
-
-// the bulk of the candidate view (lead table, read names) is final once stage B is done: in snfb_run it is copied on its own
-// stream while the consensus kernels run
-static int cand_bulk_copy(snfb_ctx* ctx, cudaStream_t stream) {
-    const DevCounters& c = ctx->h_ctr;
-    if (c.n_cand > ctx->cand_cap || c.n_cand_leads > ctx->cand_lead_cap || c.n_rnames > ctx->rn_cap) return fail(ctx, "candidate output buffers too small");
-    if (ctx->h_cand.ensure(sizeof(snfb_cand) * (c.n_cand + 1)) || ctx->h_cand_leads.ensure(sizeof(snfb_lead) * (c.n_cand_leads + 1)) || ctx->h_rnames.ensure(8 * (c.n_rnames + 1)) || ctx->h_rn_off.ensure(4 * (c.n_cand + 2)) || ctx->h_task_cov.ensure(8 * ctx->n_task))
-        return fail(ctx, "out of pinned memory for the candidate view");
-    if (c.n_cand) CUDA_TRY(cudaMemcpyAsync(ctx->h_rn_off.p, ctx->b_rn_off_out.p, 4 * c.n_cand, cudaMemcpyDeviceToHost, stream));
-    if (c.n_cand_leads) CUDA_TRY(cudaMemcpyAsync(ctx->h_cand_leads.p, ctx->b_cand_leads.p, sizeof(snfb_lead) * c.n_cand_leads, cudaMemcpyDeviceToHost, stream));
-    if (c.n_rnames) CUDA_TRY(cudaMemcpyAsync(ctx->h_rnames.p, ctx->b_rnames.p, 8 * c.n_rnames, cudaMemcpyDeviceToHost, stream));
-    return 0;
-}
-
-static int fill_cand_view(snfb_ctx* ctx, snfb_cand_view* out, bool cand_copied_later = false) {
-    if (fetch_counters(ctx)) return 1;
-    const DevCounters& c = ctx->h_ctr; const uint32_t nt = ctx->n_task;
-    if (c.scratch_overflow) return fail(ctx, "candidate output buffers overflowed");
-    if (ctx->cand_prefetched) { CUDA_TRY(cudaStreamSynchronize(ctx->st_copy)); ctx->cand_prefetched = false; }
-    else if (cand_bulk_copy(ctx, ctx->st)) return 1;
-    if (c.n_cand && !cand_copied_later) CUDA_TRY(cudaMemcpyAsync(ctx->h_cand.p, ctx->b_cand.p, sizeof(snfb_cand) * c.n_cand, cudaMemcpyDeviceToHost, ctx->st));
-    std::vector<unsigned long long> cov(nt);
-    CUDA_TRY(cudaMemcpyAsync(cov.data(), ctx->b_task_cov.p, 8 * nt, cudaMemcpyDeviceToHost, ctx->st));
-    CUDA_TRY(cudaStreamSynchronize(ctx->st));
+static void finish_cand_view(snfb_ctx* ctx, const DevCounters& c, snfb_cand_view* out) {
+    const uint32_t nt = ctx->n_task;
     ctx->h_rn_off.as<uint32_t>()[c.n_cand] = (uint32_t)c.n_rnames;
     // coverage_average_total: integer base-pair sum / contig length, one rounding (postprocessing.py:130)
-    double* cm = ctx->h_task_cov.as<double>();
+    double* cm = ctx->h_task_cov.as<double>(); const unsigned long long* cov = ctx->h_task_cov_raw.as<unsigned long long>();
     for (uint32_t t = 0; t < nt; ++t) cm[t] = ctx->tasks[t].contig_len > 0 ? (double)cov[t] / (double)ctx->tasks[t].contig_len : 0.0;
     out->n_cand = c.n_cand; out->cand = ctx->h_cand.as<snfb_cand>(); out->n_cand_leads = c.n_cand_leads; out->cand_leads = ctx->h_cand_leads.as<snfb_lead>();
     out->rnames = ctx->h_rnames.as<uint64_t>(); out->rnames_off = ctx->h_rn_off.as<uint32_t>(); out->task_coverage_mean = cm; out->unverified_breaks = c.unverified_breaks;
-    if (c.unverified_breaks) return fail(ctx, "a chain cut could not be verified (cluster stdev too large); rerun with a larger cut distance");
-    return 0;
 }
 
-static int run_stage_c(snfb_ctx* ctx) {
-    if (!ctx->stage_b_done) return fail(ctx, "snfb_cluster_call must run first");
+// ------------------------------------------------------------------------------------------------ the run loop
+// upto: 1 = stage A (+ sort and bins), 2 = + stage B and the consensus plan, 3 = + consensus.
+static int run_pipeline(snfb_ctx* ctx, int upto, snfb_lead_view* leads, snfb_cand_view* cands, snfb_seq_view* seqs) {
+    if (!ctx->loaded) return fail(ctx, "no records loaded");
+    if (!ctx->have_cfg) return fail(ctx, "snfb_set_config was not called");
     cudaSetDevice(ctx->device);
-    if (ctx->n_bound == 0) return 0;
-    consensus::C c{};
-    c.cand = ctx->b_cand.as<snfb_cand>(); c.cand_rw = ctx->b_cand.as<snfb_cand>(); c.cand_leads = ctx->b_cand_leads.as<snfb_lead>(); c.cand_lead_ml = ctx->b_cand_lead_ml.as<uint32_t>();
-    c.ml_plo = ctx->b_ml_plo.as<uint32_t>(); c.ml_pn = ctx->b_ml_pn.as<uint32_t>(); c.ord = ctx->b_ord.as<uint32_t>(); c.leads = ctx->b_leads.as<snfb_lead>(); c.rec = ctx->d_rec; c.seq = ctx->d_seq;
-    c.plan_best = ctx->b_plan_best.as<uint32_t>(); c.plan_nother = ctx->b_plan_nother.as<uint32_t>(); c.plan_otot = ctx->b_plan_otot.as<uint32_t>(); c.alt_len = ctx->b_alt_len.as<uint32_t>(); c.scr_len = ctx->b_scr_len.as<uint32_t>();
-    c.alt_off = ctx->b_alt_off.as<uint32_t>(); c.scr_off = ctx->b_scr_off.as<uint32_t>(); c.cand_cap = ctx->cand_cap; c.ctr = ctx->b_ctr.as<DevCounters>(); c.cfg = ctx->cfg;
-    c.item_cap = ctx->cand_lead_cap; c.tile_cap = ctx->cand_cap + ctx->cand_lead_cap / 8 + 1024;
-    if (ctx->b_work_big.ensure(4 * ctx->cand_cap) || ctx->b_work_small.ensure(4 * ctx->cand_cap) || ctx->b_work_ctr.ensure(64) || ctx->b_items_big.ensure(16 * c.item_cap) || ctx->b_items_small.ensure(16 * c.item_cap)
-        || ctx->b_tiles.ensure(8 * c.tile_cap)) return fail(ctx, "out of device memory (consensus queue)");
-    c.work_big = ctx->b_work_big.as<uint32_t>(); c.work_small = ctx->b_work_small.as<uint32_t>(); c.work_ctr = ctx->b_work_ctr.as<uint32_t>();
-    c.items_big = ctx->b_items_big.as<consensus::C::Item>(); c.items_small = ctx->b_items_small.as<consensus::C::Item>(); c.tiles = ctx->b_tiles.as<uint2>();
-    CUDA_TRY(cudaMemsetAsync(c.work_ctr, 0, 64, ctx->st));
-    mark(ctx, "consensus_plan");
-    consensus::k_plan<<<grid_for(ctx->cand_cap, 128), 128, 0, ctx->st>>>(c); LAUNCHED(ctx, 1);
-    LAUNCHED(ctx, prims::exclusive_scan(c.alt_len, c.alt_off, ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->cand_cap, &c.ctr->n_alt_bytes, ctx->st));
-    LAUNCHED(ctx, prims::exclusive_scan(c.scr_len, c.scr_off, ctx->b_scan_tmp.as<uint32_t>(), nullptr, ctx->cand_cap, &c.ctr->n_seq_bytes, ctx->st));
-    mark(ctx, nullptr);
-    if (fetch_counters(ctx)) return 1;
-    if (ctx->want_cand_prefetch) {        // stage B's outputs are final: start their device -> host copy next to the consensus kernels
-        CUDA_TRY(cudaEventRecord(ctx->ev_copy, ctx->st)); CUDA_TRY(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_copy, 0));
-        if (cand_bulk_copy(ctx, ctx->st_copy)) return 1;
-        ctx->cand_prefetched = true;
-    }
-    if (ctx->h_ctr.n_seq_bytes > 0xfffffff0ull) return fail(ctx, "consensus scratch exceeds 64 GiB");
-    if (ctx->b_alt.ensure(ctx->h_ctr.n_alt_bytes + 16) || ctx->b_scr.ensure(ctx->h_ctr.n_seq_bytes * 16 + 64)) return fail(ctx, "out of device memory (consensus)");
-    c.alt = ctx->b_alt.as<uint8_t>(); c.scr = ctx->b_scr.as<uint8_t>(); c.alt_cap = ctx->h_ctr.n_alt_bytes; c.scr_cap16 = ctx->h_ctr.n_seq_bytes;
-    c.arena_off = nullptr;
-    if (ctx->seq_on_demand && ctx->h_ctr.n_cand) {
-        // seq on demand: the device lists the base slices it will read, the host gathers exactly those bytes from its
-        // arena into pinned staging, one H2D copy brings them in (PCIe bytes ~ algorithmic bytes instead of the whole arena)
-        mark(ctx, "seq_requests");
-        const unsigned long long req_cap = ctx->cand_lead_cap + 64;
-        if (ctx->b_seq_req.ensure(sizeof(consensus::SeqReq) * req_cap) || ctx->b_arena_off.ensure(4 * (ctx->lead_cap + 8))) return fail(ctx, "out of device memory (seq requests)");
-        DevCounters* ctr = ctx->b_ctr.as<DevCounters>();
-        CUDA_TRY(cudaMemsetAsync(&ctr->n_ev, 0, 16, ctx->st));          // n_ev / n_sa are free again after stage A: reuse as request / unit counters
-        consensus::k_seq_requests<<<grid_for(ctx->h_ctr.n_cand, 128), 128, 0, ctx->st>>>(c, ctx->b_seq_req.as<consensus::SeqReq>(), req_cap, ctx->b_arena_off.as<uint32_t>(), &ctr->n_ev, &ctr->n_sa); LAUNCHED(ctx, 1);
-        mark(ctx, nullptr);
-        if (fetch_counters(ctx)) return 1;
-        const unsigned long long nreq = ctx->h_ctr.n_ev, nunits = ctx->h_ctr.n_sa;
-        if (nreq > req_cap) return fail(ctx, "seq request list overflow");
-        if (ctx->h_seq_req.ensure(sizeof(consensus::SeqReq) * (nreq + 1)) || ctx->h_seq_arena.ensure(nunits * 16 + 64) || ctx->b_seq_arena.ensure(nunits * 16 + 64)) return fail(ctx, "out of memory (seq arena)");
-        if (nreq) {
-            CUDA_TRY(cudaMemcpyAsync(ctx->h_seq_req.p, ctx->b_seq_req.p, sizeof(consensus::SeqReq) * nreq, cudaMemcpyDeviceToHost, ctx->st));
-            CUDA_TRY(cudaStreamSynchronize(ctx->st));
-            const consensus::SeqReq* rq = ctx->h_seq_req.as<consensus::SeqReq>(); uint8_t* dst = ctx->h_seq_arena.as<uint8_t>(); const uint8_t* src = ctx->h_seq; const uint64_t nseq = ctx->n_seq;
-            #pragma omp parallel for schedule(static, 256)
-            for (long long i = 0; i < (long long)nreq; ++i) {
-                unsigned long long s0 = rq[i].src; unsigned long long nb = rq[i].nbytes; if (s0 > nseq) s0 = nseq; if (s0 + nb > nseq) nb = nseq - s0;
-                memcpy(dst + (size_t)rq[i].dst16 * 16, src + s0, (size_t)nb);
-            }
-            mark(ctx, "h2d_seq_slices", nunits * 16);
-            CUDA_TRY(cudaMemcpyAsync(ctx->b_seq_arena.p, ctx->h_seq_arena.p, nunits * 16, cudaMemcpyHostToDevice, ctx->st));
-            mark(ctx, nullptr);
+    for (uint32_t t = 0; t < ctx->n_task; ++t) if ((long long)ctx->tasks[t].contig_len / ctx->cfg.cluster_binsize >= (1ll << 26)) return fail(ctx, "contig_len / cluster_binsize must stay below 2^26 (bin field of the sort key)");
+    initial_caps(ctx);
+    ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false;
+    for (int attempt = 0; ; ++attempt) {
+        if (attempt == 6) return fail(ctx, "buffer capacities did not converge");
+        if (ensure_arenas(ctx)) return 1;
+        bind_inputs(ctx);
+        ctx->n_ev = ctx->n_ev_load;
+        cudaStream_t st = ctx->st; DevCounters* ctr = ctx->B.ctr;
+        if (enqueue_stage_a(ctx)) return 1;
+        bool mid = false, copies = false;
+        if (upto >= 2) {
+            if (enqueue_stage_b(ctx)) return 1;
+            // the host reads the counters on the copy stream while the consensus kernels run
+            CUDA_TRY(cudaEventRecord(ctx->ev_b, st)); CUDA_TRY(cudaStreamWaitEvent(ctx->st_copy, ctx->ev_b, 0));
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_mid, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, ctx->st_copy));
+            CUDA_TRY(cudaMemcpyAsync(ctx->h_work, ctx->Cc.work_ctr, 64, cudaMemcpyDeviceToHost, ctx->st_copy));
+            CUDA_TRY(cudaEventRecord(ctx->ev_mid, ctx->st_copy));
+            mid = true;
         }
-        ctx->seq_h2d_bytes = nunits * 16;
-        c.seq = ctx->b_seq_arena.as<uint8_t>(); c.arena_off = ctx->b_arena_off.as<uint32_t>();
+        if (upto >= 3 && !ctx->seq_on_demand) { if (enqueue_stage_c(ctx)) return 1; }
+        if (mid) {
+            CUDA_TRY(cudaEventSynchronize(ctx->ev_mid));
+            if (ctx->h_mid->bad_records) { cudaStreamSynchronize(st); return fail(ctx, "the record block is malformed: a record points outside its task table or arenas"); }
+            if (ctx->h_mid->unsorted) { cudaStreamSynchronize(st); return fail(ctx, "records are not coordinate sorted inside a task"); }
+            if (ctx->h_mid->ordinal_overflow) { cudaStreamSynchronize(st); return fail(ctx, "a read carries more than 65535 SV signatures (16-bit lead ordinal)"); }
+            if (!caps_fit(ctx, *ctx->h_mid, ctx->h_work, 2)) { CUDA_TRY(cudaStreamSynchronize(st)); ++ctx->reruns; continue; }
+            if (ctx->h_mid->unverified_breaks && !ctx->force_no_cuts) { CUDA_TRY(cudaStreamSynchronize(st)); ctx->force_no_cuts = true; ++ctx->reruns; continue; }   // a chain cut was wrong: redo with whole chains
+            if (cands) { if (enqueue_cand_copies(ctx, *ctx->h_mid, ctx->st_copy)) return 1; copies = true; }
+            if (upto >= 3 && ctx->seq_on_demand) { if (enqueue_stage_c(ctx)) return 1; }
+        }
+        if (upto >= 3 && seqs) {
+            const unsigned long long na = ctx->h_mid->n_alt_bytes;
+            if (ctx->h_alt.ensure(na + 16)) return fail(ctx, "out of pinned memory for the ALT arena");
+            if (na) CUDA_TRY(cudaMemcpyAsync(ctx->h_alt.p, ctx->Cc.alt, na, cudaMemcpyDeviceToHost, st));
+        }
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_fin, ctr, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->h_work + 16, ctx->Cc.work_ctr, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (copies) CUDA_TRY(cudaStreamSynchronize(ctx->st_copy));
+        CUDA_TRY(cudaGetLastError());
+        if (ctx->h_fin->bad_records) return fail(ctx, "the record block is malformed: a record points outside its task table or arenas");
+        if (ctx->h_fin->unsorted) return fail(ctx, "records are not coordinate sorted inside a task");
+        if (ctx->h_fin->ordinal_overflow) return fail(ctx, "a read carries more than 65535 SV signatures (16-bit lead ordinal)");
+        if (!caps_fit(ctx, *ctx->h_fin, upto >= 2 ? ctx->h_work + 16 : ctx->h_work, upto)) { ++ctx->reruns; continue; }
+        break;
     }
-    if (ctx->h_ctr.n_cand) {
-        mark(ctx, "consensus", ctx->h_ctr.n_seq_bytes * 16);
-        consensus::k_prep<<<148 * 8, 128, 0, ctx->st>>>(c);
-        mark(ctx, "consensus_align");
-        consensus::k_align<<<148 * 8, consensus::ALIGN_WARPS * 32, 0, ctx->st>>>(c);
-        mark(ctx, "consensus_vote");
-        consensus::k_vote<<<148 * 16, consensus::VOTE_THREADS, 0, ctx->st>>>(c); LAUNCHED(ctx, 3);
-        mark(ctx, nullptr);
-    }
-    CUDA_TRY(cudaGetLastError());
+    ctx->stage_a_done = true; ctx->stage_b_done = upto >= 2; ctx->stage_c_done = upto >= 3;
+    if (leads) { memset(leads, 0, sizeof *leads); if (fill_lead_view(ctx, leads)) return 1; }
+    if (cands) { memset(cands, 0, sizeof *cands); finish_cand_view(ctx, *ctx->h_fin, cands); }
+    if (seqs) { memset(seqs, 0, sizeof *seqs); seqs->n_alt_bytes = ctx->h_fin->n_alt_bytes; seqs->alt = ctx->h_alt.as<uint8_t>(); }
     return 0;
 }
 
-static int fill_seq_view(snfb_ctx* ctx, snfb_seq_view* out, snfb_cand_view* cands) {
-    const unsigned long long na = ctx->h_ctr.n_alt_bytes;
-    if (ctx->h_alt.ensure(na + 16)) return fail(ctx, "out of pinned memory for the ALT arena");
-    if (na) CUDA_TRY(cudaMemcpyAsync(ctx->h_alt.p, ctx->b_alt.p, na, cudaMemcpyDeviceToHost, ctx->st));
-    (void)cands;
-    if (ctx->h_ctr.n_cand && ctx->h_cand.p && ctx->h_cand.cap >= sizeof(snfb_cand) * ctx->h_ctr.n_cand) CUDA_TRY(cudaMemcpyAsync(ctx->h_cand.p, ctx->b_cand.p, sizeof(snfb_cand) * ctx->h_ctr.n_cand, cudaMemcpyDeviceToHost, ctx->st));   // alt_off/alt_len
-    CUDA_TRY(cudaStreamSynchronize(ctx->st));
-    if (fetch_counters(ctx)) return 1;
-    if (ctx->h_ctr.scratch_overflow) return fail(ctx, "consensus buffers overflowed");
-    if (out) { out->n_alt_bytes = na; out->alt = ctx->h_alt.as<uint8_t>(); }
-    return 0;
-}
+extern "C" {
 
 int snfb_extract_leads(snfb_ctx* ctx, snfb_lead_view* out) {
     if (!ctx) return 1;
-    ctx->n_ev = ctx->n_ev_load;          // keep the h2d interval of the last load
-    if (run_stage_a(ctx)) return 1;
-    if (out) { memset(out, 0, sizeof *out); if (fill_lead_view(ctx, out)) return 1; }
-    return 0;
+    return run_pipeline(ctx, 1, out, nullptr, nullptr);
 }
 int snfb_cluster_call(snfb_ctx* ctx, snfb_cand_view* out) {
     if (!ctx) return 1;
-    if (run_stage_b(ctx)) return 1;
-    if (out) { memset(out, 0, sizeof *out); if (fill_cand_view(ctx, out)) return 1; }
-    return 0;
+    if (!ctx->stage_a_done) return fail(ctx, "snfb_extract_leads must run first");
+    return run_pipeline(ctx, 2, nullptr, out, nullptr);
 }
 int snfb_consensus(snfb_ctx* ctx, snfb_seq_view* out) {
     if (!ctx) return 1;
-    if (run_stage_c(ctx)) return 1;
-    if (out) { memset(out, 0, sizeof *out); }
-    return fill_seq_view(ctx, out, nullptr);
+    if (!ctx->stage_b_done) return fail(ctx, "snfb_cluster_call must run first");
+    snfb_seq_view tmp; return run_pipeline(ctx, 3, nullptr, nullptr, out ? out : &tmp);
 }
 int snfb_run(snfb_ctx* ctx, snfb_lead_view* leads, snfb_cand_view* cands, snfb_seq_view* seqs) {
     if (!ctx) return 1;
-    ctx->n_ev = ctx->n_ev_load;
-    ctx->want_cand_prefetch = cands != nullptr; ctx->cand_prefetched = false;
-    const int rc = run_stage_a(ctx) || run_stage_b(ctx) || run_stage_c(ctx);
-    ctx->want_cand_prefetch = false;
-    if (rc) { if (ctx->cand_prefetched) { cudaStreamSynchronize(ctx->st_copy); ctx->cand_prefetched = false; } return 1; }
-    if (leads) { memset(leads, 0, sizeof *leads); if (fill_lead_view(ctx, leads)) return 1; }
-    if (cands) { memset(cands, 0, sizeof *cands); if (fill_cand_view(ctx, cands, true)) return 1; }
-    if (seqs) memset(seqs, 0, sizeof *seqs);
-    if (fill_seq_view(ctx, seqs, cands)) return 1;
-    if (!cands) { if (ctx->h_ctr.unverified_breaks) return fail(ctx, "a chain cut could not be verified"); }
-    return 0;
+    snfb_seq_view tmp; return run_pipeline(ctx, 3, leads, cands, seqs ? seqs : &tmp);
 }
 
 int snfb_last_timings(snfb_ctx* ctx, const char** names, float* ms, uint64_t* bytes, int cap) {
@@ -650,7 +796,7 @@ int snfb_last_timings(snfb_ctx* ctx, const char** names, float* ms, uint64_t* by
         float t = 0; if (cudaEventElapsedTime(&t, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) t = -1.f;
         names[n] = ctx->ev_name[i]; ms[n] = t; if (bytes) bytes[n] = ctx->ev_bytes[i]; ++n;
     }
-    if (ctx->n_ev - ctx->n_ev_load >= 2 && n < cap) {   // first stage mark .. last mark: device time of the run including its host round trips
+    if (ctx->n_ev - ctx->n_ev_load >= 2 && n < cap) {   // first stage mark .. last mark: device time of the run
         float t = 0; if (cudaEventElapsedTime(&t, ctx->ev[ctx->n_ev_load], ctx->ev[ctx->n_ev - 1]) != cudaSuccess) t = -1.f;
         names[n] = "total"; ms[n] = t; if (bytes) bytes[n] = 0; ++n;
     }
@@ -659,15 +805,120 @@ int snfb_last_timings(snfb_ctx* ctx, const char** names, float* ms, uint64_t* by
 
 int snfb_device_candidates(snfb_ctx* ctx, void** dptr, uint64_t* n_cand) {
     if (!ctx || !ctx->stage_b_done) return 1;
-    if (dptr) *dptr = ctx->b_cand.p; if (n_cand) *n_cand = ctx->h_ctr.n_cand; return 0;
+    if (dptr) *dptr = ctx->B.cand; if (n_cand) *n_cand = ctx->h_fin->n_cand; return 0;
 }
-
 int snfb_device_alt(snfb_ctx* ctx, void** dptr, uint64_t* n_bytes) {
-    if (!ctx || !ctx->stage_b_done) return 1;
-    if (dptr) *dptr = ctx->b_alt.p; if (n_bytes) *n_bytes = ctx->h_ctr.n_alt_bytes; return 0;
+    if (!ctx || !ctx->stage_c_done) return 1;
+    if (dptr) *dptr = ctx->Cc.alt; if (n_bytes) *n_bytes = ctx->h_fin->n_alt_bytes; return 0;
 }
 uint64_t snfb_launch_count(snfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t snfb_rerun_count(snfb_ctx* ctx) { return ctx ? ctx->reruns : 0; }
 int snfb_pin_host(void* p, size_t bytes) { return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1; }
 int snfb_unpin_host(void* p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : 1; }
+
+int snfb_nccl_unique_id(void* out128) {
+    std::string e; if (!out128 || !nccl_load(&e)) return 1;
+    Id128 id; memset(&id, 0, sizeof id);
+    if (g_nccl.GetUniqueId(&id) != 0) return 2;
+    memcpy(out128, &id, 128); return 0;
+}
+int snfb_comm_init(snfb_ctx* ctx, const void* unique_id128, int rank, int nranks) {
+    if (!ctx || !unique_id128 || nranks < 1 || rank < 0 || rank >= nranks) return 1;
+    std::string e; if (!nccl_load(&e)) return fail(ctx, "NCCL: " + e);
+    cudaSetDevice(ctx->device);
+    if (ctx->comm) { g_nccl.CommDestroy(ctx->comm); ctx->comm = nullptr; }
+    Id128 id; memcpy(&id, unique_id128, 128);
+    const int rc = g_nccl.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (rc != 0) { ctx->comm = nullptr; return fail(ctx, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error")); }
+    ctx->rank = rank; ctx->nranks = nranks; ctx->gather_cap = 0; return 0;
+}
+int snfb_allgather_candidates(snfb_ctx* ctx, uint32_t flags, snfb_gather_view* out) {
+    if (!ctx || !out) return 1;
+    if (!ctx->stage_c_done) return fail(ctx, "snfb_run must run first");
+    if (ctx->nranks > 1 && !ctx->comm) return fail(ctx, "snfb_comm_init was not called");
+    cudaSetDevice(ctx->device);
+    const int nr = ctx->nranks, with_leads = (flags & SNFB_GATHER_LEADS) ? 1 : 0; cudaStream_t st = ctx->st; cluster::B& b = ctx->B;
+    memset(out, 0, sizeof *out);
+    if (ctx->h_gather.ensure(64 * 8 + (size_t)nr * (sizeof(GatherHdr) + 8) + 256)) return fail(ctx, "out of pinned memory (gather)");
+    unsigned long long* h_layout = ctx->h_gather.as<unsigned long long>();                   // [8] layout, then the header table
+    GatherHdr* h_hdr = reinterpret_cast<GatherHdr*>(h_layout + 8);
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if (ctx->gather_cap == 0) {
+            // first call: the slot size every rank uses is agreed through a small all-gather of what each rank needs
+            const DevCounters& c = *ctx->h_fin; GatherHdr h{}; h.n_cand = c.n_cand; h.n_alt = c.n_alt_bytes; h.n_rn = c.n_rnames; h.n_leads = with_leads ? c.n_cand_leads : 0;
+            unsigned long long off[6]; gather_offsets(h, off);
+            unsigned long long mx = off[5];
+            if (nr > 1) {
+                if (ctx->b_gsend.ensure(256) || ctx->b_grecv.ensure(8 * (size_t)nr + 256)) return fail(ctx, "out of device memory (gather)");
+                CUDA_TRY(cudaMemcpyAsync(ctx->b_gsend.p, &off[5], 8, cudaMemcpyHostToDevice, st));
+                if (g_nccl.AllGather(ctx->b_gsend.p, ctx->b_grecv.p, 8, 0 /* ncclChar */, ctx->comm, st) != 0) return fail(ctx, "ncclAllGather (sizes) failed");
+                std::vector<unsigned long long> all(nr);
+                CUDA_TRY(cudaMemcpyAsync(all.data(), ctx->b_grecv.p, 8 * (size_t)nr, cudaMemcpyDeviceToHost, st)); CUDA_TRY(cudaStreamSynchronize(st));
+                for (int r = 0; r < nr; ++r) mx = std::max(mx, all[r]);
+            }
+            ctx->gather_cap = (grown(mx) + 255ull) & ~255ull;
+        }
+        const unsigned long long cap = ctx->gather_cap, out_cap = (unsigned long long)nr * cap + 4096ull * 8;
+        if (ctx->b_gsend.ensure(cap + 256) || ctx->b_grecv.ensure((size_t)nr * cap + out_cap + 1024)) return fail(ctx, "out of device memory (gather)");
+        uint8_t* recv = ctx->b_grecv.as<uint8_t>(); uint8_t* merged = recv + (((size_t)nr * cap + 255) & ~(size_t)255); unsigned long long* d_layout = reinterpret_cast<unsigned long long*>(merged + out_cap);     // layout words live behind the merged arrays
+        mark(ctx, "allgather");
+        k_gather_pack<<<148 * 4, 256, 0, st>>>(b.ctr, b.cand, ctx->Cc.alt, b.rnames, b.rn_off_out, b.cand_leads, with_leads, nr > 1 ? ctx->b_gsend.as<uint8_t>() : recv, cap); LAUNCHED(ctx, 1);
+        if (nr > 1 && g_nccl.AllGather(ctx->b_gsend.p, recv, cap, 0 /* ncclChar */, ctx->comm, st) != 0) return fail(ctx, "ncclAllGather failed");
+        k_gather_merge<<<148 * 4, 256, 0, st>>>(recv, cap, nr, with_leads, merged, out_cap, d_layout); LAUNCHED(ctx, 1);
+        mark(ctx, nullptr);
+        CUDA_TRY(cudaMemcpyAsync(h_layout, d_layout, 64, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(h_hdr, recv, sizeof(GatherHdr), cudaMemcpyDeviceToHost, st));     // slot 0's header; the rest below
+        for (int r = 1; r < nr; ++r) CUDA_TRY(cudaMemcpyAsync(h_hdr + r, recv + (size_t)r * cap, sizeof(GatherHdr), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        unsigned long long mx = 0; for (int r = 0; r < nr; ++r) mx = std::max(mx, h_hdr[r].need_bytes);
+        if (h_layout[6]) { ctx->gather_cap = (grown(mx) + 255ull) & ~255ull; ++ctx->reruns; continue; }          // every rank sees the same table: the same new slot size everywhere
+        // next call: a slot size every rank derives from the same table
+        if (grown(mx) > cap) ctx->gather_cap = (grown(mx) + 255ull) & ~255ull;
+        GatherHdr tot{}; for (int r = 0; r < nr; ++r) { tot.n_cand += h_hdr[r].n_cand; tot.n_alt += h_hdr[r].n_alt; tot.n_rn += h_hdr[r].n_rn; tot.n_leads += h_hdr[r].n_leads; }
+        uint64_t* rank_n = reinterpret_cast<uint64_t*>(h_hdr + nr); for (int r = 0; r < nr; ++r) rank_n[r] = h_hdr[r].n_cand;
+        out->n_cand = tot.n_cand; out->n_alt_bytes = tot.n_alt; out->n_rnames = tot.n_rn; out->n_cand_leads = tot.n_leads; out->rank_n_cand = rank_n;
+        out->dev_buffer = merged; out->dev_bytes_per_rank = cap;
+        if (!(flags & SNFB_GATHER_DEVICE_ONLY)) {
+            const unsigned long long total = h_layout[5];
+            if (ctx->h_gather.cap < 64 * 8 + (size_t)nr * (sizeof(GatherHdr) + 8) + 256 + total + 512) {
+                // grow while keeping the table: copy it aside
+                std::vector<uint8_t> keep((size_t)64 * 8 + (size_t)nr * (sizeof(GatherHdr) + 8)); memcpy(keep.data(), ctx->h_gather.p, keep.size());
+                if (ctx->h_gather.ensure(64 * 8 + (size_t)nr * (sizeof(GatherHdr) + 8) + 256 + total + 512)) return fail(ctx, "out of pinned memory (gather result)");
+                memcpy(ctx->h_gather.p, keep.data(), keep.size());
+                h_layout = ctx->h_gather.as<unsigned long long>(); h_hdr = reinterpret_cast<GatherHdr*>(h_layout + 8); rank_n = reinterpret_cast<uint64_t*>(h_hdr + nr); out->rank_n_cand = rank_n;
+            }
+            uint8_t* hm = ctx->h_gather.as<uint8_t>() + (((size_t)64 * 8 + (size_t)nr * (sizeof(GatherHdr) + 8) + 255) & ~(size_t)255);
+            CUDA_TRY(cudaMemcpyAsync(hm, merged, total, cudaMemcpyDeviceToHost, st)); CUDA_TRY(cudaStreamSynchronize(st));
+            out->cand = reinterpret_cast<const snfb_cand*>(hm + h_layout[0]); out->alt = hm + h_layout[1]; out->rnames = reinterpret_cast<const uint64_t*>(hm + h_layout[2]);
+            out->rnames_off = reinterpret_cast<const uint32_t*>(hm + h_layout[3]); out->cand_leads = with_leads ? reinterpret_cast<const snfb_lead*>(hm + h_layout[4]) : nullptr;
+        }
+        return 0;
+    }
+    return fail(ctx, "gather buffer sizes did not converge");
+}
+
+// mean coverage of `binsize`-base bins over one task's region (snf.py:248-267: the 500-bp means the SNF writer stores)
+int snfb_coverage_bins(snfb_ctx* ctx, uint32_t task, int binsize, const double** out, uint64_t* n_bins) {
+    if (!ctx || !ctx->stage_a_done) return ctx ? fail(ctx, "snfb_extract_leads must run first") : 1;
+    if (task >= ctx->n_task || binsize <= 0 || !out || !n_bins) return fail(ctx, "bad arguments");
+    cudaSetDevice(ctx->device);
+    const snfb_task& tk = ctx->tasks[task];
+    // the reference pads the contig-long coverage vector with zeros to a multiple of the bin size and takes row means (snf.py:255-256)
+    const long long L = tk.contig_len; const long long nb = L > 0 ? (L + binsize - 1) / binsize : 0;
+    if (ctx->h_cov_bins.ensure(16 * (size_t)(nb + 1))) return fail(ctx, "out of pinned memory (coverage bins)");
+    DevBuf acc; if (acc.ensure(8 * (size_t)(nb + 1))) return fail(ctx, "out of device memory (coverage bins)");
+    CUDA_TRY(cudaMemsetAsync(acc.p, 0, 8 * (size_t)(nb + 1), ctx->st));
+    uint32_t lohi[2];
+    CUDA_TRY(cudaMemcpyAsync(&lohi[0], ctx->task_first + task, 4, cudaMemcpyDeviceToHost, ctx->st)); CUDA_TRY(cudaMemcpyAsync(&lohi[1], ctx->task_last + task, 4, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(cudaStreamSynchronize(ctx->st));
+    if (nb && lohi[1] > lohi[0]) { k_cov_bins<<<grid_for(lohi[1] - lohi[0], 256), 256, 0, ctx->st>>>(ctx->rec_pos, ctx->rec_end, ctx->rec_flags, lohi[0], lohi[1], binsize, L, nb, acc.as<unsigned long long>()); LAUNCHED(ctx, 1); }
+    unsigned long long* raw = reinterpret_cast<unsigned long long*>(ctx->h_cov_bins.as<uint8_t>() + 8 * (size_t)(nb + 1));
+    CUDA_TRY(cudaMemcpyAsync(raw, acc.p, 8 * (size_t)nb, cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(cudaStreamSynchronize(ctx->st));
+    acc.release();
+    double* o = ctx->h_cov_bins.as<double>();
+    for (long long i = 0; i < nb; ++i) o[i] = (double)raw[i] / (double)binsize;
+    *out = o; *n_bins = (uint64_t)nb; return 0;
+}
 
 }  // extern "C"

@@ -23,6 +23,11 @@ struct DevCounters {
     unsigned long long n_alt_bytes, n_seq_bytes, scratch_overflow;
     unsigned long long n_slots;        // high-water mark of the lead slot allocator (>= n_leads: warps reserve chunks)
     unsigned long long n_ev, n_sa;     // event slices / records with an SA tag found by k_scan
+    unsigned long long n_kl, n_kll;    // kept leads / kept "long" leads
+    unsigned long long n_big;          // clusters handled by a whole block
+    unsigned long long ordinal_overflow;   // reads with more than 65535 leads (the ordinal is a 16-bit field)
+    unsigned long long bad_records;    // records whose offsets point outside the block's arenas or tables (snfb_load_records fails)
+    unsigned long long n_items, n_tiles, n_req, n_req_units;   // consensus work items / vote tiles / seq-on-demand requests
 };
 
 // ---------------------------------------------------------------- small utilities

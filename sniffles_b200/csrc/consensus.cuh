@@ -13,10 +13,11 @@ constexpr int TAB = 2048;                  // > 4 x the at most ~500 strided k-m
 constexpr uint8_t DASH = 0xff;
 
 struct C {
-    const snfb_cand* cand; snfb_cand* cand_rw; const snfb_lead* cand_leads; const uint32_t* cand_lead_ml;
-    const uint32_t* ml_plo; const uint32_t* ml_pn; const uint32_t* ord; const snfb_lead* leads;
+    const snfb_cand* cand; snfb_cand* cand_rw; const snfb_lead* cand_leads;
+    const uint32_t* out_plo; const uint32_t* out_pn;     // per candidate lead: the run of `ord` entries (merge_inner parts) it was folded from
+    const uint32_t* ord; const snfb_lead* kleads;         // kept-lead indices in merge_inner order, the kept leads
     const snfb_rec* rec; const uint8_t* seq;
-    const uint32_t* arena_off;       // seq on demand: per lead slot, 16-byte unit offset of its bytes in `seq` (which then is the compact arena); nullptr = full arena
+    const uint32_t* arena_off;       // seq on demand: per kept lead, 16-byte unit offset of its bytes in `seq` (which then is the compact arena); nullptr = full arena
     uint32_t* plan_best; uint32_t* plan_nother; uint32_t* plan_otot; uint32_t* alt_len; uint32_t* scr_len; uint32_t* alt_off; uint32_t* scr_off;   // scr in units of 16 bytes
     uint8_t* alt; uint8_t* scr; unsigned long long alt_cap, scr_cap16, cand_cap;
     uint32_t* work_big; uint32_t* work_small; uint32_t* work_ctr;      // work_ctr: [0] n_big, [1] n_small, [2],[3] queue positions, [4] n_items_big, [5] n_items_small, [6],[7] item queue positions, [8] n_tiles, [9] tile queue position
@@ -31,9 +32,9 @@ __device__ __forceinline__ uint8_t seq_code(const uint8_t* sq, long long q) { co
 // choose the best read, size the outputs
 __global__ void k_plan(C c) {
     const unsigned long long nc = c.ctr->n_cand < c.cand_cap ? c.ctr->n_cand : c.cand_cap;
-    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < c.cand_cap; i += (unsigned long long)gridDim.x * blockDim.x) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nc; i += (unsigned long long)gridDim.x * blockDim.x) {
         uint32_t al = 0, sl = 0;
-        if (i < nc && c.cand[i].svtype == SNFB_INS && !c.cfg.symbolic) {
+        if (c.cand[i].svtype == SNFB_INS && !c.cfg.symbolic) {
             const snfb_cand* cd = &c.cand[i]; long nm = 0, bi = -1; long long bd = 0; long long tot = 0;
             for (int k = 0; k < cd->lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ)) continue;
                 // abs(len(seq) - svlen) + abs(ref_start - pos) * 1.5, compared exactly in halves
@@ -67,6 +68,13 @@ __global__ void k_plan(C c) {
     }
 }
 
+// the candidate records are final once the ALT offsets are known (stage C only fills the ALT bytes)
+__global__ void k_plan_finish(C c) {
+    const unsigned long long nc = c.ctr->n_cand < c.cand_cap ? c.ctr->n_cand : c.cand_cap;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < nc; i += (unsigned long long)gridDim.x * blockDim.x)
+        if (c.scr_len[i]) c.cand_rw[i].alt_off = (int)c.alt_off[i];
+}
+
 // unpack `len` bases starting at nibble `off` of sq into dst (one code per byte); `tid`/`nthr` = cooperating threads.
 // Each thread takes 8 consecutive bases per step and four steps are kept in flight so that the 4-bit arena is
 // streamed from HBM with enough loads outstanding.
@@ -86,10 +94,10 @@ __device__ __forceinline__ void unpack_span(const uint8_t* __restrict__ sq, long
 }
 // unpack the (possibly merged) sequence of candidate lead `cl_index` as 4-bit codes, one byte per base
 __device__ inline void unpack_lead(const C& c, uint32_t cl_index, uint8_t* dst) {
-    const uint32_t mi = c.cand_lead_ml[cl_index]; const uint32_t plo = c.ml_plo[mi], pn = c.ml_pn[mi];
+    const uint32_t plo = c.out_plo[cl_index], pn = c.out_pn[cl_index];
     long long o = 0;
     for (uint32_t p = 0; p < pn; ++p) {
-        const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.leads[slot];
+        const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.kleads[slot];
         const uint8_t* sq = c.arena_off ? c.seq + (size_t)c.arena_off[slot] * 16 : c.seq + c.rec[l->rec].seq_off;
         unpack_span(sq, c.arena_off ? (l->seq_off & 1) : l->seq_off, l->seq_len, dst + o, threadIdx.x, blockDim.x);
         o += l->seq_len;
@@ -109,9 +117,9 @@ __global__ void k_seq_requests(C c, SeqReq* req, unsigned long long req_cap, uin
         for (int k = 0; k < cd->lead_n; ++k) {
             const snfb_lead* cl = &c.cand_leads[cd->lead_off + k];
             if (!(cl->flags & SNFB_LF_HAS_SEQ) || (!cons && (uint32_t)k != c.plan_best[i])) continue;
-            const uint32_t mi = c.cand_lead_ml[cd->lead_off + k];
-            for (uint32_t p = 0; p < c.ml_pn[mi]; ++p) {
-                const uint32_t slot = c.ord[c.ml_plo[mi] + p]; const snfb_lead* l = &c.leads[slot];
+            const uint32_t plo = c.out_plo[cd->lead_off + k], pn = c.out_pn[cd->lead_off + k];
+            for (uint32_t p = 0; p < pn; ++p) {
+                const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.kleads[slot];
                 const unsigned long long b0 = (unsigned long long)l->seq_off >> 1, b1 = ((unsigned long long)l->seq_off + l->seq_len + 1) >> 1;
                 const uint32_t nb = (uint32_t)(b1 - b0) + 1;                                  // +1: unpack_span may touch one byte past the last base
                 const unsigned long long u = atomicAdd(n_units, (unsigned long long)((nb + 15) / 16));
@@ -127,10 +135,10 @@ constexpr int MAXHIT = 512;       // strided k-mer hits of one read are bounded 
 
 // the same with the calling warp only
 __device__ inline void unpack_lead_warp(const C& c, uint32_t cl_index, uint8_t* dst) {
-    const uint32_t mi = c.cand_lead_ml[cl_index]; const uint32_t plo = c.ml_plo[mi], pn = c.ml_pn[mi];
+    const uint32_t plo = c.out_plo[cl_index], pn = c.out_pn[cl_index];
     long long o = 0;
     for (uint32_t p = 0; p < pn; ++p) {
-        const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.leads[slot];
+        const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.kleads[slot];
         const uint8_t* sq = c.arena_off ? c.seq + (size_t)c.arena_off[slot] * 16 : c.seq + c.rec[l->rec].seq_off;
         unpack_span(sq, c.arena_off ? (l->seq_off & 1) : l->seq_off, l->seq_len, dst + o, lane_id(), 32);
         o += l->seq_len;
@@ -211,7 +219,6 @@ __global__ void __launch_bounds__(128) k_prep(C c) {
         const snfb_cand cd = c.cand[ci];
         uint32_t* tk; int* tp; uint8_t* best = cand_table(c, ci, &tk, &tp);
         unpack_lead(c, cd.lead_off + c.plan_best[ci], best);
-        if (threadIdx.x == 0) c.cand_rw[ci].alt_off = (int)c.alt_off[ci];
         const uint32_t no = c.plan_nother[ci];
         if (no == 0 || L == 0) { __syncthreads(); uint8_t* out = c.alt + c.alt_off[ci]; for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) out[h] = (uint8_t)CODE[best[h]]; continue; }
         for (int i = threadIdx.x; i < TAB; i += blockDim.x) { tk[i] = 0xffffffffu; tp[i] = -1; }
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
     for (;;) {
         uint32_t q = 0; if (lane == 0) q = atomicAdd(&c.work_ctr[6], 1u);
         q = __shfl_sync(FULL, q, 0);
-        const uint32_t nb = c.work_ctr[4], ns = c.work_ctr[5];
+        const uint32_t nb = (uint32_t)min((unsigned long long)c.work_ctr[4], c.item_cap), ns = (uint32_t)min((unsigned long long)c.work_ctr[5], c.item_cap);
         if (q >= nb + ns) break;
         const C::Item it = q < nb ? c.items_big[q] : c.items_small[q - nb];
         const uint32_t ci = it.cand; const uint32_t L = c.alt_len[ci];

@@ -277,7 +277,7 @@ struct RecClip { int32_t alen, qas, clip_left, clip_right; };                   
 constexpr uint32_t RM_PASS = 1u << 24, RM_HAS_NM = 1u << 25, RM_HAS_SA = 1u << 26;   // RecScan.meta: task (0..15) | mapq (16..23) | flags | hp (27..28)
 
 struct IndexParams {
-    const snfb_rec* rec; const uint16_t* cigar; const snfb_task* task; uint32_t n_rec;
+    const snfb_rec* rec; const uint16_t* cigar; const snfb_task* task; uint32_t n_rec; uint32_t n_task; unsigned long long n_cigar;
     int32_t* rec_pos; uint32_t* task_first; uint32_t* task_last;
     RecScan* scan; RecClip* clip; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
     DevCounters* ctr; int mapq_min, alen_min, excl, want_nm;
@@ -290,9 +290,14 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     const int task = (int)c0.x, pos = (int)c0.y; const unsigned flag = c0.z & 0xffffu, mapq = (c0.z >> 16) & 255u, aux = c0.z >> 24; unsigned hp = c0.w & 255u;
     const int nm = (int)c1.x; const uint32_t n = c1.z; const int l_seq = (int)c1.w;
     const unsigned long long cigar_off = (unsigned long long)c2.z | ((unsigned long long)c2.w << 32);
+    if ((uint32_t)task >= P.n_task || (cigar_off & 7) || cigar_off + n > P.n_cigar) {      // malformed record (counted by k_validate: the run fails); touch nothing through its offsets
+        RecScan s; s.cig8 = 0; s.n_words = 0; s.pos = pos; s.meta = 0; *reinterpret_cast<uint4*>(P.scan + i) = *reinterpret_cast<const uint4*>(&s);
+        RecClip c; c.alen = 0; c.qas = 0; c.clip_left = 0; c.clip_right = 0; *reinterpret_cast<int4*>(P.clip + i) = *reinterpret_cast<const int4*>(&c);
+        P.rec_pos[i] = pos; P.rec_flags[i] = 0; P.rec_nm[i] = -1.0; P.rec_end[i] = -1; P.rec_nlead[i] = 0; return;
+    }
     P.rec_pos[i] = pos;
     if (i == 0) P.task_first[task] = 0;
-    else { const int2 pv = __ldg(reinterpret_cast<const int2*>(P.rec + i - 1)); if (pv.x != task) { P.task_first[task] = i; P.task_last[pv.x] = i; } else if (pv.y > pos) atomicAdd(&P.ctr->unsorted, 1ULL); }
+    else { const int2 pv = __ldg(reinterpret_cast<const int2*>(P.rec + i - 1)); if (pv.x != task) { P.task_first[task] = i; if ((uint32_t)pv.x < P.n_task) P.task_last[pv.x] = i; } else if (pv.y > pos) atomicAdd(&P.ctr->unsorted, 1ULL); }
     if (i + 1 == P.n_rec) P.task_last[task] = P.n_rec;
     // clips at the two ends
     const uint16_t* cg = P.cigar + cigar_off;
@@ -447,6 +452,7 @@ __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanPar
         #undef WORD_BODY
         #undef LOAD_SLICE
         if (lane == 0) {
+            if (nlead > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL);       // the per-read lead ordinal is a 16-bit field of the lead and of the sort order
             P.rec_end[rec] = pos_r; P.rec_nlead[rec] = nlead; P.rec_big[rec] = (int)big;
             if (d.w & RM_HAS_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = rec; }
         }
@@ -568,7 +574,7 @@ __global__ void __launch_bounds__(SA_THREADS) k_sa(const SaParams P) {
         a.leads = P.leads; a.lead_cap = P.lead_cap; a.n_slots = &P.ctr->n_slots; a.slots = &slots;
         a.mapq_min = s_cfg.mapq; a.dev_keep_lowqual_splits = s_cfg.dev_keep_lowqual_splits; a.max_splits_base = s_cfg.max_splits_base; a.max_splits_kb = s_cfg.max_splits_kb;
         const unsigned added = process_sa(&s_cfg, sg, a, &soft, &overflow);
-        if (added) P.rec_nlead[rec] += added;
+        if (added) { if (a.nlead + added > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL); P.rec_nlead[rec] += added; }
     }
     for (unsigned long long sidx = slots.cur; sidx < slots.end; ++sidx) if (sidx < P.lead_cap) P.leads[sidx].rec = HOLE;   // retire the last chunk
     if (soft) atomicAdd(&P.ctr->soft_errors, soft);

@@ -27,10 +27,10 @@ def test_exports_match_header():
 
 def test_struct_sizes():
     L = binding.lib()
-    assert L.snfb_version() == 2
+    assert L.snfb_version() == 3
     want = [abi.REC_DTYPE.itemsize, abi.TASK_DTYPE.itemsize, abi.CONTIG_DTYPE.itemsize, C.sizeof(abi.Records), C.sizeof(abi.Config),
-            abi.LEAD_DTYPE.itemsize, abi.CAND_DTYPE.itemsize]
-    assert [L.snfb_sizeof(i) for i in range(7)] == want
+            abi.LEAD_DTYPE.itemsize, abi.CAND_DTYPE.itemsize, C.sizeof(abi.GatherView)]
+    assert [L.snfb_sizeof(i) for i in range(8)] == want
 
 
 def test_hash_name_matches_python():

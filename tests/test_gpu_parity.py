@@ -126,3 +126,35 @@ def test_reference_bnd_vectors_on_device(prefix):
         assert got.get(i) == e["lead"], (i, e, got.get(i))
     if prefix == "hg008":
         assert sum(e["lead"] is not None for e in exp) == 8
+
+
+def test_coverage_bins_match_numpy():
+    """snfb_coverage_bins = the reshape-mean of the per-base coverage vector the SNF writer stores (snf.py:248-267)."""
+    import numpy as np
+    from test_gpu_full_size import numpy_filter
+    blk = synth.config_block(2, 0.003)
+    cfg_ns = sconfig.default_config()
+    ok, _ = numpy_filter(blk, cfg_ns)
+    ops = blk.cigar & 15
+    adv = np.isin(ops, [0, 2, 3, 7, 8])
+    span = np.add.reduceat(np.where(adv, blk.cigar >> 4, 0).astype(np.int64), blk.rec["cigar_off"].astype(np.int64))
+    ctx = binding.Context(0)
+    try:
+        ctx.set_config(abi.Config.from_sniffles(cfg_ns))
+        ctx.load(blk)
+        ctx.extract_leads()
+        for t in (0, 5, len(blk.task) - 1):
+            L = int(blk.task[t]["contig_len"])
+            cov = np.zeros(L + 1, np.int64)
+            sel = ok & (blk.rec["task"] == t)
+            s = blk.rec["pos"][sel].astype(np.int64)
+            e = np.minimum(s + span[sel], L)
+            np.add.at(cov, s, 1)
+            np.add.at(cov, e, -1)
+            cov = np.cumsum(cov)[:L]
+            pad = -L % 500
+            want = np.pad(cov, (0, pad)).reshape(-1, 500).mean(axis=1)
+            got = ctx.coverage_bins(t, 500)
+            assert len(got) == len(want) and np.array_equal(got, want), t
+    finally:
+        ctx.close()
