@@ -5,11 +5,11 @@
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU
     python bench.py --impl reference --gpus N --steps K --warmup W  # CPU arm (oracle port, host cores)
 
-A "step" is one pass of the hot path over the whole synthetic workload (BASELINE config 2:
-30x ONT whole genome, 24 GRCh38-length contigs, ~6M reads at --scale 1).  With N ranks the
-contigs are LPT-sharded over the ranks (strong scaling: the genome is fixed), every rank runs
-the three stages on its contigs and the per-rank candidate buffers are concatenated with one
-NCCL all-gather.  `value` is timed with the inputs resident in HBM (CUDA events on the
+A "step" is one pass of the hot path over the whole synthetic workload (--config: BASELINE config 2 by default:
+30x ONT whole genome, 24 GRCh38-length contigs, ~6M reads at --scale 1; 1 = one 1 Mb contig, 3 = 60x HiFi --mosaic,
+5 = INS-heavy region).  With N ranks the contigs are LPT-sharded over the ranks (strong scaling: the genome is fixed),
+every rank runs the three stages on its contigs and the per-rank candidate buffers (records, ALT arena, read names) are
+concatenated with one NCCL all-gather issued by the library (snfb_allgather_candidates).  `value` is timed with the inputs resident in HBM (CUDA events on the
 library's stream, max over ranks); `e2e` goes through the same C-ABI call with HOST buffers:
 pinned host arenas -> H2D -> kernels -> D2H of the candidate SoA and ALT bytes, every step.
 """
@@ -133,22 +133,37 @@ def bind_near_gpu(index):
         return None
 
 
+# ------------------------------------------------------------------------------------------------ workloads (BASELINE.json configs)
+def workload_spec(args):
+    """contig lengths, reference CLI arguments and a description for --config"""
+    from sniffles_b200 import synth
+    c, sc = args.config, args.scale
+    if c == 1:
+        return dict(lens=[int(1_000_000 * sc)], cli=[], coverage=20.0, desc=f"BASELINE config 1: one 1 Mb contig x scale {sc}, ~200 ONT reads of ~100 kb @20x, germline")
+    if c == 2:
+        return dict(lens=[max(200000, int(x * sc)) for x in synth.GRCH38], cli=[], coverage=30.0, desc=f"BASELINE config 2: synthetic 30x ONT WGS, 24 GRCh38-length contigs x scale {sc}, germline")
+    if c == 3:
+        return dict(lens=[max(200000, int(x * sc)) for x in synth.GRCH38], cli=["--mosaic"], coverage=60.0, desc=f"BASELINE config 3: synthetic 60x PacBio HiFi WGS, 24 GRCh38-length contigs x scale {sc}, --mosaic low-VAF")
+    if c == 5:
+        return dict(lens=[int(5_000_000 * sc)], cli=[], coverage=20.0, desc=f"BASELINE config 5: INS-heavy stress, one 5 Mb region x scale {sc}, ~5000 sites x 20 reads, insertions 50-5000 bp")
+    raise SystemExit(f"--config {c}: no synthetic shape (config 4, population combine, is not part of this path)")
+
+
 def workload(args, mask, threads):
     from sniffles_b200 import synth
     t0 = time.time()
     blk = synth.config_block(args.config, args.scale, threads=threads, contig_mask=mask)
-    log(f"[bench] generated config {args.config} scale {args.scale}: {len(blk.rec)} records, {blk.cigar.nbytes / 1e9:.2f} GB CIGAR, {blk.seq.nbytes / 1e9:.2f} GB seq in {time.time() - t0:.1f}s")
-    return blk
+    dt = time.time() - t0
+    log(f"[bench] generated config {args.config} scale {args.scale}: {len(blk.rec)} records, {blk.cigar.nbytes / 1e9:.2f} GB CIGAR, {blk.seq.nbytes / 1e9:.2f} GB seq in {dt:.1f}s")
+    return blk, dt
 
 
 def cpu_sample(blk, cfg, ccfg, threads, target_bp=6e9):
-    """Bounded sample for the CPU arm: the trailing tasks of the block, up to ~target_bp aligned bases."""
+    """Bounded sample for the CPU arm: the smallest tasks of the block first, up to ~target_bp aligned bases; one host thread per contig
+    (the reference's own grain of parallelism, sniffles:313-358)."""
     import oracle.oracle as orc
-    from sniffles_b200 import abi
     rec = blk.rec
     tasks, counts = np.unique(rec["task"], return_counts=True)
-    # the reference's unit of CPU parallelism is the contig: take the smallest contigs first so that the bounded sample
-    # still keeps many host threads busy
     chosen, bp = [], 0
     for t in tasks[np.argsort(counts)]:
         chosen.append(int(t))
@@ -163,9 +178,61 @@ def cpu_sample(blk, cfg, ccfg, threads, target_bp=6e9):
     res = orc.run(sub, ccfg, 3, nthr)
     dt = time.perf_counter() - t0
     cpu_sample.last_result = res
+    cpu_sample.whole_block = len(chosen) == len(tasks)
     return dict(value=abp / dt / 1e9, unit="Gbp/s", cores=nthr, kind="port",
-                sample=f"oracle/snf_oracle.c (C port of the pure-Python reference) on tasks {sorted(chosen)} = {abp / 1e9:.2f} Gbp aligned, {len(res.cand)} candidates, {dt:.2f}s; "
-                       "the reference itself measured 0.0546 Gbp/s/core (BASELINE.md §2)"), abp, dt
+                sample=f"oracle/snf_oracle.c (C port of the pure-Python reference) on tasks {sorted(chosen)} = {abp / 1e9:.3f} Gbp aligned, {len(res.cand)} candidates, {dt:.2f}s"), abp, dt
+
+
+def python_reference_baseline():
+    """The reference's own Python code timed in this run when its tree is present (build container, or $SNIFFLES_REFERENCE_SRC on the box);
+    otherwise the committed measurement of the build container, labelled as such.  Never a silent quote."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "pyref"))
+        import timing
+        if timing.available():
+            m = timing.measure()
+            m["where"] = "this run"
+            return m
+    except Exception as e:
+        log(f"[bench] python reference leg failed: {e}")
+    p = os.path.join(ROOT, "tests", "golden", "python_reference_timing.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            m = json.load(f)
+        return {"absent_on_this_box": True, "measured_elsewhere": m}
+    return {"absent_on_this_box": True}
+
+
+HASH_FIELDS = ["task", "svtype", "pos", "end", "svlen", "support", "qual", "precise", "fwd", "rev", "support_long", "support_sa", "cov_upstream", "cov_start", "cov_center", "cov_end",
+               "cov_downstream", "hap_counts", "sa_count", "sa_total", "bnd_mate_contig", "bnd_mate_pos", "bnd_is_first", "bnd_is_reverse", "n_strands", "support_inline", "lead_n", "long_n",
+               "alt_len", "hp_top", "hp_support", "hp_other", "ps_top", "ps_top_null", "ps_support", "ps_other", "stdev_pos", "stdev_len"]
+
+
+def callset_hash(cand, alt, rnames, rn_off):
+    """sha256 of the call set in emission order (task id, then the producing rank's own order): every candidate field that does not
+    depend on where a rank's arenas start, the ALT bytes and the read-name hashes of every candidate.  Identical for every sharding."""
+    import hashlib
+    order = np.argsort(cand["task"], kind="stable")
+    c = cand[order]
+    h = hashlib.sha256()
+    for f in HASH_FIELDS:
+        h.update(np.ascontiguousarray(c[f]).tobytes())
+    alt = np.asarray(alt)
+    ao, al = cand["alt_off"], cand["alt_len"]
+    lo, hi = rn_off[:-1], rn_off[1:]
+    for i in order:
+        if ao[i] >= 0:
+            h.update(alt[int(ao[i]):int(ao[i]) + int(al[i])].tobytes())
+        h.update(rnames[int(lo[i]):int(hi[i])].tobytes())
+    return h.hexdigest()
+
+
+def committed_hashes():
+    p = os.path.join(ROOT, "tests", "golden", "callset_hashes.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
 
 
 PARITY_FIELDS = ["task", "svtype", "pos", "end", "svlen", "support", "qual", "precise", "fwd", "rev", "cov_upstream", "cov_start", "cov_center", "cov_end",
@@ -183,24 +250,29 @@ def same_candidates(dev, ora):
     return bool((np.asarray(dev.alt) == np.asarray(ora.alt)).all())
 
 
+def sample_mask(args, spec):
+    """contigs of the CPU arm's bounded sample (smallest first, up to --cpu-sample-gbp of sequenced bases)"""
+    lens = spec["lens"]
+    mask, bp = [False] * len(lens), 0.0
+    for c in sorted(range(len(lens)), key=lambda k: lens[k]):
+        mask[c] = True
+        bp += spec["coverage"] * lens[c]
+        if bp >= args.cpu_sample_gbp * 1e9:
+            break
+    return mask
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from sniffles_b200 import abi, config as sconfig
-    cfg = sconfig.default_config()
+    spec = workload_spec(args)
+    cfg = sconfig.default_config(*spec["cli"])
     ccfg = abi.Config.from_sniffles(cfg)
     ncores = os.cpu_count() or 1
-    # generate only the contigs the bounded sample will use (trailing contigs up to ~cpu_sample_gbp aligned bases)
-    from sniffles_b200 import synth
-    lens = [max(200000, int(x * args.scale)) for x in synth.GRCH38]
-    mask, bp = [False] * len(lens), 0.0
-    for c in sorted(range(len(lens)), key=lambda k: lens[k]):
-        mask[c] = True
-        bp += 30.0 * lens[c]
-        if bp >= args.cpu_sample_gbp * 1e9:
-            break
-    blk = workload(args, mask, ncores)
+    # generate only the contigs the bounded sample will use
+    blk, _ = workload(args, sample_mask(args, spec) if len(spec["lens"]) > 1 else None, ncores)
     per_step = []
     info = None
     for i in range(args.warmup + args.steps):
@@ -215,13 +287,27 @@ def run_reference(args):
     print(json.dumps({"impl": "reference", "metric": "aligned long-read Gbp/s through lead->cluster->consensus", "value": val, "unit": "Gbp/s",
                       "n_gpus": args.gpus, "steps": len(per_step), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
                       "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                      "config": {"workload": f"BASELINE config {args.config}: synthetic 30x ONT WGS, scale {args.scale}; CPU arm on a bounded sample ({info['sample']})"},
-                      "cpu_baseline": info, "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+                      "config": {"workload": f"{spec['desc']}; CPU arm on a bounded sample ({info['sample']})"},
+                      "cpu_baseline": info, "cpu_baseline_python": python_reference_baseline(),
+                      "e2e": {"value": val, "unit": "Gbp/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+def consensus_algorithmic_bytes(res):
+    """SURVEY 8d stage C: per INS candidate with a consensus, sum over its seq-bearing leads of ceil(len / 2) packed bases read + len(best) ALT bytes written"""
+    c = res.cand
+    ins = (c["svtype"] == 0) & (c["alt_off"] >= 0)
+    if not ins.any():
+        return 0
+    has = (res.cand_leads["flags"] & (1 << 10)) != 0
+    nb = np.where(has, (res.cand_leads["seq_len"].astype(np.int64) + 1) // 2, 0)
+    cs = np.concatenate([[0], np.cumsum(nb)])
+    lo, n = c["lead_off"][ins].astype(np.int64), c["lead_n"][ins].astype(np.int64)
+    return int((cs[lo + n] - cs[lo]).sum() + c["alt_len"][ins].astype(np.int64).sum())
 
 
 def run_b200(args):
     import torch
-    from sniffles_b200 import abi, binding, config as sconfig, synth, dist as sdist
+    from sniffles_b200 import abi, binding, config as sconfig, dist as sdist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -235,26 +321,30 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         dist.barrier()          # rank 0 has finished build() before anybody loads the libraries
-    cfg = sconfig.default_config()
+    spec = workload_spec(args)
+    cfg = sconfig.default_config(*spec["cli"])
     ccfg = abi.Config.from_sniffles(cfg)
-    lens = [max(200000, int(x * args.scale)) for x in synth.GRCH38]
+    lens = spec["lens"]
     owner = sdist.lpt_assign(lens, world)
     mask = [o == rank for o in owner] if world > 1 else None
     ncores = os.cpu_count() or 1
     old_affinity = bind_near_gpu(local)
-    blk = workload(args, mask, max(1, min(len(os.sched_getaffinity(0)), ncores // world if world > 1 else ncores)))
+    prep = {}
+    blk, prep["generate_s"] = workload(args, mask, max(1, min(len(os.sched_getaffinity(0)), ncores // world if world > 1 else ncores)))
     abp_local = aligned_bp_passing(blk, cfg)
     L = binding.lib()
     t0 = time.time()
     blk.pack16()            # BAM CIGAR words -> CIGAR16, once per block (part of packing the block, like dropping the base qualities)
-    log(f"[bench] packed CIGAR16: {blk.cigar.nbytes / 1e9:.2f} GB -> {blk.cigar16.nbytes / 1e9:.2f} GB in {time.time() - t0:.1f}s")
+    prep["pack_cigar16_s"] = time.time() - t0
+    log(f"[bench] packed CIGAR16: {blk.cigar.nbytes / 1e9:.2f} GB -> {blk.cigar16.nbytes / 1e9:.2f} GB in {prep['pack_cigar16_s']:.1f}s")
     pinned = []
     if not args.no_pin:
         t0 = time.time()
         for a in (blk.rec16, blk.cigar16, blk.var, blk.seq):
             if a.nbytes and L.snfb_pin_host(C.c_void_p(a.ctypes.data), a.nbytes) == 0:
                 pinned.append(a)
-        log(f"[bench] pinned {sum(a.nbytes for a in pinned) / 1e9:.2f} GB of host arenas in {time.time() - t0:.1f}s")
+        prep["pin_s"] = time.time() - t0
+        log(f"[bench] pinned {sum(a.nbytes for a in pinned) / 1e9:.2f} GB of host arenas in {prep['pin_s']:.1f}s")
     if old_affinity:            # every thread (the OpenMP pool was created under the narrow mask) gets all CPUs back
         for tid in os.listdir("/proc/self/task"):
             try:
@@ -263,22 +353,17 @@ def run_b200(args):
                 pass
     ctx = binding.Context(local)
     ctx.set_config(ccfg)
+    if world > 1:           # the library's own NCCL communicator: the id travels through the launcher's process group
+        box = [binding.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
     ctx.load(blk)
-
-    def gather(res):
-        """one NCCL all-gather of the per-rank candidate buffers before VCF emission"""
-        if world == 1:
-            return len(res.cand)
-        dptr, n = ctx.device_candidates()
-        nbytes = n * abi.CAND_DTYPE.itemsize
-        local = torch.as_tensor(sdist.DeviceBytes(dptr, nbytes), device="cuda") if nbytes else torch.zeros(0, dtype=torch.uint8, device="cuda")
-        parts = sdist.allgather_bytes(local)
-        return sum(p.numel() for p in parts) // abi.CAND_DTYPE.itemsize
 
     def step():
         res = ctx.run(want_leads=False, want_cands=True, want_seqs=True, copy=False)
-        n_all = gather(res)
-        return res, n_all
+        if world > 1:       # ONE all-gather of the per-rank candidate buffers before VCF emission, result left in device memory
+            ctx.allgather_candidates(device_only=True)
+        return res
 
     def barrier():
         torch.cuda.synchronize()
@@ -286,15 +371,15 @@ def run_b200(args):
             dist.barrier()
 
     for _ in range(args.warmup):
-        res, n_all = step()
+        res = step()
     barrier()
-    launches0 = ctx.launch_count()
+    launches0, reruns0 = ctx.launch_count(), ctx.rerun_count()
     sampler = ClockSampler(local)
     sampler.start()
     dev_ms, kern = 0.0, {}
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        res, n_all = step()
+        res = step()
         for name, ms, by in ctx.timings():
             if name == "h2d_records":
                 continue
@@ -306,6 +391,7 @@ def run_b200(args):
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = ctx.launch_count() - launches0
+    reruns = ctx.rerun_count() - reruns0
     # max over ranks
     tt = torch.tensor([dev_ms, wall * 1e3, float(abp_local)], device="cuda", dtype=torch.float64)
     if dist is not None:
@@ -322,49 +408,89 @@ def run_b200(args):
     # ---- end to end through the C ABI with host buffers (H2D + kernels + D2H every step) ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     full_bytes = blk.rec16.nbytes + blk.cigar16.nbytes + blk.var.nbytes + blk.seq.nbytes
+    ctx.load(blk, seq_on_demand=not args.e2e_full_seq)          # untimed: sizes the seq-on-demand buffers
+    step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         ctx.load(blk, seq_on_demand=not args.e2e_full_seq)      # host arenas; the 4-bit seq arena is fetched on demand (slices only)
-        res, n_all = step()
+        res = step()
     slice_bytes = sum(by for name, ms, by in ctx.timings() if name == "h2d_seq_slices")
     h2d = blk.rec16.nbytes + blk.cigar16.nbytes + blk.var.nbytes + (blk.seq.nbytes if args.e2e_full_seq else slice_bytes)
     barrier()
     e2e_wall = (time.perf_counter() - t0) / e2e_steps
     d2h = res.cand.nbytes + res.cand_leads.nbytes + res.rnames.nbytes + res.alt.nbytes
-    et = torch.tensor([e2e_wall], device="cuda", dtype=torch.float64)
+    # the same call fed the BAM's own 32-bit CIGAR words: the library converts them to CIGAR16 on the host inside snfb_load_records
+    t0 = time.perf_counter()
+    ctx.load(blk, seq_on_demand=not args.e2e_full_seq, cigar16=False)
+    step()
+    barrier()
+    e2e_bam32 = time.perf_counter() - t0
+    et = torch.tensor([e2e_wall, e2e_bam32], device="cuda", dtype=torch.float64)
     if dist is not None:
         dist.all_reduce(et, op=dist.ReduceOp.MAX)
     e2e_val = abp_total / float(et[0]) / 1e9
 
-    # ---- roofline of the dominant kernel (stage A lead extraction) ----
+    # ---- parity: the gathered call set of this run against the committed hash of the N = 1 run (itself checked against the oracle) ----
     ctx.load(blk)
     full = ctx.run(want_leads=True, want_cands=True, want_seqs=True, copy=False)       # also the run the full-size parity check compares with the oracle
+    if world > 1:
+        g = ctx.allgather_candidates(device_only=False)
+        n_all = g.n_cand
+        digest = callset_hash(g.cand, g.alt, g.rnames, g.rn_off) if rank == 0 else None
+    else:
+        n_all = len(full.cand)
+        digest = callset_hash(full.cand, full.alt, full.rnames, full.rn_off)
+    key = f"config{args.config}_scale{args.scale}"
+    committed = committed_hashes().get(key)
+
+    # ---- rooflines: the streaming stage-A kernel, and the consensus kernels (dominant on config 5) ----
+    peak, peak_src = measured_peak()
     alg, alg_read = algorithmic_bytes_stage_a(blk, len(full.leads), full.n_pass)
     k_ms = kern.get("k_scan", [0.0, 0])[0] / args.steps
-    peak, peak_src = measured_peak()
     achieved = alg / (k_ms / 1e3) / 1e9 if k_ms > 0 else 0.0
-    traffic = ncu_traffic() if (args.config == 2 and args.scale == 1.0) else None      # the capture is of this workload at full size
-    roof = {"bound": "hbm", "kernel": "extract::k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
-            "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-            "traffic": traffic.get("dram_bytes_per_launch") if traffic else None}
+    traffic = ncu_traffic() if (args.config == 2 and args.scale == 1.0 and world == 1) else None      # the capture is of this workload at full size
+    roof_a = {"bound": "hbm", "kernel": "extract::k_scan", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None,
+              "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms, "traffic": traffic.get("dram_bytes_per_launch") if traffic else None}
+    c_ms = sum(kern.get(k, [0.0, 0])[0] for k in ("consensus", "consensus_align", "consensus_vote")) / args.steps
+    c_alg = consensus_algorithmic_bytes(full)
+    c_ach = c_alg / (c_ms / 1e3) / 1e9 if c_ms > 0 else 0.0
+    roof_c = {"bound": "hbm", "kernel": "consensus::k_prep + k_align + k_vote", "achieved": c_ach, "peak": peak, "unit": "GB/s", "frac": c_ach / peak if peak else None, "peak_source": peak_src,
+              "algorithmic_bytes_per_launch": c_alg, "kernel_ms": c_ms, "traffic": None}
+    roof = roof_c if c_ms > k_ms else roof_a
     if rank == 0:
         out = {"metric": "aligned long-read Gbp/s through lead->cluster->consensus", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_per_step, "device_ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-               "config": {"workload": f"BASELINE config {args.config}: synthetic 30x ONT WGS, 24 GRCh38-length contigs x scale {args.scale}, {abp_total / 1e9:.2f} Gbp aligned, germline",
-                          "records_rank0": int(len(blk.rec)), "candidates_total": int(n_all), "parallelism": f"contig LPT over {world} GPU(s), one NCCL all-gather of candidates",
-                          "l2": f"inputs {full_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed",
-                          "cigar": f"CIGAR16 ({blk.cigar16.nbytes / 1e9:.2f} GB; the BAM words are {blk.cigar.nbytes / 1e9:.2f} GB)"},
-               "clocks": clocks, "gpu_launches": int(launches),
+               "config": {"workload": f"{spec['desc']}, {abp_total / 1e9:.3f} Gbp aligned",
+                          "records_rank0": int(len(blk.rec)), "candidates_total": int(n_all), "parallelism": f"contig LPT over {world} GPU(s), one NCCL all-gather (library call) of candidate records + ALT arena + read names",
+                          "l2": f"inputs {full_bytes / 1e9:.2f} GB per rank vs 126 MB L2" + ("" if full_bytes > 4e8 else "; the whole input fits in L2 (stated, not flushed: the reference-sized workload is this small)"),
+                          "cigar": f"CIGAR16 ({blk.cigar16.nbytes / 1e9:.3f} GB; the BAM words are {blk.cigar.nbytes / 1e9:.3f} GB)"},
+               "clocks": clocks, "gpu_launches": int(launches), "reruns_in_timed_region": int(reruns),
                "e2e": {"value": e2e_val, "unit": "Gbp/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": e2e_steps, "ms_per_step": float(et[0]) * 1e3,
-                       "pinned": bool(pinned), "seq": "full arena" if args.e2e_full_seq else "on demand (slices requested by the device, gathered on the host)"},
-               "roofline": roof, "stage_ms": {k: v[0] / args.steps for k, v in kern.items()}}
+                       "pinned": bool(pinned), "seq": "full arena" if args.e2e_full_seq else "on demand (slices requested by the device, gathered on the host)",
+                       "bam32_in_ms": float(et[1]) * 1e3, "bam32_in_note": "one step fed BAM CIGAR words: snfb_load_records converts them to CIGAR16 on the host first"},
+               "host_prep": {k: round(v, 3) for k, v in prep.items()},
+               "roofline": roof, "rooflines": [roof_a, roof_c], "stage_ms": {k: v[0] / args.steps for k, v in kern.items()},
+               "callset_sha256": digest}
+        if committed:
+            out["parity_vs_n1"] = {"identical": digest == committed["sha256"], "n1_candidates": committed.get("n_cand"), "this_run_candidates": int(n_all),
+                                   "source": "tests/golden/callset_hashes.json (written by the 1-GPU run whose call set equals the oracle's)"}
+        elif world > 1:
+            out["parity_vs_n1"] = {"identical": None, "note": f"no committed N=1 hash for {key}"}
         if world == 1 and not args.no_cpu:
             info, _, _ = cpu_sample(blk, cfg, ccfg, ncores, target_bp=args.cpu_sample_gbp * 1e9)
             out["cpu_baseline"] = info
-            if args.cpu_sample_gbp * 1e9 >= abp_total:        # the oracle saw the whole block: compare it with the device run, candidate by candidate
-                out["parity_full_size"] = {"candidates": int(len(full.cand)), "alt_bytes": int(len(full.alt)), "identical_to_oracle": same_candidates(full, cpu_sample.last_result)}
+            if cpu_sample.whole_block:        # the oracle saw the whole block: compare it with the device run, candidate by candidate
+                same = same_candidates(full, cpu_sample.last_result)
+                out["parity_full_size"] = {"candidates": int(len(full.cand)), "alt_bytes": int(len(full.alt)), "identical_to_oracle": same}
+                if same and args.write_hash:
+                    hs = committed_hashes()
+                    hs[key] = {"sha256": digest, "n_cand": int(len(full.cand)), "alt_bytes": int(len(full.alt))}
+                    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+                    with open(os.path.join(ROOT, "gpurun_out", "callset_hashes.json"), "w") as f:
+                        json.dump(hs, f, indent=1, sort_keys=True)
+            out["cpu_baseline_python"] = python_reference_baseline()
         print(json.dumps(out))
     for a in pinned:
         L.snfb_unpin_host(C.c_void_p(a.ctypes.data))
@@ -379,13 +505,14 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=2, help="BASELINE.json config index (2 = 30x ONT WGS)")
-    ap.add_argument("--scale", type=float, default=float(os.environ.get("SNFB_BENCH_SCALE", "1.0")), help="contig length multiplier (1.0 = full GRCh38 lengths)")
+    ap.add_argument("--config", type=int, default=int(os.environ.get("SNFB_BENCH_CONFIG", "2")), help="BASELINE.json config index: 1, 2 (default: 30x ONT WGS), 3 (60x HiFi --mosaic), 5 (INS-heavy)")
+    ap.add_argument("--scale", type=float, default=float(os.environ.get("SNFB_BENCH_SCALE", "1.0")), help="contig length multiplier (1.0 = the named size)")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--cpu-sample-gbp", type=float, default=1000.0, help="aligned Gbp of the CPU arm's sample (smallest contigs first); the default takes every contig: one host thread per contig, the reference's own grain")
+    ap.add_argument("--cpu-sample-gbp", type=float, default=1000.0, help="sequenced Gbp of the CPU arm's sample (smallest contigs first); the default takes every contig: one host thread per contig, the reference's own grain")
     ap.add_argument("--no-pin", action="store_true")
     ap.add_argument("--e2e-full-seq", action="store_true", help="e2e: copy the whole seq arena every step instead of the on-demand slices")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--write-hash", action="store_true", help="1 GPU: when the call set equals the oracle's, write its hash to gpurun_out/callset_hashes.json (to be committed under tests/golden/)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("[bench] note: timing rules ask for >= 3 warm-up steps")

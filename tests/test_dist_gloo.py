@@ -31,13 +31,22 @@ def _worker(rank, world, port, q):
     cfg = abi.Config.from_sniffles(sconfig.default_config())
     res = orc.run(sdist.subset_block(blk, mine), cfg, 3, 1)
     assert set(np.unique(res.cand["task"])) <= set(mine)
-    parts = sdist.gather_struct_arrays(res.cand, device="cpu")
-    merged = sdist.merge_rank_candidates(parts)
+    merged = sdist.gather_results(res, device="cpu")          # cand + ALT arena + read names + candidate leads, offsets rebased
     if rank == 0:
         full = orc.run(blk, cfg, 3, 1)
-        keys = ["task", "svtype", "pos", "svlen", "support", "qual", "cov_center", "stdev_pos"]
-        ok = len(full.cand) == len(merged) and all((full.cand[k] == merged[k]).all() for k in keys)
-        q.put((ok, len(full.cand), len(merged), owner))
+        order = merged.in_emission_order()
+        keys = ["task", "svtype", "pos", "svlen", "support", "qual", "cov_center", "stdev_pos", "lead_n", "long_n", "alt_len"]
+        ok = len(full.cand) == len(merged.cand) and all((full.cand[k] == merged.cand[k][order]).all() for k in keys)
+        # the arenas behind the offsets: ALT sequences, read names and lead tables of every candidate, including those of rank > 0
+        if ok:
+            for i, j in enumerate(order):
+                a, b = full.cand[i], merged.cand[j]
+                ok = ok and full.alt_of(i) == merged.alt_of(int(j))
+                ok = ok and (full.rnames[full.rn_off[i]:full.rn_off[i + 1]] == merged.rnames[merged.rn_off[j]:merged.rn_off[j + 1]]).all()
+                la = full.cand_leads[a["lead_off"]:a["lead_off"] + a["lead_n"] + a["long_n"]]
+                lb = merged.cand_leads[b["lead_off"]:b["lead_off"] + b["lead_n"] + b["long_n"]]
+                ok = ok and len(la) == len(lb) and all((la[f] == lb[f]).all() for f in ("ref_start", "svlen", "qname_hash", "flags"))
+        q.put((ok, len(full.cand), len(merged.cand), owner, int((np.asarray([full.alt_of(i) is not None for i in range(len(full.cand))])).sum())))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,12 +59,12 @@ def test_two_rank_gather_equals_single_process():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    ok, n_full, n_merged, owner = q.get(timeout=240)
+    ok, n_full, n_merged, owner, n_alt = q.get(timeout=240)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok, (n_full, n_merged, owner)
-    assert n_full > 20 and sorted(set(owner)) == [0, 1]
+    assert n_full > 20 and sorted(set(owner)) == [0, 1] and n_alt > 5
 
 
 def test_lpt_balances_grch38():
