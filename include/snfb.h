@@ -346,6 +346,9 @@ typedef struct snfb_gather_view {
 int         snfb_nccl_unique_id(void* out128);
 int         snfb_comm_init(snfb_ctx* ctx, const void* unique_id128, int rank, int nranks);
 int         snfb_allgather_candidates(snfb_ctx* ctx, uint32_t flags, snfb_gather_view* out);
+/* self-check of the exact statistics.stdev arithmetic (host build of the routine the kernels use): the correctly rounded sqrt(P / Q) for
+ * P = p_hi * 2^64 + p_lo; slow != 0 selects the limb-by-limb restatement of CPython's _float_sqrt_of_frac, 0 the verified fast path */
+double      snfb_selftest_sqrt_frac(uint64_t p_hi, uint64_t p_lo, uint64_t q, int slow);
 /* BAM CIGAR words -> CIGAR16 (host code, OpenMP; no GPU needed).  rec_out receives copies of rec_in with cigar_off / n_cigar
  * rewritten for the 16-bit arena.  Call with out16 == NULL to get the number of 16-bit words the arena needs (a multiple
  * of 8); returns that number, or UINT64_MAX when a record holds an op the path does not know (B) or out_cap is too small. */

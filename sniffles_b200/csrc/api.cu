@@ -235,7 +235,8 @@ int snfb_ctx_create(int device, snfb_ctx** out) {
     if (ctx->h_ctr_buf.ensure(2 * sizeof(DevCounters) + 256) || ctx->b_ctr.ensure(sizeof(DevCounters) + 64)) { delete ctx; return 5; }
     ctx->h_mid = ctx->h_ctr_buf.as<DevCounters>(); ctx->h_fin = ctx->h_mid + 1; ctx->h_work = reinterpret_cast<uint32_t*>(ctx->h_fin + 1);
     memset(ctx->h_ctr_buf.p, 0, 2 * sizeof(DevCounters) + 256);
-    cudaFuncSetAttribute(cluster::k_cluster_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster::CW_SMEM);
+    cudaFuncSetAttribute(cluster::k_cluster_warp<cluster::SMALL_CAP, cluster::CWS_WARPS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster::CwCfg<cluster::SMALL_CAP, cluster::CWS_WARPS>::smem);
+    cudaFuncSetAttribute(cluster::k_cluster_warp<cluster::WARP_CAP, cluster::CWM_WARPS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster::CwCfg<cluster::WARP_CAP, cluster::CWM_WARPS>::smem);
     cudaFuncSetAttribute(cluster::k_cluster_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cluster::CB_SMEM);
     *out = ctx; return 0;
 }
@@ -420,7 +421,7 @@ static void carve_l(snfb_ctx* ctx, Carver& c) {
     b.kl_off = c.take<uint32_t>(n); b.kll_off = c.take<uint32_t>(n); b.kb_idx = c.take<uint32_t>(n); b.kl = c.take<uint32_t>(n); b.kll = c.take<uint32_t>(n); b.kleads = c.take<snfb_lead>(n); b.klleads = c.take<snfb_lead>(n);
     b.kb_bin = c.take<uint32_t>(n); b.kb_lead_off = c.take<uint32_t>(n); b.kb_lead_n = c.take<uint32_t>(n); b.kb_long_off = c.take<uint32_t>(n); b.kb_long_n = c.take<uint32_t>(n); b.kb_seed = c.take<int32_t>(n); b.kb_chain = c.take<uint32_t>(n); b.kb_repeat = c.take<uint8_t>(n);
     b.seg_start = c.take<uint32_t>(n); b.c_next = c.take<uint32_t>(n); b.c_last = c.take<uint32_t>(n); b.c_sd = c.take<double>(n); b.c_mean = c.take<double>(n); b.c_rep = c.take<uint8_t>(n);
-    b.seg_sd_last = c.take<double>(n); b.seg_maxsd_first = c.take<double>(n); b.cl_first = c.take<uint32_t>(n); b.cl_last = c.take<uint32_t>(n); b.cl_rep = c.take<uint8_t>(n); b.big_list = c.take<uint32_t>(n);
+    b.seg_sd_last = c.take<double>(n); b.seg_maxsd_first = c.take<double>(n); b.cl_first = c.take<uint32_t>(n); b.cl_last = c.take<uint32_t>(n); b.cl_rep = c.take<uint8_t>(n); b.big_list = c.take<uint32_t>(n); b.mid_list = c.take<uint32_t>(n);
     b.g_khi = c.take<uint64_t>(n); b.g_klo = c.take<uint64_t>(n); b.g_u32 = c.take<uint32_t>((size_t)cluster::coop::NU32 * n);
     b.ord = c.take<uint32_t>(n); b.st_leads = c.take<snfb_lead>(n); b.st_plo = c.take<uint32_t>(n); b.st_pn = c.take<uint32_t>(n); b.st_rn = c.take<uint64_t>(n); b.cand_tmp = c.take<snfb_cand>(n); b.sub_valid = c.take<uint8_t>(n);
     b.cl_nsub = c.take<uint32_t>(n); b.cl_nvalid = c.take<uint32_t>(n); b.cl_nlead = c.take<uint32_t>(n); b.cl_nrn = c.take<uint32_t>(n); b.cl_cand_base = c.take<uint32_t>(n); b.cl_lead_base = c.take<uint32_t>(n); b.cl_rn_base = c.take<uint32_t>(n);
@@ -560,8 +561,9 @@ static int enqueue_stage_b(snfb_ctx* ctx) {
     // clusters too large for one warp's shared memory go to a block each, next to the warp-per-cluster kernel
     CUDA_TRY(cudaEventRecord(ctx->ev_fork, st)); CUDA_TRY(cudaStreamWaitEvent(ctx->st_side, ctx->ev_fork, 0));
     cluster::k_cluster_block<<<148, cluster::CB_THREADS, cluster::CB_SMEM, ctx->st_side>>>(b);
+    cluster::k_cluster_warp<cluster::WARP_CAP, cluster::CWM_WARPS, true><<<148 * 2, cluster::CWM_WARPS * 32, cluster::CwCfg<cluster::WARP_CAP, cluster::CWM_WARPS>::smem, ctx->st_side>>>(b);
     CUDA_TRY(cudaEventRecord(ctx->ev_join, ctx->st_side));
-    cluster::k_cluster_warp<<<148 * 3, cluster::CW_WARPS * 32, cluster::CW_SMEM, st>>>(b);
+    cluster::k_cluster_warp<cluster::SMALL_CAP, cluster::CWS_WARPS, false><<<148 * 4, cluster::CWS_WARPS * 32, cluster::CwCfg<cluster::SMALL_CAP, cluster::CWS_WARPS>::smem, st>>>(b);
     CUDA_TRY(cudaStreamWaitEvent(st, ctx->ev_join, 0));
     mark(ctx, "emit_cands");
     LAUNCHED(ctx, prims::exclusive_scan(b.cl_nvalid, b.cl_cand_base, b.scan_tmp, &ctr->n_clusters, nb, &ctr->n_cand, st));
@@ -570,7 +572,7 @@ static int enqueue_stage_b(snfb_ctx* ctx) {
     cluster::k_emit_cands<<<148 * 8, 128, 0, st>>>(b);
     mark(ctx, "coverage");
     if (ctx->n_mask) { cluster::k_mask_bp<<<grid_for((unsigned long long)ctx->n_mask * 32, 128), 128, 0, st>>>(b, ctx->b_mask_task.as<uint32_t>(), ctx->n_mask, ctx->task_cov); LAUNCHED(ctx, 1); }
-    cluster::k_coverage<<<148 * 8, 128, 0, st>>>(b); LAUNCHED(ctx, 12);
+    cluster::k_coverage<<<148 * 32, 128, 0, st>>>(b); LAUNCHED(ctx, 13);
     // consensus plan: best read per INS candidate, sizes and offsets of the ALT bytes and of the scratch; the candidate records are final after this
     consensus::C& c = ctx->Cc;
     CUDA_TRY(cudaMemsetAsync(c.work_ctr, 0, 64, st));
@@ -812,6 +814,7 @@ int snfb_device_alt(snfb_ctx* ctx, void** dptr, uint64_t* n_bytes) {
     if (dptr) *dptr = ctx->Cc.alt; if (n_bytes) *n_bytes = ctx->h_fin->n_alt_bytes; return 0;
 }
 uint64_t snfb_launch_count(snfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
+double snfb_selftest_sqrt_frac(uint64_t p_hi, uint64_t p_lo, uint64_t q, int slow) { const u128 P = ((u128)p_hi << 64) | p_lo; return slow ? sqrt_frac_rn_slow(P, q) : sqrt_frac_rn(P, q); }
 uint64_t snfb_rerun_count(snfb_ctx* ctx) { return ctx ? ctx->reruns : 0; }
 int snfb_pin_host(void* p, size_t bytes) { return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1; }
 int snfb_unpin_host(void* p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : 1; }

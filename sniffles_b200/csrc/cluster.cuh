@@ -20,7 +20,8 @@ namespace cluster {
 constexpr int TYPE_SHIFT = 26;               // key = task << 29 | svtype << 26 | bin
 constexpr int TASK_SHIFT = 29;
 constexpr uint32_t NONE = 0xffffffffu;
-constexpr int WARP_CAP = 128;               // leads one warp stages in shared memory; larger clusters take a whole block
+constexpr int SMALL_CAP = 48;               // clusters up to this size: the dense warp-per-cluster kernel
+constexpr int WARP_CAP = 128;               // mid-sized clusters, still one warp each (from a list); larger clusters take a whole block
 constexpr int BLOCK_CAP = 1024;             // leads one block stages in shared memory; larger clusters work in global scratch
 
 struct B {
@@ -48,7 +49,7 @@ struct B {
     uint32_t* c_next; uint32_t* c_last; double* c_sd; double* c_mean; uint8_t* c_rep;
     double* seg_sd_last; double* seg_maxsd_first;
     uint32_t* cl_first; uint32_t* cl_last; uint8_t* cl_rep;
-    uint32_t* big_list;             // clusters with more leads than one warp stages in shared memory
+    uint32_t* big_list; uint32_t* mid_list;      // clusters with more than WARP_CAP / SMALL_CAP leads
     // global workspace of the clusters too large for shared memory, indexed in kept-lead space
     uint64_t* g_khi; uint64_t* g_klo; uint32_t* g_u32;
     // per-lead results of the cluster kernel
@@ -254,6 +255,7 @@ __global__ void k_cluster_build(B b) {
             const uint32_t c = b.scan[k], kl_ = b.c_last[k]; b.cl_first[c] = (uint32_t)k; b.cl_last[c] = kl_; b.cl_rep[c] = b.c_rep[k];
             const uint32_t n = b.kb_lead_off[kl_] + b.kb_lead_n[kl_] - b.kb_lead_off[k];
             if (n > (uint32_t)WARP_CAP) b.big_list[atomicAdd(&b.ctr->n_big, 1ULL)] = c;
+            else if (n > (uint32_t)SMALL_CAP) b.mid_list[atomicAdd(&b.ctr->n_mid, 1ULL)] = c;
         }
 }
 
@@ -725,34 +727,37 @@ __device__ __forceinline__ coop::WS smem_ws(uint8_t* base, int cap) {
 }
 __host__ __device__ constexpr size_t ws_bytes(int cap) { return (size_t)cap * (64 + 16 + 4 * coop::NU32); }
 
-constexpr int CW_WARPS = 4;                                   // warps per block of the warp-per-cluster kernel
-constexpr size_t CW_SMEM = CW_WARPS * ws_bytes(WARP_CAP) + 64;
-// one warp per cluster of at most WARP_CAP leads
-__global__ void __launch_bounds__(CW_WARPS * 32) k_cluster_warp(const __grid_constant__ B b) {
+// one warp per cluster, the cluster's leads staged in the warp's slice of shared memory.  Two instantiations: clusters of at most
+// SMALL_CAP leads (the bulk: 8 warps per block, 4 blocks per SM) and the mid-sized ones up to WARP_CAP from a list.
+template <int CAP, int WARPS> struct CwCfg { static constexpr size_t smem = WARPS * ws_bytes(CAP) + 64; };
+template <int CAP, int WARPS, bool LIST>
+__global__ void __launch_bounds__(WARPS * 32, LIST ? 1 : 4) k_cluster_warp(const __grid_constant__ B b) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = lane_id();
-    uint8_t* base = smem + (size_t)warp * ws_bytes(WARP_CAP);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + CW_WARPS * ws_bytes(WARP_CAP)) + warp;
-    const coop::WS ws = smem_ws(base, WARP_CAP);
+    uint8_t* base = smem + (size_t)warp * ws_bytes(CAP);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + WARPS * ws_bytes(CAP)) + warp;
+    const coop::WS ws = smem_ws(base, CAP);
     if (lane == 0) { coop::mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
     unsigned phase = 0;
-    const unsigned long long ncl = b.ctr->n_clusters;
-    const unsigned long long nw = (unsigned long long)gridDim.x * CW_WARPS;
+    const unsigned long long n_items = LIST ? b.ctr->n_mid : b.ctr->n_clusters;
+    const unsigned long long nw = (unsigned long long)gridDim.x * WARPS;
     coop::WarpG g;
-    for (unsigned long long c = (unsigned long long)blockIdx.x * CW_WARPS + warp; c < ncl; c += nw) {
+    for (unsigned long long q = (unsigned long long)blockIdx.x * WARPS + warp; q < n_items; q += nw) {
+        const uint32_t c = LIST ? b.mid_list[q] : (uint32_t)q;
         const uint32_t kf = b.cl_first[c], kl_ = b.cl_last[c];
         const uint32_t lo = b.kb_lead_off[kf], n = b.kb_lead_off[kl_] + b.kb_lead_n[kl_] - lo;
-        if (n > (uint32_t)WARP_CAP) continue;                 // k_cluster_block takes it
+        if (!LIST && n > (uint32_t)CAP) continue;             // the list kernels take it
         __syncwarp();                                         // the previous cluster's reads of the staged leads are done
         if (lane == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             coop::mbar_expect_tx(bar, n * 64u); coop::bulk_g2s(base, b.kleads + lo, n * 64u, bar);
         }
         coop::mbar_wait(bar, phase); phase ^= 1u;
-        process_cluster(g, b, (uint32_t)c, ws);
+        process_cluster(g, b, c, ws);
     }
 }
+constexpr int CWS_WARPS = 8, CWM_WARPS = 4;
 constexpr int CB_THREADS = 256;
 constexpr size_t CB_SMEM = ws_bytes(BLOCK_CAP) + 72 * 8 + 64;
 // one block per cluster of more than WARP_CAP leads (from big_list)

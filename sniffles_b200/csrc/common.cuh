@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
+#include <math.h>
 #include "../../include/snfb.h"
 
 #define FULL 0xffffffffu
@@ -24,7 +26,7 @@ struct DevCounters {
     unsigned long long n_slots;        // high-water mark of the lead slot allocator (>= n_leads: warps reserve chunks)
     unsigned long long n_ev, n_sa;     // event slices / records with an SA tag found by k_scan
     unsigned long long n_kl, n_kll;    // kept leads / kept "long" leads
-    unsigned long long n_big;          // clusters handled by a whole block
+    unsigned long long n_big, n_mid;   // clusters handled by a whole block / by the mid-sized warp kernel
     unsigned long long ordinal_overflow;   // reads with more than 65535 leads (the ordinal is a 16-bit field)
     unsigned long long bad_records;    // records whose offsets point outside the block's arenas or tables (snfb_load_records fails)
     unsigned long long n_items, n_tiles, n_req, n_req_units;   // consensus work items / vote tiles / seq-on-demand requests
@@ -71,20 +73,27 @@ __device__ inline uint64_t qname_hash_warp(const uint8_t* s, int n) {   // all 3
 // ---------------------------------------------------------------- exact statistics.stdev
 // RN(sqrt(P/Q)) for P < 2^128, 0 < Q < 2^63: the value CPython 3.12's statistics.stdev returns
 // for integer data with P = n*Sxx - Sx^2 and Q = n*(n-1) (statistics.py _float_sqrt_of_frac).
-__device__ inline int bitlen_u128(u128 x) {
-    uint64_t hi = (uint64_t)(x >> 64), lo = (uint64_t)x;
-    return hi ? 128 - __clzll((long long)hi) : (lo ? 64 - __clzll((long long)lo) : 0);
+__host__ __device__ inline int clz64_hd(uint64_t x) {
+#ifdef __CUDA_ARCH__
+    return __clzll((long long)x);
+#else
+    return x ? __builtin_clzll(x) : 64;
+#endif
 }
-__device__ inline double sqrt_frac_rn(u128 P, uint64_t Q) {
+__host__ __device__ inline int bitlen_u128(u128 x) {
+    uint64_t hi = (uint64_t)(x >> 64), lo = (uint64_t)x;
+    return hi ? 128 - clz64_hd(hi) : (lo ? 64 - clz64_hd(lo) : 0);
+}
+// the reference algorithm, limb by limb: numerator shifted to 111+ significant quotient bits, long division, integer square root,
+// round-to-odd, one final rounding (statistics.py _float_sqrt_of_frac).  Slow (a 288-bit long division): only the fallback of the fast path below.
+__host__ __device__ inline double sqrt_frac_rn_slow(u128 P, uint64_t Q) {
     if (P == 0) return 0.0;
     int bl = bitlen_u128(P) - bitlen_u128((u128)Q);
     int s = 111 - bl; if (s < 0) s = 0; if (s & 1) ++s;
     // numerator P << s in 32-bit limbs (at most 128 + 112 bits)
     uint32_t num[9];
-    #pragma unroll
     for (int i = 0; i < 9; ++i) num[i] = 0;
     int w = s >> 5, o = s & 31;
-    #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint64_t limb = (uint64_t)((P >> (32 * i)) & 0xFFFFFFFFu) << o;
         // disjoint bit ranges: or-ing is exact
@@ -93,7 +102,6 @@ __device__ inline double sqrt_frac_rn(u128 P, uint64_t Q) {
     }
     // long division by Q (Q < 2^63 so rem*2^32 + limb fits in u128)
     uint32_t quo[9]; u128 rem = 0;
-    #pragma unroll
     for (int i = 8; i >= 0; --i) { u128 cur = (rem << 32) | num[i]; u128 q = cur / Q; quo[i] = (uint32_t)q; rem = cur - q * Q; }
     u128 V = ((u128)quo[3] << 96) | ((u128)quo[2] << 64) | ((u128)quo[1] << 32) | quo[0];
     double vf = (double)(uint64_t)(V >> 64) * 18446744073709551616.0 + (double)(uint64_t)V;
@@ -104,6 +112,66 @@ __device__ inline double sqrt_frac_rn(u128 P, uint64_t Q) {
     bool sticky = ((u128)a * a != V) || rem != 0;
     a |= (uint64_t)sticky;
     return ldexp((double)a, -(s >> 1));     // u64 -> double is round-to-nearest-even: the single rounding
+}
+// ---- fast path: a floating-point guess, then an EXACT check that it is the correctly rounded value: x = P / Q lies between the squares of the
+//      midpoints to the neighbouring doubles.  The comparisons are done in 256-bit integers, so the result is the same bit pattern as above.
+struct U256 { uint64_t w[4]; };
+__host__ __device__ inline U256 mul_128_64(u128 a, uint64_t b) {
+    const u128 lo = (u128)(uint64_t)a * b; const u128 hi = (u128)(uint64_t)(a >> 64) * b + (uint64_t)(lo >> 64);
+    U256 r; r.w[0] = (uint64_t)lo; r.w[1] = (uint64_t)hi; r.w[2] = (uint64_t)(hi >> 64); r.w[3] = 0; return r;
+}
+__host__ __device__ inline int cmp256(const U256& a, const U256& b) {
+    for (int i = 3; i >= 0; --i) if (a.w[i] != b.w[i]) return a.w[i] < b.w[i] ? -1 : 1;
+    return 0;
+}
+// sign of (m * 2^e)^2 * Q - P for m < 2^55; 2 when the operands do not fit the 256-bit comparison (the caller falls back)
+__host__ __device__ inline int cmp_mid_sq(uint64_t m, int e, u128 P, uint64_t Q) {
+    const U256 A = mul_128_64((u128)m * m, Q);
+    if (e >= 0) return 2;
+    const int s = -2 * e;
+    if (bitlen_u128(P) + s > 255) return -1;          // P * 2^s has more bits than A can have (A < 2^174): A is smaller
+    U256 R; R.w[0] = R.w[1] = R.w[2] = R.w[3] = 0;
+    const int ws = s >> 6, bs = s & 63; const uint64_t lo = (uint64_t)P, hi = (uint64_t)(P >> 64);
+    if (ws < 4) R.w[ws] = lo << bs;
+    if (ws + 1 < 4) R.w[ws + 1] = (hi << bs) | (bs ? lo >> (64 - bs) : 0ull);
+    if (ws + 2 < 4) R.w[ws + 2] = bs ? hi >> (64 - bs) : 0ull;
+    return cmp256(A, R);
+}
+__host__ __device__ inline double bits_to_f8(long long b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(b);
+#else
+    double d; memcpy(&d, &b, 8); return d;
+#endif
+}
+__host__ __device__ inline long long f8_to_bits(double d) {
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(d);
+#else
+    long long b; memcpy(&b, &d, 8); return b;
+#endif
+}
+__host__ __device__ inline double sqrt_frac_rn(u128 P, uint64_t Q) {
+    if (P == 0) return 0.0;
+    const double pf = (double)(uint64_t)(P >> 64) * 18446744073709551616.0 + (double)(uint64_t)P;
+    double d = sqrt(pf / (double)Q);
+    for (int it = 0; it < 6; ++it) {
+        const long long bits = f8_to_bits(d); const int ex = (int)((bits >> 52) & 0x7ff);
+        if (ex == 0 || ex == 0x7ff || bits < 0) break;
+        const uint64_t M = ((uint64_t)bits & ((1ull << 52) - 1)) | (1ull << 52); const int E = ex - 1075;      // d = M * 2^E
+        // midpoints to the neighbouring doubles (below a power of two the spacing halves)
+        const bool pow2 = M == (1ull << 52);
+        const int c_lo = pow2 ? cmp_mid_sq(4 * M - 1, E - 2, P, Q) : cmp_mid_sq(2 * M - 1, E - 1, P, Q);
+        if (c_lo == 2) break;
+        if (c_lo > 0) { d = bits_to_f8(bits - 1); continue; }                          // the lower midpoint is already above sqrt(x): d is too large
+        if (c_lo == 0) return (M & 1) ? bits_to_f8(bits - 1) : d;                       // exactly half way: ties to even
+        const int c_hi = cmp_mid_sq(2 * M + 1, E - 1, P, Q);
+        if (c_hi == 2) break;
+        if (c_hi < 0) { d = bits_to_f8(bits + 1); continue; }                          // the upper midpoint is below sqrt(x): d is too small
+        if (c_hi == 0) return (M & 1) ? bits_to_f8(bits + 1) : d;
+        return d;
+    }
+    return sqrt_frac_rn_slow(P, Q);
 }
 
 // exact sample stdev of int values v[0..n) accessed through a functor (values fit in int32)
