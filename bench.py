@@ -195,7 +195,7 @@ def python_reference_baseline():
             return m
     except Exception as e:
         log(f"[bench] python reference leg failed: {e}")
-    p = os.path.join(ROOT, "tests", "golden", "python_reference_timing.json")
+    p = os.path.join(ROOT, "tests", "expected", "python_reference_timing.json")
     if os.path.exists(p):
         with open(p) as f:
             m = json.load(f)
@@ -228,7 +228,7 @@ def callset_hash(cand, alt, rnames, rn_off):
 
 
 def committed_hashes():
-    p = os.path.join(ROOT, "tests", "golden", "callset_hashes.json")
+    p = os.path.join(ROOT, "tests", "expected", "callset_hashes.json")
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
@@ -475,7 +475,7 @@ def run_b200(args):
                "callset_sha256": digest}
         if committed:
             out["parity_vs_n1"] = {"identical": digest == committed["sha256"], "n1_candidates": committed.get("n_cand"), "this_run_candidates": int(n_all),
-                                   "source": "tests/golden/callset_hashes.json (written by the 1-GPU run whose call set equals the oracle's)"}
+                                   "source": "tests/expected/callset_hashes.json (written by the 1-GPU run whose call set equals the oracle's)"}
         elif world > 1:
             out["parity_vs_n1"] = {"identical": None, "note": f"no committed N=1 hash for {key}"}
         if world == 1 and not args.no_cpu:
@@ -512,7 +512,7 @@ def main():
     ap.add_argument("--no-pin", action="store_true")
     ap.add_argument("--e2e-full-seq", action="store_true", help="e2e: copy the whole seq arena every step instead of the on-demand slices")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--write-hash", action="store_true", help="1 GPU: when the call set equals the oracle's, write its hash to gpurun_out/callset_hashes.json (to be committed under tests/golden/)")
+    ap.add_argument("--write-hash", action="store_true", help="1 GPU: when the call set equals the oracle's, write its hash to gpurun_out/callset_hashes.json (to be committed under tests/expected/)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         log("[bench] note: timing rules ask for >= 3 warm-up steps")

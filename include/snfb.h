@@ -57,16 +57,20 @@ enum { SNFB_SRC_INLINE = 0, SNFB_SRC_SPLIT_PRIM = 1, SNFB_SRC_SPLIT_SUP = 2, SNF
  * SNFB_CIGAR_BAM32: the BAM record's own words, len<<4|op (op: MIDNSHP=X = 0..8), 4 bytes per op.
  *
  * SNFB_CIGAR_16 (what the kernels read; snfb_pack_cigar16 produces it): 2-byte words, half the PCIe and HBM bytes.
- *   base word       bit 15 = 0, bits 12..14 = class, bits 0..11 = length & 0xfff
+ *   base word       bit 15 = 0, bit 14 = E, bits 11..13 = class, bits 0..10 = length & 0x7ff
  *                   class: 0 P (and the zero-length pad word 0x0000), 1 I, 2 D, 3 M/=/X, 4 H, 5 S, 6 N
- *                   (bit 12: the op advances the read, bit 13: it advances the reference, bit 14: clip / skip)
- *   extension word  bit 15 = 1, bits 12..14 = level (1 or 2), bits 0..11 = payload: adds payload << (12 * level) to the
+ *                   (bit 11: the op advances the read, bit 12: it advances the reference)
+ *                   E: the op is an I / D / S of at least the block's event length (snfb_records.cigar_evt_min, default
+ *                   SNFB_CIGAR16_EVT_MIN = 11: every SV signature and every indel the NM correction counts).  The streaming kernel
+ *                   only sums lengths and ORs this bit; a configuration that looks at shorter events re-flags the arena on the device.
+ *   extension word  bit 15 = 1, bits 12..14 = level (1 or 2), bits 0..11 = payload: adds payload << (11 + 12 * (level - 1)) to the
  *                   length of the base word it follows (level 1, then level 2; lengths up to 2^28 as in BAM)
  *   A base word and its extension words never straddle a 16-byte boundary and every record starts on one; the gaps and
  *   the tail of the arena are filled with pad words, so a 16-byte load never needs masking.
  *   M, = and X are one class: the path never tells them apart (leadprov.py:137-142 OPLIST). */
 #define SNFB_CIGAR_BAM32 0u
 #define SNFB_CIGAR_16 1u
+#define SNFB_CIGAR16_EVT_MIN 11u
 
 /* aux_flags bits of snfb_rec */
 #define SNFB_AUX_NM 1u
@@ -147,6 +151,8 @@ typedef struct snfb_records {
     uint32_t cigar_fmt;   /* SNFB_CIGAR_*; BAM32 host arenas are converted on the host inside snfb_load_records (device arenas must be CIGAR16) */
     const int32_t*  mask;
     const uint32_t* mask_task_off;   /* [n_task + 1]; may be NULL when n_mask == 0 */
+    uint32_t cigar_evt_min;          /* CIGAR16: the event length the E bits were set for (0 = SNFB_CIGAR16_EVT_MIN) */
+    uint32_t _pad2;
 } snfb_records;
 
 /* Flat POD of the reference's config values that the path reads (config.py:449-619). */
@@ -351,8 +357,9 @@ int         snfb_allgather_candidates(snfb_ctx* ctx, uint32_t flags, snfb_gather
 double      snfb_selftest_sqrt_frac(uint64_t p_hi, uint64_t p_lo, uint64_t q, int slow);
 /* BAM CIGAR words -> CIGAR16 (host code, OpenMP; no GPU needed).  rec_out receives copies of rec_in with cigar_off / n_cigar
  * rewritten for the 16-bit arena.  Call with out16 == NULL to get the number of 16-bit words the arena needs (a multiple
- * of 8); returns that number, or UINT64_MAX when a record holds an op the path does not know (B) or out_cap is too small. */
-uint64_t    snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, snfb_rec* rec_out, uint16_t* out16, uint64_t out_cap);
+ * of 8); returns that number, or UINT64_MAX when a record holds an op the path does not know (B) or out_cap is too small.
+ * evt_min: event length of the E bits (0 = SNFB_CIGAR16_EVT_MIN). */
+uint64_t    snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, snfb_rec* rec_out, uint16_t* out16, uint64_t out_cap, uint32_t evt_min);
 /* page-lock / unlock caller-owned host memory so that snfb_load_records copies at full PCIe rate */
 int         snfb_pin_host(void* p, size_t bytes);
 int         snfb_unpin_host(void* p);

@@ -3,7 +3,7 @@ synthetic blocks, htslib decode excluded (the reads are materialised before the 
 leg of bench.py.  TEST / BASELINE INFRASTRUCTURE: runs only where the reference tree exists
 (/root/reference/src or $SNIFFLES_REFERENCE_SRC); bench.py falls back to the committed measurement otherwise.
 
-    python oracle/pyref/timing.py --write          # refresh tests/golden/python_reference_timing.json (build container)
+    python oracle/pyref/timing.py --write          # refresh tests/expected/python_reference_timing.json (build container)
 """
 import json
 import logging
@@ -18,7 +18,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(_HERE))
 sys.path[:0] = [ROOT, _HERE]
-OUT = os.path.join(ROOT, "tests", "golden", "python_reference_timing.json")
+OUT = os.path.join(ROOT, "tests", "expected", "python_reference_timing.json")
 
 
 def available():

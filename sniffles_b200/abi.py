@@ -48,7 +48,8 @@ class Records(C.Structure):
                 ("rec", C.c_void_p), ("cigar", C.c_void_p), ("var", C.c_void_p), ("seq", C.c_void_p),
                 ("n_task", C.c_uint32), ("n_contig", C.c_uint32), ("n_tr", C.c_uint32), ("on_device", C.c_uint32),
                 ("task", C.c_void_p), ("contig", C.c_void_p), ("tr", C.c_void_p),
-                ("n_mask", C.c_uint32), ("cigar_fmt", C.c_uint32), ("mask", C.c_void_p), ("mask_task_off", C.c_void_p)]
+                ("n_mask", C.c_uint32), ("cigar_fmt", C.c_uint32), ("mask", C.c_void_p), ("mask_task_off", C.c_void_p),
+                ("cigar_evt_min", C.c_uint32), ("_pad2", C.c_uint32)]
 
 
 class Config(C.Structure):

@@ -57,7 +57,7 @@ def lib():
         L.snfb_selftest_sqrt_frac.restype = C.c_double
         L.snfb_selftest_sqrt_frac.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
         L.snfb_pack_cigar16.restype = C.c_uint64
-        L.snfb_pack_cigar16.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.snfb_pack_cigar16.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
         _LIB = L
     return _LIB
 
@@ -66,17 +66,17 @@ class SnfbError(RuntimeError):
     pass
 
 
-def pack_cigar16(rec: np.ndarray, cigar32: np.ndarray):
+def pack_cigar16(rec: np.ndarray, cigar32: np.ndarray, evt_min: int = 0):
     """BAM CIGAR words -> (rec16, cigar16) of include/snfb.h (host code of the library; needs no GPU)."""
     L = lib()
     rec = np.ascontiguousarray(rec)
     cigar32 = np.ascontiguousarray(cigar32, dtype="<u4")
-    need = L.snfb_pack_cigar16(rec.ctypes.data, len(rec), cigar32.ctypes.data, None, None, 0)
+    need = L.snfb_pack_cigar16(rec.ctypes.data, len(rec), cigar32.ctypes.data, None, None, 0, int(evt_min))
     if need == 0xFFFFFFFFFFFFFFFF:
         raise SnfbError("snfb_pack_cigar16: a CIGAR holds an operation the path does not know")
     rec16 = np.empty(len(rec), abi.REC_DTYPE)
     cigar16 = np.empty(int(need), "<u2")
-    got = L.snfb_pack_cigar16(rec.ctypes.data, len(rec), cigar32.ctypes.data, rec16.ctypes.data, cigar16.ctypes.data, int(need))
+    got = L.snfb_pack_cigar16(rec.ctypes.data, len(rec), cigar32.ctypes.data, rec16.ctypes.data, cigar16.ctypes.data, int(need), int(evt_min))
     if got != need:
         raise SnfbError("snfb_pack_cigar16 failed")
     return rec16, cigar16

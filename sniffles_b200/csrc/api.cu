@@ -88,7 +88,7 @@ struct snfb_ctx {
     int device = 0; cudaStream_t st = nullptr, st_copy = nullptr, st_side = nullptr; cudaEvent_t ev_b = nullptr, ev_mid = nullptr, ev_fork = nullptr, ev_join = nullptr; std::string err;
     snfb_config cfg{}; bool have_cfg = false;
     // records
-    bool loaded = false, on_device = false, seq_on_demand = false; const uint8_t* h_seq = nullptr;
+    bool loaded = false, on_device = false, seq_on_demand = false; const uint8_t* h_seq = nullptr; uint32_t evt_min = 0;     // E-bit threshold of the loaded CIGAR16 arena
     uint64_t n_rec = 0, n_cigar = 0, n_var = 0, n_seq = 0; uint32_t n_task = 0, n_contig = 0, n_tr = 0, n_mask = 0;
     const snfb_rec* d_rec = nullptr; const uint16_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
     DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp, b_mask, b_mask_off, b_mask_task;
@@ -99,6 +99,7 @@ struct snfb_ctx {
     DevBuf b_ctr, arena_r, arena_l, arena_c;            // counters; per-record arrays; per-lead arrays (stages A + B); stage C
     uint64_t arena_r_for = 0; Caps arena_l_for, arena_c_for; uint32_t arena_r_tasks = 0;
     // per-record (arena_r)
+    uint32_t* pass_flag; uint32_t* pass_groups; uint32_t* pidx; uint32_t* vst; extract::PDesc* pdesc; uint32_t* pvs;
     int32_t* rec_pos; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead; uint32_t* rec_lead_off; uint32_t* sa_list; extract::RecScan* scanrec; extract::RecClip* clip; int32_t* rec_big;
     uint32_t* task_first; uint32_t* task_last; uint32_t* task_reads; unsigned long long* task_cov; int32_t* task_span; double* task_nm; double* nm_part; unsigned* nm_cnt; extract::Seg* sa_seg; uint32_t* scan_tmp_r;
     // per-lead (arena_l): stage A leads + the whole of stage B
@@ -117,6 +118,13 @@ struct snfb_ctx {
     cudaEvent_t ev[MAX_TIMINGS + 1]; const char* ev_name[MAX_TIMINGS + 1]; uint64_t ev_bytes[MAX_TIMINGS + 1]; int n_ev = 0; int n_ev_load = 0; uint64_t launches = 0; uint64_t reruns = 0;
 };
 
+// the shortest I / D / S the configured path looks at: SV signatures of minsvlen_screen, indels above 10 for the NM correction (leadprov.py:198-224)
+static uint32_t evt_need(const snfb_ctx* ctx) {
+    if (!ctx->have_cfg) return SNFB_CIGAR16_EVT_MIN;
+    int t = ctx->cfg.minsvlen_screen < 1 ? 1 : ctx->cfg.minsvlen_screen;
+    if ((ctx->cfg.qc_nm_measure || ctx->cfg.phase) && t > 11) t = 11;
+    return (uint32_t)(t < (int)SNFB_CIGAR16_EVT_MIN ? t : (int)SNFB_CIGAR16_EVT_MIN);
+}
 static void ctx_fail(snfb_ctx* ctx, const char* what, const char* msg) { ctx->err = std::string(what) + ": " + msg; }
 static int fail(snfb_ctx* ctx, const std::string& m) { ctx->err = m; return 1; }
 
@@ -268,7 +276,7 @@ int snfb_set_config(snfb_ctx* ctx, const snfb_config* cfg) {
 }
 
 // ---- BAM CIGAR words -> CIGAR16 (include/snfb.h).  Host code; the only place the 32-bit form is read. ----
-static inline int c16_group_words(uint32_t len) { return len < (1u << 12) ? 1 : (len < (1u << 24) ? 2 : 3); }
+static inline int c16_group_words(uint32_t len) { return len < (1u << 11) ? 1 : (len < (1u << 23) ? 2 : 3); }
 static const uint8_t C16_CLASS[9] = { 3, 1, 2, 6, 5, 4, 0, 3, 3 };     // M I D N S H P = X
 // number of 16-bit words of one record, pad words included (a group never straddles an 8-word boundary); 0 = bad op
 static inline uint64_t c16_count(const uint32_t* cg, uint32_t n, bool* bad) {
@@ -281,18 +289,20 @@ static inline uint64_t c16_count(const uint32_t* cg, uint32_t n, bool* bad) {
     }
     return k;
 }
-static inline void c16_write(const uint32_t* cg, uint32_t n, uint16_t* out) {
+static inline void c16_write(const uint32_t* cg, uint32_t n, uint16_t* out, uint32_t evt_min) {
     uint64_t k = 0;
     for (uint32_t i = 0; i < n; ++i) {
-        const uint32_t len = cg[i] >> 4; const int g = c16_group_words(len);
+        const uint32_t len = cg[i] >> 4; const int g = c16_group_words(len); const unsigned cls = C16_CLASS[cg[i] & 15u];
         if ((k & 7) + g > 8) { while (k & 7) out[k++] = 0; }
-        out[k++] = (uint16_t)((C16_CLASS[cg[i] & 15u] << 12) | (len & 0xfffu));
-        if (g >= 2) out[k++] = (uint16_t)(0x8000u | (1u << 12) | ((len >> 12) & 0xfffu));
-        if (g >= 3) out[k++] = (uint16_t)(0x8000u | (2u << 12) | ((len >> 24) & 0xfffu));
+        const unsigned e = ((cls == 1 || cls == 2 || cls == 5) && len >= evt_min) ? 0x4000u : 0u;      // E: an I / D / S the streaming kernel has to look at
+        out[k++] = (uint16_t)(e | (cls << 11) | (len & 0x7ffu));
+        if (g >= 2) out[k++] = (uint16_t)(0x8000u | (1u << 12) | ((len >> 11) & 0xfffu));
+        if (g >= 3) out[k++] = (uint16_t)(0x8000u | (2u << 12) | ((len >> 23) & 0xfffu));
     }
 }
-uint64_t snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, snfb_rec* rec_out, uint16_t* out16, uint64_t out_cap) {
+uint64_t snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, snfb_rec* rec_out, uint16_t* out16, uint64_t out_cap, uint32_t evt_min) {
     if (n_rec && (!rec_in || !cigar32)) return UINT64_MAX;
+    if (evt_min == 0) evt_min = SNFB_CIGAR16_EVT_MIN;
     std::vector<uint64_t> off(n_rec + 1, 0);
     bool bad = false;
     #pragma omp parallel for schedule(static) reduction(|| : bad)
@@ -306,7 +316,7 @@ uint64_t snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_
     for (long long i = 0; i < (long long)n_rec; ++i) {
         uint16_t* dst = out16 + off[i]; const uint64_t span = off[i + 1] - off[i];
         memset(dst, 0, 2 * span);
-        c16_write(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, dst);
+        c16_write(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, dst, evt_min);
         bool b = false;
         snfb_rec r = rec_in[i]; r.n_cigar = (uint32_t)c16_count(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, &b); r.cigar_off = off[i];
         rec_out[i] = r;
@@ -350,12 +360,14 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
         if (R->on_device == SNFB_MEM_DEVICE) return fail(ctx, "device-resident records must carry CIGAR16 (convert with snfb_pack_cigar16)");
         for (uint64_t i = 0; i < R->n_rec; ++i) if (R->rec[i].cigar_off + (uint64_t)R->rec[i].n_cigar > R->n_cigar) return fail(ctx, "a record's CIGAR lies outside the cigar arena");
         // host conversion: the kernels only read CIGAR16
-        const uint64_t need = snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), nullptr, nullptr, 0);
+        const uint64_t need = snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), nullptr, nullptr, 0, 0);
         if (need == UINT64_MAX) return fail(ctx, "a CIGAR holds an operation the path does not know");
         if (ctx->h_c16.ensure(2 * need + 16) || ctx->h_rec16.ensure(sizeof(snfb_rec) * (R->n_rec + 1))) return fail(ctx, "out of pinned memory for the CIGAR16 conversion");
-        if (snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), ctx->h_rec16.as<snfb_rec>(), ctx->h_c16.as<uint16_t>(), need) != need) return fail(ctx, "CIGAR16 conversion failed");
+        if (snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), ctx->h_rec16.as<snfb_rec>(), ctx->h_c16.as<uint16_t>(), need, evt_need(ctx)) != need) return fail(ctx, "CIGAR16 conversion failed");
         src_rec = ctx->h_rec16.as<snfb_rec>(); src_cigar = ctx->h_c16.as<uint16_t>(); n_words = need;
+        ctx->evt_min = evt_need(ctx);
     } else if (R->cigar_fmt != SNFB_CIGAR_16) return fail(ctx, "unknown cigar_fmt");
+    else ctx->evt_min = R->cigar_evt_min ? R->cigar_evt_min : SNFB_CIGAR16_EVT_MIN;
     if (n_words & 7) return fail(ctx, "a CIGAR16 arena must be padded to a multiple of 8 words");
     ctx->n_cigar = n_words;
     mark(ctx, "h2d_records", sizeof(snfb_rec) * R->n_rec + 2 * n_words + R->n_var + (R->on_device == SNFB_MEM_HOST_SEQ_ON_DEMAND ? 0 : R->n_seq));
@@ -404,6 +416,7 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
 static void carve_r(snfb_ctx* ctx, Carver& c) {
     const size_t n = ctx->n_rec + 1, nt = ctx->n_task;
     ctx->rec_pos = c.take<int32_t>(n); ctx->rec_end = c.take<int32_t>(n); ctx->rec_flags = c.take<uint8_t>(n); ctx->rec_nm = c.take<double>(n); ctx->rec_nlead = c.take<uint32_t>(n); ctx->rec_lead_off = c.take<uint32_t>(n);
+    ctx->pass_flag = c.take<uint32_t>(n); ctx->pass_groups = c.take<uint32_t>(n); ctx->pidx = c.take<uint32_t>(n); ctx->vst = c.take<uint32_t>(n); ctx->pdesc = c.take<extract::PDesc>(n); ctx->pvs = c.take<uint32_t>(n + 1);
     ctx->sa_list = c.take<uint32_t>(n); ctx->scanrec = c.take<extract::RecScan>(n); ctx->clip = c.take<extract::RecClip>(n); ctx->rec_big = c.take<int32_t>(n);
     ctx->task_first = c.take<uint32_t>(nt); ctx->task_last = c.take<uint32_t>(nt); ctx->task_reads = c.take<uint32_t>(nt); ctx->task_cov = c.take<unsigned long long>(nt); ctx->task_span = c.take<int32_t>(nt); ctx->task_nm = c.take<double>(nt);
     const size_t cpt = (ctx->n_rec + extract::NM_CHUNK - 1) / extract::NM_CHUNK + 1;
@@ -485,25 +498,34 @@ static int enqueue_stage_a(snfb_ctx* ctx) {
     CUDA_TRY(cudaMemsetAsync(ctx->task_reads, 0, 4 * nt, st)); CUDA_TRY(cudaMemsetAsync(ctx->task_cov, 0, 8 * nt, st)); CUDA_TRY(cudaMemsetAsync(ctx->task_span, 0, 4 * nt, st));
     CUDA_TRY(cudaMemsetAsync(ctx->task_nm, 0, 8 * nt, st));
     extract::ScanParams S{};
-    S.scan = ctx->scanrec; S.cigar = ctx->d_cigar; S.task = b.task; S.n_rec = (uint32_t)nrec; S.rec_end = ctx->rec_end; S.rec_nlead = ctx->rec_nlead; S.rec_big = ctx->rec_big;
+    S.pdesc = ctx->pdesc; S.pvs = ctx->pvs; S.cigar = ctx->d_cigar; S.task = b.task; S.rec_end = ctx->rec_end; S.rec_nlead = ctx->rec_nlead; S.rec_big = ctx->rec_big;
     S.ev = ctx->ev_buf; S.ev_cap = ctx->cap.lead; S.n_ev = &ctr->n_ev; S.sa_list = ctx->sa_list; S.n_sa = &ctr->n_sa; S.ctr = ctr; S.minsv = cf.minsvlen_screen;
-    { const bool want_nm = cf.qc_nm_measure || cf.phase; int t = cf.minsvlen_screen < 1 ? 1 : cf.minsvlen_screen; if (want_nm && t > 11) t = 11; if (t > 0x1000) t = 0x1000;
-      S.gt_add = (uint32_t)(0x1000 - t) * 0x00010001u; }
+    if (evt_need(ctx) < ctx->evt_min) {
+        // the block's E bits were set for longer events than this configuration looks at: lower the threshold in place
+        if (ctx->on_device) return fail(ctx, "the device-resident CIGAR16 arena was packed with a larger event length than the configuration needs: repack with snfb_pack_cigar16(evt_min)");
+        extract::k_reflag<<<148 * 8, 256, 0, st>>>(const_cast<uint16_t*>(ctx->d_cigar), ctx->n_cigar, evt_need(ctx)); LAUNCHED(ctx, 1);
+        ctx->evt_min = evt_need(ctx);
+    }
     mark(ctx, "k_rec_index");
     if (nrec) {
         k_validate<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(ctx->d_rec, (uint32_t)nrec, nt, ctx->n_cigar, ctx->n_var, ctx->n_seq, ctx->seq_on_demand ? 0 : 1, ctr);
         extract::IndexParams I{};
-        I.rec = ctx->d_rec; I.cigar = ctx->d_cigar; I.task = S.task; I.n_rec = (uint32_t)nrec; I.n_task = nt; I.rec_pos = ctx->rec_pos; I.task_first = ctx->task_first; I.task_last = ctx->task_last;
-        I.scan = ctx->scanrec; I.clip = ctx->clip; I.rec_end = S.rec_end; I.rec_flags = ctx->rec_flags; I.rec_nm = ctx->rec_nm; I.rec_nlead = S.rec_nlead; I.ctr = ctr;
+        I.rec = ctx->d_rec; I.cigar = ctx->d_cigar; I.task = b.task; I.n_rec = (uint32_t)nrec; I.n_task = nt; I.rec_pos = ctx->rec_pos; I.task_first = ctx->task_first; I.task_last = ctx->task_last;
+        I.scan = ctx->scanrec; I.clip = ctx->clip; I.rec_end = ctx->rec_end; I.rec_flags = ctx->rec_flags; I.rec_nm = ctx->rec_nm; I.rec_nlead = ctx->rec_nlead; I.ctr = ctr;
         I.mapq_min = cf.mapq; I.alen_min = cf.min_alignment_length; I.excl = cf.exclude_flags; I.want_nm = (cf.qc_nm_measure || cf.phase) ? 1 : 0; I.n_cigar = ctx->n_cigar;
+        I.pass_flag = ctx->pass_flag; I.pass_groups = ctx->pass_groups;
         extract::k_rec_index<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(I);
+        // sweep order of the streaming kernel: ordinal and first virtual group of every passing record
+        LAUNCHED(ctx, prims::exclusive_scan(ctx->pass_flag, ctx->pidx, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_passrec, st));
+        LAUNCHED(ctx, prims::exclusive_scan(ctx->pass_groups, ctx->vst, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_vgroups, st));
+        extract::PDescParams D{}; D.scan = ctx->scanrec; D.pidx = ctx->pidx; D.vst = ctx->vst; D.n_rec = (uint32_t)nrec; D.pdesc = ctx->pdesc; D.pvs = ctx->pvs; D.ctr = ctr;
+        extract::k_pdesc<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(D); LAUNCHED(ctx, 1);
         // algorithmic bytes of the streaming kernel: scan descriptors + CIGAR16 words (+ its per-record outputs and event slices, added by bench.py)
         mark(ctx, "k_scan", sizeof(extract::RecScan) * nrec + 2 * ctx->n_cigar);
-        unsigned long long blocks = (nrec + 7) / 8; const unsigned long long maxb = 148ull * 6 * 4;
-        extract::k_scan<<<(int)std::min(blocks, maxb), 256, 0, st>>>(S);
+        extract::k_scan<<<148 * 8, 256, 0, st>>>(S);
         mark(ctx, "k_rec_post");
         extract::PostParams Q{};
-        Q.scan = I.scan; Q.clip = I.clip; Q.task = S.task; Q.n_rec = (uint32_t)nrec; Q.rec_end = S.rec_end; Q.rec_big = S.rec_big; Q.rec_nm = ctx->rec_nm;
+        Q.scan = I.scan; Q.clip = I.clip; Q.task = b.task; Q.n_rec = (uint32_t)nrec; Q.rec_end = ctx->rec_end; Q.rec_big = ctx->rec_big; Q.rec_nm = ctx->rec_nm;
         Q.task_reads = ctx->task_reads; Q.task_cov_bp = ctx->task_cov; Q.task_maxspan = ctx->task_span;
         extract::k_rec_post<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(Q);
         mark(ctx, "k_emit");
@@ -513,8 +535,8 @@ static int enqueue_stage_a(snfb_ctx* ctx) {
         extract::k_emit<<<148 * 16, 128, 0, st>>>(E);
         mark(ctx, "k_sa");
         extract::SaParams A{};
-        A.rec = ctx->d_rec; A.clip = ctx->clip; A.var = ctx->d_var; A.task = S.task; A.contig = b.contig; A.n_contig = ctx->n_contig;
-        A.sa_list = S.sa_list; A.n_sa = S.n_sa; A.rec_end = S.rec_end; A.rec_nlead = S.rec_nlead; A.leads = E.leads; A.lead_cap = ctx->cap.lead; A.ctr = ctr; A.cfg = cf; A.seg_scratch = ctx->sa_seg;
+        A.rec = ctx->d_rec; A.clip = ctx->clip; A.var = ctx->d_var; A.task = b.task; A.contig = b.contig; A.n_contig = ctx->n_contig;
+        A.sa_list = S.sa_list; A.n_sa = S.n_sa; A.rec_end = ctx->rec_end; A.rec_nlead = ctx->rec_nlead; A.leads = E.leads; A.lead_cap = ctx->cap.lead; A.ctr = ctr; A.cfg = cf; A.seg_scratch = ctx->sa_seg;
         extract::k_sa<<<extract::SA_BLOCKS, extract::SA_THREADS, 0, st>>>(A);
         mark(ctx, "k_task_nm");
         const int cpt = (int)((nrec + extract::NM_CHUNK - 1) / extract::NM_CHUNK);
@@ -522,7 +544,7 @@ static int enqueue_stage_a(snfb_ctx* ctx) {
         extract::k_task_nm<<<nt, 256, 0, st>>>(ctx->task_first, ctx->task_last, ctx->nm_part, ctx->nm_cnt, cpt, ctx->task_nm); LAUNCHED(ctx, 8);
     }
     mark(ctx, "scan_rec_leads");
-    LAUNCHED(ctx, prims::exclusive_scan(S.rec_nlead, ctx->rec_lead_off, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_leads, st));
+    LAUNCHED(ctx, prims::exclusive_scan(ctx->rec_nlead, ctx->rec_lead_off, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_leads, st));
     const unsigned long long nb = b.n_bound; const int g = grid_for(nb, 256);
     mark(ctx, "sort_leads");
     cluster::k_scatter_keys<<<g, 256, 0, st>>>(b);

@@ -248,9 +248,14 @@ __device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp
 //   k_emit  one warp per event slice: reload the slice (L2), prefix positions, write the 64-byte leads to exact slots.
 //   k_sa    one warp per record with an SA tag: Lead.for_bnd + read_itersplits (lane-serial text parsing).
 // ================================================================================================
-// CIGAR16 classes (include/snfb.h): bit 0 = advances the read, bit 1 = advances the reference
+// CIGAR16 (include/snfb.h): base word = [15] 0 | [14] E | [13:11] class | [10:0] length & 0x7ff; class bit 0 (word bit 11) = advances the
+// read, class bit 1 (word bit 12) = advances the reference; E = an I / D / S of at least the block's event length (what the streaming
+// kernel must look at).  Extension word = [15] 1 | [14:12] level (1, 2) | [11:0] payload, adding payload << (11 + 12 * (level - 1)).
 constexpr unsigned C16_I = 1, C16_D = 2, C16_M = 3, C16_H = 4, C16_S = 5;
+constexpr unsigned C16_LEN_BITS = 11, C16_LEN_MASK = 0x7ffu, C16_E = 0x4000u;
 __device__ __forceinline__ bool c16_is_event(unsigned cls) { return (0x26u >> cls) & 1u; }        // I D S
+__device__ __forceinline__ unsigned c16_class(unsigned w) { return (w >> C16_LEN_BITS) & 7u; }
+__device__ __forceinline__ unsigned c16_ext_add(unsigned e) { return (e & 0xfffu) << (C16_LEN_BITS + 12u * (((e >> 12) & 7u) - 1u)); }
 
 // the eight 16-bit words one lane holds -> up to eight ops at their word positions (cls 0 / len 0 where a pad, P or
 // extension word sits).  Groups never straddle a 16-byte boundary, so this is lane-local.
@@ -262,10 +267,10 @@ __device__ __forceinline__ void c16_decode8(const uint32_t (&ww)[4], unsigned (&
     for (int h = 0; h < 8; ++h) {
         unsigned c = 0, l = 0;
         if (!(x[h] & 0x8000u)) {
-            c = (x[h] >> 12) & 7u; l = x[h] & 0xfffu;
+            c = c16_class(x[h]); l = x[h] & C16_LEN_MASK;
             if (h + 1 < 8 && (x[h + 1 < 8 ? h + 1 : 7] & 0x8000u)) {
-                const unsigned e1 = x[h + 1 < 8 ? h + 1 : 7]; l += (e1 & 0xfffu) << (12u * ((e1 >> 12) & 7u));
-                if (h + 2 < 8 && (x[h + 2 < 8 ? h + 2 : 7] & 0x8000u)) { const unsigned e2 = x[h + 2 < 8 ? h + 2 : 7]; l += (e2 & 0xfffu) << (12u * ((e2 >> 12) & 7u)); }
+                l += c16_ext_add(x[h + 1 < 8 ? h + 1 : 7]);
+                if (h + 2 < 8 && (x[h + 2 < 8 ? h + 2 : 7] & 0x8000u)) l += c16_ext_add(x[h + 2 < 8 ? h + 2 : 7]);
             }
         }
         cls[h] = c; len[h] = l;
@@ -280,6 +285,7 @@ struct IndexParams {
     const snfb_rec* rec; const uint16_t* cigar; const snfb_task* task; uint32_t n_rec; uint32_t n_task; unsigned long long n_cigar;
     int32_t* rec_pos; uint32_t* task_first; uint32_t* task_last;
     RecScan* scan; RecClip* clip; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
+    uint32_t* pass_flag; uint32_t* pass_groups;      // 1 / number of 16-byte CIGAR16 groups for a passing record, else 0 (scanned into the sweep order)
     DevCounters* ctr; int mapq_min, alen_min, excl, want_nm;
 };
 // leadprov.py:488-516 (filters), pysam query_alignment_start / query_alignment_end
@@ -293,7 +299,7 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     if ((uint32_t)task >= P.n_task || (cigar_off & 7) || cigar_off + n > P.n_cigar) {      // malformed record (counted by k_validate: the run fails); touch nothing through its offsets
         RecScan s; s.cig8 = 0; s.n_words = 0; s.pos = pos; s.meta = 0; *reinterpret_cast<uint4*>(P.scan + i) = *reinterpret_cast<const uint4*>(&s);
         RecClip c; c.alen = 0; c.qas = 0; c.clip_left = 0; c.clip_right = 0; *reinterpret_cast<int4*>(P.clip + i) = *reinterpret_cast<const int4*>(&c);
-        P.rec_pos[i] = pos; P.rec_flags[i] = 0; P.rec_nm[i] = -1.0; P.rec_end[i] = -1; P.rec_nlead[i] = 0; return;
+        P.rec_pos[i] = pos; P.rec_flags[i] = 0; P.rec_nm[i] = -1.0; P.rec_end[i] = -1; P.rec_nlead[i] = 0; P.pass_flag[i] = 0; P.pass_groups[i] = 0; return;
     }
     P.rec_pos[i] = pos;
     if (i == 0) P.task_first[task] = 0;
@@ -305,8 +311,8 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     { bool first = true; uint32_t k = 0;
       while (k < n) {
           const unsigned w = __ldg(cg + k); if (w == 0) { ++k; continue; }
-          unsigned len = w & 0xfffu; const unsigned cls = (w >> 12) & 7u; uint32_t k2 = k + 1;
-          while (k2 < n) { const unsigned e = __ldg(cg + k2); if (!(e & 0x8000u)) break; len += (e & 0xfffu) << (12u * ((e >> 12) & 7u)); ++k2; }
+          unsigned len = w & C16_LEN_MASK; const unsigned cls = c16_class(w); uint32_t k2 = k + 1;
+          while (k2 < n) { const unsigned e = __ldg(cg + k2); if (!(e & 0x8000u)) break; len += c16_ext_add(e); ++k2; }
           if (first) { if (cls == C16_S || cls == C16_H) clip_left = (int)len; first = false; fe = k2; }
           if (cls == C16_S) qas += (int)len; else if (cls != C16_H) break;
           k = k2;
@@ -315,8 +321,8 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
       while (k >= (long)fe) {
           long b = k; while (b > (long)fe && (__ldg(cg + b) & 0x8000u)) --b;
           const unsigned w = __ldg(cg + b); if (w == 0) { k = b - 1; continue; }
-          unsigned len = w & 0xfffu; const unsigned cls = (w >> 12) & 7u;
-          for (long e2 = b + 1; e2 <= k; ++e2) { const unsigned e = __ldg(cg + e2); len += (e & 0xfffu) << (12u * ((e >> 12) & 7u)); }
+          unsigned len = w & C16_LEN_MASK; const unsigned cls = c16_class(w);
+          for (long e2 = b + 1; e2 <= k; ++e2) { const unsigned e = __ldg(cg + e2); len += c16_ext_add(e); }
           if (last) { if (cls == C16_S || cls == C16_H) clip_right = (int)len; last = false; }
           if (cls == C16_S) qae -= (int)len; else if (cls != C16_H) break;
           k = b - 1;
@@ -336,71 +342,56 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     P.rec_flags[i] = pass ? (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2)) : (uint8_t)0;
     P.rec_nm[i] = has_nm ? (double)nm : -1.0;        // k_rec_post turns it into (nm - big) / (alen + 1)
     P.rec_end[i] = -1; P.rec_nlead[i] = 0;
+    P.pass_flag[i] = pass ? 1u : 0u; P.pass_groups[i] = pass ? (n + 7u) >> 3 : 0u;
 }
 
 // one SV signature found by k_scan (an I / D / S op of at least minsvlen_screen inside the task's region): all k_emit needs to build its lead
 struct Event { uint32_t rec; uint32_t len; uint32_t pos_q; int32_t pos_r; uint32_t k_cls; uint32_t pad[3]; };   // k_cls: k | class << 16
 
+// descriptor of one PASSING record in the order the streaming kernel sweeps them (32 bytes, loaded as a window of 32 per warp)
+struct PDesc { uint32_t cig8; uint32_t vs; int32_t pos; uint32_t meta; uint32_t rec; uint32_t pad0, pad1, pad2; };   // vs: first virtual group
+
 struct ScanParams {
-    const RecScan* scan; const uint16_t* cigar; const snfb_task* task;
-    uint32_t n_rec;
+    const PDesc* pdesc; const uint32_t* pvs;          // [n_pass], [n_pass + 1] (pvs[n_pass] = total virtual groups)
+    const uint16_t* cigar; const snfb_task* task;
     int32_t* rec_end; uint32_t* rec_nlead; int32_t* rec_big;
     Event* ev; unsigned long long ev_cap; unsigned long long* n_ev;
     uint32_t* sa_list; unsigned long long* n_sa;
     DevCounters* ctr;
     int minsv;
-    uint32_t gt_add;      // (0x1000 - t) in both halves: bit 12 / 28 of (length + gt_add) says length >= t, t = the shortest length the rare path cares about
 };
 
-// rare path of k_scan: a slice with an I / D / S that may be a signature (or count for the NM correction) or an extension word.  SV signatures are
-// appended to the event list (any order: a lead's place is fixed later by its record and k).  Returns (big << 32) | leads counted.
-__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr,
-                                                      uint32_t rec, unsigned pos_q, int pos_r, unsigned k0, int tk_start, int tk_end) {
-    const int lane = lane_id();
-    const uint32_t ww[4] = { w0, w1, w2, w3 };
-    unsigned cls[8], len[8];
-    c16_decode8(ww, cls, len);
-    unsigned big = 0, evm = 0;
-    #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (len[j] > 10u && (cls[j] == C16_I || cls[j] == C16_D)) big += len[j];             // get_cigar_indels, minoplen 10
-        if (c16_is_event(cls[j]) && (int)len[j] >= P->minsv) evm |= 1u << j; }
-    big = __reduce_add_sync(FULL, big);
-    unsigned count = 0;
-    if (__any_sync(FULL, evm != 0)) {
-        unsigned iq = lq, ir = lr;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned tq = __shfl_up_sync(FULL, iq, o), tr = __shfl_up_sync(FULL, ir, o); if (lane >= o) { iq += tq; ir += tr; } }
-        const unsigned q0 = pos_q + iq - lq; const int r0 = pos_r + (int)(ir - lr);
-        // which signatures stay inside the task's region (leadprov.py:464-466)
-        unsigned emm = 0, cnt = 0; { int r2 = r0;
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; if (rs >= tk_start && rs < tk_end) { emm |= 1u << j; ++cnt; } }
-                r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); } }
-        unsigned inc = cnt;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-        count = __shfl_sync(FULL, inc, 31);
-        if (count) {
-            unsigned long long e0 = 0; if (lane == 0) e0 = atomicAdd(P->n_ev, (unsigned long long)count);
-            e0 = __shfl_sync(FULL, e0, 0);
-            unsigned mine = inc - cnt; unsigned q2 = q0; int r2 = r0;
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (emm & (1u << j)) {
-                    const unsigned long long e = e0 + mine;
-                    if (e < P->ev_cap) { uint4* dst = reinterpret_cast<uint4*>(P->ev + e); dst[0] = make_uint4(rec, len[j], q2, (uint32_t)r2); dst[1] = make_uint4((k0 + mine) | (cls[j] << 16), 0u, 0u, 0u); }
-                    else atomicAdd(&P->ctr->lead_overflow, 1ULL);
-                    ++mine;
-                }
-                q2 += len[j] * (cls[j] & 1u); r2 += (int)(len[j] * ((cls[j] >> 1) & 1u));
-            }
-        }
+// thread per record: passing records get their ordinal and first virtual group from two scans; this writes their sweep descriptors
+struct PDescParams { const RecScan* scan; const uint32_t* pidx; const uint32_t* vst; uint32_t n_rec; PDesc* pdesc; uint32_t* pvs; const DevCounters* ctr; };
+__global__ void __launch_bounds__(256) k_pdesc(const PDescParams P) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i == 0) P.pvs[P.ctr->n_passrec] = (uint32_t)P.ctr->n_vgroups;
+    if (i >= P.n_rec) return;
+    const uint4 d = __ldg(reinterpret_cast<const uint4*>(P.scan + i));
+    if (!(d.w & RM_PASS)) return;
+    const uint32_t p = P.pidx[i], vs = P.vst[i];
+    PDesc o; o.cig8 = d.x; o.vs = vs; o.pos = (int32_t)d.z; o.meta = d.w; o.rec = i; o.pad0 = o.pad1 = o.pad2 = 0;
+    uint4* dst = reinterpret_cast<uint4*>(P.pdesc + p); dst[0] = make_uint4(o.cig8, o.vs, (uint32_t)o.pos, o.meta); dst[1] = make_uint4(o.rec, 0u, 0u, 0u);
+    P.pvs[p] = vs;
+}
+// lowers the E-bit threshold of a CIGAR16 arena in place (a config that cares about shorter events than the block was packed for)
+__global__ void k_reflag(uint16_t* __restrict__ cigar, unsigned long long n_words, unsigned evt_min) {
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n_words; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned w = cigar[i]; if (w & 0x8000u) continue;
+        const unsigned cls = c16_class(w);
+        if (!c16_is_event(cls) || (w & C16_E)) continue;
+        bool big = (w & C16_LEN_MASK) >= evt_min;
+        if (!big && (i & 7) != 7) big = (cigar[i + 1] & 0x8000u) != 0;          // an extension word follows: the length is at least 2048
+        if (big) cigar[i] = (uint16_t)(w | C16_E);
     }
-    return ((unsigned long long)big << 32) | count;
 }
 
+// segmented inclusive scan over the lanes of a warp; seg0 = the lane the calling lane's segment starts at
+__device__ __forceinline__ unsigned seg_incl_scan(unsigned v, int lane, int seg0) {
+    #pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, v, o); if (lane - o >= seg0) v += t; }
+    return v;
+}
 // read / reference advance of a lane's eight words when one of them is an extension word
 __device__ __noinline__ uint2 lane_sums_ext(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     const uint32_t ww[4] = { w0, w1, w2, w3 };
@@ -410,53 +401,198 @@ __device__ __noinline__ uint2 lane_sums_ext(uint32_t w0, uint32_t w1, uint32_t w
     for (int j = 0; j < 8; ++j) { lq += len[j] * (cls[j] & 1u); lr += len[j] * ((cls[j] >> 1) & 1u); }
     return make_uint2(lq, lr);
 }
-
-__global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanParams P) {
+// rare path of k_scan: a step in which some lane holds a flagged word (E bit or extension word).  Every lane passes its own record
+// (a step can span several short records: segments), the positions / lead ordinal its segment starts from, and its region.
+// SV signatures are appended to the event list (any order: a lead's place is fixed later by its record and k).
+// Returns (big << 32) | events counted, per lane.
+__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr, int seg0,
+                                                      uint32_t rec, unsigned base_q, int base_r, unsigned base_k, int tk_start, int tk_end) {
     const int lane = lane_id();
-    const unsigned nwarps = gridDim.x * 8;
-    int tk_id = -1, tk_start = 0, tk_end = 0;
-    unsigned rec = blockIdx.x * 8 + (threadIdx.x >> 5);
-    uint4 dnext = rec < P.n_rec ? __ldg(reinterpret_cast<const uint4*>(P.scan + rec)) : make_uint4(0, 0, 0, 0);
-    for (; rec < P.n_rec; rec += nwarps) {
-        const uint4 d = dnext;
-        { const unsigned nrec2 = rec + nwarps; dnext = nrec2 < P.n_rec ? __ldg(reinterpret_cast<const uint4*>(P.scan + nrec2)) : make_uint4(0, 0, 0, 0); }
-        if (!(d.w & RM_PASS)) continue;
-        const int n = (int)d.y, r_pos = (int)d.z, r_task = (int)(d.w & 0xffffu);
-        const uint4* __restrict__ cga = reinterpret_cast<const uint4*>(P.cigar) + d.x + lane;
-        const int li0 = lane * 8;
-        #define LOAD_SLICE(base) (((base) + li0 < n) ? __ldg(cga + ((base) >> 3)) : make_uint4(0, 0, 0, 0))
-        uint4 va = LOAD_SLICE(0), vb = LOAD_SLICE(256);
-        if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; }
-        unsigned pos_q = 0; int pos_r = r_pos; unsigned big = 0, nlead = 0; const uint32_t gt_add = P.gt_add;
-        // Two ops per 32-bit word: both halves are summed at once (a lane's eight 12-bit lengths cannot overflow 16 bits).
-        // bit 12 / 28 of `rb` flags a half that needs the rare path: an I / D / S of at least the length the path cares about
-        // (minsvlen_screen, or 11 when the NM correction is wanted), or an extension word.
-        #define WORD_BODY(w) { const uint32_t s_ = (w) >> 12, s1_ = (w) >> 1, s2_ = (w) >> 2; \
-            aq += (w) & ((s_ & 0x00010001u) * 0xfffu); ar += (w) & (((s_ >> 1) & 0x00010001u) * 0xfffu); \
-            rb |= ((((w) & 0x0fff0fffu) + gt_add) & ((w) ^ s1_) & ~(s1_ & s2_)) | ((w) >> 3); }
-        #define SLICE_BODY(v, base) { \
-            const uint32_t w0 = (v).x, w1 = (v).y, w2 = (v).z, w3 = (v).w; \
-            uint32_t aq = 0, ar = 0, rb = 0; \
-            WORD_BODY(w0) WORD_BODY(w1) WORD_BODY(w2) WORD_BODY(w3) \
-            unsigned lq = (aq & 0xffffu) + (aq >> 16), lr = (ar & 0xffffu) + (ar >> 16); \
-            if ((w0 | w1 | w2 | w3) & 0x80008000u) { const uint2 t_ = lane_sums_ext(w0, w1, w2, w3); lq = t_.x; lr = t_.y; } \
-            const unsigned tot_q = __reduce_add_sync(FULL, lq), tot_r = __reduce_add_sync(FULL, lr); \
-            if (__any_sync(FULL, (rb & 0x10001000u) != 0u)) { const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, rec, pos_q, pos_r, nlead, tk_start, tk_end); \
-                big += (unsigned)(rr >> 32); nlead += (unsigned)rr; } \
-            pos_q += tot_q; pos_r += (int)tot_r; }
-        for (int base = 0; base < n; base += 512) {
-            { const uint4 v = va; va = LOAD_SLICE(base + 512); SLICE_BODY(v, base) }
-            if (base + 256 < n) { const uint4 v = vb; vb = LOAD_SLICE(base + 768); SLICE_BODY(v, base + 256) }
-        }
-        #undef SLICE_BODY
-        #undef WORD_BODY
-        #undef LOAD_SLICE
-        if (lane == 0) {
-            if (nlead > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL);       // the per-read lead ordinal is a 16-bit field of the lead and of the sort order
-            P.rec_end[rec] = pos_r; P.rec_nlead[rec] = nlead; P.rec_big[rec] = (int)big;
-            if (d.w & RM_HAS_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = rec; }
+    const uint32_t ww[4] = { w0, w1, w2, w3 };
+    unsigned cls[8], len[8];
+    c16_decode8(ww, cls, len);
+    unsigned big = 0, evm = 0;
+    #pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        if (len[j] > 10u && (cls[j] == C16_I || cls[j] == C16_D)) big += len[j];             // get_cigar_indels, minoplen 10
+        if (c16_is_event(cls[j]) && (int)len[j] >= P->minsv) evm |= 1u << j; }
+    unsigned cnt = 0, emm = 0;
+    if (__any_sync(FULL, evm != 0)) {
+        const unsigned q0 = base_q + seg_incl_scan(lq, lane, seg0) - lq; const int r0 = base_r + (int)(seg_incl_scan(lr, lane, seg0) - lr);
+        // which signatures stay inside the task's region (leadprov.py:464-466)
+        { int r2 = r0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; if (rs >= tk_start && rs < tk_end) { emm |= 1u << j; ++cnt; } }
+                r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); } }
+        const unsigned kseg = seg_incl_scan(cnt, lane, seg0) - cnt;           // events of my record in earlier lanes of this step
+        unsigned inc = cnt;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        const unsigned count = __shfl_sync(FULL, inc, 31);
+        if (count) {
+            unsigned long long e0 = 0; if (lane == 0) e0 = atomicAdd(P->n_ev, (unsigned long long)count);
+            e0 = __shfl_sync(FULL, e0, 0);
+            unsigned mine = inc - cnt, kk = base_k + kseg; unsigned q2 = q0; int r2 = r0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (emm & (1u << j)) {
+                    const unsigned long long e = e0 + mine;
+                    if (e < P->ev_cap) { uint4* dst = reinterpret_cast<uint4*>(P->ev + e); dst[0] = make_uint4(rec, len[j], q2, (uint32_t)r2); dst[1] = make_uint4((kk & 0xffffu) | (cls[j] << 16), 0u, 0u, 0u); }
+                    else atomicAdd(&P->ctr->lead_overflow, 1ULL);
+                    ++mine; ++kk;
+                }
+                q2 += len[j] * (cls[j] & 1u); r2 += (int)(len[j] * ((cls[j] >> 1) & 1u));
+            }
         }
     }
+    return ((unsigned long long)big << 32) | cnt;
+}
+
+// first ordinal p in [0, np] with pvs[p] >= target (pvs ascending; pvs[np] = total); the whole warp searches 32 ways per round
+__device__ inline uint32_t warp_lower_bound(const uint32_t* __restrict__ pvs, uint32_t np, unsigned long long target) {
+    const int lane = lane_id(); uint32_t lo = 0, hi = np;          // answer in [lo, hi]
+    while (hi > lo) {
+        if (hi - lo <= 32) { const uint32_t idx = lo + lane; const bool pr = idx < hi && (unsigned long long)pvs[idx] < target; return lo + __popc(__ballot_sync(FULL, pr)); }
+        const uint32_t step = (hi - lo + 31) / 32; const unsigned long long idx = (unsigned long long)lo + (unsigned long long)lane * step;
+        const bool pr = idx < hi && (unsigned long long)pvs[idx] < target;
+        const int k = __popc(__ballot_sync(FULL, pr));
+        if (k == 0) return lo;
+        const unsigned long long nhi = (unsigned long long)lo + (unsigned long long)k * step;
+        lo = lo + (uint32_t)(k - 1) * step + 1; if (nhi < hi) hi = (uint32_t)nhi;
+    }
+    return lo;
+}
+
+// The streaming kernel.  The CIGAR16 groups (16 bytes = 8 words) of the PASSING records form one virtual sequence; every warp owns a
+// range of whole records of about total / #warps groups and sweeps it 32 groups (512 bytes) per step, one group per lane, regardless of
+// where records begin and end: a step that spans several short records is handled as segments.  Per 32-bit word (two ops) the hot loop
+// does two masked sums (read / reference advance, both halves at once) and one OR (the E / extension flags); everything else is per step.
+__global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanParams P) {
+    const int lane = lane_id();
+    const uint32_t np = (uint32_t)P.ctr->n_passrec; const unsigned long long V = P.ctr->n_vgroups;
+    if (np == 0) return;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (unsigned long long)gridDim.x * 8;
+    const uint32_t p_lo = gw == 0 ? 0u : warp_lower_bound(P.pvs, np, V * gw / nwarps);
+    const uint32_t p_hi = gw + 1 == nwarps ? np : warp_lower_bound(P.pvs, np, V * (gw + 1) / nwarps);
+    if (p_lo >= p_hi) return;
+    const uint4* __restrict__ cig4 = reinterpret_cast<const uint4*>(P.cigar);
+    const unsigned long long Gend = P.pvs[p_hi];
+    // current record (warp-uniform) and the window of the 32 records after `pbase` (lane j: ordinal pbase + 1 + j)
+    uint32_t pcur = p_lo, pbase = p_lo;
+    uint32_t cur_cig8, cur_vs, cur_meta, cur_rec; int cur_pos; unsigned long long cur_vend;
+    { const uint4 a = __ldg(reinterpret_cast<const uint4*>(P.pdesc + pcur)); const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(P.pdesc + pcur) + 4);
+      cur_cig8 = a.x; cur_vs = a.y; cur_pos = (int)a.z; cur_meta = a.w; cur_rec = r; cur_vend = P.pvs[pcur + 1]; }
+    uint32_t w_cig8 = 0, w_vs = 0xffffffffu, w_meta = 0, w_rec = 0; int w_pos = 0;
+    #define LOAD_WINDOW() { const uint32_t q_ = pbase + 1 + (uint32_t)lane; if (q_ < p_hi) { const uint4 a_ = __ldg(reinterpret_cast<const uint4*>(P.pdesc + q_)); \
+        w_cig8 = a_.x; w_vs = a_.y; w_pos = (int)a_.z; w_meta = a_.w; w_rec = __ldg(reinterpret_cast<const uint32_t*>(P.pdesc + q_) + 4); } else { w_vs = 0xffffffffu; w_cig8 = 0; w_meta = 0; w_rec = 0; w_pos = 0; } }
+    LOAD_WINDOW()
+    unsigned long long G = cur_vs;
+    unsigned acc_q = 0, acc_big = 0, acc_n = 0; int acc_r = cur_pos;     // the record in progress
+    int tk_id = -1, tk_start = 0, tk_end = 0;
+    while (G < Gend) {
+        if (pcur - pbase >= 8) { pbase = pcur; LOAD_WINDOW() }
+        // record starts inside (G, G + 32): one bit per start; the window's last lane is a sentinel the step stops in front of
+        const bool has = w_vs != 0xffffffffu && pbase + 1 + (uint32_t)lane > pcur && (unsigned long long)w_vs < G + 32;
+        const unsigned cbit = has ? 1u << (unsigned)((unsigned long long)w_vs - G) : 0u;
+        unsigned bmask = __reduce_or_sync(FULL, cbit);
+        int lim = (Gend - G) < 32ull ? (int)(Gend - G) : 32;
+        { const unsigned lastbit = __shfl_sync(FULL, cbit, 31); if (lastbit) { const int cut = __ffs(lastbit) - 1; if (cut < lim) lim = cut; bmask &= lastbit - 1u; } }
+        const int nb = __popc(bmask);
+        const unsigned below = bmask & (0xffffffffu >> (31 - lane));         // starts at lanes <= mine
+        const int my_k = __popc(below);
+        const int seg0 = my_k ? 31 - __clz(below) : 0;
+        const int wl = (int)(pcur - pbase) + my_k - 1;                        // window lane of my record (my_k > 0)
+        const uint32_t s_cig8 = __shfl_sync(FULL, w_cig8, wl & 31), s_vs = __shfl_sync(FULL, w_vs, wl & 31);
+        const uint32_t m_cig8 = my_k ? s_cig8 : cur_cig8, m_vs = my_k ? s_vs : cur_vs;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (lane < lim) {
+            const uint4* src = cig4 + m_cig8 + (uint32_t)(G + (unsigned long long)lane - m_vs);
+            v = __ldg(src);
+            if (nb == 0 && G + 32ull + (unsigned long long)lane < cur_vend) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + 32));   // the next step of the same record
+        }
+        const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
+        uint32_t aq = 0, ar = 0;
+        #define WORD_BODY(w) { const uint32_t t_ = (w) >> 11; aq += (w) & ((t_ & 0x00010001u) * 0x7ffu); ar += (w) & (((t_ >> 1) & 0x00010001u) * 0x7ffu); }
+        WORD_BODY(w0) WORD_BODY(w1) WORD_BODY(w2) WORD_BODY(w3)
+        #undef WORD_BODY
+        const uint32_t rb = (w0 | w1 | w2 | w3) & 0xC000C000u;
+        unsigned lq = (aq & 0xffffu) + (aq >> 16), lr = (ar & 0xffffu) + (ar >> 16);
+        if (rb & 0x80008000u) { const uint2 t_ = lane_sums_ext(w0, w1, w2, w3); lq = t_.x; lr = t_.y; }
+        const bool any_rare = __any_sync(FULL, rb != 0u);
+        if (nb == 0) {
+            // ---- the whole step belongs to the record in progress (the common case)
+            if (any_rare) {
+                const int r_task = (int)(cur_meta & 0xffffu);
+                if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; }
+                const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, 0, cur_rec, acc_q, acc_r, acc_n, tk_start, tk_end);
+                acc_big += __reduce_add_sync(FULL, (unsigned)(rr >> 32)); acc_n += __reduce_add_sync(FULL, (unsigned)rr);
+            }
+            acc_q += __reduce_add_sync(FULL, lq); acc_r += (int)__reduce_add_sync(FULL, lr);
+            G += (unsigned)lim;
+            if (G == cur_vend) {       // the record ends with this step
+                if (lane == 0) {
+                    if (acc_n > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL);
+                    P.rec_end[cur_rec] = acc_r; P.rec_nlead[cur_rec] = acc_n; P.rec_big[cur_rec] = (int)acc_big;
+                    if (cur_meta & RM_HAS_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = cur_rec; }
+                }
+                ++pcur;
+                if (pcur < p_hi) { const int l2 = (int)(pcur - pbase) - 1;
+                    cur_cig8 = __shfl_sync(FULL, w_cig8, l2); cur_vs = __shfl_sync(FULL, w_vs, l2); cur_pos = __shfl_sync(FULL, w_pos, l2); cur_meta = __shfl_sync(FULL, w_meta, l2); cur_rec = __shfl_sync(FULL, w_rec, l2);
+                    cur_vend = P.pvs[pcur + 1];
+                    acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
+            }
+            continue;
+        }
+        // ---- several records in this step: segment 0 continues the record in progress, segment s is ordinal pcur + s
+        const uint32_t s_meta = __shfl_sync(FULL, w_meta, wl & 31), s_rec = __shfl_sync(FULL, w_rec, wl & 31); const int s_pos = __shfl_sync(FULL, w_pos, wl & 31);
+        const uint32_t m_meta = my_k ? s_meta : cur_meta, m_rec = my_k ? s_rec : cur_rec;
+        unsigned l_big = 0, l_cnt = 0;
+        if (any_rare) {
+            const snfb_task t = P.task[m_meta & 0xffffu];
+            const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, seg0, m_rec, my_k ? 0u : acc_q, my_k ? s_pos : acc_r, my_k ? 0u : acc_n, t.start, t.end);
+            l_big = (unsigned)(rr >> 32); l_cnt = (unsigned)rr;
+        }
+        // per-segment totals; lane s keeps the outputs of segment s when that record ends in this step
+        G += (unsigned)lim;
+        uint32_t o_rec = 0, o_meta = 0, o_n = 0; int o_end = 0, o_big = 0; bool o_valid = false;
+        unsigned last_q = 0, last_big = 0, last_n = 0; int last_r = 0;
+        for (int sg = 0; sg <= nb; ++sg) {
+            const bool mine = my_k == sg && lane < lim;
+            const unsigned tq = __reduce_add_sync(FULL, mine ? lq : 0u), tr = __reduce_add_sync(FULL, mine ? lr : 0u);
+            unsigned tb = 0, tn = 0;
+            if (any_rare) { tb = __reduce_add_sync(FULL, mine ? l_big : 0u); tn = __reduce_add_sync(FULL, mine ? l_cnt : 0u); }
+            const int wls = (int)(pcur - pbase) + sg - 1;
+            const uint32_t g_rec = sg ? __shfl_sync(FULL, w_rec, wls & 31) : cur_rec, g_meta = sg ? __shfl_sync(FULL, w_meta, wls & 31) : cur_meta;
+            const int g_pos = sg ? __shfl_sync(FULL, w_pos, wls & 31) : cur_pos;
+            const unsigned bq = sg ? 0u : acc_q, bb = sg ? 0u : acc_big, bn = sg ? 0u : acc_n; const int br = sg ? g_pos : acc_r;
+            (void)g_pos;
+            if (sg < nb) { if (lane == sg) { o_valid = true; o_rec = g_rec; o_meta = g_meta; o_end = br + (int)tr; o_big = (int)(bb + tb); o_n = bn + tn; } }
+            else { last_q = bq + tq; last_r = br + (int)tr; last_big = bb + tb; last_n = bn + tn; }
+        }
+        // the last segment becomes the record in progress, or ends exactly with the step
+        pcur += (uint32_t)nb;
+        { const int l2 = (int)(pcur - pbase) - 1;
+          cur_cig8 = __shfl_sync(FULL, w_cig8, l2); cur_vs = __shfl_sync(FULL, w_vs, l2); cur_pos = __shfl_sync(FULL, w_pos, l2); cur_meta = __shfl_sync(FULL, w_meta, l2); cur_rec = __shfl_sync(FULL, w_rec, l2);
+          cur_vend = P.pvs[pcur + 1]; }
+        acc_q = last_q; acc_r = last_r; acc_big = last_big; acc_n = last_n;
+        if (G == cur_vend) {
+            if (lane == nb) { o_valid = true; o_rec = cur_rec; o_meta = cur_meta; o_end = acc_r; o_big = (int)acc_big; o_n = acc_n; }
+            ++pcur;
+            if (pcur < p_hi) {
+                if (pcur - pbase >= 32) { pbase = pcur - 1; LOAD_WINDOW() }
+                const int l2 = (int)(pcur - pbase) - 1;
+                cur_cig8 = __shfl_sync(FULL, w_cig8, l2); cur_vs = __shfl_sync(FULL, w_vs, l2); cur_pos = __shfl_sync(FULL, w_pos, l2); cur_meta = __shfl_sync(FULL, w_meta, l2); cur_rec = __shfl_sync(FULL, w_rec, l2);
+                cur_vend = P.pvs[pcur + 1];
+                acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
+        }
+        if (o_valid) {
+            if (o_n > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL);
+            P.rec_end[o_rec] = o_end; P.rec_nlead[o_rec] = o_n; P.rec_big[o_rec] = o_big;
+            if (o_meta & RM_HAS_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = o_rec; }
+        }
+    }
+    #undef LOAD_WINDOW
 }
 
 // per read nm (leadprov.py:517-526) and the per-task bookkeeping of iter_region (read count, covered bases, longest span)
