@@ -179,7 +179,34 @@ def run_task(block, t, config, finalize=True):
     if finalize:
         final = tk.finalize_candidates(cands, not qc, config)
         out["final"] = [_final_dict(c) for c in final]
+        out["vcf"], out["vcf_ref"] = reference_vcf_lines(final, config, None), reference_vcf_lines(final, config, FakeFasta())
     return out
+
+
+class FakeFasta:
+    """deterministic reference bases (with a few IUPAC codes) for the VCF writer's REF / anchor fetches; same class feeds both writers"""
+    ALPHABET = "ACGTACGTACGTRYNACGTSWK"
+
+    def fetch(self, contig, start=None, end=None):
+        if start is None or end is None or start < 0 or end < start:
+            raise ValueError("bad interval")
+        h = sum(ord(ch) for ch in contig)
+        return "".join(self.ALPHABET[(h + 7 * p + (p >> 5)) % len(self.ALPHABET)] for p in range(start, end))
+
+
+def reference_vcf_lines(final, config, fasta):
+    """records the reference's own VCF.write_call emits for the finalized calls (vcf.py:216-350), on deep copies"""
+    import copy
+    import io
+    from sniffles import vcf as refvcf
+    if not getattr(config, "sample_ids_vcf", None):
+        config.sample_ids_vcf = [(0, "SAMPLE")]
+    buf = io.StringIO()
+    w = refvcf.VCF(config, buf)
+    w.reference_handle = fasta
+    for c in final:
+        w.write_call(copy.deepcopy(c))
+    return buf.getvalue().splitlines()
 
 
 def lead_tuple(ld):

@@ -289,6 +289,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 
 // ---- thread groups ----
 struct WarpG {
+    static constexpr bool is_warp = true;
+    __device__ __forceinline__ int maxi(int v) const { return __reduce_max_sync(FULL, v); }
     __device__ __forceinline__ int tid() const { return (int)(threadIdx.x & 31u); }
     __device__ __forceinline__ int nthr() const { return 32; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
@@ -305,7 +307,17 @@ struct WarpG {
     __device__ __forceinline__ unsigned long long bcast(unsigned long long v) const { return __shfl_sync(FULL, v, 0); }
 };
 struct BlockG {
+    static constexpr bool is_warp = false;
     unsigned long long* red;      // shared scratch: 72 entries
+    __device__ inline int maxi(int v) const {
+        v = __reduce_max_sync(FULL, v);
+        const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+        if ((threadIdx.x & 31) == 0) red[w] = (unsigned long long)(long long)v;
+        __syncthreads();
+        int t = (int)(long long)red[0]; for (int i = 1; i < nw; ++i) { const int x = (int)(long long)red[i]; if (x > t) t = x; }
+        __syncthreads();
+        return t;
+    }
     __device__ __forceinline__ int tid() const { return (int)threadIdx.x; }
     __device__ __forceinline__ int nthr() const { return (int)blockDim.x; }
     __device__ __forceinline__ void sync() const { __syncthreads(); }
@@ -354,6 +366,14 @@ template <class G> __device__ __forceinline__ double bcast_f8(const G& g, double
 __device__ __forceinline__ bool lt2(uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl) { return ah < bh || (ah == bh && al < bl); }
 template <class G> __device__ inline void sort2(const G& g, uint64_t* hi, uint64_t* lo, int n) {    // ascending by (hi, lo)
     if (n < 2) return;
+    if (G::is_warp && n <= 32) {                      // one element per lane: its rank is the number of smaller elements (register shuffles, no network)
+        const int i = g.tid(); const uint64_t xh = i < n ? hi[i] : 0, xl = i < n ? lo[i] : 0; int rank = 0;
+        for (int j = 0; j < n; ++j) { const uint64_t yh = __shfl_sync(FULL, xh, j), yl = __shfl_sync(FULL, xl, j); rank += lt2(yh, yl, xh, xl) ? 1 : 0; }
+        g.sync();
+        if (i < n) { hi[rank] = xh; lo[rank] = xl; }
+        g.sync();
+        return;
+    }
     int lp = 1; while ((1 << lp) < n) ++lp;
     const int half = 1 << (lp - 1);
     for (int lk = 1; lk <= lp; ++lk) {
@@ -370,6 +390,14 @@ template <class G> __device__ inline void sort2(const G& g, uint64_t* hi, uint64
 }
 template <class G> __device__ inline void sort1(const G& g, uint64_t* a, int n) {                     // ascending, unsigned (ties are equal values: order-free)
     if (n < 2) return;
+    if (G::is_warp && n <= 32) {
+        const int i = g.tid(); const uint64_t x = i < n ? a[i] : 0; int rank = 0;
+        for (int j = 0; j < n; ++j) { const uint64_t y = __shfl_sync(FULL, x, j); rank += (y < x || (y == x && j < i)) ? 1 : 0; }
+        g.sync();
+        if (i < n) a[rank] = x;
+        g.sync();
+        return;
+    }
     int lp = 1; while ((1 << lp) < n) ++lp;
     const int half = 1 << (lp - 1);
     for (int lk = 1; lk <= lp; ++lk) {
@@ -420,19 +448,23 @@ template <class G> __device__ inline double stdev_trim_sorted(const G& g, const 
     return stdev_sorted(g, a + lo, m);
 }
 
+// util.center = median_modes over a sorted (biased) array (util.py:49-58): the upper median of the distinct values whose multiplicity is
+// within 2 of the largest one.  Cooperative: run heads, run lengths, the qualifying runs.  s0 / s1: scratch of n entries each.
+template <class G> __device__ inline long long center_sorted(const G& g, const uint64_t* a, int n, uint32_t* s0, uint32_t* s1) {
+    const int nh = compact(g, n, s0, [&](int i) { return i == 0 || a[i] != a[i - 1]; });
+    int mx = 0; for (int h = g.tid(); h < nh; h += g.nthr()) { const int c = (int)((h + 1 < nh ? s0[h + 1] : (uint32_t)n) - s0[h]); if (c > mx) mx = c; }
+    const int maxc = g.maxi(mx);
+    const int m = compact(g, nh, s1, [&](int h) { return maxc - (int)((h + 1 < nh ? s0[h + 1] : (uint32_t)n) - s0[h]) < 3; });
+    const long long r = unbias64(a[s0[s1[m / 2]]]);
+    g.sync();
+    return r;
+}
+
 constexpr int NU32 = 15;
 struct WS { const snfb_lead* L; uint64_t* khi; uint64_t* klo; uint32_t* u[NU32]; };
 
 }  // namespace coop
 
-// util.center = median_modes over a sorted (biased) array (util.py:49-58)
-__device__ inline long long center_sorted(const uint64_t* a, long n) {
-    long maxc = 0; for (long i = 0; i < n;) { long j = i; while (j < n && a[j] == a[i]) ++j; if (j - i > maxc) maxc = j - i; i = j; }
-    long m = 0; for (long i = 0; i < n;) { long j = i; while (j < n && a[j] == a[i]) ++j; if (maxc - (j - i) < 3) ++m; i = j; }
-    const long want = m / 2; long k = 0;
-    for (long i = 0; i < n;) { long j = i; while (j < n && a[j] == a[i]) ++j; if (maxc - (j - i) < 3) { if (k == want) return unbias64(a[i]); ++k; } i = j; }
-    return unbias64(a[0]);
-}
 __device__ inline int cmp_decstr(long long a, long long b) {     // strcmp(str(a), str(b)) for the PS tie break
     char x[24], y[24]; int nx = 0, ny = 0;
     { unsigned long long v = a < 0 ? (unsigned long long)(-a) : (unsigned long long)a; char t[24]; int k = 0; do { t[k++] = (char)('0' + v % 10); v /= 10; } while (v); if (a < 0) x[nx++] = '-'; while (k) x[nx++] = t[--k]; }
@@ -568,8 +600,7 @@ __device__ void process_cluster(const G& g, const B& b, const uint32_t c, const 
         for (int i = tid; i < ns; i += nthr) w[i] = bias64(ml_svlen[SUB_ML(i)]);
         g.sync();
         sort1(g, w, ns);
-        long long svlen = 0; if (tid == 0) svlen = center_sorted(w, ns);
-        svlen = bcast_ll(g, svlen);
+        const long long svlen = center_sorted(g, w, ns, sA, sB);
         const bool single = svtype == SNFB_SINGLE_LEFT || svtype == SNFB_SINGLE_RIGHT;
         if (!single && svtype != SNFB_BND && (svlen < 0 ? -svlen : svlen) < cfg.minsvlen_screen) { g.sync(); continue; }
         double sd_len = __longlong_as_double(0x7ff8000000000000LL);
@@ -578,8 +609,7 @@ __device__ void process_cluster(const G& g, const B& b, const uint32_t c, const 
         for (int i = tid; i < ns; i += nthr) w[i] = bias64(SUB_LEAD(i).ref_start);
         g.sync();
         sort1(g, w, ns);
-        long long ref_start = 0; if (tid == 0) ref_start = center_sorted(w, ns);
-        ref_start = bcast_ll(g, ref_start);
+        const long long ref_start = center_sorted(g, w, ns, sA, sB);
         const double sd_pos = stdev_trim_sorted(g, w, ns);
         g.sync();
         const bool precise = svtype != SNFB_BND ? (__dadd_rn(sd_pos, sd_len) < (double)cfg.precise) : (sd_pos < (double)cfg.precise);
@@ -639,8 +669,8 @@ __device__ void process_cluster(const G& g, const B& b, const uint32_t c, const 
             nf = g.sum(nf); nr = g.sum(nr);
             g.sync();
             sort1(g, w, m);
-            long long mp = 0; if (tid == 0) mp = center_sorted(w, m);
-            bnd_contig = best; bnd_pos = (int)bcast_ll(g, mp); bnd_first = nf > m - nf; bnd_rev = nr > m - nr;
+            const long long mp = center_sorted(g, w, m, sA, sB);
+            bnd_contig = best; bnd_pos = (int)mp; bnd_first = nf > m - nf; bnd_rev = nr > m - nr;
             sort1(g, w2, m);
             nq = compact(g, m, sA, [&](int i) { return i == 0 || w2[i] != w2[i - 1]; });
             for (int i = tid; i < nq; i += nthr) w[i] = w2[sA[i]];

@@ -410,7 +410,11 @@ __device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restric
     const int lane = lane_id();
     const uint32_t ww[4] = { w0, w1, w2, w3 };
     unsigned cls[8], len[8];
-    c16_decode8(ww, cls, len);
+    if (__any_sync(FULL, ((w0 | w1 | w2 | w3) & 0x80008000u) != 0u)) c16_decode8(ww, cls, len);
+    else {                                            // no extension word anywhere in the step: plain field extraction
+        #pragma unroll
+        for (int h = 0; h < 8; ++h) { const unsigned x = (ww[h >> 1] >> (16 * (h & 1))) & 0xffffu; cls[h] = c16_class(x); len[h] = x & C16_LEN_MASK; }
+    }
     unsigned big = 0, evm = 0;
     #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -466,8 +470,9 @@ __device__ inline uint32_t warp_lower_bound(const uint32_t* __restrict__ pvs, ui
 
 // The streaming kernel.  The CIGAR16 groups (16 bytes = 8 words) of the PASSING records form one virtual sequence; every warp owns a
 // range of whole records of about total / #warps groups and sweeps it 32 groups (512 bytes) per step, one group per lane, regardless of
-// where records begin and end: a step that spans several short records is handled as segments.  Per 32-bit word (two ops) the hot loop
-// does two masked sums (read / reference advance, both halves at once) and one OR (the E / extension flags); everything else is per step.
+// where records begin and end: a step that spans several short records is handled as segments (at most one record boundary per step is the
+// fast case: ONT reads are ~1.5 steps long).  Per 32-bit word (two ops) the hot loop does two masked sums (read / reference advance, both
+// halves at once) and one OR (the E / extension flags); everything else is per step.
 __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanParams P) {
     const int lane = lane_id();
     const uint32_t np = (uint32_t)P.ctr->n_passrec; const unsigned long long V = P.ctr->n_vgroups;
@@ -477,39 +482,46 @@ __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanPar
     const uint32_t p_hi = gw + 1 == nwarps ? np : warp_lower_bound(P.pvs, np, V * (gw + 1) / nwarps);
     if (p_lo >= p_hi) return;
     const uint4* __restrict__ cig4 = reinterpret_cast<const uint4*>(P.cigar);
-    const unsigned long long Gend = P.pvs[p_hi];
+    const uint32_t Gend = P.pvs[p_hi];
     // current record (warp-uniform) and the window of the 32 records after `pbase` (lane j: ordinal pbase + 1 + j)
     uint32_t pcur = p_lo, pbase = p_lo;
-    uint32_t cur_cig8, cur_vs, cur_meta, cur_rec; int cur_pos; unsigned long long cur_vend;
+    uint32_t cur_cig8, cur_vs, cur_meta, cur_rec, cur_vend; int cur_pos;
     { const uint4 a = __ldg(reinterpret_cast<const uint4*>(P.pdesc + pcur)); const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(P.pdesc + pcur) + 4);
       cur_cig8 = a.x; cur_vs = a.y; cur_pos = (int)a.z; cur_meta = a.w; cur_rec = r; cur_vend = P.pvs[pcur + 1]; }
     uint32_t w_cig8 = 0, w_vs = 0xffffffffu, w_meta = 0, w_rec = 0; int w_pos = 0;
     #define LOAD_WINDOW() { const uint32_t q_ = pbase + 1 + (uint32_t)lane; if (q_ < p_hi) { const uint4 a_ = __ldg(reinterpret_cast<const uint4*>(P.pdesc + q_)); \
         w_cig8 = a_.x; w_vs = a_.y; w_pos = (int)a_.z; w_meta = a_.w; w_rec = __ldg(reinterpret_cast<const uint32_t*>(P.pdesc + q_) + 4); } else { w_vs = 0xffffffffu; w_cig8 = 0; w_meta = 0; w_rec = 0; w_pos = 0; } }
+    // the record of ordinal `pcur` becomes the current one (its descriptor sits in the window; the end of the last record of the range is Gend)
+    #define ENTER_CUR() { const int l2_ = (int)(pcur - pbase) - 1; \
+        cur_cig8 = __shfl_sync(FULL, w_cig8, l2_); cur_vs = __shfl_sync(FULL, w_vs, l2_); cur_pos = __shfl_sync(FULL, w_pos, l2_); cur_meta = __shfl_sync(FULL, w_meta, l2_); cur_rec = __shfl_sync(FULL, w_rec, l2_); \
+        const uint32_t nv_ = __shfl_sync(FULL, w_vs, (l2_ + 1) & 31); cur_vend = pcur + 1 >= p_hi ? Gend : (l2_ + 1 < 32 ? nv_ : P.pvs[pcur + 1]); }
+    #define FINISH_REC(rec_, meta_, end_, n_, big_) { if ((n_) > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL); \
+        P.rec_end[rec_] = (end_); P.rec_nlead[rec_] = (n_); P.rec_big[rec_] = (int)(big_); \
+        if ((meta_) & RM_HAS_SA) { const unsigned long long e_ = atomicAdd(P.n_sa, 1ULL); P.sa_list[e_] = (rec_); } }
     LOAD_WINDOW()
-    unsigned long long G = cur_vs;
+    uint32_t G = cur_vs;
     unsigned acc_q = 0, acc_big = 0, acc_n = 0; int acc_r = cur_pos;     // the record in progress
     int tk_id = -1, tk_start = 0, tk_end = 0;
     while (G < Gend) {
         if (pcur - pbase >= 8) { pbase = pcur; LOAD_WINDOW() }
         // record starts inside (G, G + 32): one bit per start; the window's last lane is a sentinel the step stops in front of
-        const bool has = w_vs != 0xffffffffu && pbase + 1 + (uint32_t)lane > pcur && (unsigned long long)w_vs < G + 32;
-        const unsigned cbit = has ? 1u << (unsigned)((unsigned long long)w_vs - G) : 0u;
+        const uint32_t dv = w_vs - G;
+        const bool has = dv < 32u && pbase + 1 + (uint32_t)lane > pcur;            // w_vs = 0xffffffff (no record) never lands in the step: Gend <= 2^32 - 64
+        const unsigned cbit = has ? 1u << dv : 0u;
         unsigned bmask = __reduce_or_sync(FULL, cbit);
-        int lim = (Gend - G) < 32ull ? (int)(Gend - G) : 32;
-        { const unsigned lastbit = __shfl_sync(FULL, cbit, 31); if (lastbit) { const int cut = __ffs(lastbit) - 1; if (cut < lim) lim = cut; bmask &= lastbit - 1u; } }
+        int lim = (Gend - G) < 32u ? (int)(Gend - G) : 32;
+        if (bmask >> 24) { const unsigned lastbit = __shfl_sync(FULL, cbit, 31); if (lastbit) { const int cut = __ffs(lastbit) - 1; if (cut < lim) lim = cut; bmask &= lastbit - 1u; } }   // only a step dense with starts can reach the sentinel
         const int nb = __popc(bmask);
-        const unsigned below = bmask & (0xffffffffu >> (31 - lane));         // starts at lanes <= mine
-        const int my_k = __popc(below);
-        const int seg0 = my_k ? 31 - __clz(below) : 0;
-        const int wl = (int)(pcur - pbase) + my_k - 1;                        // window lane of my record (my_k > 0)
-        const uint32_t s_cig8 = __shfl_sync(FULL, w_cig8, wl & 31), s_vs = __shfl_sync(FULL, w_vs, wl & 31);
-        const uint32_t m_cig8 = my_k ? s_cig8 : cur_cig8, m_vs = my_k ? s_vs : cur_vs;
+        const int my_k = __popc(bmask & (0xffffffffu >> (31 - lane)));       // starts at lanes <= mine
+        uint32_t m_cig8 = cur_cig8, m_vs = cur_vs;
+        if (nb) { const int wl = (int)(pcur - pbase) + my_k - 1;             // window lane of my record (my_k > 0)
+            const uint32_t s_cig8 = __shfl_sync(FULL, w_cig8, wl & 31), s_vs = __shfl_sync(FULL, w_vs, wl & 31);
+            if (my_k) { m_cig8 = s_cig8; m_vs = s_vs; } }
         uint4 v = make_uint4(0, 0, 0, 0);
         if (lane < lim) {
-            const uint4* src = cig4 + m_cig8 + (uint32_t)(G + (unsigned long long)lane - m_vs);
+            const uint4* src = cig4 + (m_cig8 + (G + (uint32_t)lane - m_vs));
             v = __ldg(src);
-            if (nb == 0 && G + 32ull + (unsigned long long)lane < cur_vend) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + 32));   // the next step of the same record
+            if (nb == 0 && G + 32u + (uint32_t)lane < cur_vend) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + 32));   // the next step of the same record
         }
         const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
         uint32_t aq = 0, ar = 0;
@@ -520,41 +532,52 @@ __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanPar
         unsigned lq = (aq & 0xffffu) + (aq >> 16), lr = (ar & 0xffffu) + (ar >> 16);
         if (rb & 0x80008000u) { const uint2 t_ = lane_sums_ext(w0, w1, w2, w3); lq = t_.x; lr = t_.y; }
         const bool any_rare = __any_sync(FULL, rb != 0u);
-        if (nb == 0) {
-            // ---- the whole step belongs to the record in progress (the common case)
+        G += (uint32_t)lim;
+        if (nb <= 1) {
+            // ---- at most one record starts inside the step: segment 0 = the record in progress, segment 1 = the next one
+            const bool in0 = my_k == 0;
+            unsigned tq = __reduce_add_sync(FULL, lq), tr = __reduce_add_sync(FULL, lr), tq0 = tq, tr0 = tr;
+            if (nb) { tq0 = __reduce_add_sync(FULL, in0 ? lq : 0u); tr0 = __reduce_add_sync(FULL, in0 ? lr : 0u); }
+            unsigned tb0 = 0, tn0 = 0, tb1 = 0, tn1 = 0;
             if (any_rare) {
-                const int r_task = (int)(cur_meta & 0xffffu);
-                if (r_task != tk_id) { const snfb_task t = P.task[r_task]; tk_id = r_task; tk_start = t.start; tk_end = t.end; }
-                const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, 0, cur_rec, acc_q, acc_r, acc_n, tk_start, tk_end);
-                acc_big += __reduce_add_sync(FULL, (unsigned)(rr >> 32)); acc_n += __reduce_add_sync(FULL, (unsigned)rr);
+                int t_task = (int)(cur_meta & 0xffffu); uint32_t t_rec = cur_rec; unsigned bq = acc_q, bn = acc_n; int br = acc_r, seg0 = 0;
+                if (nb) { const int wl = (int)(pcur - pbase);                 // the next record: window lane pcur + 1 - pbase - 1
+                    const uint32_t n_meta = __shfl_sync(FULL, w_meta, wl), n_rec = __shfl_sync(FULL, w_rec, wl); const int n_pos = __shfl_sync(FULL, w_pos, wl);
+                    if (!in0) { t_task = (int)(n_meta & 0xffffu); t_rec = n_rec; bq = 0; bn = 0; br = n_pos; seg0 = __ffs(bmask) - 1; } }
+                if (t_task != tk_id) { const snfb_task t = P.task[t_task]; tk_id = t_task; tk_start = t.start; tk_end = t.end; }     // per lane when the two records sit on different tasks
+                const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, seg0, t_rec, bq, br, bn, tk_start, tk_end);
+                if (nb) tk_id = -1;                                                // lanes may hold different tasks now: reload next time
+                const unsigned lb = (unsigned)(rr >> 32), ln = (unsigned)rr;
+                const unsigned tb = __reduce_add_sync(FULL, lb), tn = __reduce_add_sync(FULL, ln);
+                tb0 = tb; tn0 = tn;
+                if (nb) { tb0 = __reduce_add_sync(FULL, in0 ? lb : 0u); tn0 = __reduce_add_sync(FULL, in0 ? ln : 0u); tb1 = tb - tb0; tn1 = tn - tn0; }
             }
-            acc_q += __reduce_add_sync(FULL, lq); acc_r += (int)__reduce_add_sync(FULL, lr);
-            G += (unsigned)lim;
-            if (G == cur_vend) {       // the record ends with this step
-                if (lane == 0) {
-                    if (acc_n > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL);
-                    P.rec_end[cur_rec] = acc_r; P.rec_nlead[cur_rec] = acc_n; P.rec_big[cur_rec] = (int)acc_big;
-                    if (cur_meta & RM_HAS_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = cur_rec; }
-                }
+            acc_q += tq0; acc_r += (int)tr0; acc_big += tb0; acc_n += tn0;
+            if (nb) {                                 // the record in progress ended inside the step; the next one is in progress now
+                if (lane == 0) FINISH_REC(cur_rec, cur_meta, acc_r, acc_n, acc_big)
+                ++pcur; ENTER_CUR()
+                acc_q = tq - tq0; acc_r = cur_pos + (int)(tr - tr0); acc_big = tb1; acc_n = tn1;
+            }
+            if (G == cur_vend) {                      // the record in progress ends with the step
+                if (lane == 0) FINISH_REC(cur_rec, cur_meta, acc_r, acc_n, acc_big)
                 ++pcur;
-                if (pcur < p_hi) { const int l2 = (int)(pcur - pbase) - 1;
-                    cur_cig8 = __shfl_sync(FULL, w_cig8, l2); cur_vs = __shfl_sync(FULL, w_vs, l2); cur_pos = __shfl_sync(FULL, w_pos, l2); cur_meta = __shfl_sync(FULL, w_meta, l2); cur_rec = __shfl_sync(FULL, w_rec, l2);
-                    cur_vend = P.pvs[pcur + 1];
-                    acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
+                if (pcur < p_hi) { ENTER_CUR() acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
             }
             continue;
         }
-        // ---- several records in this step: segment 0 continues the record in progress, segment s is ordinal pcur + s
+        // ---- several records start in this step (short records): segment s is ordinal pcur + s
+        const unsigned below = bmask & (0xffffffffu >> (31 - lane));
+        const int seg0 = my_k ? 31 - __clz(below) : 0;
+        const int wl = (int)(pcur - pbase) + my_k - 1;
         const uint32_t s_meta = __shfl_sync(FULL, w_meta, wl & 31), s_rec = __shfl_sync(FULL, w_rec, wl & 31); const int s_pos = __shfl_sync(FULL, w_pos, wl & 31);
         const uint32_t m_meta = my_k ? s_meta : cur_meta, m_rec = my_k ? s_rec : cur_rec;
         unsigned l_big = 0, l_cnt = 0;
         if (any_rare) {
-            const snfb_task t = P.task[m_meta & 0xffffu];
+            const snfb_task t = P.task[m_meta & 0xffffu]; tk_id = -1;
             const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, seg0, m_rec, my_k ? 0u : acc_q, my_k ? s_pos : acc_r, my_k ? 0u : acc_n, t.start, t.end);
             l_big = (unsigned)(rr >> 32); l_cnt = (unsigned)rr;
         }
         // per-segment totals; lane s keeps the outputs of segment s when that record ends in this step
-        G += (unsigned)lim;
         uint32_t o_rec = 0, o_meta = 0, o_n = 0; int o_end = 0, o_big = 0; bool o_valid = false;
         unsigned last_q = 0, last_big = 0, last_n = 0; int last_r = 0;
         for (int sg = 0; sg <= nb; ++sg) {
@@ -566,32 +589,24 @@ __global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanPar
             const uint32_t g_rec = sg ? __shfl_sync(FULL, w_rec, wls & 31) : cur_rec, g_meta = sg ? __shfl_sync(FULL, w_meta, wls & 31) : cur_meta;
             const int g_pos = sg ? __shfl_sync(FULL, w_pos, wls & 31) : cur_pos;
             const unsigned bq = sg ? 0u : acc_q, bb = sg ? 0u : acc_big, bn = sg ? 0u : acc_n; const int br = sg ? g_pos : acc_r;
-            (void)g_pos;
             if (sg < nb) { if (lane == sg) { o_valid = true; o_rec = g_rec; o_meta = g_meta; o_end = br + (int)tr; o_big = (int)(bb + tb); o_n = bn + tn; } }
             else { last_q = bq + tq; last_r = br + (int)tr; last_big = bb + tb; last_n = bn + tn; }
         }
         // the last segment becomes the record in progress, or ends exactly with the step
         pcur += (uint32_t)nb;
-        { const int l2 = (int)(pcur - pbase) - 1;
-          cur_cig8 = __shfl_sync(FULL, w_cig8, l2); cur_vs = __shfl_sync(FULL, w_vs, l2); cur_pos = __shfl_sync(FULL, w_pos, l2); cur_meta = __shfl_sync(FULL, w_meta, l2); cur_rec = __shfl_sync(FULL, w_rec, l2);
-          cur_vend = P.pvs[pcur + 1]; }
+        ENTER_CUR()
         acc_q = last_q; acc_r = last_r; acc_big = last_big; acc_n = last_n;
         if (G == cur_vend) {
             if (lane == nb) { o_valid = true; o_rec = cur_rec; o_meta = cur_meta; o_end = acc_r; o_big = (int)acc_big; o_n = acc_n; }
             ++pcur;
             if (pcur < p_hi) {
                 if (pcur - pbase >= 32) { pbase = pcur - 1; LOAD_WINDOW() }
-                const int l2 = (int)(pcur - pbase) - 1;
-                cur_cig8 = __shfl_sync(FULL, w_cig8, l2); cur_vs = __shfl_sync(FULL, w_vs, l2); cur_pos = __shfl_sync(FULL, w_pos, l2); cur_meta = __shfl_sync(FULL, w_meta, l2); cur_rec = __shfl_sync(FULL, w_rec, l2);
-                cur_vend = P.pvs[pcur + 1];
-                acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
+                ENTER_CUR() acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
         }
-        if (o_valid) {
-            if (o_n > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL);
-            P.rec_end[o_rec] = o_end; P.rec_nlead[o_rec] = o_n; P.rec_big[o_rec] = o_big;
-            if (o_meta & RM_HAS_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = o_rec; }
-        }
+        if (o_valid) FINISH_REC(o_rec, o_meta, o_end, o_n, o_big)
     }
+    #undef FINISH_REC
+    #undef ENTER_CUR
     #undef LOAD_WINDOW
 }
 

@@ -112,9 +112,11 @@ def calls_from_result(res, task_index, lo, hi, contig_names, task_contig, task_i
                 info["SUPPORT_LONG"] = int(c["support_long"])
             elif svtype == "DEL":
                 info["SUPPORT_SA"] = int(c["support_sa"])
-        info["STDEV_POS"] = float(c["stdev_pos"])
+        # util.stdev returns the int 0 for fewer than two values (util.py:25-27): a one-lead cluster prints STDEV_POS=0, not 0.000
+        one = int(c["fwd"]) + int(c["rev"]) < 2
+        info["STDEV_POS"] = 0 if one else float(c["stdev_pos"])
         if not math.isnan(float(c["stdev_len"])):
-            info["STDEV_LEN"] = float(c["stdev_len"])
+            info["STDEV_LEN"] = 0 if one else float(c["stdev_len"])
         sa_total = int(c["sa_total"])
         qs, rl, nm = [], [], []
         if want_leads:
