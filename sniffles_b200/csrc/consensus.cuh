@@ -206,14 +206,15 @@ __device__ __forceinline__ uint8_t* cand_table(const C& c, uint32_t ci, uint32_t
 }
 
 __global__ void __launch_bounds__(128) k_prep(C c) {
-    __shared__ uint32_t s_cand;
+
     static const char CODE[17] = "=ACMGRSVTWYHKDBN";
-    for (;;) {
+    // static interleaved assignment (heavy candidates first in the list, so they spread over the blocks): a shared atomic queue position
+    // serialises in L2 once items are short (measured: ~2 ns per pop, the whole of k_align's time at full size)
+    const uint32_t nbig = c.work_ctr[0], nsmall = c.work_ctr[1];
+    for (uint32_t q = blockIdx.x; q < nbig + nsmall; q += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x == 0) { const uint32_t q = atomicAdd(&c.work_ctr[2], 1u); const uint32_t nb = c.work_ctr[0], ns = c.work_ctr[1];
-            s_cand = q < nb ? c.work_big[q] : (q < nb + ns ? c.work_small[q - nb] : 0xffffffffu); }
-        __syncthreads();
-        const uint32_t ci = s_cand; if (ci == 0xffffffffu) break;
+        const uint32_t ci = q < nbig ? c.work_big[q] : c.work_small[q - nbig];
+
         const uint32_t L = c.alt_len[ci];
         if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) { if (threadIdx.x == 0) atomicAdd(&c.ctr->scratch_overflow, 1ULL); continue; }
         const snfb_cand cd = c.cand[ci];
@@ -238,11 +239,9 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp]; int* run_st = h_a[warp];   /* per-run identity sum */ int* run_len = h_b[warp];
     const int klen = 6;
-    for (;;) {
-        uint32_t q = 0; if (lane == 0) q = atomicAdd(&c.work_ctr[6], 1u);
-        q = __shfl_sync(FULL, q, 0);
-        const uint32_t nb = (uint32_t)min((unsigned long long)c.work_ctr[4], c.item_cap), ns = (uint32_t)min((unsigned long long)c.work_ctr[5], c.item_cap);
-        if (q >= nb + ns) break;
+    const uint32_t nb = (uint32_t)min((unsigned long long)c.work_ctr[4], c.item_cap), ns = (uint32_t)min((unsigned long long)c.work_ctr[5], c.item_cap);
+    const uint32_t nwarps = gridDim.x * ALIGN_WARPS;
+    for (uint32_t q = blockIdx.x * ALIGN_WARPS + warp; q < nb + ns; q += nwarps) {       // interleaved: the heavy items (first in the list) spread over all warps
         const C::Item it = q < nb ? c.items_big[q] : c.items_small[q - nb];
         const uint32_t ci = it.cand; const uint32_t L = c.alt_len[ci];
         if ((unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
@@ -360,11 +359,12 @@ constexpr int VOTE_THREADS = 64;      // most candidates are a few hundred colum
 __global__ void __launch_bounds__(VOTE_THREADS) k_vote(C c) {
     __shared__ uint2 s_tile; __shared__ int s_nacc, s_nlist; __shared__ uint16_t s_rows[VOTE_LIST];
     static const char CODE[17] = "=ACMGRSVTWYHKDBN";
-    for (;;) {
+    const uint32_t ntiles = (uint32_t)min((unsigned long long)c.work_ctr[8], c.tile_cap);
+    for (uint32_t q = blockIdx.x; q < ntiles; q += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x == 0) { const uint32_t q = atomicAdd(&c.work_ctr[9], 1u); s_tile = q < c.work_ctr[8] && q < c.tile_cap ? c.tiles[q] : make_uint2(0xffffffffu, 0); }
+        if (threadIdx.x == 0) s_tile = c.tiles[q];
         __syncthreads();
-        const uint32_t ci = s_tile.x; if (ci == 0xffffffffu) break;
+        const uint32_t ci = s_tile.x;
         const uint32_t L = c.alt_len[ci], no = c.plan_nother[ci];
         if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
         const Layout y = cand_layout(c, ci, L, no);
