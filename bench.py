@@ -353,6 +353,7 @@ def run_b200(args):
                 pass
     ctx = binding.Context(local)
     ctx.set_config(ccfg)
+    os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     if world > 1:           # the library's own NCCL communicator: the id travels through the launcher's process group
         box = [binding.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(box, src=0)

@@ -448,6 +448,7 @@ static void carve_c(snfb_ctx* ctx, Carver& c) {
     cc.alt_off = c.take<uint32_t>(k.cand + 1); cc.scr_off = c.take<uint32_t>(k.cand + 1); cc.work_big = c.take<uint32_t>(k.cand + 1); cc.work_small = c.take<uint32_t>(k.cand + 1); cc.work_ctr = c.take<uint32_t>(64);
     cc.items_big = c.take<consensus::C::Item>(k.item + 1); cc.items_small = c.take<consensus::C::Item>(k.item + 1); cc.tiles = c.take<uint2>(k.tile + 1);
     cc.alt = c.take<uint8_t>(k.alt + 64); cc.scr = c.take<uint8_t>(k.scr16 * 16 + 64);
+    cc.dbg = getenv("SNFB_DEBUG") ? c.take<unsigned long long>(148 * 8 * consensus::ALIGN_WARPS * 8 + 8) : nullptr;
     ctx->seq_req = c.take<consensus::SeqReq>(k.req + 1); ctx->seq_arena = c.take<uint8_t>(k.req16 * 16 + 64);
 }
 static int ensure_arenas(snfb_ctx* ctx) {
@@ -838,6 +839,12 @@ int snfb_device_alt(snfb_ctx* ctx, void** dptr, uint64_t* n_bytes) {
 uint64_t snfb_launch_count(snfb_ctx* ctx) { return ctx ? ctx->launches : 0; }
 double snfb_selftest_sqrt_frac(uint64_t p_hi, uint64_t p_lo, uint64_t q, int slow) { const u128 P = ((u128)p_hi << 64) | p_lo; return slow ? sqrt_frac_rn_slow(P, q) : sqrt_frac_rn(P, q); }
 uint64_t snfb_rerun_count(snfb_ctx* ctx) { return ctx ? ctx->reruns : 0; }
+/* developer aid (SNFB_DEBUG set when the ctx ran): per-warp timing of the consensus alignment kernel, 8 words per warp */
+int snfb_debug_dump(snfb_ctx* ctx, uint64_t* out, uint64_t n_words) {
+    if (!ctx || !ctx->Cc.dbg || !out) return 1;
+    const uint64_t have = 148ull * 8 * consensus::ALIGN_WARPS * 8; if (n_words > have) n_words = have;
+    return cudaMemcpy(out, ctx->Cc.dbg, 8 * n_words, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : 1;
+}
 int snfb_pin_host(void* p, size_t bytes) { return cudaHostRegister(p, bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : 1; }
 int snfb_unpin_host(void* p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : 1; }
 

@@ -24,6 +24,7 @@ struct C {
     // item pipeline: one (candidate, supporting read) pair per warp, one (candidate, column tile) per block
     struct Item { uint32_t cand; uint32_t k; uint32_t row; uint32_t rd_off; };
     Item* items_big; Item* items_small; uint2* tiles; unsigned long long item_cap, tile_cap;
+    unsigned long long* dbg;          // optional (SNFB_DEBUG): per warp of k_align [busy cycles, end time, items, longest item cycles, its L, its Lo]
     DevCounters* ctr; snfb_config cfg;
 };
 
@@ -206,15 +207,14 @@ __device__ __forceinline__ uint8_t* cand_table(const C& c, uint32_t ci, uint32_t
 }
 
 __global__ void __launch_bounds__(128) k_prep(C c) {
-
+    __shared__ uint32_t s_cand;
     static const char CODE[17] = "=ACMGRSVTWYHKDBN";
-    // static interleaved assignment (heavy candidates first in the list, so they spread over the blocks): a shared atomic queue position
-    // serialises in L2 once items are short (measured: ~2 ns per pop, the whole of k_align's time at full size)
-    const uint32_t nbig = c.work_ctr[0], nsmall = c.work_ctr[1];
-    for (uint32_t q = blockIdx.x; q < nbig + nsmall; q += gridDim.x) {
+    for (;;) {
         __syncthreads();
-        const uint32_t ci = q < nbig ? c.work_big[q] : c.work_small[q - nbig];
-
+        if (threadIdx.x == 0) { const uint32_t q = atomicAdd(&c.work_ctr[2], 1u); const uint32_t nb = c.work_ctr[0], ns = c.work_ctr[1];
+            s_cand = q < nb ? c.work_big[q] : (q < nb + ns ? c.work_small[q - nb] : 0xffffffffu); }
+        __syncthreads();
+        const uint32_t ci = s_cand; if (ci == 0xffffffffu) break;
         const uint32_t L = c.alt_len[ci];
         if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) { if (threadIdx.x == 0) atomicAdd(&c.ctr->scratch_overflow, 1ULL); continue; }
         const snfb_cand cd = c.cand[ci];
@@ -239,11 +239,16 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
     const int lane = lane_id(), warp = threadIdx.x >> 5;
     int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp]; int* run_st = h_a[warp];   /* per-run identity sum */ int* run_len = h_b[warp];
     const int klen = 6;
-    const uint32_t nb = (uint32_t)min((unsigned long long)c.work_ctr[4], c.item_cap), ns = (uint32_t)min((unsigned long long)c.work_ctr[5], c.item_cap);
-    const uint32_t nwarps = gridDim.x * ALIGN_WARPS;
-    for (uint32_t q = blockIdx.x * ALIGN_WARPS + warp; q < nb + ns; q += nwarps) {       // interleaved: the heavy items (first in the list) spread over all warps
+    unsigned long long d_busy = 0, d_items = 0, d_max = 0, d_L = 0, d_Lo = 0, d_cL = 0, d_cLo = 0; long long d_t0 = 0; const long long d_start = clock64();
+    for (;;) {
+        if (c.dbg && d_t0) { const unsigned long long dt = (unsigned long long)(clock64() - d_t0); d_busy += dt; if (dt > d_max) { d_max = dt; d_L = d_cL; d_Lo = d_cLo; } d_t0 = 0; }
+        uint32_t q = 0; if (lane == 0) q = atomicAdd(&c.work_ctr[6], 1u);
+        q = __shfl_sync(FULL, q, 0);
+        const uint32_t nb = (uint32_t)min((unsigned long long)c.work_ctr[4], c.item_cap), ns = (uint32_t)min((unsigned long long)c.work_ctr[5], c.item_cap);
+        if (q >= nb + ns) break;
         const C::Item it = q < nb ? c.items_big[q] : c.items_small[q - nb];
         const uint32_t ci = it.cand; const uint32_t L = c.alt_len[ci];
+        if (c.dbg) { d_t0 = clock64(); ++d_items; d_cL = L; }
         if ((unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
         const snfb_cand* cd = &c.cand[ci];
         uint32_t* t_key; int* t_pos; cand_table(c, ci, &t_key, &t_pos);
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
         uint8_t* best = y.best; uint8_t* acc = y.acc;
         const snfb_lead* l = &c.cand_leads[cd->lead_off + it.k];
         const long Lo = l->seq_len; uint8_t* rd = y.oth + it.rd_off; uint8_t* row = y.rows + (size_t)it.row * y.Ls;
+        d_cLo = (unsigned long long)Lo;
         const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
         unpack_lead_warp(c, cd->lead_off + it.k, rd);
         __syncwarp();
@@ -344,6 +350,8 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
         if (lane == 0) acc[it.row] = __ddiv_rn((double)span, (double)L) > 0.2;
         __syncwarp();
     }
+    if (c.dbg && lane == 0) { unsigned long long* o = c.dbg + (size_t)(blockIdx.x * ALIGN_WARPS + warp) * 8;
+        o[0] = d_busy; o[1] = (unsigned long long)(clock64() - d_start); o[2] = d_items; o[3] = d_max; o[4] = d_L; o[5] = d_Lo; o[6] = 0; o[7] = 0; }
 }
 
 // column vote (consensus.py:365-380), one block per (candidate, 4096-column tile); every thread takes four adjacent columns
@@ -359,12 +367,11 @@ constexpr int VOTE_THREADS = 64;      // most candidates are a few hundred colum
 __global__ void __launch_bounds__(VOTE_THREADS) k_vote(C c) {
     __shared__ uint2 s_tile; __shared__ int s_nacc, s_nlist; __shared__ uint16_t s_rows[VOTE_LIST];
     static const char CODE[17] = "=ACMGRSVTWYHKDBN";
-    const uint32_t ntiles = (uint32_t)min((unsigned long long)c.work_ctr[8], c.tile_cap);
-    for (uint32_t q = blockIdx.x; q < ntiles; q += gridDim.x) {
+    for (;;) {
         __syncthreads();
-        if (threadIdx.x == 0) s_tile = c.tiles[q];
+        if (threadIdx.x == 0) { const uint32_t q = atomicAdd(&c.work_ctr[9], 1u); s_tile = q < c.work_ctr[8] && q < c.tile_cap ? c.tiles[q] : make_uint2(0xffffffffu, 0); }
         __syncthreads();
-        const uint32_t ci = s_tile.x;
+        const uint32_t ci = s_tile.x; if (ci == 0xffffffffu) break;
         const uint32_t L = c.alt_len[ci], no = c.plan_nother[ci];
         if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
         const Layout y = cand_layout(c, ci, L, no);
