@@ -183,6 +183,45 @@ def run_task(block, t, config, finalize=True):
     return out
 
 
+def write_reference_snf(block, config_args, path):
+    """The reference's own --snf output for a block: every task runs CallTask's SNF branch (parallel.py:279-292: store the candidates,
+    annotate_block_coverages, write_and_index) and SNFile.write_results joins the parts (snf.py:193-224)."""
+    import io
+    import os
+    import types
+    import_reference()
+    from sniffles import leadprov, parallel, snf as refsnf
+    from sniffles.region import Region
+    config = make_config("--snf", path, *config_args)
+    if not hasattr(config, "mode"):
+        config.mode = "call_sample"
+    config.task_read_id_offset_mult = 10 ** 9
+    results = []
+    for t in range(len(block.task)):
+        task = block.task[t]
+        contig = block.contig_names[int(task["contig"])]
+        tk = parallel.CallTask(id=int(task["task_id"]), sv_id=0, contig=contig, start=int(task["start"]), end=int(task["end"]), config=config, tandem_repeats=None)
+        tk.lead_provider = leadprov.LeadProvider(config, tk.id * config.task_read_id_offset_mult, contig)
+        tk.lead_provider.build_leadtab([Region(contig, tk.start, tk.end)], DuckBam(block, t))
+        cands = tk.call_candidates(False, config)
+        tk.finalize_candidates(cands, True, config)
+        part = f"{path}.tmp_{tk.id}.snf"
+        with open(part, "wb") as handle:
+            out = refsnf.SNFile(config, handle)
+            for c in cands:
+                out.store(c)
+            out.annotate_block_coverages(tk.lead_provider)
+            out.write_and_index()
+        results.append(types.SimpleNamespace(task_id=tk.id, contig=contig, snf_index=out.get_index(), snf_total_length=out.get_total_length(), snf_candidate_count=len(cands),
+                                             snf_filename=part, has_snf=True, coverage_average_total=tk.coverage_average_total))
+    with open(path, "wb") as handle:
+        final = refsnf.SNFile(config, handle)
+        for r in results:
+            final.add_result(r)
+        final.write_results(config, list(block.contig_names))
+    return path
+
+
 class FakeFasta:
     """deterministic reference bases (with a few IUPAC codes) for the VCF writer's REF / anchor fetches; same class feeds both writers"""
     ALPHABET = "ACGTACGTACGTRYNACGTSWK"

@@ -15,12 +15,11 @@ nw = 148 * 8 * 4
 out = np.zeros(nw * 8, "<u8")
 rc = binding.lib().snfb_debug_dump(ctx._h, out.ctypes.data, len(out)); print("rc", rc)
 d = out.reshape(nw, 8)
-busy, total, items, mx, L, Lo = (d[:, i].astype(np.float64) for i in range(6))
+busy, total, items = (d[:, i].astype(np.float64) for i in range(3))
+ph = d[:, 3:8].astype(np.float64).sum(axis=0)
 print("warps", nw, "items", int(items.sum()), "cands", len(res.cand))
 print("elapsed cycles per warp: min %.0f median %.0f max %.0f" % (total.min(), np.median(total), total.max()))
-print("busy  cycles per warp: min %.0f median %.0f max %.0f  (busy/elapsed median %.2f)" % (busy.min(), np.median(busy), busy.max(), np.median(busy / np.maximum(total, 1))))
+print("busy  cycles per warp: median %.0f max %.0f" % (np.median(busy), busy.max()))
 print("cycles per item: mean %.0f" % (busy.sum() / max(items.sum(), 1)))
-o = np.argsort(-mx)[:10]
-print("longest items (cycles, L, Lo):", [(int(mx[i]), int(L[i]), int(Lo[i])) for i in o])
-pct = np.percentile(mx, [50, 90, 99])
-print("per-warp longest item percentiles 50/90/99:", pct)
+names = ["unpack", "probe", "automaton+segments(3a)", "run filter(3b)", "row write(3c)"]
+print("phase shares:", {n: round(float(v / ph.sum()), 3) for n, v in zip(names, ph)})

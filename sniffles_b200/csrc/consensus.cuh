@@ -240,6 +240,8 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
     int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp]; int* run_st = h_a[warp];   /* per-run identity sum */ int* run_len = h_b[warp];
     const int klen = 6;
     unsigned long long d_busy = 0, d_items = 0, d_max = 0, d_L = 0, d_Lo = 0, d_cL = 0, d_cLo = 0; long long d_t0 = 0; const long long d_start = clock64();
+    unsigned long long d_ph[5] = { 0, 0, 0, 0, 0 }; long long d_pt = 0;
+    #define PHASE(k) if (c.dbg) { const long long n_ = clock64(); d_ph[k] += (unsigned long long)(n_ - d_pt); d_pt = n_; }
     for (;;) {
         if (c.dbg && d_t0) { const unsigned long long dt = (unsigned long long)(clock64() - d_t0); d_busy += dt; if (dt > d_max) { d_max = dt; d_L = d_cL; d_Lo = d_cLo; } d_t0 = 0; }
         uint32_t q = 0; if (lane == 0) q = atomicAdd(&c.work_ctr[6], 1u);
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
         if (q >= nb + ns) break;
         const C::Item it = q < nb ? c.items_big[q] : c.items_small[q - nb];
         const uint32_t ci = it.cand; const uint32_t L = c.alt_len[ci];
-        if (c.dbg) { d_t0 = clock64(); ++d_items; d_cL = L; }
+        if (c.dbg) { d_t0 = clock64(); d_pt = d_t0; ++d_items; d_cL = L; }
         if ((unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
         const snfb_cand* cd = &c.cand[ci];
         uint32_t* t_key; int* t_pos; cand_table(c, ci, &t_key, &t_pos);
@@ -261,6 +263,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
         const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
         unpack_lead_warp(c, cd->lead_off + it.k, rd);
         __syncwarp();
+        PHASE(0)
         // (1) anchor hits in j order (table lives in global scratch, L2 resident)
         int nh = 0;
         const long nk = Lo - klen > 0 ? (Lo - klen + skip - 1) / skip : 0;
@@ -275,6 +278,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
         }
         if (nh > MAXHIT) nh = MAXHIT;
         __syncwarp();
+        PHASE(1)
         // (2) anchor automaton (consensus.py:306-338) in closed form: a hit is accepted iff its i exceeds every earlier hit's i
         //     (the accepted hits are the left-to-right maxima), and len(conseq) before accepted hit m is
         //     min(L, c0 + j[m-1] - j[0]) because every step appends min(j step, room left).  Compacted in place.
@@ -313,6 +317,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
         }
         span = (long)__reduce_add_sync(FULL, (unsigned)span);
         __syncwarp();
+        PHASE(2)
         // (3b) dash-free runs (= chains of copied segments) survive only with identity > 0.5 and more than 5 matches
         //      (consensus.py:343-360); decided on the segment list before anything is written.  A non-empty dashed segment
         //      ends a run; run ids are prefix counts of those, the per-run sums are accumulated in shared memory.
@@ -338,6 +343,7 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
             }
             __syncwarp();
         }
+        PHASE(3)
         // (3c) write the row once
         for (long q2 = lane; q2 < c0; q2 += 32) row[q2] = DASH;
         for (int m = 1 + lane; m < na; m += 32) {
@@ -349,9 +355,11 @@ __global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
           for (long q2 = cl + lane; q2 < (long)L; q2 += 32) row[q2] = DASH; }
         if (lane == 0) acc[it.row] = __ddiv_rn((double)span, (double)L) > 0.2;
         __syncwarp();
+        PHASE(4)
     }
     if (c.dbg && lane == 0) { unsigned long long* o = c.dbg + (size_t)(blockIdx.x * ALIGN_WARPS + warp) * 8;
-        o[0] = d_busy; o[1] = (unsigned long long)(clock64() - d_start); o[2] = d_items; o[3] = d_max; o[4] = d_L; o[5] = d_Lo; o[6] = 0; o[7] = 0; }
+        o[0] = d_busy; o[1] = (unsigned long long)(clock64() - d_start); o[2] = d_items; o[3] = d_ph[0]; o[4] = d_ph[1]; o[5] = d_ph[2]; o[6] = d_ph[3]; o[7] = d_ph[4]; }
+    #undef PHASE
 }
 
 // column vote (consensus.py:365-380), one block per (candidate, 4096-column tile); every thread takes four adjacent columns

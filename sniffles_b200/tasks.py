@@ -46,6 +46,28 @@ def cand_ranges(cand, n_task):
     return list(zip(lo.tolist(), hi.tolist()))
 
 
+_BAM = {}      # per-process open BAM files (path -> bamio.BamFile)
+
+
+def open_bam(path):
+    from . import bamio
+    if path not in _BAM:
+        _BAM[path] = bamio.BamFile(path)
+    return _BAM[path]
+
+
+def gpu_count():
+    """GPUs this process may use: SNFB_N_GPUS, else what the CUDA runtime reports (the worker with id w binds to w % n)"""
+    import os
+    if os.environ.get("SNFB_N_GPUS"):
+        return max(1, int(os.environ["SNFB_N_GPUS"]))
+    try:
+        import torch
+        return max(1, torch.cuda.device_count())
+    except Exception:
+        return 1
+
+
 @dataclass
 class Task:
     id: int
@@ -61,14 +83,49 @@ class Task:
     genotype_svs: list = None
     regions: list = None
     result: object = None
-    # the device pass this task reads from, and its index in that block
+    # the device pass this task reads from, and its index in that block.  Either handed in (several tasks sharing one block and one
+    # device pass: run_block), or built by the task itself from its BAM region on first use, the way the reference's worker does.
     block_run: BlockRun = None
     task_index: int = 0
     coverage_average_total: float = 0.0
+    device: int = 0
+
+    # ---- the reference's way: Task(id, sv_id, contig, start, end, config, bam=..., tandem_repeats=...) and a worker (parallel.py:47-60, 741-746)
+    def _own_block(self):
+        """records of [start, end) from the task's BAM (`self.bam`: an open bamio.BamFile or a path; default config.input), packed for the device"""
+        from . import bamio
+        bam = self.bam if self.bam is not None else getattr(self.config, "input", None)
+        if isinstance(bam, str):
+            bam = open_bam(bam)
+        if bam is None:
+            raise RuntimeError("Task has neither a block_run nor a BAM to read its region from")
+        cidx = bam.name_to_id[self.contig]
+        recs = [(0, r) for r in bam.fetch(self.contig, self.start, self.end)]
+        tr = {0: [(int(a), int(b)) for a, b in self.tandem_repeats]} if self.tandem_repeats else None
+        return bamio.pack_records(bam.contigs, recs, [(cidx, int(self.start), int(self.end), int(self.id))], tandem_repeats=tr)
+
+    def _ctx(self):
+        return device_context(self.device)
+
+    def bind(self, worker=None):
+        """device = worker.id % n_gpus: a context per process and device, created lazily after the fork"""
+        if worker is not None and getattr(worker, "id", None) is not None:
+            self.device = int(worker.id) % gpu_count()
+        return self
 
     def build_leadtab(self):
         """parallel.py:90-102 — returns (externals, read_count).  Leads outside the region are dropped on the
         device, exactly as the caller discards `externals` (parallel.py:264)."""
+        if self.block_run is None:
+            block = self._own_block()
+            ctx = self._ctx()
+            ctx.set_config(abi.Config.from_sniffles(self.config))
+            ctx.load(block, cigar16=False)                       # BAM words: the library converts them (snfb_load_records)
+            res = ctx.extract_leads()                            # snfb_extract_leads
+            rec_nm = abi.view(res._rec_nm_ptr, "<f8", len(block.rec)).copy() if getattr(res, "_rec_nm_ptr", None) else None
+            self.block_run = BlockRun(block, res, None, rec_nm)
+            self.task_index = 0
+            self._staged = True
         r = self.block_run.result
         self.config.average_regional_nm = float(r.task_mean_nm[self.task_index])      # leadprov.py:577-578
         self.config.qc_nm_threshold = self.config.average_regional_nm
@@ -77,6 +134,14 @@ class Task:
     def call_candidates(self, keep_qc_fails, config):
         """parallel.py:104-127"""
         br = self.block_run
+        if getattr(self, "_staged", False):
+            ctx = self._ctx()
+            cv = ctx.cluster_call()                              # snfb_cluster_call: candidate records (ALT offsets already planned)
+            sv = ctx.consensus()                                 # snfb_consensus: annotate_sv's INS sequences, which the calls below carry
+            r = br.result
+            r.cand, r.cand_leads, r.rnames, r.rn_off, r.task_cov_mean, r.alt = cv.cand, cv.cand_leads, cv.rnames, cv.rn_off, cv.task_cov_mean, sv.alt
+            br.cand_range = cand_ranges(r.cand, len(br.block.task))
+            self._staged = False
         lo, hi = br.cand_range[self.task_index]
         need_leads = bool(config.mosaic) or bool(config.phase)
         calls = postprocess.calls_from_result(br.result, self.task_index, lo, hi, br.block.contig_names, self.contig, self.id, config,
@@ -94,6 +159,7 @@ class CallTask(Task):
     def execute(self, worker=None):
         """parallel.py:256-297 (VCF path; SNF parts are a "next" row)"""
         config = self.config
+        self.bind(worker)
         qc = not (config.snf is not None or config.no_qc)
         _, read_count = self.build_leadtab()
         cands = self.call_candidates(qc, config)

@@ -118,7 +118,20 @@ def make_config_dump():
         json.dump(out, f, indent=1, sort_keys=True)
 
 
+def make_snf():
+    """the reference's own .snf for one fixture block (the SNF reader / writer are pinned against it)"""
+    kw, args = FIXTURES["c2_ont_wgs_small"]
+    kw2 = dict(kw)
+    blk = synth.generate(kw2.pop("seed"), kw2.pop("contig_len"), kw2.pop("coverage"), **kw2)
+    path = os.path.join(HERE, "c2_ont_wgs_small.snf")
+    harness.write_reference_snf(blk, args, path)
+    print("snf", os.path.getsize(path) // 1024, "KiB")
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["snf"]:
+        make_snf()
+        sys.exit(0)
     if len(sys.argv) > 1:
         make_synthetic(set(sys.argv[1:]))
         sys.exit(0)

@@ -158,3 +158,32 @@ def test_coverage_bins_match_numpy():
             assert len(got) == len(want) and np.array_equal(got, want), t
     finally:
         ctx.close()
+
+
+def test_calltask_from_bam_region(tmp_path):
+    """A CallTask built the reference's way (id, contig, region, config, bam path, tandem repeats — sniffles:313-358) executes through
+    BAM region fetch -> packer -> snfb_load_records -> the three per-stage exports, bound to device worker.id % n_gpus, and gives the
+    calls of the block-level run."""
+    from sniffles_b200 import bamio, tasks
+    blk = synth.generate(91, [260_000, 150_000], 20.0, len_mean=9000.0, len_sd=2500.0, sv_spacing=6000.0, tr_frac=0.2)
+    path = str(tmp_path / "x.bam")
+    bamio.write_bam(path, blk)
+    cfg = sconfig.default_config()
+    br = tasks.run_block(blk, cfg, 0)
+
+    class Worker:
+        id = 5
+
+    for t, name in enumerate(blk.contig_names):
+        tk = blk.task[t]
+        o, n = int(tk["tr_off"]), int(tk["tr_n"])
+        tr = [(int(blk.tr[2 * (o + k)]), int(blk.tr[2 * (o + k) + 1])) for k in range(n)]
+        want = tasks.CallTask(id=t, sv_id=0, contig=name, start=0, end=int(tk["end"]), config=sconfig.default_config(), block_run=br, task_index=t)
+        w_calls, w_reads = want.execute()
+        got = tasks.CallTask(id=t, sv_id=0, contig=name, start=0, end=int(tk["end"]), config=sconfig.default_config(), bam=path, tandem_repeats=tr)
+        g_calls, g_reads = got.execute(Worker())
+        assert got.device == 5 % tasks.gpu_count()
+        assert g_reads == w_reads and len(g_calls) == len(w_calls) > 5
+        for a, b in zip(g_calls, w_calls):
+            assert (a.svtype, a.pos, a.end, a.svlen, a.support, a.filter, a.alt, a.id) == (b.svtype, b.pos, b.end, b.svlen, b.support, b.filter, b.alt, b.id)
+            assert a.genotypes == b.genotypes and a.info == b.info
