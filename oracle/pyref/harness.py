@@ -200,7 +200,11 @@ def write_reference_snf(block, config_args, path):
     for t in range(len(block.task)):
         task = block.task[t]
         contig = block.contig_names[int(task["contig"])]
-        tk = parallel.CallTask(id=int(task["task_id"]), sv_id=0, contig=contig, start=int(task["start"]), end=int(task["end"]), config=config, tandem_repeats=None)
+        tr = None
+        if int(task["tr_n"]) > 0:
+            o, n = int(task["tr_off"]), int(task["tr_n"])
+            tr = [(int(block.tr[2 * (o + k)]), int(block.tr[2 * (o + k) + 1])) for k in range(n)]
+        tk = parallel.CallTask(id=int(task["task_id"]), sv_id=0, contig=contig, start=int(task["start"]), end=int(task["end"]), config=config, tandem_repeats=tr)
         tk.lead_provider = leadprov.LeadProvider(config, tk.id * config.task_read_id_offset_mult, contig)
         tk.lead_provider.build_leadtab([Region(contig, tk.start, tk.end)], DuckBam(block, t))
         cands = tk.call_candidates(False, config)
