@@ -514,12 +514,12 @@ static int enqueue_stage_a(snfb_ctx* ctx) {
         I.rec = ctx->d_rec; I.cigar = ctx->d_cigar; I.task = b.task; I.n_rec = (uint32_t)nrec; I.n_task = nt; I.rec_pos = ctx->rec_pos; I.task_first = ctx->task_first; I.task_last = ctx->task_last;
         I.scan = ctx->scanrec; I.clip = ctx->clip; I.rec_end = ctx->rec_end; I.rec_flags = ctx->rec_flags; I.rec_nm = ctx->rec_nm; I.rec_nlead = ctx->rec_nlead; I.ctr = ctr;
         I.mapq_min = cf.mapq; I.alen_min = cf.min_alignment_length; I.excl = cf.exclude_flags; I.want_nm = (cf.qc_nm_measure || cf.phase) ? 1 : 0; I.n_cigar = ctx->n_cigar;
-        I.pass_flag = ctx->pass_flag; I.pass_groups = ctx->pass_groups; I.rec_big = ctx->rec_big;
+        I.pass_flag = ctx->pass_flag; I.pass_groups = ctx->pass_groups;
         extract::k_rec_index<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(I);
         // sweep order of the streaming kernel: ordinal and first virtual group of every passing record
         LAUNCHED(ctx, prims::exclusive_scan(ctx->pass_flag, ctx->pidx, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_passrec, st));
         LAUNCHED(ctx, prims::exclusive_scan(ctx->pass_groups, ctx->vst, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_vgroups, st));
-        extract::PDescParams D{}; D.scan = ctx->scanrec; D.pidx = ctx->pidx; D.vst = ctx->vst; D.n_rec = (uint32_t)nrec; D.pdesc = ctx->pdesc; D.pvs = ctx->pvs; D.ctr = ctr; D.sa_list = ctx->sa_list; D.n_sa = &ctr->n_sa;
+        extract::PDescParams D{}; D.scan = ctx->scanrec; D.pidx = ctx->pidx; D.vst = ctx->vst; D.n_rec = (uint32_t)nrec; D.pdesc = ctx->pdesc; D.pvs = ctx->pvs; D.ctr = ctr;
         extract::k_pdesc<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(D); LAUNCHED(ctx, 1);
         // algorithmic bytes of the streaming kernel: scan descriptors + CIGAR16 words (+ its per-record outputs and event slices, added by bench.py)
         mark(ctx, "k_scan", sizeof(extract::RecScan) * nrec + 2 * ctx->n_cigar);

@@ -284,7 +284,7 @@ constexpr uint32_t RM_PASS = 1u << 24, RM_HAS_NM = 1u << 25, RM_HAS_SA = 1u << 2
 struct IndexParams {
     const snfb_rec* rec; const uint16_t* cigar; const snfb_task* task; uint32_t n_rec; uint32_t n_task; unsigned long long n_cigar;
     int32_t* rec_pos; uint32_t* task_first; uint32_t* task_last;
-    RecScan* scan; RecClip* clip; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead; int32_t* rec_big;
+    RecScan* scan; RecClip* clip; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
     uint32_t* pass_flag; uint32_t* pass_groups;      // 1 / number of 16-byte CIGAR16 groups for a passing record, else 0 (scanned into the sweep order)
     DevCounters* ctr; int mapq_min, alen_min, excl, want_nm;
 };
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     if ((uint32_t)task >= P.n_task || (cigar_off & 7) || cigar_off + n > P.n_cigar) {      // malformed record (counted by k_validate: the run fails); touch nothing through its offsets
         RecScan s; s.cig8 = 0; s.n_words = 0; s.pos = pos; s.meta = 0; *reinterpret_cast<uint4*>(P.scan + i) = *reinterpret_cast<const uint4*>(&s);
         RecClip c; c.alen = 0; c.qas = 0; c.clip_left = 0; c.clip_right = 0; *reinterpret_cast<int4*>(P.clip + i) = *reinterpret_cast<const int4*>(&c);
-        P.rec_pos[i] = pos; P.rec_flags[i] = 0; P.rec_nm[i] = -1.0; P.rec_end[i] = -1; P.rec_nlead[i] = 0; P.rec_big[i] = 0; P.pass_flag[i] = 0; P.pass_groups[i] = 0; return;
+        P.rec_pos[i] = pos; P.rec_flags[i] = 0; P.rec_nm[i] = -1.0; P.rec_end[i] = -1; P.rec_nlead[i] = 0; P.pass_flag[i] = 0; P.pass_groups[i] = 0; return;
     }
     P.rec_pos[i] = pos;
     if (i == 0) P.task_first[task] = 0;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     *reinterpret_cast<int4*>(P.clip + i) = *reinterpret_cast<const int4*>(&c);
     P.rec_flags[i] = pass ? (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2)) : (uint8_t)0;
     P.rec_nm[i] = has_nm ? (double)nm : -1.0;        // k_rec_post turns it into (nm - big) / (alen + 1)
-    P.rec_end[i] = -1; P.rec_nlead[i] = 0; P.rec_big[i] = 0;
+    P.rec_end[i] = -1; P.rec_nlead[i] = 0;
     P.pass_flag[i] = pass ? 1u : 0u; P.pass_groups[i] = pass ? (n + 7u) >> 3 : 0u;
 }
 
@@ -362,7 +362,7 @@ struct ScanParams {
 };
 
 // thread per record: passing records get their ordinal and first virtual group from two scans; this writes their sweep descriptors
-struct PDescParams { const RecScan* scan; const uint32_t* pidx; const uint32_t* vst; uint32_t n_rec; PDesc* pdesc; uint32_t* pvs; const DevCounters* ctr; uint32_t* sa_list; unsigned long long* n_sa; };
+struct PDescParams { const RecScan* scan; const uint32_t* pidx; const uint32_t* vst; uint32_t n_rec; PDesc* pdesc; uint32_t* pvs; const DevCounters* ctr; };
 __global__ void __launch_bounds__(256) k_pdesc(const PDescParams P) {
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i == 0) P.pvs[P.ctr->n_passrec] = (uint32_t)P.ctr->n_vgroups;
@@ -373,7 +373,6 @@ __global__ void __launch_bounds__(256) k_pdesc(const PDescParams P) {
     PDesc o; o.cig8 = d.x; o.vs = vs; o.pos = (int32_t)d.z; o.meta = d.w; o.rec = i; o.pad0 = o.pad1 = o.pad2 = 0;
     uint4* dst = reinterpret_cast<uint4*>(P.pdesc + p); dst[0] = make_uint4(o.cig8, o.vs, (uint32_t)o.pos, o.meta); dst[1] = make_uint4(o.rec, 0u, 0u, 0u);
     P.pvs[p] = vs;
-    if (d.w & RM_HAS_SA) { const unsigned long long e = atomicAdd(P.n_sa, 1ULL); P.sa_list[e] = i; }      // records whose SA tag k_sa parses (any order)
 }
 // lowers the E-bit threshold of a CIGAR16 arena in place (a config that cares about shorter events than the block was packed for)
 __global__ void k_reflag(uint16_t* __restrict__ cigar, unsigned long long n_words, unsigned evt_min) {
@@ -403,11 +402,11 @@ __device__ __noinline__ uint2 lane_sums_ext(uint32_t w0, uint32_t w1, uint32_t w
     return make_uint2(lq, lr);
 }
 // rare path of k_scan: a step in which some lane holds a flagged word (E bit or extension word).  Every lane passes its own record
-// (a step can span several short records: segments), the positions its segment starts from, and its region.
-// SV signatures are appended to the event list (any order: a lead's place is fixed later by its record and k); the record's lead
-// count and NM correction are kept in rec_nlead / rec_big (zeroed by k_rec_index) and only ever touched here.
-__device__ __noinline__ void scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr, int seg0,
-                                       uint32_t rec, unsigned base_q, int base_r, int tk_start, int tk_end) {
+// (a step can span several short records: segments), the positions / lead ordinal its segment starts from, and its region.
+// SV signatures are appended to the event list (any order: a lead's place is fixed later by its record and k).
+// Returns (big << 32) | events counted, per lane.
+__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr, int seg0,
+                                                      uint32_t rec, unsigned base_q, int base_r, unsigned base_k, int tk_start, int tk_end) {
     const int lane = lane_id();
     const uint32_t ww[4] = { w0, w1, w2, w3 };
     unsigned cls[8], len[8];
@@ -421,40 +420,37 @@ __device__ __noinline__ void scan_rare(const ScanParams* __restrict__ P, uint32_
     for (int j = 0; j < 8; ++j) {
         if (len[j] > 10u && (cls[j] == C16_I || cls[j] == C16_D)) big += len[j];             // get_cigar_indels, minoplen 10
         if (c16_is_event(cls[j]) && (int)len[j] >= P->minsv) evm |= 1u << j; }
-    if (big) atomicAdd(reinterpret_cast<unsigned*>(P->rec_big + rec), big);
-    if (!__any_sync(FULL, evm != 0)) return;
-    const unsigned q0 = base_q + seg_incl_scan(lq, lane, seg0) - lq; const int r0 = base_r + (int)(seg_incl_scan(lr, lane, seg0) - lr);
-    // which signatures stay inside the task's region (leadprov.py:464-466)
     unsigned cnt = 0, emm = 0;
-    { int r2 = r0;
+    if (__any_sync(FULL, evm != 0)) {
+        const unsigned q0 = base_q + seg_incl_scan(lq, lane, seg0) - lq; const int r0 = base_r + (int)(seg_incl_scan(lr, lane, seg0) - lr);
+        // which signatures stay inside the task's region (leadprov.py:464-466)
+        { int r2 = r0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; if (rs >= tk_start && rs < tk_end) { emm |= 1u << j; ++cnt; } }
+                r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); } }
+        const unsigned kseg = seg_incl_scan(cnt, lane, seg0) - cnt;           // events of my record in earlier lanes of this step
+        unsigned inc = cnt;
         #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; if (rs >= tk_start && rs < tk_end) { emm |= 1u << j; ++cnt; } }
-            r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); } }
-    const unsigned kseg = seg_incl_scan(cnt, lane, seg0) - cnt;           // events of my record in earlier lanes of this step
-    unsigned inc = cnt;
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-    const unsigned count = __shfl_sync(FULL, inc, 31);
-    if (!count) return;
-    // events of the record in earlier steps: a record is swept by one warp, step after step, so its counter is only behind by this step's lanes
-    unsigned base_k = 0; if (cnt) base_k = atomicAdd(P->rec_nlead + rec, 0u);
-    __syncwarp();
-    if (cnt) { const unsigned now = atomicAdd(P->rec_nlead + rec, cnt) + cnt; if (now > 0xffffu) atomicAdd(&P->ctr->ordinal_overflow, 1ULL); }
-    unsigned long long e0 = 0; if (lane == 0) e0 = atomicAdd(P->n_ev, (unsigned long long)count);
-    e0 = __shfl_sync(FULL, e0, 0);
-    unsigned mine = inc - cnt, kk = base_k + kseg; unsigned q2 = q0; int r2 = r0;
-    #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (emm & (1u << j)) {
-            const unsigned long long e = e0 + mine;
-            if (e < P->ev_cap) { uint4* dst = reinterpret_cast<uint4*>(P->ev + e); dst[0] = make_uint4(rec, len[j], q2, (uint32_t)r2); dst[1] = make_uint4((kk & 0xffffu) | (cls[j] << 16), 0u, 0u, 0u); }
-            else atomicAdd(&P->ctr->lead_overflow, 1ULL);
-            ++mine; ++kk;
+        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        const unsigned count = __shfl_sync(FULL, inc, 31);
+        if (count) {
+            unsigned long long e0 = 0; if (lane == 0) e0 = atomicAdd(P->n_ev, (unsigned long long)count);
+            e0 = __shfl_sync(FULL, e0, 0);
+            unsigned mine = inc - cnt, kk = base_k + kseg; unsigned q2 = q0; int r2 = r0;
+            #pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (emm & (1u << j)) {
+                    const unsigned long long e = e0 + mine;
+                    if (e < P->ev_cap) { uint4* dst = reinterpret_cast<uint4*>(P->ev + e); dst[0] = make_uint4(rec, len[j], q2, (uint32_t)r2); dst[1] = make_uint4((kk & 0xffffu) | (cls[j] << 16), 0u, 0u, 0u); }
+                    else atomicAdd(&P->ctr->lead_overflow, 1ULL);
+                    ++mine; ++kk;
+                }
+                q2 += len[j] * (cls[j] & 1u); r2 += (int)(len[j] * ((cls[j] >> 1) & 1u));
+            }
         }
-        q2 += len[j] * (cls[j] & 1u); r2 += (int)(len[j] * ((cls[j] >> 1) & 1u));
     }
-    __syncwarp();          // the counter updates above are ordered before the next step's reads by other lanes
+    return ((unsigned long long)big << 32) | cnt;
 }
 
 // first ordinal p in [0, np] with pvs[p] >= target (pvs ascending; pvs[np] = total); the whole warp searches 32 ways per round
@@ -474,16 +470,10 @@ __device__ inline uint32_t warp_lower_bound(const uint32_t* __restrict__ pvs, ui
 
 // The streaming kernel.  The CIGAR16 groups (16 bytes = 8 words) of the PASSING records form one virtual sequence; every warp owns a
 // range of whole records of about total / #warps groups and sweeps it 32 groups (512 bytes) per step, one group per lane, regardless of
-// where records begin and end.  Record boundaries inside a step make segments; the per-record reference span comes from ONE segmented
-// scan over the lanes, and the lane that holds a record's last group stores its end — the cost of a step does not depend on how many
-// records it touches (an ONT read is ~1.5 steps long).  Per 32-bit word (two ops) the hot loop does two masked sums (read / reference
-// advance, both halves at once) and one OR (the E / extension flags).
-// The loop is software pipelined: where a step's groups lie (which record each lane reads) depends only on the record table, never on
-// the CIGAR data, so the 512-byte load of step s + 1 is issued before the data of step s is looked at — two loads in flight per warp.
-struct StepMap {                 // where the 32 groups of one step come from
-    unsigned bmask; int lim, nb, my_k, seg0; uint32_t m_rec, m_meta, vend_last, Gn; int m_pos; bool ended_last;
-};
-__global__ void __launch_bounds__(256, 3) k_scan(const __grid_constant__ ScanParams P) {
+// where records begin and end: a step that spans several short records is handled as segments (at most one record boundary per step is the
+// fast case: ONT reads are ~1.5 steps long).  Per 32-bit word (two ops) the hot loop does two masked sums (read / reference advance, both
+// halves at once) and one OR (the E / extension flags); everything else is per step.
+__global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanParams P) {
     const int lane = lane_id();
     const uint32_t np = (uint32_t)P.ctr->n_passrec; const unsigned long long V = P.ctr->n_vgroups;
     if (np == 0) return;
@@ -493,45 +483,47 @@ __global__ void __launch_bounds__(256, 3) k_scan(const __grid_constant__ ScanPar
     if (p_lo >= p_hi) return;
     const uint4* __restrict__ cig4 = reinterpret_cast<const uint4*>(P.cigar);
     const uint32_t Gend = P.pvs[p_hi];
-    // window of 32 record descriptors: lane j holds ordinal pbase + j; `pcur` is the record the next step's first group belongs to
+    // current record (warp-uniform) and the window of the 32 records after `pbase` (lane j: ordinal pbase + 1 + j)
     uint32_t pcur = p_lo, pbase = p_lo;
+    uint32_t cur_cig8, cur_vs, cur_meta, cur_rec, cur_vend; int cur_pos;
+    { const uint4 a = __ldg(reinterpret_cast<const uint4*>(P.pdesc + pcur)); const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(P.pdesc + pcur) + 4);
+      cur_cig8 = a.x; cur_vs = a.y; cur_pos = (int)a.z; cur_meta = a.w; cur_rec = r; cur_vend = P.pvs[pcur + 1]; }
     uint32_t w_cig8 = 0, w_vs = 0xffffffffu, w_meta = 0, w_rec = 0; int w_pos = 0;
-    #define LOAD_WINDOW() { const uint32_t q_ = pbase + (uint32_t)lane; if (q_ < p_hi) { const uint4 a_ = __ldg(reinterpret_cast<const uint4*>(P.pdesc + q_)); \
+    #define LOAD_WINDOW() { const uint32_t q_ = pbase + 1 + (uint32_t)lane; if (q_ < p_hi) { const uint4 a_ = __ldg(reinterpret_cast<const uint4*>(P.pdesc + q_)); \
         w_cig8 = a_.x; w_vs = a_.y; w_pos = (int)a_.z; w_meta = a_.w; w_rec = __ldg(reinterpret_cast<const uint32_t*>(P.pdesc + q_) + 4); } else { w_vs = 0xffffffffu; w_cig8 = 0; w_meta = 0; w_rec = 0; w_pos = 0; } }
-    // map the step that starts at group G_ (advances pcur / the window) and issue its load into V_
-    #define MAP_AND_LOAD(M_, V_, G_) { \
-        if (pcur - pbase >= 8) { pbase = pcur; LOAD_WINDOW() } \
-        const uint32_t dv_ = w_vs - (G_); \
-        const bool has_ = dv_ < 32u && pbase + (uint32_t)lane > pcur;      /* w_vs = 0xffffffff (no record) never lands in the step: Gend <= 2^32 - 64 */ \
-        const unsigned cbit_ = has_ ? 1u << dv_ : 0u; \
-        unsigned bm_ = __reduce_or_sync(FULL, cbit_); \
-        int lim_ = (Gend - (G_)) < 32u ? (int)(Gend - (G_)) : 32; \
-        if (bm_ >> 23) { const unsigned lastbit_ = __shfl_sync(FULL, cbit_, 31); if (lastbit_) { const int cut_ = __ffs(lastbit_) - 1; if (cut_ < lim_) lim_ = cut_; bm_ &= lastbit_ - 1u; } }   /* the window's last lane is a sentinel the step stops in front of */ \
-        const int nb_ = __popc(bm_); \
-        const unsigned below_ = bm_ & (0xffffffffu >> (31 - lane)); \
-        const int mk_ = __popc(below_); \
-        const int wl_ = (int)(pcur - pbase) + mk_;                          /* window lane of my record */ \
-        const uint32_t mc_ = __shfl_sync(FULL, w_cig8, wl_), mv_ = __shfl_sync(FULL, w_vs, wl_); \
-        (M_).m_rec = __shfl_sync(FULL, w_rec, wl_); (M_).m_pos = __shfl_sync(FULL, w_pos, wl_); (M_).m_meta = __shfl_sync(FULL, w_meta, wl_); \
-        const int wle_ = (int)(pcur - pbase) + nb_ + 1; \
-        const uint32_t nv_ = __shfl_sync(FULL, w_vs, wle_ & 31); \
-        (M_).vend_last = pcur + (uint32_t)nb_ + 1 >= p_hi ? Gend : nv_;      /* wle_ <= 31: the sentinel keeps the last record of a step inside the window */ \
-        (M_).bmask = bm_; (M_).lim = lim_; (M_).nb = nb_; (M_).my_k = mk_; (M_).seg0 = mk_ ? 31 - __clz(below_) : 0; \
-        (M_).Gn = (G_) + (uint32_t)lim_; (M_).ended_last = (M_).Gn == (M_).vend_last; \
-        (V_) = make_uint4(0, 0, 0, 0); \
-        if (lane < lim_) (V_) = __ldg(cig4 + (mc_ + ((G_) + (uint32_t)lane - mv_))); \
-        pcur += (uint32_t)nb_ + ((M_).ended_last ? 1u : 0u); }
+    // the record of ordinal `pcur` becomes the current one (its descriptor sits in the window; the end of the last record of the range is Gend)
+    #define ENTER_CUR() { const int l2_ = (int)(pcur - pbase) - 1; \
+        cur_cig8 = __shfl_sync(FULL, w_cig8, l2_); cur_vs = __shfl_sync(FULL, w_vs, l2_); cur_pos = __shfl_sync(FULL, w_pos, l2_); cur_meta = __shfl_sync(FULL, w_meta, l2_); cur_rec = __shfl_sync(FULL, w_rec, l2_); \
+        const uint32_t nv_ = __shfl_sync(FULL, w_vs, (l2_ + 1) & 31); cur_vend = pcur + 1 >= p_hi ? Gend : (l2_ + 1 < 32 ? nv_ : P.pvs[pcur + 1]); }
+    #define FINISH_REC(rec_, meta_, end_, n_, big_) { if ((n_) > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL); \
+        P.rec_end[rec_] = (end_); P.rec_nlead[rec_] = (n_); P.rec_big[rec_] = (int)(big_); \
+        if ((meta_) & RM_HAS_SA) { const unsigned long long e_ = atomicAdd(P.n_sa, 1ULL); P.sa_list[e_] = (rec_); } }
     LOAD_WINDOW()
-    uint32_t G = __shfl_sync(FULL, w_vs, 0);
-    unsigned acc_q = 0; int acc_r = __shfl_sync(FULL, w_pos, 0);        // read / reference position reached in the record in progress
-    StepMap A; uint4 va;
-    MAP_AND_LOAD(A, va, G)
-    for (;;) {
-        // the next step's load goes out before this step's data is touched
-        StepMap B; uint4 vb = make_uint4(0, 0, 0, 0); const bool more = A.Gn < Gend;
-        int fresh_pos = 0;                                                   // position of the record a fresh step 'B' starts (when A's last record ended)
-        if (more) { MAP_AND_LOAD(B, vb, A.Gn) fresh_pos = __shfl_sync(FULL, B.m_pos, 0); }
-        const uint32_t w0 = va.x, w1 = va.y, w2 = va.z, w3 = va.w;
+    uint32_t G = cur_vs;
+    unsigned acc_q = 0, acc_big = 0, acc_n = 0; int acc_r = cur_pos;     // the record in progress
+    int tk_id = -1, tk_start = 0, tk_end = 0;
+    while (G < Gend) {
+        if (pcur - pbase >= 8) { pbase = pcur; LOAD_WINDOW() }
+        // record starts inside (G, G + 32): one bit per start; the window's last lane is a sentinel the step stops in front of
+        const uint32_t dv = w_vs - G;
+        const bool has = dv < 32u && pbase + 1 + (uint32_t)lane > pcur;            // w_vs = 0xffffffff (no record) never lands in the step: Gend <= 2^32 - 64
+        const unsigned cbit = has ? 1u << dv : 0u;
+        unsigned bmask = __reduce_or_sync(FULL, cbit);
+        int lim = (Gend - G) < 32u ? (int)(Gend - G) : 32;
+        if (bmask >> 24) { const unsigned lastbit = __shfl_sync(FULL, cbit, 31); if (lastbit) { const int cut = __ffs(lastbit) - 1; if (cut < lim) lim = cut; bmask &= lastbit - 1u; } }   // only a step dense with starts can reach the sentinel
+        const int nb = __popc(bmask);
+        const int my_k = __popc(bmask & (0xffffffffu >> (31 - lane)));       // starts at lanes <= mine
+        uint32_t m_cig8 = cur_cig8, m_vs = cur_vs;
+        if (nb) { const int wl = (int)(pcur - pbase) + my_k - 1;             // window lane of my record (my_k > 0)
+            const uint32_t s_cig8 = __shfl_sync(FULL, w_cig8, wl & 31), s_vs = __shfl_sync(FULL, w_vs, wl & 31);
+            if (my_k) { m_cig8 = s_cig8; m_vs = s_vs; } }
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (lane < lim) {
+            const uint4* src = cig4 + (m_cig8 + (G + (uint32_t)lane - m_vs));
+            v = __ldg(src);
+            if (nb == 0 && G + 32u + (uint32_t)lane < cur_vend) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + 32));   // the next step of the same record
+        }
+        const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
         uint32_t aq = 0, ar = 0;
         #define WORD_BODY(w) { const uint32_t t_ = (w) >> 11; aq += (w) & ((t_ & 0x00010001u) * 0x7ffu); ar += (w) & (((t_ >> 1) & 0x00010001u) * 0x7ffu); }
         WORD_BODY(w0) WORD_BODY(w1) WORD_BODY(w2) WORD_BODY(w3)
@@ -539,26 +531,82 @@ __global__ void __launch_bounds__(256, 3) k_scan(const __grid_constant__ ScanPar
         const uint32_t rb = (w0 | w1 | w2 | w3) & 0xC000C000u;
         unsigned lq = (aq & 0xffffu) + (aq >> 16), lr = (ar & 0xffffu) + (ar >> 16);
         if (rb & 0x80008000u) { const uint2 t_ = lane_sums_ext(w0, w1, w2, w3); lq = t_.x; lr = t_.y; }
-        // positions my segment starts from
-        const unsigned base_q = A.my_k ? 0u : acc_q; const int base_r = A.my_k ? A.m_pos : acc_r;
-        if (__any_sync(FULL, rb != 0u)) {
-            const snfb_task t = P.task[A.m_meta & 0xffffu];
-            scan_rare(&P, w0, w1, w2, w3, lq, lr, A.seg0, A.m_rec, base_q, base_r, t.start, t.end);
+        const bool any_rare = __any_sync(FULL, rb != 0u);
+        G += (uint32_t)lim;
+        if (nb <= 1) {
+            // ---- at most one record starts inside the step: segment 0 = the record in progress, segment 1 = the next one
+            const bool in0 = my_k == 0;
+            unsigned tq = __reduce_add_sync(FULL, lq), tr = __reduce_add_sync(FULL, lr), tq0 = tq, tr0 = tr;
+            if (nb) { tq0 = __reduce_add_sync(FULL, in0 ? lq : 0u); tr0 = __reduce_add_sync(FULL, in0 ? lr : 0u); }
+            unsigned tb0 = 0, tn0 = 0, tb1 = 0, tn1 = 0;
+            if (any_rare) {
+                int t_task = (int)(cur_meta & 0xffffu); uint32_t t_rec = cur_rec; unsigned bq = acc_q, bn = acc_n; int br = acc_r, seg0 = 0;
+                if (nb) { const int wl = (int)(pcur - pbase);                 // the next record: window lane pcur + 1 - pbase - 1
+                    const uint32_t n_meta = __shfl_sync(FULL, w_meta, wl), n_rec = __shfl_sync(FULL, w_rec, wl); const int n_pos = __shfl_sync(FULL, w_pos, wl);
+                    if (!in0) { t_task = (int)(n_meta & 0xffffu); t_rec = n_rec; bq = 0; bn = 0; br = n_pos; seg0 = __ffs(bmask) - 1; } }
+                if (t_task != tk_id) { const snfb_task t = P.task[t_task]; tk_id = t_task; tk_start = t.start; tk_end = t.end; }     // per lane when the two records sit on different tasks
+                const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, seg0, t_rec, bq, br, bn, tk_start, tk_end);
+                if (nb) tk_id = -1;                                                // lanes may hold different tasks now: reload next time
+                const unsigned lb = (unsigned)(rr >> 32), ln = (unsigned)rr;
+                const unsigned tb = __reduce_add_sync(FULL, lb), tn = __reduce_add_sync(FULL, ln);
+                tb0 = tb; tn0 = tn;
+                if (nb) { tb0 = __reduce_add_sync(FULL, in0 ? lb : 0u); tn0 = __reduce_add_sync(FULL, in0 ? ln : 0u); tb1 = tb - tb0; tn1 = tn - tn0; }
+            }
+            acc_q += tq0; acc_r += (int)tr0; acc_big += tb0; acc_n += tn0;
+            if (nb) {                                 // the record in progress ended inside the step; the next one is in progress now
+                if (lane == 0) FINISH_REC(cur_rec, cur_meta, acc_r, acc_n, acc_big)
+                ++pcur; ENTER_CUR()
+                acc_q = tq - tq0; acc_r = cur_pos + (int)(tr - tr0); acc_big = tb1; acc_n = tn1;
+            }
+            if (G == cur_vend) {                      // the record in progress ends with the step
+                if (lane == 0) FINISH_REC(cur_rec, cur_meta, acc_r, acc_n, acc_big)
+                ++pcur;
+                if (pcur < p_hi) { ENTER_CUR() acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
+            }
+            continue;
         }
-        // one segmented scan for both sums: high word = read advance, low word = reference advance
-        unsigned long long sc = ((unsigned long long)lq << 32) | lr;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned long long t = __shfl_up_sync(FULL, sc, o); if (lane - o >= A.seg0) sc += t; }
-        const unsigned tot_q = base_q + (unsigned)(sc >> 32); const int tot_r = base_r + (int)(unsigned)sc;
-        const bool end_here = lane < A.lim && ((lane + 1 < A.lim && ((A.bmask >> (lane + 1)) & 1u)) || (lane == A.lim - 1 && A.ended_last));
-        if (end_here) P.rec_end[A.m_rec] = tot_r;
-        if (!more) break;
-        // carry into the next step: a fresh record starts at its own position, a continued one where this step left it
-        if (A.ended_last) { acc_q = 0; acc_r = fresh_pos; }
-        else { acc_q = __shfl_sync(FULL, tot_q, A.lim - 1); acc_r = __shfl_sync(FULL, tot_r, A.lim - 1); }
-        A = B; va = vb;
+        // ---- several records start in this step (short records): segment s is ordinal pcur + s
+        const unsigned below = bmask & (0xffffffffu >> (31 - lane));
+        const int seg0 = my_k ? 31 - __clz(below) : 0;
+        const int wl = (int)(pcur - pbase) + my_k - 1;
+        const uint32_t s_meta = __shfl_sync(FULL, w_meta, wl & 31), s_rec = __shfl_sync(FULL, w_rec, wl & 31); const int s_pos = __shfl_sync(FULL, w_pos, wl & 31);
+        const uint32_t m_meta = my_k ? s_meta : cur_meta, m_rec = my_k ? s_rec : cur_rec;
+        unsigned l_big = 0, l_cnt = 0;
+        if (any_rare) {
+            const snfb_task t = P.task[m_meta & 0xffffu]; tk_id = -1;
+            const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, seg0, m_rec, my_k ? 0u : acc_q, my_k ? s_pos : acc_r, my_k ? 0u : acc_n, t.start, t.end);
+            l_big = (unsigned)(rr >> 32); l_cnt = (unsigned)rr;
+        }
+        // per-segment totals; lane s keeps the outputs of segment s when that record ends in this step
+        uint32_t o_rec = 0, o_meta = 0, o_n = 0; int o_end = 0, o_big = 0; bool o_valid = false;
+        unsigned last_q = 0, last_big = 0, last_n = 0; int last_r = 0;
+        for (int sg = 0; sg <= nb; ++sg) {
+            const bool mine = my_k == sg && lane < lim;
+            const unsigned tq = __reduce_add_sync(FULL, mine ? lq : 0u), tr = __reduce_add_sync(FULL, mine ? lr : 0u);
+            unsigned tb = 0, tn = 0;
+            if (any_rare) { tb = __reduce_add_sync(FULL, mine ? l_big : 0u); tn = __reduce_add_sync(FULL, mine ? l_cnt : 0u); }
+            const int wls = (int)(pcur - pbase) + sg - 1;
+            const uint32_t g_rec = sg ? __shfl_sync(FULL, w_rec, wls & 31) : cur_rec, g_meta = sg ? __shfl_sync(FULL, w_meta, wls & 31) : cur_meta;
+            const int g_pos = sg ? __shfl_sync(FULL, w_pos, wls & 31) : cur_pos;
+            const unsigned bq = sg ? 0u : acc_q, bb = sg ? 0u : acc_big, bn = sg ? 0u : acc_n; const int br = sg ? g_pos : acc_r;
+            if (sg < nb) { if (lane == sg) { o_valid = true; o_rec = g_rec; o_meta = g_meta; o_end = br + (int)tr; o_big = (int)(bb + tb); o_n = bn + tn; } }
+            else { last_q = bq + tq; last_r = br + (int)tr; last_big = bb + tb; last_n = bn + tn; }
+        }
+        // the last segment becomes the record in progress, or ends exactly with the step
+        pcur += (uint32_t)nb;
+        ENTER_CUR()
+        acc_q = last_q; acc_r = last_r; acc_big = last_big; acc_n = last_n;
+        if (G == cur_vend) {
+            if (lane == nb) { o_valid = true; o_rec = cur_rec; o_meta = cur_meta; o_end = acc_r; o_big = (int)acc_big; o_n = acc_n; }
+            ++pcur;
+            if (pcur < p_hi) {
+                if (pcur - pbase >= 32) { pbase = pcur - 1; LOAD_WINDOW() }
+                ENTER_CUR() acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
+        }
+        if (o_valid) FINISH_REC(o_rec, o_meta, o_end, o_n, o_big)
     }
-    #undef MAP_AND_LOAD
+    #undef FINISH_REC
+    #undef ENTER_CUR
     #undef LOAD_WINDOW
 }
 
