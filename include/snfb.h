@@ -17,6 +17,7 @@
  *   snfb_consensus         <- postprocessing.annotate_sv INS branch (postprocessing.py:33-66)
  *                             + consensus.novel_from_reads (consensus.py:280-394);
  *                             call site Task.finalize_candidates parallel.py:145
+ *   snfb_poa               <- spoa.poa as LocalAsm.assembly calls it (local_asm.py:287-291); call site parallel.py:186-196
  *   snfb_coverage_bins     <- SNFile.annotate_block_coverages' reshape-mean of lead_provider.coverage
  *                             (snf.py:248-267)
  *   snfb_allgather_candidates <- the parent collecting every worker's finished task results before VCF
@@ -352,6 +353,24 @@ typedef struct snfb_gather_view {
 int         snfb_nccl_unique_id(void* out128);
 int         snfb_comm_init(snfb_ctx* ctx, const void* unique_id128, int rank, int nranks);
 int         snfb_allgather_candidates(snfb_ctx* ctx, uint32_t flags, snfb_gather_view* out);
+/* ---- local assembly (LocalAsm, local_asm.py:254-304; gate parallel.py:186-196): the partial-order alignment the reference hands to pyspoa ----
+ * A job is either mode 0: consensus of n_seq sequences = poa(read windows, local, min_coverage) (local_asm.py:287), or mode 1: the two-row
+ * MSA of (sequence 0, sequence 1) = poa([consensus, ref], local, genmsa, m, n, g, e, q, c) (local_asm.py:289-291).  Sequences are bytes
+ * compared for equality only; rows of an MSA use 255 for '-'.  out_len[k] = length / number of columns, -1 when the graph outgrew its
+ * bounds, -2 when the job does not fit the scratch.  The algorithm is the one restated in oracle/poa_oracle.c (parity with pyspoa unpinned). */
+typedef struct snfb_poa_job {
+    uint64_t seq_off;        /* first byte of the job's sequences in seqs[]                                        */
+    uint32_t offs_off;       /* index in offs[] of the job's n_seq + 1 offsets (relative to seq_off, ascending)    */
+    uint32_t n_seq;
+    int32_t  min_cov;        /* mode 0: round(0.5 n) (local_asm.py:285)                                            */
+    int32_t  m, n, g, e, q, c;  /* match, mismatch, gap open / extend, second affine piece open / extend             */
+    int32_t  band;           /* half width of the band around a node's column (>= the longest sequence: no band)   */
+    uint32_t mode;
+    uint32_t out_cap;        /* bytes per output row                                                               */
+    uint64_t out_off;        /* mode 0: one row at out[out_off], mode 1: two rows of out_cap bytes                 */
+} snfb_poa_job;
+int         snfb_poa(snfb_ctx* ctx, const snfb_poa_job* jobs, uint32_t n_jobs, const uint8_t* seqs, uint64_t n_seq_bytes, const int32_t* offs, uint64_t n_offs,
+                     uint8_t* out, uint64_t out_bytes, int32_t* out_len);
 /* developer aid: with SNFB_DEBUG set in the environment the consensus alignment kernel records, per warp, busy cycles / elapsed cycles / items /
  * longest item (cycles, consensus length, read length); returns 1 when nothing was recorded */
 int         snfb_debug_dump(snfb_ctx* ctx, uint64_t* out, uint64_t n_words);

@@ -124,6 +124,11 @@ class SeqView(C.Structure):
 GATHER_LEADS, GATHER_DEVICE_ONLY = 1, 2
 
 
+class PoaJob(C.Structure):
+    _fields_ = [("seq_off", C.c_uint64), ("offs_off", C.c_uint32), ("n_seq", C.c_uint32), ("min_cov", C.c_int32)] + [(k, C.c_int32) for k in ("m", "n", "g", "e", "q", "c", "band")] + [
+        ("mode", C.c_uint32), ("out_cap", C.c_uint32), ("out_off", C.c_uint64)]
+
+
 class GatherView(C.Structure):
     _fields_ = [("n_cand", C.c_uint64), ("cand", C.c_void_p), ("n_alt_bytes", C.c_uint64), ("alt", C.c_void_p),
                 ("n_rnames", C.c_uint64), ("rnames", C.c_void_p), ("rnames_off", C.c_void_p),

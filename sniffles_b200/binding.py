@@ -16,7 +16,7 @@ EXPORTS = ["snfb_version", "snfb_sizeof", "snfb_hash_name", "snfb_ctx_create", "
            "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
            "snfb_last_timings", "snfb_device_candidates", "snfb_device_alt", "snfb_launch_count",
            "snfb_pin_host", "snfb_unpin_host", "snfb_pack_cigar16", "snfb_rerun_count", "snfb_coverage_bins",
-           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates", "snfb_selftest_sqrt_frac", "snfb_debug_dump"]
+           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates", "snfb_selftest_sqrt_frac", "snfb_debug_dump", "snfb_poa"]
 
 
 def lib():
@@ -55,6 +55,7 @@ def lib():
         L.snfb_comm_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.snfb_allgather_candidates.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GatherView)]
         L.snfb_debug_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.snfb_poa.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
         L.snfb_selftest_sqrt_frac.restype = C.c_double
         L.snfb_selftest_sqrt_frac.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
         L.snfb_pack_cigar16.restype = C.c_uint64
@@ -252,6 +253,53 @@ class Context:
             g.rn_off = cp(abi.view(gv.rnames_off, "<u4", gv.n_cand + 1))
             g.cand_leads = cp(abi.view(gv.cand_leads, abi.LEAD_DTYPE, gv.n_cand_leads)) if with_leads else np.zeros(0, abi.LEAD_DTYPE)
         return g
+
+    def poa(self, jobs):
+        """Partial-order alignment jobs on the device (snfb_poa; LocalAsm's two spoa calls, local_asm.py:287-291).
+        jobs: dicts with seqs (list of bytes), mode (0 consensus / 1 two-row MSA), min_cov, scores (m, n, g, e, q, c), band.
+        Returns per job: bytes (mode 0), (row_a, row_b) with b'-' gaps (mode 1), or None when the job failed."""
+        n = len(jobs)
+        if n == 0:
+            return []
+        J = (abi.PoaJob * n)()
+        flat, offs, out_off = [], [], 0
+        seq_off = 0
+        for k, jb in enumerate(jobs):
+            seqs = [bytes(x) for x in jb["seqs"]]
+            total = sum(len(x) for x in seqs)
+            J[k].seq_off, J[k].offs_off, J[k].n_seq = seq_off, len(offs), len(seqs)
+            o = 0
+            for x in seqs:
+                offs.append(o)
+                o += len(x)
+            offs.append(o)
+            flat.extend(seqs)
+            seq_off += total
+            J[k].min_cov = int(jb.get("min_cov", 1))
+            J[k].m, J[k].n, J[k].g, J[k].e, J[k].q, J[k].c = [int(x) for x in jb["scores"]]
+            J[k].band = int(min(jb.get("band", 1 << 28), 1 << 28))
+            J[k].mode = int(jb.get("mode", 0))
+            cap = total + 16
+            J[k].out_cap, J[k].out_off = cap, out_off
+            out_off += cap * (2 if J[k].mode == 1 else 1)
+        sq = np.frombuffer(b"".join(flat), "u1").copy() if seq_off else np.zeros(1, "u1")
+        of = np.asarray(offs, dtype="<i4")
+        out = np.zeros(max(out_off, 1), "u1")
+        ln = np.zeros(n, "<i4")
+        self._check(self._lib.snfb_poa(self._h, J, n, sq.ctypes.data, seq_off, of.ctypes.data, len(of), out.ctypes.data, out_off, ln.ctypes.data), "snfb_poa")
+        res = []
+        dec = lambda r: bytes(45 if x == 255 else x for x in r)
+        for k in range(n):
+            L = int(ln[k])
+            if L < 0:
+                res.append(None)
+            elif J[k].mode == 0:
+                res.append(out[J[k].out_off:J[k].out_off + L].tobytes())
+            else:
+                a = out[J[k].out_off:J[k].out_off + L]
+                b = out[J[k].out_off + J[k].out_cap:J[k].out_off + J[k].out_cap + L]
+                res.append((dec(a), dec(b)))
+        return res
 
     def device_alt(self):
         p = C.c_void_p()

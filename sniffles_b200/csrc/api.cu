@@ -22,6 +22,7 @@
 #include "extract.cuh"
 #include "cluster.cuh"
 #include "consensus.cuh"
+#include "poa.cuh"
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -927,6 +928,46 @@ int snfb_allgather_candidates(snfb_ctx* ctx, uint32_t flags, snfb_gather_view* o
         return 0;
     }
     return fail(ctx, "gather buffer sizes did not converge");
+}
+
+// partial-order-alignment jobs (LocalAsm, local_asm.py:254-304): host buffers in, host buffers out; a block per job
+int snfb_poa(snfb_ctx* ctx, const snfb_poa_job* jobs, uint32_t n_jobs, const uint8_t* seqs, uint64_t n_seq_bytes, const int32_t* offs, uint64_t n_offs, uint8_t* out, uint64_t out_bytes, int32_t* out_len) {
+    if (!ctx || (n_jobs && (!jobs || !seqs || !offs || !out || !out_len))) return ctx ? fail(ctx, "snfb_poa: null argument") : 1;
+    if (n_jobs == 0) return 0;
+    cudaSetDevice(ctx->device);
+    // scratch: the largest job decides the per-block size; as many blocks as a third of the free memory allows
+    size_t smax = 0;
+    for (uint32_t k = 0; k < n_jobs; ++k) {
+        const snfb_poa_job& j = jobs[k];
+        if ((uint64_t)j.offs_off + j.n_seq + 1 > n_offs) return fail(ctx, "snfb_poa: offsets outside offs[]");
+        const int32_t* o = offs + j.offs_off; int total = 0, maxl = 0;
+        for (uint32_t i = 0; i < j.n_seq; ++i) { const int l = o[i + 1] - o[i]; if (l < 0) return fail(ctx, "snfb_poa: decreasing offsets"); total += l; if (l > maxl) maxl = l; }
+        if (j.seq_off + (uint64_t)(j.n_seq ? o[j.n_seq] : 0) > n_seq_bytes) return fail(ctx, "snfb_poa: sequences outside seqs[]");
+        if (j.out_off + (uint64_t)j.out_cap * (j.mode == 1 ? 2 : 1) > out_bytes) return fail(ctx, "snfb_poa: output outside out[]");
+        if (j.mode == 1 && j.n_seq != 2) return fail(ctx, "snfb_poa: the MSA mode takes exactly two sequences");
+        const int bw = 2 * j.band + 1 < maxl ? 2 * j.band + 1 : (maxl > 0 ? maxl : 1);
+        smax = std::max(smax, poa::scratch_bytes(total, maxl, bw));
+    }
+    size_t free_b = 0, total_b = 0; cudaMemGetInfo(&free_b, &total_b);
+    size_t nblk = std::min<size_t>(n_jobs, 148 * 2);
+    while (nblk > 1 && nblk * smax > free_b / 3) --nblk;
+    if (smax > free_b / 2) return fail(ctx, "snfb_poa: a job needs more scratch than the device has free");
+    DevBuf d_jobs, d_seqs, d_offs, d_out, d_len, d_scr, d_ctr;
+    int rc = d_jobs.ensure(sizeof(snfb_poa_job) * n_jobs) | d_seqs.ensure(n_seq_bytes + 16) | d_offs.ensure(4 * n_offs + 16) | d_out.ensure(out_bytes + 16) | d_len.ensure(4 * (size_t)n_jobs) | d_scr.ensure(nblk * smax) | d_ctr.ensure(64);
+    auto done = [&](int r) { d_jobs.release(); d_seqs.release(); d_offs.release(); d_out.release(); d_len.release(); d_scr.release(); d_ctr.release(); return r; };
+    if (rc) return done(fail(ctx, "snfb_poa: out of device memory"));
+    cudaStream_t st = ctx->st;
+    cudaMemcpyAsync(d_jobs.p, jobs, sizeof(snfb_poa_job) * n_jobs, cudaMemcpyHostToDevice, st); cudaMemcpyAsync(d_seqs.p, seqs, n_seq_bytes, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d_offs.p, offs, 4 * n_offs, cudaMemcpyHostToDevice, st); cudaMemsetAsync(d_ctr.p, 0, 64, st); cudaMemsetAsync(d_out.p, 0, out_bytes, st);
+    poa::Params P{}; P.jobs = d_jobs.as<poa::Job>(); P.n_jobs = n_jobs; P.seqs = d_seqs.as<uint8_t>(); P.offs = d_offs.as<int>(); P.out = d_out.as<uint8_t>(); P.out_len = d_len.as<int>();
+    P.scratch = d_scr.as<uint8_t>(); P.scratch_per_block = smax; P.next_job = d_ctr.as<unsigned>();
+    mark(ctx, "poa");
+    poa::k_poa<<<(unsigned)nblk, poa::THREADS, 0, st>>>(P); LAUNCHED(ctx, 1);
+    mark(ctx, nullptr);
+    cudaMemcpyAsync(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(out_len, d_len.p, 4 * (size_t)n_jobs, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(fail(ctx, std::string("snfb_poa: ") + cudaGetErrorString(e)));
+    return done(0);
 }
 
 // mean coverage of `binsize`-base bins over one task's region (snf.py:248-267: the 500-bp means the SNF writer stores)

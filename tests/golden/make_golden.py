@@ -128,7 +128,60 @@ def make_snf():
     print("snf", os.path.getsize(path) // 1024, "KiB")
 
 
+def make_local_asm_vectors():
+    """the reference's own LocalAsm.select_padding / solve_ins / solve_del / SPOA.set on seeded alignment strings
+    (local_asm.py:26-252): pins the host side of the local assembly; the POA itself (pyspoa) is absent here"""
+    import random
+    import types
+    harness.import_reference()
+    from sniffles import local_asm
+    rnd = random.Random(2024)
+    out = dict(padding=[], scores=[], solve=[])
+    for svlen in [45, 50, 120, 399, 400, 401, 800, 1200, 1201, 3000, 9999, 10000, -60, -400, -401, -5000]:
+        sv = types.SimpleNamespace(svlen=svlen)
+        la = local_asm.LocalAsm.__new__(local_asm.LocalAsm)
+        la.sv = sv
+        out["padding"].append([svlen, la.select_padding("sv"), la.select_padding("half")])
+        sp = local_asm.SPOA()
+        sp.set(svlen)
+        out["scores"].append([svlen, sp.match, sp.miss, sp.gap_open, sp.gap_expand, sp.gap_open2, sp.gap_expand2])
+    bases = "ACGT"
+    for k in range(240):
+        svtype = "INS" if k % 2 == 0 else "DEL"
+        svlen = rnd.choice([50, 80, 150, 400, 900, 2000])
+        L = rnd.randrange(200, 1500)
+        core = "".join(rnd.choice(bases) for _ in range(L))
+        cut = rnd.randrange(20, L - 20)
+        gap = max(1, int(svlen * rnd.choice([0.5, 0.86, 0.95, 1.0, 1.05, 1.14, 1.3])))
+        extra = rnd.choice([0, 0, 1, 2, 4])            # more small gap runs somewhere
+        insseq = "".join(rnd.choice(bases) for _ in range(gap))
+        if svtype == "INS":
+            sv_aln, ref_aln = core[:cut] + insseq + core[cut:], core[:cut] + "-" * gap + core[cut:]
+        else:
+            sv_aln, ref_aln = core[:cut] + "-" * gap + core[cut:], core[:cut] + insseq + core[cut:]
+        for _ in range(extra):
+            p = rnd.randrange(5, len(sv_aln) - 5)
+            g = rnd.randrange(1, 6)
+            if rnd.random() < 0.5:
+                sv_aln, ref_aln = sv_aln[:p] + "-" * g + sv_aln[p:], ref_aln[:p] + "".join(rnd.choice(bases) for _ in range(g)) + ref_aln[p:]
+            else:
+                sv_aln, ref_aln = sv_aln[:p] + "".join(rnd.choice(bases) for _ in range(g)) + sv_aln[p:], ref_aln[:p] + "-" * g + ref_aln[p:]
+        ref_pos = rnd.choice([0, 1000, 123456])
+        sv = types.SimpleNamespace(svlen=svlen if svtype == "INS" else -svlen, svtype=svtype)
+        la = local_asm.LocalAsm.__new__(local_asm.LocalAsm)
+        la.sv = sv
+        region = f"ctg1:{ref_pos}-{ref_pos + 5000}"
+        res = la.solve_ins(region, sv_aln, ref_aln) if svtype == "INS" else la.solve_del(region, sv_aln, ref_aln)
+        out["solve"].append(dict(svtype=svtype, svlen=sv.svlen, ref_pos=ref_pos, sv_aln=sv_aln, ref_aln=ref_aln, want=[res[0], res[1], bool(res[2])]))
+    with open(os.path.join(HERE, "local_asm_vectors.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("local_asm vectors", len(out["solve"]), "accepted", sum(v["want"][2] for v in out["solve"]))
+
+
 if __name__ == "__main__":
+    if sys.argv[1:] == ["lasm"]:
+        make_local_asm_vectors()
+        sys.exit(0)
     if sys.argv[1:] == ["snf"]:
         make_snf()
         sys.exit(0)

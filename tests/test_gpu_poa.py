@@ -1,0 +1,90 @@
+"""Local-assembly POA on the device: the CUDA kernel against the CPU restatement (oracle/poa_oracle.c), job for job,
+byte for byte — more than 200 synthetic QC-failed INS / DEL shaped jobs (read pile-ups and consensus-vs-reference alignments), and the
+LocalAsm driver end to end.  Parity with pyspoa itself is unpinned (absent from this image); tolerance stated in DESIGN.md."""
+import random
+import re
+import types
+
+import pytest
+
+from sniffles_b200 import binding, local_asm
+from test_local_asm import _mut, _edit
+
+pytestmark = pytest.mark.gpu
+
+
+def _jobs(seed, n_jobs):
+    from oracle import poa  # noqa: F401
+    rnd = random.Random(seed)
+    jobs = []
+    for k in range(n_jobs):
+        size = rnd.choice([50, 80, 150, 300, 600])
+        L = rnd.randrange(150, 900)
+        truth = bytes(rnd.choice(b"ACGT") for _ in range(L + size))
+        if k % 3 == 2:          # consensus-vs-reference: planted INS (gap in the reference row) or DEL (gap in the consensus row)
+            cut = rnd.randrange(40, L - 40)
+            with_ev, without = truth, truth[:cut] + truth[cut + size:]
+            a, b = (with_ev, without) if rnd.random() < 0.5 else (without, with_ev)
+            jobs.append(dict(seqs=[_mut(rnd, a, 0.01, 0.01), b], mode=1, scores=local_asm.spoa_scores(size), band=rnd.choice([1 << 28, size + 256])))
+        else:                   # read pile-up; some reads do not carry the event
+            n = rnd.randrange(5, 24)
+            cut = rnd.randrange(40, L - 40)
+            alt = truth[:cut] + truth[cut + size:]
+            reads = [_mut(rnd, truth if rnd.random() < 0.8 else alt, rnd.choice([0.01, 0.03]), rnd.choice([0.01, 0.04])) for _ in range(n)]
+            jobs.append(dict(seqs=reads, mode=0, min_cov=round(n * 0.5), scores=local_asm.DEFAULT_SCORES, band=rnd.choice([1 << 28, 64, size + 256])))
+    return jobs
+
+
+def test_device_poa_equals_the_restatement():
+    from oracle import poa
+    jobs = _jobs(5, 240)
+    ctx = binding.Context(0)
+    try:
+        got = ctx.poa(jobs)
+    finally:
+        ctx.close()
+    assert len(got) == len(jobs) and all(g is not None for g in got)
+    for jb, g in zip(jobs, got):
+        if jb["mode"] == 0:
+            want = poa.consensus(jb["seqs"], jb["min_cov"], jb["scores"], jb["band"])
+        else:
+            want = poa.pair_msa(jb["seqs"][0], jb["seqs"][1], jb["scores"], jb["band"])
+        assert g == want
+
+
+def test_local_asm_driver_end_to_end():
+    """LocalAsm.assembly's flow on synthetic QC-failed calls: windows -> device consensus -> device alignment against the reference window ->
+    solve_ins / solve_del -> the call is rescued with its position (local_asm.py:254-304)."""
+    rnd = random.Random(9)
+    genome = bytes(rnd.choice(b"ACGT") for _ in range(60000)).decode()
+    jobs, truth = [], []
+    for k in range(24):
+        svtype = "INS" if k % 2 == 0 else "DEL"
+        size = rnd.choice([60, 120, 350, 700])
+        pos = 8000 + 2000 * k
+        pad = local_asm.select_padding(size if svtype == "INS" else -size, "sv")
+        ins = "".join(rnd.choice("ACGT") for _ in range(size))
+        sample = genome[:pos] + ins + genome[pos:] if svtype == "INS" else genome[:pos] + genome[pos + size:]
+        call = types.SimpleNamespace(svtype=svtype, svlen=size if svtype == "INS" else -size, pos=pos + rnd.randrange(-3, 4), end=0, contig="ctg1", filter="SUPPORT_MIN",
+                                     qc=False, support=8, rnames=None, info={})
+        call.end = call.pos + 1 if svtype == "INS" else call.pos + size
+        call.set_info = lambda key, val, c=call: c.info.__setitem__(key, val)
+        reads = []
+        for _ in range(9):
+            rs = pos - pad - rnd.randrange(500, 3000)
+            seq = _mut(rnd, sample[rs:rs + 3 * pad + size + 6000].encode(), 0.01, 0.01).decode()
+            reads.append((rs, seq))
+        wins, a, b = local_asm.read_windows(svtype, call.pos, call.end, call.svlen if svtype == "INS" else call.svlen, reads)
+        assert len(wins) >= 5
+        jobs.append(local_asm.AsmJob(call, wins, a, b))
+        truth.append((svtype, pos, size))
+    ctx = binding.Context(0)
+    try:
+        ok = local_asm.assemble(ctx, jobs, lambda contig, start, stop: genome[start - 1:stop])      # fas.fetch(region="c:start-stop"): 1-based inclusive
+    finally:
+        ctx.close()
+    assert sum(ok) >= 20, ok
+    for j, good, (svtype, pos, size) in zip(jobs, ok, truth):
+        if good:
+            assert j.call.filter == "PASS" and j.call.qc and j.call.info.get("LASM") is True
+            assert abs(j.call.pos - pos) <= 25, (svtype, j.call.pos, pos)
