@@ -120,6 +120,20 @@ _OPTIONS = [
     (("--dev-inline-sa-support-max",), dict(type=float, default=0.80)),
     (("--dev-min-close-edge-dist",), dict(type=int, default=500)),
     (("--dev-min-read-close-edge-prop",), dict(type=float, default=0.75)),
+    (("--combine-high-confidence",), dict(type=float, default=0.0)),           # multi-sample arguments, config.py:297-312
+    (("--combine-low-confidence",), dict(type=float, default=0.2)),
+    (("--combine-low-confidence-abs",), dict(type=int, default=2)),
+    (("--combine-null-min-coverage",), dict(type=int, default=5)),
+    (("--combine-match",), dict(type=int, default=250)),
+    (("--combine-match-max",), dict(type=int, default=1000)),
+    (("--combine-separate-intra",), dict(action="store_true", default=False)),
+    (("--combine-output-filtered",), dict(action="store_true", default=False)),
+    (("--combine-pair-relabel",), dict(action="store_true", default=False)),
+    (("--combine-pair-relabel-threshold",), dict(type=int, default=20)),
+    (("--combine-pctseq",), dict(type=float, default=0.7)),
+    (("--combine-support-threshold",), dict(type=int, default=3)),
+    (("--combine-consensus",), dict(action="store_true", default=False)),
+    (("--dev-combine-medians",), dict(action="store_true", default=False)),
     (("--gpus",), dict(type=int, default=1)),          # new: number of B200s to shard contigs over
 ]
 
@@ -178,6 +192,10 @@ class SnifflesConfig(argparse.Namespace):
         if self.genotype_ploidy != 2:
             raise SystemExit("Currently only --genotype-ploidy 2 is supported")
         self.snf_block_size = 10 ** 5
+        self.combine_exhaustive = False                 # config.py:576-580
+        self.combine_relabel_rare = False
+        self.combine_overlap_abs = 2500
+        self.combine_min_size = 100
         self.precise = 25
         self.tandem_repeat_region_pad = 500
         self.id_prefix = "Sniffles2."

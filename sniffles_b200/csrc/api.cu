@@ -449,7 +449,7 @@ static void carve_c(snfb_ctx* ctx, Carver& c) {
     cc.alt_off = c.take<uint32_t>(k.cand + 1); cc.scr_off = c.take<uint32_t>(k.cand + 1); cc.work_big = c.take<uint32_t>(k.cand + 1); cc.work_small = c.take<uint32_t>(k.cand + 1); cc.work_ctr = c.take<uint32_t>(64);
     cc.items_big = c.take<consensus::C::Item>(k.item + 1); cc.items_small = c.take<consensus::C::Item>(k.item + 1); cc.tiles = c.take<uint2>(k.tile + 1);
     cc.alt = c.take<uint8_t>(k.alt + 64); cc.scr = c.take<uint8_t>(k.scr16 * 16 + 64);
-    cc.dbg = getenv("SNFB_DEBUG") ? c.take<unsigned long long>(148 * 8 * consensus::ALIGN_WARPS * 8 + 8) : nullptr;
+    cc.dbg = getenv("SNFB_DEBUG") ? c.take<unsigned long long>(148 * 9 * consensus::ALIGN_WARPS * 8 + 8) : nullptr;
     ctx->seq_req = c.take<consensus::SeqReq>(k.req + 1); ctx->seq_arena = c.take<uint8_t>(k.req16 * 16 + 64);
 }
 static int ensure_arenas(snfb_ctx* ctx) {
@@ -643,7 +643,7 @@ static int enqueue_stage_c(snfb_ctx* ctx) {
     mark(ctx, "consensus");
     consensus::k_prep<<<148 * 8, 128, 0, st>>>(c);
     mark(ctx, "consensus_align");
-    consensus::k_align<<<148 * 8, consensus::ALIGN_WARPS * 32, 0, st>>>(c);
+    consensus::k_align<<<148 * 7, consensus::ALIGN_WARPS * 32, 0, st>>>(c);
     mark(ctx, "consensus_vote");
     consensus::k_vote<<<148 * 16, consensus::VOTE_THREADS, 0, st>>>(c); LAUNCHED(ctx, 3);
     mark(ctx, nullptr);

@@ -11,6 +11,9 @@ namespace consensus {
 constexpr int THREADS = 128;
 constexpr int TAB = 2048;                  // > 4 x the at most ~500 strided k-mers of the best read
 constexpr uint8_t DASH = 0xff;
+// strided k-mer hits of one read are bounded by (L + 6) / skip + 1 (skip = 3 + L / 500): < 512 for every L, < 384 for L <= HEAVY_L.
+// The light items run with the smaller per-warp hit arrays, i.e. with more warps per SM (they are latency bound).
+constexpr int MAXHIT = 512, MAXHIT_LIGHT = 384; constexpr uint32_t HEAVY_L = 3000;
 
 struct C {
     const snfb_cand* cand; snfb_cand* cand_rw; const snfb_lead* cand_leads;
@@ -40,13 +43,13 @@ __global__ void k_plan(C c) {
             for (int k = 0; k < cd->lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ)) continue;
                 // abs(len(seq) - svlen) + abs(ref_start - pos) * 1.5, compared exactly in halves
                 long long a = (long long)l->seq_len - cd->svlen; if (a < 0) a = -a; long long p = (long long)l->ref_start - cd->pos; if (p < 0) p = -p;
-                const long long d = 2 * a + 3 * p; if (nm == 0 || d < bd) { bd = d; bi = k; } ++nm; tot += l->seq_len; }
+                const long long d = 2 * a + 3 * p; if (nm == 0 || d < bd) { bd = d; bi = k; } ++nm; tot += ((long long)l->seq_len + 7) & ~7ll; }
             if (nm > 0) {
                 const uint32_t L = (uint32_t)c.cand_leads[cd->lead_off + bi].seq_len; al = L;
                 const bool cons = (nm - 1 >= c.cfg.consensus_min_reads) && !c.cfg.no_consensus;
-                c.plan_best[i] = (uint32_t)bi; c.plan_nother[i] = cons ? (uint32_t)(nm - 1) : 0u; c.plan_otot[i] = (uint32_t)(tot - L);
-                // scratch: best codes | others' codes | (4-byte aligned) one row of align4(L) per other read | accept flags | anchor table; 16-byte units
-                const unsigned long long bytes = cons ? (unsigned long long)tot + 4 + (unsigned long long)(nm - 1) * ((L + 3u) & ~3u) + (unsigned long long)(nm - 1) * 16 + 64 + 16 + TAB * 8 : (unsigned long long)L + 16;
+                c.plan_best[i] = (uint32_t)bi; c.plan_nother[i] = cons ? (uint32_t)(nm - 1) : 0u; c.plan_otot[i] = (uint32_t)(tot - ((L + 7u) & ~7u));
+                // scratch: best codes | others' codes (every read in a slot of align8(len) bytes) | one row of align4(L) per other read | accept flags | anchor table; 16-byte units
+                const unsigned long long bytes = cons ? (unsigned long long)tot + 8 + (unsigned long long)(nm - 1) * ((L + 3u) & ~3u) + (unsigned long long)(nm - 1) * 16 + 64 + 16 + TAB * 8 : (unsigned long long)L + 24;
                 sl = (uint32_t)((bytes + 15) / 16);
                 c.cand_rw[i].alt_len = (int)L;
                 // work queue: the heavy tail (long insertions with many reads) is scheduled first
@@ -54,12 +57,12 @@ __global__ void k_plan(C c) {
                 if (work > 60000ull) c.work_big[atomicAdd(&c.work_ctr[0], 1u)] = (uint32_t)i; else c.work_small[atomicAdd(&c.work_ctr[1], 1u)] = (uint32_t)i;
                 if (cons) {
                     // one work item per supporting read (heavy rows first) and one per 4096-column tile of the vote
-                    const bool heavy = L > 4000u; C::Item* dst = heavy ? c.items_big : c.items_small;
+                    const bool heavy = L > HEAVY_L; C::Item* dst = heavy ? c.items_big : c.items_small;
                     const uint32_t base = atomicAdd(&c.work_ctr[heavy ? 4 : 5], (uint32_t)(nm - 1));
                     uint32_t row = 0, ro = 0;
                     for (int k = 0; k < cd->lead_n; ++k) { const snfb_lead* l = &c.cand_leads[cd->lead_off + k]; if (!(l->flags & SNFB_LF_HAS_SEQ) || k == bi) continue;
                         if ((unsigned long long)base + row < c.item_cap) { C::Item it; it.cand = (uint32_t)i; it.k = (uint32_t)k; it.row = row; it.rd_off = ro; dst[base + row] = it; }
-                        ++row; ro += (uint32_t)l->seq_len; }
+                        ++row; ro += ((uint32_t)l->seq_len + 7u) & ~7u; }
                     const uint32_t nt = (L + 4095u) / 4096u; const uint32_t tb = atomicAdd(&c.work_ctr[8], nt);
                     for (uint32_t t = 0; t < nt; ++t) if ((unsigned long long)tb + t < c.tile_cap) c.tiles[tb + t] = make_uint2((uint32_t)i, t);
                 }
@@ -77,35 +80,55 @@ __global__ void k_plan_finish(C c) {
 }
 
 // unpack `len` bases starting at nibble `off` of sq into dst (one code per byte); `tid`/`nthr` = cooperating threads.
-// Each thread takes 8 consecutive bases per step and four steps are kept in flight so that the 4-bit arena is
-// streamed from HBM with enough loads outstanding.
+// A thread takes 8 consecutive bases per step: two aligned words of the 4-bit arena (the second only when the bases reach
+// into it), nibbles swapped into little-endian order, one funnel shift to the first base, two spreads, one 8-byte store.
+__device__ __forceinline__ uint32_t nib_swap(uint32_t w) { return ((w & 0x0f0f0f0fu) << 4) | ((w >> 4) & 0x0f0f0f0fu); }
+__device__ __forceinline__ uint32_t spread4(uint32_t x) { const uint32_t t = (x | (x << 8)) & 0x00ff00ffu; return (t | (t << 4)) & 0x0f0f0f0fu; }
+__device__ __forceinline__ uint2 unpack8(const uint8_t* __restrict__ sq, long long q, int n) {
+    const uintptr_t A = (uintptr_t)(sq + (q >> 1));
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(A & ~(uintptr_t)3);
+    const int qn = (int)((A & 3) << 1) | (int)(q & 1);
+    const uint32_t lo = nib_swap(__ldg(w)), hi = qn + n > 8 ? nib_swap(__ldg(w + 1)) : 0u;
+    const uint32_t x = __funnelshift_r(lo, hi, 4 * qn);
+    return make_uint2(spread4(x & 0xffffu), spread4(x >> 16));
+}
 __device__ __forceinline__ void unpack_span(const uint8_t* __restrict__ sq, long long off, int len, uint8_t* __restrict__ dst, int tid, int nthr) {
-    const int stride = nthr * 8;
-    for (int j0 = tid * 8; j0 < len; j0 += 4 * stride) {
-        uint8_t v[4][5];
+    const int full = ((uintptr_t)dst & 7) == 0 ? (len & ~7) : 0;          // whole 8-base groups go out as aligned 8-byte stores, eight loads in flight
+    int jb = tid * 8;
+    for (; jb + 7 * nthr * 8 < full; jb += 8 * nthr * 8) {
+        uint2 v[8];
         #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int jb = j0 + u * stride; const long long q = off + jb; const uint8_t* p = sq + (q >> 1);
-            #pragma unroll
-            for (int t = 0; t < 5; ++t) v[u][t] = (jb + 2 * t - (int)(q & 1) < len + 1 && jb < len) ? __ldg(p + t) : (uint8_t)0; }
+        for (int u = 0; u < 8; ++u) v[u] = unpack8(sq, off + jb + u * nthr * 8, 8);
         #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int jb = j0 + u * stride; const int ph = (int)((off + jb) & 1);
-            #pragma unroll
-            for (int t = 0; t < 8; ++t) { const int nb = t + ph; const uint8_t by = v[u][nb >> 1]; if (jb + t < len) dst[jb + t] = (nb & 1) ? (by & 15) : (by >> 4); } }
+        for (int u = 0; u < 8; ++u) *reinterpret_cast<uint2*>(dst + jb + u * nthr * 8) = v[u];
+    }
+    for (; jb < full; jb += nthr * 8) *reinterpret_cast<uint2*>(dst + jb) = unpack8(sq, off + jb, 8);
+    for (; jb < len; jb += nthr * 8) {
+        const int n = min(8, len - jb); const uint2 v = unpack8(sq, off + jb, n);
+        for (int t = 0; t < n; ++t) dst[jb + t] = (uint8_t)(((t < 4 ? v.x : v.y) >> (8 * (t & 3))) & 15u);
     }
 }
-// unpack the (possibly merged) sequence of candidate lead `cl_index` as 4-bit codes, one byte per base
-__device__ inline void unpack_lead(const C& c, uint32_t cl_index, uint8_t* dst) {
+// unpack the (possibly merged) sequence of candidate lead `cl_index` as 4-bit codes, one byte per base, by `nthr` cooperating threads
+__device__ inline void unpack_lead(const C& c, uint32_t cl_index, uint8_t* dst, int tid, int nthr) {
     const uint32_t plo = c.out_plo[cl_index], pn = c.out_pn[cl_index];
     long long o = 0;
     for (uint32_t p = 0; p < pn; ++p) {
         const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.kleads[slot];
         const uint8_t* sq = c.arena_off ? c.seq + (size_t)c.arena_off[slot] * 16 : c.seq + c.rec[l->rec].seq_off;
-        unpack_span(sq, c.arena_off ? (l->seq_off & 1) : l->seq_off, l->seq_len, dst + o, threadIdx.x, blockDim.x);
+        unpack_span(sq, c.arena_off ? (l->seq_off & 1) : l->seq_off, l->seq_len, dst + o, tid, nthr);
         o += l->seq_len;
     }
 }
 
 __device__ __forceinline__ uint32_t kmer6(const uint8_t* s) { return (uint32_t)s[0] | ((uint32_t)s[1] << 4) | ((uint32_t)s[2] << 8) | ((uint32_t)s[3] << 12) | ((uint32_t)s[4] << 16) | ((uint32_t)s[5] << 20); }
+// the same from an unaligned pointer with aligned 32-bit loads (reads at most 3 bytes past s + 5)
+__device__ __forceinline__ uint32_t kmer6_u(const uint8_t* s) {
+    const uintptr_t A = (uintptr_t)s; const uint32_t* w = reinterpret_cast<const uint32_t*>(A & ~(uintptr_t)3); const uint32_t sh = (uint32_t)(A & 3) * 8;
+    const uint32_t l0 = w[0], l1 = w[1], l2 = sh > 16 ? w[2] : 0u;
+    const uint32_t x0 = __funnelshift_r(l0, l1, sh), x1 = __funnelshift_r(l1, l2, sh);
+    uint32_t t = x0 & 0x0f0f0f0fu; t = (t | (t >> 4)) & 0x00ff00ffu; t = (t | (t >> 8)) & 0xffffu;
+    return t | ((x1 & 15u) << 16) | (((x1 >> 8) & 15u) << 20);
+}
 __device__ __forceinline__ uint32_t kslot(uint32_t key) { return (key * 2654435761u) >> 21; }    // top 11 bits
 
 // seq on demand: the base slices stage C will read, as (source byte offset in the host seq arena, bytes, destination unit)
@@ -132,19 +155,7 @@ __global__ void k_seq_requests(C c, SeqReq* req, unsigned long long req_cap, uin
     }
 }
 
-constexpr int MAXHIT = 512;       // strided k-mer hits of one read are bounded by (L + 6) / skip + 1 < 512 (skip = 3 + L / 500)
 
-// the same with the calling warp only
-__device__ inline void unpack_lead_warp(const C& c, uint32_t cl_index, uint8_t* dst) {
-    const uint32_t plo = c.out_plo[cl_index], pn = c.out_pn[cl_index];
-    long long o = 0;
-    for (uint32_t p = 0; p < pn; ++p) {
-        const uint32_t slot = c.ord[plo + p]; const snfb_lead* l = &c.kleads[slot];
-        const uint8_t* sq = c.arena_off ? c.seq + (size_t)c.arena_off[slot] * 16 : c.seq + c.rec[l->rec].seq_off;
-        unpack_span(sq, c.arena_off ? (l->seq_off & 1) : l->seq_off, l->seq_len, dst + o, lane_id(), 32);
-        o += l->seq_len;
-    }
-}
 
 // ================================================================================================
 // k_prep (block per candidate: unpack the best read, build its anchor table in global
@@ -192,10 +203,117 @@ __device__ __forceinline__ void fill_dash(uint8_t* dst, long n) {
     for (; q < n; ++q) dst[q] = DASH;
 }
 
-// scratch layout of one consensus candidate: best[L] | other reads' codes [otot] | rows[no][Ls] (4-byte aligned, Ls = align4(L)) | accept[no] | ... | table
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p) {
+    const uintptr_t A = (uintptr_t)p; const uint32_t* w = reinterpret_cast<const uint32_t*>(A & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (uint32_t)(A & 3) * 8);
+}
+// match_count with the words of [0, n) dealt round robin to the G lanes of a group; the caller adds the lanes up
+template <int G>
+__device__ __forceinline__ int group_match(const uint8_t* a, const uint8_t* b, long n, int sub) {
+    int mt = 0;
+    #pragma unroll 2
+    for (long q = 4L * sub; q < n; q += 4L * G) {
+        const uint32_t x = load_u32_unaligned(a + q) ^ load_u32_unaligned(b + q);
+        uint32_t eq = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x) & 0x80808080u;
+        if (n - q < 4) eq &= (1u << (8 * (n - q))) - 1u;
+        mt += __popc(eq);
+    }
+    return mt;
+}
+template <int G> __device__ __forceinline__ int group_sum(int v) {
+    #pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+// ---- cooperating groups of k_align: one warp (light items) or the whole block (heavy items).  `tid` order = element order.
+struct WarpGrp {
+    static constexpr int NTHR = 32; int tid;
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    // exclusive prefix sum over the group in tid order; tot = group total
+    __device__ __forceinline__ int excl(int v, int& tot) const {
+        int inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (tid >= o) inc += t; }
+        tot = __shfl_sync(FULL, inc, 31); return inc - v;
+    }
+    // max over the threads before this one (-1 when none); tot = group max
+    __device__ __forceinline__ int exclmax(int v, int& tot) const {
+        int inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (tid >= o) inc = max(inc, t); }
+        tot = __shfl_sync(FULL, inc, 31); int e = __shfl_up_sync(FULL, inc, 1); if (tid == 0) e = -1; return e;
+    }
+    __device__ __forceinline__ long sum(long v) const { return (long)__reduce_add_sync(FULL, (unsigned)v); }
+};
+template <int WARPS>
+struct BlockGrp {
+    static constexpr int NTHR = WARPS * 32; int tid; int* red;          // red: 2 * WARPS ints of shared memory
+    __device__ __forceinline__ void sync() const { __syncthreads(); }
+    __device__ __forceinline__ int excl(int v, int& tot) const {
+        const int lane = tid & 31, w = tid >> 5; int inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) red[w] = inc;
+        __syncthreads();
+        int base = 0, all = 0;
+        #pragma unroll
+        for (int k = 0; k < WARPS; ++k) { const int t = red[k]; if (k < w) base += t; all += t; }
+        __syncthreads();
+        tot = all; return base + inc - v;
+    }
+    __device__ __forceinline__ int exclmax(int v, int& tot) const {
+        const int lane = tid & 31, w = tid >> 5; int inc = v;
+        #pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc = max(inc, t); }
+        int e = __shfl_up_sync(FULL, inc, 1); if (lane == 0) e = -1;
+        if (lane == 31) red[w] = inc;
+        __syncthreads();
+        int all = -1;
+        #pragma unroll
+        for (int k = 0; k < WARPS; ++k) { const int t = red[k]; if (k < w) e = max(e, t); all = max(all, t); }
+        __syncthreads();
+        tot = all; return e;
+    }
+    __device__ __forceinline__ long sum(long v) const {
+        const int lane = tid & 31, w = tid >> 5; const int sv = (int)__reduce_add_sync(FULL, (unsigned)v);
+        if (lane == 0) red[w] = sv;
+        __syncthreads();
+        int all = 0;
+        #pragma unroll
+        for (int k = 0; k < WARPS; ++k) all += red[k];
+        __syncthreads();
+        return (long)all;
+    }
+};
+
+// (3a) of k_align with G lanes per segment (1: short segments, a lane walks its own; 8: long segments, coalesced words); `tid` of
+// `nthr` cooperating threads (whole warps)
+template <int G>
+__device__ __forceinline__ long segments_pass(const int* hi, const int* hj, int* hcl, int na, long c0, long j0, long L, const uint8_t* rd, const uint8_t* best, int tid, int nthr) {
+    const int PER = nthr / G; const int grp = tid / G, sub = tid % G; long span = 0;
+    for (int mb = 1; mb < na; mb += PER) {
+        const int m = mb + grp; const bool v = m < na;
+        long li = 0, lj = 0, i = 0, j = 0; if (v) { li = hi[m - 1]; lj = hj[m - 1]; i = hi[m]; j = hj[m]; }
+        long cs = c0 + lj - j0; if (cs > L) cs = L;
+        const long d = j - lj; long fwd_j = d; if (cs + fwd_j > L) fwd_j = L - cs;
+        const bool el = v && i - li == fwd_j && fwd_j > 0;
+        long nc = 0; if (el) { nc = L - 1 - li; if (nc > d) nc = d; if (nc < 0) nc = 0; }      // positions past the end of the best read never match
+        const int mt = group_sum<G>(group_match<G>(rd + lj + 1, best + li + 1, nc, sub));
+        // column identity of the copied bases.  Without drift (cs == li, nothing clamped) it is the same sum shifted by one
+        // position, and both end positions are anchor k-mer bases that match by construction: reuse mt
+        int st = -1; bool second = false;
+        if (el) { if (sub == 0) span += d; if (__ddiv_rn((double)mt, (double)d) >= 0.5) { if (cs == li && fwd_j == d && nc == d) st = mt; else second = true; } }
+        const int m2 = group_sum<G>(group_match<G>(rd + lj, best + cs, second ? fwd_j : 0, sub));
+        if (second) st = m2;
+        if (v && sub == 0) hcl[m] = st;
+    }
+    return span;
+}
+
+// scratch layout of one consensus candidate: best[align8(L)] | other reads' codes [otot] | rows[no][Ls] (Ls = align4(L)) | accept[no] | ... | table
 struct Layout { uint8_t* best; uint8_t* oth; uint8_t* rows; uint8_t* acc; uint32_t Ls; };
 __device__ __forceinline__ Layout cand_layout(const C& c, uint32_t ci, uint32_t L, uint32_t no) {
-    Layout y; y.best = c.scr + (size_t)c.scr_off[ci] * 16; y.oth = y.best + L;
+    Layout y; y.best = c.scr + (size_t)c.scr_off[ci] * 16; y.oth = y.best + ((L + 7u) & ~7u);
     y.rows = reinterpret_cast<uint8_t*>(((uintptr_t)(y.oth + c.plan_otot[ci]) + 3) & ~(uintptr_t)3); y.Ls = (L + 3u) & ~3u; y.acc = y.rows + (size_t)no * y.Ls;
     return y;
 }
@@ -219,147 +337,172 @@ __global__ void __launch_bounds__(128) k_prep(C c) {
         if ((unsigned long long)c.alt_off[ci] + L > c.alt_cap || (unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) { if (threadIdx.x == 0) atomicAdd(&c.ctr->scratch_overflow, 1ULL); continue; }
         const snfb_cand cd = c.cand[ci];
         uint32_t* tk; int* tp; uint8_t* best = cand_table(c, ci, &tk, &tp);
-        unpack_lead(c, cd.lead_off + c.plan_best[ci], best);
+        unpack_lead(c, cd.lead_off + c.plan_best[ci], best, threadIdx.x, blockDim.x);
         const uint32_t no = c.plan_nother[ci];
         if (no == 0 || L == 0) { __syncthreads(); uint8_t* out = c.alt + c.alt_off[ci]; for (uint32_t h = threadIdx.x; h < L; h += blockDim.x) out[h] = (uint8_t)CODE[best[h]]; continue; }
         for (int i = threadIdx.x; i < TAB; i += blockDim.x) { tk[i] = 0xffffffffu; tp[i] = -1; }
         __syncthreads();
         const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
         for (long i = (long)threadIdx.x * skip; i < (long)L - 6; i += (long)blockDim.x * skip) {
-            const uint32_t key = kmer6(best + i); uint32_t s = kslot(key);
+            const uint32_t key = kmer6_u(best + i); uint32_t s = kslot(key);
             for (;;) { const uint32_t old = atomicCAS(&tk[s], 0xffffffffu, key); if (old == 0xffffffffu || old == key) break; s = (s + 1) & (TAB - 1); }
             if (atomicCAS(&tp[s], -1, (int)i) != -1) tp[s] = -2;
         }
     }
 }
 
-constexpr int ALIGN_WARPS = 4;
-__global__ void __launch_bounds__(ALIGN_WARPS * 32, 5) k_align(C c) {
-    __shared__ int h_i[ALIGN_WARPS][MAXHIT], h_j[ALIGN_WARPS][MAXHIT], h_cl[ALIGN_WARPS][MAXHIT], h_a[ALIGN_WARPS][MAXHIT], h_b[ALIGN_WARPS][MAXHIT];
-    const int lane = lane_id(), warp = threadIdx.x >> 5;
-    int* hi = h_i[warp]; int* hj = h_j[warp]; int* hcl = h_cl[warp]; int* run_st = h_a[warp];   /* per-run identity sum */ int* run_len = h_b[warp];
-    const int klen = 6;
-    unsigned long long d_busy = 0, d_items = 0, d_max = 0, d_L = 0, d_Lo = 0, d_cL = 0, d_cLo = 0; long long d_t0 = 0; const long long d_start = clock64();
-    unsigned long long d_ph[5] = { 0, 0, 0, 0, 0 }; long long d_pt = 0;
+// one (candidate, supporting read) item by the cooperating group g; hi / hj / hcl / run_st / run_len hold `cap` ints each
+template <typename G>
+__device__ __forceinline__ void align_item(const C& c, const C::Item it, const G g, int* hi, int* hj, int* hcl, int* run_st, int* run_len, int cap, unsigned long long* d_ph) {
+    const int tid = g.tid; constexpr int NT = G::NTHR; const int klen = 6;
+    long long d_pt = c.dbg ? clock64() : 0;
     #define PHASE(k) if (c.dbg) { const long long n_ = clock64(); d_ph[k] += (unsigned long long)(n_ - d_pt); d_pt = n_; }
-    for (;;) {
-        if (c.dbg && d_t0) { const unsigned long long dt = (unsigned long long)(clock64() - d_t0); d_busy += dt; if (dt > d_max) { d_max = dt; d_L = d_cL; d_Lo = d_cLo; } d_t0 = 0; }
-        uint32_t q = 0; if (lane == 0) q = atomicAdd(&c.work_ctr[6], 1u);
-        q = __shfl_sync(FULL, q, 0);
-        const uint32_t nb = (uint32_t)min((unsigned long long)c.work_ctr[4], c.item_cap), ns = (uint32_t)min((unsigned long long)c.work_ctr[5], c.item_cap);
-        if (q >= nb + ns) break;
-        const C::Item it = q < nb ? c.items_big[q] : c.items_small[q - nb];
-        const uint32_t ci = it.cand; const uint32_t L = c.alt_len[ci];
-        if (c.dbg) { d_t0 = clock64(); d_pt = d_t0; ++d_items; d_cL = L; }
-        if ((unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) continue;
-        const snfb_cand* cd = &c.cand[ci];
-        uint32_t* t_key; int* t_pos; cand_table(c, ci, &t_key, &t_pos);
-        const uint32_t no = c.plan_nother[ci];
-        const Layout y = cand_layout(c, ci, L, no);
-        uint8_t* best = y.best; uint8_t* acc = y.acc;
-        const snfb_lead* l = &c.cand_leads[cd->lead_off + it.k];
-        const long Lo = l->seq_len; uint8_t* rd = y.oth + it.rd_off; uint8_t* row = y.rows + (size_t)it.row * y.Ls;
-        d_cLo = (unsigned long long)Lo;
-        const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
-        unpack_lead_warp(c, cd->lead_off + it.k, rd);
-        __syncwarp();
-        PHASE(0)
-        // (1) anchor hits in j order (table lives in global scratch, L2 resident)
-        int nh = 0;
-        const long nk = Lo - klen > 0 ? (Lo - klen + skip - 1) / skip : 0;
-        for (long kb = 0; kb < nk; kb += 32) {
-            const long kk = kb + lane; const long j = kk * skip; int ai = -1;
-            if (kk < nk) { const uint32_t key = kmer6(rd + j); uint32_t s = kslot(key);
-                for (;;) { const uint32_t tk = t_key[s]; if (tk == 0xffffffffu) break; if (tk == key) { ai = t_pos[s]; break; } s = (s + 1) & (TAB - 1); }
-                if (ai >= 0) { long d = ai - j; if (d < 0) d = -d; if (d > klen) ai = -1; } }
-            const unsigned hm = __ballot_sync(FULL, ai >= 0);
-            if (ai >= 0) { const int p = nh + __popc(hm & lanemask_lt()); if (p < MAXHIT) { hi[p] = ai; hj[p] = (int)j; } }
-            nh += __popc(hm);
+    const uint32_t ci = it.cand; const uint32_t L = c.alt_len[ci];
+    if ((unsigned long long)c.scr_off[ci] + c.scr_len[ci] > c.scr_cap16) return;
+    const snfb_cand* cd = &c.cand[ci];
+    uint32_t* t_key; int* t_pos; cand_table(c, ci, &t_key, &t_pos);
+    const uint32_t no = c.plan_nother[ci];
+    const Layout y = cand_layout(c, ci, L, no);
+    uint8_t* best = y.best; uint8_t* acc = y.acc;
+    const snfb_lead* l = &c.cand_leads[cd->lead_off + it.k];
+    const long Lo = l->seq_len; uint8_t* rd = y.oth + it.rd_off; uint8_t* row = y.rows + (size_t)it.row * y.Ls;
+    const long skip = c.cfg.consensus_kmer_skip_base + (long)__dmul_rn((double)L, c.cfg.consensus_kmer_skip_seqlen_mult);
+    unpack_lead(c, cd->lead_off + it.k, rd, tid, NT);
+    g.sync();
+    PHASE(0)
+    // (1) anchor hits in j order (table lives in global scratch, L2 resident); four k-mers per thread in flight
+    int nh = 0;
+    const long nk = Lo - klen > 0 ? (Lo - klen + skip - 1) / skip : 0;
+    for (long kb = 0; kb < nk; kb += 4 * NT) {
+        uint32_t key[4], sl[4], tk[4]; int ai[4];
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) { const long kk = kb + u * NT + tid; key[u] = kk < nk ? kmer6_u(rd + kk * skip) : 0u; sl[u] = kslot(key[u]); }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) tk[u] = kb + u * NT + tid < nk ? t_key[sl[u]] : 0xffffffffu;
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) while (tk[u] != 0xffffffffu && tk[u] != key[u]) { sl[u] = (sl[u] + 1) & (TAB - 1); tk[u] = t_key[sl[u]]; }
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) ai[u] = tk[u] != 0xffffffffu ? t_pos[sl[u]] : -1;
+        #pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (kb + (long)u * NT >= nk) break;
+            const long j = (kb + u * NT + tid) * skip;
+            if (ai[u] >= 0) { long d = ai[u] - j; if (d < 0) d = -d; if (d > klen) ai[u] = -1; }
+            int tot; const int off = g.excl(ai[u] >= 0 ? 1 : 0, tot);
+            if (ai[u] >= 0) { const int p = nh + off; if (p < cap) { hi[p] = ai[u]; hj[p] = (int)j; } }
+            nh += tot;
         }
-        if (nh > MAXHIT) nh = MAXHIT;
-        __syncwarp();
-        PHASE(1)
-        // (2) anchor automaton (consensus.py:306-338) in closed form: a hit is accepted iff its i exceeds every earlier hit's i
-        //     (the accepted hits are the left-to-right maxima), and len(conseq) before accepted hit m is
-        //     min(L, c0 + j[m-1] - j[0]) because every step appends min(j step, room left).  Compacted in place.
-        int na = 0, pm = -1;
-        for (int hb = 0; hb < nh; hb += 32) {
-            const int h = hb + lane; const int vi = h < nh ? hi[h] : -1, vj = h < nh ? hj[h] : 0;
-            int inc = vi;
-            #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc = max(inc, t); }
-            int exc = __shfl_up_sync(FULL, inc, 1); if (lane == 0) exc = -1; exc = max(exc, pm);
-            const bool accp = h < nh && vi > exc;
-            const unsigned am = __ballot_sync(FULL, accp);
-            __syncwarp();
-            if (accp) { const int p = na + __popc(am & lanemask_lt()); hi[p] = vi; hj[p] = vj; }
-            na += __popc(am); pm = max(pm, __shfl_sync(FULL, inc, 31));
-            __syncwarp();
+    }
+    if (nh > cap) nh = cap;
+    g.sync();
+    PHASE(1)
+    // (2) anchor automaton (consensus.py:306-338) in closed form: a hit is accepted iff its i exceeds every earlier hit's i
+    //     (the accepted hits are the left-to-right maxima), and len(conseq) before accepted hit m is
+    //     min(L, c0 + j[m-1] - j[0]) because every step appends min(j step, room left).  Compacted in place.
+    int na = 0, pm = -1;
+    for (int hb = 0; hb < nh; hb += NT) {
+        const int h = hb + tid; const int vi = h < nh ? hi[h] : -1, vj = h < nh ? hj[h] : 0;
+        int tmax; const int exc = max(g.exclmax(vi, tmax), pm);
+        const bool accp = h < nh && vi > exc;
+        int tot; const int off = g.excl(accp ? 1 : 0, tot);
+        g.sync();
+        if (accp) { hi[na + off] = vi; hj[na + off] = vj; }
+        na += tot; pm = max(pm, tmax);
+        g.sync();
+    }
+    const long j0 = na ? hj[0] : 0, c0 = (na && j0 > 0) ? hi[0] : 0;
+    // (3a) agreement with the best read along the diagonal decides copy / dash; a copied segment also gets its column identity
+    //      (the bases it shares with the best read at the columns it lands on)
+    long span = skip > 12 ? segments_pass<8>(hi, hj, hcl, na, c0, j0, (long)L, rd, best, tid, NT) : segments_pass<1>(hi, hj, hcl, na, c0, j0, (long)L, rd, best, tid, NT);
+    span = g.sum(span);
+    g.sync();
+    PHASE(2)
+    // (3b) dash-free runs (= chains of copied segments) survive only with identity > 0.5 and more than 5 matches
+    //      (consensus.py:343-360); decided on the segment list before anything is written.  A non-empty dashed segment
+    //      ends a run; run ids are prefix counts of those, the per-run sums are accumulated in shared memory.
+    {
+        int* hr = hi;                                   // the anchor i positions are no longer needed
+        for (int m = tid; m < na; m += NT) { run_st[m] = 0; run_len[m] = 0; }
+        g.sync();
+        int run_base = 0;
+        for (int mb = 1; mb < na; mb += NT) {
+            const int m = mb + tid; int st = -1; long len = 0;
+            if (m < na) { const long lj = hj[m - 1]; long cs = c0 + lj - j0; if (cs > (long)L) cs = (long)L; len = hj[m] - lj; if (cs + len > (long)L) len = (long)L - cs; st = hcl[m]; }
+            int tot; const int rid = run_base + g.excl((m < na && st < 0 && len > 0) ? 1 : 0, tot);
+            g.sync();
+            if (m < na) { hr[m] = rid; if (st >= 0) { atomicAdd(&run_st[rid], st); atomicAdd(&run_len[rid], (int)len); } }
+            run_base += tot;
         }
-        const long j0 = na ? hj[0] : 0, c0 = (na && j0 > 0) ? hi[0] : 0;
-        // (3a) lane per segment: agreement with the best read along the diagonal decides copy / dash; a copied segment also
-        //      gets its column identity (the bases it shares with the best read at the columns it lands on)
-        long span = 0;
-        for (int m = 1 + lane; m < na; m += 32) {
-            const long li = hi[m - 1], lj = hj[m - 1], i = hi[m], j = hj[m];
-            long cs = c0 + lj - j0; if (cs > (long)L) cs = (long)L;
-            const long d = j - lj; long fwd_j = d; if (cs + fwd_j > (long)L) fwd_j = (long)L - cs;
-            int st = -1;
-            if (i - li == fwd_j && fwd_j > 0) {
-                span += d;
-                long nc = (long)L - 1 - li; if (nc > d) nc = d;                       // positions past the end of the best read never match
-                const int mt = nc > 0 ? match_count(rd + lj + 1, best + li + 1, nc) : 0;
-                // column identity of the copied bases.  Without drift (cs == li, nothing clamped) it is the same sum shifted by one
-                // position, and both end positions are anchor k-mer bases that match by construction: reuse mt
-                if (__ddiv_rn((double)mt, (double)d) >= 0.5) st = (cs == li && fwd_j == d && nc == d) ? mt : match_count(rd + lj, best + cs, fwd_j);
+        g.sync();
+        for (int m = 1 + tid; m < na; m += NT) {
+            if (hcl[m] < 0) continue;
+            const int r = hr[m], ident = run_st[r];
+            if (!(__ddiv_rn((double)ident, (double)run_len[r]) > 0.5 && ident > 5)) hcl[m] = -1;
+        }
+        g.sync();
+    }
+    PHASE(3)
+    // (3c) the row: every copied segment lands at row[cs + t] = rd[lj + t] with cs - lj = c0 - j0 for all of them, so the row is
+    //      one shifted copy of the read between the first and the last anchor (coalesced words), dashes outside, and the
+    //      rejected segments dashed afterwards
+    {
+        long cl = 0; if (na) { cl = c0 + hj[na - 1] - j0; if (cl > (long)L) cl = (long)L; }
+        const uint8_t* src0 = rd + (j0 - c0);
+        #pragma unroll 4
+        for (long X = 4L * tid; X < (long)L; X += 4L * NT) {
+            uint32_t v = 0xffffffffu;
+            if (X + 4 > c0 && X < cl) {
+                v = load_u32_unaligned(src0 + X);
+                if (X < c0) v |= (1u << (8 * (c0 - X))) - 1u;                         // bytes before c0
+                if (X + 4 > cl) v |= ~((1u << (8 * (cl - X))) - 1u);                    // bytes from cl on
             }
-            hcl[m] = st;
+            *reinterpret_cast<uint32_t*>(row + X) = v;
         }
-        span = (long)__reduce_add_sync(FULL, (unsigned)span);
-        __syncwarp();
-        PHASE(2)
-        // (3b) dash-free runs (= chains of copied segments) survive only with identity > 0.5 and more than 5 matches
-        //      (consensus.py:343-360); decided on the segment list before anything is written.  A non-empty dashed segment
-        //      ends a run; run ids are prefix counts of those, the per-run sums are accumulated in shared memory.
-        {
-            int* hr = hi;                                   // the anchor i positions are no longer needed
-            for (int m = lane; m < na; m += 32) { run_st[m] = 0; run_len[m] = 0; }
-            __syncwarp();
-            int run_base = 0;
-            for (int mb = 1; mb < na; mb += 32) {
-                const int m = mb + lane; int st = -1; long len = 0;
-                if (m < na) { const long lj = hj[m - 1]; long cs = c0 + lj - j0; if (cs > (long)L) cs = (long)L; len = hj[m] - lj; if (cs + len > (long)L) len = (long)L - cs; st = hcl[m]; }
-                const unsigned bm = __ballot_sync(FULL, m < na && st < 0 && len > 0);
-                const int rid = run_base + __popc(bm & lanemask_lt());
-                __syncwarp();
-                if (m < na) { hr[m] = rid; if (st >= 0) { atomicAdd(&run_st[rid], st); atomicAdd(&run_len[rid], (int)len); } }
-                run_base += __popc(bm);
-            }
-            __syncwarp();
-            for (int m = 1 + lane; m < na; m += 32) {
-                if (hcl[m] < 0) continue;
-                const int r = hr[m], ident = run_st[r];
-                if (!(__ddiv_rn((double)ident, (double)run_len[r]) > 0.5 && ident > 5)) hcl[m] = -1;
-            }
-            __syncwarp();
-        }
-        PHASE(3)
-        // (3c) write the row once
-        for (long q2 = lane; q2 < c0; q2 += 32) row[q2] = DASH;
-        for (int m = 1 + lane; m < na; m += 32) {
+        g.sync();
+        for (int m = 1 + tid; m < na; m += NT) {
+            if (hcl[m] >= 0) continue;
             const long lj = hj[m - 1]; long cs = c0 + lj - j0; if (cs > (long)L) cs = (long)L;
             long len = hj[m] - lj; if (cs + len > (long)L) len = (long)L - cs;
-            if (len > 0) { if (hcl[m] >= 0) copy_bytes(row + cs, rd + lj, len); else fill_dash(row + cs, len); }
+            if (len > 0) fill_dash(row + cs, len);
         }
-        { long cl = 0; if (na) { cl = c0 + hj[na - 1] - j0; if (cl > (long)L) cl = (long)L; }
-          for (long q2 = cl + lane; q2 < (long)L; q2 += 32) row[q2] = DASH; }
-        if (lane == 0) acc[it.row] = __ddiv_rn((double)span, (double)L) > 0.2;
-        __syncwarp();
-        PHASE(4)
+    }
+    if (tid == 0) acc[it.row] = __ddiv_rn((double)span, (double)L) > 0.2;
+    g.sync();
+    PHASE(4)
+    #undef PHASE
+}
+
+// Heavy items (long insertions) first, the whole block on one item (the longest insertion's reads are the tail of the step);
+// then the light items, one per warp.  Per-warp hit arrays of MAXHIT_LIGHT entries; a block item uses all of them as one array.
+constexpr int ALIGN_WARPS = 4;
+__global__ void __launch_bounds__(ALIGN_WARPS * 32, 7) k_align(C c) {
+    __shared__ int sm[5][ALIGN_WARPS * MAXHIT_LIGHT]; __shared__ int s_red[2 * ALIGN_WARPS]; __shared__ uint32_t s_q;
+    static_assert(ALIGN_WARPS * MAXHIT_LIGHT >= MAXHIT, "a block item needs MAXHIT entries");
+    const int lane = lane_id(), warp = threadIdx.x >> 5;
+    unsigned long long d_busy = 0, d_items = 0, d_ph[5] = { 0, 0, 0, 0, 0 }; const long long d_start = c.dbg ? clock64() : 0;
+    const uint32_t nb = (uint32_t)min((unsigned long long)c.work_ctr[4], c.item_cap), ns = (uint32_t)min((unsigned long long)c.work_ctr[5], c.item_cap);
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_q = atomicAdd(&c.work_ctr[6], 1u);
+        __syncthreads();
+        const uint32_t q = s_q; if (q >= nb) break;
+        const long long t0 = c.dbg ? clock64() : 0;
+        BlockGrp<ALIGN_WARPS> g; g.tid = threadIdx.x; g.red = s_red;
+        align_item(c, c.items_big[q], g, sm[0], sm[1], sm[2], sm[3], sm[4], ALIGN_WARPS * MAXHIT_LIGHT, d_ph);
+        if (c.dbg) { d_busy += (unsigned long long)(clock64() - t0); if (warp == 0) ++d_items; }
+    }
+    __syncthreads();
+    for (;;) {
+        uint32_t q = 0; if (lane == 0) q = atomicAdd(&c.work_ctr[7], 1u);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= ns) break;
+        const long long t0 = c.dbg ? clock64() : 0;
+        WarpGrp g; g.tid = lane; const int o = warp * MAXHIT_LIGHT;
+        align_item(c, c.items_small[q], g, sm[0] + o, sm[1] + o, sm[2] + o, sm[3] + o, sm[4] + o, MAXHIT_LIGHT, d_ph);
+        if (c.dbg) { d_busy += (unsigned long long)(clock64() - t0); ++d_items; }
     }
     if (c.dbg && lane == 0) { unsigned long long* o = c.dbg + (size_t)(blockIdx.x * ALIGN_WARPS + warp) * 8;
         o[0] = d_busy; o[1] = (unsigned long long)(clock64() - d_start); o[2] = d_items; o[3] = d_ph[0]; o[4] = d_ph[1]; o[5] = d_ph[2]; o[6] = d_ph[3]; o[7] = d_ph[4]; }
-    #undef PHASE
 }
 
 // column vote (consensus.py:365-380), one block per (candidate, 4096-column tile); every thread takes four adjacent columns
@@ -397,6 +540,45 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote(C c) {
         uint8_t* out = c.alt + c.alt_off[ci];
         const uint32_t h_end = min(L, (s_tile.y + 1u) * 4096u);
         for (uint32_t h = s_tile.y * 4096u + threadIdx.x * 4u; h < h_end; h += blockDim.x * 4u) {
+            const uint32_t bw = *reinterpret_cast<const uint32_t*>(best + h);
+            // fast path: the four columns of a word are counted byte-parallel.  A, C, G, T are the one-hot codes 1, 2, 4, 8, so bit k
+            // of a byte is that base's vote; dashes (0xff) are cleared first; anything else (ambiguity codes, '=') shows up as a byte
+            // with two bits set or as a column whose votes and dashes do not add up to the rows, and sends the word down the exact path
+            if (nlist == s_nacc && nlist < 255) {
+                uint32_t cA = 0, cC = 0, cG = 0, cT = 0, cD = 0, multi = 0;
+                for (int r0 = 0; r0 < nlist; r0 += 8) {
+                    uint32_t cv[8];
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u) cv[u] = r0 + u < nlist ? *reinterpret_cast<const uint32_t*>(rows + (size_t)s_rows[r0 + u] * Ls + h) : 0xffffffffu;
+                    #pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t hb = cv[u] & 0x80808080u, d1 = hb >> 7, t = cv[u] & ~(hb | (hb - d1));
+                        cD += d1; multi |= ((t | 0x10101010u) - 0x01010101u) & t;
+                        cA += t & 0x01010101u; cC += (t >> 1) & 0x01010101u; cG += (t >> 2) & 0x01010101u; cT += (t >> 3) & 0x01010101u;
+                    }
+                }
+                // padding rows of the last group of eight counted as dashes
+                const uint32_t padded = (uint32_t)((nlist + 7) & ~7);
+                const uint32_t tot = cA + cC + cG + cT + cD;                      // per byte: rows accounted for (<= 255 + 7 would overflow: bounded by padded <= 256 only when nlist <= 248)
+                const bool best_ok = (((bw | 0x10101010u) - 0x01010101u) & bw) == 0 && ((bw - 0x01010101u) & ~bw & 0x80808080u) == 0;
+                if (multi == 0 && best_ok && padded <= 248 && tot == padded * 0x01010101u) {
+                    #pragma unroll
+                    for (int b2 = 0; b2 < 4; ++b2) {
+                        if (h + b2 >= h_end) break;
+                        const uint32_t bc = (bw >> (8 * b2)) & 255u; uint32_t res = bc;
+                        const int nal = (int)padded - (int)((cD >> (8 * b2)) & 255u);
+                        if (!(nal < 2 || __ddiv_rn((double)nal, maxal) < 0.25)) {
+                            int v4[4] = { (int)((cA >> (8 * b2)) & 255u), (int)((cC >> (8 * b2)) & 255u), (int)((cG >> (8 * b2)) & 255u), (int)((cT >> (8 * b2)) & 255u) };
+                            int t0 = -1, t1 = -1, c0 = 0, nd = 0;
+                            #pragma unroll
+                            for (int k = 0; k < 4; ++k) { const int v = v4[k] + ((bc >> k) & 1u); if (!v) continue; ++nd; if (v > t0) { t1 = t0; t0 = v; c0 = 1 << k; } else if (v > t1) t1 = v; }
+                            if (nd > 1 && t0 - t1 >= 3) res = (uint32_t)c0;
+                        }
+                        out[h + b2] = (uint8_t)CODE[res];
+                    }
+                    continue;
+                }
+            }
             unsigned long long cnt[4][4]; int nal[4];
             #pragma unroll
             for (int b2 = 0; b2 < 4; ++b2) { nal[b2] = 0; cnt[b2][0] = cnt[b2][1] = cnt[b2][2] = cnt[b2][3] = 0; }
@@ -415,7 +597,6 @@ __global__ void __launch_bounds__(VOTE_THREADS) k_vote(C c) {
                 #pragma unroll
                 for (int b2 = 0; b2 < 4; ++b2) { const uint32_t cc = (v >> (8 * b2)) & 255u; if (cc != DASH) { vote_add(cnt[b2], cc); ++nal[b2]; } }
             }
-            const uint32_t bw = *reinterpret_cast<const uint32_t*>(best + h);
             #pragma unroll
             for (int b2 = 0; b2 < 4; ++b2) {
                 if (h + b2 >= h_end) break;
