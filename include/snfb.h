@@ -371,6 +371,35 @@ typedef struct snfb_poa_job {
 } snfb_poa_job;
 int         snfb_poa(snfb_ctx* ctx, const snfb_poa_job* jobs, uint32_t n_jobs, const uint8_t* seqs, uint64_t n_seq_bytes, const int32_t* offs, uint64_t n_offs,
                      uint8_t* out, uint64_t out_bytes, int32_t* out_len);
+/* ---- multi-sample combine: the grouping of CombineTask.execute (parallel.py:443-572) -----------------------------------
+ * The host reads the SNF blocks and lays the candidates out the way the reference visits them: a CHAIN is one (task, svtype) — its groups are
+ * carried from chunk to chunk and from block to block (groups_keep, parallel.py:475,563) —, a CHUNK is one call of
+ * cluster.resolve_block_groups (cluster.py:356-390): the candidates of the bins accumulated up to bin_max_candidates, already in the order
+ * sorted(key=support, reverse=True) gives them.  The device runs every chain: nearest-group assignment with the reference's distance and
+ * limits, SVGroup.from_candidate / add_candidate running means (sv.py:265-321), after each chunk the coverage of the samples a group does not
+ * include (max over the chunks it lives through, parallel.py:538-552) and the keep / call split (parallel.py:554-557).
+ * Outputs, per candidate: its group slot; per group slot (slot = chain.cand_off + order of creation): the chunk at whose end it was called
+ * (n_chunk = kept to the end of the chain, -1 = unused slot), its position among the groups called then, the non-included coverages.
+ * group.align_call (edlib edit distance, sv.py:282-292) is not evaluated: as in the reference without edlib, every pair passes. */
+typedef struct snfb_combine_chain { uint32_t cand_off, n_cand, chunk_off, n_chunk, is_bnd, pad; } snfb_combine_chain;
+typedef struct snfb_combine_chunk { int32_t cand_off, n_cand, curr_bin, size, cov_block, pad; } snfb_combine_chunk;   /* cov_block: row of cov[] of the block being read, -1 none */
+typedef struct snfb_combine_in {
+    uint32_t n_chain, n_chunk, n_cand, n_samples;
+    const snfb_combine_chain* chains; const snfb_combine_chunk* chunks;
+    const int32_t* pos; const int32_t* svlen; const uint32_t* sample;        /* per candidate; sample = index into the sample list   */
+    const int32_t* mate_contig; const int32_t* mate_pos;                     /* BND chains only (any consistent contig numbering)     */
+    uint32_t n_cov_block; int32_t bins_per_block, cov_binsize, pad;
+    const int64_t* block_start;                                              /* [n_cov_block]                                         */
+    const int32_t* cov;                                                      /* [n_cov_block][n_samples][bins_per_block]; -1 = the sample has no such block / key */
+    int32_t combine_match, combine_match_max, cluster_merge_bnd, combine_separate_intra, combine_overlap_abs, pad2;
+} snfb_combine_in;
+typedef struct snfb_combine_out {
+    uint32_t* cand_group;     /* [n_cand]                 */
+    int32_t*  emit_chunk;     /* [n_cand] per group slot  */
+    uint32_t* emit_ord;       /* [n_cand] per group slot  */
+    int32_t*  cov_non;        /* [n_cand][n_samples]; -1 where the sample is included (never probed) */
+} snfb_combine_out;
+int         snfb_combine_groups(snfb_ctx* ctx, const snfb_combine_in* in, snfb_combine_out* out);
 /* developer aid: with SNFB_DEBUG set in the environment the consensus alignment kernel records, per warp, busy cycles / elapsed cycles / items /
  * longest item (cycles, consensus length, read length); returns 1 when nothing was recorded */
 int         snfb_debug_dump(snfb_ctx* ctx, uint64_t* out, uint64_t n_words);

@@ -291,3 +291,38 @@ def _final_dict(c):
     return dict(svtype=c.svtype, pos=c.pos, svlen=c.svlen, support=c.support, filter=c.filter, qc=bool(c.qc),
                 alt=c.alt, gt=None if gt is None else [gt[0], gt[1], gt[2], gt[3], gt[4], list(gt[5]) if gt[5] else None],
                 vaf=c.info.get("VAF"), phase=c.info.get("PHASE"), id=c.id)
+
+
+def combine_call_dict(c):
+    """what a combined call is compared on (both sides build it with this function)"""
+    gts = {int(k): [v[0], v[1], v[2], v[3], v[4], list(v[5]) if v[5] else None] + ([v[6]] if len(v) > 6 else []) for k, v in sorted(c.genotypes.items())}
+    return dict(contig=c.contig, svtype=c.svtype, pos=c.pos, end=c.end, svlen=c.svlen, id=c.id, alt=c.alt, qual=c.qual, filter=c.filter,
+                precise=bool(c.precise), support=c.support, fwd=c.fwd, rev=c.rev, nm=c.nm,
+                cov=[c.coverage_upstream, c.coverage_start, c.coverage_center, c.coverage_end, c.coverage_downstream],
+                info={k: c.info[k] for k in sorted(c.info)}, genotypes=gts, n_rnames=None if c.rnames is None else len(c.rnames))
+
+
+def reference_combine(snf_paths, contigs, config_args=()):
+    """The reference's own multi-sample combine over SNF files: the setup of sniffles:372-437, then one CombineTask per contig
+    (sniffles:466-476) executed in this process (parallel.py:443-572).  Returns (config, {contig: [SVCall]}, vcf_lines)."""
+    import_reference()
+    from sniffles import parallel, snf as refsnf
+    config = make_config(*config_args)
+    config.mode = "combine"
+    config.input = list(snf_paths)
+    config.snf_input_info, config.sample_ids_vcf = [], []
+    for k, path in enumerate(snf_paths):
+        f = refsnf.SNFile(config, open(path, "rb"), filename=path)
+        f.read_header()
+        sid = f.header["config"].get("sample_id") or os.path.splitext(os.path.basename(path))[0]
+        config.snf_input_info.append({"internal_id": k, "sample_id": sid, "filename": path})
+        config.sample_ids_vcf.append((k, sid))
+        f.close()
+    out, tid = {}, 0
+    for name, length in contigs:
+        task = parallel.CombineTask(id=tid, contig=name, start=0, end=length - 1, assigned_process_id=None, sv_id=0, config=config, regions=None)
+        res = task.execute()
+        out[name] = list(res.svcalls) if getattr(res, "svcalls", None) else []
+        tid += 1
+    lines = reference_vcf_lines([c for name, _ in contigs for c in out[name]], config, FakeFasta())
+    return config, out, lines

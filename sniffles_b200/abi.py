@@ -129,6 +129,20 @@ class PoaJob(C.Structure):
         ("mode", C.c_uint32), ("out_cap", C.c_uint32), ("out_off", C.c_uint64)]
 
 
+class CombineIn(C.Structure):                                   # snfb_combine_in
+    _fields_ = [("n_chain", C.c_uint32), ("n_chunk", C.c_uint32), ("n_cand", C.c_uint32), ("n_samples", C.c_uint32),
+                ("chains", C.c_void_p), ("chunks", C.c_void_p), ("pos", C.c_void_p), ("svlen", C.c_void_p), ("sample", C.c_void_p),
+                ("mate_contig", C.c_void_p), ("mate_pos", C.c_void_p),
+                ("n_cov_block", C.c_uint32), ("bins_per_block", C.c_int32), ("cov_binsize", C.c_int32), ("pad", C.c_int32),
+                ("block_start", C.c_void_p), ("cov", C.c_void_p),
+                ("combine_match", C.c_int32), ("combine_match_max", C.c_int32), ("cluster_merge_bnd", C.c_int32),
+                ("combine_separate_intra", C.c_int32), ("combine_overlap_abs", C.c_int32), ("pad2", C.c_int32)]
+
+
+class CombineOut(C.Structure):                                  # snfb_combine_out
+    _fields_ = [("cand_group", C.c_void_p), ("emit_chunk", C.c_void_p), ("emit_ord", C.c_void_p), ("cov_non", C.c_void_p)]
+
+
 class GatherView(C.Structure):
     _fields_ = [("n_cand", C.c_uint64), ("cand", C.c_void_p), ("n_alt_bytes", C.c_uint64), ("alt", C.c_void_p),
                 ("n_rnames", C.c_uint64), ("rnames", C.c_void_p), ("rnames_off", C.c_void_p),

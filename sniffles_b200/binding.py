@@ -16,7 +16,7 @@ EXPORTS = ["snfb_version", "snfb_sizeof", "snfb_hash_name", "snfb_ctx_create", "
            "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
            "snfb_last_timings", "snfb_device_candidates", "snfb_device_alt", "snfb_launch_count",
            "snfb_pin_host", "snfb_unpin_host", "snfb_pack_cigar16", "snfb_rerun_count", "snfb_coverage_bins",
-           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates", "snfb_selftest_sqrt_frac", "snfb_debug_dump", "snfb_poa"]
+           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates", "snfb_selftest_sqrt_frac", "snfb_debug_dump", "snfb_poa", "snfb_combine_groups"]
 
 
 def lib():
@@ -300,6 +300,26 @@ class Context:
                 b = out[J[k].out_off + J[k].out_cap:J[k].out_off + J[k].out_cap + L]
                 res.append((dec(a), dec(b)))
         return res
+
+    def combine_groups(self, plan, config):
+        """The grouping of multi-sample combine on the device (snfb_combine_groups; cluster.resolve_block_groups + the chunk loop of
+        CombineTask.execute).  plan: combine.Plan.  Returns (cand_group, emit_chunk, emit_ord, cov_non[n_cand][n_samples])."""
+        from . import combine
+        a = combine.plan_arrays(plan, config)
+        n, S = len(a["pos"]), a["n_samples"]
+        out = (np.zeros(max(n, 1), "<u4"), np.full(max(n, 1), -1, "<i4"), np.zeros(max(n, 1), "<u4"), np.full((max(n, 1), S), -1, "<i4"))
+        if n == 0:
+            return out
+        I, O = abi.CombineIn(), abi.CombineOut()
+        I.n_chain, I.n_chunk, I.n_cand, I.n_samples = len(a["chains"]), len(a["chunks"]), n, S
+        for k in ("chains", "chunks", "pos", "svlen", "sample", "mate_contig", "mate_pos", "block_start", "cov"):
+            setattr(I, k, a[k].ctypes.data)
+        I.n_cov_block, I.bins_per_block, I.cov_binsize = len(a["block_start"]), a["bins_per_block"], a["cov_binsize"]
+        I.combine_match, I.combine_match_max, I.cluster_merge_bnd = int(config.combine_match), int(config.combine_match_max), int(config.cluster_merge_bnd)
+        I.combine_separate_intra, I.combine_overlap_abs = int(bool(config.combine_separate_intra)), int(config.combine_overlap_abs)
+        O.cand_group, O.emit_chunk, O.emit_ord, O.cov_non = (x.ctypes.data for x in out)
+        self._check(self._lib.snfb_combine_groups(self._h, C.byref(I), C.byref(O)), "snfb_combine_groups")
+        return out
 
     def device_alt(self):
         p = C.c_void_p()

@@ -23,6 +23,7 @@
 #include "cluster.cuh"
 #include "consensus.cuh"
 #include "poa.cuh"
+#include "combine.cuh"
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -967,6 +968,63 @@ int snfb_poa(snfb_ctx* ctx, const snfb_poa_job* jobs, uint32_t n_jobs, const uin
     cudaMemcpyAsync(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(out_len, d_len.p, 4 * (size_t)n_jobs, cudaMemcpyDeviceToHost, st);
     const cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return done(fail(ctx, std::string("snfb_poa: ") + cudaGetErrorString(e)));
+    return done(0);
+}
+
+// multi-sample combine: every (task, svtype) chain of the plan by one warp (combine.cuh); host buffers in, host buffers out
+int snfb_combine_groups(snfb_ctx* ctx, const snfb_combine_in* in, snfb_combine_out* out) {
+    if (!ctx || !in || !out) return ctx ? fail(ctx, "snfb_combine_groups: null argument") : 1;
+    if (in->n_cand == 0 || in->n_chain == 0) return 0;
+    if (!in->chains || !in->chunks || !in->pos || !in->svlen || !in->sample || !out->cand_group || !out->emit_chunk || !out->emit_ord || !out->cov_non)
+        return fail(ctx, "snfb_combine_groups: null array");
+    if (in->n_samples == 0 || in->bins_per_block <= 0 || in->cov_binsize <= 0) return fail(ctx, "snfb_combine_groups: bad sample count / coverage geometry");
+    // the plan must tile [0, n_cand) and [0, n_chunk): chains in order, chunks of a chain consecutive
+    { uint64_t c = 0, k = 0;
+      for (uint32_t i = 0; i < in->n_chain; ++i) { const snfb_combine_chain& ch = in->chains[i];
+          if (ch.cand_off != c || ch.chunk_off != k || ch.n_chunk == 0) return fail(ctx, "snfb_combine_groups: chains do not tile the candidates / chunks");
+          uint64_t cc = c;
+          for (uint32_t j = 0; j < ch.n_chunk; ++j) { if (k + j >= in->n_chunk) return fail(ctx, "snfb_combine_groups: chunk index out of range"); const snfb_combine_chunk& ck = in->chunks[k + j];
+              if ((uint64_t)ck.cand_off != cc || ck.n_cand <= 0 || ck.cov_block < -1 || ck.cov_block >= (int64_t)in->n_cov_block) return fail(ctx, "snfb_combine_groups: bad chunk"); cc += ck.n_cand; }
+          if (cc != c + ch.n_cand) return fail(ctx, "snfb_combine_groups: chunk sizes do not add up to the chain");
+          if (ch.is_bnd && (!in->mate_contig || !in->mate_pos)) return fail(ctx, "snfb_combine_groups: BND chain without mate arrays");
+          c += ch.n_cand; k += ch.n_chunk; }
+      if (c != in->n_cand || k != in->n_chunk) return fail(ctx, "snfb_combine_groups: plan does not cover n_cand / n_chunk");
+      for (uint32_t i = 0; i < in->n_cand; ++i) if (in->sample[i] >= in->n_samples) return fail(ctx, "snfb_combine_groups: sample index out of range"); }
+    cudaSetDevice(ctx->device);
+    const size_t n = in->n_cand, S = in->n_samples, W = (S + 31) / 32, ncov = (size_t)in->n_cov_block * S * in->bins_per_block;
+    DevBuf b_in, b_state, b_out;
+    // inputs in one buffer, group state in one, outputs in one
+    Carver ci, cs, co;
+    auto lay = [&](Carver& c, combine::P& P, bool in_, bool st_, bool out_) {
+        if (in_) { P.chains = c.take<snfb_combine_chain>(in->n_chain); P.chunks = c.take<snfb_combine_chunk>(in->n_chunk); P.pos = c.take<int32_t>(n); P.svlen = c.take<int32_t>(n); P.sample = c.take<uint32_t>(n);
+                   P.mate_contig = c.take<int32_t>(n); P.mate_pos = c.take<int32_t>(n); P.block_start = c.take<long long>(in->n_cov_block + 1); P.cov = c.take<int32_t>(ncov + 1); }
+        if (st_) { P.g_pos = c.take<double>(n); P.g_len = c.take<double>(n); P.g_mate = c.take<double>(n); P.g_n = c.take<uint32_t>(n); P.g_mc = c.take<int32_t>(n); P.g_incl = c.take<uint32_t>(n * W); P.act = c.take<uint32_t>(n);
+                   P.next_chain = c.take<unsigned int>(4); }
+        if (out_) { P.cand_group = c.take<uint32_t>(n); P.emit_chunk = c.take<int32_t>(n); P.emit_ord = c.take<uint32_t>(n); P.cov_non = c.take<int32_t>(n * S); }
+    };
+    combine::P P{};
+    lay(ci, P, true, false, false); lay(cs, P, false, true, false); lay(co, P, false, false, true);
+    auto done = [&](int r) { b_in.release(); b_state.release(); b_out.release(); return r; };
+    if (b_in.ensure(ci.off + 256) | b_state.ensure(cs.off + 256) | b_out.ensure(co.off + 256)) return done(fail(ctx, "snfb_combine_groups: out of device memory"));
+    ci = Carver{ b_in.as<uint8_t>(), 0 }; cs = Carver{ b_state.as<uint8_t>(), 0 }; co = Carver{ b_out.as<uint8_t>(), 0 };
+    lay(ci, P, true, false, false); lay(cs, P, false, true, false); lay(co, P, false, false, true);
+    P.n_chain = in->n_chain; P.n_chunk = in->n_chunk; P.n_cand = in->n_cand; P.n_samples = in->n_samples; P.words = (uint32_t)W;
+    P.bins_per_block = in->bins_per_block; P.cov_binsize = in->cov_binsize;
+    P.combine_match = in->combine_match; P.combine_match_max = in->combine_match_max; P.cluster_merge_bnd = in->cluster_merge_bnd; P.separate_intra = in->combine_separate_intra; P.overlap_abs = in->combine_overlap_abs;
+    cudaStream_t st = ctx->st;
+    auto up = [&](const void* dst, const void* src, size_t bytes) { if (bytes && src) cudaMemcpyAsync(const_cast<void*>(dst), src, bytes, cudaMemcpyHostToDevice, st); };
+    up(P.chains, in->chains, sizeof(snfb_combine_chain) * in->n_chain); up(P.chunks, in->chunks, sizeof(snfb_combine_chunk) * in->n_chunk);
+    up(P.pos, in->pos, 4 * n); up(P.svlen, in->svlen, 4 * n); up(P.sample, in->sample, 4 * n); up(P.mate_contig, in->mate_contig, 4 * n); up(P.mate_pos, in->mate_pos, 4 * n);
+    up(P.block_start, in->block_start, 8 * (size_t)in->n_cov_block); up(P.cov, in->cov, 4 * ncov);
+    cudaMemsetAsync(P.next_chain, 0, 16, st);
+    mark(ctx, "combine_groups");
+    const unsigned blocks = (unsigned)std::min<size_t>((in->n_chain + 3) / 4, 148 * 4);
+    combine::k_combine<<<blocks, 128, 0, st>>>(P); LAUNCHED(ctx, 1);
+    mark(ctx, nullptr);
+    cudaMemcpyAsync(out->cand_group, P.cand_group, 4 * n, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(out->emit_chunk, P.emit_chunk, 4 * n, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(out->emit_ord, P.emit_ord, 4 * n, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(out->cov_non, P.cov_non, 4 * n * S, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(fail(ctx, std::string("snfb_combine_groups: ") + cudaGetErrorString(e)));
     return done(0);
 }
 

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(128) k_combine(const P p) {
                 const int cpos = p.pos[c], clen = p.svlen[c]; const uint32_t smp = p.sample[c];
                 const int cmc = ch.is_bnd ? p.mate_contig[c] : 0, cmp = ch.is_bnd ? p.mate_pos[c] : 0;
                 const double alen = (double)(clen < 0 ? -(long long)clen : (long long)clen);
-                double bd = CUDART_INF; uint32_t bi = 0xffffffffu;
+                double bd = __longlong_as_double(0x7ff0000000000000ll); uint32_t bi = 0xffffffffu;
                 for (uint32_t a0 = 0; a0 < n_act; a0 += 32) {
                     const uint32_t a = a0 + lane;
                     if (a < n_act) {

@@ -183,7 +183,7 @@ static inline void read_span(const snfb_synth_params* p, rng_t* r, int c, int64_
  * holds such a site.  Everything else of an unowned contig is never generated. */
 static int read_may_reach_owned(const model_t* m, int c, int64_t idx, int64_t nreads) {
     const snfb_synth_params* p = m->p;
-    rng_t r = { mix64(p->seed ^ mix64(((uint64_t)(uint32_t)c << 40) ^ (uint64_t)idx)) };
+    rng_t r = { mix64(p->seed ^ mix64(p->sample * 0xD1B54A32D192ED03ull) * (p->sample != 0) ^ mix64(((uint64_t)(uint32_t)c << 40) ^ (uint64_t)idx)) };
     int64_t start, Lr; read_span(p, &r, c, idx, nreads, &start, &Lr);
     int64_t s0 = m->site_first[c], s1 = m->site_first[c + 1];
     int64_t lo = s0, hi = s1;
@@ -198,7 +198,7 @@ static int read_may_reach_owned(const model_t* m, int c, int64_t idx, int64_t nr
 
 static void gen_read(const model_t* m, local_t* L, int c, int64_t idx, int64_t nreads, int src) {
     const snfb_synth_params* p = m->p;
-    rng_t r = { mix64(p->seed ^ mix64(((uint64_t)(uint32_t)c << 40) ^ (uint64_t)idx)) };
+    rng_t r = { mix64(p->seed ^ mix64(p->sample * 0xD1B54A32D192ED03ull) * (p->sample != 0) ^ mix64(((uint64_t)(uint32_t)c << 40) ^ (uint64_t)idx)) };
     int64_t clen = p->contig_len[c];
     int64_t start, Lr; read_span(p, &r, c, idx, nreads, &start, &Lr);
     int rev = (int)(rnext(&r) & 1);
@@ -226,6 +226,7 @@ static void gen_read(const model_t* m, local_t* L, int c, int64_t idx, int64_t n
         if (st->pos >= end - 300) break;
         uint64_t h = mix64(seq_seed ^ (uint64_t)si * 0x9E3779B97F4A7C15ull);
         if (!carries(st, read_hap, h)) continue;
+        if (p->site_keep > 0.0 && (double)(mix64(p->seed ^ mix64(p->sample + 0x51ull) ^ (uint64_t)si * 0xA24BAED4963EE407ull) >> 11) * (1.0 / 9007199254740992.0) >= p->site_keep) continue;
         int jit[5] = { 0, 0, 0, (int)(h & 1) ? 1 : -1, (int)(h & 2) ? 2 : -2 };
         int64_t sp = st->pos + jit[(h >> 8) % 5];
         if (sp <= pos + 10 || sp >= end - 10) continue;

@@ -42,6 +42,10 @@ typedef struct snfb_synth_params {
     int32_t  threads;          /* 0 = omp default */
     int32_t  _pad;
     const uint8_t* contig_mask; /* NULL = all; otherwise only contigs with mask[c] != 0 get reads and keep records (rank sharding) */
+    /* population shapes (config 4): samples share `seed` (the planted sites) and differ in `sample` (their reads; 0 = the single-sample stream);
+     * a sample carries each site with probability `site_keep` (0 = every site) */
+    uint64_t sample;
+    double   site_keep;
 } snfb_synth_params;
 
 typedef struct snfb_synth_site {

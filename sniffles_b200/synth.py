@@ -25,7 +25,7 @@ class _Params(C.Structure):
                 ("phased_frac", C.c_double), ("tr_frac", C.c_double), ("ins_noise", C.c_double),
                 ("mosaic", C.c_int32), ("with_seq", C.c_int32), ("ins_only", C.c_int32),
                 ("sv_min", C.c_int32), ("sv_max", C.c_int32), ("threads", C.c_int32), ("_pad", C.c_int32),
-                ("contig_mask", C.POINTER(C.c_uint8))]
+                ("contig_mask", C.POINTER(C.c_uint8)), ("sample", C.c_uint64), ("site_keep", C.c_double)]
 
 
 SITE_DTYPE = np.dtype([("contig", "<i4"), ("pos", "<i4"), ("svtype", "<i4"), ("size", "<i4"),
@@ -125,7 +125,7 @@ class _Owner:
 def generate(seed: int, contig_len, coverage: float, *, len_model=0, len_mean=15000.0, len_sd=0.6 * 1000,
              len_min=1000, len_max=200000, tech="ont", clip_prob=0.10, lowmapq_prob=0.05,
              secondary_prob=0.02, sv_spacing=120000.0, phased_frac=0.5, tr_frac=0.15, ins_noise=0.03,
-             mosaic=False, with_seq=True, ins_only=False, sv_min=50, sv_max=5000, threads=0, contig_mask=None) -> RecordBlock:
+             mosaic=False, with_seq=True, ins_only=False, sv_min=50, sv_max=5000, threads=0, contig_mask=None, sample=0, site_keep=0.0) -> RecordBlock:
     lib = host_lib()
     lens = (C.c_int32 * len(contig_len))(*[int(x) for x in contig_len])
     p = _Params()
@@ -136,6 +136,7 @@ def generate(seed: int, contig_len, coverage: float, *, len_model=0, len_mean=15
     p.sv_spacing, p.phased_frac, p.tr_frac, p.ins_noise = sv_spacing, phased_frac, tr_frac, ins_noise
     p.mosaic, p.with_seq, p.ins_only = int(mosaic), int(with_seq), int(ins_only)
     p.sv_min, p.sv_max, p.threads = int(sv_min), int(sv_max), int(threads)
+    p.sample, p.site_keep = int(sample), float(site_keep)
     mask = None
     if contig_mask is not None:
         mask = (C.c_uint8 * len(contig_len))(*[1 if m else 0 for m in contig_mask])
@@ -157,8 +158,12 @@ def generate(seed: int, contig_len, coverage: float, *, len_model=0, len_mean=15
 
 
 # ---- the BASELINE.json configurations; `scale` shrinks contig lengths ----
-def config_block(index: int, scale: float = 1.0, threads: int = 0, with_seq: bool = True, contig_mask=None) -> RecordBlock:
+def config_block(index: int, scale: float = 1.0, threads: int = 0, with_seq: bool = True, contig_mask=None, sample: int = 1) -> RecordBlock:
     seed = 1000 + index
+    if index == 4:      # one of the 50 samples of the population shape: 30x ONT like config 2, shared sites, 60 % of them per sample
+        return generate(seed, [max(200000, int(x * scale)) for x in GRCH38], 30.0, len_model=1, len_mean=15000.0,
+                        len_sd=600.0, len_min=1000, len_max=200000, tech="ont", threads=threads, with_seq=with_seq, contig_mask=contig_mask,
+                        sample=sample, site_keep=0.6)
     if index == 1:      # 1 Mb contig, ~200 ONT reads of ~100 kb @20x
         return generate(seed, [int(1_000_000 * scale)], 20.0, len_model=0, len_mean=100000.0, len_sd=10000.0,
                         len_min=1000, len_max=200000, tech="ont", sv_spacing=25000.0, threads=threads, with_seq=with_seq)

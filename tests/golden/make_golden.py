@@ -173,7 +173,7 @@ def make_local_asm_vectors():
         region = f"ctg1:{ref_pos}-{ref_pos + 5000}"
         res = la.solve_ins(region, sv_aln, ref_aln) if svtype == "INS" else la.solve_del(region, sv_aln, ref_aln)
         out["solve"].append(dict(svtype=svtype, svlen=sv.svlen, ref_pos=ref_pos, sv_aln=sv_aln, ref_aln=ref_aln, want=[res[0], res[1], bool(res[2])]))
-    with open(os.path.join(HERE, "local_asm_vectors.json"), "w") as f:
+    with open(os.path.join(HERE, "local_asm", "vectors.json"), "w") as f:
         json.dump(out, f, separators=(",", ":"))
     print("local_asm vectors", len(out["solve"]), "accepted", sum(v["want"][2] for v in out["solve"]))
 

@@ -1,4 +1,4 @@
-"""Local assembly.  Host side against vectors the reference's own LocalAsm produced (tests/golden/local_asm_vectors.json:
+"""Local assembly.  Host side against vectors the reference's own LocalAsm produced (tests/golden/local_asm/vectors.json:
 select_padding, the SPOA score classes, solve_ins / solve_del accept + position + sequence decisions).  The partial-order alignment itself
 replaces pyspoa, which is not in this image (parity unpinned): the CPU restatement is sanity-checked here, the CUDA kernel is checked against
 it in the GPU tests."""
@@ -11,7 +11,7 @@ import pytest
 from sniffles_b200 import local_asm
 from test_oracle_golden import GOLDEN, NAMES  # noqa: F401  (NAMES: keeps the fixture glob in one place)
 
-with open(os.path.join(GOLDEN, "local_asm_vectors.json")) as f:
+with open(os.path.join(GOLDEN, "local_asm", "vectors.json")) as f:
     VEC = json.load(f)
 
 
