@@ -380,7 +380,10 @@ int         snfb_poa(snfb_ctx* ctx, const snfb_poa_job* jobs, uint32_t n_jobs, c
  * include (max over the chunks it lives through, parallel.py:538-552) and the keep / call split (parallel.py:554-557).
  * Outputs, per candidate: its group slot; per group slot (slot = chain.cand_off + order of creation): the chunk at whose end it was called
  * (n_chunk = kept to the end of the chain, -1 = unused slot), its position among the groups called then, the non-included coverages.
- * group.align_call (edlib edit distance, sv.py:282-292) is not evaluated: as in the reference without edlib, every pair passes. */
+ * group.align_call (sv.py:282-292): with combine_pctseq != 0 and the ALT strings given, a candidate joins the nearest eligible group only if
+ * (len_mean - editDistance(ALT of the group's first candidate, its ALT)) / len_mean > combine_pctseq — edlib.align's default global edit
+ * distance, computed on the device (bit-vector blocks, one warp per pair).  combine_pctseq = 0 (or alt = NULL) is the reference's behaviour
+ * without edlib / with --combine-pctseq 0: every pair passes. */
 typedef struct snfb_combine_chain { uint32_t cand_off, n_cand, chunk_off, n_chunk, is_bnd, pad; } snfb_combine_chain;
 typedef struct snfb_combine_chunk { int32_t cand_off, n_cand, curr_bin, size, cov_block, pad; } snfb_combine_chunk;   /* cov_block: row of cov[] of the block being read, -1 none */
 typedef struct snfb_combine_in {
@@ -392,6 +395,8 @@ typedef struct snfb_combine_in {
     const int64_t* block_start;                                              /* [n_cov_block]                                         */
     const int32_t* cov;                                                      /* [n_cov_block][n_samples][bins_per_block]; -1 = the sample has no such block / key */
     int32_t combine_match, combine_match_max, cluster_merge_bnd, combine_separate_intra, combine_overlap_abs, pad2;
+    double  combine_pctseq;
+    const uint8_t* alt; const uint64_t* alt_off; const uint32_t* alt_len; uint64_t n_alt_bytes;   /* per candidate ALT bytes: alt[alt_off[i] .. + alt_len[i]) */
 } snfb_combine_in;
 typedef struct snfb_combine_out {
     uint32_t* cand_group;     /* [n_cand]                 */
@@ -406,6 +411,8 @@ int         snfb_debug_dump(snfb_ctx* ctx, uint64_t* out, uint64_t n_words);
 /* self-check of the exact statistics.stdev arithmetic (host build of the routine the kernels use): the correctly rounded sqrt(P / Q) for
  * P = p_hi * 2^64 + p_lo; slow != 0 selects the limb-by-limb restatement of CPython's _float_sqrt_of_frac, 0 the verified fast path */
 double      snfb_selftest_sqrt_frac(uint64_t p_hi, uint64_t p_lo, uint64_t q, int slow);
+/* self-check of the device edit distance behind group.align_call: n_pairs pairs (a_off/a_len, b_off/b_len into bytes[]), distances to out[] */
+int         snfb_selftest_edit_distance(snfb_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* a_off, const uint32_t* a_len, const uint64_t* b_off, const uint32_t* b_len, uint32_t n_pairs, int32_t* out);
 /* BAM CIGAR words -> CIGAR16 (host code, OpenMP; no GPU needed).  rec_out receives copies of rec_in with cigar_off / n_cigar
  * rewritten for the 16-bit arena.  Call with out16 == NULL to get the number of 16-bit words the arena needs (a multiple
  * of 8); returns that number, or UINT64_MAX when a record holds an op the path does not know (B) or out_cap is too small.

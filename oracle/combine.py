@@ -10,6 +10,26 @@ import math
 import numpy as np
 
 
+def levenshtein(a, b):
+    """global edit distance (edlib.align(a, b)['editDistance'] with the defaults), textbook dynamic programme on numpy rows"""
+    if len(a) > len(b):
+        a, b = b, a
+    if len(a) == 0:
+        return len(b)
+    A = np.frombuffer(bytes(a), np.uint8)
+    prev = np.arange(len(a) + 1, dtype=np.int64)
+    idx = np.arange(len(a) + 1, dtype=np.int64)
+    for j, cb in enumerate(bytes(b), 1):
+        sub = prev[:-1] + (A != cb)
+        cur = np.empty_like(prev)
+        cur[0] = j
+        np.minimum(sub, prev[1:] + 1, out=cur[1:])
+        # the insertion recurrence cur[i] = min(cur[i], cur[i-1] + 1) is a running minimum of (cur[i] - i)
+        cur = np.minimum.accumulate(cur - idx) + idx
+        prev = cur
+    return int(prev[-1])
+
+
 def combine_groups(arrays, config):
     a = arrays
     n, S = len(a["pos"]), a["n_samples"]
@@ -19,6 +39,8 @@ def combine_groups(arrays, config):
     cov_non = np.full((max(n, 1), S), -1, "<i4")
     n_chunk = len(a["chunks"])
     step, per_block = a["cov_binsize"], a["bins_per_block"]
+    pctseq = float(getattr(config, "combine_pctseq", 0.0) or 0.0)
+    alt_of = lambda i: a["alt"][int(a["alt_off"][i]):int(a["alt_off"][i]) + int(a["alt_len"][i])].tobytes()
     for c0, nc, k0, nk, is_bnd, _ in a["chains"].tolist():
         act, n_groups = [], 0                      # act: list of group dicts
         for k in range(k0, k0 + nk):
@@ -35,9 +57,13 @@ def combine_groups(arrays, config):
                         minlen = float(min(abs(g["len"]), abs(svlen)))
                         ok = minlen > 0 and dist <= config.combine_match * math.sqrt(minlen) and dist <= config.combine_match_max
                     if dist < best_dist and ok and (not config.combine_separate_intra or smp not in g["incl"]):
+                        if not is_bnd and pctseq:                    # SVGroup.align_call (sv.py:282-292)
+                            d = levenshtein(alt_of(g["first"]), alt_of(c))
+                            if not ((g["len"] - d) / g["len"]) > pctseq:
+                                continue
                         best, best_dist = g, dist
                 if best is None:
-                    g = dict(slot=c0 + n_groups, pos=float(pos), len=float(abs(svlen)), mate=int(a["mate_pos"][c]) if is_bnd else 0,
+                    g = dict(first=c, slot=c0 + n_groups, pos=float(pos), len=float(abs(svlen)), mate=int(a["mate_pos"][c]) if is_bnd else 0,
                              mc=int(a["mate_contig"][c]) if is_bnd else 0, n=1, incl={smp})
                     n_groups += 1
                     act.append(g)

@@ -13,7 +13,7 @@ import harness                                     # noqa: E402
 from oracle import combine as ocombine             # noqa: E402
 from sniffles_b200 import combine, config as sconfig, snf, synth   # noqa: E402
 
-ARGS = [[], ["--combine-separate-intra"], ["--combine-match", "60"], ["--combine-match-max", "300"], ["--combine-low-confidence", "0.5", "--combine-low-confidence-abs", "3"],
+ARGS = [[], ["--combine-pctseq", "0.985"], ["--combine-pctseq", "0.99", "--combine-separate-intra"], ["--combine-pctseq", "0"], ["--combine-separate-intra"], ["--combine-match", "60"], ["--combine-match-max", "300"], ["--combine-low-confidence", "0.5", "--combine-low-confidence-abs", "3"],
         ["--combine-output-filtered"], ["--combine-support-threshold", "6"], ["--combine-null-min-coverage", "30"], ["--combine-pair-relabel"], ["--combine-high-confidence", "0.5"],
         ["--dev-combine-medians"], ["--cluster-merge-bnd", "300"]]
 

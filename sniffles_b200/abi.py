@@ -136,7 +136,8 @@ class CombineIn(C.Structure):                                   # snfb_combine_i
                 ("n_cov_block", C.c_uint32), ("bins_per_block", C.c_int32), ("cov_binsize", C.c_int32), ("pad", C.c_int32),
                 ("block_start", C.c_void_p), ("cov", C.c_void_p),
                 ("combine_match", C.c_int32), ("combine_match_max", C.c_int32), ("cluster_merge_bnd", C.c_int32),
-                ("combine_separate_intra", C.c_int32), ("combine_overlap_abs", C.c_int32), ("pad2", C.c_int32)]
+                ("combine_separate_intra", C.c_int32), ("combine_overlap_abs", C.c_int32), ("pad2", C.c_int32),
+                ("combine_pctseq", C.c_double), ("alt", C.c_void_p), ("alt_off", C.c_void_p), ("alt_len", C.c_void_p), ("n_alt_bytes", C.c_uint64)]
 
 
 class CombineOut(C.Structure):                                  # snfb_combine_out

@@ -16,7 +16,7 @@ EXPORTS = ["snfb_version", "snfb_sizeof", "snfb_hash_name", "snfb_ctx_create", "
            "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
            "snfb_last_timings", "snfb_device_candidates", "snfb_device_alt", "snfb_launch_count",
            "snfb_pin_host", "snfb_unpin_host", "snfb_pack_cigar16", "snfb_rerun_count", "snfb_coverage_bins",
-           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates", "snfb_selftest_sqrt_frac", "snfb_debug_dump", "snfb_poa", "snfb_combine_groups"]
+           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates", "snfb_selftest_sqrt_frac", "snfb_debug_dump", "snfb_poa", "snfb_combine_groups", "snfb_selftest_edit_distance"]
 
 
 def lib():
@@ -56,6 +56,8 @@ def lib():
         L.snfb_allgather_candidates.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(abi.GatherView)]
         L.snfb_debug_dump.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.snfb_poa.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.snfb_combine_groups.argtypes = [C.c_void_p, C.POINTER(abi.CombineIn), C.POINTER(abi.CombineOut)]
+        L.snfb_selftest_edit_distance.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.snfb_selftest_sqrt_frac.restype = C.c_double
         L.snfb_selftest_sqrt_frac.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_int]
         L.snfb_pack_cigar16.restype = C.c_uint64
@@ -317,8 +319,26 @@ class Context:
         I.n_cov_block, I.bins_per_block, I.cov_binsize = len(a["block_start"]), a["bins_per_block"], a["cov_binsize"]
         I.combine_match, I.combine_match_max, I.cluster_merge_bnd = int(config.combine_match), int(config.combine_match_max), int(config.cluster_merge_bnd)
         I.combine_separate_intra, I.combine_overlap_abs = int(bool(config.combine_separate_intra)), int(config.combine_overlap_abs)
+        I.combine_pctseq = float(getattr(config, "combine_pctseq", 0.0) or 0.0)
+        if I.combine_pctseq != 0.0:
+            I.alt, I.alt_off, I.alt_len, I.n_alt_bytes = a["alt"].ctypes.data, a["alt_off"].ctypes.data, a["alt_len"].ctypes.data, len(a["alt"])
         O.cand_group, O.emit_chunk, O.emit_ord, O.cov_non = (x.ctypes.data for x in out)
         self._check(self._lib.snfb_combine_groups(self._h, C.byref(I), C.byref(O)), "snfb_combine_groups")
+        return out
+
+    def edit_distances(self, pairs):
+        """device edit distance of (bytes, bytes) pairs (snfb_selftest_edit_distance)"""
+        n = len(pairs)
+        if n == 0:
+            return np.zeros(0, "<i4")
+        flat = [x for p in pairs for x in p]
+        lens = np.array([len(x) for x in flat], "<u4")
+        offs = np.zeros(len(flat), "<u8")
+        offs[1:] = np.cumsum(lens[:-1], dtype=np.uint64)
+        by = np.frombuffer(b"".join(bytes(x) for x in flat) + b"\0", "u1").copy()
+        ao, bo, al, bl = (np.ascontiguousarray(v) for v in (offs[0::2], offs[1::2], lens[0::2], lens[1::2]))
+        out = np.zeros(n, "<i4")
+        self._check(self._lib.snfb_selftest_edit_distance(self._h, by.ctypes.data, len(by), ao.ctypes.data, al.ctypes.data, bo.ctypes.data, bl.ctypes.data, n, out.ctypes.data), "snfb_selftest_edit_distance")
         return out
 
     def device_alt(self):

@@ -8,8 +8,8 @@ Split of the work:
     SVGroup.from_candidate / add_candidate, the coverage of the samples a group does not include, the keep / call split;
   * host: SVGroup.call per emitted group in the reference's emission order (sv.py:323-481).
 
-`group.align_call` (sv.py:282-292) needs edlib; where edlib is absent the reference's own `align is None` branch returns True for every pair,
-and that is the behaviour reproduced here (config.combine_pctseq is accepted and ignored; stated in DESIGN.md)."""
+`group.align_call` (sv.py:282-292, edlib's global edit distance between ALT strings) is evaluated on the device when config.combine_pctseq != 0
+(the default 0.7); `--combine-pctseq 0` gives the reference's behaviour without edlib."""
 import statistics
 from dataclasses import dataclass, field
 
@@ -279,5 +279,11 @@ def plan_arrays(plan: Plan, config):
     per_block = config.snf_block_size // step
     cov = np.stack(plan.cov_rows).astype(np.int32) if plan.cov_rows else np.zeros((0, len(config.snf_input_info), per_block), np.int32)
     block_start = np.array(plan.cov_blocks, np.int64)
-    return dict(pos=pos, svlen=svlen, sample=sample, mate_contig=mate_contig, mate_pos=mate_pos, chains=chains, chunks=chunks, cov=np.ascontiguousarray(cov),
+    alts = [c.alt.encode("latin-1") if isinstance(c.alt, str) else bytes(c.alt or b"") for c in plan.cands]
+    alt_len = np.fromiter((len(x) for x in alts), np.uint32, n)
+    alt_off = np.zeros(n, np.uint64)
+    if n:
+        alt_off[1:] = np.cumsum(alt_len[:-1], dtype=np.uint64)
+    alt = np.frombuffer(b"".join(alts) + b"\0", np.uint8).copy()
+    return dict(alt=alt, alt_off=alt_off, alt_len=alt_len, pos=pos, svlen=svlen, sample=sample, mate_contig=mate_contig, mate_pos=mate_pos, chains=chains, chunks=chunks, cov=np.ascontiguousarray(cov),
                 block_start=block_start, bins_per_block=per_block, cov_binsize=step, n_samples=len(config.snf_input_info))

@@ -992,14 +992,20 @@ int snfb_combine_groups(snfb_ctx* ctx, const snfb_combine_in* in, snfb_combine_o
       for (uint32_t i = 0; i < in->n_cand; ++i) if (in->sample[i] >= in->n_samples) return fail(ctx, "snfb_combine_groups: sample index out of range"); }
     cudaSetDevice(ctx->device);
     const size_t n = in->n_cand, S = in->n_samples, W = (S + 31) / 32, ncov = (size_t)in->n_cov_block * S * in->bins_per_block;
+    const bool use_alt = in->combine_pctseq != 0.0 && in->alt && in->alt_off && in->alt_len;
+    uint32_t max_alt = 16;
+    if (use_alt) for (uint32_t i = 0; i < in->n_cand; ++i) { if (in->alt_off[i] + in->alt_len[i] > in->n_alt_bytes) return fail(ctx, "snfb_combine_groups: ALT outside alt[]"); max_alt = std::max(max_alt, in->alt_len[i]); }
+    max_alt = (max_alt + 15u) & ~15u;
+    const unsigned blocks = (unsigned)std::min<size_t>((in->n_chain + 3) / 4, 148 * 4);
     DevBuf b_in, b_state, b_out;
     // inputs in one buffer, group state in one, outputs in one
     Carver ci, cs, co;
     auto lay = [&](Carver& c, combine::P& P, bool in_, bool st_, bool out_) {
         if (in_) { P.chains = c.take<snfb_combine_chain>(in->n_chain); P.chunks = c.take<snfb_combine_chunk>(in->n_chunk); P.pos = c.take<int32_t>(n); P.svlen = c.take<int32_t>(n); P.sample = c.take<uint32_t>(n);
-                   P.mate_contig = c.take<int32_t>(n); P.mate_pos = c.take<int32_t>(n); P.block_start = c.take<long long>(in->n_cov_block + 1); P.cov = c.take<int32_t>(ncov + 1); }
+                   P.mate_contig = c.take<int32_t>(n); P.mate_pos = c.take<int32_t>(n); P.block_start = c.take<long long>(in->n_cov_block + 1); P.cov = c.take<int32_t>(ncov + 1);
+                   if (use_alt) { P.alt = c.take<uint8_t>(in->n_alt_bytes + 16); P.alt_off = c.take<unsigned long long>(n); P.alt_len = c.take<uint32_t>(n); } }
         if (st_) { P.g_pos = c.take<double>(n); P.g_len = c.take<double>(n); P.g_mate = c.take<double>(n); P.g_n = c.take<uint32_t>(n); P.g_mc = c.take<int32_t>(n); P.g_incl = c.take<uint32_t>(n * W); P.act = c.take<uint32_t>(n);
-                   P.next_chain = c.take<unsigned int>(4); }
+                   P.next_chain = c.take<unsigned int>(4); P.g_first = c.take<uint32_t>(n); P.ex_stamp = c.take<uint32_t>(n); if (use_alt) P.hs = c.take<int8_t>((size_t)blocks * 4 * max_alt + 16); }
         if (out_) { P.cand_group = c.take<uint32_t>(n); P.emit_chunk = c.take<int32_t>(n); P.emit_ord = c.take<uint32_t>(n); P.cov_non = c.take<int32_t>(n * S); }
     };
     combine::P P{};
@@ -1016,15 +1022,38 @@ int snfb_combine_groups(snfb_ctx* ctx, const snfb_combine_in* in, snfb_combine_o
     up(P.chains, in->chains, sizeof(snfb_combine_chain) * in->n_chain); up(P.chunks, in->chunks, sizeof(snfb_combine_chunk) * in->n_chunk);
     up(P.pos, in->pos, 4 * n); up(P.svlen, in->svlen, 4 * n); up(P.sample, in->sample, 4 * n); up(P.mate_contig, in->mate_contig, 4 * n); up(P.mate_pos, in->mate_pos, 4 * n);
     up(P.block_start, in->block_start, 8 * (size_t)in->n_cov_block); up(P.cov, in->cov, 4 * ncov);
+    P.pctseq = use_alt ? in->combine_pctseq : 0.0; P.max_alt = max_alt;
+    if (use_alt) { up(P.alt, in->alt, in->n_alt_bytes); up(P.alt_off, in->alt_off, 8 * n); up(P.alt_len, in->alt_len, 4 * n); }
     cudaMemsetAsync(P.next_chain, 0, 16, st);
     mark(ctx, "combine_groups");
-    const unsigned blocks = (unsigned)std::min<size_t>((in->n_chain + 3) / 4, 148 * 4);
     combine::k_combine<<<blocks, 128, 0, st>>>(P); LAUNCHED(ctx, 1);
     mark(ctx, nullptr);
     cudaMemcpyAsync(out->cand_group, P.cand_group, 4 * n, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(out->emit_chunk, P.emit_chunk, 4 * n, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(out->emit_ord, P.emit_ord, 4 * n, cudaMemcpyDeviceToHost, st); cudaMemcpyAsync(out->cov_non, P.cov_non, 4 * n * S, cudaMemcpyDeviceToHost, st);
     const cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return done(fail(ctx, std::string("snfb_combine_groups: ") + cudaGetErrorString(e)));
+    return done(0);
+}
+
+int snfb_selftest_edit_distance(snfb_ctx* ctx, const uint8_t* bytes, uint64_t n_bytes, const uint64_t* a_off, const uint32_t* a_len, const uint64_t* b_off, const uint32_t* b_len, uint32_t n_pairs, int32_t* out) {
+    if (!ctx || !bytes || !a_off || !a_len || !b_off || !b_len || !out) return ctx ? fail(ctx, "snfb_selftest_edit_distance: null argument") : 1;
+    if (n_pairs == 0) return 0;
+    uint32_t max_len = 16;
+    for (uint32_t i = 0; i < n_pairs; ++i) { if (a_off[i] + a_len[i] > n_bytes || b_off[i] + b_len[i] > n_bytes) return fail(ctx, "snfb_selftest_edit_distance: string outside bytes[]"); max_len = std::max(max_len, std::max(a_len[i], b_len[i])); }
+    max_len = (max_len + 15u) & ~15u;
+    cudaSetDevice(ctx->device);
+    const unsigned blocks = (unsigned)std::min<uint32_t>((n_pairs + 3) / 4, 148 * 4);
+    DevBuf d_b, d_o, d_hs, d_out;
+    auto done = [&](int r) { d_b.release(); d_o.release(); d_hs.release(); d_out.release(); return r; };
+    if (d_b.ensure(n_bytes + 16) | d_o.ensure((size_t)n_pairs * 24 + 64) | d_hs.ensure((size_t)blocks * 4 * max_len + 16) | d_out.ensure((size_t)n_pairs * 4)) return done(fail(ctx, "snfb_selftest_edit_distance: out of device memory"));
+    unsigned long long* ao = d_o.as<unsigned long long>(); unsigned long long* bo = ao + n_pairs; uint32_t* al = reinterpret_cast<uint32_t*>(bo + n_pairs); uint32_t* bl = al + n_pairs;
+    cudaStream_t st = ctx->st;
+    cudaMemcpyAsync(d_b.p, bytes, n_bytes, cudaMemcpyHostToDevice, st); cudaMemcpyAsync(ao, a_off, 8 * (size_t)n_pairs, cudaMemcpyHostToDevice, st); cudaMemcpyAsync(bo, b_off, 8 * (size_t)n_pairs, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(al, a_len, 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, st); cudaMemcpyAsync(bl, b_len, 4 * (size_t)n_pairs, cudaMemcpyHostToDevice, st);
+    combine::k_edit_selftest<<<blocks, 128, 0, st>>>(d_b.as<uint8_t>(), ao, al, bo, bl, n_pairs, d_hs.as<int8_t>(), max_len, d_out.as<int>()); LAUNCHED(ctx, 1);
+    cudaMemcpyAsync(out, d_out.p, 4 * (size_t)n_pairs, cudaMemcpyDeviceToHost, st);
+    const cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return done(fail(ctx, std::string("snfb_selftest_edit_distance: ") + cudaGetErrorString(e)));
     return done(0);
 }
 

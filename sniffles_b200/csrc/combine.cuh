@@ -21,7 +21,54 @@ struct P {
     uint32_t* act;                                 // [n_cand] active group list of the chain, at chain.cand_off
     uint32_t* cand_group; int32_t* emit_chunk; uint32_t* emit_ord; int32_t* cov_non;
     unsigned int* next_chain;
+    // group.align_call (sv.py:282-292): pctseq > 0 switches it on.  alt: the candidates' ALT strings; g_first: the candidate that opened the group;
+    // ex_stamp[g] == c + 1: group g failed the alignment test for candidate c; hs: per warp, max_alt bytes of carries between passes
+    double pctseq; const uint8_t* alt; const unsigned long long* alt_off; const uint32_t* alt_len; uint32_t* g_first; uint32_t* ex_stamp; int8_t* hs; uint32_t max_alt;
 };
+
+// Levenshtein distance (edlib.align(a, b) defaults: global alignment, task "distance") by one warp: Myers' bit-vector recurrence in 64-row blocks
+// (Hyyro's block formulation, the one edlib implements), lane = block, the text streamed through the lanes as a wavefront (lane l works on column
+// s - l at step s, its horizontal carry-in is lane l-1's carry-out of the step before); patterns of more than 32 blocks take several passes,
+// the carries of a pass's last block wait in hs[].  The shorter string is the pattern.  The result is exact for any byte strings.
+__device__ inline int edit_distance_warp(const uint8_t* a, int m, const uint8_t* b, int n, int8_t* hs) {
+    const int lane = lane_id();
+    if (m > n) { const uint8_t* t = a; a = b; b = t; const int ti = m; m = n; n = ti; }
+    if (m == 0) return n;
+    const int W = (m + 63) / 64; int score = m;
+    for (int p0 = 0; p0 < W; p0 += 32) {
+        const int blk = p0 + lane; const bool vb = blk < W; const bool last = blk == W - 1;
+        unsigned long long eq[5] = { 0, 0, 0, 0, 0 };            // A C G T N
+        const int rows = vb ? min(64, m - blk * 64) : 0;
+        for (int k = 0; k < rows; ++k) { const uint8_t ch = a[blk * 64 + k]; const int idx = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : ch == 'N' ? 4 : -1;
+            #pragma unroll
+            for (int q = 0; q < 5; ++q) if (idx == q) eq[q] |= 1ull << k; }
+        unsigned long long Pv = ~0ull, Mv = 0ull; int hout = 0;
+        const unsigned long long top = last ? 1ull << ((m - 1) & 63) : 1ull << 63;
+        for (int s = 0; s < n + 31; ++s) {
+            const int hprev = __shfl_up_sync(FULL, hout, 1);
+            const int j = s - lane; const bool act = vb && j >= 0 && j < n;
+            if (act) {
+                const uint8_t c = b[j];
+                unsigned long long Eq;
+                if (c == 'A') Eq = eq[0]; else if (c == 'C') Eq = eq[1]; else if (c == 'G') Eq = eq[2]; else if (c == 'T') Eq = eq[3]; else if (c == 'N') Eq = eq[4];
+                else { Eq = 0; for (int k = 0; k < rows; ++k) if (a[blk * 64 + k] == c) Eq |= 1ull << k; }
+                const int hin = lane == 0 ? (p0 == 0 ? 1 : (int)hs[j]) : hprev;
+                const unsigned long long Xv = Eq | Mv;
+                if (hin < 0) Eq |= 1ull;
+                const unsigned long long Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+                unsigned long long Ph = Mv | ~(Xh | Pv), Mh = Pv & Xh;
+                hout = (Ph & top) ? 1 : ((Mh & top) ? -1 : 0);
+                Ph <<= 1; Mh <<= 1;
+                if (hin < 0) Mh |= 1ull; else if (hin > 0) Ph |= 1ull;
+                Pv = Mh | ~(Xv | Ph); Mv = Ph & Xv;
+                if (last) score += hout; else if (lane == 31) hs[j] = (int8_t)hout;
+            }
+        }
+        __syncwarp();
+    }
+    return __shfl_sync(FULL, score, (W - 1) & 31);
+}
+
 
 __global__ void __launch_bounds__(128) k_combine(const P p) {
     const int lane = lane_id();
@@ -39,35 +86,46 @@ __global__ void __launch_bounds__(128) k_combine(const P p) {
                 const int cpos = p.pos[c], clen = p.svlen[c]; const uint32_t smp = p.sample[c];
                 const int cmc = ch.is_bnd ? p.mate_contig[c] : 0, cmp = ch.is_bnd ? p.mate_pos[c] : 0;
                 const double alen = (double)(clen < 0 ? -(long long)clen : (long long)clen);
-                double bd = __longlong_as_double(0x7ff0000000000000ll); uint32_t bi = 0xffffffffu;
-                for (uint32_t a0 = 0; a0 < n_act; a0 += 32) {
-                    const uint32_t a = a0 + lane;
-                    if (a < n_act) {
-                        const uint32_t g = act[a]; const double gp = p.g_pos[g];
-                        double dist; bool ok;
-                        if (ch.is_bnd) {
-                            dist = __dadd_rn(fabs(__dsub_rn(gp, (double)cpos)), fabs(__dsub_rn(p.g_mate[g], (double)cmp)));
-                            ok = dist <= (double)(p.cluster_merge_bnd * 2) && p.g_mc[g] == cmc;
-                        } else {
-                            const double gl = fabs(p.g_len[g]);
-                            dist = __dadd_rn(fabs(__dsub_rn(gp, (double)cpos)), fabs(__dsub_rn(gl, alen)));
-                            const double minlen = gl < alen ? gl : alen;
-                            ok = minlen > 0.0 && dist <= __dmul_rn((double)p.combine_match, __dsqrt_rn(minlen)) && dist <= (double)p.combine_match_max;
+                double bd; uint32_t bi;
+                for (;;) {
+                    bd = __longlong_as_double(0x7ff0000000000000ll); bi = 0xffffffffu;
+                    for (uint32_t a0 = 0; a0 < n_act; a0 += 32) {
+                        const uint32_t a = a0 + lane;
+                        if (a < n_act) {
+                            const uint32_t g = act[a]; const double gp = p.g_pos[g];
+                            double dist; bool ok;
+                            if (ch.is_bnd) {
+                                dist = __dadd_rn(fabs(__dsub_rn(gp, (double)cpos)), fabs(__dsub_rn(p.g_mate[g], (double)cmp)));
+                                ok = dist <= (double)(p.cluster_merge_bnd * 2) && p.g_mc[g] == cmc;
+                            } else {
+                                const double gl = fabs(p.g_len[g]);
+                                dist = __dadd_rn(fabs(__dsub_rn(gp, (double)cpos)), fabs(__dsub_rn(gl, alen)));
+                                const double minlen = gl < alen ? gl : alen;
+                                ok = minlen > 0.0 && dist <= __dmul_rn((double)p.combine_match, __dsqrt_rn(minlen)) && dist <= (double)p.combine_match_max && p.ex_stamp[g] != c + 1u;
+                            }
+                            if (ok && dist < bd && (!p.separate_intra || !((p.g_incl[(size_t)g * W + (smp >> 5)] >> (smp & 31)) & 1u))) { bd = dist; bi = a; }
                         }
-                        if (ok && dist < bd && (!p.separate_intra || !((p.g_incl[(size_t)g * W + (smp >> 5)] >> (smp & 31)) & 1u))) { bd = dist; bi = a; }
                     }
-                }
-                // first minimum in list order: smallest distance, then smallest list index
-                #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const double od = __shfl_xor_sync(FULL, bd, o); const uint32_t oi = __shfl_xor_sync(FULL, bi, o);
-                    if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                    // first minimum in list order: smallest distance, then smallest list index
+                    #pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const double od = __shfl_xor_sync(FULL, bd, o); const uint32_t oi = __shfl_xor_sync(FULL, bi, o);
+                        if (od < bd || (od == bd && oi < bi)) { bd = od; bi = oi; }
+                    }
+                    if (bi == 0xffffffffu || ch.is_bnd || !(p.pctseq != 0.0)) break;
+                    // the nearest eligible group must also align (only groups that pass can become the best one, so testing them nearest first is the reference's result)
+                    const uint32_t g = act[bi], fc = p.g_first[g];
+                    const int d = edit_distance_warp(p.alt + p.alt_off[fc], (int)p.alt_len[fc], p.alt + p.alt_off[c], (int)p.alt_len[c], p.hs + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * p.max_alt);
+                    const double lm = p.g_len[g];
+                    if (__ddiv_rn(__dsub_rn(lm, (double)d), lm) > p.pctseq) break;
+                    if (lane == 0) p.ex_stamp[g] = c + 1u;
+                    __syncwarp();
                 }
                 uint32_t g;
                 if (bi == 0xffffffffu) {                          // SVGroup.from_candidate
                     g = ch.cand_off + n_groups;
                     if (lane == 0) {
-                        p.g_pos[g] = (double)cpos; p.g_len[g] = alen; p.g_mate[g] = (double)cmp; p.g_mc[g] = cmc; p.g_n[g] = 1u; act[n_act] = g;
+                        p.g_pos[g] = (double)cpos; p.g_len[g] = alen; p.g_mate[g] = (double)cmp; p.g_mc[g] = cmc; p.g_n[g] = 1u; act[n_act] = g; p.g_first[g] = c; p.ex_stamp[g] = 0u;
                         p.emit_chunk[g] = (int32_t)p.n_chunk; p.emit_ord[g] = 0u;
                     }
                     for (uint32_t w = lane; w < W; w += 32) p.g_incl[(size_t)g * W + w] = (w == (smp >> 5)) ? (1u << (smp & 31)) : 0u;
@@ -119,6 +177,16 @@ __global__ void __launch_bounds__(128) k_combine(const P p) {
         // groups still kept at the end of the chain are called last, in list order (parallel.py:565-566)
         for (uint32_t a = lane; a < n_act; a += 32) { const uint32_t g = act[a]; p.emit_chunk[g] = (int32_t)p.n_chunk; p.emit_ord[g] = a; }
         for (uint32_t g = ch.cand_off + n_groups + lane; g < ch.cand_off + ch.n_cand; g += 32) p.emit_chunk[g] = -1;     // unused slots
+        __syncwarp();
+    }
+}
+
+// self-check: one warp per pair
+__global__ void k_edit_selftest(const uint8_t* bytes, const unsigned long long* a_off, const uint32_t* a_len, const unsigned long long* b_off, const uint32_t* b_len, uint32_t n_pairs, int8_t* hs, uint32_t max_len, int* out) {
+    const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = w; i < n_pairs; i += nw) {
+        const int d = edit_distance_warp(bytes + a_off[i], (int)a_len[i], bytes + b_off[i], (int)b_len[i], hs + (size_t)w * max_len);
+        if (lane_id() == 0) out[i] = d;
         __syncwarp();
     }
 }

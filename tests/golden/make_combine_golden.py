@@ -1,6 +1,6 @@
 """Generates tests/golden/combine/: four synthetic samples that share planted SV sites, each written as an SNF by the UNMODIFIED reference
 (oracle/pyref/harness.write_reference_snf), and the reference's own multi-sample combine over them (harness.reference_combine:
-CombineTask.execute per contig) as call dictionaries and VCF records.  Run in the build container (needs /root/reference):
+CombineTask.execute per contig, with oracle/pyref/stubs/edlib standing in for edlib's edit distance) as call dictionaries and VCF records.  Run in the build container (needs /root/reference):
     python tests/golden/make_combine_golden.py"""
 import json
 import os
@@ -35,7 +35,8 @@ def main():
         paths.append(p)
     names = [f"ctg{i + 1}" for i in range(len(CONTIGS))]
     cases = {}
-    for label, args in (("default", []), ("separate_intra", ["--combine-separate-intra"]), ("loose", ["--combine-match", "100", "--combine-low-confidence", "0.6", "--combine-output-filtered"])):
+    for label, args in (("default", []), ("no_alignment", ["--combine-pctseq", "0"]), ("strict_alignment", ["--combine-pctseq", "0.985", "--combine-separate-intra"]),
+                        ("loose", ["--combine-match", "100", "--combine-low-confidence", "0.6", "--combine-output-filtered"])):
         config, calls, lines = harness.reference_combine(paths, list(zip(names, CONTIGS)), args)
         cases[label] = dict(args=args, calls={c: [harness.combine_call_dict(x) for x in v] for c, v in calls.items()}, vcf=lines)
         print(label, {c: len(v) for c, v in calls.items()}, len(lines), "VCF records")

@@ -112,3 +112,54 @@ def test_device_grouping_equals_the_restatement_and_the_reference(label):
         assert np.array_equal(out[2][:n][used], ref[2][:n][used]) and np.array_equal(out[3][:n][used], ref[3][:n][used])
         assert [norm(call_dict(c)) for c in calls[name]] == case["calls"][name]
     assert ctx.launch_count() > 0
+
+
+def test_edit_distance_restatements_agree():
+    """oracle/combine.levenshtein (numpy rows) and the edlib stand-in the reference runs with (bit vectors on Python integers)"""
+    import random
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "pyref", "stubs"))
+    import edlib
+    r = random.Random(5)
+    for _ in range(120):
+        a = bytes(r.choice(b"ACGT") for _ in range(r.randrange(0, 200)))
+        b = bytearray(a) if r.random() < 0.6 else bytearray(r.choice(b"ACGTN") for _ in range(r.randrange(0, 200)))
+        for _ in range(r.randrange(0, 25)):
+            if b and r.random() < 0.5:
+                del b[r.randrange(len(b))]
+            else:
+                b.insert(r.randrange(len(b) + 1), r.choice(b"ACGT"))
+        assert ocombine.levenshtein(a, bytes(b)) == edlib.levenshtein(a, bytes(b))
+    assert ocombine.levenshtein(b"kitten", b"sitting") == 3 and ocombine.levenshtein(b"", b"abc") == 3 and ocombine.levenshtein(b"<DEL>", b"<DEL>") == 0
+
+
+@pytest.mark.gpu
+def test_device_edit_distance():
+    """the kernel behind group.align_call against the restatement: block boundaries (63/64/65 rows), several passes (> 2048 rows), other alphabets"""
+    import random
+    from sniffles_b200 import binding
+    sys.path.insert(0, os.path.join(ROOT, "oracle", "pyref", "stubs"))
+    import edlib
+    r = random.Random(9)
+    pairs = [(b"", b""), (b"", b"ACGT"), (b"A", b"A"), (b"A", b"C"), (b"<DEL>", b"<DEL>"), (b"<DEL>", b"<DUP>"), (b"kitten", b"sitting")]
+    for la in (1, 2, 31, 63, 64, 65, 127, 128, 129, 500, 2047, 2048, 2049, 4100, 6000):
+        a = bytes(r.choice(b"ACGT") for _ in range(la))
+        for mode in range(3):
+            if mode == 0:
+                b = bytearray(a)
+                for _ in range(max(1, la // 20)):
+                    k = r.randrange(3)
+                    if k == 0 and b:
+                        del b[r.randrange(len(b))]
+                    elif k == 1:
+                        b.insert(r.randrange(len(b) + 1), r.choice(b"ACGTN"))
+                    elif b:
+                        b[r.randrange(len(b))] = r.choice(b"ACGTRYK")
+            elif mode == 1:
+                b = bytearray(r.choice(b"ACGT") for _ in range(r.randrange(1, 2 * la + 2)))
+            else:
+                b = bytearray(a[la // 3:]) + bytearray(r.choice(b"acgtn") for _ in range(la // 5))
+            pairs.append((a, bytes(b)))
+    ctx = binding.Context(0)
+    got = ctx.edit_distances(pairs)
+    want = [edlib.levenshtein(a, b) for a, b in pairs]
+    assert got.tolist() == want
