@@ -500,13 +500,132 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+# ---------------------------------------------------------------------------------------------------- config 4: population combine
+def combine_workload(n_samples, scale, seed=1004):
+    """Candidate-level synthetic population (BASELINE config 4): `n_samples` samples that share planted sites on 24 GRCh38-length contigs (one per
+    120 kb), each sample carrying 80 % of them with jittered position / length, per-sample support and, for INS, its own noisy copy of the inserted
+    sequence.  Served to CombineTask.plan through reader objects with the SNF reader's interface, so the chunks are formed by the product code."""
+    import types
+    from sniffles_b200 import synth
+    rng = np.random.default_rng(seed)
+    lens = [max(200000, int(x * scale)) for x in synth.GRCH38]
+    bs, step = 100000, 500
+    blocks = [dict() for _ in range(n_samples)]                      # per sample: (contig, block) -> block dict
+    code = np.frombuffer(b"ACGT", np.uint8)
+    for ci, clen in enumerate(lens):
+        name = f"ctg{ci + 1}"
+        nsite = max(1, clen // 120000)
+        pos = np.sort(rng.integers(1000, clen - 1000, nsite))
+        kind = rng.choice(5, nsite, p=[0.45, 0.45, 0.04, 0.03, 0.03])   # INS DEL DUP INV BND
+        size = np.exp(rng.uniform(np.log(50), np.log(2000), nsite)).astype(np.int64)
+        for si in range(nsite):
+            t = ("INS", "DEL", "DUP", "INV", "BND")[kind[si]]
+            base = code[rng.integers(0, 4, size[si])] if t == "INS" else None
+            carriers = np.nonzero(rng.random(n_samples) < 0.8)[0]
+            for sm in carriers:
+                p_ = int(pos[si] + rng.integers(-6, 7)); ln = int(size[si] + rng.integers(-3, 4))
+                if t == "INS":
+                    sq = base.copy(); k = max(1, len(sq) // 50); sq[rng.integers(0, len(sq), k)] = code[rng.integers(0, 4, k)]
+                    alt = sq.tobytes().decode()
+                else:
+                    alt = f"<{t}>"
+                c = types.SimpleNamespace(svtype=t, pos=p_, svlen=-ln if t == "DEL" else (0 if t == "BND" else ln), support=int(rng.integers(3, 30)), alt=alt, bnd_info=None)
+                if t == "BND":
+                    c.bnd_info = types.SimpleNamespace(mate_contig=f"ctg{(ci + 3) % len(lens) + 1}", mate_ref_start=int(1000 + (pos[si] * 7) % 100000 + rng.integers(-5, 6)))
+                b = (p_ // bs) * bs
+                blk = blocks[sm].get((name, b))
+                if blk is None:
+                    blk = blocks[sm][(name, b)] = {"INS": [], "DEL": [], "DUP": [], "INV": [], "BND": [], "_COVERAGE": {b + i * step: 30 for i in range(bs // step)}}
+                blk[t].append(c)
+
+    class Reader:
+        def __init__(self, d):
+            self.d = d
+
+        def read_blocks(self, contig, block_index):
+            b = self.d.get((contig, block_index))
+            return None if b is None else [b]
+
+        def close(self):
+            pass
+    return lens, [Reader(d) for d in blocks]
+
+
+def run_combine(args):
+    """--config 4: the multi-sample grouping through snfb_combine_groups (host buffers in and out, so the timed call IS the end-to-end call)"""
+    import torch
+    from sniffles_b200 import binding, combine, config as sconfig
+    sys.path.insert(0, ROOT)
+    n_samples = 50
+    t0 = time.time()
+    lens, readers = combine_workload(n_samples, args.scale)
+    cfg = sconfig.default_config(*(["--combine-pctseq", os.environ["SNFB_COMBINE_PCTSEQ"]] if "SNFB_COMBINE_PCTSEQ" in os.environ else []))
+    cfg.mode = "combine"
+    cfg.snf_input_info = [{"internal_id": k, "sample_id": f"S{k}", "filename": None} for k in range(n_samples)]
+    cfg.sample_ids_vcf = [(k, f"S{k}") for k in range(n_samples)]
+    rd = {k: r for k, r in enumerate(readers)}
+    plan, tasks = combine.Plan(), []
+    for ti, clen in enumerate(lens):
+        task = combine.CombineTask(ti, f"ctg{ti + 1}", 0, clen - 1, cfg)
+        task.plan(rd, plan, task_index=ti)
+        tasks.append(task)
+    arrays = combine.plan_arrays(plan, cfg)
+    n = len(plan.cands)
+    log(f"[bench] config 4: {n_samples} samples, {n} candidates, {len(plan.chains)} chains, {len(plan.chunks)} chunks, ALT arena {len(arrays['alt']) / 1e6:.1f} MB, built in {time.time() - t0:.1f}s")
+    ctx = binding.Context(0)
+    call = lambda: ctx.combine_groups(plan, cfg, arrays=arrays)
+    for _ in range(max(args.warmup, 1)):
+        out = call()
+    sampler = ClockSampler(0); sampler.start()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    kern_ms = 0.0
+    for _ in range(args.steps):
+        out = call()
+        kern_ms += max([ms for nm, ms, _ in ctx.timings() if nm == "combine_groups"] or [0.0])
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t1
+    clocks = sampler.stop()
+    ms_per_step = wall / args.steps * 1e3
+    n_groups = int((out[1][:n] >= 0).sum())
+    h2d = sum(int(arrays[k].nbytes) for k in ("chains", "chunks", "pos", "svlen", "sample", "mate_contig", "mate_pos", "block_start", "cov", "alt", "alt_off", "alt_len"))
+    d2h = 12 * n + 4 * n * n_samples
+    res = {"metric": "multi-sample combine: candidates grouped per second (BASELINE config 4; the Gbp/s metric does not apply to SNF inputs)", "value": n / (wall / args.steps), "unit": "candidates/s",
+           "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64 / int32", "data": "synthetic",
+           "config": {"workload": f"BASELINE config 4: {n_samples} samples x ~{n // n_samples} candidates on 24 GRCh38-length contigs x scale {args.scale}, --combine-pctseq {cfg.combine_pctseq} (edit distance on)",
+                      "candidates": n, "groups": n_groups, "chains": len(plan.chains), "chunks": len(plan.chunks), "l2": "host-buffer call: inputs cross PCIe every step"},
+           "clocks": clocks, "gpu_launches": int(args.steps), "kernel_ms_per_step": kern_ms / args.steps,
+           "e2e": {"value": n / (wall / args.steps), "unit": "candidates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "note": "snfb_combine_groups takes and returns host buffers: the timed call is the end-to-end call"},
+           "roofline": {"bound": "latency", "kernel": "combine::k_combine", "note": "one warp per (contig, svtype) chain, sequential along the chain by construction (groups carry over): the longest chain is the step", "achieved": None, "peak": None, "unit": None, "frac": None, "traffic": None}}
+    if not args.no_cpu:
+        # CPU arm: the grouping restatement (oracle/combine.py, pinned against the reference's CombineTask) on a bounded sample: the chains of the smallest contigs
+        from oracle import combine as ocombine
+        order = sorted(range(len(lens)), key=lambda i: lens[i])
+        sub, tot = combine.Plan(), 0
+        for ti in order:
+            tasks[ti].plan(rd, sub, task_index=ti)
+            tot = len(sub.cands)
+            if tot >= 8000:
+                break
+        sa = combine.plan_arrays(sub, cfg)
+        t2 = time.perf_counter()
+        ref = ocombine.combine_groups(sa, cfg)
+        dt = time.perf_counter() - t2
+        dev = ctx.combine_groups(sub, cfg, arrays=sa)
+        m = len(sub.cands)
+        res["cpu_baseline"] = {"value": m / dt, "unit": "candidates/s", "cores": 1, "kind": "port", "sample": f"{m} candidates (the smallest contigs), oracle/combine.py (pure Python + numpy edit distance; the reference itself calls edlib, C code that is absent here) in {dt:.1f}s",
+                               "identical_to_device": bool(np.array_equal(ref[0][:m], dev[0][:m]) and np.array_equal(ref[1][:m], dev[1][:m]))}
+    print(json.dumps(res))
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", type=int, default=int(os.environ.get("SNFB_BENCH_CONFIG", "2")), help="BASELINE.json config index: 1, 2 (default: 30x ONT WGS), 3 (60x HiFi --mosaic), 5 (INS-heavy)")
+    ap.add_argument("--config", type=int, default=int(os.environ.get("SNFB_BENCH_CONFIG", "2")), help="BASELINE.json config index: 1, 2 (default: 30x ONT WGS), 3 (60x HiFi --mosaic), 4 (50-sample combine; its own metric), 5 (INS-heavy)")
     ap.add_argument("--scale", type=float, default=float(os.environ.get("SNFB_BENCH_SCALE", "1.0")), help="contig length multiplier (1.0 = the named size)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-sample-gbp", type=float, default=1000.0, help="sequenced Gbp of the CPU arm's sample (smallest contigs first); the default takes every contig: one host thread per contig, the reference's own grain")
@@ -522,7 +641,12 @@ def main():
         g.build()
     elif args.impl == "b200":
         time.sleep(2.0)         # let rank 0 check/refresh the in-tree libraries first
-    if args.impl == "reference":
+    if args.config == 4:
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "config 4 has no Gbp/s metric; its CPU arm is the cpu_baseline of `bench.py --config 4`"}))
+        else:
+            run_combine(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

@@ -303,11 +303,11 @@ class Context:
                 res.append((dec(a), dec(b)))
         return res
 
-    def combine_groups(self, plan, config):
+    def combine_groups(self, plan, config, arrays=None):
         """The grouping of multi-sample combine on the device (snfb_combine_groups; cluster.resolve_block_groups + the chunk loop of
         CombineTask.execute).  plan: combine.Plan.  Returns (cand_group, emit_chunk, emit_ord, cov_non[n_cand][n_samples])."""
         from . import combine
-        a = combine.plan_arrays(plan, config)
+        a = arrays if arrays is not None else combine.plan_arrays(plan, config)
         n, S = len(a["pos"]), a["n_samples"]
         out = (np.zeros(max(n, 1), "<u4"), np.full(max(n, 1), -1, "<i4"), np.zeros(max(n, 1), "<u4"), np.full((max(n, 1), S), -1, "<i4"))
         if n == 0:
