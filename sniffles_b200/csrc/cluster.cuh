@@ -364,7 +364,7 @@ template <class G> __device__ __forceinline__ double bcast_f8(const G& g, double
 // ---- bitonic network with ascending comparators only: positions >= n behave as +infinity and are never touched, so the
 //      arrays need exactly n entries.  Keys must be distinct for a deterministic result (callers put the index in the low key).
 __device__ __forceinline__ bool lt2(uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl) { return ah < bh || (ah == bh && al < bl); }
-template <class G> __device__ inline void sort2(const G& g, uint64_t* hi, uint64_t* lo, int n) {    // ascending by (hi, lo)
+template <class G> __device__ __noinline__ void sort2(const G& g, uint64_t* hi, uint64_t* lo, int n) {    // ascending by (hi, lo)
     if (n < 2) return;
     if (G::is_warp && n <= 32) {                      // one element per lane: its rank is the number of smaller elements (register shuffles, no network)
         const int i = g.tid(); const uint64_t xh = i < n ? hi[i] : 0, xl = i < n ? lo[i] : 0; int rank = 0;
@@ -388,7 +388,7 @@ template <class G> __device__ inline void sort2(const G& g, uint64_t* hi, uint64
         }
     }
 }
-template <class G> __device__ inline void sort1(const G& g, uint64_t* a, int n) {                     // ascending, unsigned (ties are equal values: order-free)
+template <class G> __device__ __noinline__ void sort1(const G& g, uint64_t* a, int n) {                     // ascending, unsigned (ties are equal values: order-free)
     if (n < 2) return;
     if (G::is_warp && n <= 32) {
         const int i = g.tid(); const uint64_t x = i < n ? a[i] : 0; int rank = 0;
@@ -430,7 +430,7 @@ template <class G> __device__ inline int count_distinct_sorted(const G& g, const
     return (int)g.sum(c);
 }
 // exact sample stdev of the biased-int64 values a[0..m): statistics.stdev through P = m Sxx - Sx^2, Q = m (m - 1) (common.cuh)
-template <class G> __device__ inline double stdev_sorted(const G& g, const uint64_t* a, long m) {
+template <class G> __device__ __noinline__ double stdev_sorted(const G& g, const uint64_t* a, long m) {
     if (m < 2) return 0.0;
     const long long base = unbias64(a[0]);
     long long sx = 0; u128 sxx = 0;
@@ -450,7 +450,7 @@ template <class G> __device__ inline double stdev_trim_sorted(const G& g, const 
 
 // util.center = median_modes over a sorted (biased) array (util.py:49-58): the upper median of the distinct values whose multiplicity is
 // within 2 of the largest one.  Cooperative: run heads, run lengths, the qualifying runs.  s0 / s1: scratch of n entries each.
-template <class G> __device__ inline long long center_sorted(const G& g, const uint64_t* a, int n, uint32_t* s0, uint32_t* s1) {
+template <class G> __device__ __noinline__ long long center_sorted(const G& g, const uint64_t* a, int n, uint32_t* s0, uint32_t* s1) {
     const int nh = compact(g, n, s0, [&](int i) { return i == 0 || a[i] != a[i - 1]; });
     int mx = 0; for (int h = g.tid(); h < nh; h += g.nthr()) { const int c = (int)((h + 1 < nh ? s0[h + 1] : (uint32_t)n) - s0[h]); if (c > mx) mx = c; }
     const int maxc = g.maxi(mx);
