@@ -94,9 +94,9 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of the lead kernel from the committed ncu capture, if any."""
-    p = os.path.join(ROOT, "profiles", "k_scan_dram.json")
+def ncu_traffic(name="k_scan_dram.json"):
+    """DRAM bytes per launch of a kernel (group) from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", name)
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
@@ -457,7 +457,7 @@ def run_b200(args):
     c_alg = consensus_algorithmic_bytes(full)
     c_ach = c_alg / (c_ms / 1e3) / 1e9 if c_ms > 0 else 0.0
     roof_c = {"bound": "hbm", "kernel": "consensus::k_prep + k_align + k_vote", "achieved": c_ach, "peak": peak, "unit": "GB/s", "frac": c_ach / peak if peak else None, "peak_source": peak_src,
-              "algorithmic_bytes_per_launch": c_alg, "kernel_ms": c_ms, "traffic": None}
+              "algorithmic_bytes_per_launch": c_alg, "kernel_ms": c_ms, "traffic": (ncu_traffic("consensus_dram.json") or {}).get("dram_bytes_per_launch") if traffic else None}
     roof = roof_c if c_ms > k_ms else roof_a
     if rank == 0:
         out = {"metric": "aligned long-read Gbp/s through lead->cluster->consensus", "value": value, "unit": "Gbp/s", "n_gpus": world, "steps": args.steps,

@@ -272,6 +272,7 @@ const char* snfb_last_error(snfb_ctx* ctx) { return ctx ? ctx->err.c_str() : "nu
 
 int snfb_set_config(snfb_ctx* ctx, const snfb_config* cfg) {
     if (!ctx || !cfg) return 1;
+    ctx->force_no_cuts = false;      // a new configuration decides again where chains of bins may be cut
     if (cfg->consensus_kmer_len != 6) return fail(ctx, "consensus_kmer_len must be 6 (the reference fixes it, config.py:550)");
     if (cfg->cluster_binsize <= 0 || cfg->cluster_resplit_binsize <= 0 || cfg->coverage_binsize <= 0) return fail(ctx, "bin sizes must be positive");
     ctx->cfg = *cfg; ctx->have_cfg = true; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false; return 0;
@@ -339,7 +340,7 @@ __global__ void k_validate(const snfb_rec* __restrict__ rec, uint32_t n_rec, uin
 int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     if (!ctx || !R) return 1;
     cudaSetDevice(ctx->device);
-    ctx->loaded = false; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false;
+    ctx->loaded = false; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false; ctx->force_no_cuts = false;
     if (R->n_task == 0 || R->n_task > 65535) return fail(ctx, "n_task must be in 1..65535");
     if (R->n_rec > 0xfffffff0ull) return fail(ctx, "too many records in one block");
     if (!R->task || (R->n_rec && (!R->rec || !R->cigar))) return fail(ctx, "null table in the record block");

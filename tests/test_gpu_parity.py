@@ -38,6 +38,30 @@ def test_bam_words_converted_by_the_library():
     _run(synth.config_block(2, 0.003), cigar16=False)
 
 
+def test_wrong_chain_cut_is_detected_and_recovered():
+    """Stage B cuts chains of bins where the gap exceeds max(cluster_merge_bnd, cluster_repeat_h_max) and verifies the stdev criterion afterwards
+    (k_verify_cuts).  With an absurd --cluster-r the criterion does fire across such gaps: the library must notice (unverified_breaks), run again
+    without cuts, and still return the reference's clusters (here 11 candidates instead of 456)."""
+    import oracle.oracle as orc
+    blk = synth.generate(77, [600000], 20.0, len_model=0, len_mean=20000.0, len_sd=2000.0, len_min=5000, len_max=60000, tech="ont", sv_spacing=1300.0,
+                         ins_only=True, tr_frac=0.0, clip_prob=0.0, sv_min=50, sv_max=400, threads=4)
+    cfg = abi.Config.from_sniffles(sconfig.default_config("--cluster-r", "2000"))
+    ctx = binding.Context(0)
+    try:
+        ctx.set_config(cfg)
+        ctx.load(blk)
+        got = ctx.run()
+        reruns = ctx.rerun_count()
+        again = ctx.run()                          # the decision is remembered for this block: no further re-run
+        assert ctx.rerun_count() == reruns
+    finally:
+        ctx.close()
+    want = orc.run(blk, cfg, 3, 4)
+    devcheck.assert_same(want, got)
+    devcheck.assert_same(want, again)
+    assert reruns >= 1 and len(got.cand) < 50
+
+
 def test_config3_hifi_mosaic():
     _run(synth.config_block(3, 0.003), "--mosaic")
 
