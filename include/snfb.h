@@ -7,6 +7,9 @@
  *
  *   snfb_load_records      <- pysam `bam.fetch()` iteration + AlignedSegment accessors
  *                             (leadprov.py:488, accessor list SURVEY.md §2)
+ *   snfb_load_bam          <- the same call site fed COMPRESSED BAM bytes: htslib's BGZF inflate, record decode, region
+ *                             filter and long-CIGAR (CG) escape behind `bam.fetch(contig, start, end)` run on the device
+ *                             (parallel.py:95-98, leadprov.py:488)
  *   snfb_extract_leads     <- LeadProvider.build_leadtab / iter_region / read_iterindels /
  *                             Lead.for_bnd / read_itersplits (leadprov.py:445-670),
  *                             sv.classify_splits (sv.py:649-782); call site parallel.py:90-102
@@ -315,6 +318,39 @@ int         snfb_consensus(snfb_ctx* ctx, snfb_seq_view* out);
  * a ctx, or a block unlike the previous one) is repeated with capacities that fit; snfb_rerun_count counts those.
  * The views (any may be NULL) are filled after the final synchronisation. */
 int         snfb_run(snfb_ctx* ctx, snfb_lead_view* leads, snfb_cand_view* cands, snfb_seq_view* seqs);
+/* ---- device BAM ingest: compressed BGZF bytes in, the packed record block built in device memory ----
+ * `bgzf` holds whole BGZF blocks back to back (host memory; any selection of a file's blocks, in file order).  A span is a
+ * record-aligned range of the inflated stream that belongs to one task, given the way a BAI index gives it: (byte offset of a
+ * BGZF block inside `bgzf`, offset inside that block's inflated data) for its begin and its end — i.e. a BAM virtual offset with
+ * the file offset rebased to `bgzf`.  cend == n_bytes with uend == 0 means "to the end of the buffer".  Spans are listed task by
+ * task in file order and must not overlap (merge the index chunks first, as htslib does); cutting a span at any record-aligned
+ * offset (the linear index of the BAI provides one per 16 kb window) only adds parallelism.  The library inflates every block
+ * (one warp per block), follows the block_size chain of every span, decodes the records, keeps those `bam.fetch(contig, start,
+ * end)` would return for the span's task (task.contig is the BAM reference id), restores CIGARs of more than 65535 operations
+ * from the CG:B,I tag, and writes snfb_rec + CIGAR16 + names/SA + 4-bit bases exactly as snfb_load_records expects them.
+ * The BGZF CRC32 is not verified (a corrupt block is caught by the DEFLATE decoder or the inflated size).  Tables (tasks, contigs,
+ * tandem repeats, N mask) have the meaning they have in snfb_records. */
+typedef struct snfb_bam_span {
+    uint64_t cbeg, cend;      /* byte offsets of BGZF block starts inside bgzf[] */
+    uint32_t ubeg, uend;      /* offsets inside those blocks' inflated data */
+    uint32_t task;
+    uint32_t _pad;
+} snfb_bam_span;
+typedef struct snfb_bam_input {
+    const uint8_t* bgzf; uint64_t n_bytes;
+    const snfb_bam_span* span; uint64_t n_span;
+    uint32_t n_task, n_contig, n_tr, n_mask;
+    const snfb_task* task; const snfb_contig* contig; const int32_t* tr; const int32_t* mask; const uint32_t* mask_task_off;
+} snfb_bam_input;
+int         snfb_load_bam(snfb_ctx* ctx, const snfb_bam_input* in);
+/* what the last snfb_load_bam built: out[0] records, out[1] CIGAR16 words, out[2] var bytes, out[3] seq bytes, out[4] raw records seen,
+ * out[5] BGZF blocks, out[6] inflated bytes, out[7] compressed bytes */
+int         snfb_ingest_sizes(snfb_ctx* ctx, uint64_t out[8]);
+/* copies the block snfb_load_bam built back to the host (tests / inspection); any pointer may be NULL */
+int         snfb_ingest_fetch(snfb_ctx* ctx, snfb_rec* rec, uint16_t* cigar16, uint8_t* var, uint8_t* seq);
+/* inflate whole BGZF blocks on the device and return the inflated stream (tests / inspection).  Returns 0 and *out_len = bytes;
+ * out may be NULL to get the size only. */
+int         snfb_inflate_bgzf(snfb_ctx* ctx, const uint8_t* bgzf, uint64_t n_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_len);
 /* device-time accounting of the last run: per-kernel milliseconds from CUDA events on
  * the ctx stream; names[i] is a static string.  Returns the number of entries. */
 int         snfb_last_timings(snfb_ctx* ctx, const char** names, float* ms, uint64_t* bytes, int cap);

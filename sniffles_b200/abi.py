@@ -52,6 +52,16 @@ class Records(C.Structure):
                 ("cigar_evt_min", C.c_uint32), ("_pad2", C.c_uint32)]
 
 
+SPAN_DTYPE = np.dtype([("cbeg", "<u8"), ("cend", "<u8"), ("ubeg", "<u4"), ("uend", "<u4"), ("task", "<u4"), ("_pad", "<u4")])      # snfb_bam_span
+assert SPAN_DTYPE.itemsize == 32
+
+
+class BamInput(C.Structure):                                    # snfb_bam_input
+    _fields_ = [("bgzf", C.c_void_p), ("n_bytes", C.c_uint64), ("span", C.c_void_p), ("n_span", C.c_uint64),
+                ("n_task", C.c_uint32), ("n_contig", C.c_uint32), ("n_tr", C.c_uint32), ("n_mask", C.c_uint32),
+                ("task", C.c_void_p), ("contig", C.c_void_p), ("tr", C.c_void_p), ("mask", C.c_void_p), ("mask_task_off", C.c_void_p)]
+
+
 class Config(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         "mapq", "min_alignment_length", "exclude_flags", "minsvlen", "minsvlen_screen", "long_ins_length",

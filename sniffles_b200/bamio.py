@@ -222,6 +222,90 @@ class BamFile:
                     yield r
             seen_to = max(seen_to, v)
 
+    # ---- device ingest (snfb_load_bam): the index work stays on the host, the bytes stay compressed
+    def merged_chunks(self, contig, start, end):
+        """disjoint, ascending virtual-offset ranges holding every record `fetch(contig, start, end)` would look at (the BAI chunks of
+        the region's bins behind the linear-index minimum, merged the way htslib merges them)"""
+        rid = self.name_to_id[contig]
+        bins, lin = self.index[rid]
+        min_off = lin[start >> 14] if (start >> 14) < len(lin) else (lin[-1] if lin else 0)
+        chunks = sorted(c for b in reg2bins(max(start, 0), max(end, start + 1)) if b in bins and b != 37450 for c in bins[b] if c[1] > min_off)
+        merged = []
+        for beg, stop in chunks:
+            beg = max(beg, min_off)
+            if merged and beg <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], stop)
+            else:
+                merged.append([beg, stop])
+        return [(a, b) for a, b in merged if b > a]
+
+    def _bsize_at(self, coffset):
+        """total size of the BGZF block that starts at a file offset (0 at end of file)"""
+        self.bgzf.f.seek(coffset)
+        head = self.bgzf.f.read(18)
+        if len(head) < 18:
+            return 0
+        xlen = struct.unpack("<H", head[10:12])[0]
+        extra = head[12:] + self.bgzf.f.read(max(xlen - 6, 0))
+        i = 0
+        while i + 4 <= len(extra):
+            slen = struct.unpack("<H", extra[i + 2:i + 4])[0]
+            if extra[i] == 66 and extra[i + 1] == 67:
+                return struct.unpack("<H", extra[i + 4:i + 6])[0] + 1
+            i += 4 + slen
+        raise ValueError("BGZF block without a BC field")
+
+    def device_input(self, regions, split=True):
+        """regions: [(contig, start, end)] = the tasks, in task order.  Returns (bgzf, spans): the compressed bytes of every BGZF block the
+        regions need (file order, each block once) and abi.SPAN_DTYPE rows — the merged index chunks of each task, cut at the linear
+        index's record-aligned offsets so that every ~16 kb window is its own parallel walk on the device."""
+        pieces = []                                      # (task, vbeg, vend)
+        for t, (contig, start, end) in enumerate(regions):
+            _, lin = self.index[self.name_to_id[contig]]
+            anchors = sorted(set(lin)) if split else []
+            for vb, ve in self.merged_chunks(contig, start, end):
+                cuts = [vb] + [a for a in anchors if vb < a < ve] + [ve]
+                pieces.extend((t, cuts[k], cuts[k + 1]) for k in range(len(cuts) - 1))
+        # file intervals [cb, ce) that hold the blocks of the pieces; a piece that ends inside a block needs that block too
+        iv, bs_cache = [], {}
+        for _, vb, ve in pieces:
+            cb, ce = vb >> 16, ve >> 16
+            if ve & 0xffff:
+                if ce not in bs_cache:
+                    bs_cache[ce] = self._bsize_at(ce)
+                ce += bs_cache[ce]
+            iv.append((cb, ce))
+        iv.sort()
+        merged = []
+        for a, b in iv:
+            if merged and a <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], b)
+            else:
+                merged.append([a, b])
+        starts, base, parts = [], [], []
+        off = 0
+        for a, b in merged:
+            self.bgzf.f.seek(a)
+            d = self.bgzf.f.read(b - a)
+            if len(d) != b - a:
+                raise ValueError("truncated BAM file")
+            starts.append(a)
+            base.append(off)
+            parts.append(d)
+            off += len(d)
+        bgzf = np.frombuffer(b"".join(parts), "u1") if parts else np.zeros(0, "u1")
+        import bisect
+
+        def to_buf(c):                                   # file offset of a block start (or of an interval's end) -> offset in bgzf
+            k = bisect.bisect_right(starts, c) - 1
+            if k < 0 or c > merged[k][1]:
+                raise ValueError("virtual offset outside the loaded intervals")
+            return base[k] + (c - starts[k])
+        spans = np.zeros(len(pieces), abi.SPAN_DTYPE)
+        for i, (t, vb, ve) in enumerate(pieces):
+            spans[i] = (to_buf(vb >> 16), to_buf(ve >> 16), vb & 0xffff, ve & 0xffff, t, 0)
+        return bgzf, spans
+
 
 def pack_records(contigs, recs, tasks, with_seq=True, tandem_repeats=None) -> RecordBlock:
     """records (already grouped by task, coordinate sorted inside a task) -> packed block of include/snfb.h.
@@ -264,16 +348,18 @@ def pack_records(contigs, recs, tasks, with_seq=True, tandem_repeats=None) -> Re
 
 
 # ------------------------------------------------------------------------------------------------ writer (tests / benchmark inputs)
-def _bgzf_block(data: bytes) -> bytes:
-    c = zlib.compressobj(6, zlib.DEFLATED, -15)
+def _bgzf_block(data: bytes, level: int = 6) -> bytes:
+    c = zlib.compressobj(level, zlib.DEFLATED, -15)
     comp = c.compress(data) + c.flush()
     bsize = len(comp) + 25
     return (b"\x1f\x8b\x08\x04\x00\x00\x00\x00\x00\xff\x06\x00BC\x02\x00" + struct.pack("<H", bsize) + comp
             + struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
 
 
-def write_bam(path, blk: RecordBlock, block_bytes=0xff00):
-    """packed block -> coordinate-sorted BAM + BAI (records keep the block's order; one contig per task).  Returns the paths."""
+def write_bam(path, blk: RecordBlock, block_bytes=0xff00, level=6, qual_seed=None):
+    """packed block -> coordinate-sorted BAM + BAI (records keep the block's order; one contig per task).  Returns the paths.
+    qual_seed: None writes the "qualities absent" bytes 0xff; an integer writes noisy phred values (what makes a real BAM hard to compress)."""
+    qrng = np.random.default_rng(qual_seed) if qual_seed is not None else None
     names = blk.contig_names
     text = b"@HD\tVN:1.6\tSO:coordinate\n" + b"".join(f"@SQ\tSN:{n}\tLN:{int(c['length'])}\n".encode() for n, c in zip(names, blk.contig))
     head = b"BAM\1" + struct.pack("<i", len(text)) + text + struct.pack("<i", len(names))
@@ -287,7 +373,7 @@ def write_bam(path, blk: RecordBlock, block_bytes=0xff00):
     def flush():
         nonlocal buf, coff
         if buf:
-            blk_b = _bgzf_block(bytes(buf))
+            blk_b = _bgzf_block(bytes(buf), level)
             out.write(blk_b)
             coff += len(blk_b)
             buf = bytearray()
@@ -332,7 +418,7 @@ def write_bam(path, blk: RecordBlock, block_bytes=0xff00):
             cig_b = struct.pack("<II", (l_seq << 4) | 4, ((end - pos) << 4) | 3)
             n_cig = 2
         body = struct.pack("<iiBBHHHiiii", rid, pos, len(qname), int(r["mapq"]), reg2bin(pos, end), n_cig, int(r["flag"]), l_seq, -1, -1, 0) \
-            + qname + cig_b + seq + b"\xff" * l_seq + aux
+            + qname + cig_b + seq + (b"\xff" * l_seq if qrng is None else np.clip(qrng.normal(22.0, 9.0, l_seq), 2, 50).astype("u1").tobytes()) + aux
         data = struct.pack("<i", len(body)) + body
         if len(buf) + len(data) > block_bytes:
             flush()

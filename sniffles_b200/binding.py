@@ -16,7 +16,8 @@ EXPORTS = ["snfb_version", "snfb_sizeof", "snfb_hash_name", "snfb_ctx_create", "
            "snfb_load_records", "snfb_extract_leads", "snfb_cluster_call", "snfb_consensus", "snfb_run",
            "snfb_last_timings", "snfb_device_candidates", "snfb_device_alt", "snfb_launch_count",
            "snfb_pin_host", "snfb_unpin_host", "snfb_pack_cigar16", "snfb_rerun_count", "snfb_coverage_bins",
-           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates", "snfb_selftest_sqrt_frac", "snfb_debug_dump", "snfb_poa", "snfb_combine_groups", "snfb_selftest_edit_distance"]
+           "snfb_nccl_unique_id", "snfb_comm_init", "snfb_allgather_candidates", "snfb_selftest_sqrt_frac", "snfb_debug_dump", "snfb_poa", "snfb_combine_groups", "snfb_selftest_edit_distance",
+           "snfb_load_bam", "snfb_ingest_sizes", "snfb_ingest_fetch", "snfb_inflate_bgzf"]
 
 
 def lib():
@@ -37,6 +38,10 @@ def lib():
         L.snfb_last_error.argtypes = [C.c_void_p]
         L.snfb_set_config.argtypes = [C.c_void_p, C.POINTER(abi.Config)]
         L.snfb_load_records.argtypes = [C.c_void_p, C.POINTER(abi.Records)]
+        L.snfb_load_bam.argtypes = [C.c_void_p, C.POINTER(abi.BamInput)]
+        L.snfb_ingest_sizes.argtypes = [C.c_void_p, C.c_void_p]
+        L.snfb_ingest_fetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.snfb_inflate_bgzf.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.snfb_extract_leads.argtypes = [C.c_void_p, C.POINTER(abi.LeadView)]
         L.snfb_cluster_call.argtypes = [C.c_void_p, C.POINTER(abi.CandView)]
         L.snfb_consensus.argtypes = [C.c_void_p, C.POINTER(abi.SeqView)]
@@ -164,6 +169,46 @@ class Context:
             rs.on_device = 2
         self._block = block          # keep host arrays alive during the async copy
         self._check(self._lib.snfb_load_records(self._h, C.byref(rs)), "snfb_load_records")
+
+    def load_bam(self, bgzf: np.ndarray, spans: np.ndarray, tables):
+        """Device BAM ingest (snfb_load_bam): `bgzf` = whole BGZF blocks (uint8), `spans` = abi.SPAN_DTYPE rows (bamio.BamFile.device_input
+        builds both from the BAI index), `tables` = anything with the task / contig / tr (/ mask) arrays of a RecordBlock.  The record block is
+        built in device memory; returns the sizes dict of snfb_ingest_sizes."""
+        bgzf = np.ascontiguousarray(bgzf, dtype="u1")
+        spans = np.ascontiguousarray(spans, dtype=abi.SPAN_DTYPE)
+        I = abi.BamInput()
+        I.bgzf, I.n_bytes, I.span, I.n_span = bgzf.ctypes.data, len(bgzf), spans.ctypes.data, len(spans)
+        I.n_task, I.n_contig, I.n_tr = len(tables.task), len(tables.contig), len(tables.tr) // 2
+        I.task, I.contig, I.tr = tables.task.ctypes.data, tables.contig.ctypes.data, tables.tr.ctypes.data
+        mask = getattr(tables, "mask", None)
+        if mask is not None and len(mask):
+            I.n_mask, I.mask, I.mask_task_off = len(mask) // 2, mask.ctypes.data, tables.mask_task_off.ctypes.data
+        self._block = tables
+        self._check(self._lib.snfb_load_bam(self._h, C.byref(I)), "snfb_load_bam")
+        return self.ingest_sizes()
+
+    def ingest_sizes(self):
+        out = np.zeros(8, "<u8")
+        if self._lib.snfb_ingest_sizes(self._h, out.ctypes.data) != 0:
+            raise SnfbError("snfb_ingest_sizes: no block was built by snfb_load_bam on this context")
+        return dict(zip(("n_rec", "n_cigar", "n_var", "n_seq", "n_raw", "n_blocks", "raw_bytes", "bgzf_bytes"), (int(x) for x in out)))
+
+    def ingest_fetch(self):
+        """host copies (rec, cigar16, var, seq) of the block snfb_load_bam built — tests and inspection"""
+        z = self.ingest_sizes()
+        rec, cig = np.zeros(z["n_rec"], abi.REC_DTYPE), np.zeros(z["n_cigar"], "<u2")
+        var, seq = np.zeros(z["n_var"], "u1"), np.zeros(z["n_seq"], "u1")
+        self._check(self._lib.snfb_ingest_fetch(self._h, rec.ctypes.data, cig.ctypes.data, var.ctypes.data, seq.ctypes.data), "snfb_ingest_fetch")
+        return rec, cig, var, seq
+
+    def inflate_bgzf(self, bgzf: np.ndarray) -> bytes:
+        """whole BGZF blocks -> their inflated bytes, decoded on the device (snfb_inflate_bgzf)"""
+        bgzf = np.ascontiguousarray(bgzf, dtype="u1")
+        n = C.c_uint64()
+        self._check(self._lib.snfb_inflate_bgzf(self._h, bgzf.ctypes.data, len(bgzf), None, 0, C.byref(n)), "snfb_inflate_bgzf")
+        out = np.zeros(max(int(n.value), 1), "u1")
+        self._check(self._lib.snfb_inflate_bgzf(self._h, bgzf.ctypes.data, len(bgzf), out.ctypes.data, len(out), C.byref(n)), "snfb_inflate_bgzf")
+        return out[:int(n.value)].tobytes()
 
     def run(self, want_leads=True, want_cands=True, want_seqs=True, copy=True) -> Result:
         lv, cv, sv = abi.LeadView(), abi.CandView(), abi.SeqView()

@@ -24,6 +24,7 @@
 #include "consensus.cuh"
 #include "poa.cuh"
 #include "combine.cuh"
+#include "ingest.cuh"
 
 struct DevBuf {
     void* p = nullptr; size_t cap = 0;
@@ -95,6 +96,7 @@ struct snfb_ctx {
     const snfb_rec* d_rec = nullptr; const uint16_t* d_cigar = nullptr; const uint8_t* d_var = nullptr; const uint8_t* d_seq = nullptr;
     DevBuf b_rec, b_cigar, b_var, b_seq, b_task, b_contig, b_tr, b_trp, b_mask, b_mask_off, b_mask_task;
     HostBuf h_c16, h_rec16;        // BAM32 host input converted to CIGAR16 before the upload
+    DevBuf b_comp, b_raw, b_ing; HostBuf h_ing; uint64_t ing_sizes[8] = {0, 0, 0, 0, 0, 0, 0, 0}; bool from_bam = false;      // device BAM ingest: BGZF bytes, inflated stream, work arrays
     std::vector<snfb_task> tasks;
     // capacities and the three arenas carved by them
     Caps cap; bool force_no_cuts = false;
@@ -257,10 +259,10 @@ void snfb_ctx_destroy(snfb_ctx* ctx) {
     cudaStreamSynchronize(ctx->st); cudaStreamSynchronize(ctx->st_copy); cudaStreamSynchronize(ctx->st_side);
     if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
     DevBuf* bufs[] = { &ctx->b_rec, &ctx->b_cigar, &ctx->b_var, &ctx->b_seq, &ctx->b_task, &ctx->b_contig, &ctx->b_tr, &ctx->b_trp, &ctx->b_mask, &ctx->b_mask_off, &ctx->b_mask_task,
-                       &ctx->b_ctr, &ctx->arena_r, &ctx->arena_l, &ctx->arena_c, &ctx->b_gsend, &ctx->b_grecv };
+                       &ctx->b_ctr, &ctx->arena_r, &ctx->arena_l, &ctx->arena_c, &ctx->b_gsend, &ctx->b_grecv, &ctx->b_comp, &ctx->b_raw, &ctx->b_ing };
     for (DevBuf* b : bufs) b->release();
     HostBuf* hb[] = { &ctx->h_c16, &ctx->h_rec16, &ctx->h_seq_req, &ctx->h_seq_arena, &ctx->h_ctr_buf, &ctx->h_leads, &ctx->h_task_reads, &ctx->h_task_nm, &ctx->h_rec_nm, &ctx->h_cand, &ctx->h_cand_leads,
-                      &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_task_cov_raw, &ctx->h_alt, &ctx->h_cov_bins, &ctx->h_gather };
+                      &ctx->h_rnames, &ctx->h_rn_off, &ctx->h_task_cov, &ctx->h_task_cov_raw, &ctx->h_alt, &ctx->h_cov_bins, &ctx->h_gather, &ctx->h_ing };
     for (HostBuf* b : hb) b->release();
     for (int i = 0; i <= MAX_TIMINGS; ++i) cudaEventDestroy(ctx->ev[i]);
     cudaEventDestroy(ctx->ev_b); cudaEventDestroy(ctx->ev_mid); cudaEventDestroy(ctx->ev_fork); cudaEventDestroy(ctx->ev_join);
@@ -337,14 +339,8 @@ __global__ void k_validate(const snfb_rec* __restrict__ rec, uint32_t n_rec, uin
     if (bad) atomicAdd(&ctr->bad_records, 1ULL);
 }
 
-int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
-    if (!ctx || !R) return 1;
-    cudaSetDevice(ctx->device);
-    ctx->loaded = false; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false; ctx->force_no_cuts = false;
-    if (R->n_task == 0 || R->n_task > 65535) return fail(ctx, "n_task must be in 1..65535");
-    if (R->n_rec > 0xfffffff0ull) return fail(ctx, "too many records in one block");
-    if (!R->task || (R->n_rec && (!R->rec || !R->cigar))) return fail(ctx, "null table in the record block");
-    // host-side checks of the small tables
+// host-side checks of the small tables of a block
+static int check_tables(snfb_ctx* ctx, const snfb_records* R) {
     for (uint32_t t = 0; t < R->n_task; ++t) {
         const snfb_task& k = R->task[t];
         if (k.tr_n < 0 || k.tr_off < 0 || (uint64_t)k.tr_off + (uint64_t)k.tr_n > R->n_tr) return fail(ctx, "task table: tandem-repeat range outside tr[]");
@@ -355,6 +351,44 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     if (R->n_mask && R->mask && R->mask_task_off) {
         for (uint32_t t = 0; t < R->n_task; ++t) if (R->mask_task_off[t] > R->mask_task_off[t + 1] || R->mask_task_off[t + 1] > R->n_mask) return fail(ctx, "mask_task_off must be non-decreasing and end at n_mask");
     }
+    return 0;
+}
+// task / contig / tandem-repeat / N-mask tables -> device
+static int upload_tables(snfb_ctx* ctx, const snfb_records* R) {
+    ctx->tasks.assign(R->task, R->task + R->n_task);
+    if (ctx->b_task.ensure(sizeof(snfb_task) * R->n_task) || ctx->b_contig.ensure(sizeof(snfb_contig) * (R->n_contig + 1)) || ctx->b_tr.ensure(8 * ((size_t)R->n_tr + 1)) || ctx->b_trp.ensure(4 * ((size_t)R->n_tr + 1)))
+        return fail(ctx, "out of device memory for the task tables");
+    CUDA_TRY(cudaMemcpyAsync(ctx->b_task.p, R->task, sizeof(snfb_task) * R->n_task, cudaMemcpyHostToDevice, ctx->st));
+    if (R->n_contig) CUDA_TRY(cudaMemcpyAsync(ctx->b_contig.p, R->contig, sizeof(snfb_contig) * R->n_contig, cudaMemcpyHostToDevice, ctx->st));
+    if (R->n_tr) {
+        // running maximum of the interval ends per task: makes the reference's forward-only scan (cluster.py:240-246) a binary search
+        std::vector<int32_t> pm(R->n_tr);
+        for (uint32_t t = 0; t < R->n_task; ++t) { int32_t m = INT32_MIN; for (int k = 0; k < R->task[t].tr_n; ++k) { const int idx = R->task[t].tr_off + k; if (R->tr[2 * idx + 1] > m) m = R->tr[2 * idx + 1]; pm[idx] = m; } }
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_tr.p, R->tr, 8 * (size_t)R->n_tr, cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_trp.p, pm.data(), 4 * (size_t)R->n_tr, cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaStreamSynchronize(ctx->st));     // pm is a stack-owned staging vector
+    }
+    ctx->n_mask = (R->mask && R->mask_task_off) ? R->n_mask : 0;
+    if (ctx->n_mask) {
+        std::vector<uint32_t> mt(ctx->n_mask);
+        for (uint32_t t = 0; t < R->n_task; ++t) for (uint32_t m = R->mask_task_off[t]; m < R->mask_task_off[t + 1] && m < ctx->n_mask; ++m) mt[m] = t;
+        if (ctx->b_mask.ensure(8 * (size_t)ctx->n_mask) || ctx->b_mask_off.ensure(4 * ((size_t)R->n_task + 1)) || ctx->b_mask_task.ensure(4 * (size_t)ctx->n_mask)) return fail(ctx, "out of device memory (N mask)");
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask.p, R->mask, 8 * (size_t)ctx->n_mask, cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask_off.p, R->mask_task_off, 4 * ((size_t)R->n_task + 1), cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask_task.p, mt.data(), 4 * (size_t)ctx->n_mask, cudaMemcpyHostToDevice, ctx->st));
+        CUDA_TRY(cudaStreamSynchronize(ctx->st));
+    }
+    return 0;
+}
+
+int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
+    if (!ctx || !R) return 1;
+    cudaSetDevice(ctx->device);
+    ctx->loaded = false; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false; ctx->force_no_cuts = false;
+    if (R->n_task == 0 || R->n_task > 65535) return fail(ctx, "n_task must be in 1..65535");
+    if (R->n_rec > 0xfffffff0ull) return fail(ctx, "too many records in one block");
+    if (!R->task || (R->n_rec && (!R->rec || !R->cigar))) return fail(ctx, "null table in the record block");
+    if (check_tables(ctx, R)) return 1;
     ctx->n_rec = R->n_rec; ctx->n_cigar = R->n_cigar; ctx->n_var = R->n_var; ctx->n_seq = R->n_seq;
     ctx->n_task = R->n_task; ctx->n_contig = R->n_contig; ctx->n_tr = R->n_tr; ctx->on_device = R->on_device == SNFB_MEM_DEVICE; ctx->seq_on_demand = R->on_device == SNFB_MEM_HOST_SEQ_ON_DEMAND; ctx->h_seq = ctx->seq_on_demand ? R->seq : nullptr;
     ctx->n_ev = 0;
@@ -385,32 +419,190 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
         if (!ctx->seq_on_demand) CUDA_TRY(cudaMemcpyAsync(ctx->b_seq.p, R->seq, R->n_seq, cudaMemcpyHostToDevice, ctx->st));
         ctx->d_rec = ctx->b_rec.as<snfb_rec>(); ctx->d_cigar = ctx->b_cigar.as<uint16_t>(); ctx->d_var = ctx->b_var.as<uint8_t>(); ctx->d_seq = ctx->b_seq.as<uint8_t>();
     }
-    ctx->tasks.assign(R->task, R->task + R->n_task);
-    if (ctx->b_task.ensure(sizeof(snfb_task) * R->n_task) || ctx->b_contig.ensure(sizeof(snfb_contig) * (R->n_contig + 1)) || ctx->b_tr.ensure(8 * ((size_t)R->n_tr + 1)) || ctx->b_trp.ensure(4 * ((size_t)R->n_tr + 1)))
-        return fail(ctx, "out of device memory for the task tables");
-    CUDA_TRY(cudaMemcpyAsync(ctx->b_task.p, R->task, sizeof(snfb_task) * R->n_task, cudaMemcpyHostToDevice, ctx->st));
-    if (R->n_contig) CUDA_TRY(cudaMemcpyAsync(ctx->b_contig.p, R->contig, sizeof(snfb_contig) * R->n_contig, cudaMemcpyHostToDevice, ctx->st));
-    if (R->n_tr) {
-        // running maximum of the interval ends per task: makes the reference's forward-only scan (cluster.py:240-246) a binary search
-        std::vector<int32_t> pm(R->n_tr);
-        for (uint32_t t = 0; t < R->n_task; ++t) { int32_t m = INT32_MIN; for (int k = 0; k < R->task[t].tr_n; ++k) { const int idx = R->task[t].tr_off + k; if (R->tr[2 * idx + 1] > m) m = R->tr[2 * idx + 1]; pm[idx] = m; } }
-        CUDA_TRY(cudaMemcpyAsync(ctx->b_tr.p, R->tr, 8 * (size_t)R->n_tr, cudaMemcpyHostToDevice, ctx->st));
-        CUDA_TRY(cudaMemcpyAsync(ctx->b_trp.p, pm.data(), 4 * (size_t)R->n_tr, cudaMemcpyHostToDevice, ctx->st));
-        CUDA_TRY(cudaStreamSynchronize(ctx->st));     // pm is a stack-owned staging vector
-    }
-    ctx->n_mask = (R->mask && R->mask_task_off) ? R->n_mask : 0;
-    if (ctx->n_mask) {
-        std::vector<uint32_t> mt(ctx->n_mask);
-        for (uint32_t t = 0; t < R->n_task; ++t) for (uint32_t m = R->mask_task_off[t]; m < R->mask_task_off[t + 1] && m < ctx->n_mask; ++m) mt[m] = t;
-        if (ctx->b_mask.ensure(8 * (size_t)ctx->n_mask) || ctx->b_mask_off.ensure(4 * ((size_t)R->n_task + 1)) || ctx->b_mask_task.ensure(4 * (size_t)ctx->n_mask)) return fail(ctx, "out of device memory (N mask)");
-        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask.p, R->mask, 8 * (size_t)ctx->n_mask, cudaMemcpyHostToDevice, ctx->st));
-        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask_off.p, R->mask_task_off, 4 * ((size_t)R->n_task + 1), cudaMemcpyHostToDevice, ctx->st));
-        CUDA_TRY(cudaMemcpyAsync(ctx->b_mask_task.p, mt.data(), 4 * (size_t)ctx->n_mask, cudaMemcpyHostToDevice, ctx->st));
-        CUDA_TRY(cudaStreamSynchronize(ctx->st));
-    }
+    if (upload_tables(ctx, R)) return 1;
     mark(ctx, nullptr);
     ctx->n_ev_load = ctx->n_ev;
     ctx->loaded = true; return 0;
+}
+
+
+// ---- device BAM ingest ----
+// BGZF block headers of a buffer of whole blocks (SAM spec §4.1): payload offset / length, inflated size, start of every block
+static int walk_bgzf(snfb_ctx* ctx, const uint8_t* z, uint64_t n, std::vector<ingest::BgzfBlock>& blocks, std::vector<uint64_t>& cstart, uint64_t* raw_len) {
+    uint64_t o = 0, uo = 0;
+    while (o < n) {
+        if (o + 18 > n || z[o] != 0x1f || z[o + 1] != 0x8b || z[o + 2] != 8 || !(z[o + 3] & 4)) return fail(ctx, "not a BGZF block (gzip member with an extra field expected)");
+        const uint32_t xlen = z[o + 10] | (z[o + 11] << 8);
+        if (o + 12 + xlen > n) return fail(ctx, "truncated BGZF header");
+        uint32_t bsize = 0; uint64_t e = o + 12; const uint64_t xend = o + 12 + xlen;
+        while (e + 4 <= xend) { const uint32_t slen = z[e + 2] | (z[e + 3] << 8); if (z[e] == 66 && z[e + 1] == 67 && slen == 2 && e + 6 <= xend) bsize = (z[e + 4] | (z[e + 5] << 8)) + 1u; e += 4 + slen; }
+        if (!bsize || bsize < 12 + xlen + 8 || o + bsize > n) return fail(ctx, "BGZF block without a BC field or truncated");
+        ingest::BgzfBlock b; b.in_off = o + 12 + xlen; b.in_len = bsize - 12 - xlen - 8;
+        memcpy(&b.isize, z + o + bsize - 4, 4); b.out_off = uo;
+        if (b.isize > 65536u) return fail(ctx, "BGZF block claims more than 64 KiB of data");
+        blocks.push_back(b); cstart.push_back(o);
+        uo += b.isize; o += bsize;
+    }
+    *raw_len = uo; return 0;
+}
+static int inflate_to_device(snfb_ctx* ctx, const uint8_t* z, uint64_t n, std::vector<uint64_t>& cstart, std::vector<ingest::BgzfBlock>& blocks, uint64_t* raw_len) {
+    if (walk_bgzf(ctx, z, n, blocks, cstart, raw_len)) return 1;
+    if (*raw_len >= (1ull << 36)) return fail(ctx, "more than 64 GiB of inflated BAM in one ingest call: split the task list");
+    if (ctx->b_comp.ensure(n + 64) || ctx->b_raw.ensure(*raw_len + 64)) return fail(ctx, "out of device memory for the BGZF bytes / the inflated stream");
+    mark(ctx, "h2d_bgzf", n);
+    CUDA_TRY(cudaMemcpyAsync(ctx->b_comp.p, z, n, cudaMemcpyHostToDevice, ctx->st));
+    CUDA_TRY(cudaMemsetAsync(ctx->b_comp.as<uint8_t>() + n, 0, 64, ctx->st));
+    CUDA_TRY(cudaMemsetAsync(ctx->b_raw.as<uint8_t>() + *raw_len, 0, 64, ctx->st));
+    return 0;
+}
+
+int snfb_inflate_bgzf(snfb_ctx* ctx, const uint8_t* bgzf, uint64_t n_bytes, uint8_t* out, uint64_t out_cap, uint64_t* out_len) {
+    if (!ctx || !bgzf || !out_len) return 1;
+    cudaSetDevice(ctx->device);
+    std::vector<ingest::BgzfBlock> blocks; std::vector<uint64_t> cstart; uint64_t raw_len = 0;
+    ctx->n_ev = 0;
+    if (inflate_to_device(ctx, bgzf, n_bytes, cstart, blocks, &raw_len)) return 1;
+    *out_len = raw_len;
+    const size_t nb = blocks.size();
+    if (ctx->b_ing.ensure(256 + sizeof(ingest::BgzfBlock) * (nb + 1))) return fail(ctx, "out of device memory (ingest tables)");
+    ingest::IngestCounters* d_ctr = ctx->b_ing.as<ingest::IngestCounters>(); ingest::BgzfBlock* d_blk = reinterpret_cast<ingest::BgzfBlock*>(ctx->b_ing.as<uint8_t>() + 256);
+    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(ingest::IngestCounters), ctx->st));
+    CUDA_TRY(cudaMemcpyAsync(d_blk, blocks.data(), sizeof(ingest::BgzfBlock) * nb, cudaMemcpyHostToDevice, ctx->st));
+    mark(ctx, "inflate", n_bytes + raw_len);
+    if (nb) { ingest::k_inflate<<<(unsigned)std::min<size_t>((nb + ingest::INF_WARPS - 1) / ingest::INF_WARPS, 148 * 8), ingest::INF_WARPS * 32, 0, ctx->st>>>(ctx->b_comp.as<uint8_t>(), d_blk, (unsigned)nb, ctx->b_raw.as<uint8_t>(), d_ctr); LAUNCHED(ctx, 1); }
+    mark(ctx, nullptr);
+    ingest::IngestCounters hc;
+    CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, ctx->st));
+    CUDA_TRY(cudaStreamSynchronize(ctx->st));
+    if (hc.bad_blocks) return fail(ctx, "inflate: " + std::to_string(hc.bad_blocks) + " BGZF block(s) failed to decode (first: block " + std::to_string(hc.first_bad_block) + ", code " + std::to_string(hc.first_bad_code) + ")");
+    if (out) {
+        if (out_cap < raw_len) return fail(ctx, "snfb_inflate_bgzf: output buffer too small");
+        CUDA_TRY(cudaMemcpy(out, ctx->b_raw.p, raw_len, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+int snfb_load_bam(snfb_ctx* ctx, const snfb_bam_input* in) {
+    if (!ctx || !in) return 1;
+    cudaSetDevice(ctx->device);
+    ctx->loaded = false; ctx->from_bam = false; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false; ctx->force_no_cuts = false;
+    if (in->n_task == 0 || in->n_task > 65535) return fail(ctx, "n_task must be in 1..65535");
+    if (!in->task || (in->n_bytes && !in->bgzf) || (in->n_span && !in->span)) return fail(ctx, "null table in the BAM input");
+    snfb_records T; memset(&T, 0, sizeof(T));
+    T.n_task = in->n_task; T.n_contig = in->n_contig; T.n_tr = in->n_tr; T.n_mask = in->n_mask; T.task = in->task; T.contig = in->contig; T.tr = in->tr; T.mask = in->mask; T.mask_task_off = in->mask_task_off;
+    if (check_tables(ctx, &T)) return 1;
+    ctx->n_ev = 0;
+    std::vector<ingest::BgzfBlock> blocks; std::vector<uint64_t> cstart; uint64_t raw_len = 0;
+    if (inflate_to_device(ctx, in->bgzf, in->n_bytes, cstart, blocks, &raw_len)) return 1;
+    const size_t nb = blocks.size(); const uint64_t ns = in->n_span;
+    // spans: virtual offsets -> offsets in the inflated stream
+    std::vector<ingest::Span> spans(ns);
+    for (uint64_t i = 0; i < ns; ++i) {
+        const snfb_bam_span& sp = in->span[i];
+        if (sp.task >= in->n_task) return fail(ctx, "span: task index out of range");
+        auto resolve = [&](uint64_t c, uint32_t u, uint64_t* out) -> bool {
+            if (c == in->n_bytes) { *out = raw_len; return u == 0; }
+            auto it = std::lower_bound(cstart.begin(), cstart.end(), c);
+            if (it == cstart.end() || *it != c) return false;
+            const ingest::BgzfBlock& b = blocks[(size_t)(it - cstart.begin())];
+            if (u > b.isize) return false;
+            *out = b.out_off + u; return true;
+        };
+        uint64_t ub = 0, ue = 0;
+        if (!resolve(sp.cbeg, sp.ubeg, &ub) || !resolve(sp.cend, sp.uend, &ue) || ue < ub) return fail(ctx, "span: a virtual offset does not name a BGZF block of the buffer");
+        if (i && spans[i - 1].task > sp.task) return fail(ctx, "spans must be listed task by task");
+        if (i && spans[i - 1].task == sp.task && spans[i - 1].uend > ub) return fail(ctx, "spans of a task must be in file order and must not overlap");
+        spans[i].ubeg = ub; spans[i].uend = ue; spans[i].task = sp.task; spans[i]._pad = 0;
+    }
+    if (upload_tables(ctx, &T)) return 1;
+    // fixed part of the work area
+    Carver m0; ingest::IngestCounters* d_ctr = nullptr; ingest::BgzfBlock* d_blk = nullptr; ingest::Span* d_span = nullptr; uint32_t* span_cnt = nullptr; uint32_t* span_base = nullptr; uint32_t* scan_tmp0 = nullptr;
+    auto carve0 = [&](Carver& c) { d_ctr = c.take<ingest::IngestCounters>(1); d_blk = c.take<ingest::BgzfBlock>(nb + 1); d_span = c.take<ingest::Span>(ns + 1); span_cnt = c.take<uint32_t>(ns + 1); span_base = c.take<uint32_t>(ns + 1); scan_tmp0 = c.take<uint32_t>(prims::scan_tmp_elems(ns + 1) + 16); };
+    carve0(m0);
+    if (ctx->b_ing.ensure(m0.off + 256)) return fail(ctx, "out of device memory (ingest tables)");
+    { Carver a; a.base = ctx->b_ing.as<uint8_t>(); carve0(a); }
+    cudaStream_t st = ctx->st; const uint8_t* raw = ctx->b_raw.as<uint8_t>();
+    CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(ingest::IngestCounters), st));
+    CUDA_TRY(cudaMemcpyAsync(d_blk, blocks.data(), sizeof(ingest::BgzfBlock) * nb, cudaMemcpyHostToDevice, st));
+    if (ns) CUDA_TRY(cudaMemcpyAsync(d_span, spans.data(), sizeof(ingest::Span) * ns, cudaMemcpyHostToDevice, st));
+    mark(ctx, "inflate", in->n_bytes + raw_len);
+    if (nb) { ingest::k_inflate<<<(unsigned)std::min<size_t>((nb + ingest::INF_WARPS - 1) / ingest::INF_WARPS, 148 * 8), ingest::INF_WARPS * 32, 0, st>>>(ctx->b_comp.as<uint8_t>(), d_blk, (unsigned)nb, ctx->b_raw.as<uint8_t>(), d_ctr); LAUNCHED(ctx, 1); }
+    mark(ctx, "walk_records", 0);
+    if (ns) {
+        ingest::k_walk<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(raw, raw_len, d_span, (unsigned)ns, 0, span_cnt, nullptr, nullptr, 0, d_ctr); LAUNCHED(ctx, 1);
+        LAUNCHED(ctx, prims::exclusive_scan(span_cnt, span_base, scan_tmp0, nullptr, ns, &d_ctr->n_raw, st));
+    }
+    if (ctx->h_ing.ensure(2 * sizeof(ingest::IngestCounters))) return fail(ctx, "out of pinned memory");
+    ingest::IngestCounters* hc = ctx->h_ing.as<ingest::IngestCounters>();
+    CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, sizeof(*hc), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    if (hc->bad_blocks) return fail(ctx, "inflate: " + std::to_string(hc->bad_blocks) + " BGZF block(s) failed to decode (first: block " + std::to_string(hc->first_bad_block) + ", code " + std::to_string(hc->first_bad_code) + ")");
+    if (hc->bad_chain) return fail(ctx, "BAM record chain broken in " + std::to_string(hc->bad_chain) + " span(s): a span does not start or end on a record boundary, or the data is truncated");
+    const uint64_t n_raw = hc->n_raw;
+    if (n_raw > 0xfffffff0ull) return fail(ctx, "too many records in one block");
+    // per-raw-record work arrays live behind the fixed part
+    ingest::RawRec* recs = nullptr; uint32_t *keep = nullptr, *idx = nullptr, *groups = nullptr, *grp_off = nullptr, *var16 = nullptr, *var_off = nullptr, *seq16 = nullptr, *seq_off = nullptr, *scan_tmp = nullptr;
+    auto carve1 = [&](Carver& c) { carve0(c); recs = c.take<ingest::RawRec>(n_raw + 1); keep = c.take<uint32_t>(n_raw + 1); idx = c.take<uint32_t>(n_raw + 1); groups = c.take<uint32_t>(n_raw + 1); grp_off = c.take<uint32_t>(n_raw + 1);
+                                   var16 = c.take<uint32_t>(n_raw + 1); var_off = c.take<uint32_t>(n_raw + 1); seq16 = c.take<uint32_t>(n_raw + 1); seq_off = c.take<uint32_t>(n_raw + 1); scan_tmp = c.take<uint32_t>(prims::scan_tmp_elems(n_raw + 1) + 16); };
+    Carver m1; carve1(m1);
+    if (m1.off + 256 > ctx->b_ing.cap) {
+        // grow without losing the fixed part: a new buffer, the fixed part copied over
+        DevBuf nbuf; if (nbuf.ensure(m1.off + 256)) return fail(ctx, "out of device memory (ingest work arrays)");
+        CUDA_TRY(cudaMemcpyAsync(nbuf.p, ctx->b_ing.p, m0.off, cudaMemcpyDeviceToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        ctx->b_ing.release(); ctx->b_ing = nbuf;
+    }
+    { Carver a; a.base = ctx->b_ing.as<uint8_t>(); carve1(a); }
+    const uint32_t evt = evt_need(ctx);
+    uint64_t n_rec = 0, n_groups = 0, n_var16 = 0, n_seq16 = 0;
+    if (n_raw) {
+        const unsigned warp_grid = (unsigned)std::min<uint64_t>((n_raw + 7) / 8, 148ull * 16);
+        ingest::k_walk<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(raw, raw_len, d_span, (unsigned)ns, 1, span_cnt, span_base, recs, n_raw, d_ctr);
+        mark(ctx, "parse_records", 0);
+        ingest::k_parse<<<(unsigned)((n_raw + 127) / 128), 128, 0, st>>>(raw, recs, (unsigned)n_raw, ctx->b_task.as<snfb_task>(), d_ctr);
+        mark(ctx, "record_sizes", 0);
+        ingest::k_rec_sizes<<<warp_grid, 256, 0, st>>>(raw, recs, (unsigned)n_raw, ctx->b_task.as<snfb_task>(), evt, keep, groups, var16, seq16, d_ctr); LAUNCHED(ctx, 3);
+        LAUNCHED(ctx, prims::exclusive_scan(keep, idx, scan_tmp, nullptr, n_raw, &d_ctr->n_keep, st));
+        LAUNCHED(ctx, prims::exclusive_scan(groups, grp_off, scan_tmp, nullptr, n_raw, &d_ctr->n_groups, st));
+        LAUNCHED(ctx, prims::exclusive_scan(var16, var_off, scan_tmp, nullptr, n_raw, &d_ctr->n_var, st));
+        LAUNCHED(ctx, prims::exclusive_scan(seq16, seq_off, scan_tmp, nullptr, n_raw, &d_ctr->n_seq16, st));
+        CUDA_TRY(cudaMemcpyAsync(hc, d_ctr, sizeof(*hc), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (hc->malformed || hc->bad_cigar) return fail(ctx, std::to_string(hc->malformed) + " malformed BAM record(s), " + std::to_string(hc->bad_cigar) + " with a CIGAR operation the path does not know");
+        n_rec = hc->n_keep; n_groups = hc->n_groups; n_var16 = hc->n_var; n_seq16 = hc->n_seq16;
+    }
+    const uint64_t n_words = 8 * n_groups + 8;               // one zero group of slack after the last record (as snfb_pack_cigar16)
+    if (ctx->b_rec.ensure(sizeof(snfb_rec) * (n_rec + 1)) || ctx->b_cigar.ensure(2 * (n_words + 16)) || ctx->b_var.ensure(16 * n_var16 + 16) || ctx->b_seq.ensure(16 * n_seq16 + 16))
+        return fail(ctx, "out of device memory for the record block");
+    mark(ctx, "pack_records", sizeof(snfb_rec) * n_rec + 2 * n_words + 16 * n_var16 + 16 * n_seq16);
+    CUDA_TRY(cudaMemsetAsync(ctx->b_cigar.as<uint16_t>() + 8 * n_groups, 0, 2 * 24, st));
+    if (n_raw) {
+        const unsigned warp_grid = (unsigned)std::min<uint64_t>((n_raw + 7) / 8, 148ull * 16);
+        ingest::k_pack<<<warp_grid, 256, 0, st>>>(raw, recs, (unsigned)n_raw, evt, keep, idx, grp_off, groups, var_off, seq_off, ctx->b_rec.as<snfb_rec>(), ctx->b_cigar.as<uint16_t>(), ctx->b_var.as<uint8_t>(), ctx->b_seq.as<uint8_t>()); LAUNCHED(ctx, 1);
+    }
+    mark(ctx, nullptr);
+    ctx->n_ev_load = ctx->n_ev;
+    ctx->n_rec = n_rec; ctx->n_cigar = n_words; ctx->n_var = 16 * n_var16; ctx->n_seq = 16 * n_seq16; ctx->n_task = in->n_task; ctx->n_contig = in->n_contig; ctx->n_tr = in->n_tr;
+    ctx->on_device = false; ctx->seq_on_demand = false; ctx->h_seq = nullptr; ctx->evt_min = evt;
+    ctx->d_rec = ctx->b_rec.as<snfb_rec>(); ctx->d_cigar = ctx->b_cigar.as<uint16_t>(); ctx->d_var = ctx->b_var.as<uint8_t>(); ctx->d_seq = ctx->b_seq.as<uint8_t>();
+    ctx->ing_sizes[0] = n_rec; ctx->ing_sizes[1] = n_words; ctx->ing_sizes[2] = 16 * n_var16; ctx->ing_sizes[3] = 16 * n_seq16; ctx->ing_sizes[4] = n_raw; ctx->ing_sizes[5] = nb; ctx->ing_sizes[6] = raw_len; ctx->ing_sizes[7] = in->n_bytes;
+    CUDA_TRY(cudaStreamSynchronize(st));
+    ctx->loaded = true; ctx->from_bam = true; return 0;
+}
+
+int snfb_ingest_sizes(snfb_ctx* ctx, uint64_t out[8]) {
+    if (!ctx || !out || !ctx->from_bam) return 1;
+    for (int i = 0; i < 8; ++i) out[i] = ctx->ing_sizes[i];
+    return 0;
+}
+int snfb_ingest_fetch(snfb_ctx* ctx, snfb_rec* rec, uint16_t* cigar16, uint8_t* var, uint8_t* seq) {
+    if (!ctx || !ctx->from_bam || !ctx->loaded) return ctx ? fail(ctx, "snfb_ingest_fetch: no block built by snfb_load_bam") : 1;
+    cudaSetDevice(ctx->device);
+    if (rec && ctx->n_rec) CUDA_TRY(cudaMemcpy(rec, ctx->d_rec, sizeof(snfb_rec) * ctx->n_rec, cudaMemcpyDeviceToHost));
+    if (cigar16 && ctx->n_cigar) CUDA_TRY(cudaMemcpy(cigar16, ctx->d_cigar, 2 * ctx->n_cigar, cudaMemcpyDeviceToHost));
+    if (var && ctx->n_var) CUDA_TRY(cudaMemcpy(var, ctx->d_var, ctx->n_var, cudaMemcpyDeviceToHost));
+    if (seq && ctx->n_seq) CUDA_TRY(cudaMemcpy(seq, ctx->d_seq, ctx->n_seq, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 }  // extern "C"

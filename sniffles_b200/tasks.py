@@ -89,20 +89,28 @@ class Task:
     task_index: int = 0
     coverage_average_total: float = 0.0
     device: int = 0
+    device_ingest: bool = True      # a task that reads its own BAM region ships the COMPRESSED bytes: inflate + record decode on the GPU (snfb_load_bam)
 
     # ---- the reference's way: Task(id, sv_id, contig, start, end, config, bam=..., tandem_repeats=...) and a worker (parallel.py:47-60, 741-746)
-    def _own_block(self):
-        """records of [start, end) from the task's BAM (`self.bam`: an open bamio.BamFile or a path; default config.input), packed for the device"""
-        from . import bamio
+    def _open(self):
         bam = self.bam if self.bam is not None else getattr(self.config, "input", None)
         if isinstance(bam, str):
             bam = open_bam(bam)
         if bam is None:
             raise RuntimeError("Task has neither a block_run nor a BAM to read its region from")
+        return bam
+
+    def _tables(self, bam, recs=()):
+        from . import bamio
         cidx = bam.name_to_id[self.contig]
-        recs = [(0, r) for r in bam.fetch(self.contig, self.start, self.end)]
         tr = {0: [(int(a), int(b)) for a, b in self.tandem_repeats]} if self.tandem_repeats else None
-        return bamio.pack_records(bam.contigs, recs, [(cidx, int(self.start), int(self.end), int(self.id))], tandem_repeats=tr)
+        return bamio.pack_records(bam.contigs, list(recs), [(cidx, int(self.start), int(self.end), int(self.id))], tandem_repeats=tr)
+
+    def _own_block(self):
+        """records of [start, end) from the task's BAM (`self.bam`: an open bamio.BamFile or a path; default config.input), decoded and
+        packed on the HOST (device_ingest=False; also what the tests compare the device ingest with)"""
+        bam = self._open()
+        return self._tables(bam, [(0, r) for r in bam.fetch(self.contig, self.start, self.end)])
 
     def _ctx(self):
         return device_context(self.device)
@@ -117,12 +125,21 @@ class Task:
         """parallel.py:90-102 — returns (externals, read_count).  Leads outside the region are dropped on the
         device, exactly as the caller discards `externals` (parallel.py:264)."""
         if self.block_run is None:
-            block = self._own_block()
             ctx = self._ctx()
             ctx.set_config(abi.Config.from_sniffles(self.config))
-            ctx.load(block, cigar16=False)                       # BAM words: the library converts them (snfb_load_records)
+            if self.device_ingest:
+                # the reference's `bam.fetch(contig, start, end)` (parallel.py:95-98, leadprov.py:488) with htslib's work on the GPU: the host
+                # only resolves the BAI index; BGZF inflate, record decode, region filter and CIGAR16 packing are snfb_load_bam
+                bam = self._open()
+                block = self._tables(bam)
+                bgzf, spans = bam.device_input([(self.contig, int(self.start), int(self.end))])
+                n_rec = ctx.load_bam(bgzf, spans, block)["n_rec"]
+            else:
+                block = self._own_block()
+                ctx.load(block, cigar16=False)                   # BAM words: the library converts them (snfb_load_records)
+                n_rec = len(block.rec)
             res = ctx.extract_leads()                            # snfb_extract_leads
-            rec_nm = abi.view(res._rec_nm_ptr, "<f8", len(block.rec)).copy() if getattr(res, "_rec_nm_ptr", None) else None
+            rec_nm = abi.view(res._rec_nm_ptr, "<f8", n_rec).copy() if getattr(res, "_rec_nm_ptr", None) else None
             self.block_run = BlockRun(block, res, None, rec_nm)
             self.task_index = 0
             self._staged = True

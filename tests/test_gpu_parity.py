@@ -204,10 +204,11 @@ def test_calltask_from_bam_region(tmp_path):
         tr = [(int(blk.tr[2 * (o + k)]), int(blk.tr[2 * (o + k) + 1])) for k in range(n)]
         want = tasks.CallTask(id=t, sv_id=0, contig=name, start=0, end=int(tk["end"]), config=sconfig.default_config(), block_run=br, task_index=t)
         w_calls, w_reads = want.execute()
-        got = tasks.CallTask(id=t, sv_id=0, contig=name, start=0, end=int(tk["end"]), config=sconfig.default_config(), bam=path, tandem_repeats=tr)
-        g_calls, g_reads = got.execute(Worker())
-        assert got.device == 5 % tasks.gpu_count()
-        assert g_reads == w_reads and len(g_calls) == len(w_calls) > 5
-        for a, b in zip(g_calls, w_calls):
-            assert (a.svtype, a.pos, a.end, a.svlen, a.support, a.filter, a.alt, a.id) == (b.svtype, b.pos, b.end, b.svlen, b.support, b.filter, b.alt, b.id)
-            assert a.genotypes == b.genotypes and a.info == b.info
+        for device_ingest in (True, False):            # compressed bytes decoded on the GPU (snfb_load_bam) / host reader + snfb_load_records
+            got = tasks.CallTask(id=t, sv_id=0, contig=name, start=0, end=int(tk["end"]), config=sconfig.default_config(), bam=path, tandem_repeats=tr, device_ingest=device_ingest)
+            g_calls, g_reads = got.execute(Worker())
+            assert got.device == 5 % tasks.gpu_count()
+            assert g_reads == w_reads and len(g_calls) == len(w_calls) > 5
+            for a, b in zip(g_calls, w_calls):
+                assert (a.svtype, a.pos, a.end, a.svlen, a.support, a.filter, a.alt, a.id) == (b.svtype, b.pos, b.end, b.svlen, b.support, b.filter, b.alt, b.id)
+                assert a.genotypes == b.genotypes and a.info == b.info

@@ -1,0 +1,157 @@
+"""Device BAM ingest, the parts checkable without a GPU: the DEFLATE decoder, the BAM record decoder and the CIGAR16
+converter of sniffles_b200/csrc/ingest_core.h in their one-lane host build, against zlib and the host reader; and the index work of
+bamio.device_input (merged chunks, spans cut at the linear index, compressed-block selection)."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+import ingest_emul
+from sniffles_b200 import abi, bamio, binding, synth
+
+
+def _streams():
+    rnd = random.Random(7)
+    yield b""
+    yield b"a"
+    yield b"abc" * 3000
+    yield b"\0" * 65280
+    yield bytes(rnd.getrandbits(8) for _ in range(65280))
+    yield bytes(rnd.choice(b"ACGT") for _ in range(65280))
+    yield open(__file__, "rb").read()
+    for _ in range(12):
+        n, alpha = rnd.randint(1, 65280), rnd.randint(1, 255)
+        yield bytes(rnd.randint(0, alpha) for _ in range(n))
+
+
+def test_inflate_equals_zlib():
+    """stored, fixed and dynamic blocks, long codes (more than 9 bits), run-length code lengths, overlapping matches"""
+    n = 0
+    for data in _streams():
+        for level in (0, 1, 6, 9):
+            for strat in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                c = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strat)
+                comp = c.compress(data) + c.flush()
+                rc, out = ingest_emul.inflate(comp, len(data))
+                assert rc == 0 and out == data, (len(data), level, strat)
+                n += 1
+    assert n > 300
+
+
+def test_inflate_rejects_corrupt_streams():
+    data = open(__file__, "rb").read()
+    comp = zlib.compress(data)[2:-4]
+    rnd = random.Random(5)
+    for _ in range(200):
+        b = bytearray(comp)
+        b[rnd.randrange(len(b))] ^= 1 << rnd.randrange(8)
+        rc, out = ingest_emul.inflate(bytes(b), len(data))
+        try:
+            want = zlib.decompress(bytes(b), -15)
+        except zlib.error:
+            want = None
+        if want is not None and len(want) == len(data):
+            assert rc == 0 and out == want                 # a flip zlib tolerates (padding bits, an unused code) decodes the same way
+        else:
+            assert rc != 0 or out != data
+    rc, _ = ingest_emul.inflate(comp, len(data) - 1)          # output smaller than the stream produces
+    assert rc != 0
+    rc, _ = ingest_emul.inflate(comp[:len(comp) // 2], len(data))      # truncated input
+    assert rc != 0
+
+
+@pytest.fixture(scope="module")
+def bam(tmp_path_factory):
+    blk = synth.generate(77, [260_000, 150_000, 90_000], 14.0, len_mean=9000.0, len_sd=2500.0, sv_spacing=5000.0, phased_frac=0.5)
+    path = str(tmp_path_factory.mktemp("ingest") / "t.bam")
+    bamio.write_bam(path, blk)
+    return blk, path
+
+
+def _same(dev, host, evt_min=11):
+    assert len(dev) == len(host)
+    recs = [(0, h) for h in host]
+    for d, h in zip(dev, host):
+        assert (d["pos"], d["flag"], d["mapq"], d["l_seq"], d["qname"]) == (h["pos"], h["flag"], h["mapq"], h["l_seq"], bytes(h["qname"]))
+        assert (d["cigar"] == h["cigar"]).all() and (d["seq"] == h["seq"]).all()
+        a = h["aux"]
+        assert (d["nm"], d["hp"], d["ps"], d["sa"]) == (a.get("NM"), a.get("HP"), a.get("PS"), a.get("SA"))
+    # CIGAR16 words: the layout snfb_pack_cigar16 writes
+    if host:
+        rec = np.zeros(len(host), abi.REC_DTYPE)
+        off = 0
+        for i, h in enumerate(host):
+            rec[i]["cigar_off"], rec[i]["n_cigar"] = off, len(h["cigar"])
+            off += len(h["cigar"])
+        rec16, c16 = binding.pack_cigar16(rec, np.concatenate([h["cigar"] for h in host]), evt_min)
+        for d, r in zip(dev, rec16):
+            o, n = int(r["cigar_off"]), int(r["n_cigar"])
+            assert d["n_words"] == n and (d["cigar16"][:n] == c16[o:o + n]).all() and not d["cigar16"][n:].any()
+
+
+def test_whole_contigs_equal_host_reader(bam):
+    blk, path = bam
+    f = bamio.BamFile(path)
+    regions = [(n, 0, f.get_reference_length(n)) for n in blk.contig_names]
+    bgzf, spans = f.device_input(regions)
+    assert len(spans) > 3 * len(regions)                    # cut at the linear index: many parallel walks
+    task = np.zeros(len(regions), abi.TASK_DTYPE)
+    for t, (n, a, b) in enumerate(regions):
+        task[t] = (t, a, b, b, t, 0, 0, 0)
+    dev = ingest_emul.load_bam(bgzf, spans, task)
+    for t, (n, a, b) in enumerate(regions):
+        _same([d for d in dev if d["task"] == t], list(f.fetch(n, a, b)))
+    assert len(dev) == len(blk.rec)
+    f.close()
+
+
+def test_regions_equal_host_fetch(bam):
+    """region tasks: records that overlap two regions appear in both, unsplit spans give the same records as split ones"""
+    blk, path = bam
+    f = bamio.BamFile(path)
+    rnd = np.random.default_rng(11)
+    regions = []
+    for _ in range(12):
+        t = int(rnd.integers(0, 3))
+        L = f.get_reference_length(blk.contig_names[t])
+        a = int(rnd.integers(0, L - 1000))
+        regions.append((blk.contig_names[t], a, min(L, a + int(rnd.integers(1, 70000)))))
+    regions.append((blk.contig_names[0], 250_000, 260_000))
+    task = np.zeros(len(regions), abi.TASK_DTYPE)
+    for t, (n, a, b) in enumerate(regions):
+        task[t] = (f.name_to_id[n], a, b, f.get_reference_length(n), t, 0, 0, 0)
+    for split in (True, False):
+        bgzf, spans = f.device_input(regions, split=split)
+        dev = ingest_emul.load_bam(bgzf, spans, task)
+        for t, (n, a, b) in enumerate(regions):
+            _same([d for d in dev if d["task"] == t], list(f.fetch(n, a, b)))
+    small, _ = f.device_input([(blk.contig_names[1], 40_000, 45_000)])
+    assert len(small) < 0.25 * len(open(path, "rb").read())      # only the blocks a region touches are shipped
+    f.close()
+
+
+def test_long_cigar_and_wide_ops(tmp_path):
+    """the CG:B,I escape (more than 65535 ops) and operations of 2^11 / 2^23 bases and more (extension words, group padding)"""
+    n = 70000
+    cig = np.empty(n, "<u4"); cig[0::2] = (3 << 4) | 0; cig[1::2] = (1 << 4) | 2
+    l_seq = 3 * (n // 2)
+    wide = np.array([(5 << 4) | 4, (2047 << 4) | 0, (2048 << 4) | 2, (7 << 4) | 0, (9_000_000 << 4) | 3, (1 << 4) | 7, (3000 << 4) | 1, (1 << 4) | 8, (2 << 4) | 8, (40 << 4) | 1, (4000 << 4) | 4], "<u4")
+    l2 = 5 + 2047 + 7 + 1 + 3000 + 1 + 2 + 40 + 4000
+    rec = np.zeros(2, abi.REC_DTYPE)
+    rec[0] = (0, 100, 0, 60, abi.AUX_NM, 0, 2, 0, 5, 0, n, l_seq, 0, 0, 0, 0, 0)
+    rec[1] = (0, 200, 16, 33, abi.AUX_NM | abi.AUX_HP | abi.AUX_PS | abi.AUX_SA, 2, 3, 0, 77, 12345, len(wide), l2, 21, 0, n, (l_seq + 1) // 2, 2)
+    contig = np.zeros(1, abi.CONTIG_DTYPE); contig[0] = (abi.fnv1a64(b"c"), 20_000_000, 0)
+    task = np.zeros(1, abi.TASK_DTYPE); task[0] = (0, 0, 20_000_000, 20_000_000, 0, 0, 0, 0)
+    var = np.frombuffer(b"rd" + b"abc" + b"c,500,+,100M50S,60,3;", "u1")
+    blk = synth.RecordBlock(rec=rec, cigar=np.concatenate([cig, wide]), var=var, seq=np.full((l_seq + 1) // 2 + (l2 + 1) // 2, 0x12, "u1"), task=task, contig=contig,
+                            tr=np.zeros(0, "<i4"), contig_names=["c"])
+    path = str(tmp_path / "long.bam")
+    bamio.write_bam(path, blk)
+    f = bamio.BamFile(path)
+    bgzf, spans = f.device_input([("c", 0, 20_000_000)])
+    dev = ingest_emul.load_bam(bgzf, spans, task)
+    host = list(f.fetch("c", 0, 20_000_000))
+    assert len(host) == 2 and len(host[0]["cigar"]) == n
+    _same(dev, host)
+    f.close()
