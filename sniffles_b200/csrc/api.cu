@@ -101,9 +101,9 @@ struct snfb_ctx {
     // capacities and the three arenas carved by them
     Caps cap; bool force_no_cuts = false;
     DevBuf b_ctr, arena_r, arena_l, arena_c;            // counters; per-record arrays; per-lead arrays (stages A + B); stage C
-    uint64_t arena_r_for = 0; Caps arena_l_for, arena_c_for; uint32_t arena_r_tasks = 0;
+    uint64_t arena_r_for = 0, arena_r_cigar = 0; Caps arena_l_for, arena_c_for; uint32_t arena_r_tasks = 0;
     // per-record (arena_r)
-    uint32_t* pass_flag; uint32_t* pass_groups; uint32_t* pidx; uint32_t* vst; extract::PDesc* pdesc; uint32_t* pvs;
+    uint32_t* pass_chunks; uint32_t* choff; uint32_t* rec_foff; uint32_t* rec_nf; uint2* cdesc; uint2* csum; uint32_t* flist; uint2* fcnt; unsigned long long chunk_cap = 0;      // the chunk table of the CIGAR walk (extract.cuh)
     int32_t* rec_pos; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead; uint32_t* rec_lead_off; uint32_t* sa_list; extract::RecScan* scanrec; extract::RecClip* clip; int32_t* rec_big;
     uint32_t* task_first; uint32_t* task_last; uint32_t* task_reads; unsigned long long* task_cov; int32_t* task_span; double* task_nm; double* nm_part; unsigned* nm_cnt; extract::Seg* sa_seg; uint32_t* scan_tmp_r;
     // per-lead (arena_l): stage A leads + the whole of stage B
@@ -217,6 +217,22 @@ __global__ void k_gather_merge(const uint8_t* recv, unsigned long long cap, int 
         b_cand += h.n_cand; b_alt += h.n_alt; b_rn += h.n_rn; b_leads += h.n_leads;
     }
     if (tid == 0) reinterpret_cast<uint32_t*>(out + o_ro)[tot.n_cand] = (uint32_t)tot.n_rn;
+}
+
+// lanes per BGZF block of the DEFLATE kernel: SNFB_INFLATE_LANES = 32, 16 or 8 (measured default below)
+template <int NL> static void launch_inflate_nl(snfb_ctx* ctx, const ingest::BgzfBlock* d_blk, unsigned nb, ingest::IngestCounters* d_ctr) {
+    static bool attr = false;
+    const size_t smem = ingest::inflate_smem_bytes<NL>();
+    if (!attr) { cudaFuncSetAttribute(ingest::k_inflate<NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    const unsigned per_block = ingest::INF_WARPS * (32 / NL);
+    const unsigned resident = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (smem + 1024)));
+    const unsigned grid = std::min<unsigned>((nb + per_block - 1) / per_block, 148u * resident);
+    ingest::k_inflate<NL><<<grid, ingest::INF_WARPS * 32, smem, ctx->st>>>(ctx->b_comp.as<uint8_t>(), d_blk, nb, ctx->b_raw.as<uint8_t>(), d_ctr);
+}
+static void launch_inflate(snfb_ctx* ctx, const ingest::BgzfBlock* d_blk, unsigned nb, ingest::IngestCounters* d_ctr) {
+    static int lanes = 0;
+    if (!lanes) { const char* e = getenv("SNFB_INFLATE_LANES"); lanes = e ? atoi(e) : 16; if (lanes != 32 && lanes != 16 && lanes != 8) lanes = 16; }
+    if (lanes == 32) launch_inflate_nl<32>(ctx, d_blk, nb, d_ctr); else if (lanes == 16) launch_inflate_nl<16>(ctx, d_blk, nb, d_ctr); else launch_inflate_nl<8>(ctx, d_blk, nb, d_ctr);
 }
 
 extern "C" {
@@ -386,7 +402,7 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     cudaSetDevice(ctx->device);
     ctx->loaded = false; ctx->stage_a_done = ctx->stage_b_done = ctx->stage_c_done = false; ctx->force_no_cuts = false;
     if (R->n_task == 0 || R->n_task > 65535) return fail(ctx, "n_task must be in 1..65535");
-    if (R->n_rec > 0xfffffff0ull) return fail(ctx, "too many records in one block");
+    if (R->n_rec >= (1ull << 28)) return fail(ctx, "too many records in one block (2^28)");
     if (!R->task || (R->n_rec && (!R->rec || !R->cigar))) return fail(ctx, "null table in the record block");
     if (check_tables(ctx, R)) return 1;
     ctx->n_rec = R->n_rec; ctx->n_cigar = R->n_cigar; ctx->n_var = R->n_var; ctx->n_seq = R->n_seq;
@@ -469,7 +485,7 @@ int snfb_inflate_bgzf(snfb_ctx* ctx, const uint8_t* bgzf, uint64_t n_bytes, uint
     CUDA_TRY(cudaMemsetAsync(d_ctr, 0, sizeof(ingest::IngestCounters), ctx->st));
     CUDA_TRY(cudaMemcpyAsync(d_blk, blocks.data(), sizeof(ingest::BgzfBlock) * nb, cudaMemcpyHostToDevice, ctx->st));
     mark(ctx, "inflate", n_bytes + raw_len);
-    if (nb) { ingest::k_inflate<<<(unsigned)std::min<size_t>((nb + ingest::INF_WARPS - 1) / ingest::INF_WARPS, 148 * 8), ingest::INF_WARPS * 32, 0, ctx->st>>>(ctx->b_comp.as<uint8_t>(), d_blk, (unsigned)nb, ctx->b_raw.as<uint8_t>(), d_ctr); LAUNCHED(ctx, 1); }
+    if (nb) { launch_inflate(ctx, d_blk, (unsigned)nb, d_ctr); LAUNCHED(ctx, 1); }
     mark(ctx, nullptr);
     ingest::IngestCounters hc;
     CUDA_TRY(cudaMemcpyAsync(&hc, d_ctr, sizeof(hc), cudaMemcpyDeviceToHost, ctx->st));
@@ -526,7 +542,7 @@ int snfb_load_bam(snfb_ctx* ctx, const snfb_bam_input* in) {
     CUDA_TRY(cudaMemcpyAsync(d_blk, blocks.data(), sizeof(ingest::BgzfBlock) * nb, cudaMemcpyHostToDevice, st));
     if (ns) CUDA_TRY(cudaMemcpyAsync(d_span, spans.data(), sizeof(ingest::Span) * ns, cudaMemcpyHostToDevice, st));
     mark(ctx, "inflate", in->n_bytes + raw_len);
-    if (nb) { ingest::k_inflate<<<(unsigned)std::min<size_t>((nb + ingest::INF_WARPS - 1) / ingest::INF_WARPS, 148 * 8), ingest::INF_WARPS * 32, 0, st>>>(ctx->b_comp.as<uint8_t>(), d_blk, (unsigned)nb, ctx->b_raw.as<uint8_t>(), d_ctr); LAUNCHED(ctx, 1); }
+    if (nb) { launch_inflate(ctx, d_blk, (unsigned)nb, d_ctr); LAUNCHED(ctx, 1); }
     mark(ctx, "walk_records", 0);
     if (ns) {
         ingest::k_walk<<<(unsigned)((ns + 127) / 128), 128, 0, st>>>(raw, raw_len, d_span, (unsigned)ns, 0, span_cnt, nullptr, nullptr, 0, d_ctr); LAUNCHED(ctx, 1);
@@ -539,7 +555,7 @@ int snfb_load_bam(snfb_ctx* ctx, const snfb_bam_input* in) {
     if (hc->bad_blocks) return fail(ctx, "inflate: " + std::to_string(hc->bad_blocks) + " BGZF block(s) failed to decode (first: block " + std::to_string(hc->first_bad_block) + ", code " + std::to_string(hc->first_bad_code) + ")");
     if (hc->bad_chain) return fail(ctx, "BAM record chain broken in " + std::to_string(hc->bad_chain) + " span(s): a span does not start or end on a record boundary, or the data is truncated");
     const uint64_t n_raw = hc->n_raw;
-    if (n_raw > 0xfffffff0ull) return fail(ctx, "too many records in one block");
+    if (n_raw >= (1ull << 28)) return fail(ctx, "too many records in one block (2^28)");
     // per-raw-record work arrays live behind the fixed part
     ingest::RawRec* recs = nullptr; uint32_t *keep = nullptr, *idx = nullptr, *groups = nullptr, *grp_off = nullptr, *var16 = nullptr, *var_off = nullptr, *seq16 = nullptr, *seq_off = nullptr, *scan_tmp = nullptr;
     auto carve1 = [&](Carver& c) { carve0(c); recs = c.take<ingest::RawRec>(n_raw + 1); keep = c.take<uint32_t>(n_raw + 1); idx = c.take<uint32_t>(n_raw + 1); groups = c.take<uint32_t>(n_raw + 1); grp_off = c.take<uint32_t>(n_raw + 1);
@@ -611,7 +627,9 @@ int snfb_ingest_fetch(snfb_ctx* ctx, snfb_rec* rec, uint16_t* cigar16, uint8_t* 
 static void carve_r(snfb_ctx* ctx, Carver& c) {
     const size_t n = ctx->n_rec + 1, nt = ctx->n_task;
     ctx->rec_pos = c.take<int32_t>(n); ctx->rec_end = c.take<int32_t>(n); ctx->rec_flags = c.take<uint8_t>(n); ctx->rec_nm = c.take<double>(n); ctx->rec_nlead = c.take<uint32_t>(n); ctx->rec_lead_off = c.take<uint32_t>(n);
-    ctx->pass_flag = c.take<uint32_t>(n); ctx->pass_groups = c.take<uint32_t>(n); ctx->pidx = c.take<uint32_t>(n); ctx->vst = c.take<uint32_t>(n); ctx->pdesc = c.take<extract::PDesc>(n); ctx->pvs = c.take<uint32_t>(n + 1);
+    ctx->pass_chunks = c.take<uint32_t>(n); ctx->choff = c.take<uint32_t>(n); ctx->rec_foff = c.take<uint32_t>(n); ctx->rec_nf = c.take<uint32_t>(n);
+    // a record of g groups has ceil(g / CH) chunks: at most g / CH + 1
+    ctx->chunk_cap = ctx->n_cigar / (8ull * extract::CH) + ctx->n_rec + 1; { const size_t nc = (size_t)ctx->chunk_cap + 1; ctx->cdesc = c.take<uint2>(nc); ctx->csum = c.take<uint2>(nc); ctx->flist = c.take<uint32_t>(nc); ctx->fcnt = c.take<uint2>(nc); }
     ctx->sa_list = c.take<uint32_t>(n); ctx->scanrec = c.take<extract::RecScan>(n); ctx->clip = c.take<extract::RecClip>(n); ctx->rec_big = c.take<int32_t>(n);
     ctx->task_first = c.take<uint32_t>(nt); ctx->task_last = c.take<uint32_t>(nt); ctx->task_reads = c.take<uint32_t>(nt); ctx->task_cov = c.take<unsigned long long>(nt); ctx->task_span = c.take<int32_t>(nt); ctx->task_nm = c.take<double>(nt);
     const size_t cpt = (ctx->n_rec + extract::NM_CHUNK - 1) / extract::NM_CHUNK + 1;
@@ -647,11 +665,11 @@ static void carve_c(snfb_ctx* ctx, Carver& c) {
     ctx->seq_req = c.take<consensus::SeqReq>(k.req + 1); ctx->seq_arena = c.take<uint8_t>(k.req16 * 16 + 64);
 }
 static int ensure_arenas(snfb_ctx* ctx) {
-    if (ctx->arena_r_for != ctx->n_rec + 1 || ctx->arena_r_tasks != ctx->n_task || !ctx->arena_r.p) {
+    if (ctx->arena_r_for != ctx->n_rec + 1 || ctx->arena_r_tasks != ctx->n_task || ctx->arena_r_cigar != ctx->n_cigar || !ctx->arena_r.p) {
         Carver m; carve_r(ctx, m);
         if (ctx->arena_r.ensure(m.off + 256)) return fail(ctx, "out of device memory (per-record arrays)");
         Carver a; a.base = ctx->arena_r.as<uint8_t>(); carve_r(ctx, a);
-        ctx->arena_r_for = ctx->n_rec + 1; ctx->arena_r_tasks = ctx->n_task;
+        ctx->arena_r_for = ctx->n_rec + 1; ctx->arena_r_tasks = ctx->n_task; ctx->arena_r_cigar = ctx->n_cigar;
     }
     if (ctx->arena_l_for.lead != ctx->cap.lead || !ctx->arena_l.p) {
         Carver m; carve_l(ctx, m);
@@ -693,8 +711,10 @@ static int enqueue_stage_a(snfb_ctx* ctx) {
     CUDA_TRY(cudaMemsetAsync(ctx->task_first, 0, 4 * nt, st)); CUDA_TRY(cudaMemsetAsync(ctx->task_last, 0, 4 * nt, st));
     CUDA_TRY(cudaMemsetAsync(ctx->task_reads, 0, 4 * nt, st)); CUDA_TRY(cudaMemsetAsync(ctx->task_cov, 0, 8 * nt, st)); CUDA_TRY(cudaMemsetAsync(ctx->task_span, 0, 4 * nt, st));
     CUDA_TRY(cudaMemsetAsync(ctx->task_nm, 0, 8 * nt, st));
-    extract::ScanParams S{};
-    S.pdesc = ctx->pdesc; S.pvs = ctx->pvs; S.cigar = ctx->d_cigar; S.task = b.task; S.rec_end = ctx->rec_end; S.rec_nlead = ctx->rec_nlead; S.rec_big = ctx->rec_big;
+    extract::ChunkParams S{};
+    S.scan = ctx->scanrec; S.choff = ctx->choff; S.n_rec = (uint32_t)nrec; S.cigar = ctx->d_cigar; S.task = b.task; S.cdesc = ctx->cdesc; S.csum = ctx->csum; S.flist = ctx->flist; S.fcnt = ctx->fcnt;
+    S.rec_foff = ctx->rec_foff; S.rec_nf = ctx->rec_nf; S.n_chunks = &ctr->n_chunks; S.n_flag = &ctr->n_flagged; S.chunk_cap = ctx->chunk_cap;
+    S.rec_end = ctx->rec_end; S.rec_nlead = ctx->rec_nlead; S.rec_big = ctx->rec_big;
     S.ev = ctx->ev_buf; S.ev_cap = ctx->cap.lead; S.n_ev = &ctr->n_ev; S.sa_list = ctx->sa_list; S.n_sa = &ctr->n_sa; S.ctr = ctr; S.minsv = cf.minsvlen_screen;
     if (evt_need(ctx) < ctx->evt_min) {
         // the block's E bits were set for longer events than this configuration looks at: lower the threshold in place
@@ -709,16 +729,18 @@ static int enqueue_stage_a(snfb_ctx* ctx) {
         I.rec = ctx->d_rec; I.cigar = ctx->d_cigar; I.task = b.task; I.n_rec = (uint32_t)nrec; I.n_task = nt; I.rec_pos = ctx->rec_pos; I.task_first = ctx->task_first; I.task_last = ctx->task_last;
         I.scan = ctx->scanrec; I.clip = ctx->clip; I.rec_end = ctx->rec_end; I.rec_flags = ctx->rec_flags; I.rec_nm = ctx->rec_nm; I.rec_nlead = ctx->rec_nlead; I.ctr = ctr;
         I.mapq_min = cf.mapq; I.alen_min = cf.min_alignment_length; I.excl = cf.exclude_flags; I.want_nm = (cf.qc_nm_measure || cf.phase) ? 1 : 0; I.n_cigar = ctx->n_cigar;
-        I.pass_flag = ctx->pass_flag; I.pass_groups = ctx->pass_groups;
+        I.pass_chunks = ctx->pass_chunks;
         extract::k_rec_index<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(I);
-        // sweep order of the streaming kernel: ordinal and first virtual group of every passing record
-        LAUNCHED(ctx, prims::exclusive_scan(ctx->pass_flag, ctx->pidx, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_passrec, st));
-        LAUNCHED(ctx, prims::exclusive_scan(ctx->pass_groups, ctx->vst, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_vgroups, st));
-        extract::PDescParams D{}; D.scan = ctx->scanrec; D.pidx = ctx->pidx; D.vst = ctx->vst; D.n_rec = (uint32_t)nrec; D.pdesc = ctx->pdesc; D.pvs = ctx->pvs; D.ctr = ctr;
-        extract::k_pdesc<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(D); LAUNCHED(ctx, 1);
-        // algorithmic bytes of the streaming kernel: scan descriptors + CIGAR16 words (+ its per-record outputs and event slices, added by bench.py)
-        mark(ctx, "k_scan", sizeof(extract::RecScan) * nrec + 2 * ctx->n_cigar);
-        extract::k_scan<<<148 * 8, 256, 0, st>>>(S);
+        // the chunk table: every passing record's CIGAR16 groups in chunks of CH, one thread of the streaming kernel per chunk
+        LAUNCHED(ctx, prims::exclusive_scan(ctx->pass_chunks, ctx->choff, ctx->scan_tmp_r, nullptr, nrec, &ctr->n_chunks, st));
+        extract::k_cdesc<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(S); LAUNCHED(ctx, 2);
+        // algorithmic bytes of the streaming kernel: chunk descriptors + CIGAR16 words + its per-chunk sums (bench.py adds the last two from the counters)
+        mark(ctx, "k_scan", 2 * ctx->n_cigar);
+        extract::k_chunk_sum<<<148 * 8, 256, 0, st>>>(S);
+        mark(ctx, "k_scan_rare");
+        extract::k_rec_base<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(S);
+        extract::k_chunk_rare<<<148 * 8, 128, 0, st>>>(S);
+        extract::k_rec_fin<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(S); LAUNCHED(ctx, 4);
         mark(ctx, "k_rec_post");
         extract::PostParams Q{};
         Q.scan = I.scan; Q.clip = I.clip; Q.task = b.task; Q.n_rec = (uint32_t)nrec; Q.rec_end = ctx->rec_end; Q.rec_big = ctx->rec_big; Q.rec_nm = ctx->rec_nm;
@@ -726,7 +748,7 @@ static int enqueue_stage_a(snfb_ctx* ctx) {
         extract::k_rec_post<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(Q);
         mark(ctx, "k_emit");
         extract::EmitParams E{};
-        E.rec = ctx->d_rec; E.clip = ctx->clip; E.var = ctx->d_var; E.ev = S.ev; E.n_ev = S.n_ev; E.ev_cap = ctx->cap.lead;
+        E.rec = ctx->d_rec; E.clip = ctx->clip; E.var = ctx->d_var; E.ev = S.ev; E.n_ev = S.n_ev; E.ev_cap = ctx->cap.lead; E.fcnt = ctx->fcnt;
         E.leads = ctx->leads; E.ctr = ctr; E.maxlen = cf.dev_seq_cache_maxlen; E.detect_large_ins = cf.detect_large_ins; E.longinslen = (double)cf.long_ins_length / 2.0;
         extract::k_emit<<<148 * 16, 128, 0, st>>>(E);
         mark(ctx, "k_sa");

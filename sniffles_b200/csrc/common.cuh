@@ -24,9 +24,9 @@ struct DevCounters {
     unsigned long long unverified_breaks;
     unsigned long long n_alt_bytes, n_seq_bytes, scratch_overflow;
     unsigned long long n_slots;        // high-water mark of the lead slot allocator (>= n_leads: warps reserve chunks)
-    unsigned long long n_ev, n_sa;     // event slices / records with an SA tag found by k_scan
+    unsigned long long n_ev, n_sa;     // SV signatures found by the CIGAR walk / records with an SA tag
     unsigned long long n_kl, n_kll;    // kept leads / kept "long" leads
-    unsigned long long n_passrec, n_vgroups;   // passing records / their 16-byte CIGAR16 groups (the streaming kernel's sweep space)
+    unsigned long long n_chunks, n_flagged;    // chunks of the CIGAR walk (CH 16-byte groups of one passing record each) / chunks holding an E-flagged or extension word
     unsigned long long n_big, n_mid;   // clusters handled by a whole block / by the mid-sized warp kernel
     unsigned long long ordinal_overflow;   // reads with more than 65535 leads (the ordinal is a 16-bit field)
     unsigned long long bad_records;    // records whose offsets point outside the block's arenas or tables (snfb_load_records fails)

@@ -240,13 +240,12 @@ __device__ __noinline__ unsigned process_sa(const snfb_config* __restrict__ cfgp
 // Stage A kernels:
 //   k_rec_index (thread per record): task boundaries, sortedness, and everything that only needs the record core and the
 //           clip ops at the two ends of its CIGAR: query_alignment_start/end, the read filters of iter_region, the
-//           16-byte scan descriptor k_scan streams from and the clip facts k_emit / k_sa use.
-//   k_scan  (hot, HBM-bound): one warp per passing record streams its CIGAR16 words once (16-byte loads, 256 words per
-//           warp step): reference end, the NM correction, lead counts — and for every 256-word slice that holds an SV
-//           signature one 32-byte "event slice" entry.  No lead is built here.
+//           16-byte scan descriptor and the clip facts k_emit / k_sa use, the record's chunk count.
+//   k_cdesc / k_chunk_sum (hot, HBM-bound) / k_rec_base / k_chunk_rare / k_rec_fin: the CIGAR walk, see "stage A streaming: chunks" below:
+//           reference end, the NM correction, lead counts, and one 32-byte Event per SV signature.  No lead is built here.
 //   k_rec_post (thread per record): nm per read (the division), per-task read count / covered bases / longest span.
-//   k_emit  one warp per event slice: reload the slice (L2), prefix positions, write the 64-byte leads to exact slots.
-//   k_sa    one warp per record with an SA tag: Lead.for_bnd + read_itersplits (lane-serial text parsing).
+//   k_emit  one thread per Event: the 64-byte lead.
+//   k_sa    one thread per record with an SA tag: Lead.for_bnd + read_itersplits.
 // ================================================================================================
 // CIGAR16 (include/snfb.h): base word = [15] 0 | [14] E | [13:11] class | [10:0] length & 0x7ff; class bit 0 (word bit 11) = advances the
 // read, class bit 1 (word bit 12) = advances the reference; E = an I / D / S of at least the block's event length (what the streaming
@@ -277,7 +276,9 @@ __device__ __forceinline__ void c16_decode8(const uint32_t (&ww)[4], unsigned (&
     }
 }
 
-struct RecScan { uint32_t cig8; uint32_t n_words; int32_t pos; uint32_t meta; };    // what k_scan needs, one 16-byte load
+struct RecScan { uint32_t cig8; uint32_t n_words; int32_t pos; uint32_t meta; };    // what the CIGAR walk needs of a record, one 16-byte load
+constexpr int CH = 16;                                                              // 16-byte groups per chunk of the streaming pass (k_chunk_sum)
+__host__ __device__ __forceinline__ uint32_t chunks_of(uint32_t n_words) { return (((n_words + 7u) >> 3) + (uint32_t)CH - 1u) / (uint32_t)CH; }
 struct RecClip { int32_t alen, qas, clip_left, clip_right; };                        // query_alignment_length/start, first / last op if it is a clip
 constexpr uint32_t RM_PASS = 1u << 24, RM_HAS_NM = 1u << 25, RM_HAS_SA = 1u << 26;   // RecScan.meta: task (0..15) | mapq (16..23) | flags | hp (27..28)
 
@@ -285,7 +286,7 @@ struct IndexParams {
     const snfb_rec* rec; const uint16_t* cigar; const snfb_task* task; uint32_t n_rec; uint32_t n_task; unsigned long long n_cigar;
     int32_t* rec_pos; uint32_t* task_first; uint32_t* task_last;
     RecScan* scan; RecClip* clip; int32_t* rec_end; uint8_t* rec_flags; double* rec_nm; uint32_t* rec_nlead;
-    uint32_t* pass_flag; uint32_t* pass_groups;      // 1 / number of 16-byte CIGAR16 groups for a passing record, else 0 (scanned into the sweep order)
+    uint32_t* pass_chunks;      // number of chunks (CH 16-byte CIGAR16 groups each) of a passing record, else 0 (scanned into the chunk table)
     DevCounters* ctr; int mapq_min, alen_min, excl, want_nm;
 };
 // leadprov.py:488-516 (filters), pysam query_alignment_start / query_alignment_end
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     if ((uint32_t)task >= P.n_task || (cigar_off & 7) || cigar_off + n > P.n_cigar) {      // malformed record (counted by k_validate: the run fails); touch nothing through its offsets
         RecScan s; s.cig8 = 0; s.n_words = 0; s.pos = pos; s.meta = 0; *reinterpret_cast<uint4*>(P.scan + i) = *reinterpret_cast<const uint4*>(&s);
         RecClip c; c.alen = 0; c.qas = 0; c.clip_left = 0; c.clip_right = 0; *reinterpret_cast<int4*>(P.clip + i) = *reinterpret_cast<const int4*>(&c);
-        P.rec_pos[i] = pos; P.rec_flags[i] = 0; P.rec_nm[i] = -1.0; P.rec_end[i] = -1; P.rec_nlead[i] = 0; P.pass_flag[i] = 0; P.pass_groups[i] = 0; return;
+        P.rec_pos[i] = pos; P.rec_flags[i] = 0; P.rec_nm[i] = -1.0; P.rec_end[i] = -1; P.rec_nlead[i] = 0; P.pass_chunks[i] = 0; return;
     }
     P.rec_pos[i] = pos;
     if (i == 0) P.task_first[task] = 0;
@@ -342,18 +343,35 @@ __global__ void __launch_bounds__(256) k_rec_index(const IndexParams P) {
     P.rec_flags[i] = pass ? (uint8_t)(RF_PASS | (has_nm ? RF_HAS_NM : 0) | (hp << 2)) : (uint8_t)0;
     P.rec_nm[i] = has_nm ? (double)nm : -1.0;        // k_rec_post turns it into (nm - big) / (alen + 1)
     P.rec_end[i] = -1; P.rec_nlead[i] = 0;
-    P.pass_flag[i] = pass ? 1u : 0u; P.pass_groups[i] = pass ? (n + 7u) >> 3 : 0u;
+    P.pass_chunks[i] = pass ? chunks_of(n) : 0u;
 }
 
-// one SV signature found by k_scan (an I / D / S op of at least minsvlen_screen inside the task's region): all k_emit needs to build its lead
-struct Event { uint32_t rec; uint32_t len; uint32_t pos_q; int32_t pos_r; uint32_t k_cls; uint32_t pad[3]; };   // k_cls: k | class << 16
+// one SV signature found by k_chunk_rare (an I / D / S op of at least minsvlen_screen inside the task's region): all k_emit needs to build its lead
+struct Event { uint32_t rec; uint32_t len; uint32_t pos_q; int32_t pos_r; uint32_t k_cls; uint32_t fidx; uint32_t pad[2]; };   // k_cls: ordinal inside its flagged chunk | class << 16; fidx: that chunk's place in the flagged list
 
-// descriptor of one PASSING record in the order the streaming kernel sweeps them (32 bytes, loaded as a window of 32 per warp)
-struct PDesc { uint32_t cig8; uint32_t vs; int32_t pos; uint32_t meta; uint32_t rec; uint32_t pad0, pad1, pad2; };   // vs: first virtual group
-
-struct ScanParams {
-    const PDesc* pdesc; const uint32_t* pvs;          // [n_pass], [n_pass + 1] (pvs[n_pass] = total virtual groups)
+// ---- stage A streaming: chunks ----------------------------------------------------------------------------------------------
+// A passing record's CIGAR16 groups (16 bytes = 8 words) are cut into CHUNKS of up to CH groups (256 bytes); a chunk belongs to one
+// record.  The work splits into a dense streaming pass and a sparse one:
+//   k_chunk_sum   one THREAD per chunk walks its groups sequentially: per 32-bit word (two ops) two masked sums (read / reference
+//                 advance, both halves at once) and one OR (E / extension flags).  No cross-lane traffic at all: the instruction count
+//                 per byte is what the masked sums cost, and the kernel runs at memory speed.  Writes (read advance, reference advance,
+//                 "has a flagged word") per chunk.
+//   k_rec_base    one thread per record: exclusive prefix over its chunks -> absolute (query, reference) position at every chunk start,
+//                 reference_end of the record; the record's flagged chunks are appended to a dense list (contiguous per record, in order).
+//   k_chunk_rare  one thread per FLAGGED chunk (0.4 % of the groups hold an I / D / S of event length or an extension word; ~6 % of
+//                 the chunks): walks the chunk again with its base positions, decodes the flagged groups, applies the region test
+//                 (leadprov.py:464-466) and appends one Event per SV signature with its ordinal inside the chunk.
+//   k_rec_fin     one thread per record: prefix over its flagged chunks' event counts -> ordinal base per flagged chunk, lead count
+//                 and "big indel" sum of the record (get_cigar_indels), SA list.  k_emit adds the base to an event's ordinal.
+struct ChunkParams {
+    const RecScan* scan; const uint32_t* choff; uint32_t n_rec;          // choff: exclusive scan of the records' chunk counts
     const uint16_t* cigar; const snfb_task* task;
+    uint2* cdesc;            // per chunk: first group (index of the 16-byte group in the arena), record << 4 | groups - 1
+    uint2* csum;             // per chunk: k_chunk_sum (read advance | flag << 31, reference advance) -> k_rec_base (query pos | flag << 31, reference pos) at the chunk start
+    uint32_t* flist;         // flagged chunks, contiguous per record
+    uint2* fcnt;             // per flagged chunk: (events, big) -> k_rec_fin: (ordinal base, -)
+    uint32_t* rec_foff; uint32_t* rec_nf;
+    const unsigned long long* n_chunks; unsigned long long* n_flag; unsigned long long chunk_cap;
     int32_t* rec_end; uint32_t* rec_nlead; int32_t* rec_big;
     Event* ev; unsigned long long ev_cap; unsigned long long* n_ev;
     uint32_t* sa_list; unsigned long long* n_sa;
@@ -361,18 +379,17 @@ struct ScanParams {
     int minsv;
 };
 
-// thread per record: passing records get their ordinal and first virtual group from two scans; this writes their sweep descriptors
-struct PDescParams { const RecScan* scan; const uint32_t* pidx; const uint32_t* vst; uint32_t n_rec; PDesc* pdesc; uint32_t* pvs; const DevCounters* ctr; };
-__global__ void __launch_bounds__(256) k_pdesc(const PDescParams P) {
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
-    if (i == 0) P.pvs[P.ctr->n_passrec] = (uint32_t)P.ctr->n_vgroups;
-    if (i >= P.n_rec) return;
+// thread per record: chunk descriptors of a passing record
+__global__ void __launch_bounds__(256) k_cdesc(const ChunkParams P) {
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x; if (i >= P.n_rec) return;
     const uint4 d = __ldg(reinterpret_cast<const uint4*>(P.scan + i));
     if (!(d.w & RM_PASS)) return;
-    const uint32_t p = P.pidx[i], vs = P.vst[i];
-    PDesc o; o.cig8 = d.x; o.vs = vs; o.pos = (int32_t)d.z; o.meta = d.w; o.rec = i; o.pad0 = o.pad1 = o.pad2 = 0;
-    uint4* dst = reinterpret_cast<uint4*>(P.pdesc + p); dst[0] = make_uint4(o.cig8, o.vs, (uint32_t)o.pos, o.meta); dst[1] = make_uint4(o.rec, 0u, 0u, 0u);
-    P.pvs[p] = vs;
+    const uint32_t g = (d.y + 7u) >> 3, c0 = P.choff[i];
+    for (uint32_t j = 0, left = g; left; ++j) {
+        const uint32_t n = left < (uint32_t)CH ? left : (uint32_t)CH;
+        if ((unsigned long long)c0 + j < P.chunk_cap) P.cdesc[c0 + j] = make_uint2(d.x + j * (uint32_t)CH, (i << 4) | (n - 1u));
+        left -= n;
+    }
 }
 // lowers the E-bit threshold of a CIGAR16 arena in place (a config that cares about shorter events than the block was packed for)
 __global__ void k_reflag(uint16_t* __restrict__ cigar, unsigned long long n_words, unsigned evt_min) {
@@ -386,12 +403,6 @@ __global__ void k_reflag(uint16_t* __restrict__ cigar, unsigned long long n_word
     }
 }
 
-// segmented inclusive scan over the lanes of a warp; seg0 = the lane the calling lane's segment starts at
-__device__ __forceinline__ unsigned seg_incl_scan(unsigned v, int lane, int seg0) {
-    #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, v, o); if (lane - o >= seg0) v += t; }
-    return v;
-}
 // read / reference advance of a lane's eight words when one of them is an extension word
 __device__ __noinline__ uint2 lane_sums_ext(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3) {
     const uint32_t ww[4] = { w0, w1, w2, w3 };
@@ -401,213 +412,163 @@ __device__ __noinline__ uint2 lane_sums_ext(uint32_t w0, uint32_t w1, uint32_t w
     for (int j = 0; j < 8; ++j) { lq += len[j] * (cls[j] & 1u); lr += len[j] * ((cls[j] >> 1) & 1u); }
     return make_uint2(lq, lr);
 }
-// rare path of k_scan: a step in which some lane holds a flagged word (E bit or extension word).  Every lane passes its own record
-// (a step can span several short records: segments), the positions / lead ordinal its segment starts from, and its region.
-// SV signatures are appended to the event list (any order: a lead's place is fixed later by its record and k).
-// Returns (big << 32) | events counted, per lane.
-__device__ __noinline__ unsigned long long scan_rare(const ScanParams* __restrict__ P, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, unsigned lq, unsigned lr, int seg0,
-                                                      uint32_t rec, unsigned base_q, int base_r, unsigned base_k, int tk_start, int tk_end) {
-    const int lane = lane_id();
-    const uint32_t ww[4] = { w0, w1, w2, w3 };
-    unsigned cls[8], len[8];
-    if (__any_sync(FULL, ((w0 | w1 | w2 | w3) & 0x80008000u) != 0u)) c16_decode8(ww, cls, len);
-    else {                                            // no extension word anywhere in the step: plain field extraction
-        #pragma unroll
-        for (int h = 0; h < 8; ++h) { const unsigned x = (ww[h >> 1] >> (16 * (h & 1))) & 0xffffu; cls[h] = c16_class(x); len[h] = x & C16_LEN_MASK; }
-    }
-    unsigned big = 0, evm = 0;
-    #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        if (len[j] > 10u && (cls[j] == C16_I || cls[j] == C16_D)) big += len[j];             // get_cigar_indels, minoplen 10
-        if (c16_is_event(cls[j]) && (int)len[j] >= P->minsv) evm |= 1u << j; }
-    unsigned cnt = 0, emm = 0;
-    if (__any_sync(FULL, evm != 0)) {
-        const unsigned q0 = base_q + seg_incl_scan(lq, lane, seg0) - lq; const int r0 = base_r + (int)(seg_incl_scan(lr, lane, seg0) - lr);
-        // which signatures stay inside the task's region (leadprov.py:464-466)
-        { int r2 = r0;
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (evm & (1u << j)) { const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2; if (rs >= tk_start && rs < tk_end) { emm |= 1u << j; ++cnt; } }
-                r2 += (int)(len[j] * ((cls[j] >> 1) & 1u)); } }
-        const unsigned kseg = seg_incl_scan(cnt, lane, seg0) - cnt;           // events of my record in earlier lanes of this step
-        unsigned inc = cnt;
-        #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-        const unsigned count = __shfl_sync(FULL, inc, 31);
-        if (count) {
-            unsigned long long e0 = 0; if (lane == 0) e0 = atomicAdd(P->n_ev, (unsigned long long)count);
-            e0 = __shfl_sync(FULL, e0, 0);
-            unsigned mine = inc - cnt, kk = base_k + kseg; unsigned q2 = q0; int r2 = r0;
-            #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                if (emm & (1u << j)) {
-                    const unsigned long long e = e0 + mine;
-                    if (e < P->ev_cap) { uint4* dst = reinterpret_cast<uint4*>(P->ev + e); dst[0] = make_uint4(rec, len[j], q2, (uint32_t)r2); dst[1] = make_uint4((kk & 0xffffu) | (cls[j] << 16), 0u, 0u, 0u); }
-                    else atomicAdd(&P->ctr->lead_overflow, 1ULL);
-                    ++mine; ++kk;
-                }
-                q2 += len[j] * (cls[j] & 1u); r2 += (int)(len[j] * ((cls[j] >> 1) & 1u));
-            }
-        }
-    }
-    return ((unsigned long long)big << 32) | cnt;
-}
 
-// first ordinal p in [0, np] with pvs[p] >= target (pvs ascending; pvs[np] = total); the whole warp searches 32 ways per round
-__device__ inline uint32_t warp_lower_bound(const uint32_t* __restrict__ pvs, uint32_t np, unsigned long long target) {
-    const int lane = lane_id(); uint32_t lo = 0, hi = np;          // answer in [lo, hi]
-    while (hi > lo) {
-        if (hi - lo <= 32) { const uint32_t idx = lo + lane; const bool pr = idx < hi && (unsigned long long)pvs[idx] < target; return lo + __popc(__ballot_sync(FULL, pr)); }
-        const uint32_t step = (hi - lo + 31) / 32; const unsigned long long idx = (unsigned long long)lo + (unsigned long long)lane * step;
-        const bool pr = idx < hi && (unsigned long long)pvs[idx] < target;
-        const int k = __popc(__ballot_sync(FULL, pr));
-        if (k == 0) return lo;
-        const unsigned long long nhi = (unsigned long long)lo + (unsigned long long)k * step;
-        lo = lo + (uint32_t)(k - 1) * step + 1; if (nhi < hi) hi = (uint32_t)nhi;
-    }
-    return lo;
-}
+// per 32-bit word (two ops): the halves' lengths masked by "advances the read" (class bit 0 = word bit 11) / "advances the reference" (bit 12)
+#define SNFB_WORD_BODY(w, aq, ar) { const uint32_t t_ = (w) >> 11; aq += (w) & ((t_ & 0x00010001u) * 0x7ffu); ar += (w) & (((t_ >> 1) & 0x00010001u) * 0x7ffu); }
 
-// The streaming kernel.  The CIGAR16 groups (16 bytes = 8 words) of the PASSING records form one virtual sequence; every warp owns a
-// range of whole records of about total / #warps groups and sweeps it 32 groups (512 bytes) per step, one group per lane, regardless of
-// where records begin and end: a step that spans several short records is handled as segments (at most one record boundary per step is the
-// fast case: ONT reads are ~1.5 steps long).  Per 32-bit word (two ops) the hot loop does two masked sums (read / reference advance, both
-// halves at once) and one OR (the E / extension flags); everything else is per step.
-__global__ void __launch_bounds__(256, 4) k_scan(const __grid_constant__ ScanParams P) {
-    const int lane = lane_id();
-    const uint32_t np = (uint32_t)P.ctr->n_passrec; const unsigned long long V = P.ctr->n_vgroups;
-    if (np == 0) return;
-    const unsigned long long gw = (unsigned long long)blockIdx.x * 8 + (threadIdx.x >> 5), nwarps = (unsigned long long)gridDim.x * 8;
-    const uint32_t p_lo = gw == 0 ? 0u : warp_lower_bound(P.pvs, np, V * gw / nwarps);
-    const uint32_t p_hi = gw + 1 == nwarps ? np : warp_lower_bound(P.pvs, np, V * (gw + 1) / nwarps);
-    if (p_lo >= p_hi) return;
+// The streaming kernel: one thread per chunk.  A thread issues the loads of 8 groups (128 bytes) before it touches the first of them,
+// so a warp keeps 4 KB in flight; groups behind the end of a short chunk read as pad words (all-zero words advance nothing).  The packed
+// half-word sums hold 32 values of at most 2047 before they could carry into the neighbouring half: they are folded every 8 groups.
+__global__ void __launch_bounds__(256, 4) k_chunk_sum(const __grid_constant__ ChunkParams P) {
+    unsigned long long n = *P.n_chunks; if (n > P.chunk_cap) n = P.chunk_cap;
     const uint4* __restrict__ cig4 = reinterpret_cast<const uint4*>(P.cigar);
-    const uint32_t Gend = P.pvs[p_hi];
-    // current record (warp-uniform) and the window of the 32 records after `pbase` (lane j: ordinal pbase + 1 + j)
-    uint32_t pcur = p_lo, pbase = p_lo;
-    uint32_t cur_cig8, cur_vs, cur_meta, cur_rec, cur_vend; int cur_pos;
-    { const uint4 a = __ldg(reinterpret_cast<const uint4*>(P.pdesc + pcur)); const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(P.pdesc + pcur) + 4);
-      cur_cig8 = a.x; cur_vs = a.y; cur_pos = (int)a.z; cur_meta = a.w; cur_rec = r; cur_vend = P.pvs[pcur + 1]; }
-    uint32_t w_cig8 = 0, w_vs = 0xffffffffu, w_meta = 0, w_rec = 0; int w_pos = 0;
-    #define LOAD_WINDOW() { const uint32_t q_ = pbase + 1 + (uint32_t)lane; if (q_ < p_hi) { const uint4 a_ = __ldg(reinterpret_cast<const uint4*>(P.pdesc + q_)); \
-        w_cig8 = a_.x; w_vs = a_.y; w_pos = (int)a_.z; w_meta = a_.w; w_rec = __ldg(reinterpret_cast<const uint32_t*>(P.pdesc + q_) + 4); } else { w_vs = 0xffffffffu; w_cig8 = 0; w_meta = 0; w_rec = 0; w_pos = 0; } }
-    // the record of ordinal `pcur` becomes the current one (its descriptor sits in the window; the end of the last record of the range is Gend)
-    #define ENTER_CUR() { const int l2_ = (int)(pcur - pbase) - 1; \
-        cur_cig8 = __shfl_sync(FULL, w_cig8, l2_); cur_vs = __shfl_sync(FULL, w_vs, l2_); cur_pos = __shfl_sync(FULL, w_pos, l2_); cur_meta = __shfl_sync(FULL, w_meta, l2_); cur_rec = __shfl_sync(FULL, w_rec, l2_); \
-        const uint32_t nv_ = __shfl_sync(FULL, w_vs, (l2_ + 1) & 31); cur_vend = pcur + 1 >= p_hi ? Gend : (l2_ + 1 < 32 ? nv_ : P.pvs[pcur + 1]); }
-    #define FINISH_REC(rec_, meta_, end_, n_, big_) { if ((n_) > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL); \
-        P.rec_end[rec_] = (end_); P.rec_nlead[rec_] = (n_); P.rec_big[rec_] = (int)(big_); \
-        if ((meta_) & RM_HAS_SA) { const unsigned long long e_ = atomicAdd(P.n_sa, 1ULL); P.sa_list[e_] = (rec_); } }
-    LOAD_WINDOW()
-    uint32_t G = cur_vs;
-    unsigned acc_q = 0, acc_big = 0, acc_n = 0; int acc_r = cur_pos;     // the record in progress
-    int tk_id = -1, tk_start = 0, tk_end = 0;
-    while (G < Gend) {
-        if (pcur - pbase >= 8) { pbase = pcur; LOAD_WINDOW() }
-        // record starts inside (G, G + 32): one bit per start; the window's last lane is a sentinel the step stops in front of
-        const uint32_t dv = w_vs - G;
-        const bool has = dv < 32u && pbase + 1 + (uint32_t)lane > pcur;            // w_vs = 0xffffffff (no record) never lands in the step: Gend <= 2^32 - 64
-        const unsigned cbit = has ? 1u << dv : 0u;
-        unsigned bmask = __reduce_or_sync(FULL, cbit);
-        int lim = (Gend - G) < 32u ? (int)(Gend - G) : 32;
-        if (bmask >> 24) { const unsigned lastbit = __shfl_sync(FULL, cbit, 31); if (lastbit) { const int cut = __ffs(lastbit) - 1; if (cut < lim) lim = cut; bmask &= lastbit - 1u; } }   // only a step dense with starts can reach the sentinel
-        const int nb = __popc(bmask);
-        const int my_k = __popc(bmask & (0xffffffffu >> (31 - lane)));       // starts at lanes <= mine
-        uint32_t m_cig8 = cur_cig8, m_vs = cur_vs;
-        if (nb) { const int wl = (int)(pcur - pbase) + my_k - 1;             // window lane of my record (my_k > 0)
-            const uint32_t s_cig8 = __shfl_sync(FULL, w_cig8, wl & 31), s_vs = __shfl_sync(FULL, w_vs, wl & 31);
-            if (my_k) { m_cig8 = s_cig8; m_vs = s_vs; } }
-        uint4 v = make_uint4(0, 0, 0, 0);
-        if (lane < lim) {
-            const uint4* src = cig4 + (m_cig8 + (G + (uint32_t)lane - m_vs));
-            v = __ldg(src);
-            if (nb == 0 && G + 32u + (uint32_t)lane < cur_vend) asm volatile("prefetch.global.L2 [%0];" :: "l"(src + 32));   // the next step of the same record
-        }
-        const uint32_t w0 = v.x, w1 = v.y, w2 = v.z, w3 = v.w;
-        uint32_t aq = 0, ar = 0;
-        #define WORD_BODY(w) { const uint32_t t_ = (w) >> 11; aq += (w) & ((t_ & 0x00010001u) * 0x7ffu); ar += (w) & (((t_ >> 1) & 0x00010001u) * 0x7ffu); }
-        WORD_BODY(w0) WORD_BODY(w1) WORD_BODY(w2) WORD_BODY(w3)
-        #undef WORD_BODY
-        const uint32_t rb = (w0 | w1 | w2 | w3) & 0xC000C000u;
-        unsigned lq = (aq & 0xffffu) + (aq >> 16), lr = (ar & 0xffffu) + (ar >> 16);
-        if (rb & 0x80008000u) { const uint2 t_ = lane_sums_ext(w0, w1, w2, w3); lq = t_.x; lr = t_.y; }
-        const bool any_rare = __any_sync(FULL, rb != 0u);
-        G += (uint32_t)lim;
-        if (nb <= 1) {
-            // ---- at most one record starts inside the step: segment 0 = the record in progress, segment 1 = the next one
-            const bool in0 = my_k == 0;
-            unsigned tq = __reduce_add_sync(FULL, lq), tr = __reduce_add_sync(FULL, lr), tq0 = tq, tr0 = tr;
-            if (nb) { tq0 = __reduce_add_sync(FULL, in0 ? lq : 0u); tr0 = __reduce_add_sync(FULL, in0 ? lr : 0u); }
-            unsigned tb0 = 0, tn0 = 0, tb1 = 0, tn1 = 0;
-            if (any_rare) {
-                int t_task = (int)(cur_meta & 0xffffu); uint32_t t_rec = cur_rec; unsigned bq = acc_q, bn = acc_n; int br = acc_r, seg0 = 0;
-                if (nb) { const int wl = (int)(pcur - pbase);                 // the next record: window lane pcur + 1 - pbase - 1
-                    const uint32_t n_meta = __shfl_sync(FULL, w_meta, wl), n_rec = __shfl_sync(FULL, w_rec, wl); const int n_pos = __shfl_sync(FULL, w_pos, wl);
-                    if (!in0) { t_task = (int)(n_meta & 0xffffu); t_rec = n_rec; bq = 0; bn = 0; br = n_pos; seg0 = __ffs(bmask) - 1; } }
-                if (t_task != tk_id) { const snfb_task t = P.task[t_task]; tk_id = t_task; tk_start = t.start; tk_end = t.end; }     // per lane when the two records sit on different tasks
-                const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, seg0, t_rec, bq, br, bn, tk_start, tk_end);
-                if (nb) tk_id = -1;                                                // lanes may hold different tasks now: reload next time
-                const unsigned lb = (unsigned)(rr >> 32), ln = (unsigned)rr;
-                const unsigned tb = __reduce_add_sync(FULL, lb), tn = __reduce_add_sync(FULL, ln);
-                tb0 = tb; tn0 = tn;
-                if (nb) { tb0 = __reduce_add_sync(FULL, in0 ? lb : 0u); tn0 = __reduce_add_sync(FULL, in0 ? ln : 0u); tb1 = tb - tb0; tn1 = tn - tn0; }
+    for (unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; c < n; c += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint2 d = __ldg(P.cdesc + c);
+        const int ng = (int)(d.y & 15u) + 1;
+        const uint4* src = cig4 + d.x;
+        uint32_t q = 0, r = 0, flags = 0;
+        #pragma unroll 1
+        for (int g0 = 0; g0 < ng; g0 += 8) {
+            uint4 v[8];
+            #pragma unroll
+            for (int g = 0; g < 8; ++g) v[g] = g0 + g < ng ? __ldg(src + g0 + g) : make_uint4(0u, 0u, 0u, 0u);
+            uint32_t aq = 0, ar = 0;
+            #pragma unroll
+            for (int g = 0; g < 8; ++g) {
+                const uint32_t rb = (v[g].x | v[g].y | v[g].z | v[g].w) & 0xC000C000u;
+                flags |= rb;
+                if (rb & 0x80008000u) { const uint2 t = lane_sums_ext(v[g].x, v[g].y, v[g].z, v[g].w); q += t.x; r += t.y; }      // an extension word: the group is decoded op by op
+                else { SNFB_WORD_BODY(v[g].x, aq, ar) SNFB_WORD_BODY(v[g].y, aq, ar) SNFB_WORD_BODY(v[g].z, aq, ar) SNFB_WORD_BODY(v[g].w, aq, ar) }
             }
-            acc_q += tq0; acc_r += (int)tr0; acc_big += tb0; acc_n += tn0;
-            if (nb) {                                 // the record in progress ended inside the step; the next one is in progress now
-                if (lane == 0) FINISH_REC(cur_rec, cur_meta, acc_r, acc_n, acc_big)
-                ++pcur; ENTER_CUR()
-                acc_q = tq - tq0; acc_r = cur_pos + (int)(tr - tr0); acc_big = tb1; acc_n = tn1;
-            }
-            if (G == cur_vend) {                      // the record in progress ends with the step
-                if (lane == 0) FINISH_REC(cur_rec, cur_meta, acc_r, acc_n, acc_big)
-                ++pcur;
-                if (pcur < p_hi) { ENTER_CUR() acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
-            }
-            continue;
+            q += (aq & 0xffffu) + (aq >> 16); r += (ar & 0xffffu) + (ar >> 16);
         }
-        // ---- several records start in this step (short records): segment s is ordinal pcur + s
-        const unsigned below = bmask & (0xffffffffu >> (31 - lane));
-        const int seg0 = my_k ? 31 - __clz(below) : 0;
-        const int wl = (int)(pcur - pbase) + my_k - 1;
-        const uint32_t s_meta = __shfl_sync(FULL, w_meta, wl & 31), s_rec = __shfl_sync(FULL, w_rec, wl & 31); const int s_pos = __shfl_sync(FULL, w_pos, wl & 31);
-        const uint32_t m_meta = my_k ? s_meta : cur_meta, m_rec = my_k ? s_rec : cur_rec;
-        unsigned l_big = 0, l_cnt = 0;
-        if (any_rare) {
-            const snfb_task t = P.task[m_meta & 0xffffu]; tk_id = -1;
-            const unsigned long long rr = scan_rare(&P, w0, w1, w2, w3, lq, lr, seg0, m_rec, my_k ? 0u : acc_q, my_k ? s_pos : acc_r, my_k ? 0u : acc_n, t.start, t.end);
-            l_big = (unsigned)(rr >> 32); l_cnt = (unsigned)rr;
-        }
-        // per-segment totals; lane s keeps the outputs of segment s when that record ends in this step
-        uint32_t o_rec = 0, o_meta = 0, o_n = 0; int o_end = 0, o_big = 0; bool o_valid = false;
-        unsigned last_q = 0, last_big = 0, last_n = 0; int last_r = 0;
-        for (int sg = 0; sg <= nb; ++sg) {
-            const bool mine = my_k == sg && lane < lim;
-            const unsigned tq = __reduce_add_sync(FULL, mine ? lq : 0u), tr = __reduce_add_sync(FULL, mine ? lr : 0u);
-            unsigned tb = 0, tn = 0;
-            if (any_rare) { tb = __reduce_add_sync(FULL, mine ? l_big : 0u); tn = __reduce_add_sync(FULL, mine ? l_cnt : 0u); }
-            const int wls = (int)(pcur - pbase) + sg - 1;
-            const uint32_t g_rec = sg ? __shfl_sync(FULL, w_rec, wls & 31) : cur_rec, g_meta = sg ? __shfl_sync(FULL, w_meta, wls & 31) : cur_meta;
-            const int g_pos = sg ? __shfl_sync(FULL, w_pos, wls & 31) : cur_pos;
-            const unsigned bq = sg ? 0u : acc_q, bb = sg ? 0u : acc_big, bn = sg ? 0u : acc_n; const int br = sg ? g_pos : acc_r;
-            if (sg < nb) { if (lane == sg) { o_valid = true; o_rec = g_rec; o_meta = g_meta; o_end = br + (int)tr; o_big = (int)(bb + tb); o_n = bn + tn; } }
-            else { last_q = bq + tq; last_r = br + (int)tr; last_big = bb + tb; last_n = bn + tn; }
-        }
-        // the last segment becomes the record in progress, or ends exactly with the step
-        pcur += (uint32_t)nb;
-        ENTER_CUR()
-        acc_q = last_q; acc_r = last_r; acc_big = last_big; acc_n = last_n;
-        if (G == cur_vend) {
-            if (lane == nb) { o_valid = true; o_rec = cur_rec; o_meta = cur_meta; o_end = acc_r; o_big = (int)acc_big; o_n = acc_n; }
-            ++pcur;
-            if (pcur < p_hi) {
-                if (pcur - pbase >= 32) { pbase = pcur - 1; LOAD_WINDOW() }
-                ENTER_CUR() acc_q = 0; acc_big = 0; acc_n = 0; acc_r = cur_pos; }
-        }
-        if (o_valid) FINISH_REC(o_rec, o_meta, o_end, o_n, o_big)
+        P.csum[c] = make_uint2(q | (flags ? 0x80000000u : 0u), r);
     }
-    #undef FINISH_REC
-    #undef ENTER_CUR
-    #undef LOAD_WINDOW
+}
+
+// thread per record: positions at every chunk start, reference_end, the record's flagged chunks (slots reserved once per block)
+__global__ void __launch_bounds__(256) k_rec_base(const ChunkParams P) {
+    __shared__ unsigned long long s_base;
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    uint32_t c0 = 0, nch = 0, nf = 0; bool pass = false;
+    if (i < P.n_rec) {
+        const uint4 d = __ldg(reinterpret_cast<const uint4*>(P.scan + i));
+        if (d.w & RM_PASS) {
+            pass = true; c0 = P.choff[i]; nch = chunks_of(d.y);
+            if ((unsigned long long)c0 + nch > P.chunk_cap) nch = (unsigned long long)c0 < P.chunk_cap ? (uint32_t)(P.chunk_cap - c0) : 0u;
+            uint32_t q = 0; int r = (int)d.z;
+            for (uint32_t j = 0; j < nch; ++j) {
+                const uint2 s = P.csum[c0 + j];
+                P.csum[c0 + j] = make_uint2(q | (s.x & 0x80000000u), (uint32_t)r);
+                q += s.x & 0x7fffffffu; r += (int)s.y; nf += s.x >> 31;
+            }
+            P.rec_end[i] = r;
+        }
+    }
+    uint32_t tot; const uint32_t mine = prims::block_excl_scan(nf, &tot);
+    if (threadIdx.x == 0) s_base = tot ? atomicAdd(P.n_flag, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    if (i < P.n_rec) {
+        const uint32_t f0 = (uint32_t)s_base + mine;
+        if (nf) { uint32_t k = 0; for (uint32_t j = 0; j < nch; ++j) if (P.csum[c0 + j].x >> 31) { if ((unsigned long long)f0 + k < P.chunk_cap) P.flist[f0 + k] = c0 + j; ++k; } }
+        P.rec_foff[i] = f0; P.rec_nf[i] = pass ? nf : 0u;
+    }
+}
+
+// thread per flagged chunk: SV signatures (read_iterindels, leadprov.py:583-670) and the indels get_cigar_indels counts (leadprov.py:198-224).
+// The flagged groups are decoded twice — to count the chunk's signatures, then, with event slots reserved once per block, to write them.
+__global__ void __launch_bounds__(128) k_chunk_rare(const __grid_constant__ ChunkParams P) {
+    __shared__ unsigned long long s_base;
+    unsigned long long n = *P.n_flag; if (n > P.chunk_cap) n = P.chunk_cap;
+    const uint4* __restrict__ cig4 = reinterpret_cast<const uint4*>(P.cigar);
+    for (unsigned long long f0 = (unsigned long long)blockIdx.x * 128; f0 < n; f0 += (unsigned long long)gridDim.x * 128) {
+        const unsigned long long f = f0 + threadIdx.x; const bool valid = f < n;
+        uint32_t pq[CH]; int pr[CH]; unsigned mask = 0, cnt = 0, big = 0; uint32_t rec = 0; const uint4* src = cig4; int tk_start = 0, tk_end = 0;
+        if (valid) {
+            const uint32_t c = P.flist[f];
+            const uint2 d = __ldg(P.cdesc + c), base = P.csum[c];
+            const int ng = (int)(d.y & 15u) + 1; rec = d.y >> 4; src = cig4 + d.x;
+            const snfb_task tk = P.task[P.scan[rec].meta & 0xffffu]; tk_start = tk.start; tk_end = tk.end;
+            // positions in front of every group, which groups hold a flagged word
+            uint32_t q = base.x & 0x7fffffffu; int r = (int)base.y;
+            #pragma unroll 1
+            for (int g = 0; g < ng; ++g) {
+                const uint4 v = __ldg(src + g);
+                pq[g] = q; pr[g] = r;
+                const uint32_t rb = (v.x | v.y | v.z | v.w) & 0xC000C000u;
+                if (rb) mask |= 1u << g;
+                if (rb & 0x80008000u) { const uint2 t = lane_sums_ext(v.x, v.y, v.z, v.w); q += t.x; r += (int)t.y; }
+                else { uint32_t aq = 0, ar = 0; SNFB_WORD_BODY(v.x, aq, ar) SNFB_WORD_BODY(v.y, aq, ar) SNFB_WORD_BODY(v.z, aq, ar) SNFB_WORD_BODY(v.w, aq, ar)
+                       q += (aq & 0xffffu) + (aq >> 16); r += (int)((ar & 0xffffu) + (ar >> 16)); }
+            }
+        }
+        unsigned long long e = 0;
+        #pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            unsigned k = 0, m = mask;
+            while (m) {
+                const int g = __ffs(m) - 1; m &= m - 1u;
+                const uint4 v = __ldg(src + g);
+                const uint32_t ww[4] = { v.x, v.y, v.z, v.w };
+                unsigned cls[8], len[8]; c16_decode8(ww, cls, len);
+                uint32_t q2 = pq[g]; int r2 = pr[g];
+                #pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (pass == 0 && len[j] > 10u && (cls[j] == C16_I || cls[j] == C16_D)) big += len[j];            // get_cigar_indels, minoplen 10
+                    if (c16_is_event(cls[j]) && (int)len[j] >= P.minsv) {
+                        const int rs = cls[j] == C16_D ? r2 + (int)len[j] : r2;
+                        if (rs >= tk_start && rs < tk_end) {                                       // the signature stays inside the task's region (leadprov.py:464-466)
+                            if (pass == 1) {
+                                if (e + k < P.ev_cap) { uint4* dst = reinterpret_cast<uint4*>(P.ev + e + k); dst[0] = make_uint4(rec, len[j], q2, (uint32_t)r2); dst[1] = make_uint4((k & 0xffffu) | (cls[j] << 16), (uint32_t)f, 0u, 0u); }
+                                else atomicAdd(&P.ctr->lead_overflow, 1ULL);
+                            }
+                            ++k;
+                        }
+                    }
+                    q2 += len[j] * (cls[j] & 1u); r2 += (int)(len[j] * ((cls[j] >> 1) & 1u));
+                }
+            }
+            if (pass == 0) {
+                cnt = k;
+                // one reservation of event slots per block
+                __shared__ uint32_t wsum[4];
+                uint32_t inc = prims::warp_incl_scan(cnt);
+                if (lane_id() == 31) wsum[threadIdx.x >> 5] = inc;
+                __syncthreads();
+                const uint32_t w = threadIdx.x >> 5; uint32_t before = 0, tot = 0;
+                #pragma unroll
+                for (int x = 0; x < 4; ++x) { const uint32_t t = wsum[x]; if ((uint32_t)x < w) before += t; tot += t; }
+                if (threadIdx.x == 0) s_base = tot ? atomicAdd(P.n_ev, (unsigned long long)tot) : 0ull;
+                __syncthreads();
+                e = s_base + before + inc - cnt;
+                __syncthreads();
+            }
+        }
+        if (valid) P.fcnt[f] = make_uint2(cnt, big);
+    }
+}
+
+// thread per record: ordinal base of every flagged chunk, lead count and big-indel sum of the record, the SA work list (slots reserved once per block)
+__global__ void __launch_bounds__(256) k_rec_fin(const ChunkParams P) {
+    __shared__ unsigned long long s_base;
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    uint32_t has_sa = 0;
+    if (i < P.n_rec) {
+        const uint32_t meta = P.scan[i].meta;
+        if (meta & RM_PASS) {
+            const uint32_t f0 = P.rec_foff[i]; uint32_t nf = P.rec_nf[i];
+            if ((unsigned long long)f0 + nf > P.chunk_cap) nf = (unsigned long long)f0 < P.chunk_cap ? (uint32_t)(P.chunk_cap - f0) : 0u;
+            uint32_t k = 0, big = 0;
+            for (uint32_t j = 0; j < nf; ++j) { const uint2 e = P.fcnt[f0 + j]; P.fcnt[f0 + j] = make_uint2(k, 0u); k += e.x; big += e.y; }
+            if (k > 0xffffu) atomicAdd(&P.ctr->ordinal_overflow, 1ULL);
+            P.rec_nlead[i] = k; P.rec_big[i] = (int)big;
+            has_sa = (meta & RM_HAS_SA) ? 1u : 0u;
+        }
+    }
+    uint32_t tot; const uint32_t mine = prims::block_excl_scan(has_sa, &tot);
+    if (threadIdx.x == 0) s_base = tot ? atomicAdd(P.n_sa, (unsigned long long)tot) : 0ull;
+    __syncthreads();
+    if (has_sa) P.sa_list[s_base + mine] = i;
 }
 
 // per read nm (leadprov.py:517-526) and the per-task bookkeeping of iter_region (read count, covered bases, longest span)
@@ -644,7 +605,7 @@ __global__ void __launch_bounds__(256) k_rec_post(const PostParams P) {
 
 struct EmitParams {
     const snfb_rec* rec; const RecClip* clip; const uint8_t* var;
-    const Event* ev; const unsigned long long* n_ev; unsigned long long ev_cap;
+    const Event* ev; const unsigned long long* n_ev; unsigned long long ev_cap; const uint2* fcnt;      // fcnt[fidx].x: ordinal base of the event's chunk inside its record
     snfb_lead* leads; DevCounters* ctr;
     int maxlen, detect_large_ins; double longinslen;
 };
@@ -664,7 +625,7 @@ __global__ void __launch_bounds__(128) k_emit(const EmitParams P) {
     const unsigned long long n_all = *P.n_ev, n = n_all < P.ev_cap ? n_all : P.ev_cap;
     if (blockIdx.x == 0 && threadIdx.x == 0) P.ctr->n_slots = n_all;
     for (unsigned long long e = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (unsigned long long)gridDim.x * blockDim.x) {
-        const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(P.ev + e)); const uint32_t kc = __ldg(reinterpret_cast<const uint32_t*>(P.ev + e) + 4);
+        const uint4 e0 = __ldg(reinterpret_cast<const uint4*>(P.ev + e)); const uint2 kf = __ldg(reinterpret_cast<const uint2*>(P.ev + e) + 2); const uint32_t kc = kf.x;
         const uint32_t rec = e0.x; const int ln = (int)e0.y, pqi = (int)e0.z, pr = (int)e0.w; const unsigned op = kc >> 16;
         const uint4* core = reinterpret_cast<const uint4*>(P.rec + rec);
         const uint4 c0 = __ldg(core), c3 = __ldg(core + 3);
@@ -676,7 +637,7 @@ __global__ void __launch_bounds__(128) k_emit(const EmitParams P) {
         const bool use_clips = P.detect_large_ins && !is_supp && !has_sa;
         snfb_lead L;
         L.rec = rec; L.qname_hash = qname_hash_thread(P.var + var_off, l_qname); L.read_len = alen; L.seq_off = -1; L.seq_len = 0; L.mate_contig = -1; L.mate_pos = 0; L.nm_sa = 0;
-        L.task = (uint16_t)r_task; L.k = (uint16_t)(kc & 0xffffu);
+        L.task = (uint16_t)r_task; L.k = (uint16_t)(((kc & 0xffffu) + P.fcnt[kf.y].x) & 0xffffu);
         uint32_t f = (rev ? SNFB_LF_REVERSE : 0u) | (mapq << 16) | ((uint32_t)SNFB_SRC_INLINE << 3) | (hp << 24) | (is_supp ? SNFB_LF_IS_SA : 0u);
         if (op == C16_I) { f |= SNFB_INS; L.ref_start = pr; L.ref_end = pr; L.qry_start = pqi; L.qry_end = pqi + ln; L.svlen = ln;
             if (ln <= P.maxlen) { f |= SNFB_LF_HAS_SEQ; L.seq_off = pqi; L.seq_len = ln; } }

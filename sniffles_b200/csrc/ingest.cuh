@@ -23,17 +23,26 @@ struct IngestCounters { unsigned long long bad_blocks, first_bad_block, first_ba
 
 constexpr int INF_WARPS = 8;
 
+// NL lanes per BGZF block: 32 = one block per warp, 16 / 8 = two / four blocks per warp (their decodes share the warp's instruction
+// stream where they run the same path — a literal-heavy stream mostly does — and diverge where they do not)
+template <int NL>
 __global__ void __launch_bounds__(INF_WARPS * 32) k_inflate(const uint8_t* __restrict__ comp, const BgzfBlock* __restrict__ blocks, unsigned n_blocks, uint8_t* __restrict__ raw, IngestCounters* ctr) {
-    __shared__ WarpTables tables[INF_WARPS];
-    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (unsigned b = blockIdx.x * INF_WARPS + w; b < n_blocks; b += gridDim.x * INF_WARPS) {
+    extern __shared__ __align__(16) uint8_t inflate_smem[];
+    constexpr int GPW = 32 / NL;                              // groups per warp
+    WarpTables* tables = reinterpret_cast<WarpTables*>(inflate_smem);
+    const int w = threadIdx.x >> 5, g = (threadIdx.x & 31) / NL, lane = (threadIdx.x & 31) % NL;
+    const unsigned gmask = NL == 32 ? 0xffffffffu : (((1u << (NL & 31)) - 1u) << (g * NL));
+    WarpTables* T = tables + (w * GPW + g);
+    const unsigned stride = gridDim.x * INF_WARPS * GPW;
+    for (unsigned b = (blockIdx.x * INF_WARPS + w) * GPW + g; b < n_blocks; b += stride) {
         const BgzfBlock B = blocks[b];
         uint32_t produced = 0;
-        int rc = inflate_stream<32>(comp, B.in_off, B.in_off + B.in_len, raw + B.out_off, B.isize, &tables[w], lane, &produced);
+        int rc = inflate_stream<NL>(comp, B.in_off, B.in_off + B.in_len, raw + B.out_off, B.isize, T, lane, gmask, &produced);
         if (rc == INF_OK && produced != B.isize) rc = INF_LENGTH_MISMATCH;
         if (rc != INF_OK && lane == 0) { if (atomicAdd(&ctr->bad_blocks, 1ULL) == 0) { ctr->first_bad_block = b; ctr->first_bad_code = (unsigned long long)rc; } }
     }
 }
+template <int NL> constexpr size_t inflate_smem_bytes() { return sizeof(WarpTables) * INF_WARPS * (32 / NL); }
 
 // mode 0: span_cnt[s] = records in the span; mode 1: rec_body[base[s] + k] / rec_bs / rec_task
 __global__ void k_walk(const uint8_t* __restrict__ raw, unsigned long long raw_len, const Span* __restrict__ spans, unsigned n_spans, int mode,

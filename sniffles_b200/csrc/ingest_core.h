@@ -78,18 +78,29 @@ struct WarpTables {
 
 enum { INF_OK = 0, INF_BAD_BLOCK_TYPE = 1, INF_BAD_STORED = 2, INF_BAD_CODE = 3, INF_OVERSUBSCRIBED = 4, INF_BAD_SYMBOL = 5, INF_BAD_DISTANCE = 6, INF_OUTPUT_OVERRUN = 7, INF_INPUT_OVERRUN = 8, INF_LENGTH_MISMATCH = 9 };
 
+// A decoding group = NL lanes of a warp (NL = 32: the whole warp; NL = 16 / 8: two / four BGZF blocks per warp, each decoded by its own
+// lanes with its own tables — the groups share the warp's instruction stream wherever they happen to take the same path, and
+// diverge like any threads where they do not).  gmask = the lanes of the group, for __syncwarp.
+SNFB_HD void group_sync(unsigned gmask) {
+#if defined(__CUDA_ARCH__)
+    __syncwarp(gmask);
+#else
+    (void)gmask;
+#endif
+}
+
 // canonical Huffman code from code lengths: per-length counts, symbols in code order, and the look-up table for codes of at most
 // `fbits` bits (bit-reversed: DEFLATE packs codes starting at the most significant bit into a stream read from the least).
 // Returns < 0 when the lengths over-subscribe the code space, otherwise the unused code space (0 = complete).
 template <int NL>
-SNFB_HD int huff_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* symtab, uint16_t* fast, int fbits, int lane) {
-    warp_sync();                                       // lens[] was written by lane 0
+SNFB_HD int huff_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* symtab, uint16_t* fast, int fbits, int lane, unsigned gmask) {
+    group_sync(gmask);                                 // lens[] was written by lane 0
     if (lane == 0) {
         for (int l = 0; l < 16; ++l) count[l] = 0;
         for (int s = 0; s < n; ++s) count[lens[s]]++;
     }
     for (int j = lane; j < (1 << fbits); j += NL) fast[j] = 0;
-    warp_sync();
+    group_sync(gmask);
     int left = 1;
     for (int len = 1; len <= 15; ++len) { left <<= 1; left -= (int)count[len]; if (left < 0) return -1; }
     if (lane == 0) {
@@ -97,7 +108,7 @@ SNFB_HD int huff_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* sy
         for (int len = 1; len < 15; ++len) offs[len + 1] = (uint16_t)(offs[len] + count[len]);
         for (int s = 0; s < n; ++s) if (lens[s]) symtab[offs[lens[s]]++] = (uint16_t)s;
     }
-    warp_sync();
+    group_sync(gmask);
     unsigned code = 0, idx = 0;
     for (int len = 1; len <= fbits; ++len) {
         const unsigned cnt = count[len];
@@ -107,22 +118,28 @@ SNFB_HD int huff_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* sy
         }
         code = (code + cnt) << 1; idx += cnt;
     }
-    warp_sync();
+    group_sync(gmask);
     return left;
 }
 
-// next symbol from the low bits of bb; *nbits = its code length; -1 = no such code
-SNFB_HD int huff_decode(uint64_t bb, const uint16_t* fast, int fbits, const uint16_t* count, const uint16_t* symtab, int* nbits) {
-    const unsigned e = fast[(unsigned)bb & ((1u << fbits) - 1u)];
-    if (e) { *nbits = (int)(e & 15u); return (int)(e >> 4); }
+// a code longer than the look-up table: canonical decode bit by bit (zlib's puff).  Returns symbol | length << 16, or -1 = no such code
+SNFB_HDN int huff_decode_slow(uint64_t bb, const uint16_t* count, const uint16_t* symtab) {
     int code = 0, first = 0, index = 0;
     for (int len = 1; len <= 15; ++len) {
         code |= (int)((bb >> (len - 1)) & 1u);
         const int cnt = count[len];
-        if (code - cnt < first) { *nbits = len; return symtab[index + (code - first)]; }
+        if (code - cnt < first) return (int)symtab[index + (code - first)] | (len << 16);
         index += cnt; first += cnt; first <<= 1; code <<= 1;
     }
-    *nbits = 0; return -1;
+    return -1;
+}
+// next symbol from the low bits of bb; *nbits = its code length; -1 = no such code
+SNFB_HD int huff_decode(uint64_t bb, const uint16_t* fast, int fbits, const uint16_t* count, const uint16_t* symtab, int* nbits) {
+    const unsigned e = fast[(unsigned)bb & ((1u << fbits) - 1u)];
+    if (e) { *nbits = (int)(e & 15u); return (int)(e >> 4); }
+    const int r = huff_decode_slow(bb, count, symtab);
+    *nbits = r < 0 ? 0 : r >> 16;
+    return r < 0 ? -1 : (r & 0xffff);
 }
 
 // order in which a dynamic header stores the code-length code lengths (RFC 1951 §3.2.7), 5 bits each
@@ -132,26 +149,43 @@ SNFB_HD int clen_order(int i) {
     return (int)(((i < 12 ? lo >> (5 * i) : hi >> (5 * (i - 12)))) & 31ull);
 }
 
-// Inflate one raw DEFLATE stream in[ipos .. iend) into out[0 .. out_cap); every lane of the warp calls it with the same arguments
-// (lane = its index, NL = lanes).  Returns INF_*; *out_len = bytes produced.
+// the i-th 32-bit word of the stream, counted from the 4-byte aligned address at or below its first byte (one aligned load on the device)
+SNFB_HD uint32_t stream_word(const uint8_t* base, uint32_t i) {
+#if defined(__CUDA_ARCH__)
+    return reinterpret_cast<const uint32_t*>(base)[i];
+#else
+    uint32_t v; memcpy(&v, base + 4ull * i, 4); return v;
+#endif
+}
+
+// Inflate one raw DEFLATE stream in[ipos .. iend) into out[0 .. out_cap); every lane of the group calls it with the same arguments
+// (lane = its index in the group, NL = lanes, gmask = the group's lanes in the warp).  `in` is 4-byte aligned with 16 readable bytes
+// behind iend.  Returns INF_*; *out_len = bytes produced.
 template <int NL>
-SNFB_HD int inflate_stream(const uint8_t* in, uint64_t ipos, uint64_t iend, uint8_t* out, uint32_t out_cap, WarpTables* T, int lane, uint32_t* out_len) {
-    uint64_t bb = 0; int bc = 0; uint64_t ip = ipos; uint32_t op = 0; int err = INF_OK; bool last = false;
-#define SNFB_REFILL() do { if (bc <= 32) { bb |= (uint64_t)ld32u(in, ip) << bc; ip += 4; bc += 32; } } while (0)
+SNFB_HD int inflate_stream(const uint8_t* in, uint64_t ipos, uint64_t iend, uint8_t* out, uint32_t out_cap, WarpTables* T, int lane, unsigned gmask, uint32_t* out_len) {
+    const uint8_t* base = in + (ipos & ~3ull);                                    // the stream as aligned 32-bit words
+    const uint32_t iend_rel = (uint32_t)(ipos & 3ull) + (uint32_t)(iend - ipos);    // its end, in bytes from base
+    const uint32_t iw_limit = ((iend_rel + 3u) >> 2) + 2u;                          // words a well-formed stream can touch (8 bytes of look-ahead)
+    uint64_t bb = 0; int bc = 0; uint32_t iw = 0, op = 0; int err = INF_OK; bool last = false, ovr = false;
+#define SNFB_REFILL() do { if (bc <= 32) { uint32_t w_ = 0; if (iw < iw_limit) w_ = stream_word(base, iw); else ovr = true; bb |= (uint64_t)w_ << bc; ++iw; bc += 32; } } while (0)
 #define SNFB_TAKE(n) do { bb >>= (n); bc -= (n); } while (0)
+    SNFB_REFILL(); SNFB_TAKE(8 * (int)(ipos & 3ull));
     do {
-        warp_sync();                                   // nobody still reads the previous block's tables
-        if (ip > iend + 8) { err = INF_INPUT_OVERRUN; break; }
+        group_sync(gmask);                             // nobody still reads the previous block's tables
+        if (ovr) break;
         SNFB_REFILL();
         last = (bb & 1u) != 0; const unsigned type = (unsigned)(bb >> 1) & 3u; SNFB_TAKE(3);
         if (type == 0) {                               // stored
             SNFB_TAKE(bc & 7);
-            ip -= (uint64_t)(bc >> 3); bb = 0; bc = 0;
-            const uint32_t len = ld16u(in, ip), nlen = ld16u(in, ip + 2); ip += 4;
-            if ((len ^ 0xffffu) != nlen || ip + len > iend) { err = INF_BAD_STORED; break; }
+            uint32_t rel = 4u * iw - (uint32_t)(bc >> 3);      // first unread byte
+            if (rel + 4u > iend_rel) { err = INF_BAD_STORED; break; }
+            const uint32_t len = ld16u(base, rel), nlen = ld16u(base, rel + 2); rel += 4;
+            if ((len ^ 0xffffu) != nlen || rel + len > iend_rel) { err = INF_BAD_STORED; break; }
             if (op + len > out_cap) { err = INF_OUTPUT_OVERRUN; break; }
-            for (uint32_t j = lane; j < len; j += NL) out[op + j] = in[ip + j];
-            op += len; ip += len;
+            for (uint32_t j = lane; j < len; j += NL) out[op + j] = base[rel + j];
+            op += len; rel += len;
+            iw = rel >> 2; bb = 0; bc = 0;
+            SNFB_REFILL(); SNFB_TAKE(8 * (int)(rel & 3u));
             continue;
         }
         if (type == 3) { err = INF_BAD_BLOCK_TYPE; break; }
@@ -166,12 +200,13 @@ SNFB_HD int inflate_stream(const uint8_t* in, uint64_t ipos, uint64_t iend, uint
             }
             nlit = 288; ndist = 30;
         } else {                                       // dynamic code
+            SNFB_REFILL();
             nlit = (int)(bb & 31u) + 257; ndist = (int)((bb >> 5) & 31u) + 1; const int nclen = (int)((bb >> 10) & 15u) + 4; SNFB_TAKE(14);
             if (nlit > 286 || ndist > 30) { err = INF_BAD_CODE; break; }
             if (lane == 0) for (int i = 0; i < 19; ++i) T->lens[i] = 0;
-            warp_sync();
+            group_sync(gmask);
             for (int i = 0; i < nclen; ++i) { SNFB_REFILL(); if (lane == 0) T->lens[clen_order(i)] = (uint8_t)(bb & 7u); SNFB_TAKE(3); }
-            if (huff_build<NL>(T->lens, 19, T->dist_count, T->dist_sym, T->dist_fast, DIST_FAST_BITS, lane) != 0) { err = INF_BAD_CODE; break; }   // the code-length code must be complete
+            if (huff_build<NL>(T->lens, 19, T->dist_count, T->dist_sym, T->dist_fast, DIST_FAST_BITS, lane, gmask) != 0) { err = INF_BAD_CODE; break; }   // the code-length code must be complete
             int i = 0, prev = 0;
             while (i < nlit + ndist) {
                 SNFB_REFILL();
@@ -188,51 +223,57 @@ SNFB_HD int inflate_stream(const uint8_t* in, uint64_t ipos, uint64_t iend, uint
                 i += rep; prev = val;
             }
             if (err) break;
-            warp_sync();
+            group_sync(gmask);
             if (T->lens[256] == 0) { err = INF_BAD_CODE; break; }      // no end-of-block code
             // the distance lengths follow the literal/length lengths: move them to their own base so both builds read aligned arrays
             if (lane == 0) { uint8_t tmp[32]; for (int k = 0; k < ndist; ++k) tmp[k] = T->lens[nlit + k]; for (int k = 0; k < ndist; ++k) T->lens[288 + k] = tmp[k]; }
         }
-        if (huff_build<NL>(T->lens, nlit, T->lit_count, T->lit_sym, T->lit_fast, LIT_FAST_BITS, lane) < 0) { err = INF_OVERSUBSCRIBED; break; }
-        if (huff_build<NL>(T->lens + 288, ndist, T->dist_count, T->dist_sym, T->dist_fast, DIST_FAST_BITS, lane) < 0) { err = INF_OVERSUBSCRIBED; break; }
+        if (huff_build<NL>(T->lens, nlit, T->lit_count, T->lit_sym, T->lit_fast, LIT_FAST_BITS, lane, gmask) < 0) { err = INF_OVERSUBSCRIBED; break; }
+        if (huff_build<NL>(T->lens + 288, ndist, T->dist_count, T->dist_sym, T->dist_fast, DIST_FAST_BITS, lane, gmask) < 0) { err = INF_OVERSUBSCRIBED; break; }
+        const uint16_t* lit_fast = T->lit_fast;
         for (;;) {
-            if (ip > iend + 8) { err = INF_INPUT_OVERRUN; break; }
             SNFB_REFILL();
-            int nb; const int sym = huff_decode(bb, T->lit_fast, LIT_FAST_BITS, T->lit_count, T->lit_sym, &nb);
-            if (sym < 0) { err = INF_BAD_SYMBOL; break; }
+            unsigned e = lit_fast[(unsigned)bb & ((1u << LIT_FAST_BITS) - 1u)];
+            int nb, sym;
+            if (e) { nb = (int)(e & 15u); sym = (int)(e >> 4); }
+            else { const int r_ = huff_decode_slow(bb, T->lit_count, T->lit_sym); if (r_ < 0) { err = INF_BAD_SYMBOL; break; } sym = r_ & 0xffff; nb = r_ >> 16; }
             SNFB_TAKE(nb);
-            if (sym < 256) {
+            if (sym < 256) {                           // literal; the bits for a second one are already in the buffer (18 or more)
                 if (op >= out_cap) { err = INF_OUTPUT_OVERRUN; break; }
                 if (lane == 0) out[op] = (uint8_t)sym;
-                ++op; continue;
+                ++op;
+                e = lit_fast[(unsigned)bb & ((1u << LIT_FAST_BITS) - 1u)];
+                if (e - 1u < (256u << 4) - 1u && op < out_cap) { SNFB_TAKE((int)(e & 15u)); if (lane == 0) out[op] = (uint8_t)(e >> 4); ++op; }
+                continue;
             }
             if (sym == 256) break;
             if (sym > 285) { err = INF_BAD_SYMBOL; break; }
             uint32_t len;
             if (sym < 265) len = (uint32_t)(sym - 254);
             else if (sym == 285) len = 258;
-            else { const int e = (sym - 261) >> 2; len = 3u + ((4u + (unsigned)((sym - 261) & 3)) << e) + ((unsigned)bb & ((1u << e) - 1u)); SNFB_TAKE(e); }
+            else { const int x = (sym - 261) >> 2; len = 3u + ((4u + (unsigned)((sym - 261) & 3)) << x) + ((unsigned)bb & ((1u << x) - 1u)); SNFB_TAKE(x); }
             SNFB_REFILL();
             const int dsym = huff_decode(bb, T->dist_fast, DIST_FAST_BITS, T->dist_count, T->dist_sym, &nb);
             if (dsym < 0 || dsym > 29) { err = INF_BAD_DISTANCE; break; }
             SNFB_TAKE(nb);
             uint32_t dist;
             if (dsym < 4) dist = (uint32_t)dsym + 1u;
-            else { const int e = (dsym >> 1) - 1; dist = 1u + ((2u + (unsigned)(dsym & 1)) << e) + ((unsigned)bb & ((1u << e) - 1u)); SNFB_TAKE(e); }
+            else { const int x = (dsym >> 1) - 1; dist = 1u + ((2u + (unsigned)(dsym & 1)) << x) + ((unsigned)bb & ((1u << x) - 1u)); SNFB_TAKE(x); }
             if (dist > op) { err = INF_BAD_DISTANCE; break; }
             if (op + len > out_cap) { err = INF_OUTPUT_OVERRUN; break; }
-            warp_sync();                               // the bytes the match reads were written by other lanes
+            group_sync(gmask);                         // the bytes the match reads were written by other lanes
             const uint8_t* src = out + op - dist; uint8_t* dst = out + op;
             if (dist >= len) { for (uint32_t j = lane; j < len; j += NL) dst[j] = src[j]; }
             else { for (uint32_t j = lane; j < len; j += NL) dst[j] = src[j % dist]; }
             op += len;
+            if (ovr) break;
         }
-    } while (!last && !err);
+    } while (!last && !err && !ovr);
 #undef SNFB_REFILL
 #undef SNFB_TAKE
-    warp_sync();
+    group_sync(gmask);
     *out_len = op;
-    if (!err && ip - (uint64_t)(bc >> 3) > iend) err = INF_INPUT_OVERRUN;
+    if (!err && (ovr || 4u * iw - (uint32_t)(bc >> 3) > iend_rel)) err = INF_INPUT_OVERRUN;
     return err;
 }
 

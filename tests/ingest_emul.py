@@ -28,7 +28,7 @@ def lib():
         if not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(_SRC), os.path.getmtime(_CORE)):
             subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-Wall", "-o", _SO, _SRC])
         L = C.CDLL(_SO)
-        L.ingest_host_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
+        L.ingest_host_inflate.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint32, C.POINTER(C.c_uint32)]
         L.ingest_host_sizeof_rawrec.restype = C.c_uint64
         L.ingest_host_parse.restype = C.c_int64
         L.ingest_host_parse.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_uint64]
@@ -39,12 +39,12 @@ def lib():
     return _L
 
 
-def inflate(comp: bytes, n_out: int):
-    """raw DEFLATE -> (rc, bytes)"""
-    buf = np.frombuffer(comp + b"\0" * 16, "u1").copy()
+def inflate(comp: bytes, n_out: int, lead: int = 0):
+    """raw DEFLATE -> (rc, bytes); `lead` junk bytes in front of the stream exercise the unaligned start"""
+    buf = np.frombuffer(b"\xa5" * lead + comp + b"\0" * 16, "u1").copy()
     out = np.zeros(n_out + 8, "u1")
     ol = C.c_uint32(0)
-    rc = lib().ingest_host_inflate(buf.ctypes.data, len(comp), out.ctypes.data, n_out, C.byref(ol))
+    rc = lib().ingest_host_inflate(buf.ctypes.data, lead, lead + len(comp), out.ctypes.data, n_out, C.byref(ol))
     return rc, out[:ol.value].tobytes()
 
 
@@ -72,9 +72,9 @@ def load_bam(bgzf: np.ndarray, spans: np.ndarray, task_table: np.ndarray, evt_mi
     blocks = walk_bgzf(z)
     starts = [b[0] for b in blocks]
     uoff, raw = [], bytearray()
-    for (_, po, pl, isz) in blocks:
+    for k, (_, po, pl, isz) in enumerate(blocks):
         uoff.append(len(raw))
-        rc, d = inflate(z[po:po + pl], isz)
+        rc, d = inflate(z[po:po + pl], isz, lead=k % 4)
         assert rc == 0 and len(d) == isz, (rc, len(d), isz)
         raw += d
     raw_len = len(raw)

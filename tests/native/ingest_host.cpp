@@ -8,10 +8,10 @@
 
 extern "C" {
 
-// raw DEFLATE stream -> out; returns INF_* (0 = ok); *out_len = bytes produced.  `in` must have 8 readable bytes behind in_len.
-int ingest_host_inflate(const uint8_t* in, uint64_t in_len, uint8_t* out, uint32_t out_cap, uint32_t* out_len) {
+// raw DEFLATE stream in[ipos .. iend) -> out; returns INF_* (0 = ok); *out_len = bytes produced.  `in` must have 16 readable bytes behind iend.
+int ingest_host_inflate(const uint8_t* in, uint64_t ipos, uint64_t iend, uint8_t* out, uint32_t out_cap, uint32_t* out_len) {
     ingest::WarpTables* T = (ingest::WarpTables*)malloc(sizeof(ingest::WarpTables));
-    const int rc = ingest::inflate_stream<1>(in, 0, in_len, out, out_cap, T, 0, out_len);
+    const int rc = ingest::inflate_stream<1>(in, ipos, iend, out, out_cap, T, 0, 1u, out_len);
     free(T);
     return rc;
 }
