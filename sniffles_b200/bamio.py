@@ -157,7 +157,12 @@ class BamFile:
             self.contigs.append((d[:l_name - 1].decode(), struct.unpack("<i", d[l_name:l_name + 4])[0]))
         self.first_record = v
         self.name_to_id = {n: i for i, (n, _) in enumerate(self.contigs)}
-        self.index = self._load_bai(index_path or path + ".bai")
+        import os
+        if index_path is None:
+            index_path = next((p for p in (path + ".bai", path + ".csi", path[:-4] + ".bai" if path.endswith(".bam") else path + ".bai") if os.path.exists(p)), path + ".bai")
+        self.min_shift, self.depth = 14, 5
+        self.index = self._load_csi(index_path) if index_path.endswith(".csi") else self._load_bai(index_path)
+        self.meta_bin = ((1 << ((self.depth + 1) * 3)) - 1) // 7 + 1          # 37450 for the BAI layout
 
     def close(self):
         self.bgzf.close()
@@ -183,23 +188,84 @@ class BamFile:
             p += 4
             lin = list(struct.unpack(f"<{n_intv}Q", d[p:p + 8 * n_intv]))
             p += 8 * n_intv
-            refs.append((bins, lin))
+            refs.append((bins, lin, None))
         return refs
+
+    def _load_csi(self, path):
+        """CSI (SAM spec §5.3 / CSIv1): a BGZF file; bins of a configurable geometry (min_shift, depth), every bin with the smallest virtual
+        offset of a record overlapping its first window (`loffset`) instead of BAI's linear index"""
+        with open(path, "rb") as f:
+            z = f.read()
+        d, o = b"", 0
+        while o < len(z):                                # concatenated gzip members
+            dec = zlib.decompressobj(31)
+            d += dec.decompress(z[o:])
+            o = len(z) - len(dec.unused_data)
+        if d[:4] != b"CSI\1":
+            raise ValueError("not a CSI index")
+        self.min_shift, self.depth, l_aux = struct.unpack("<iii", d[4:16])
+        p = 16 + l_aux
+        n_ref = struct.unpack("<i", d[p:p + 4])[0]
+        p += 4
+        refs = []
+        for _ in range(n_ref):
+            n_bin = struct.unpack("<i", d[p:p + 4])[0]
+            p += 4
+            bins, loff = {}, {}
+            for _ in range(n_bin):
+                b, lo, n_chunk = struct.unpack("<IQi", d[p:p + 16])
+                p += 16
+                bins[b] = [struct.unpack("<QQ", d[p + 16 * k:p + 16 * k + 16]) for k in range(n_chunk)]
+                loff[b] = lo
+                p += 16 * n_chunk
+            refs.append((bins, None, loff))
+        return refs
+
+    # ---- index queries shared by fetch and device_input
+    def _reg2bins(self, beg, end):
+        end -= 1
+        bins, t, s = [], 0, self.min_shift + 3 * self.depth
+        for lvl in range(self.depth + 1):
+            bins.extend(range(t + (beg >> s), t + (end >> s) + 1))
+            t += 1 << (3 * lvl)
+            s -= 3
+        return bins
+
+    def _min_offset(self, rid, start):
+        """smallest virtual offset a record overlapping `start` can have: BAI's linear index, or CSI's per-bin loffset found the way
+        htslib looks it up (the leaf bin of start, else the nearest earlier sibling / ancestor that exists)"""
+        bins, lin, loff = self.index[rid]
+        if lin is not None:
+            w = start >> 14
+            return lin[w] if w < len(lin) else (lin[-1] if lin else 0)
+        first_leaf = ((1 << (3 * self.depth)) - 1) // 7
+        b = first_leaf + (start >> self.min_shift)
+        while b:
+            if b in loff:
+                return loff[b]
+            parent = (b - 1) >> 3
+            b = b - 1 if b > (parent << 3) + 1 else parent
+        return loff.get(0, 0)
+
+    def _anchors(self, rid):
+        """record-aligned virtual offsets inside a contig's data: where the device ingest may cut its spans"""
+        bins, lin, loff = self.index[rid]
+        return sorted(set(lin if lin is not None else loff.values()))
 
     def get_reference_length(self, contig):
         return self.contigs[self.name_to_id[contig]][1]
 
     def count_mapped(self, contig):
         """mapped-read count of the pseudo-bin 37450 (what get_index_statistics reports), or None"""
-        bins, _ = self.index[self.name_to_id[contig]]
-        ch = bins.get(37450)
+        bins = self.index[self.name_to_id[contig]][0]
+        ch = bins.get(self.meta_bin)
         return int(ch[1][0]) if ch and len(ch) > 1 else None
 
     def fetch(self, contig, start, end):
         rid = self.name_to_id[contig]
-        bins, lin = self.index[rid]
-        min_off = lin[start >> 14] if (start >> 14) < len(lin) else (lin[-1] if lin else 0)
-        chunks = sorted(c for b in reg2bins(max(start, 0), max(end, start + 1)) if b in bins and b != 37450 for c in bins[b] if c[1] > min_off)
+        bins = self.index[rid][0]
+        min_off = self._min_offset(rid, max(start, 0))
+        chunks = sorted(c for b in self._reg2bins(max(start, 0), max(end, start + 1)) if b in bins and b != self.meta_bin for c in bins[b] if c[1] > min_off)
         seen_to = 0
         for beg, stop in chunks:
             v = max(beg, seen_to, min_off)
@@ -227,9 +293,9 @@ class BamFile:
         """disjoint, ascending virtual-offset ranges holding every record `fetch(contig, start, end)` would look at (the BAI chunks of
         the region's bins behind the linear-index minimum, merged the way htslib merges them)"""
         rid = self.name_to_id[contig]
-        bins, lin = self.index[rid]
-        min_off = lin[start >> 14] if (start >> 14) < len(lin) else (lin[-1] if lin else 0)
-        chunks = sorted(c for b in reg2bins(max(start, 0), max(end, start + 1)) if b in bins and b != 37450 for c in bins[b] if c[1] > min_off)
+        bins = self.index[rid][0]
+        min_off = self._min_offset(rid, max(start, 0))
+        chunks = sorted(c for b in self._reg2bins(max(start, 0), max(end, start + 1)) if b in bins and b != self.meta_bin for c in bins[b] if c[1] > min_off)
         merged = []
         for beg, stop in chunks:
             beg = max(beg, min_off)
@@ -261,8 +327,7 @@ class BamFile:
         index's record-aligned offsets so that every ~16 kb window is its own parallel walk on the device."""
         pieces = []                                      # (task, vbeg, vend)
         for t, (contig, start, end) in enumerate(regions):
-            _, lin = self.index[self.name_to_id[contig]]
-            anchors = sorted(set(lin)) if split else []
+            anchors = self._anchors(self.name_to_id[contig]) if split else []
             for vb, ve in self.merged_chunks(contig, start, end):
                 cuts = [vb] + [a for a in anchors if vb < a < ve] + [ve]
                 pieces.extend((t, cuts[k], cuts[k + 1]) for k in range(len(cuts) - 1))
@@ -356,9 +421,10 @@ def _bgzf_block(data: bytes, level: int = 6) -> bytes:
             + struct.pack("<II", zlib.crc32(data) & 0xffffffff, len(data)))
 
 
-def write_bam(path, blk: RecordBlock, block_bytes=0xff00, level=6, qual_seed=None):
+def write_bam(path, blk: RecordBlock, block_bytes=0xff00, level=6, qual_seed=None, index="bai"):
     """packed block -> coordinate-sorted BAM + BAI (records keep the block's order; one contig per task).  Returns the paths.
-    qual_seed: None writes the "qualities absent" bytes 0xff; an integer writes noisy phred values (what makes a real BAM hard to compress)."""
+    qual_seed: None writes the "qualities absent" bytes 0xff; an integer writes noisy phred values (what makes a real BAM hard to compress).
+    index: "bai" or "csi" (the BAI bin geometry, min_shift 14 / depth 5, with per-bin loffsets derived from the linear index as htslib derives them)."""
     qrng = np.random.default_rng(qual_seed) if qual_seed is not None else None
     names = blk.contig_names
     text = b"@HD\tVN:1.6\tSO:coordinate\n" + b"".join(f"@SQ\tSN:{n}\tLN:{int(c['length'])}\n".encode() for n, c in zip(names, blk.contig))
@@ -367,7 +433,7 @@ def write_bam(path, blk: RecordBlock, block_bytes=0xff00, level=6, qual_seed=Non
         head += struct.pack("<i", len(n) + 1) + n.encode() + b"\0" + struct.pack("<i", int(c["length"]))
     out = open(path, "wb")
     buf, coff = bytearray(), 0
-    index = [({}, []) for _ in names]
+    index_tabs = [({}, []) for _ in names]
     stats = [[None, None, 0] for _ in names]
 
     def flush():
@@ -431,7 +497,7 @@ def write_bam(path, blk: RecordBlock, block_bytes=0xff00, level=6, qual_seed=Non
         else:
             buf += data
         v1 = (coff << 16) | len(buf)
-        bins, lin = index[rid]
+        bins, lin = index_tabs[rid]
         ch = bins.setdefault(reg2bin(pos, end), [])
         if ch and ch[-1][1] == v0:
             ch[-1] = (ch[-1][0], v1)
@@ -449,12 +515,29 @@ def write_bam(path, blk: RecordBlock, block_bytes=0xff00, level=6, qual_seed=Non
     flush()
     out.write(_BGZF_EOF)
     out.close()
+    for _, lin in index_tabs:
+        for w in range(1, len(lin)):                   # empty windows inherit the previous offset
+            if lin[w] == 0:
+                lin[w] = lin[w - 1]
+    if index == "csi":
+        body = b"CSI\1" + struct.pack("<iii", 14, 5, 0) + struct.pack("<i", len(names))
+        level_first = [((1 << (3 * l)) - 1) // 7 for l in range(6)]
+        for (bins, lin), st in zip(index_tabs, stats):
+            body += struct.pack("<i", len(bins) + (1 if st[2] else 0))
+            for b, ch in bins.items():
+                lvl = max(l for l in range(6) if level_first[l] <= b)
+                w = (b - level_first[lvl]) << (3 * (5 - lvl))
+                body += struct.pack("<IQi", b, lin[w] if w < len(lin) else 0, len(ch)) + b"".join(struct.pack("<QQ", v0, v1) for v0, v1 in ch)
+            if st[2]:
+                body += struct.pack("<IQi", 37450, 0, 2) + struct.pack("<QQ", st[0], st[1]) + struct.pack("<QQ", st[2], 0)
+        with open(path + ".csi", "wb") as f:
+            for k in range(0, len(body), 0xff00):
+                f.write(_bgzf_block(body[k:k + 0xff00], level))
+            f.write(_BGZF_EOF)
+        return path, path + ".csi"
     with open(path + ".bai", "wb") as f:
         f.write(b"BAI\1" + struct.pack("<i", len(names)))
-        for (bins, lin), st in zip(index, stats):
-            for w in range(1, len(lin)):               # empty windows inherit the previous offset
-                if lin[w] == 0:
-                    lin[w] = lin[w - 1]
+        for (bins, lin), st in zip(index_tabs, stats):
             nb = len(bins) + (1 if st[2] else 0)
             f.write(struct.pack("<i", nb))
             for b, ch in bins.items():

@@ -77,3 +77,64 @@ def test_long_cigar_escape(tmp_path):
     rs = list(f.fetch("c", 0, 1_000_000))
     assert len(rs) == 1 and len(rs[0]["cigar"]) == n and (rs[0]["cigar"] == cig).all()
     f.close()
+
+
+def test_csi_index_equals_bai(bam, tmp_path):
+    """the same records through a CSI index (BGZF-compressed, per-bin loffsets instead of the linear index) — the reference's own test
+    BAMs carry .csi indices"""
+    blk, path = bam
+    p2 = str(tmp_path / "c.bam")
+    bamio.write_bam(p2, blk, index="csi")
+    fa, fb = bamio.BamFile(path), bamio.BamFile(p2)
+    assert fb.index[0][1] is None and fb.index[0][2] and fa.index[0][1] is not None
+    rnd = np.random.default_rng(2)
+    for _ in range(40):
+        t = int(rnd.integers(0, 2))
+        L = fa.get_reference_length(blk.contig_names[t])
+        a = int(rnd.integers(0, L - 10)); b = a + int(rnd.integers(1, 80000))
+        assert [_key(r) for r in fa.fetch(blk.contig_names[t], a, b)] == [_key(r) for r in fb.fetch(blk.contig_names[t], a, b)]
+        assert fa.merged_chunks(blk.contig_names[t], a, b) and fb.merged_chunks(blk.contig_names[t], a, b)
+    for n in blk.contig_names:
+        assert fa.count_mapped(n) == fb.count_mapped(n)
+    fa.close(); fb.close()
+
+
+REF_DATA = "/root/reference/src/tests/data"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DATA), reason="the reference's test BAMs only exist in the build container")
+@pytest.mark.parametrize("name", ["hg008.bam", "hg002.bam"])
+def test_reference_bams_through_csi_and_device_spans(name):
+    """htslib-written files: region fetch through their .csi equals a linear scan, the one-lane host build of the device DEFLATE decoder
+    inflates every block like zlib, and the spans of device_input cover exactly the records of every contig"""
+    import struct
+    import zlib
+    import ingest_emul
+    f = bamio.BamFile(os.path.join(REF_DATA, name))
+    v, allr = f.first_record, []
+    while True:
+        d, v2 = f.bgzf.read_from(v, 4)
+        if len(d) < 4:
+            break
+        b, v = f.bgzf.read_from(v2, struct.unpack("<i", d)[0])
+        r = bamio.decode_record(b)
+        if r["ref_id"] >= 0:
+            allr.append(r)
+    assert allr
+    z = open(os.path.join(REF_DATA, name), "rb").read()
+    for k, (_, po, pl, isz) in enumerate(ingest_emul.walk_bgzf(z)):
+        rc, got = ingest_emul.inflate(z[po:po + pl], isz, lead=k % 4)
+        assert rc == 0 and got == zlib.decompress(z[po:po + pl], -15)
+    key = lambda r: (r["pos"], bytes(r["qname"]), r["flag"])
+    rnd = np.random.default_rng(1)
+    for rid in sorted({r["ref_id"] for r in allr}):
+        rs = [r for r in allr if r["ref_id"] == rid]
+        cname, L = f.contigs[rid]
+        lo, hi = min(r["pos"] for r in rs), max(r["pos"] + max(bamio.ref_span(r["cigar"]), 1) for r in rs)
+        for _ in range(20):
+            a = int(rnd.integers(max(lo - 50000, 0), hi)); b = a + int(rnd.integers(1, 200000))
+            assert [key(r) for r in f.fetch(cname, a, b)] == [key(r) for r in rs if r["pos"] < b and r["pos"] + max(bamio.ref_span(r["cigar"]), 1) > a]
+        task = np.zeros(1, abi.TASK_DTYPE); task[0] = (rid, 0, L, L, 0, 0, 0, 0)
+        bg, sp = f.device_input([(cname, 0, L)])
+        assert [(d["pos"], d["qname"], d["flag"]) for d in ingest_emul.load_bam(bg, sp, task)] == [key(r) for r in rs]
+    f.close()
