@@ -104,7 +104,7 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(name="k_scan_dram.json"):
+def ncu_traffic(name="k_chunk_sum_dram.json"):
     """DRAM bytes per launch of a kernel (group) from the committed ncu capture, if any."""
     p = os.path.join(ROOT, "profiles", name)
     if os.path.exists(p):
