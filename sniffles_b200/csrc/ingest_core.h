@@ -247,20 +247,21 @@ SNFB_HD int inflate_stream(const uint8_t* in, uint64_t ipos, uint64_t iend, uint
                 continue;
             }
             if (sym == 256) break;
-            if (sym > 285) { err = INF_BAD_SYMBOL; break; }
-            uint32_t len;
-            if (sym < 265) len = (uint32_t)(sym - 254);
-            else if (sym == 285) len = 258;
-            else { const int x = (sym - 261) >> 2; len = 3u + ((4u + (unsigned)((sym - 261) & 3)) << x) + ((unsigned)bb & ((1u << x) - 1u)); SNFB_TAKE(x); }
+            // length and distance without a branch per case (RFC 1951 §3.2.5): every check of the match is folded into one test
+            const unsigned s2 = (unsigned)sym - 257u;                                  // 0..28 are lengths; 28 = 258 without extra bits
+            int x = s2 < 8u ? 0 : (int)(((s2 - 4u) >> 2) & 7u);
+            uint32_t len = s2 < 8u ? s2 + 3u : 3u + ((4u + ((s2 - 4u) & 3u)) << x);
+            if (s2 >= 28u) { len = 258u; x = 0; }
+            len += (unsigned)bb & ((1u << x) - 1u); SNFB_TAKE(x);
             SNFB_REFILL();
-            const int dsym = huff_decode(bb, T->dist_fast, DIST_FAST_BITS, T->dist_count, T->dist_sym, &nb);
-            if (dsym < 0 || dsym > 29) { err = INF_BAD_DISTANCE; break; }
+            int dsym = huff_decode(bb, T->dist_fast, DIST_FAST_BITS, T->dist_count, T->dist_sym, &nb);
+            bool bad = s2 > 28u || (unsigned)dsym > 29u;
+            if (bad) dsym = 0;
             SNFB_TAKE(nb);
-            uint32_t dist;
-            if (dsym < 4) dist = (uint32_t)dsym + 1u;
-            else { const int x = (dsym >> 1) - 1; dist = 1u + ((2u + (unsigned)(dsym & 1)) << x) + ((unsigned)bb & ((1u << x) - 1u)); SNFB_TAKE(x); }
-            if (dist > op) { err = INF_BAD_DISTANCE; break; }
-            if (op + len > out_cap) { err = INF_OUTPUT_OVERRUN; break; }
+            const int dx = dsym < 4 ? 0 : (dsym >> 1) - 1;
+            const uint32_t dist = (dsym < 4 ? (uint32_t)dsym + 1u : 1u + ((2u + (unsigned)(dsym & 1)) << dx)) + ((unsigned)bb & ((1u << dx) - 1u));
+            SNFB_TAKE(dx);
+            if (bad || dist > op || op + len > out_cap) { err = bad ? INF_BAD_SYMBOL : (dist > op ? INF_BAD_DISTANCE : INF_OUTPUT_OVERRUN); break; }
             group_sync(gmask);                         // the bytes the match reads were written by other lanes
             const uint8_t* src = out + op - dist; uint8_t* dst = out + op;
             if (dist >= len) { for (uint32_t j = lane; j < len; j += NL) dst[j] = src[j]; }
