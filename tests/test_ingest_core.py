@@ -155,3 +155,59 @@ def test_long_cigar_and_wide_ops(tmp_path):
     assert len(host) == 2 and len(host[0]["cigar"]) == n
     _same(dev, host)
     f.close()
+
+
+def test_aux_fields_of_every_type(tmp_path):
+    """records carrying every aux type of the SAM spec (A c C s S i I f Z H and B arrays of every subtype, as ONT / PacBio BAMs do:
+    MM / ML / ip / pw ...) around the tags the path reads; integer tags in their narrow encodings; the device record decoder against the host reader"""
+    import struct
+    rnd = np.random.default_rng(9)
+
+    def aux_blob(k):
+        parts = [b"RGZ" + b"grp%d" % k + b"\0", b"XAA" + b"q", b"Xcc" + struct.pack("<b", -5), b"XfF".replace(b"F", b"f") + struct.pack("<f", 1.5)]
+        parts.append(b"MLBC" + struct.pack("<I", 7 + k) + bytes(range(7 + k)))
+        parts.append(b"pwBS" + struct.pack("<I", 3) + struct.pack("<3H", 1, 2, 3))
+        parts.append(b"ipBs" + struct.pack("<I", 2) + struct.pack("<2h", -1, 2))
+        parts.append(b"XiBi" + struct.pack("<I", 1) + struct.pack("<i", -7))
+        parts.append(b"XIBI" + struct.pack("<I", 2) + struct.pack("<2I", 9, 10))
+        parts.append(b"XFBf" + struct.pack("<I", 2) + struct.pack("<2f", 0.5, 2.5))
+        parts.append(b"XbBc" + struct.pack("<I", 3) + bytes([1, 255, 3]))
+        parts.append(b"MMZ" + b"C+m,5,12,0;" * (1 + k % 3) + b"\0")
+        parts.append(b"XHH" + b"1AE301" + b"\0")
+        nm = [b"NMC" + struct.pack("<B", 200), b"NMs" + struct.pack("<h", -3 + k), b"NMS" + struct.pack("<H", 40000), b"NMi" + struct.pack("<i", 123456), b"NMI" + struct.pack("<I", 77), b"NMc" + struct.pack("<b", 9)][k % 6]
+        parts.insert(int(rnd.integers(0, len(parts))), nm)
+        if k % 2:
+            parts.insert(int(rnd.integers(0, len(parts))), b"HPC" + struct.pack("<B", 1 + k % 2))
+            parts.insert(int(rnd.integers(0, len(parts))), b"PSi" + struct.pack("<i", 1000 + k))
+        if k % 3 == 0:
+            parts.insert(int(rnd.integers(0, len(parts))), b"SAZ" + b"ctg,%d,+,50M20S,60,1;" % (100 + k) + b"\0")
+        return b"".join(parts)
+
+    recs = []
+    for k in range(40):
+        qname = b"read_%d" % k + b"x" * (k % 7) + b"\0"
+        cig = np.array([(10 + k << 4) | 4, (300 << 4) | 0, (15 << 4) | 1, (200 << 4) | 0], "<u4")
+        l_seq = 10 + k + 300 + 15 + 200
+        seq = bytes(rnd.integers(0, 256, (l_seq + 1) // 2, dtype=np.uint8))
+        body = struct.pack("<iiBBHHHiiii", 0, 1000 + 50 * k, len(qname), 60, 4681, len(cig), 16 if k % 2 else 0, l_seq, -1, -1, 0) + qname + cig.tobytes() + seq + b"\x11" * l_seq + aux_blob(k)
+        recs.append(struct.pack("<i", len(body)) + body)
+    raw = b"".join(recs)
+    want = [bamio.decode_record(r[4:]) for r in recs]
+    L = ingest_emul.lib()
+    rawa = np.frombuffer(raw + b"\0" * 64, "u1").copy()
+    out = np.zeros(len(recs), ingest_emul.RAWREC_DTYPE)
+    assert L.ingest_host_parse(rawa.ctypes.data, len(raw), 0, len(raw), out.ctypes.data, len(recs)) == len(recs)
+    for r, h in zip(out, want):
+        a = h["aux"]
+        assert r["status"] == 0 and int(r["pos"]) == h["pos"] and int(r["l_seq"]) == h["l_seq"] and int(r["n_cig"]) == len(h["cigar"]) and int(r["flag"]) == h["flag"]
+        af = int(r["aux_flags"])
+        assert (af & abi.AUX_NM != 0, af & abi.AUX_HP != 0, af & abi.AUX_PS != 0, af & abi.AUX_SA != 0) == ("NM" in a, "HP" in a, "PS" in a, "SA" in a)
+        assert int(r["nm"]) == int(a.get("NM", 0)) and int(r["hp"]) == int(a.get("HP", 0)) and int(r["ps"]) == int(a.get("PS", 0))
+        assert bytes(rawa[int(r["sa_src"]):int(r["sa_src"]) + int(r["sa_len"])]) == a.get("SA", b"")
+        assert bytes(rawa[int(r["body"]) + 32:int(r["body"]) + 32 + int(r["l_qname"])]) == bytes(h["qname"])
+    # truncated / malformed records are reported, never walked out of bounds
+    bad = bytearray(recs[0])
+    bad[4 + 32 + len(b"read_0\0") + 16 + (525 + 1) // 2 + 525 + 2] = ord("?")       # the type byte of the first aux field
+    o1 = np.zeros(1, ingest_emul.RAWREC_DTYPE)
+    b2 = np.frombuffer(bytes(bad) + b"\0" * 64, "u1").copy()
+    assert L.ingest_host_parse(b2.ctypes.data, len(bad), 0, len(bad), o1.ctypes.data, 1) == 1 and o1[0]["status"] == 1
