@@ -45,6 +45,13 @@ def lib():
         L.so_hash_name.argtypes = [C.c_char_p, C.c_size_t]
         L.so_sqrt_frac.restype = C.c_double
         L.so_sqrt_frac.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64]
+        L.so_center.restype = C.c_long
+        L.so_center.argtypes = [C.c_void_p, C.c_long]
+        L.so_stdev.restype = C.c_double
+        L.so_stdev.argtypes = [C.c_void_p, C.c_long]
+        L.so_stdev_trim.restype = C.c_double
+        L.so_stdev_trim.argtypes = [C.c_void_p, C.c_long]
+        L.so_cigar_analyze.argtypes = [C.c_char_p, C.c_int, C.c_void_p]
         _LIB = L
     return _LIB
 

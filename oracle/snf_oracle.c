@@ -915,3 +915,8 @@ void so_free(so_result* r) {
     free(r->rnames); free(r->rn_off); free(r->alt); free(r);
 }
 double so_sqrt_frac(uint64_t p_hi, uint64_t p_lo, uint64_t q) { return sqrt_frac_rn(((u128)p_hi << 64) | p_lo, q); }
+/* unit-level entry points for the known-answer vectors of SURVEY.md Appendix A (tests/test_known_answers.py) */
+long so_center(const long* v, long n) { return center(v, n); }
+double so_stdev(const long* v, long n) { return stdev_ints(v, n); }
+double so_stdev_trim(const long* v, long n) { return stdev_trim(v, n); }
+int so_cigar_analyze(const uint8_t* c, int n, long out[4]) { return cigar_analyze(c, n, &out[0], &out[1], &out[2], &out[3]); }

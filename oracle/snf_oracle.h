@@ -21,6 +21,10 @@ void so_free(so_result* r);
 uint64_t so_hash_name(const uint8_t* s, size_t n);
 uint64_t so_qname_hash(const uint8_t* s, size_t n);
 double so_sqrt_frac(uint64_t p_hi, uint64_t p_lo, uint64_t q);
+long so_center(const long* v, long n);
+double so_stdev(const long* v, long n);
+double so_stdev_trim(const long* v, long n);
+int so_cigar_analyze(const uint8_t* c, int n, long out[4]);
 #ifdef __cplusplus
 }
 #endif
