@@ -325,7 +325,7 @@ int         snfb_run(snfb_ctx* ctx, snfb_lead_view* leads, snfb_cand_view* cands
  * the file offset rebased to `bgzf`.  cend == n_bytes with uend == 0 means "to the end of the buffer".  Spans are listed task by
  * task in file order and must not overlap (merge the index chunks first, as htslib does); cutting a span at any record-aligned
  * offset (the linear index of the BAI provides one per 16 kb window) only adds parallelism.  The library inflates every block
- * (one warp per block), follows the block_size chain of every span, decodes the records, keeps those `bam.fetch(contig, start,
+ * (16 lanes of a warp per block), follows the block_size chain of every span, decodes the records, keeps those `bam.fetch(contig, start,
  * end)` would return for the span's task (task.contig is the BAM reference id), restores CIGARs of more than 65535 operations
  * from the CG:B,I tag, and writes snfb_rec + CIGAR16 + names/SA + 4-bit bases exactly as snfb_load_records expects them.
  * The BGZF CRC32 is not verified (a corrupt block is caught by the DEFLATE decoder or the inflated size).  Tables (tasks, contigs,

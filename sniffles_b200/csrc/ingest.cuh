@@ -2,8 +2,9 @@
 // Replaces the host decode behind `bam.fetch(contig, start, end)` (parallel.py:95-98, leadprov.py:488): only the BGZF bytes cross
 // PCIe; inflate, record decode, filtering to the task's region, the CG long-CIGAR escape and the CIGAR16 packing run here.
 //
-//   k_inflate      one warp per BGZF block (ingest_core.h inflate_stream<32>): Huffman tables of the warp in shared memory, the
-//                  scalar decode executed redundantly by all lanes, match copies / table fills / stored blocks split across lanes
+//   k_inflate<NL>  NL = 32 / 16 / 8 lanes per BGZF block (ingest_core.h inflate_stream<NL>; 16 by default): the Huffman tables of a block in
+//                  shared memory, the scalar decode executed redundantly by the block's lanes, match copies / table fills / stored blocks split
+//                  across them; two or four blocks share a warp's instruction stream wherever they run the same path
 //   k_walk         one thread per span (a record-aligned range of the inflated stream, cut at the BAI's linear-index anchors):
 //                  follows the block_size chain, first to count, then to write the record offsets
 //   k_parse        one thread per raw record: fixed fields, aux walk (NM, HP, PS, SA, CG), task filter on contig and end
