@@ -68,6 +68,26 @@ def gpu_count():
         return 1
 
 
+def load_tandem_repeats(filename, padding):
+    """util.load_tandem_repeats (util.py:121-147): BED of tandem repeats -> {contig: [(start - padding clipped at 0, end + padding), ...]},
+    in file order unless some contig's starts go backwards, in which case every contig is sorted (the reference sorts all of them then).
+    The result is what `Task(tandem_repeats=...)` takes per contig (sniffles:313-358)."""
+    contigs_tr, unsorted = {}, False
+    with open(filename, "r") as handle:
+        for line in handle:
+            parts = line.split("\t")
+            if len(parts) >= 3:
+                contig, start, end = parts[0], int(parts[1]), int(parts[2])
+                iv = contigs_tr.setdefault(contig, [])
+                if iv and start < iv[-1][0]:              # compared with the previous PADDED start, as the reference does (util.py:134-136)
+                    unsorted = True
+                iv.append((max(0, start - padding), end + padding))
+    if unsorted:
+        for contig in contigs_tr:
+            contigs_tr[contig].sort()
+    return contigs_tr
+
+
 @dataclass
 class Task:
     id: int

@@ -1,4 +1,4 @@
-"""Generates tests/golden/known_answers.json by asking the UNMODIFIED reference (imported from /root/reference through oracle/pyref):
+"""Generates tests/golden/known/known_answers.json by asking the UNMODIFIED reference (imported from /root/reference through oracle/pyref):
 the known-answer vectors of SURVEY.md Appendix A — util.center / trim / stdev, leadprov.CIGAR_analyze — and the clusters the reference
 forms on the hand-built blocks of tests/known_blocks.py (cluster.resplit's negative-index wrap, compute_metrics' over-long sample).
 Run in the build container:  python tests/golden/make_known_answers.py"""
@@ -35,7 +35,7 @@ def main():
         out["blocks"][name] = dict(svlens=svlens, read_count=res["read_count"],
                                    cands=[dict(svtype=c["svtype"], pos=c["pos"], svlen=c["svlen"], support=c["support"], n_leads=c["n_leads"], cluster_id=c["cluster_id"],
                                                stdev_pos=c["stdev_pos"], stdev_len=c["stdev_len"], lead_svlens=[ld[2] for ld in c["leads"]]) for c in res["cands"]])
-    with open(os.path.join(ROOT, "tests", "golden", "known_answers.json"), "w") as f:
+    with open(os.path.join(ROOT, "tests", "golden", "known", "known_answers.json"), "w") as f:
         json.dump(out, f, indent=1)
     for k, v in out["blocks"].items():
         print(k, [(c["cluster_id"], c["svlen"], c["support"], c["lead_svlens"][:8]) for c in v["cands"]])

@@ -38,3 +38,19 @@ def test_epilogue_matches_reference(name):
     cfg = sconfig.default_config(*fx["args"])
     res = orc.run(blk, abi.Config.from_sniffles(cfg), 3, 2, keep_rec_nm=True)
     check_final(fx, blk, res, res.rec_nm, cfg)
+
+
+def test_load_tandem_repeats_matches_reference(tmp_path):
+    """util.load_tandem_repeats (util.py:121-147): padding, file order kept, everything sorted once one contig's starts go backwards
+    (compared with the PADDED previous start).  Expected values written down from the unmodified reference (same inputs, build container)."""
+    from sniffles_b200 import tasks
+    bed1 = tmp_path / "sorted.bed"
+    bed1.write_text("chr1\t100\t200\tx\nchr1\t150\t400\nchr2\t10\t20\nshort\tline\nchr1\t9000\t9100\textra\tcols\n")
+    assert tasks.load_tandem_repeats(str(bed1), 500) == {"chr1": [(0, 700), (0, 900), (8500, 9600)], "chr2": [(0, 520)]}
+    bed2 = tmp_path / "unsorted.bed"
+    bed2.write_text("chr1\t5000\t5100\nchr1\t1000\t1100\nchr2\t800\t900\nchr2\t700\t950\nchr2\t10\t20\n")
+    # chr2: 700 is not below the previous padded start 300, but chr1 is unsorted -> every contig is sorted
+    assert tasks.load_tandem_repeats(str(bed2), 500) == {"chr1": [(500, 1600), (4500, 5600)], "chr2": [(0, 520), (200, 1450), (300, 1400)]}
+    bed3 = tmp_path / "kept.bed"
+    bed3.write_text("chr2\t800\t900\nchr2\t700\t950\n")                  # 700 >= 300: not flagged, file order kept
+    assert tasks.load_tandem_repeats(str(bed3), 500) == {"chr2": [(300, 1400), (200, 1450)]}

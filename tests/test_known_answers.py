@@ -1,5 +1,5 @@
 """Known-answer vectors: behaviours that are easy to "fix" by accident, pinned by outputs of the unmodified
-reference (tests/golden/known_answers.json, written by tests/golden/make_known_answers.py in the build container) — util.center / trim /
+reference (tests/golden/known/known_answers.json, written by tests/golden/make_known_answers.py in the build container) — util.center / trim /
 stdev, leadprov.CIGAR_analyze, and the clusters the reference forms on hand-built blocks (cluster.resplit's negative-index wrap,
 compute_metrics' over-long sample, merge_inner on equal leads).  CPU: the oracle; GPU (-m gpu): the CUDA path on the same blocks."""
 import ctypes as C
@@ -14,7 +14,7 @@ import oracle.oracle as orc
 from sniffles_b200 import abi
 from sniffles_b200 import config as sconfig
 
-KA = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "known_answers.json")))
+KA = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "known", "known_answers.json")))
 
 
 def _longs(v):
