@@ -1,6 +1,7 @@
 """Device BAM ingest, the parts checkable without a GPU: the DEFLATE decoder, the BAM record decoder and the CIGAR16
 converter of sniffles_b200/csrc/ingest_core.h in their one-lane host build, against zlib and the host reader; and the index work of
 bamio.device_input (merged chunks, spans cut at the linear index, compressed-block selection)."""
+import os
 import random
 import zlib
 
@@ -211,3 +212,30 @@ def test_aux_fields_of_every_type(tmp_path):
     o1 = np.zeros(1, ingest_emul.RAWREC_DTYPE)
     b2 = np.frombuffer(bytes(bad) + b"\0" * 64, "u1").copy()
     assert L.ingest_host_parse(b2.ctypes.data, len(bad), 0, len(bad), o1.ctypes.data, 1) == 1 and o1[0]["status"] == 1
+
+
+def test_contig_shards_of_a_bam_partition_its_records(bam):
+    """multi-GPU ingest: contigs are LPT-assigned by the index's mapped-read counts; every rank ships only the BGZF blocks of its
+    own contigs and the ranks' blocks together are exactly the file's records"""
+    from sniffles_b200 import dist
+    blk, path = bam
+    f = bamio.BamFile(path)
+    names = blk.contig_names
+    owner = dist.lpt_assign([f.count_mapped(n) for n in names], 2)
+    assert sorted(set(owner)) == [0, 1]
+    total, shipped = 0, 0
+    for rank in (0, 1):
+        mine = [t for t in range(len(names)) if owner[t] == rank]
+        regions = [(names[t], 0, f.get_reference_length(names[t])) for t in mine]
+        task = np.zeros(len(mine), abi.TASK_DTYPE)
+        for k, t in enumerate(mine):
+            task[k] = (t, 0, regions[k][2], regions[k][2], t, 0, 0, 0)
+        bgzf, spans = f.device_input(regions)
+        dev = ingest_emul.load_bam(bgzf, spans, task)
+        for k, t in enumerate(mine):
+            _same([d for d in dev if d["task"] == k], list(f.fetch(names[t], 0, regions[k][2])))
+        total += len(dev)
+        shipped += len(bgzf)
+    assert total == len(blk.rec)
+    assert shipped < 1.2 * os.path.getsize(path)            # a block shared by two contigs' boundary may travel twice, nothing more
+    f.close()
