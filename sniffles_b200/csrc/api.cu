@@ -310,7 +310,7 @@ static inline uint64_t c16_count(const uint32_t* cg, uint32_t n, bool* bad) {
     }
     return k;
 }
-static inline void c16_write(const uint32_t* cg, uint32_t n, uint16_t* out, uint32_t evt_min) {
+static inline uint64_t c16_write(const uint32_t* cg, uint32_t n, uint16_t* out, uint32_t evt_min) {      // returns the words written (= c16_count)
     uint64_t k = 0;
     for (uint32_t i = 0; i < n; ++i) {
         const uint32_t len = cg[i] >> 4; const int g = c16_group_words(len); const unsigned cls = C16_CLASS[cg[i] & 15u];
@@ -320,29 +320,39 @@ static inline void c16_write(const uint32_t* cg, uint32_t n, uint16_t* out, uint
         if (g >= 2) out[k++] = (uint16_t)(0x8000u | (1u << 12) | ((len >> 11) & 0xfffu));
         if (g >= 3) out[k++] = (uint16_t)(0x8000u | (2u << 12) | ((len >> 23) & 0xfffu));
     }
+    return k;
+}
+// pass 1: off[i] = first word of record i in the 16-bit arena (every record starts a 16-byte group); false when an op code is unknown
+static bool c16_offsets(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, std::vector<uint64_t>& off) {
+    off.assign(n_rec + 1, 0);
+    bool bad = false;
+    #pragma omp parallel for schedule(static) reduction(|| : bad)
+    for (long long i = 0; i < (long long)n_rec; ++i) { bool b = false; const uint64_t w = c16_count(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, &b); bad = bad || b; off[i + 1] = (w + 7) & ~7ull; }
+    if (bad) return false;
+    for (uint64_t i = 0; i < n_rec; ++i) off[i + 1] += off[i];
+    return true;
+}
+// pass 2: the words and the rewritten records
+static void c16_fill(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, const std::vector<uint64_t>& off, snfb_rec* rec_out, uint16_t* out16, uint32_t evt_min) {
+    #pragma omp parallel for schedule(static)
+    for (long long i = 0; i < (long long)n_rec; ++i) {
+        uint16_t* dst = out16 + off[i]; const uint64_t span = off[i + 1] - off[i];
+        const uint64_t k = c16_write(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, dst, evt_min);
+        if (k < span) memset(dst + k, 0, 2 * (span - k));
+        snfb_rec r = rec_in[i]; r.n_cigar = (uint32_t)k; r.cigar_off = off[i];
+        rec_out[i] = r;
+    }
+    memset(out16 + off[n_rec], 0, 16);                            // one zero group of slack after the last record
 }
 uint64_t snfb_pack_cigar16(const snfb_rec* rec_in, uint64_t n_rec, const uint32_t* cigar32, snfb_rec* rec_out, uint16_t* out16, uint64_t out_cap, uint32_t evt_min) {
     if (n_rec && (!rec_in || !cigar32)) return UINT64_MAX;
     if (evt_min == 0) evt_min = SNFB_CIGAR16_EVT_MIN;
-    std::vector<uint64_t> off(n_rec + 1, 0);
-    bool bad = false;
-    #pragma omp parallel for schedule(static) reduction(|| : bad)
-    for (long long i = 0; i < (long long)n_rec; ++i) { bool b = false; const uint64_t w = c16_count(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, &b); bad = bad || b; off[i + 1] = (w + 7) & ~7ull; }
-    if (bad) return UINT64_MAX;
-    for (uint64_t i = 0; i < n_rec; ++i) off[i + 1] += off[i];
-    const uint64_t total = off[n_rec] + 8;                       // one zero group of slack after the last record
+    std::vector<uint64_t> off;
+    if (!c16_offsets(rec_in, n_rec, cigar32, off)) return UINT64_MAX;
+    const uint64_t total = off[n_rec] + 8;
     if (!out16) return total;
     if (!rec_out || out_cap < total) return UINT64_MAX;
-    #pragma omp parallel for schedule(static)
-    for (long long i = 0; i < (long long)n_rec; ++i) {
-        uint16_t* dst = out16 + off[i]; const uint64_t span = off[i + 1] - off[i];
-        memset(dst, 0, 2 * span);
-        c16_write(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, dst, evt_min);
-        bool b = false;
-        snfb_rec r = rec_in[i]; r.n_cigar = (uint32_t)c16_count(cigar32 + rec_in[i].cigar_off, rec_in[i].n_cigar, &b); r.cigar_off = off[i];
-        rec_out[i] = r;
-    }
-    memset(out16 + off[n_rec], 0, 16);
+    c16_fill(rec_in, n_rec, cigar32, off, rec_out, out16, evt_min);
     return total;
 }
 
@@ -412,11 +422,12 @@ int snfb_load_records(snfb_ctx* ctx, const snfb_records* R) {
     if (R->cigar_fmt == SNFB_CIGAR_BAM32) {
         if (R->on_device == SNFB_MEM_DEVICE) return fail(ctx, "device-resident records must carry CIGAR16 (convert with snfb_pack_cigar16)");
         for (uint64_t i = 0; i < R->n_rec; ++i) if (R->rec[i].cigar_off + (uint64_t)R->rec[i].n_cigar > R->n_cigar) return fail(ctx, "a record's CIGAR lies outside the cigar arena");
-        // host conversion: the kernels only read CIGAR16
-        const uint64_t need = snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), nullptr, nullptr, 0, 0);
-        if (need == UINT64_MAX) return fail(ctx, "a CIGAR holds an operation the path does not know");
+        // host conversion: the kernels only read CIGAR16 (two passes over the BAM words: offsets, then the words)
+        std::vector<uint64_t> off;
+        if (!c16_offsets(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), off)) return fail(ctx, "a CIGAR holds an operation the path does not know");
+        const uint64_t need = off[R->n_rec] + 8;
         if (ctx->h_c16.ensure(2 * need + 16) || ctx->h_rec16.ensure(sizeof(snfb_rec) * (R->n_rec + 1))) return fail(ctx, "out of pinned memory for the CIGAR16 conversion");
-        if (snfb_pack_cigar16(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), ctx->h_rec16.as<snfb_rec>(), ctx->h_c16.as<uint16_t>(), need, evt_need(ctx)) != need) return fail(ctx, "CIGAR16 conversion failed");
+        c16_fill(R->rec, R->n_rec, reinterpret_cast<const uint32_t*>(R->cigar), off, ctx->h_rec16.as<snfb_rec>(), ctx->h_c16.as<uint16_t>(), evt_need(ctx));
         src_rec = ctx->h_rec16.as<snfb_rec>(); src_cigar = ctx->h_c16.as<uint16_t>(); n_words = need;
         ctx->evt_min = evt_need(ctx);
     } else if (R->cigar_fmt != SNFB_CIGAR_16) return fail(ctx, "unknown cigar_fmt");
