@@ -651,8 +651,7 @@ def run_ingest(args):
     Workload: a coordinate-sorted BAM written from the config-2 generator (noisy base qualities, so the DEFLATE streams look like a real
     file's), its blocks tiled `--ingest-tiles` times as independent tasks.  value = inflated BAM bytes per second of the ingest kernels
     (CUDA events); e2e = the whole snfb_load_bam call from pinned host memory, plus the full path (ingest + lead -> cluster -> consensus)."""
-    import tempfile, zlib
-    from concurrent.futures import ThreadPoolExecutor
+    import tempfile
     import torch
     from sniffles_b200 import abi, bamio, binding, synth, config as sconfig
     t0 = time.time()
